@@ -1,0 +1,170 @@
+/*
+ * pynite_b200.h -- C ABI of the B200-native stiffness-assembly + linear-solve library.
+ *
+ * The reference (JWock82/Pynite) is pure Python and has no FFI; its "operator interface" for this
+ * path is the set of Python functions listed beside each entry point below (file:line relative to
+ * /root/reference/Pynite).  A maintainer who wanted the reference itself to use this library would
+ * bind these symbols with ctypes exactly as pynite_b200/engine.py does.
+ *
+ * Conventions
+ *   - every pointer is a HOST pointer to caller-owned memory; the library copies in/out;
+ *   - integers are int32 unless stated, reals are IEEE binary64;
+ *   - a global DOF is node_id*6 + k, k = 0..5 for DX DY DZ RX RY RZ (FEModel3D.py:66-94);
+ *   - return value 0 = success, negative = pn_status error; pn_last_error() gives the text;
+ *   - one pn_ctx per model and per GPU; calls on one ctx are not re-entrant.
+ *   - there is no CPU implementation behind any entry point: without a CUDA device pn_create fails.
+ */
+#ifndef PYNITE_B200_H
+#define PYNITE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pn_ctx pn_ctx;
+
+enum pn_status {
+    PN_OK = 0,
+    PN_ERR_CUDA = -1,          /* CUDA runtime error (text in pn_last_error)                       */
+    PN_ERR_ARG = -2,           /* bad argument / call order                                        */
+    PN_ERR_SINGULAR = -3,      /* Analysis.py:172,239  "stiffness matrix is singular"              */
+    PN_ERR_UNSTABLE_NODE = -4, /* Analysis.py:111-166  zero diagonal on an unsupported DOF         */
+    PN_ERR_NOT_CONVERGED = -5, /* iterative solver hit max_iter before reaching tol                */
+    PN_ERR_NO_DEVICE = -6
+};
+
+enum pn_elem_kind { PN_SPRING = 1, PN_MEMBER = 2, PN_QUAD = 3, PN_PLATE = 4 };
+
+/* flags for pn_symbolic */
+#define PN_SYM_DENSE_MEMBER_BLOCKS 1u /* keep all 144 entries of every member block (Kg has no zero
+                                          filter: FEModel3D.py:1859-1885); used by the P-Delta solve */
+
+/* solver selection for pn_solve_* */
+#define PN_SOLVER_DIRECT 0 /* sparse multifrontal LDL^T + FP64 iterative refinement                */
+#define PN_SOLVER_PCG 1    /* node-block-Jacobi preconditioned CG, all right-hand sides at once    */
+
+typedef struct pn_sizes {
+    int64_t n_dof;    /* 6 * nodes                                                                 */
+    int64_t nnz_coo;  /* COO entries the reference would emit (FEModel3D.py:1773-1791)             */
+    int64_t nnz_csr;  /* stored entries after duplicate summation (.tocsr(), FEModel3D.py:2279)    */
+    int64_t n1, n2;   /* unknown / known DOF counts (Analysis.py:1412-1505)                        */
+    int64_t nnz11, nnz12, nnz21, nnz22;
+} pn_sizes;
+
+typedef struct pn_solve_opts {
+    int32_t solver;          /* PN_SOLVER_*                                                        */
+    int32_t check_stability; /* residual / finiteness check of Analysis.py:228-239                 */
+    int32_t max_iter;        /* PCG iteration cap (0 = library default)                            */
+    int32_t refine_steps;    /* iterative-refinement sweeps after the direct solve (default 2)     */
+    double tol;              /* PCG: relative residual target per right-hand side (default 1e-12)  */
+    double singular_tol;     /* Analysis.py:176  tol = 1e-6 on ||K x - b|| / ||b||                 */
+} pn_solve_opts;
+
+typedef struct pn_stats {
+    double ms_elements;   /* element stiffness kernels                                             */
+    double ms_symbolic;   /* pattern + scatter map + partition maps                                */
+    double ms_scatter;    /* COO -> CSR scatter-add                                                */
+    double ms_partition;  /* K11 / K12 / K21 / K22 value gather                                    */
+    double ms_rhs;        /* load vectors and K12 * D2                                             */
+    double ms_factor;     /* direct: numeric factorisation; PCG: preconditioner setup              */
+    double ms_solve;      /* triangular solves + refinement, or PCG iterations                     */
+    double ms_reactions;  /* element end forces and reactions                                      */
+    double ms_spmm;       /* time inside the SpMM kernel only (summed over launches)               */
+    int64_t spmm_launches;
+    int64_t kernel_launches; /* kernels of this library launched since pn_create                   */
+    int64_t iterations;      /* PCG iterations (max over right-hand sides) / refinement sweeps     */
+    double max_rel_residual; /* max over combos of ||K11 x - b|| / ||b||                            */
+    int64_t factor_nnz;      /* stored entries of the direct factor                                */
+    double factor_flops;
+} pn_stats;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+int pn_create(pn_ctx **out, int device_id);
+void pn_destroy(pn_ctx *ctx);
+const char *pn_last_error(pn_ctx *ctx);
+const char *pn_version(void);
+
+/* ---- model upload: replaces the object reads inside FEModel3D.Ke (FEModel3D.py:1587-1771) ------
+ * nodes:   Node3D.py:28-85.  support_mask bit k = DOF k supported; enforced_mask likewise;
+ *          spring_flag[n*6+k]: bit0 = spring defined, bit1 = active (FEModel3D.py:1590-1593).
+ * springs: Spring3D.py:25-43.  members: Member3D.py:37-105 (sub-members after descritize,
+ *          PhysMember.py:37-200); props = E, G, A, Iy, Iz, J; releases bit k = local DOF k released.
+ * quads / plates: Quad3D.py:30-57, Plate3D.py:16-72; props = t, E, nu, kx_mod, ky_mod.            */
+int pn_set_nodes(pn_ctx *ctx, int64_t n_nodes, const double *xyz, const uint8_t *support_mask,
+                 const uint8_t *enforced_mask, const double *enforced_val, const double *spring_k,
+                 const uint8_t *spring_flag);
+int pn_set_springs(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *ks, const uint8_t *active);
+int pn_set_members(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *props, const double *rotation_deg,
+                   const uint16_t *releases, const uint8_t *active);
+int pn_set_quads(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props);
+int pn_set_plates(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props);
+
+/* ---- per-element global matrices, for inspection and parity tests -----------------------------
+ * Member3D.Ke :1038, Spring3D.Ke :191, Quad3D.Ke :858, Plate3D.Ke :502 -> out[count][nd*nd], nd = 12 or 24.
+ * Member3D.Kg :1048 with axial force P[m] -> out[count][144].                                     */
+int pn_element_ke(pn_ctx *ctx, int kind, double *out);
+int pn_member_kg(pn_ctx *ctx, const double *P, double *out);
+
+/* ---- symbolic phase: FEModel3D._build_dof_vector :66, _append_sparse_block :99 (zero filter),
+ *      coo_matrix + tocsr pattern (:1791, :2279), Analysis._partition_D :1412, _partition :1508 -- */
+int pn_symbolic(pn_ctx *ctx, uint32_t flags);
+int pn_get_sizes(pn_ctx *ctx, pn_sizes *out);
+int pn_get_coo(pn_ctx *ctx, int32_t *row, int32_t *col, double *data); /* emission order           */
+int pn_get_pattern(pn_ctx *ctx, int32_t *indptr, int32_t *indices);    /* CSR of Ke, sorted        */
+int pn_get_partition(pn_ctx *ctx, int32_t *d1, int32_t *d2, double *d2_values);
+/* block: 0 = K11, 1 = K12, 2 = K21, 3 = K22; any output pointer may be NULL */
+int pn_get_block(pn_ctx *ctx, int block, int32_t *indptr, int32_t *indices, double *data);
+
+/* ---- numeric assembly: duplicate summation of .tocsr() (FEModel3D.py:2279) -------------------- */
+int pn_assemble_ke(pn_ctx *ctx);
+int pn_get_csr_values(pn_ctx *ctx, double *data);
+/* Analysis._check_stability :111-168; on PN_ERR_UNSTABLE_NODE the first *n_bad (<= cap) DOFs are
+ * written to bad_dofs                                                                             */
+int pn_check_nodal_stability(pn_ctx *ctx, int32_t *bad_dofs, int64_t cap, int64_t *n_bad);
+
+/* ---- loads: FEModel3D.P :2184, FEModel3D.FER :2136, Member3D.fer :742, Quad3D.fer :721,
+ *      Plate3D.fer :324, FixedEndReactions.py ----------------------------------------------------
+ * nodal loads: (dof, case, value) triplets in model order.
+ * member loads: kind 0..5 = point Fx Fy Fz Mx My Mz (local), 6..11 = point FX FY FZ MX MY MZ
+ *   (global), params = (P, x, -, -); 12..14 = distributed Fx Fy Fz, 15..17 = FX FY FZ,
+ *   params = (w1, w2, x1, x2).  Entries must be grouped by member (ascending member index).
+ * pressures: (element, case, value) triplets.                                                     */
+int pn_set_loads(pn_ctx *ctx, int32_t n_case,
+                 int64_t n_nodal, const int32_t *nl_dof, const int32_t *nl_case, const double *nl_val,
+                 int64_t n_mload, const int32_t *ml_member, const int32_t *ml_case, const int32_t *ml_kind,
+                 const double *ml_params,
+                 int64_t n_qp, const int32_t *qp_elem, const int32_t *qp_case, const double *qp_val,
+                 int64_t n_pp, const int32_t *pp_elem, const int32_t *pp_case, const double *pp_val);
+/* LoadCombo.py:8-21: factors[n_combo][n_case] */
+int pn_set_combos(pn_ctx *ctx, int32_t n_combo, const double *factors);
+/* which: 0 = P, 1 = FER; out[6N] for one combo */
+int pn_get_load_vector(pn_ctx *ctx, int32_t combo, int32_t which, double *out);
+
+/* ---- solve: FEModel3D.analyze_linear :2287-2320 (all combos), Analysis._solve_unknown_disp :176,
+ *      _store_displacements :847, _calc_reactions :1059 ------------------------------------------
+ * D_out[n_combo][6N], Rxn_out[n_combo][6N] (either may be NULL).                                  */
+int pn_solve_linear(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats);
+/* Analysis._PDelta :329-471 + FEModel3D.Kg :1802: solve, P = EA/L (d6 - d0), Kg, K = Ke + Kg, re-solve */
+int pn_solve_pdelta(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats);
+/* global geometric stiffness for one solved combo as COO, 144 entries per active member, unfiltered
+ * (FEModel3D.py:1826-1892); first_step != 0 uses P = 0.  row/col/data sized 144 * active members  */
+int pn_get_kg_coo(pn_ctx *ctx, int32_t combo, int32_t first_step, int32_t *row, int32_t *col, double *data,
+                  int64_t *n_out);
+
+/* ---- element end forces of a solved combo: Member3D.f :872 / F :1072, Spring3D.f :86 / F :200,
+ *      Quad3D.f :713 / F :798, Plate3D.f :316 / F :403.  out[count][nd]; local != 0 -> local axes;
+ *      pdelta != 0 uses the (ke + kg(P)) branch of Member3D.f :886-891                             */
+int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32_t pdelta, double *out);
+
+/* ---- building blocks exposed for measurement and tests ----------------------------------------
+ * Y[n1][s] = K11 * X[n1][s] (row-major, s right-hand sides), repeated `repeat` times; returns the
+ * average kernel time in ms through *ms_out (CUDA events on the launching stream).                */
+int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repeat, double *ms_out);
+int pn_get_stats(pn_ctx *ctx, pn_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYNITE_B200_H */

@@ -1,0 +1,322 @@
+"""`FEModel3D`: the reference's model facade, with the assembly + solve path running on a B200.
+
+Builders (`add_node` ... `add_quad_surface_pressure`) keep the reference signatures, naming rules
+and error behaviour (`Pynite/FEModel3D.py:224-1549`).  The three analysis drivers
+(`analyze_linear` :2250, `analyze` :2334, `analyze_PDelta` :2413) keep their keyword arguments, but
+everything between "objects are numbered" and "results are stored" -- element stiffness, COO->CSR
+assembly, partition, right-hand sides, the solve for every load combination, reactions -- is done by
+the sm_100a library behind `pynite_b200.engine` (C ABI in `include/pynite_b200.h`).
+
+There is no CPU solver in this package: `sparse=False` raises NotImplementedError and a missing
+CUDA library raises at the first analysis call.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from pynite_b200 import analysis as _analysis
+from pynite_b200.LoadCombo import LoadCombo
+from pynite_b200.Material import Material, Section
+from pynite_b200.Member3D import PhysMember
+from pynite_b200.Node3D import Node3D
+from pynite_b200.Quad3D import Plate3D, Quad3D
+from pynite_b200.Spring3D import Spring3D
+
+_NODE_DOFS = ('DX', 'DY', 'DZ', 'RX', 'RY', 'RZ')
+_NODE_LOADS = ('FX', 'FY', 'FZ', 'MX', 'MY', 'MZ')
+_MEMBER_PT = ('Fx', 'Fy', 'Fz', 'FX', 'FY', 'FZ', 'Mx', 'My', 'Mz', 'MX', 'MY', 'MZ')
+_MEMBER_DIST = ('Fx', 'Fy', 'Fz', 'FX', 'FY', 'FZ')
+
+
+class FEModel3D:
+
+    def __init__(self):
+        self.nodes = {}
+        self.materials = {}
+        self.sections = {}
+        self.springs = {}
+        self.members = {}
+        self.quads = {}
+        self.plates = {}
+        self.meshes = {}
+        self.load_combos = {}
+        self._D = {}        # {combo: (6N, 1) displacement vector}
+        self._Rxn = {}      # {combo: (6N, 1) reaction vector}; read through node.RxnFX[...] etc.
+        self.solution = None
+        self._engine = None     # device context (lazy)
+        self._run = None        # bookkeeping of the last GPU analysis (arrays, combo index)
+        self.last_stats = None  # per-phase timings / solver statistics of the last analysis
+
+    def __repr__(self):
+        return f"FEModel3D(solution={self.solution!r})"
+
+    # ------------------------------------------------------------------------------------------
+    # naming helpers
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _auto_name(name, table, prefix, kind):
+        """User name must be new; empty/None gets prefix + count, bumped until unused."""
+        if name:
+            if name in table:
+                raise NameError(f"{kind} name '{name}' already exists")
+            return name
+        name = prefix + str(len(table))
+        bump = 1
+        while name in table:
+            name = prefix + str(len(table) + bump)
+            bump += 1
+        return name
+
+    def unique_name(self, dictionary, prefix):
+        """First unused prefix+integer name (reference helper used by mesh builders)."""
+        i = 1
+        while prefix + str(i) in dictionary:
+            i += 1
+        return prefix + str(i)
+
+    def _nodes_by_name(self, *names):
+        try:
+            return [self.nodes[n] for n in names]
+        except KeyError as e:
+            raise NameError(f"Node '{e.args[0]}' does not exist in the model")
+
+    @property
+    def load_cases(self):
+        """Sorted list of every load case named by a load (`FEModel3D.py:169-222`)."""
+        cases = []
+        for node in self.nodes.values():
+            cases.extend(load[2] for load in node.NodeLoads)
+        for member in self.members.values():
+            cases.extend(load[3] for load in member.PtLoads)
+            cases.extend(load[5] for load in member.DistLoads)
+        for shell in list(self.plates.values()) + list(self.quads.values()):
+            cases.extend(load[1] for load in shell.pressures)
+        return sorted(dict.fromkeys(cases))
+
+    # ------------------------------------------------------------------------------------------
+    # builders
+    # ------------------------------------------------------------------------------------------
+    def add_node(self, name, X, Y, Z):
+        name = self._auto_name(name, self.nodes, 'N', 'Node')
+        self.nodes[name] = Node3D(self, name, X, Y, Z)
+        self.solution = None
+        return name
+
+    def add_material(self, name, E, G, nu, rho, fy=None):
+        name = self._auto_name(name, self.materials, 'M', 'Material')
+        self.materials[name] = Material(self, name, E, G, nu, rho, fy)
+        self.solution = None
+        return name
+
+    def add_section(self, name, A, Iy, Iz, J):
+        name = self._auto_name(name, self.sections, 'SC', 'Section')
+        self.sections[name] = Section(self, name, A, Iy, Iz, J)
+        return name
+
+    def add_spring(self, name, i_node, j_node, ks, tension_only=False, comp_only=False):
+        name = self._auto_name(name, self.springs, 'S', 'Spring')
+        ni, nj = self._nodes_by_name(i_node, j_node)
+        self.springs[name] = Spring3D(name, ni, nj, ks, self.load_combos,
+                                      tension_only=tension_only, comp_only=comp_only)
+        self.solution = None
+        return name
+
+    def add_member(self, name, i_node, j_node, material_name, section_name, rotation=0.0,
+                   tension_only=False, comp_only=False):
+        name = self._auto_name(name, self.members, 'M', 'Member')
+        ni, nj = self._nodes_by_name(i_node, j_node)
+        self.members[name] = PhysMember(self, name, ni, nj, material_name, section_name,
+                                        rotation=rotation, tension_only=tension_only, comp_only=comp_only)
+        self.solution = None
+        return name
+
+    def add_plate(self, name, i_node, j_node, m_node, n_node, t, material_name, kx_mod=1.0, ky_mod=1.0):
+        name = self._auto_name(name, self.plates, 'P', 'Plate')
+        n = self._nodes_by_name(i_node, j_node, m_node, n_node)
+        self.plates[name] = Plate3D(name, n[0], n[1], n[2], n[3], t, material_name, self, kx_mod, ky_mod)
+        self.solution = None
+        return name
+
+    def add_quad(self, name, i_node, j_node, m_node, n_node, t, material_name, kx_mod=1.0, ky_mod=1.0):
+        name = self._auto_name(name, self.quads, 'Q', 'Quad')
+        n = self._nodes_by_name(i_node, j_node, m_node, n_node)
+        self.quads[name] = Quad3D(name, n[0], n[1], n[2], n[3], t, material_name, self, kx_mod, ky_mod)
+        self.solution = None
+        return name
+
+    def delete_node(self, node_name):
+        """Removes a node and every member / plate / quad attached to it (`FEModel3D.py:1060-1077`)."""
+        self.nodes.pop(node_name)
+
+        def touches(elem, attrs):
+            return any(getattr(elem, a).name == node_name for a in attrs)
+        self.members = {k: v for k, v in self.members.items() if not touches(v, ('i_node', 'j_node'))}
+        four = ('i_node', 'j_node', 'm_node', 'n_node')
+        self.plates = {k: v for k, v in self.plates.items() if not touches(v, four)}
+        self.quads = {k: v for k, v in self.quads.items() if not touches(v, four)}
+        self.solution = None
+
+    def delete_spring(self, spring_name):
+        self.springs.pop(spring_name)
+        self.solution = None
+
+    def delete_member(self, member_name):
+        self.members.pop(member_name)
+        self.solution = None
+
+    def def_support(self, node_name, support_DX=False, support_DY=False, support_DZ=False,
+                    support_RX=False, support_RY=False, support_RZ=False):
+        (node,) = self._nodes_by_name(node_name)
+        node.support_DX = support_DX
+        node.support_DY = support_DY
+        node.support_DZ = support_DZ
+        node.support_RX = support_RX
+        node.support_RY = support_RY
+        node.support_RZ = support_RZ
+        self.solution = None
+
+    def def_support_spring(self, node_name, dof, stiffness, direction=None):
+        if dof not in _NODE_DOFS:
+            raise ValueError("Invalid support spring degree of freedom. Specify 'DX', 'DY', 'DZ', 'RX', 'RY', or 'RZ'")
+        if direction not in ('+', '-', None):
+            raise ValueError("Invalid support spring direction. Specify '+', '-', or None.")
+        (node,) = self._nodes_by_name(node_name)
+        setattr(node, 'spring_' + dof, [stiffness, direction, True])
+        self.solution = None
+
+    def def_node_disp(self, node_name, direction, magnitude):
+        if direction not in _NODE_DOFS:
+            raise ValueError(f"direction must be 'DX', 'DY', 'DZ', 'RX', 'RY', or 'RZ'. {direction} was given.")
+        (node,) = self._nodes_by_name(node_name)
+        setattr(node, 'Enforced' + direction, magnitude)
+        self.solution = None
+
+    def def_releases(self, member_name, Dxi=False, Dyi=False, Dzi=False, Rxi=False, Ryi=False, Rzi=False,
+                     Dxj=False, Dyj=False, Dzj=False, Rxj=False, Ryj=False, Rzj=False):
+        try:
+            self.members[member_name].Releases = [Dxi, Dyi, Dzi, Rxi, Ryi, Rzi, Dxj, Dyj, Dzj, Rxj, Ryj, Rzj]
+        except KeyError:
+            raise NameError(f"Member '{member_name}' does not exist in the model")
+        self.solution = None
+
+    def add_load_combo(self, name, factors, combo_tags=None):
+        self.load_combos[name] = LoadCombo(name, combo_tags, factors)
+        self.solution = None
+
+    def add_node_load(self, node_name, direction, P, case='Case 1'):
+        if direction not in _NODE_LOADS:
+            raise ValueError(f"direction must be 'FX', 'FY', 'FZ', 'MX', 'MY', or 'MZ'. {direction} was given.")
+        (node,) = self._nodes_by_name(node_name)
+        node.NodeLoads.append((direction, P, case))
+        self.solution = None
+
+    def add_member_pt_load(self, member_name, direction, P, x, case='Case 1'):
+        if direction not in _MEMBER_PT:
+            raise ValueError("direction must be 'Fx', 'Fy', 'Fz', 'FX', 'FY', FZ', 'Mx', 'My', 'Mz', 'MX', 'MY', or 'MZ'. "
+                             f"{direction} was given.")
+        try:
+            self.members[member_name].PtLoads.append((direction, P, x, case))
+        except KeyError:
+            raise NameError(f"Member '{member_name}' does not exist in the model")
+        self.solution = None
+
+    def add_member_dist_load(self, member_name, direction, w1, w2, x1=None, x2=None, case='Case 1',
+                             self_weight=False):
+        if direction not in _MEMBER_DIST:
+            raise ValueError(f"direction must be 'Fx', 'Fy', 'Fz', 'FX', 'FY', or 'FZ'. {direction} was given.")
+        try:
+            member = self.members[member_name]
+        except KeyError:
+            raise NameError(f"Member '{member_name}' does not exist in the model")
+        start = 0 if x1 is None else x1
+        end = member.L() if x2 is None else x2
+        member.DistLoads.append((direction, w1, w2, start, end, case, self_weight))
+        self.solution = None
+
+    def add_member_self_weight(self, global_direction, factor, case='Case 1'):
+        if global_direction in ('Fx', 'Fy', 'Fz'):
+            raise ValueError(f"Local direction '{global_direction}' is not allowed for self-weight.  "
+                             "Use global directions 'FX', 'FY', or 'FZ' instead.")
+        if global_direction not in ('FX', 'FY', 'FZ'):
+            raise ValueError(f"Direction must be 'FX', 'FY', or 'FZ'. {global_direction} was given.")
+        for member in self.members.values():
+            w = factor*member.material.rho*member.section.A
+            self.add_member_dist_load(member.name, global_direction, w, w, case=case, self_weight=True)
+
+    def add_plate_surface_pressure(self, plate_name, pressure, case='Case 1'):
+        try:
+            self.plates[plate_name].pressures.append([pressure, case])
+        except KeyError:
+            raise NameError(f"Plate '{plate_name}' does not exist in the model")
+        self.solution = None
+
+    def add_quad_surface_pressure(self, quad_name, pressure, case='Case 1'):
+        try:
+            self.quads[quad_name].pressures.append([pressure, case])
+        except KeyError:
+            raise NameError(f"Quad '{quad_name}' does not exist in the model")
+        self.solution = None
+
+    def delete_loads(self):
+        """Removes every load and clears stored results (`FEModel3D.py:1509-1549`)."""
+        for member in self.members.values():
+            member.DistLoads = []
+            member.PtLoads = []
+        for shell in list(self.plates.values()) + list(self.quads.values()):
+            shell.pressures = []
+        for node in self.nodes.values():
+            node.NodeLoads = []
+        self._D = {}
+        self._Rxn = {}
+        self.solution = None
+
+    # ------------------------------------------------------------------------------------------
+    # matrices / vectors for inspection (computed on the GPU, returned as the reference returns them)
+    # ------------------------------------------------------------------------------------------
+    def Ke(self, combo_name='Combo 1', log=False, check_stability=True, sparse=True):
+        """Global elastic stiffness as `scipy.sparse.coo_matrix`, entries in the reference's
+        emission order with exact zeros dropped (`FEModel3D.py:1551-1800`)."""
+        return _analysis.global_Ke(self, combo_name, log, check_stability, sparse)
+
+    def Kg(self, combo_name='Combo 1', log=False, sparse=True, first_step=True):
+        """Global geometric stiffness as `coo_matrix` (`FEModel3D.py:1802-1895`)."""
+        return _analysis.global_Kg(self, combo_name, log, sparse, first_step)
+
+    def FER(self, combo_name='Combo 1'):
+        """Global fixed-end reaction vector (6N, 1) (`FEModel3D.py:2136-2182`)."""
+        return _analysis.global_load_vector(self, combo_name, 'FER')
+
+    def P(self, combo_name='Combo 1'):
+        """Global nodal force vector (6N, 1) (`FEModel3D.py:2184-2235`)."""
+        return _analysis.global_load_vector(self, combo_name, 'P')
+
+    def D(self, combo_name='Combo 1'):
+        """Global displacement vector of a solved combo (`FEModel3D.py:2237-2248`)."""
+        return self._D[combo_name]
+
+    # ------------------------------------------------------------------------------------------
+    # analysis drivers
+    # ------------------------------------------------------------------------------------------
+    def analyze_linear(self, log=False, check_stability=True, check_statics=False, sparse=True,
+                       combo_tags=None):
+        """First-order linear analysis: K assembled once, all combos solved as one multi-RHS job."""
+        _analysis.run_linear(self, log, check_stability, check_statics, sparse, combo_tags)
+
+    def analyze(self, log=False, check_stability=True, check_statics=False, max_iter=30, sparse=True,
+                combo_tags=None, spring_tolerance=0, member_tolerance=0, num_steps=1):
+        """First-order analysis with tension/compression-only iteration (`FEModel3D.py:2334-2411`)."""
+        _analysis.run_first_order(self, log, check_stability, check_statics, max_iter, sparse, combo_tags,
+                                  spring_tolerance, member_tolerance, num_steps)
+
+    def analyze_PDelta(self, log=False, check_stability=True, max_iter=30, sparse=True, combo_tags=None):
+        """Two-step P-Delta analysis (`FEModel3D.py:2413-2467`, `Analysis.py:329-471`)."""
+        _analysis.run_pdelta(self, log, check_stability, max_iter, sparse, combo_tags)
+
+    # ------------------------------------------------------------------------------------------
+    # result plumbing used by the element objects
+    # ------------------------------------------------------------------------------------------
+    def _element_force(self, kind, elem_id, combo_name, local):
+        return _analysis.element_force(self, kind, elem_id, combo_name, local)
+
+    def _member_dircos(self, sub):
+        return _analysis.member_dircos_host(sub)

@@ -1,0 +1,223 @@
+"""Frame member records: analysis sub-members and the user-facing physical member.
+
+`Member3D` carries what `Pynite/Member3D.py:37-105` stores for the stiffness path (nodes, material,
+section, roll angle, loads, releases, tension/compression-only flags, per-combo activity).  All
+stiffness math (`_ke_unc` :176, `ke` :147, `kg` :210, `T` :933, `Ke` :1038, `fer` :742, `f` :872)
+runs in the sm_100a member kernels (`csrc/elem_member.cuh`); `f()/F()` here read the end forces the
+GPU solve produced.
+
+`PhysMember.descritize` restates `Pynite/PhysMember.py:37-200`: a physical member is split at every
+model node lying strictly inside it (perpendicular distance <= 1e-12 (1+L)), sub-members are named
+name+'a', 'b', ... by distance along the member, end releases go to the end sub-members, and
+distributed / point loads are clipped onto the sub-members.
+"""
+from __future__ import annotations
+
+from math import isclose
+
+import numpy as np
+
+
+class Member3D:
+
+    def __init__(self, model, name, i_node, j_node, material_name, section_name,
+                 rotation=0.0, tension_only=False, comp_only=False):
+        self.name = name
+        self.ID = None
+        self.i_node = i_node
+        self.j_node = j_node
+        try:
+            self.material = model.materials[material_name]
+        except KeyError:
+            raise NameError(f"No material named '{material_name}'")
+        try:
+            self.section = model.sections[section_name]
+        except KeyError:
+            raise NameError(f"No section names '{section_name}'")
+        self.rotation = rotation
+        self.PtLoads = []        # (direction, P, x, case)
+        self.DistLoads = []      # (direction, w1, w2, x1, x2, case, self_weight)
+        self.Releases = [False]*12
+        self.tension_only = tension_only
+        self.comp_only = comp_only
+        self.active = {}         # {combo name: bool}
+        self._solved_combo = None
+        self.model = model
+
+    def __repr__(self):
+        return f"Member3D(name={self.name!r}, i_node={self.i_node.name!r}, j_node={self.j_node.name!r})"
+
+    def L(self):
+        return self.i_node.distance(self.j_node)
+
+    def f(self, combo_name='Combo 1'):
+        """Local end forces (12, 1) for a combo, from the last GPU solve (`Member3D.py:872-918`)."""
+        return self.model._element_force('member', self.ID, combo_name, local=True)
+
+    def F(self, combo_name='Combo 1'):
+        """Global end forces (12, 1) for a combo (`Member3D.py:1072-1078`)."""
+        return self.model._element_force('member', self.ID, combo_name, local=False)
+
+
+class PhysMember(Member3D):
+
+    def __init__(self, model, name, i_node, j_node, material_name, section_name,
+                 rotation=0.0, tension_only=False, comp_only=False):
+        super().__init__(model, name, i_node, j_node, material_name, section_name,
+                         rotation, tension_only, comp_only)
+        self.sub_members = {}
+
+    def __repr__(self):
+        return f"PhysMember(name={self.name!r}, i_node={self.i_node.name!r}, j_node={self.j_node.name!r})"
+
+    def descritize(self, node_index=None):
+        """Splits the member at interior collinear nodes (see module docstring).
+
+        `node_index` is an optional `flatten.NodeIndex` (coordinate arrays sorted by X) that limits
+        the collinearity scan to the member's bounding box; without it every node is scanned.
+        """
+        self.sub_members = {}
+        ni, nj = self.i_node, self.j_node
+        Xi, Yi, Zi = ni.X, ni.Y, ni.Z
+        Xj, Yj, Zj = nj.X, nj.Y, nj.Z
+        L = np.linalg.norm(np.array([Xj - Xi, Yj - Yi, Zj - Zi]))
+        if L == 0:
+            return
+        u = np.array([Xj - Xi, Yj - Yi, Zj - Zi])/L
+
+        stations = [(ni, 0.0), (nj, L)]
+        tol = 1e-12*(1.0 + L)
+        bb = 1e-9*(1.0 + L)
+        lo = (min(Xi, Xj) - bb, min(Yi, Yj) - bb, min(Zi, Zj) - bb)
+        hi = (max(Xi, Xj) + bb, max(Yi, Yj) + bb, max(Zi, Zj) + bb)
+
+        if node_index is None:
+            from pynite_b200.flatten import NodeIndex
+            node_index = NodeIndex(self.model)
+        cand, X, Y, Z = node_index.in_box(lo, hi)
+        if cand.size:
+            dx, dy, dz = X - Xi, Y - Yi, Z - Zi
+            t = dx*u[0] + dy*u[1] + dz*u[2]
+            px, py, pz = dx - t*u[0], dy - t*u[1], dz - t*u[2]
+            d_perp = (px**2 + py**2 + pz**2)**0.5
+            keep = (t > 0.0) & (t < L) & (d_perp <= tol)
+            nodes = node_index.nodes
+            # Model (insertion) order, as the reference scans `model.nodes.values()`.
+            for k in np.sort(cand[keep]):
+                node = nodes[k]
+                if node is ni or node is nj:
+                    continue
+                sel = np.nonzero(cand == k)[0][0]
+                stations.append((node, t[sel]))
+        stations.sort(key=lambda s: s[1])
+
+        n_sub = len(stations) - 1
+        combos = list(self.model.load_combos.keys())
+        for i in range(n_sub):
+            sub_name = self.name + chr(i + 97)
+            a_node, xi = stations[i]
+            b_node, xj = stations[i + 1]
+            sub = Member3D(self.model, sub_name, a_node, b_node, self.material.name,
+                           self.section.name, self.rotation, self.tension_only, self.comp_only)
+            for combo_name in combos:
+                sub.active[combo_name] = True
+            if i == 0:
+                sub.Releases[0:6] = self.Releases[0:6]
+            if i == n_sub - 1:
+                sub.Releases[6:12] = self.Releases[6:12]
+
+            for direction, w1, w2, x1_load, x2_load, case, self_weight in self.DistLoads:
+                if x1_load <= xj and x2_load > xi:
+                    span = x2_load - x1_load
+                    if x1_load > xi:
+                        x1 = x1_load - xi
+                    else:
+                        x1 = 0
+                        w1 = (w2 - w1)/span*(xi - x1_load) + w1
+                    if x2_load < xj:
+                        x2 = x2_load - xi
+                    else:
+                        x2 = xj - xi
+                        # NOTE: evaluated with the *already clipped* w1, exactly as the reference's
+                        # late-binding closure does (`PhysMember.py:165-178`).
+                        w2 = (w2 - w1)/span*(xj - x1_load) + w1
+                    sub.DistLoads.append([direction, w1, w2, x1, x2, case, self_weight])
+
+            for direction, P, x, case in self.PtLoads:
+                if x >= xi and x < xj or (isclose(x, xj) and isclose(xj, self.L())):
+                    sub.PtLoads.append([direction, P, x - xi, case])
+
+            self.sub_members[sub_name] = sub
+
+    # -- axial-force extremes used by the tension/compression-only iteration ------------------
+    def _axial_extremes(self, combo_name):
+        """(max, min) axial force over all sub-members (`Analysis.py:1022,1037` consumers).
+
+        Sign convention as the reference's `Member3D.axial`: positive = compression.  The axial
+        force at station x of a sub-member is f[0] (local i-end force) plus the axial loads applied
+        between 0 and x; extremes of a piecewise linear/quadratic diagram are at load stations and
+        at interior stationary points of distributed loads.
+        """
+        model = self.model
+        combo = model.load_combos[combo_name]
+        best_max, best_min = -np.inf, np.inf
+        for sub in self.sub_members.values():
+            f0 = sub.f(combo_name)[0, 0]
+            L = sub.L()
+            R = model._member_dircos(sub)
+            pts, dists = [], []
+            for direction, P, x, case in sub.PtLoads:
+                factor = combo.factors.get(case)
+                if factor is None:
+                    continue
+                if direction == 'Fx':
+                    pts.append((x, factor*P))
+                elif direction in ('FX', 'FY', 'FZ'):
+                    g = np.zeros(3)
+                    g['XYZ'.index(direction[1])] = P
+                    pts.append((x, factor*(R @ g)[0]))
+            for direction, w1, w2, x1, x2, case, _sw in sub.DistLoads:
+                factor = combo.factors.get(case)
+                if factor is None:
+                    continue
+                if direction == 'Fx':
+                    dists.append((x1, x2, factor*w1, factor*w2))
+                elif direction in ('FX', 'FY', 'FZ'):
+                    k = 'XYZ'.index(direction[1])
+                    g1 = np.zeros(3)
+                    g2 = np.zeros(3)
+                    g1[k], g2[k] = w1, w2
+                    dists.append((x1, x2, factor*(R @ g1)[0], factor*(R @ g2)[0]))
+
+            def axial_at(x, after):
+                n = f0
+                for xp, p in pts:
+                    if xp < x or (after and xp == x):
+                        n += p
+                for x1, x2, p1, p2 in dists:
+                    if x > x1 and x2 > x1:
+                        xe = min(x, x2)
+                        pe = p1 + (p2 - p1)*(xe - x1)/(x2 - x1)
+                        n += 0.5*(p1 + pe)*(xe - x1)
+                return n
+
+            stations = {0.0, L}
+            for xp, _p in pts:
+                stations.add(xp)
+            for x1, x2, p1, p2 in dists:
+                stations.add(x1)
+                stations.add(x2)
+                if p1*p2 < 0:
+                    stations.add(x1 + (x2 - x1)*p1/(p1 - p2))
+            for x in stations:
+                for after in (False, True):
+                    n = axial_at(x, after)
+                    best_max = max(best_max, n)
+                    best_min = min(best_min, n)
+        return best_max, best_min
+
+    def max_axial(self, combo_name='Combo 1'):
+        return self._axial_extremes(combo_name)[0]
+
+    def min_axial(self, combo_name='Combo 1'):
+        return self._axial_extremes(combo_name)[1]

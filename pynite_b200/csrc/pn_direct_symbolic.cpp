@@ -1,0 +1,308 @@
+// Host-side symbolic analysis for the multifrontal solver.  See pn_direct_symbolic.h.
+#include "pn_direct_symbolic.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+
+namespace pn {
+
+void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xyz, const std::vector<ConnView> &conn,
+                        std::vector<int32_t> &vstart, std::vector<double> &coords, std::vector<int64_t> &adj_ptr,
+                        std::vector<int32_t> &adj) {
+    // vertices = nodes with at least one free DOF, in node order, so K11 rows stay contiguous per vertex
+    std::vector<int32_t> vid(n_nodes, -1);
+    vstart.clear();
+    coords.clear();
+    int32_t nv = 0;
+    for (int64_t nd = 0; nd < n_nodes; ++nd) {
+        int32_t first = -1, cnt = 0;
+        for (int k = 0; k < 6; ++k) {
+            int32_t ni = newidx[6 * nd + k];
+            if (ni >= 0) { if (first < 0) first = ni; ++cnt; }
+        }
+        if (cnt) {
+            vid[nd] = nv++;
+            vstart.push_back(first);
+            coords.push_back(xyz[3 * nd]); coords.push_back(xyz[3 * nd + 1]); coords.push_back(xyz[3 * nd + 2]);
+        }
+    }
+    // vstart needs an end sentinel: rows are contiguous and ascending over vertices
+    {
+        int64_t n1 = 0;
+        for (int64_t d = 0; d < 6 * n_nodes; ++d) if (newidx[d] >= 0) ++n1;
+        vstart.push_back((int32_t)n1);
+    }
+    // count, fill (with duplicates), then sort + unique per vertex
+    std::vector<int64_t> deg(nv + 1, 0);
+    for (const ConnView &cv : conn)
+        for (int64_t e = 0; e < cv.count; ++e) {
+            if (cv.active && !cv.active[e]) continue;
+            for (int a = 0; a < cv.nn; ++a) {
+                int32_t va = vid[cv.nodes[cv.nn * e + a]];
+                if (va < 0) continue;
+                for (int b = 0; b < cv.nn; ++b) {
+                    int32_t vb = vid[cv.nodes[cv.nn * e + b]];
+                    if (vb >= 0 && vb != va) ++deg[va];
+                }
+            }
+        }
+    std::vector<int64_t> ptr(nv + 1, 0);
+    for (int32_t v = 0; v < nv; ++v) ptr[v + 1] = ptr[v] + deg[v];
+    std::vector<int32_t> raw(ptr[nv]);
+    std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+    for (const ConnView &cv : conn)
+        for (int64_t e = 0; e < cv.count; ++e) {
+            if (cv.active && !cv.active[e]) continue;
+            for (int a = 0; a < cv.nn; ++a) {
+                int32_t va = vid[cv.nodes[cv.nn * e + a]];
+                if (va < 0) continue;
+                for (int b = 0; b < cv.nn; ++b) {
+                    int32_t vb = vid[cv.nodes[cv.nn * e + b]];
+                    if (vb >= 0 && vb != va) raw[fill[va]++] = vb;
+                }
+            }
+        }
+    std::vector<int64_t> cnt(nv, 0);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int32_t v = 0; v < nv; ++v) {
+        auto b = raw.begin() + ptr[v], e = raw.begin() + ptr[v + 1];
+        std::sort(b, e);
+        cnt[v] = std::unique(b, e) - b;
+    }
+    adj_ptr.assign(nv + 1, 0);
+    for (int32_t v = 0; v < nv; ++v) adj_ptr[v + 1] = adj_ptr[v] + cnt[v];
+    adj.resize(adj_ptr[nv]);
+#pragma omp parallel for schedule(static)
+    for (int32_t v = 0; v < nv; ++v) std::copy(raw.begin() + ptr[v], raw.begin() + ptr[v] + cnt[v], adj.begin() + adj_ptr[v]);
+}
+
+namespace {
+
+struct Builder {
+    int32_t nv;
+    const int32_t *vstart;
+    const double *coords;
+    const int64_t *adj_ptr;
+    const int32_t *adj;
+    int leaf_size;
+    std::vector<int32_t> region;          // scratch marker per vertex
+    int32_t next_region = 1;
+    // outputs at vertex level
+    std::vector<std::vector<int32_t>> front_verts;   // own vertices of each front (post-order ids)
+    std::vector<int32_t> parent;
+
+    // Orders the vertex set `verts` and everything it induces; returns the ids of the fronts that are the
+    // roots of this set's elimination forest (to be attached to the caller's separator).
+    void dissect(std::vector<int32_t> &verts, std::vector<int32_t> &roots_out) {
+        if ((int)verts.size() <= leaf_size) {
+            if (verts.empty()) return;
+            int32_t id = (int32_t)front_verts.size();
+            std::sort(verts.begin(), verts.end());
+            front_verts.push_back(verts);
+            parent.push_back(-1);
+            roots_out.push_back(id);
+            return;
+        }
+        // widest coordinate axis
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int32_t v : verts)
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = std::min(lo[k], coords[3 * v + k]);
+                hi[k] = std::max(hi[k], coords[3 * v + k]);
+            }
+        int axis = 0;
+        for (int k = 1; k < 3; ++k) if (hi[k] - lo[k] > hi[axis] - lo[axis]) axis = k;
+        size_t mid = verts.size() / 2;
+        auto cmp = [&](int32_t a, int32_t b) {
+            double ca = coords[3 * a + axis], cb = coords[3 * b + axis];
+            return ca < cb || (ca == cb && a < b);
+        };
+        std::nth_element(verts.begin(), verts.begin() + mid, verts.end(), cmp);
+        // keep vertices with the same coordinate as the median on one side when possible, so that
+        // separators of structured meshes are straight lines / planes
+        {
+            double cm = coords[3 * verts[mid] + axis];
+            size_t lo_cnt = 0;
+            for (int32_t v : verts) if (coords[3 * v + axis] < cm) ++lo_cnt;
+            if (lo_cnt > verts.size() / 4) {
+                auto it = std::partition(verts.begin(), verts.end(), [&](int32_t v) { return coords[3 * v + axis] < cm; });
+                mid = it - verts.begin();
+            }
+        }
+        int32_t ra = next_region++, rb = next_region++;
+        for (size_t i = 0; i < verts.size(); ++i) region[verts[i]] = i < mid ? ra : rb;
+        std::vector<int32_t> A, B, S;
+        // separator = vertices of B touching A (B holds the median plane, which is the natural cut)
+        for (size_t i = 0; i < verts.size(); ++i) {
+            int32_t v = verts[i];
+            if (i < mid) { A.push_back(v); continue; }
+            bool touches = false;
+            for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k)
+                if (region[adj[k]] == ra) { touches = true; break; }
+            (touches ? S : B).push_back(v);
+        }
+        std::vector<int32_t>().swap(verts);
+        std::vector<int32_t> child_roots;
+        dissect(A, child_roots);
+        dissect(B, child_roots);
+        if (S.empty()) {          // A and B are disconnected: no separator, pass the forests up
+            roots_out.insert(roots_out.end(), child_roots.begin(), child_roots.end());
+            return;
+        }
+        int32_t id = (int32_t)front_verts.size();
+        std::sort(S.begin(), S.end());
+        front_verts.push_back(S);
+        parent.push_back(-1);
+        for (int32_t r : child_roots) parent[r] = id;
+        roots_out.push_back(id);
+    }
+};
+
+}  // namespace
+
+void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double *coords, const int64_t *adj_ptr,
+                     const int32_t *adj, int leaf_size, DirectSym &out) {
+    out = DirectSym();
+    out.n = n;
+    if (n == 0 || nv == 0) { out.level_ptr.assign(1, 0); return; }
+    Builder b;
+    b.nv = nv; b.vstart = vstart; b.coords = coords; b.adj_ptr = adj_ptr; b.adj = adj; b.leaf_size = leaf_size;
+    b.region.assign(nv, 0);
+    std::vector<int32_t> all(nv);
+    std::iota(all.begin(), all.end(), 0);
+    std::vector<int32_t> roots;
+    b.dissect(all, roots);
+    const int32_t nf = (int32_t)b.front_verts.size();
+
+    // vertex elimination positions (post-order front ids = elimination order) and DOF positions
+    std::vector<int32_t> vfront(nv), vorder(nv);      // vorder: rank of the vertex in elimination order
+    std::vector<int32_t> vert_seq;                     // vertices in elimination order
+    vert_seq.reserve(nv);
+    std::vector<int32_t> f_vbeg(nf + 1, 0);
+    for (int32_t f = 0; f < nf; ++f) {
+        f_vbeg[f] = (int32_t)vert_seq.size();
+        for (int32_t v : b.front_verts[f]) { vfront[v] = f; vorder[v] = (int32_t)vert_seq.size(); vert_seq.push_back(v); }
+    }
+    f_vbeg[nf] = (int32_t)vert_seq.size();
+    if ((int32_t)vert_seq.size() != nv) throw std::runtime_error("direct_symbolic: vertices lost in dissection");
+    std::vector<int32_t> vdofpos(nv + 1, 0);           // DOF elimination position of vertex with order r
+    for (int32_t r = 0; r < nv; ++r) {
+        int32_t v = vert_seq[r];
+        vdofpos[r + 1] = vdofpos[r] + (vstart[v + 1] - vstart[v]);
+    }
+    out.perm_pos.assign(n, -1);
+    out.dof_front.assign(n, -1);
+    for (int32_t r = 0; r < nv; ++r) {
+        int32_t v = vert_seq[r];
+        for (int32_t k = 0; k < vstart[v + 1] - vstart[v]; ++k) {
+            out.perm_pos[vstart[v] + k] = vdofpos[r] + k;
+            out.dof_front[vstart[v] + k] = vfront[v];
+        }
+    }
+
+    // boundary vertex sets, bottom-up (as vertex orders, ascending)
+    std::vector<std::vector<int32_t>> bnd(nf);
+    std::vector<std::vector<int32_t>> children(nf);
+    for (int32_t f = 0; f < nf; ++f) if (b.parent[f] >= 0) children[b.parent[f]].push_back(f);
+    for (int32_t f = 0; f < nf; ++f) {
+        int32_t vend = f_vbeg[f + 1];
+        std::vector<int32_t> cur;
+        for (int32_t v : b.front_verts[f])
+            for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k) {
+                int32_t o = vorder[adj[k]];
+                if (o >= vend) cur.push_back(o);
+            }
+        std::sort(cur.begin(), cur.end());
+        cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
+        for (int32_t c : children[f]) {
+            std::vector<int32_t> merged;
+            merged.reserve(cur.size() + bnd[c].size());
+            auto first = std::lower_bound(bnd[c].begin(), bnd[c].end(), vend);
+            std::set_union(cur.begin(), cur.end(), first, bnd[c].end(), std::back_inserter(merged));
+            cur.swap(merged);
+        }
+        bnd[f].swap(cur);
+        // every boundary vertex must live in an ancestor; a root must have an empty boundary
+        if (b.parent[f] < 0 && !bnd[f].empty())
+            throw std::runtime_error("direct_symbolic: root front with a non-empty boundary");
+    }
+
+    // fronts, index lists
+    out.fronts.resize(nf);
+    std::vector<int32_t> depth(nf, 0);
+    for (int32_t f = nf - 1; f >= 0; --f) depth[f] = b.parent[f] < 0 ? 0 : depth[b.parent[f]] + 1;
+    int32_t maxdepth = 0;
+    int64_t total_idx = 0, total_rel = 0;
+    for (int32_t f = 0; f < nf; ++f) {
+        FrontSym &F = out.fronts[f];
+        F.parent = b.parent[f];
+        F.depth = depth[f];
+        maxdepth = std::max(maxdepth, depth[f]);
+        F.pos_start = vdofpos[f_vbeg[f]];
+        F.ns = vdofpos[f_vbeg[f + 1]] - vdofpos[f_vbeg[f]];
+        int32_t nbd = 0;
+        for (int32_t o : bnd[f]) nbd += vdofpos[o + 1] - vdofpos[o];
+        F.nb = nbd;
+        F.idx_off = total_idx;
+        F.rel_off = total_rel;
+        total_idx += F.ns + F.nb;
+        total_rel += F.nb;
+        out.max_front = std::max<int64_t>(out.max_front, F.ns + F.nb);
+        double ns = F.ns, nbv = F.nb;
+        out.factor_entries += (int64_t)(F.ns + F.nb) * F.ns + (int64_t)F.ns * F.nb;
+        out.factor_flops += 2.0 / 3.0 * ns * ns * ns + 2.0 * ns * ns * nbv + 2.0 * ns * nbv * nbv;
+    }
+    for (int32_t f = 0; f < nf; ++f) {
+        int32_t rank = 0;
+        for (int32_t c : children[f]) out.fronts[c].child_rank = rank++;
+        out.max_children = std::max(out.max_children, rank);
+    }
+    // inverse of perm_pos for index lists in K11 numbering
+    std::vector<int32_t> pos_dof(n);
+    for (int64_t d = 0; d < n; ++d) pos_dof[out.perm_pos[d]] = (int32_t)d;
+    out.fpos.resize(total_idx);
+    out.fidx.resize(total_idx);
+    out.rel.resize(total_rel);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t f = 0; f < nf; ++f) {
+        const FrontSym &F = out.fronts[f];
+        int64_t o = F.idx_off;
+        for (int32_t k = 0; k < F.ns; ++k) out.fpos[o++] = F.pos_start + k;
+        for (int32_t vo : bnd[f])
+            for (int32_t p = vdofpos[vo]; p < vdofpos[vo + 1]; ++p) out.fpos[o++] = p;
+        for (int64_t k = F.idx_off; k < F.idx_off + F.ns + F.nb; ++k) out.fidx[k] = pos_dof[out.fpos[k]];
+    }
+    int bad_rel = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t f = 0; f < nf; ++f) {
+        const FrontSym &F = out.fronts[f];
+        if (F.parent < 0) continue;
+        const FrontSym &P = out.fronts[F.parent];
+        const int32_t *pl = out.fpos.data() + P.idx_off;
+        int32_t plen = P.ns + P.nb;
+        int32_t q = 0;
+        for (int32_t k = 0; k < F.nb; ++k) {
+            int32_t p = out.fpos[F.idx_off + F.ns + k];
+            while (q < plen && pl[q] < p) ++q;
+            if (q >= plen || pl[q] != p) {
+#pragma omp atomic write
+                bad_rel = 1;
+                break;
+            }
+            out.rel[F.rel_off + k] = q;
+        }
+    }
+    if (bad_rel) throw std::runtime_error("direct_symbolic: child boundary not contained in parent front");
+    // levels: level = maxdepth - depth, so children sit exactly one level below their parent
+    int32_t nl = maxdepth + 1;
+    out.level_ptr.assign(nl + 1, 0);
+    for (int32_t f = 0; f < nf; ++f) ++out.level_ptr[maxdepth - depth[f] + 1];
+    for (int32_t l = 0; l < nl; ++l) out.level_ptr[l + 1] += out.level_ptr[l];
+    out.level_fronts.resize(nf);
+    std::vector<int32_t> fillp(out.level_ptr.begin(), out.level_ptr.end() - 1);
+    for (int32_t f = 0; f < nf; ++f) out.level_fronts[fillp[maxdepth - depth[f]]++] = f;
+}
+
+}  // namespace pn

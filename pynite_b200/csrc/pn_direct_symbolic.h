@@ -1,0 +1,55 @@
+// Symbolic analysis for the sparse direct solver (host side, no CUDA): nested-dissection ordering
+// of the node graph from node coordinates, separator tree = supernodal elimination tree, front
+// index lists and extend-add maps.  See pn_direct.cu for the numeric multifrontal factorisation.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace pn {
+
+struct FrontSym {
+    int32_t ns = 0;          // pivot DOFs eliminated in this front
+    int32_t nb = 0;          // boundary DOFs (rows/cols of the update matrix)
+    int32_t parent = -1;     // parent front or -1 for a root
+    int32_t depth = 0;       // root = 0
+    int32_t child_rank = 0;  // 0, 1, ... among the children of `parent`
+    int32_t pos_start = 0;   // elimination position of the first pivot DOF
+    int64_t idx_off = 0;     // offset into fidx / fpos (length ns + nb)
+    int64_t rel_off = 0;     // offset into rel (length nb)
+};
+
+struct DirectSym {
+    int64_t n = 0;                    // order of K11
+    std::vector<int32_t> perm_pos;    // [n] elimination position of each K11 row
+    std::vector<int32_t> dof_front;   // [n] front that eliminates each K11 row
+    std::vector<FrontSym> fronts;     // post-order: children before parents
+    std::vector<int32_t> fidx;        // front index lists as K11 row numbers
+    std::vector<int32_t> fpos;        // the same lists as elimination positions (ascending per front)
+    std::vector<int32_t> rel;         // for each boundary DOF: its position in the parent's index list
+    std::vector<int32_t> level_ptr;   // level l holds fronts level_fronts[level_ptr[l] .. level_ptr[l+1])
+    std::vector<int32_t> level_fronts;   // level 0 = deepest; every child is exactly one level below its parent
+    int32_t max_children = 0;
+    int64_t factor_entries = 0;       // stored entries of L and U
+    double factor_flops = 0;
+    int64_t max_front = 0;            // largest ns + nb
+};
+
+// Vertex graph: vertex v owns K11 rows vstart[v] .. vstart[v+1]; coords[3 v ..]; adjacency in CSR
+// (no self loops needed; symmetric).  leaf_size = vertices per leaf region.
+void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double *coords, const int64_t *adj_ptr,
+                     const int32_t *adj, int leaf_size, DirectSym &out);
+
+// Builds the vertex graph of the free DOFs from element connectivity.
+// newidx[dof] >= 0 gives the K11 row of a free DOF.  `conn` lists for each element kind are
+// (count, nodes per element, node ids, optional active flags).
+struct ConnView {
+    int64_t count;
+    int nn;
+    const int32_t *nodes;
+    const uint8_t *active;   // may be null
+};
+void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xyz, const std::vector<ConnView> &conn,
+                        std::vector<int32_t> &vstart, std::vector<double> &coords, std::vector<int64_t> &adj_ptr,
+                        std::vector<int32_t> &adj);
+
+}  // namespace pn

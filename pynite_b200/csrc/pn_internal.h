@@ -1,0 +1,236 @@
+// Internal declarations of the pynite_b200 CUDA library: context, device buffers, launcher
+// prototypes.  Not part of the public ABI (that is include/pynite_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pynite_b200.h"
+
+namespace pn {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct ArgError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct StatusError : std::runtime_error {
+    int code;
+    StatusError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define PN_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            throw pn::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(err__) +     \
+                                " (" __FILE__ ":" + std::to_string(__LINE__) + ")");               \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    int64_t n = 0;        // elements in use
+    int64_t cap = 0;      // elements allocated
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        n = cap = 0;
+    }
+    // grow-only allocation; contents are undefined afterwards
+    void resize(int64_t count) {
+        if (count > cap) {
+            if (ptr) cudaFree(ptr);
+            ptr = nullptr;
+            cap = 0;
+            PN_CUDA(cudaMalloc((void **)&ptr, (size_t)(count > 0 ? count : 1) * sizeof(T)));
+            cap = count > 0 ? count : 1;
+        }
+        n = count;
+    }
+    void zero(cudaStream_t st) {
+        if (n) PN_CUDA(cudaMemsetAsync(ptr, 0, (size_t)n * sizeof(T), st));
+    }
+    void upload(const T *host, int64_t count, cudaStream_t st) {
+        resize(count);
+        if (count) PN_CUDA(cudaMemcpyAsync(ptr, host, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void download(T *host, cudaStream_t st) const {
+        if (n) PN_CUDA(cudaMemcpyAsync(host, ptr, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+};
+
+struct Model {
+    int64_t n_nodes = 0, n_springs = 0, n_members = 0, n_quads = 0, n_plates = 0;
+    DevBuf<double> xyz;
+    DevBuf<uint8_t> support, enf_mask, nspring_flag;
+    DevBuf<double> enf_val, nspring_k;
+    DevBuf<int32_t> spring_ij;
+    DevBuf<double> spring_ks;
+    DevBuf<uint8_t> spring_active;
+    DevBuf<int32_t> mem_ij;
+    DevBuf<double> mem_props, mem_rot;
+    DevBuf<uint16_t> mem_rel;
+    DevBuf<uint8_t> mem_active;
+    DevBuf<int32_t> quad_ijmn, plate_ijmn;
+    DevBuf<double> quad_props, plate_props;
+    // host copies needed by host-side logic
+    std::vector<uint8_t> h_support, h_enf_mask, h_nspring_flag, h_spring_active, h_mem_active;
+    std::vector<double> h_enf_val, h_nspring_k, h_xyz;
+    std::vector<int32_t> h_spring_ij, h_mem_ij, h_quad_ijmn, h_plate_ijmn;
+    bool symmetric = true;      // false when a shell has kx_mod != ky_mod (membrane matrix unsymmetric)
+};
+
+struct Loads {
+    int32_t n_case = 0;
+    // nodal loads (unique (dof, case), pre-summed by the host binding)
+    DevBuf<int32_t> nl_dof, nl_case;
+    DevBuf<double> nl_val;
+    // member loads grouped by (member, case)
+    int64_t n_mloads = 0, n_mgroups = 0;
+    DevBuf<int32_t> ml_kind;
+    DevBuf<double> ml_params;
+    DevBuf<int32_t> mg_member, mg_case;
+    DevBuf<int64_t> mg_start;
+    DevBuf<double> mg_fer_local, mg_fer_global;     // [n_mgroups][12]
+    // shell pressures (unique (element, case), pre-summed by the host binding)
+    DevBuf<int32_t> qp_elem, qp_case, pp_elem, pp_case;
+    DevBuf<double> qp_val, pp_val;
+    std::vector<uint8_t> case_has_quad, case_has_plate;
+    // dense per-case vectors
+    DevBuf<double> Pcase;      // [n_case][n_dof]  nodal loads
+    DevBuf<double> fer_case;   // [n_case][ef_count] element fixed-end forces, global axes
+    DevBuf<double> Gcase;      // [n_case][n_dof]  P - FER
+    int32_t n_combo = 0;
+    DevBuf<double> factors;    // [n_combo][n_case]
+    std::vector<double> h_factors;
+    bool vectors_ready = false;
+};
+
+// A block of the partitioned matrix (K11, K12, K21, K22) in CSR with a gather map into K's values.
+struct CsrBlock {
+    int64_t rows = 0, cols = 0, nnz = 0;
+    DevBuf<int32_t> indptr, indices;
+    DevBuf<uint32_t> src;      // slot in the unpartitioned CSR
+    DevBuf<double> vals;
+};
+
+struct DirectSolver;   // pn_direct.cu
+struct PcgWork;        // pn_pcg.cu
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    pn_stats stats{};
+    int64_t launches = 0;
+    void count_launch(int64_t k = 1) { launches += k; }
+
+    Model model;
+    Loads loads;
+
+    // element-value buffer: [node springs | springs*144 | members*144 | quads*576 | plates*576]
+    DevBuf<double> ev;
+    int64_t ev_count = 0, n_nsp = 0;
+    int64_t ev_off_spring = 0, ev_off_member = 0, ev_off_quad = 0, ev_off_plate = 0;
+    DevBuf<int32_t> nsp_dof;       // global DOF of each active node support spring, model order
+    DevBuf<double> nsp_val;
+    bool ev_ready = false;
+
+    // symbolic results
+    bool symbolic_ready = false;
+    uint32_t sym_flags = 0;
+    int64_t n_dof = 0, nnz_coo = 0, nnz_csr = 0, n1 = 0, n2 = 0;
+    DevBuf<uint64_t> coo_key;      // sorted (row << 32 | col)
+    DevBuf<uint32_t> coo_src;      // ev position of each sorted COO entry
+    DevBuf<uint32_t> coo_emit;     // ev position of each COO entry in emission order
+    DevBuf<uint32_t> seg_start;    // [nnz_csr + 1] first sorted COO entry of each CSR slot
+    DevBuf<int32_t> indptr, indices;
+    DevBuf<double> vals;
+    bool vals_ready = false;
+    DevBuf<int32_t> d1, d2, newidx; // newidx[dof] >= 0: position in d1; < 0: -1 - position in d2
+    DevBuf<double> d2_val;
+    CsrBlock blk[4];               // K11, K12, K21, K22
+
+    // element-force buffer layout [springs*12 | members*12 | quads*24 | plates*24] and DOF incidence
+    int64_t ef_count = 0, ef_off_spring = 0, ef_off_member = 0, ef_off_quad = 0, ef_off_plate = 0;
+    DevBuf<uint32_t> inc_src;      // ef positions sorted by global DOF (stable = emission order)
+    DevBuf<uint32_t> inc_start;    // [n_dof + 1]
+    bool incidence_ready = false;
+
+    // solve state
+    DevBuf<double> B, X;           // [n1][s] row-major
+    DevBuf<double> kd2;            // K12 * D2, [n1]
+    DevBuf<double> D_all;          // [n_combo][n_dof]
+    DevBuf<double> ef;             // element end forces of the combo being post-processed
+    DevBuf<double> fer_combo;      // combined FER of that combo, ef layout
+    DevBuf<double> memP;           // member axial forces
+    bool solved = false;
+    bool solved_pdelta = false;
+
+    DirectSolver *direct = nullptr;
+    PcgWork *pcg = nullptr;
+
+    DevBuf<uint8_t> cub_tmp;       // scratch for cub device-wide primitives
+};
+
+// RAII timer on the context stream
+struct PhaseTimer {
+    Ctx *c;
+    double *acc;
+    PhaseTimer(Ctx *ctx, double *accum) : c(ctx), acc(accum) { cudaEventRecord(c->ev0, c->stream); }
+    ~PhaseTimer() {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        *acc += ms;
+    }
+};
+
+// ---- pn_elements.cu -------------------------------------------------------------------------------
+void launch_element_ke(Ctx *c, cudaStream_t st);
+void launch_member_kg(Ctx *c, const double *P_dev, double *out_dev, cudaStream_t st);
+void launch_member_axial(Ctx *c, const double *D_dev, double *P_dev, cudaStream_t st);
+void launch_member_fer_groups(Ctx *c, cudaStream_t st);
+void launch_shell_fer(Ctx *c, bool quad, const double *pressure_dev, double *out_dev, cudaStream_t st);
+void launch_element_forces(Ctx *c, int kind, const double *D_dev, const double *fer_dev, double *out_dev,
+                           cudaStream_t st);
+void launch_member_pdelta_forces(Ctx *c, const double *D_dev, double *F_dev, cudaStream_t st);
+void launch_forces_to_local(Ctx *c, int kind, double *F_dev, cudaStream_t st);
+
+// ---- pn_sparse.cu ---------------------------------------------------------------------------------
+void build_symbolic(Ctx *c, uint32_t flags);
+void scatter_add_values(Ctx *c, const double *ev_dev, double *vals_dev);
+void gather_block_values(Ctx *c, const double *vals_dev);
+void build_incidence(Ctx *c);
+void build_load_vectors(Ctx *c);
+void build_rhs(Ctx *c);                      // B = factors * G restricted to D1 - K12 D2
+void merge_displacements(Ctx *c);            // X, D2 -> D_all
+void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev /* [n_dof] */);
+void combine_fer(Ctx *c, int32_t combo);     // fer_combo = sum_case factor * fer_case
+int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap);
+// Y = A X for a CSR block, X/Y row-major with s columns
+void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st);
+void spmv_plain(Ctx *c, const CsrBlock &A, const double *x, double *y, cudaStream_t st);
+
+// ---- pn_pcg.cu / pn_direct.cu ---------------------------------------------------------------------
+// Solve K11 X = B for all s columns; `vals11` may differ per column when per_column_vals != 0
+// (P-Delta: one matrix per combo, same pattern): vals11 is then [s][nnz11].
+void pcg_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
+void pcg_release(Ctx *c);
+void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host);
+void direct_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
+void direct_release(Ctx *c);
+
+}  // namespace pn

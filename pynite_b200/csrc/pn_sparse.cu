@@ -1,0 +1,717 @@
+// Sparse machinery: symbolic phase (COO keys in emission order -> sorted unique CSR pattern and the
+// scatter map), deterministic COO->CSR scatter-add, partition into K11/K12/K21/K22, DOF incidence,
+// load vectors, right-hand sides, reactions, SpMM.
+//
+// Device-wide sort / scan use CUB (shipped with the CUDA toolkit) in the *symbolic* phase only, which
+// runs once per topology; the numeric kernels that run per assembly / per iteration are written here.
+#include <cub/cub.cuh>
+
+#include "pn_internal.h"
+
+namespace pn {
+
+static inline unsigned grid_for(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers: (element kind, element, local row, local col) of an element-value position
+// ------------------------------------------------------------------------------------------------
+struct EvLayout {
+    int64_t n_nsp, off_spring, off_member, off_quad, off_plate, count;
+    const int32_t *nsp_dof, *spring_ij, *mem_ij, *quad_ijmn, *plate_ijmn;
+    const uint8_t *spring_active, *mem_active;
+};
+
+__device__ __forceinline__ void ev_row_col(const EvLayout &L, int64_t p, int32_t &row, int32_t &col, int &kind,
+                                           int64_t &elem) {
+    if (p < L.n_nsp) {
+        row = col = L.nsp_dof[p];
+        kind = 0; elem = p;
+        return;
+    }
+    const int32_t *conn;
+    int nd, nn;
+    int64_t q;
+    if (p < L.off_member) { q = p - L.off_spring; conn = L.spring_ij; nd = 12; nn = 2; kind = PN_SPRING; }
+    else if (p < L.off_quad) { q = p - L.off_member; conn = L.mem_ij; nd = 12; nn = 2; kind = PN_MEMBER; }
+    else if (p < L.off_plate) { q = p - L.off_quad; conn = L.quad_ijmn; nd = 24; nn = 4; kind = PN_QUAD; }
+    else { q = p - L.off_plate; conn = L.plate_ijmn; nd = 24; nn = 4; kind = PN_PLATE; }
+    int64_t e = q / (nd * nd);
+    int rem = (int)(q - e * (nd * nd));
+    int r = rem / nd, cc = rem - r * nd;
+    row = conn[nn * e + r / 6] * 6 + r % 6;
+    col = conn[nn * e + cc / 6] * 6 + cc % 6;
+    elem = e;
+}
+
+static EvLayout make_layout(Ctx *c) {
+    EvLayout L;
+    L.n_nsp = c->n_nsp; L.off_spring = c->ev_off_spring; L.off_member = c->ev_off_member;
+    L.off_quad = c->ev_off_quad; L.off_plate = c->ev_off_plate; L.count = c->ev_count;
+    L.nsp_dof = c->nsp_dof.ptr; L.spring_ij = c->model.spring_ij.ptr; L.mem_ij = c->model.mem_ij.ptr;
+    L.quad_ijmn = c->model.quad_ijmn.ptr; L.plate_ijmn = c->model.plate_ijmn.ptr;
+    L.spring_active = c->model.spring_active.ptr; L.mem_active = c->model.mem_active.ptr;
+    return L;
+}
+
+// FEModel3D._append_sparse_block :130 keeps an entry iff value != 0.0; node support springs are
+// appended unconditionally (:1587-1690); inactive springs / members are skipped (:1696, :1717).
+__global__ void k_entry_flags(EvLayout L, const double *__restrict__ ev, int dense_members, uint8_t *__restrict__ flag) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= L.count) return;
+    uint8_t f;
+    if (p < L.n_nsp) f = 1;
+    else if (p < L.off_member) f = L.spring_active[(p - L.off_spring) / 144] && ev[p] != 0.0;
+    else if (p < L.off_quad) f = L.mem_active[(p - L.off_member) / 144] && (dense_members || ev[p] != 0.0);
+    else f = ev[p] != 0.0;
+    flag[p] = f;
+}
+
+__global__ void k_emit_coo(EvLayout L, const uint8_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                           uint64_t *__restrict__ key, uint32_t *__restrict__ src) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= L.count || !flag[p]) return;
+    int32_t row, col; int kind; int64_t e;
+    ev_row_col(L, p, row, col, kind, e);
+    uint32_t cpos = pos[p];
+    key[cpos] = ((uint64_t)(uint32_t)row << 32) | (uint32_t)col;
+    src[cpos] = (uint32_t)p;
+}
+
+__global__ void k_heads(int64_t n, const uint64_t *__restrict__ key, uint32_t *__restrict__ head) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    head[k] = (k == 0 || key[k] != key[k - 1]) ? 1u : 0u;
+}
+
+__global__ void k_fill_pattern(int64_t n, const uint64_t *__restrict__ key, const uint32_t *__restrict__ head,
+                               const uint32_t *__restrict__ incl, int32_t *__restrict__ indices,
+                               int32_t *__restrict__ slot_row, uint32_t *__restrict__ seg_start) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n || !head[k]) return;
+    uint32_t s = incl[k] - 1;
+    indices[s] = (int32_t)(key[k] & 0xffffffffu);
+    slot_row[s] = (int32_t)(key[k] >> 32);
+    seg_start[s] = (uint32_t)k;
+}
+
+// indptr[r] = first position in sorted `vals` (length n) with vals[pos] >= r, for r = 0..rows
+__global__ void k_lower_bounds(int64_t rows, int64_t n, const int32_t *__restrict__ vals, int32_t *__restrict__ indptr) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (vals[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    indptr[r] = (int32_t)lo;
+}
+__global__ void k_lower_bounds_u32(int64_t rows, int64_t n, const uint32_t *__restrict__ vals, uint32_t *__restrict__ out) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)vals[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    out[r] = (uint32_t)lo;
+}
+
+template <typename T>
+static T read_back(const T *dev, cudaStream_t st) {
+    T h;
+    PN_CUDA(cudaMemcpyAsync(&h, dev, sizeof(T), cudaMemcpyDeviceToHost, st));
+    PN_CUDA(cudaStreamSynchronize(st));
+    return h;
+}
+
+static void exclusive_scan_u8(Ctx *c, const uint8_t *in, uint32_t *out, int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, c->stream);
+    c->cub_tmp.resize((int64_t)bytes);
+    PN_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.ptr, bytes, in, out, (int)n, c->stream));
+    c->count_launch(2);
+}
+static void inclusive_scan_u32(Ctx *c, const uint32_t *in, uint32_t *out, int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, c->stream);
+    c->cub_tmp.resize((int64_t)bytes);
+    PN_CUDA(cub::DeviceScan::InclusiveSum(c->cub_tmp.ptr, bytes, in, out, (int)n, c->stream));
+    c->count_launch(2);
+}
+static void exclusive_scan_i32(Ctx *c, const int32_t *in, int32_t *out, int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, c->stream);
+    c->cub_tmp.resize((int64_t)bytes);
+    PN_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.ptr, bytes, in, out, (int)n, c->stream));
+    c->count_launch(2);
+}
+
+static int bits_for(int64_t v) {
+    int b = 1;
+    while ((1ll << b) <= v && b < 62) ++b;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// partition (Analysis._partition_D :1412-1505, _partition :1508-1540)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_known_flags(int64_t n_dof, const uint8_t *__restrict__ support, const uint8_t *__restrict__ enf,
+                              uint8_t *__restrict__ known) {
+    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= n_dof) return;
+    int64_t nd = d / 6; int k = (int)(d % 6);
+    known[d] = (((support[nd] | enf[nd]) >> k) & 1u);
+}
+__global__ void k_partition_lists(int64_t n_dof, const uint8_t *__restrict__ known, const uint32_t *__restrict__ kpos,
+                                  const uint8_t *__restrict__ enf, const double *__restrict__ enf_val,
+                                  int32_t *__restrict__ d1, int32_t *__restrict__ d2, double *__restrict__ d2_val,
+                                  int32_t *__restrict__ newidx) {
+    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= n_dof) return;
+    uint32_t kp = kpos[d];
+    if (known[d]) {
+        d2[kp] = (int32_t)d;
+        int64_t nd = d / 6; int k = (int)(d % 6);
+        d2_val[kp] = ((enf[nd] >> k) & 1u) ? enf_val[d] : 0.0;
+        newidx[d] = -1 - (int32_t)kp;
+    } else {
+        int32_t fp = (int32_t)(d - kp);
+        d1[fp] = (int32_t)d;
+        newidx[d] = fp;
+    }
+}
+// want_known: 0 -> keep columns in D1, 1 -> keep columns in D2
+__global__ void k_block_count(int64_t rows, const int32_t *__restrict__ rowlist, const int32_t *__restrict__ indptr,
+                              const int32_t *__restrict__ indices, const int32_t *__restrict__ newidx, int want_known,
+                              int32_t *__restrict__ cnt) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int32_t r = rowlist[i], n = 0;
+    for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) n += ((newidx[indices[k]] < 0) == (want_known != 0));
+    cnt[i] = n;
+}
+__global__ void k_block_fill(int64_t rows, const int32_t *__restrict__ rowlist, const int32_t *__restrict__ indptr,
+                             const int32_t *__restrict__ indices, const int32_t *__restrict__ newidx, int want_known,
+                             const int32_t *__restrict__ bptr, int32_t *__restrict__ bind, uint32_t *__restrict__ bsrc) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int32_t r = rowlist[i], o = bptr[i];
+    for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) {
+        int32_t ni = newidx[indices[k]];
+        if ((ni < 0) == (want_known != 0)) {
+            bind[o] = ni < 0 ? -1 - ni : ni;
+            bsrc[o] = (uint32_t)k;
+            ++o;
+        }
+    }
+}
+__global__ void k_gather_u32(int64_t n, const uint32_t *__restrict__ src, const double *__restrict__ in, double *__restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[src[i]];
+}
+
+static void build_partition(Ctx *c) {
+    cudaStream_t st = c->stream;
+    int64_t n = c->n_dof;
+    DevBuf<uint8_t> known;
+    DevBuf<uint32_t> kpos;
+    known.resize(n); kpos.resize(n);
+    k_known_flags<<<grid_for(n, 256), 256, 0, st>>>(n, c->model.support.ptr, c->model.enf_mask.ptr, known.ptr);
+    c->count_launch();
+    exclusive_scan_u8(c, known.ptr, kpos.ptr, n);
+    int64_t n2 = 0;
+    if (n > 0) n2 = (int64_t)read_back(kpos.ptr + n - 1, st) + read_back(known.ptr + n - 1, st);
+    c->n2 = n2; c->n1 = n - n2;
+    c->d1.resize(c->n1); c->d2.resize(c->n2); c->d2_val.resize(c->n2); c->newidx.resize(n);
+    k_partition_lists<<<grid_for(n, 256), 256, 0, st>>>(n, known.ptr, kpos.ptr, c->model.enf_mask.ptr,
+                                                         c->model.enf_val.ptr, c->d1.ptr, c->d2.ptr, c->d2_val.ptr,
+                                                         c->newidx.ptr);
+    c->count_launch();
+    for (int b = 0; b < 4; ++b) {
+        CsrBlock &B = c->blk[b];
+        const DevBuf<int32_t> &rows = (b < 2) ? c->d1 : c->d2;
+        int want_known = b & 1;
+        B.rows = rows.n; B.cols = want_known ? c->n2 : c->n1;
+        DevBuf<int32_t> cnt;
+        cnt.resize(B.rows + 1);
+        cnt.zero(st);
+        B.indptr.resize(B.rows + 1);
+        if (B.rows) {
+            k_block_count<<<grid_for(B.rows, 128), 128, 0, st>>>(B.rows, rows.ptr, c->indptr.ptr, c->indices.ptr,
+                                                                  c->newidx.ptr, want_known, cnt.ptr);
+            c->count_launch();
+        }
+        exclusive_scan_i32(c, cnt.ptr, B.indptr.ptr, B.rows + 1);
+        B.nnz = read_back(B.indptr.ptr + B.rows, st);
+        B.indices.resize(B.nnz); B.src.resize(B.nnz); B.vals.resize(B.nnz);
+        if (B.rows && B.nnz) {
+            k_block_fill<<<grid_for(B.rows, 128), 128, 0, st>>>(B.rows, rows.ptr, c->indptr.ptr, c->indices.ptr,
+                                                                 c->newidx.ptr, want_known, B.indptr.ptr, B.indices.ptr,
+                                                                 B.src.ptr);
+            c->count_launch();
+        }
+    }
+    PN_CUDA(cudaStreamSynchronize(st));
+}
+
+void gather_block_values(Ctx *c, const double *vals_dev) {
+    for (int b = 0; b < 4; ++b) {
+        CsrBlock &B = c->blk[b];
+        if (B.nnz) {
+            k_gather_u32<<<grid_for(B.nnz, 256), 256, 0, c->stream>>>(B.nnz, B.src.ptr, vals_dev, B.vals.ptr);
+            c->count_launch();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// symbolic phase
+// ------------------------------------------------------------------------------------------------
+void build_symbolic(Ctx *c, uint32_t flags) {
+    cudaStream_t st = c->stream;
+    c->sym_flags = flags;
+    c->n_dof = 6 * c->model.n_nodes;
+    EvLayout L = make_layout(c);
+    int64_t N = c->ev_count;
+    if (N >= (int64_t)0xffffffffu) throw ArgError("model too large for 32-bit element-value positions");
+
+    DevBuf<uint8_t> flag;
+    DevBuf<uint32_t> pos;
+    flag.resize(N); pos.resize(N);
+    int64_t nnz_coo = 0;
+    if (N) {
+        k_entry_flags<<<grid_for(N, 256), 256, 0, st>>>(L, c->ev.ptr, (flags & PN_SYM_DENSE_MEMBER_BLOCKS) ? 1 : 0, flag.ptr);
+        c->count_launch();
+        exclusive_scan_u8(c, flag.ptr, pos.ptr, N);
+        nnz_coo = (int64_t)read_back(pos.ptr + N - 1, st) + read_back(flag.ptr + N - 1, st);
+    }
+    c->nnz_coo = nnz_coo;
+
+    DevBuf<uint64_t> key_in;
+    key_in.resize(nnz_coo);
+    c->coo_emit.resize(nnz_coo);
+    c->coo_key.resize(nnz_coo);
+    c->coo_src.resize(nnz_coo);
+    if (nnz_coo) {
+        k_emit_coo<<<grid_for(N, 256), 256, 0, st>>>(L, flag.ptr, pos.ptr, key_in.ptr, c->coo_emit.ptr);
+        c->count_launch();
+        // stable LSD radix sort: equal keys keep emission order, which fixes the summation order
+        int end_bit = 32 + bits_for(c->n_dof);
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in.ptr, c->coo_key.ptr, c->coo_emit.ptr, c->coo_src.ptr,
+                                        (int)nnz_coo, 0, end_bit, st);
+        c->cub_tmp.resize((int64_t)bytes);
+        PN_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.ptr, bytes, key_in.ptr, c->coo_key.ptr, c->coo_emit.ptr,
+                                                c->coo_src.ptr, (int)nnz_coo, 0, end_bit, st));
+        c->count_launch(8);
+    }
+    flag.release(); pos.release(); key_in.release();
+
+    DevBuf<uint32_t> head, incl;
+    DevBuf<int32_t> slot_row;
+    head.resize(nnz_coo); incl.resize(nnz_coo);
+    int64_t nnz_csr = 0;
+    if (nnz_coo) {
+        k_heads<<<grid_for(nnz_coo, 256), 256, 0, st>>>(nnz_coo, c->coo_key.ptr, head.ptr);
+        c->count_launch();
+        inclusive_scan_u32(c, head.ptr, incl.ptr, nnz_coo);
+        nnz_csr = read_back(incl.ptr + nnz_coo - 1, st);
+    }
+    c->nnz_csr = nnz_csr;
+    c->indices.resize(nnz_csr); c->seg_start.resize(nnz_csr + 1); c->vals.resize(nnz_csr);
+    slot_row.resize(nnz_csr);
+    c->indptr.resize(c->n_dof + 1);
+    if (nnz_coo) {
+        k_fill_pattern<<<grid_for(nnz_coo, 256), 256, 0, st>>>(nnz_coo, c->coo_key.ptr, head.ptr, incl.ptr,
+                                                               c->indices.ptr, slot_row.ptr, c->seg_start.ptr);
+        c->count_launch();
+    }
+    uint32_t last = (uint32_t)nnz_coo;
+    PN_CUDA(cudaMemcpyAsync(c->seg_start.ptr + nnz_csr, &last, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    k_lower_bounds<<<grid_for(c->n_dof + 1, 256), 256, 0, st>>>(c->n_dof, nnz_csr, slot_row.ptr, c->indptr.ptr);
+    c->count_launch();
+    PN_CUDA(cudaStreamSynchronize(st));
+
+    build_partition(c);
+    c->symbolic_ready = true;
+    c->vals_ready = false;
+    c->incidence_ready = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// numeric COO -> CSR: each stored entry is the sum of its COO duplicates taken in emission order
+// (fixed at symbolic time by the stable sort), so the result is bit-reproducible run to run.
+// A warp walks 32 consecutive CSR slots per step so the 8-byte stores are fully coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_scatter_add(int64_t nnz_csr, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ src,
+                              const double *__restrict__ ev, double *__restrict__ vals) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nnz_csr) return;
+    uint32_t a = seg_start[s], b = seg_start[s + 1];
+    double acc = ev[src[a]];
+    for (uint32_t k = a + 1; k < b; ++k) acc += ev[src[k]];
+    vals[s] = acc;
+}
+
+void scatter_add_values(Ctx *c, const double *ev_dev, double *vals_dev) {
+    if (!c->nnz_csr) return;
+    k_scatter_add<<<grid_for(c->nnz_csr, 256), 256, 0, c->stream>>>(c->nnz_csr, c->seg_start.ptr, c->coo_src.ptr, ev_dev,
+                                                                     vals_dev);
+    c->count_launch();
+}
+
+// Analysis._check_stability :111-168: a zero (or absent) diagonal on an unsupported DOF.
+__global__ void k_zero_diag(int64_t n_dof, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                            const double *__restrict__ vals, const uint8_t *__restrict__ support,
+                            int32_t *__restrict__ bad, int cap, int *__restrict__ n_bad) {
+    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= n_dof) return;
+    if ((support[d / 6] >> (d % 6)) & 1u) return;
+    double diag = 0.0;
+    for (int32_t k = indptr[d]; k < indptr[d + 1]; ++k)
+        if (indices[k] == (int32_t)d) diag = vals[k];
+    if (diag == 0.0) {       // math.isclose(x, 0) with abs_tol = 0 is an exact-zero test
+        int slot = atomicAdd(n_bad, 1);
+        if (slot < cap) bad[slot] = (int32_t)d;
+    }
+}
+
+int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap) {
+    DevBuf<int32_t> bad;
+    DevBuf<int> nb;
+    bad.resize(cap); nb.resize(1);
+    nb.zero(c->stream);
+    k_zero_diag<<<grid_for(c->n_dof, 256), 256, 0, c->stream>>>(c->n_dof, c->indptr.ptr, c->indices.ptr, c->vals.ptr,
+                                                                 c->model.support.ptr, bad.ptr, (int)cap, nb.ptr);
+    c->count_launch();
+    int n = read_back(nb.ptr, c->stream);
+    int64_t m = n < cap ? n : cap;
+    if (m) {
+        PN_CUDA(cudaMemcpy(bad_host, bad.ptr, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        // the reference reports in DOF order
+        std::vector<int32_t> tmp(bad_host, bad_host + m);
+        std::sort(tmp.begin(), tmp.end());
+        for (int64_t i = 0; i < m; ++i) bad_host[i] = tmp[i];
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DOF incidence of element end-force entries (used to gather FER vectors and reactions without
+// atomics: entries of one DOF are summed in element emission order)
+// ------------------------------------------------------------------------------------------------
+struct EfLayout {
+    int64_t off_spring, off_member, off_quad, off_plate, count;
+    const int32_t *spring_ij, *mem_ij, *quad_ijmn, *plate_ijmn;
+};
+__device__ __forceinline__ int32_t ef_dof(const EfLayout &L, int64_t q) {
+    const int32_t *conn; int nd, nn; int64_t r;
+    if (q < L.off_member) { r = q - L.off_spring; conn = L.spring_ij; nd = 12; nn = 2; }
+    else if (q < L.off_quad) { r = q - L.off_member; conn = L.mem_ij; nd = 12; nn = 2; }
+    else if (q < L.off_plate) { r = q - L.off_quad; conn = L.quad_ijmn; nd = 24; nn = 4; }
+    else { r = q - L.off_plate; conn = L.plate_ijmn; nd = 24; nn = 4; }
+    int64_t e = r / nd; int k = (int)(r - e * nd);
+    return conn[nn * e + k / 6] * 6 + k % 6;
+}
+__global__ void k_ef_keys(EfLayout L, uint32_t *__restrict__ key, uint32_t *__restrict__ val) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= L.count) return;
+    key[q] = (uint32_t)ef_dof(L, q);
+    val[q] = (uint32_t)q;
+}
+
+void build_incidence(Ctx *c) {
+    if (c->incidence_ready) return;
+    cudaStream_t st = c->stream;
+    const Model &m = c->model;
+    c->ef_off_spring = 0;
+    c->ef_off_member = 12 * m.n_springs;
+    c->ef_off_quad = c->ef_off_member + 12 * m.n_members;
+    c->ef_off_plate = c->ef_off_quad + 24 * m.n_quads;
+    c->ef_count = c->ef_off_plate + 24 * m.n_plates;
+    if (c->ef_count >= (int64_t)0xffffffffu) throw ArgError("model too large for 32-bit element-force positions");
+    EfLayout L{c->ef_off_spring, c->ef_off_member, c->ef_off_quad, c->ef_off_plate, c->ef_count,
+               m.spring_ij.ptr, m.mem_ij.ptr, m.quad_ijmn.ptr, m.plate_ijmn.ptr};
+    int64_t n = c->ef_count;
+    DevBuf<uint32_t> key_in, key_out, val_in;
+    key_in.resize(n); key_out.resize(n); val_in.resize(n);
+    c->inc_src.resize(n);
+    c->inc_start.resize(c->n_dof + 1);
+    if (n) {
+        k_ef_keys<<<grid_for(n, 256), 256, 0, st>>>(L, key_in.ptr, val_in.ptr);
+        c->count_launch();
+        size_t bytes = 0;
+        int end_bit = bits_for(c->n_dof);
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in.ptr, key_out.ptr, val_in.ptr, c->inc_src.ptr, (int)n, 0,
+                                        end_bit, st);
+        c->cub_tmp.resize((int64_t)bytes);
+        PN_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.ptr, bytes, key_in.ptr, key_out.ptr, val_in.ptr,
+                                                c->inc_src.ptr, (int)n, 0, end_bit, st));
+        c->count_launch(6);
+    }
+    k_lower_bounds_u32<<<grid_for(c->n_dof + 1, 256), 256, 0, st>>>(c->n_dof, n, key_out.ptr, c->inc_start.ptr);
+    c->count_launch();
+    PN_CUDA(cudaStreamSynchronize(st));
+    c->ef.resize(c->ef_count);
+    c->fer_combo.resize(c->ef_count);
+    c->incidence_ready = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// load vectors (FEModel3D.P :2184-2235, FEModel3D.FER :2136-2182), per load case with unit factor
+// ------------------------------------------------------------------------------------------------
+__global__ void k_scatter_triplets(int64_t n, const int32_t *__restrict__ idx, const int32_t *__restrict__ cs,
+                                   const double *__restrict__ val, int64_t stride, double *__restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[(int64_t)cs[i] * stride + idx[i]] = val[i];
+}
+__global__ void k_scatter_member_fer(int64_t n_groups, const int32_t *__restrict__ g_member, const int32_t *__restrict__ g_case,
+                                     const double *__restrict__ gfer, int64_t ef_count, int64_t ef_off_member,
+                                     double *__restrict__ fer_case) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_groups * 12) return;
+    int64_t g = t / 12; int k = (int)(t % 12);
+    fer_case[(int64_t)g_case[g] * ef_count + ef_off_member + (int64_t)g_member[g] * 12 + k] = gfer[t];
+}
+// G[case][dof] = P[case][dof] - sum over incident element entries of fer_case[case][.]
+__global__ void k_case_vectors(int64_t n_dof, int n_case, const uint32_t *__restrict__ inc_start,
+                               const uint32_t *__restrict__ inc_src, const double *__restrict__ Pcase,
+                               const double *__restrict__ fer_case, int64_t ef_count, double *__restrict__ G) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_dof * n_case) return;
+    int cs = (int)(t / n_dof);
+    int64_t d = t - (int64_t)cs * n_dof;
+    const double *f = fer_case + (int64_t)cs * ef_count;
+    double acc = 0.0;
+    for (uint32_t k = inc_start[d]; k < inc_start[d + 1]; ++k) acc += f[inc_src[k]];
+    G[t] = Pcase[t] - acc;
+}
+
+void build_load_vectors(Ctx *c) {
+    cudaStream_t st = c->stream;
+    Loads &ld = c->loads;
+    const Model &m = c->model;
+    build_incidence(c);
+    int64_t n_dof = c->n_dof;
+    int nc = ld.n_case;
+    ld.Pcase.resize((int64_t)nc * n_dof);
+    ld.Gcase.resize((int64_t)nc * n_dof);
+    ld.fer_case.resize((int64_t)nc * c->ef_count);
+    ld.Pcase.zero(st);
+    ld.fer_case.zero(st);
+    if (ld.nl_val.n) {
+        k_scatter_triplets<<<grid_for(ld.nl_val.n, 256), 256, 0, st>>>(ld.nl_val.n, ld.nl_dof.ptr, ld.nl_case.ptr,
+                                                                        ld.nl_val.ptr, n_dof, ld.Pcase.ptr);
+        c->count_launch();
+    }
+    if (ld.n_mgroups) {
+        launch_member_fer_groups(c, st);
+        k_scatter_member_fer<<<grid_for(ld.n_mgroups * 12, 256), 256, 0, st>>>(
+            ld.n_mgroups, ld.mg_member.ptr, ld.mg_case.ptr, ld.mg_fer_global.ptr, c->ef_count, c->ef_off_member,
+            ld.fer_case.ptr);
+        c->count_launch();
+    }
+    for (int shell = 0; shell < 2; ++shell) {
+        bool quad = shell == 0;
+        int64_t ne = quad ? m.n_quads : m.n_plates;
+        DevBuf<double> &val = quad ? ld.qp_val : ld.pp_val;
+        if (!ne || !val.n) continue;
+        DevBuf<double> press;
+        press.resize((int64_t)nc * ne);
+        press.zero(st);
+        k_scatter_triplets<<<grid_for(val.n, 256), 256, 0, st>>>(val.n, quad ? ld.qp_elem.ptr : ld.pp_elem.ptr,
+                                                                  quad ? ld.qp_case.ptr : ld.pp_case.ptr, val.ptr, ne,
+                                                                  press.ptr);
+        c->count_launch();
+        const std::vector<uint8_t> &has = quad ? ld.case_has_quad : ld.case_has_plate;
+        for (int cs = 0; cs < nc; ++cs)
+            if (has[cs])
+                launch_shell_fer(c, quad, press.ptr + (int64_t)cs * ne,
+                                 ld.fer_case.ptr + (int64_t)cs * c->ef_count + (quad ? c->ef_off_quad : c->ef_off_plate), st);
+        PN_CUDA(cudaStreamSynchronize(st));
+    }
+    if (nc && n_dof) {
+        k_case_vectors<<<grid_for(n_dof * nc, 256), 256, 0, st>>>(n_dof, nc, c->inc_start.ptr, c->inc_src.ptr,
+                                                                   ld.Pcase.ptr, ld.fer_case.ptr, c->ef_count, ld.Gcase.ptr);
+        c->count_launch();
+    }
+    ld.vectors_ready = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// right-hand sides: B[i][j] = sum_case f[j][case] G[case][d1[i]] - (K12 D2)[i]   (FEModel3D.py:2311)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_spmv_rows(int64_t rows, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double acc = 0.0;
+    for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) acc = fma(vals[k], x[indices[k]], acc);
+    y[r] = acc;
+}
+void spmv_plain(Ctx *c, const CsrBlock &A, const double *x, double *y, cudaStream_t st) {
+    if (!A.rows) return;
+    k_spmv_rows<<<grid_for(A.rows, 128), 128, 0, st>>>(A.rows, A.indptr.ptr, A.indices.ptr, A.vals.ptr, x, y);
+    c->count_launch();
+}
+
+__global__ void k_build_rhs(int64_t n1, int s, int n_case, const int32_t *__restrict__ d1, const double *__restrict__ G,
+                            int64_t n_dof, const double *__restrict__ fac, const double *__restrict__ kd2,
+                            double *__restrict__ B) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n1 * s) return;
+    int64_t i = t / s; int j = (int)(t - i * s);
+    int64_t d = d1[i];
+    double acc = 0.0;
+    for (int cs = 0; cs < n_case; ++cs) acc = fma(fac[(int64_t)j * n_case + cs], G[(int64_t)cs * n_dof + d], acc);
+    B[t] = acc - kd2[i];
+}
+
+void build_rhs(Ctx *c) {
+    cudaStream_t st = c->stream;
+    Loads &ld = c->loads;
+    int s = ld.n_combo;
+    c->B.resize(c->n1 * s);
+    c->X.resize(c->n1 * s);
+    c->kd2.resize(c->n1);
+    c->kd2.zero(st);
+    if (c->n1 == 0) return;
+    if (c->n2) spmv_plain(c, c->blk[1], c->d2_val.ptr, c->kd2.ptr, st);
+    k_build_rhs<<<grid_for(c->n1 * s, 256), 256, 0, st>>>(c->n1, s, ld.n_case, c->d1.ptr, ld.Gcase.ptr, c->n_dof,
+                                                            ld.factors.ptr, c->kd2.ptr, c->B.ptr);
+    c->count_launch();
+}
+
+// Analysis._store_displacements / _unpartition :810-880: D = merge(D1, D2)
+__global__ void k_merge(int64_t n_dof, int s, const int32_t *__restrict__ newidx, const double *__restrict__ X,
+                        const double *__restrict__ d2_val, double *__restrict__ D) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_dof * s) return;
+    int j = (int)(t / n_dof);
+    int64_t d = t - (int64_t)j * n_dof;
+    int32_t ni = newidx[d];
+    D[t] = ni >= 0 ? X[(int64_t)ni * s + j] : d2_val[-1 - ni];
+}
+void merge_displacements(Ctx *c) {
+    int s = c->loads.n_combo;
+    c->D_all.resize((int64_t)s * c->n_dof);
+    if (!c->n_dof || !s) return;
+    k_merge<<<grid_for(c->n_dof * s, 256), 256, 0, c->stream>>>(c->n_dof, s, c->newidx.ptr, c->X.ptr, c->d2_val.ptr,
+                                                                 c->D_all.ptr);
+    c->count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// reactions (Analysis._calc_reactions :1059-1313)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_combine_fer(int64_t n, int n_case, const double *__restrict__ fac_row, const double *__restrict__ fer_case,
+                              double *__restrict__ out) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    double acc = 0.0;
+    for (int cs = 0; cs < n_case; ++cs) acc = fma(fac_row[cs], fer_case[(int64_t)cs * n + q], acc);
+    out[q] = acc;
+}
+void combine_fer(Ctx *c, int32_t combo) {
+    Loads &ld = c->loads;
+    if (!c->ef_count) return;
+    k_combine_fer<<<grid_for(c->ef_count, 256), 256, 0, c->stream>>>(
+        c->ef_count, ld.n_case, ld.factors.ptr + (int64_t)combo * ld.n_case, ld.fer_case.ptr, c->fer_combo.ptr);
+    c->count_launch();
+}
+
+__global__ void k_reactions(int64_t n_dof, int n_case, const uint8_t *__restrict__ support,
+                            const uint32_t *__restrict__ inc_start, const uint32_t *__restrict__ inc_src,
+                            const double *__restrict__ ef, const double *__restrict__ fac_row,
+                            const double *__restrict__ Pcase, const uint8_t *__restrict__ nsp_flag,
+                            const double *__restrict__ nsp_k, const double *__restrict__ D, double *__restrict__ R) {
+    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= n_dof) return;
+    uint8_t sup = support[d / 6];
+    double r = 0.0;
+    if ((sup >> (d % 6)) & 1u) {
+        for (uint32_t k = inc_start[d]; k < inc_start[d + 1]; ++k) r += ef[inc_src[k]];
+        double pl = 0.0;
+        for (int cs = 0; cs < n_case; ++cs) pl = fma(fac_row[cs], Pcase[(int64_t)cs * n_dof + d], pl);
+        r -= pl;
+    }
+    uint8_t f = nsp_flag[d];
+    if ((f & 1u) && (f & 2u)) r -= nsp_k[d] * D[d];
+    R[d] = r;
+}
+
+void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev) {
+    cudaStream_t st = c->stream;
+    Loads &ld = c->loads;
+    const Model &m = c->model;
+    const double *D = c->D_all.ptr + (int64_t)combo * c->n_dof;
+    combine_fer(c, combo);
+    launch_element_forces(c, PN_SPRING, D, nullptr, c->ef.ptr + c->ef_off_spring, st);
+    launch_element_forces(c, PN_MEMBER, D, c->fer_combo.ptr + c->ef_off_member, c->ef.ptr + c->ef_off_member, st);
+    if (pdelta) launch_member_pdelta_forces(c, D, c->ef.ptr + c->ef_off_member, st);
+    launch_element_forces(c, PN_QUAD, D, c->fer_combo.ptr + c->ef_off_quad, c->ef.ptr + c->ef_off_quad, st);
+    launch_element_forces(c, PN_PLATE, D, c->fer_combo.ptr + c->ef_off_plate, c->ef.ptr + c->ef_off_plate, st);
+    if (c->n_dof) {
+        k_reactions<<<grid_for(c->n_dof, 256), 256, 0, st>>>(c->n_dof, ld.n_case, m.support.ptr, c->inc_start.ptr,
+                                                              c->inc_src.ptr, c->ef.ptr,
+                                                              ld.factors.ptr + (int64_t)combo * ld.n_case, ld.Pcase.ptr,
+                                                              m.nspring_flag.ptr, m.nspring_k.ptr, D, rxn_dev);
+        c->count_launch();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpMM: Y[rows][s] = A X, X and Y row-major with s columns.  G lanes cooperate on one row, each lane
+// owning CPL columns spaced G apart, so every X access is a contiguous G*8-byte segment.
+// ------------------------------------------------------------------------------------------------
+template <int G, int CPL>
+__global__ void __launch_bounds__(256)
+k_spmm(int64_t rows, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+       const double *__restrict__ vals, const double *__restrict__ X, double *__restrict__ Y, int s) {
+    int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t r = gid / G;
+    int lane = (int)(gid % G);
+    if (r >= rows) return;
+    double acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+    int32_t k0 = indptr[r], k1 = indptr[r + 1];
+    for (int32_t k = k0; k < k1; ++k) {
+        double v = vals[k];
+        const double *x = X + (int64_t)indices[k] * s + lane;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+            if (lane + c * G < s) acc[c] = fma(v, x[c * G], acc[c]);
+    }
+    double *y = Y + r * s + lane;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+        if (lane + c * G < s) y[c * G] = acc[c];
+}
+
+template <int G>
+static void spmm_dispatch_cpl(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s,
+                              cudaStream_t st) {
+    int cpl = (s + G - 1) / G;
+    unsigned grid = grid_for(A.rows * G, 256);
+#define PN_SPMM(CPL_) k_spmm<G, CPL_><<<grid, 256, 0, st>>>(A.rows, A.indptr.ptr, A.indices.ptr, vals, X, Y, s)
+    if (cpl <= 1) PN_SPMM(1);
+    else if (cpl <= 2) PN_SPMM(2);
+    else if (cpl <= 4) PN_SPMM(4);
+    else if (cpl <= 8) PN_SPMM(8);
+    else throw ArgError("spmm: more than 256 right-hand sides per call");
+#undef PN_SPMM
+    c->count_launch();
+}
+
+void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st) {
+    if (!A.rows || !s) return;
+    if (s == 1) spmm_dispatch_cpl<1>(c, A, vals, X, Y, s, st);
+    else if (s == 2) spmm_dispatch_cpl<2>(c, A, vals, X, Y, s, st);
+    else if (s <= 4) spmm_dispatch_cpl<4>(c, A, vals, X, Y, s, st);
+    else if (s <= 8) spmm_dispatch_cpl<8>(c, A, vals, X, Y, s, st);
+    else if (s <= 16) spmm_dispatch_cpl<16>(c, A, vals, X, Y, s, st);
+    else spmm_dispatch_cpl<32>(c, A, vals, X, Y, s, st);
+}
+
+}  // namespace pn
