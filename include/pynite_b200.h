@@ -19,6 +19,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define PN_EXPORT __attribute__((visibility("default")))
+#else
+#define PN_EXPORT
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -81,10 +87,10 @@ typedef struct pn_stats {
 } pn_stats;
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
-int pn_create(pn_ctx **out, int device_id);
-void pn_destroy(pn_ctx *ctx);
-const char *pn_last_error(pn_ctx *ctx);
-const char *pn_version(void);
+PN_EXPORT int pn_create(pn_ctx **out, int device_id);
+PN_EXPORT void pn_destroy(pn_ctx *ctx);
+PN_EXPORT const char *pn_last_error(pn_ctx *ctx);
+PN_EXPORT const char *pn_version(void);
 
 /* ---- model upload: replaces the object reads inside FEModel3D.Ke (FEModel3D.py:1587-1771) ------
  * nodes:   Node3D.py:28-85.  support_mask bit k = DOF k supported; enforced_mask likewise;
@@ -92,37 +98,37 @@ const char *pn_version(void);
  * springs: Spring3D.py:25-43.  members: Member3D.py:37-105 (sub-members after descritize,
  *          PhysMember.py:37-200); props = E, G, A, Iy, Iz, J; releases bit k = local DOF k released.
  * quads / plates: Quad3D.py:30-57, Plate3D.py:16-72; props = t, E, nu, kx_mod, ky_mod.            */
-int pn_set_nodes(pn_ctx *ctx, int64_t n_nodes, const double *xyz, const uint8_t *support_mask,
+PN_EXPORT int pn_set_nodes(pn_ctx *ctx, int64_t n_nodes, const double *xyz, const uint8_t *support_mask,
                  const uint8_t *enforced_mask, const double *enforced_val, const double *spring_k,
                  const uint8_t *spring_flag);
-int pn_set_springs(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *ks, const uint8_t *active);
-int pn_set_members(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *props, const double *rotation_deg,
+PN_EXPORT int pn_set_springs(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *ks, const uint8_t *active);
+PN_EXPORT int pn_set_members(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *props, const double *rotation_deg,
                    const uint16_t *releases, const uint8_t *active);
-int pn_set_quads(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props);
-int pn_set_plates(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props);
+PN_EXPORT int pn_set_quads(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props);
+PN_EXPORT int pn_set_plates(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props);
 
 /* ---- per-element global matrices, for inspection and parity tests -----------------------------
  * Member3D.Ke :1038, Spring3D.Ke :191, Quad3D.Ke :858, Plate3D.Ke :502 -> out[count][nd*nd], nd = 12 or 24.
  * Member3D.Kg :1048 with axial force P[m] -> out[count][144].                                     */
-int pn_element_ke(pn_ctx *ctx, int kind, double *out);
-int pn_member_kg(pn_ctx *ctx, const double *P, double *out);
+PN_EXPORT int pn_element_ke(pn_ctx *ctx, int kind, double *out);
+PN_EXPORT int pn_member_kg(pn_ctx *ctx, const double *P, double *out);
 
 /* ---- symbolic phase: FEModel3D._build_dof_vector :66, _append_sparse_block :99 (zero filter),
  *      coo_matrix + tocsr pattern (:1791, :2279), Analysis._partition_D :1412, _partition :1508 -- */
-int pn_symbolic(pn_ctx *ctx, uint32_t flags);
-int pn_get_sizes(pn_ctx *ctx, pn_sizes *out);
-int pn_get_coo(pn_ctx *ctx, int32_t *row, int32_t *col, double *data); /* emission order           */
-int pn_get_pattern(pn_ctx *ctx, int32_t *indptr, int32_t *indices);    /* CSR of Ke, sorted        */
-int pn_get_partition(pn_ctx *ctx, int32_t *d1, int32_t *d2, double *d2_values);
+PN_EXPORT int pn_symbolic(pn_ctx *ctx, uint32_t flags);
+PN_EXPORT int pn_get_sizes(pn_ctx *ctx, pn_sizes *out);
+PN_EXPORT int pn_get_coo(pn_ctx *ctx, int32_t *row, int32_t *col, double *data); /* emission order           */
+PN_EXPORT int pn_get_pattern(pn_ctx *ctx, int32_t *indptr, int32_t *indices);    /* CSR of Ke, sorted        */
+PN_EXPORT int pn_get_partition(pn_ctx *ctx, int32_t *d1, int32_t *d2, double *d2_values);
 /* block: 0 = K11, 1 = K12, 2 = K21, 3 = K22; any output pointer may be NULL */
-int pn_get_block(pn_ctx *ctx, int block, int32_t *indptr, int32_t *indices, double *data);
+PN_EXPORT int pn_get_block(pn_ctx *ctx, int block, int32_t *indptr, int32_t *indices, double *data);
 
 /* ---- numeric assembly: duplicate summation of .tocsr() (FEModel3D.py:2279) -------------------- */
-int pn_assemble_ke(pn_ctx *ctx);
-int pn_get_csr_values(pn_ctx *ctx, double *data);
+PN_EXPORT int pn_assemble_ke(pn_ctx *ctx);
+PN_EXPORT int pn_get_csr_values(pn_ctx *ctx, double *data);
 /* Analysis._check_stability :111-168; on PN_ERR_UNSTABLE_NODE the first *n_bad (<= cap) DOFs are
  * written to bad_dofs                                                                             */
-int pn_check_nodal_stability(pn_ctx *ctx, int32_t *bad_dofs, int64_t cap, int64_t *n_bad);
+PN_EXPORT int pn_check_nodal_stability(pn_ctx *ctx, int32_t *bad_dofs, int64_t cap, int64_t *n_bad);
 
 /* ---- loads: FEModel3D.P :2184, FEModel3D.FER :2136, Member3D.fer :742, Quad3D.fer :721,
  *      Plate3D.fer :324, FixedEndReactions.py ----------------------------------------------------
@@ -131,38 +137,45 @@ int pn_check_nodal_stability(pn_ctx *ctx, int32_t *bad_dofs, int64_t cap, int64_
  *   (global), params = (P, x, -, -); 12..14 = distributed Fx Fy Fz, 15..17 = FX FY FZ,
  *   params = (w1, w2, x1, x2).  Entries must be grouped by member (ascending member index).
  * pressures: (element, case, value) triplets.                                                     */
-int pn_set_loads(pn_ctx *ctx, int32_t n_case,
+PN_EXPORT int pn_set_loads(pn_ctx *ctx, int32_t n_case,
                  int64_t n_nodal, const int32_t *nl_dof, const int32_t *nl_case, const double *nl_val,
                  int64_t n_mload, const int32_t *ml_member, const int32_t *ml_case, const int32_t *ml_kind,
                  const double *ml_params,
                  int64_t n_qp, const int32_t *qp_elem, const int32_t *qp_case, const double *qp_val,
                  int64_t n_pp, const int32_t *pp_elem, const int32_t *pp_case, const double *pp_val);
 /* LoadCombo.py:8-21: factors[n_combo][n_case] */
-int pn_set_combos(pn_ctx *ctx, int32_t n_combo, const double *factors);
+PN_EXPORT int pn_set_combos(pn_ctx *ctx, int32_t n_combo, const double *factors);
 /* which: 0 = P, 1 = FER; out[6N] for one combo */
-int pn_get_load_vector(pn_ctx *ctx, int32_t combo, int32_t which, double *out);
+PN_EXPORT int pn_get_load_vector(pn_ctx *ctx, int32_t combo, int32_t which, double *out);
 
 /* ---- solve: FEModel3D.analyze_linear :2287-2320 (all combos), Analysis._solve_unknown_disp :176,
  *      _store_displacements :847, _calc_reactions :1059 ------------------------------------------
  * D_out[n_combo][6N], Rxn_out[n_combo][6N] (either may be NULL).                                  */
-int pn_solve_linear(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats);
+PN_EXPORT int pn_solve_linear(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats);
 /* Analysis._PDelta :329-471 + FEModel3D.Kg :1802: solve, P = EA/L (d6 - d0), Kg, K = Ke + Kg, re-solve */
-int pn_solve_pdelta(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats);
+PN_EXPORT int pn_solve_pdelta(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats);
 /* global geometric stiffness for one solved combo as COO, 144 entries per active member, unfiltered
  * (FEModel3D.py:1826-1892); first_step != 0 uses P = 0.  row/col/data sized 144 * active members  */
-int pn_get_kg_coo(pn_ctx *ctx, int32_t combo, int32_t first_step, int32_t *row, int32_t *col, double *data,
+PN_EXPORT int pn_get_kg_coo(pn_ctx *ctx, int32_t combo, int32_t first_step, int32_t *row, int32_t *col, double *data,
                   int64_t *n_out);
+
+/* Analysis._sum_displacements :882-914 (load stepping in _first_order :262-305): overwrites the stored
+ * displacement vector of a solved combo, so that element forces and reactions refer to the summed state */
+PN_EXPORT int pn_set_displacements(pn_ctx *ctx, int32_t combo, const double *D);
+/* Analysis._calc_reactions :1059-1313 for one solved combo with the current element activity; out[6N] */
+PN_EXPORT int pn_reactions(pn_ctx *ctx, int32_t combo, int32_t pdelta, double *out);
 
 /* ---- element end forces of a solved combo: Member3D.f :872 / F :1072, Spring3D.f :86 / F :200,
  *      Quad3D.f :713 / F :798, Plate3D.f :316 / F :403.  out[count][nd]; local != 0 -> local axes;
  *      pdelta != 0 uses the (ke + kg(P)) branch of Member3D.f :886-891                             */
-int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32_t pdelta, double *out);
+PN_EXPORT int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32_t pdelta, double *out);
 
 /* ---- building blocks exposed for measurement and tests ----------------------------------------
  * Y[n1][s] = K11 * X[n1][s] (row-major, s right-hand sides), repeated `repeat` times; returns the
  * average kernel time in ms through *ms_out (CUDA events on the launching stream).                */
-int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repeat, double *ms_out);
-int pn_get_stats(pn_ctx *ctx, pn_stats *out);
+PN_EXPORT int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repeat, double *ms_out);
+PN_EXPORT int pn_get_stats(pn_ctx *ctx, pn_stats *out);
+PN_EXPORT int pn_reset_stats(pn_ctx *ctx);
 
 #ifdef __cplusplus
 }

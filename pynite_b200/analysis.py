@@ -1,0 +1,555 @@
+"""Analysis drivers: what `Pynite/Analysis.py` and the three `FEModel3D.analyze*` methods do, with the
+numerical work handed to the B200 library.
+
+Host side (this file) keeps the cheap, order-defining bookkeeping of the reference:
+`_prepare_model` (`Analysis.py:20-79`), `_identify_combos` (:82-108), `_renumber` (:1543-1571), the
+tension/compression-only iteration and load stepping of `_first_order` (:244-326) / `_PDelta`
+(:329-471) / `_check_TC_convergence` (:917-1056), and the console messages of `_check_stability`
+(:111-168).  Everything numerical -- element stiffness, COO->CSR assembly, partition, load vectors,
+the multi-right-hand-side solve, displacements, reactions -- runs in `libpynite_b200.so`.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import scipy.sparse as sps
+
+from pynite_b200 import engine as _eng
+from pynite_b200.LoadCombo import LoadCombo
+from pynite_b200.flatten import NodeIndex, flatten_model
+
+_DIRECTION_TEXT = ('for translation in the global X direction.', 'for translation in the global Y direction.',
+                   'for translation in the global Z direction.', 'for rotation about the global X axis.',
+                   'for rotation about the global Y axis.', 'for rotation about the global Z axis.')
+_DOFS = ('DX', 'DY', 'DZ', 'RX', 'RY', 'RZ')
+
+# solver used by the drivers: 'direct' (multifrontal LU + iterative refinement) or 'pcg'
+DEFAULT_SOLVER = 'direct'
+
+
+class RunState:
+    """Bookkeeping of the last GPU analysis of a model."""
+
+    def __init__(self, arrays, combo_names):
+        self.arrays = arrays
+        self.combo_index = {name: i for i, name in enumerate(combo_names)}
+        self.engine_combo = dict(self.combo_index)   # combo name -> index inside the engine's combo set
+        self.pdelta = False
+        self.force_cache = {}
+
+
+# ---------------------------------------------------------------------------------------------
+# model preparation
+# ---------------------------------------------------------------------------------------------
+def renumber(model):
+    """`Analysis._renumber` (:1543-1571): IDs by dictionary order; members are discretised first."""
+    for i, node in enumerate(model.nodes.values()):
+        node.ID = i
+    for i, spring in enumerate(model.springs.values()):
+        spring.ID = i
+    index = NodeIndex(model) if model.members else None
+    k = 0
+    for phys_member in model.members.values():
+        phys_member.descritize(index)
+        for member in phys_member.sub_members.values():
+            member.ID = k
+            k += 1
+    for i, plate in enumerate(model.plates.values()):
+        plate.ID = i
+    for i, quad in enumerate(model.quads.values()):
+        quad.ID = i
+
+
+def prepare_model(model):
+    """`Analysis._prepare_model` (:20-79) minus mesh generators and modal combos (out of scope)."""
+    model._D = {}
+    model._Rxn = {}
+    if model.load_combos == {}:
+        model.load_combos['Combo 1'] = LoadCombo('Combo 1', factors={'Case 1': 1.0})
+    for name in [n for n, c in model.load_combos.items() if c.combo_tags is not None and 'modal' in c.combo_tags]:
+        model.load_combos.pop(name)
+    for mesh in getattr(model, 'meshes', {}).values():
+        if not mesh.is_generated or mesh.needs_update:
+            mesh.generate()
+    combos = list(model.load_combos.keys())
+    for spring in model.springs.values():
+        for name in combos:
+            spring.active[name] = True
+    for phys_member in model.members.values():
+        for name in combos:
+            phys_member.active[name] = True
+    renumber(model)
+
+
+def identify_combos(model, combo_tags=None):
+    """`Analysis._identify_combos` (:82-108)."""
+    if combo_tags is None:
+        return list(model.load_combos.values())
+    return [c for c in model.load_combos.values()
+            if c.combo_tags is not None and any(tag in c.combo_tags for tag in combo_tags)]
+
+
+def _engine(model):
+    if model._engine is None:
+        model._engine = _eng.Engine(getattr(model, 'device', 0))
+    return model._engine
+
+
+def _report_unstable(model, err):
+    """Console lines of `Analysis._check_stability` (:153-166), then the reference's exception."""
+    nodes = list(model.nodes.values())
+    for dof in err.dofs:
+        print('* Nodal instability detected: node ' + nodes[int(dof)//6].name + ' is unstable ' + _DIRECTION_TEXT[int(dof) % 6])
+    raise Exception('Unstable node(s). See console output for details.')
+
+
+def _has_tc_features(model):
+    """True when the tension/compression-only machinery of `_check_TC_convergence` can change anything."""
+    for node in model.nodes.values():
+        for d in _DOFS:
+            if getattr(node, 'spring_' + d)[1] is not None:
+                return True
+    if any(s.tension_only or s.comp_only for s in model.springs.values()):
+        return True
+    return any(m.tension_only or m.comp_only for m in model.members.values())
+
+
+def _upload(model, combo_list, active_combo=None):
+    A = flatten_model(model, combo_list, active_combo)
+    eng = _engine(model)
+    eng.set_model(A)
+    eng.set_loads(A)
+    eng.set_combos(A.factors)
+    return A, eng
+
+
+def _assemble(model, eng, check_stability, log, flags=0):
+    if log:
+        print('- Assembling the global stiffness matrix on the GPU')
+    eng.symbolic(flags)
+    eng.assemble_ke()
+    if check_stability:
+        if log:
+            print('- Checking nodal stability')
+        try:
+            eng.check_nodal_stability()
+        except _eng.UnstableNodes as err:
+            _report_unstable(model, err)
+
+
+def _opts(check_stability):
+    return _eng.Engine.make_opts(solver=DEFAULT_SOLVER, check_stability=check_stability)
+
+
+def _store(model, combo_list, D, R):
+    for i, combo in enumerate(combo_list):
+        model._D[combo.name] = D[i].reshape(-1, 1)
+        if R is not None:
+            model._Rxn[combo.name] = R[i].reshape(-1, 1)
+
+
+def _require_sparse(sparse):
+    if sparse is not True and sparse != True:   # noqa: E712
+        raise NotImplementedError('pynite_b200 runs the sparse path on the GPU only; sparse=False is not available')
+
+
+# ---------------------------------------------------------------------------------------------
+# drivers
+# ---------------------------------------------------------------------------------------------
+def run_linear(model, log, check_stability, check_statics, sparse, combo_tags):
+    """`FEModel3D.analyze_linear` (:2250-2332): one stiffness matrix, every combo as one multi-RHS solve."""
+    _require_sparse(sparse)
+    if log:
+        print('+-------------------+')
+        print('| Analyzing: Linear |')
+        print('+-------------------+')
+    t0 = time.perf_counter()
+    prepare_model(model)
+    combo_list = identify_combos(model, combo_tags)
+    first = list(model.load_combos.keys())[0]
+    A, eng = _upload(model, combo_list, first)
+    t1 = time.perf_counter()
+    eng.reset_stats()
+    model._run = RunState(A, [c.name for c in combo_list])
+    # the reference keeps the P-Delta end-force branch alive until `solution` is reset
+    model._run.pdelta = model.solution == 'P-Delta'
+    _assemble(model, eng, check_stability, log)
+    if combo_list:
+        if log:
+            print('- Solving ' + str(len(combo_list)) + ' load combination(s)')
+        try:
+            D, R, st = eng.solve_linear(_opts(check_stability), reactions=not model._run.pdelta)
+        except _eng.SingularMatrix:
+            raise Exception(_eng.SINGULAR_MSG)
+        if model._run.pdelta:
+            R = np.stack([eng.reactions(i, True).reshape(-1) for i in range(len(combo_list))])
+        _store(model, combo_list, D, R)
+        model.last_stats = eng.stats().as_dict()
+    t2 = time.perf_counter()
+    if model.last_stats is not None:
+        model.last_stats['host_prepare_s'] = t1 - t0
+        model.last_stats['device_total_s'] = t2 - t1
+    if log:
+        print('')
+        print('- Analysis complete')
+        print('')
+    if check_statics:
+        check_statics_table(model, combo_tags)
+    model.solution = 'Linear'
+
+
+def _tc_converged(model, combo_name, log, spring_tolerance, member_tolerance):
+    """`Analysis._check_TC_convergence` (:917-1056)."""
+    convergence = True
+    if log:
+        print('- Checking for tension/compression-only support spring convergence')
+    for node in model.nodes.values():
+        for d in _DOFS:
+            spring = getattr(node, 'spring_' + d)
+            if spring[1] is not None:
+                displacement = getattr(node, d)[combo_name]
+                should_be_active = ((spring[1] == '-' and displacement <= -spring_tolerance) or
+                                    (spring[1] == '+' and displacement >= spring_tolerance))
+                if spring[2] != should_be_active:
+                    spring[2] = should_be_active
+                    convergence = False
+    if log:
+        print('- Checking for tension/compression-only spring convergence')
+    for spring in model.springs.values():
+        if spring.active[combo_name] == True:   # noqa: E712
+            if spring.tension_only and spring.axial(combo_name) > spring_tolerance:
+                if log:
+                    print(f'- Deactivating spring {spring.name}')
+                spring.active[combo_name] = False
+                convergence = False
+            elif spring.comp_only and spring.axial(combo_name) < -spring_tolerance:
+                if log:
+                    print(f'- Deactivating spring {spring.name}')
+                spring.active[combo_name] = False
+                convergence = False
+    if log:
+        print('- Checking for tension/compression-only member convergence')
+    for phys_member in model.members.values():
+        if phys_member.active[combo_name] == True:   # noqa: E712
+            deactivate = False
+            if phys_member.tension_only and phys_member.max_axial(combo_name) > member_tolerance:
+                deactivate = True
+            elif phys_member.comp_only and phys_member.min_axial(combo_name) < -member_tolerance:
+                deactivate = True
+            if deactivate:
+                if log:
+                    print(f'- Deactivating member {phys_member.name}')
+                phys_member.active[combo_name] = False
+                for sub in phys_member.sub_members.values():
+                    sub.active[combo_name] = False
+                convergence = False
+        for sub in phys_member.sub_members.values():
+            sub._solved_combo = None
+    return convergence
+
+
+def _refresh_activity(model, eng, A, combo_name):
+    """Re-reads the flags `_check_TC_convergence` may have flipped and uploads them."""
+    nodes = list(model.nodes.values())
+    for k, d in enumerate(_DOFS):
+        for i, nd in enumerate(nodes):
+            sp = getattr(nd, 'spring_' + d)
+            if sp[0] is not None:
+                A.nspring_flag[i, k] = (A.nspring_flag[i, k] & ~np.uint8(2)) | (2 if sp[2] == True else 0)   # noqa: E712
+    A.spring_active[:] = [1 if s.active.get(combo_name, True) == True else 0 for s in model.springs.values()]   # noqa: E712
+    act = []
+    for pm in model.members.values():
+        on = 1 if pm.active.get(combo_name, True) == True else 0   # noqa: E712
+        act.extend([on]*len(pm.sub_members))
+    A.mem_active[:] = act
+    eng.set_nodes(A)
+    eng.set_springs(A)
+    eng.set_members(A)
+
+
+def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_tolerance, member_tolerance,
+                    num_steps, pdelta):
+    """Shared tension/compression-only iteration: `_first_order` (:244-326) and `_PDelta` (:329-471)."""
+    A, eng = _upload(model, combo_list, combo_list[0].name if combo_list else None)
+    model._run = RunState(A, [c.name for c in combo_list])
+    model._run.pdelta = pdelta
+    n = A.n_dof
+    flags = _eng.PN_SYM_DENSE_MEMBER_BLOCKS if pdelta else 0
+    for ci, combo in enumerate(combo_list):
+        if log:
+            print('')
+            print('- Analyzing load combination ' + combo.name)
+        eng.set_combos(A.factors[ci:ci + 1])
+        model._run.engine_combo = {combo.name: 0}
+        model._run.force_cache = {}
+        total = np.zeros((n, 1))
+        load_step = 1
+        while load_step <= num_steps:
+            iter_count = 1
+            converged = False
+            while not converged:
+                if iter_count > max_iter:
+                    if pdelta:
+                        raise Exception('- Model diverged during tension/compression-only analysis')
+                    raise Exception('Model diverged during tension/compression-only analysis')
+                if log:
+                    print(f'- Analyzing load step #{load_step}' if not pdelta else
+                          '- Beginning tension/compression-only iteration #' + str(iter_count))
+                _refresh_activity(model, eng, A, combo.name)
+                _assemble(model, eng, check_stability, log, flags)
+                try:
+                    if pdelta:
+                        D, _, _ = eng.solve_pdelta(_opts(check_stability), reactions=False)
+                    else:
+                        D, _, _ = eng.solve_linear(_opts(check_stability), reactions=False)
+                except _eng.SingularMatrix:
+                    if pdelta:
+                        raise ValueError(_eng.SINGULAR_MSG_PDELTA)
+                    raise Exception(_eng.SINGULAR_MSG)
+                delta = D[0].reshape(-1, 1)/num_steps
+                total = total + delta if load_step > 1 else delta
+                model._D[combo.name] = total
+                eng.set_displacements(0, total)
+                model._run.force_cache = {}
+                converged = _tc_converged(model, combo.name, log, spring_tolerance, member_tolerance)
+                if not converged:
+                    if log:
+                        print(f'- Undoing load step #{load_step} due to failed convergence.')
+                    total = total - delta
+                    model._D[combo.name] = total
+                else:
+                    load_step += 1
+                iter_count += 1
+        # reactions with this combo's final element activity (`_calc_reactions`, :1059-1313)
+        model._Rxn[combo.name] = eng.reactions(0, pdelta)
+        # element end forces must stay readable after the engine moves on to the next combo
+        model._run.saved = getattr(model._run, 'saved', {})
+        model._run.saved[combo.name] = {kind: eng.element_forces(kind, 0, local=False, pdelta=pdelta)
+                                        for kind in ('spring', 'member', 'quad', 'plate')}
+    model.last_stats = eng.stats().as_dict()
+
+
+def run_first_order(model, log, check_stability, check_statics, max_iter, sparse, combo_tags,
+                    spring_tolerance, member_tolerance, num_steps):
+    """`FEModel3D.analyze` (:2334-2411)."""
+    _require_sparse(sparse)
+    if log:
+        print('+-----------+')
+        print('| Analyzing |')
+        print('+-----------+')
+    prepare_model(model)
+    combo_list = identify_combos(model, combo_tags)
+    if not _has_tc_features(model):
+        # No element can change state, so every combo sees the same stiffness matrix and the iteration
+        # of `_first_order` ends after one pass: solve all combos together.
+        first = list(model.load_combos.keys())[0]
+        A, eng = _upload(model, combo_list, first)
+        eng.reset_stats()
+        model._run = RunState(A, [c.name for c in combo_list])
+        _assemble(model, eng, check_stability, log)
+        if combo_list:
+            try:
+                D, R, st = eng.solve_linear(_opts(check_stability), reactions=True)
+            except _eng.SingularMatrix:
+                raise Exception(_eng.SINGULAR_MSG)
+            _store(model, combo_list, D, R)
+            model.last_stats = eng.stats().as_dict()
+    else:
+        _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_tolerance, member_tolerance,
+                        num_steps, pdelta=False)
+    if log:
+        print('')
+        print('- Analysis complete')
+        print('')
+    if check_statics:
+        check_statics_table(model, combo_tags)
+    model.solution = 'Nonlinear TC'
+
+
+def run_pdelta(model, log, check_stability, max_iter, sparse, combo_tags):
+    """`FEModel3D.analyze_PDelta` (:2413-2467) -> `Analysis._PDelta` (:329-471)."""
+    _require_sparse(sparse)
+    if log:
+        print('+--------------------+')
+        print('| Analyzing: P-Delta |')
+        print('+--------------------+')
+    prepare_model(model)
+    combo_list = identify_combos(model, combo_tags)
+    if not _has_tc_features(model):
+        first = list(model.load_combos.keys())[0]
+        A, eng = _upload(model, combo_list, first)
+        eng.reset_stats()
+        model._run = RunState(A, [c.name for c in combo_list])
+        model._run.pdelta = True
+        _assemble(model, eng, check_stability, log, _eng.PN_SYM_DENSE_MEMBER_BLOCKS)
+        if combo_list:
+            try:
+                D, R, st = eng.solve_pdelta(_opts(check_stability), reactions=True)
+            except _eng.SingularMatrix:
+                raise ValueError(_eng.SINGULAR_MSG_PDELTA)
+            _store(model, combo_list, D, R)
+            model.last_stats = eng.stats().as_dict()
+    else:
+        _per_combo_loop(model, combo_list, log, check_stability, max_iter, 0, 0, 1, pdelta=True)
+    if log:
+        print('')
+        print('- Analysis complete')
+        print('')
+    model.solution = 'P-Delta'
+
+
+# ---------------------------------------------------------------------------------------------
+# inspection helpers behind FEModel3D.Ke / Kg / FER / P and the element objects
+# ---------------------------------------------------------------------------------------------
+def _fresh_engine_state(model, combo_name):
+    """Uploads the model for a stand-alone `Ke/Kg/FER/P` call when no analysis state matches."""
+    run = model._run
+    if run is not None and model.solution is not None and combo_name in run.engine_combo:
+        return run, _engine(model)
+    if any(n.ID is None for n in model.nodes.values()) or model._run is None:
+        prepare_model(model)
+    combo = model.load_combos[combo_name]
+    A, eng = _upload(model, [combo], combo_name)
+    model._run = RunState(A, [combo_name])
+    return model._run, eng
+
+
+def global_Ke(model, combo_name, log, check_stability, sparse):
+    _require_sparse(sparse)
+    run, eng = _fresh_engine_state(model, combo_name)
+    s = eng.symbolic(0)
+    row, col, data = eng.coo()
+    if check_stability:
+        eng.assemble_ke()
+        try:
+            eng.check_nodal_stability()
+        except _eng.UnstableNodes as err:
+            _report_unstable(model, err)
+    return sps.coo_matrix((data, (row, col)), shape=(s.n_dof, s.n_dof))
+
+
+def global_Kg(model, combo_name, log, sparse, first_step):
+    _require_sparse(sparse)
+    run = model._run
+    if first_step or run is None or combo_name not in run.engine_combo:
+        run, eng = _fresh_engine_state(model, combo_name)
+        first_step = True if model.solution is None else first_step
+    eng = _engine(model)
+    row, col, data = eng.kg_coo(run.engine_combo[combo_name], first_step)
+    n = run.arrays.n_dof
+    return sps.coo_matrix((data, (row, col)), shape=(n, n))
+
+
+def global_load_vector(model, combo_name, which):
+    run, eng = _fresh_engine_state(model, combo_name)
+    return eng.load_vector(run.engine_combo[combo_name], which)
+
+
+def element_force(model, kind, elem_id, combo_name, local):
+    """End forces of one element for a solved combo (`Member3D.f/F`, `Quad3D.f/F`, `Plate3D.f/F`, `Spring3D.f/F`)."""
+    run = model._run
+    if run is None or combo_name not in model._D:
+        raise KeyError(f"load combination '{combo_name}' has not been analysed")
+    key = (kind, combo_name, bool(local))
+    if key not in run.force_cache:
+        eng = _engine(model)
+        if combo_name in run.engine_combo:
+            run.force_cache[key] = eng.element_forces(kind, run.engine_combo[combo_name], local=local, pdelta=run.pdelta)
+        else:
+            F = getattr(run, 'saved', {})[combo_name][kind]
+            run.force_cache[key] = _rotate_saved(model, kind, F) if local else F
+    return run.force_cache[key][elem_id].reshape(-1, 1)
+
+
+def _rotate_saved(model, kind, F):
+    """Global -> local end forces for results saved from an earlier combo of a per-combo analysis."""
+    out = np.empty_like(F)
+    if kind in ('spring', 'member'):
+        elems = list(model.springs.values()) if kind == 'spring' else \
+            [s for pm in model.members.values() for s in pm.sub_members.values()]
+        for i, e in enumerate(elems):
+            R = member_dircos_host(e)
+            out[i] = (F[i].reshape(4, 3) @ R.T).reshape(-1)
+    else:
+        elems = list((model.quads if kind == 'quad' else model.plates).values())
+        for i, e in enumerate(elems):
+            R = shell_dircos_host(e)
+            out[i] = (F[i].reshape(8, 3) @ R.T).reshape(-1)
+    return out
+
+
+def member_dircos_host(sub):
+    """3x3 direction cosines of a member/spring (rows = local x, y, z), as `Member3D.T` (:933-1027) builds
+    them.  Host copy used only for result post-processing of single elements (axial-force extremes)."""
+    from math import isclose
+    ni, nj = sub.i_node, sub.j_node
+    Xi, Yi, Zi, Xj, Yj, Zj = ni.X, ni.Y, ni.Z, nj.X, nj.Y, nj.Z
+    L = ni.distance(nj)
+    x = np.array([(Xj - Xi)/L, (Yj - Yi)/L, (Zj - Zi)/L])
+    if isclose(Xi, Xj) and isclose(Zi, Zj):
+        y = np.array([-1.0, 0, 0]) if Yj > Yi else np.array([1.0, 0, 0])
+        z = np.array([0.0, 0, 1.0])
+    elif isclose(Yi, Yj):
+        y = np.array([0.0, 1.0, 0])
+        z = np.cross(x, y)
+        z = z/np.linalg.norm(z)
+    else:
+        proj = np.array([Xj - Xi, 0, Zj - Zi])
+        z = np.cross(proj, x) if Yj > Yi else np.cross(x, proj)
+        z = z/np.linalg.norm(z)
+        y = np.cross(z, x)
+        y = y/np.linalg.norm(y)
+    rot = getattr(sub, 'rotation', 0.0)
+    if rot != 0.0:
+        th = np.radians(rot)
+        c, s = np.cos(th), np.sin(th)
+        y2 = y*c + np.cross(x, y)*s + x*np.dot(x, y)*(1 - c)
+        z2 = z*c + np.cross(x, z)*s + x*np.dot(x, z)*(1 - c)
+        y, z = y2/np.linalg.norm(y2), z2/np.linalg.norm(z2)
+    return np.array([x, y, z])
+
+
+def shell_dircos_host(e):
+    """Shell triad as `Quad3D.T` (:884-950) / `Plate3D.T` (:451-500): x along i->j, z = x cross (i->n)."""
+    pi = np.array([e.i_node.X, e.i_node.Y, e.i_node.Z])
+    x = np.array([e.j_node.X, e.j_node.Y, e.j_node.Z]) - pi
+    xy = np.array([e.n_node.X, e.n_node.Y, e.n_node.Z]) - pi
+    x = x/np.linalg.norm(x)
+    z = np.cross(x, xy)
+    z = z/np.linalg.norm(z)
+    y = np.cross(z, x)
+    y = y/np.linalg.norm(y)
+    return np.array([x, y, z])
+
+
+def check_statics_table(model, combo_tags=None):
+    """Sum of applied loads vs sum of reactions per combo (`Analysis._check_statics`, :1316-1409),
+    printed as a plain table.  Uses the global P and FER vectors and the stored reactions."""
+    combo_list = identify_combos(model, combo_tags)
+    run = model._run
+    eng = _engine(model)
+    xyz = run.arrays.xyz
+    print('+----------------+')
+    print('| Statics Check: |')
+    print('+----------------+')
+    print('')
+    header = ['Load Combination', 'Sum FX', 'Sum RX', 'Sum FY', 'Sum RY', 'Sum FZ', 'Sum RZ',
+              'Sum MX', 'Sum RMX', 'Sum MY', 'Sum RMY', 'Sum MZ', 'Sum RMZ']
+    print(' | '.join(header))
+    for combo in combo_list:
+        if combo.name not in run.engine_combo:
+            continue
+        j = run.engine_combo[combo.name]
+        F = (eng.load_vector(j, 'P') - eng.load_vector(j, 'FER')).reshape(-1, 6)
+        R = model._Rxn[combo.name].reshape(-1, 6)
+
+        def totals(V):
+            f = V[:, :3].sum(axis=0)
+            m = V[:, 3:].sum(axis=0) + np.cross(xyz, V[:, :3]).sum(axis=0)
+            return f, m
+        (f, m), (rf, rm) = totals(F), totals(R)
+        row = [combo.name] + ['{:.3g}'.format(v) for v in
+                              (f[0], rf[0], f[1], rf[1], f[2], rf[2], m[0], rm[0], m[1], rm[1], m[2], rm[2])]
+        print(' | '.join(row))
+    print('')

@@ -214,7 +214,7 @@ PN_HD void pn_quad_pair(const PnGpNode *A, const PnGpNode *B, const PnShellMat &
 #endif
 #include "plate_tables.inc"
 
-PN_HD void pn_plate_pair_bending(int a, int b, double width, double height, const double *props, double *kb) {
+PN_D void pn_plate_pair_bending(int a, int b, double width, double height, const double *props, double *kb) {
     double t = props[0], E = props[1], nu = props[2];
     double hb = width / 2, hc = height / 2;
     double G = E / (2 * (1 + nu));

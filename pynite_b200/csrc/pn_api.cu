@@ -1,0 +1,820 @@
+// C ABI of the pynite_b200 library (include/pynite_b200.h): argument checking, host<->device copies,
+// phase sequencing.  All arithmetic happens in the kernels of pn_elements.cu / pn_sparse.cu /
+// pn_pcg.cu / pn_direct.cu; nothing here computes on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "pn_internal.h"
+
+using namespace pn;
+
+namespace {
+
+inline Ctx *C(pn_ctx *p) { return reinterpret_cast<Ctx *>(p); }
+
+#define PN_API_BEGIN(ctx)                                                                          \
+    if (!(ctx)) return PN_ERR_ARG;                                                                 \
+    Ctx *c = C(ctx);                                                                               \
+    try {                                                                                          \
+        PN_CUDA(cudaSetDevice(c->device));
+
+#define PN_API_END                                                                                 \
+    }                                                                                              \
+    catch (const StatusError &e) { c->err = e.what(); return e.code; }                             \
+    catch (const ArgError &e) { c->err = e.what(); return PN_ERR_ARG; }                            \
+    catch (const CudaError &e) { c->err = e.what(); cudaGetLastError(); return PN_ERR_CUDA; }      \
+    catch (const std::exception &e) { c->err = e.what(); return PN_ERR_ARG; }                      \
+    return PN_OK;
+
+inline unsigned grid_for(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+void invalidate(Ctx *c) {
+    c->ev_ready = false;
+    c->symbolic_ready = false;
+    c->vals_ready = false;
+    c->incidence_ready = false;
+    c->solved = c->solved_pdelta = false;
+    c->loads.vectors_ready = false;
+    direct_release(c);
+    pcg_release(c);
+}
+
+template <typename T>
+void download(const DevBuf<T> &b, T *host, cudaStream_t st) {
+    if (host && b.n) PN_CUDA(cudaMemcpyAsync(host, b.ptr, (size_t)b.n * sizeof(T), cudaMemcpyDeviceToHost, st));
+}
+
+// element-value buffer layout and the list of active node support springs (FEModel3D.py:1587-1690)
+void layout_ev(Ctx *c) {
+    Model &m = c->model;
+    std::vector<int32_t> dof;
+    std::vector<double> val;
+    for (int64_t nd = 0; nd < m.n_nodes; ++nd)
+        for (int k = 0; k < 6; ++k) {
+            uint8_t f = m.h_nspring_flag[6 * nd + k];
+            if ((f & 1u) && (f & 2u)) {
+                dof.push_back((int32_t)(6 * nd + k));
+                val.push_back(m.h_nspring_k[6 * nd + k]);
+            }
+        }
+    c->n_nsp = (int64_t)dof.size();
+    c->nsp_dof.upload(dof.data(), c->n_nsp, c->stream);
+    c->nsp_val.upload(val.data(), c->n_nsp, c->stream);
+    c->ev_off_spring = c->n_nsp;
+    c->ev_off_member = c->ev_off_spring + 144 * m.n_springs;
+    c->ev_off_quad = c->ev_off_member + 144 * m.n_members;
+    c->ev_off_plate = c->ev_off_quad + 576 * m.n_quads;
+    c->ev_count = c->ev_off_plate + 576 * m.n_plates;
+    c->ev.resize(c->ev_count);
+    PN_CUDA(cudaStreamSynchronize(c->stream));     // dof/val are stack-local
+}
+
+void compute_ev(Ctx *c) {
+    layout_ev(c);
+    PhaseTimer tm(c, &c->stats.ms_elements);
+    if (c->n_nsp)
+        PN_CUDA(cudaMemcpyAsync(c->ev.ptr, c->nsp_val.ptr, sizeof(double) * c->n_nsp, cudaMemcpyDeviceToDevice, c->stream));
+    launch_element_ke(c, c->stream);
+    c->ev_ready = true;
+}
+
+void ensure_ev(Ctx *c) { if (!c->ev_ready) compute_ev(c); }
+
+void ensure_symbolic(Ctx *c, uint32_t flags) {
+    ensure_ev(c);
+    if (c->symbolic_ready && c->sym_flags == flags) return;
+    direct_release(c);
+    pcg_release(c);
+    PhaseTimer tm(c, &c->stats.ms_symbolic);
+    build_symbolic(c, flags);
+    c->loads.vectors_ready = c->loads.vectors_ready && c->incidence_ready;
+}
+
+void assemble(Ctx *c) {
+    {
+        PhaseTimer tm(c, &c->stats.ms_scatter);
+        scatter_add_values(c, c->ev.ptr, c->vals.ptr);
+    }
+    {
+        PhaseTimer tm(c, &c->stats.ms_partition);
+        gather_block_values(c, c->vals.ptr);
+    }
+    c->vals_ready = true;
+}
+
+void ensure_assembled(Ctx *c, uint32_t flags) {
+    ensure_symbolic(c, flags);
+    if (!c->vals_ready) assemble(c);
+}
+
+void ensure_loads(Ctx *c) {
+    if (c->loads.vectors_ready) return;
+    PhaseTimer tm(c, &c->stats.ms_rhs);
+    build_load_vectors(c);
+}
+
+pn_solve_opts default_opts(const pn_solve_opts *o) {
+    pn_solve_opts r;
+    if (o) r = *o;
+    else { r.solver = PN_SOLVER_DIRECT; r.check_stability = 1; r.max_iter = 0; r.refine_steps = 2; r.tol = 1e-12; r.singular_tol = 1e-6; }
+    if (r.singular_tol <= 0) r.singular_tol = 1e-6;
+    if (r.tol <= 0) r.tol = 1e-12;
+    return r;
+}
+
+__global__ void k_sub(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = a[t] - b[t];
+}
+__global__ void k_add(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = a[t] + b[t];
+}
+__global__ void k_put_col(int64_t n, int s, int j, const double *__restrict__ v, double *__restrict__ M) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) M[i * s + j] = v[i];
+}
+__global__ void k_gather_vals(int64_t n, const uint32_t *__restrict__ src, const double *__restrict__ in, double *__restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[src[i]];
+}
+__global__ void k_spmm_percol_api(int64_t rows, int s, int64_t nnz, const int32_t *__restrict__ indptr,
+                                  const int32_t *__restrict__ indices, const double *__restrict__ vals,
+                                  const double *__restrict__ X, double *__restrict__ Y) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= rows * s) return;
+    int64_t r = t / s; int j = (int)(t - r * s);
+    const double *v = vals + (int64_t)j * nnz;
+    double acc = 0.0;
+    for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) acc = fma(v[k], X[(int64_t)indices[k] * s + j], acc);
+    Y[t] = acc;
+}
+
+// Analysis._solve_unknown_disp :228-239: non-finite values or ||K x - b|| > tol ||b|| (||x|| > tol when
+// b = 0) mean a singular matrix.  Returns the largest relative residual.
+double residual_check(Ctx *c, const double *vals11, int percol, int s, const pn_solve_opts &o, bool raise) {
+    int64_t n1 = c->n1;
+    if (!n1 || !s) return 0.0;
+    cudaStream_t st = c->stream;
+    DevBuf<double> AX;
+    AX.resize(n1 * s);
+    if (percol) {
+        k_spmm_percol_api<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, c->blk[0].nnz, c->blk[0].indptr.ptr,
+                                                                  c->blk[0].indices.ptr, vals11, c->X.ptr, AX.ptr);
+        c->count_launch();
+    } else {
+        spmm(c, c->blk[0], vals11, c->X.ptr, AX.ptr, s, st);
+    }
+    k_sub<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, AX.ptr, c->B.ptr, AX.ptr);
+    c->count_launch();
+    std::vector<double> rr(s), bb(s), xx(s);
+    column_dots(c, n1, s, AX.ptr, AX.ptr, rr.data());
+    column_dots(c, n1, s, c->B.ptr, c->B.ptr, bb.data());
+    column_dots(c, n1, s, c->X.ptr, c->X.ptr, xx.data());
+    double worst = 0.0;
+    for (int j = 0; j < s; ++j) {
+        bool finite = std::isfinite(rr[j]) && std::isfinite(xx[j]);
+        double rn = std::sqrt(rr[j]), bn = std::sqrt(bb[j]), xn = std::sqrt(xx[j]);
+        bool bad = !finite || (bn > 0 ? rn > o.singular_tol * bn : xn > o.singular_tol);
+        double rel = bn > 0 ? rn / bn : rn;
+        if (!finite) rel = INFINITY;
+        worst = std::max(worst, rel);
+        if (bad && raise)
+            throw StatusError(PN_ERR_SINGULAR, "The stiffness matrix is singular, which indicates that the structure is unstable.");
+    }
+    return worst;
+}
+
+void run_solver(Ctx *c, const double *vals11, int percol, int s, const pn_solve_opts &o) {
+    if (!c->n1 || !s) return;
+    if (o.solver == PN_SOLVER_PCG) pcg_solve(c, vals11, percol, s, o);
+    else direct_solve(c, vals11, percol, s, o);
+    double worst = residual_check(c, vals11, percol, s, o, o.check_stability != 0);
+    c->stats.max_rel_residual = std::max(c->stats.max_rel_residual, worst);
+}
+
+// combos are processed in batches so that the [n1][s] work arrays stay bounded
+int batch_size(Ctx *c, int n_combo) {
+    int64_t per = std::max<int64_t>(c->n1, 1) * 8;          // bytes per column of one work array
+    int64_t cap = (int64_t)(8.0e9 / (double)per);            // <= 8 GB per work array
+    int s = (int)std::min<int64_t>(std::min<int64_t>(n_combo, 64), std::max<int64_t>(cap, 1));
+    return std::max(s, 1);
+}
+
+void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
+    if (!Rxn_out) return;
+    PhaseTimer tm(c, &c->stats.ms_reactions);
+    build_incidence(c);
+    DevBuf<double> rx;
+    int nc = c->loads.n_combo;
+    rx.resize((int64_t)nc * c->n_dof);
+    for (int j = 0; j < nc; ++j) compute_reactions(c, j, pdelta, rx.ptr + (int64_t)j * c->n_dof);
+    download(rx, Rxn_out, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void solve_linear_all(Ctx *c, const pn_solve_opts &o) {
+    int nc = c->loads.n_combo;
+    c->D_all.resize((int64_t)nc * c->n_dof);
+    int bs = batch_size(c, nc);
+    for (int j0 = 0; j0 < nc; j0 += bs) {
+        int s = std::min(bs, nc - j0);
+        {
+            PhaseTimer tm(c, &c->stats.ms_rhs);
+            build_rhs(c, j0, s, nullptr);
+        }
+        run_solver(c, c->blk[0].vals.ptr, 0, s, o);
+        merge_displacements(c, j0, s);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pn_version(void) { return "pynite_b200 0.1 (sm_100a)"; }
+
+int pn_create(pn_ctx **out, int device_id) {
+    if (!out) return PN_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return PN_ERR_NO_DEVICE; }
+    if (device_id < 0 || device_id >= n) return PN_ERR_ARG;
+    if (cudaSetDevice(device_id) != cudaSuccess) { cudaGetLastError(); return PN_ERR_CUDA; }
+    Ctx *c = new Ctx();
+    c->device = device_id;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return PN_ERR_CUDA;
+    }
+    *out = reinterpret_cast<pn_ctx *>(c);
+    return PN_OK;
+}
+
+void pn_destroy(pn_ctx *ctx) {
+    if (!ctx) return;
+    Ctx *c = C(ctx);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    direct_release(c);
+    pcg_release(c);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    cudaStream_t st = c->stream;
+    delete c;
+    if (st) cudaStreamDestroy(st);
+}
+
+const char *pn_last_error(pn_ctx *ctx) { return ctx ? C(ctx)->err.c_str() : "null context"; }
+
+int pn_set_nodes(pn_ctx *ctx, int64_t n_nodes, const double *xyz, const uint8_t *support_mask,
+                 const uint8_t *enforced_mask, const double *enforced_val, const double *spring_k,
+                 const uint8_t *spring_flag) {
+    PN_API_BEGIN(ctx)
+    if (n_nodes < 0 || (n_nodes && (!xyz || !support_mask || !enforced_mask || !enforced_val || !spring_k || !spring_flag)))
+        throw ArgError("pn_set_nodes: null array");
+    if (6 * n_nodes >= (int64_t)0x7fffffff) throw ArgError("pn_set_nodes: more than 2^31 DOFs");
+    Model &m = c->model;
+    cudaStream_t st = c->stream;
+    invalidate(c);
+    m.n_nodes = n_nodes;
+    m.h_xyz.assign(xyz, xyz + 3 * n_nodes);
+    m.h_support.assign(support_mask, support_mask + n_nodes);
+    m.h_enf_mask.assign(enforced_mask, enforced_mask + n_nodes);
+    m.h_enf_val.assign(enforced_val, enforced_val + 6 * n_nodes);
+    m.h_nspring_k.assign(spring_k, spring_k + 6 * n_nodes);
+    m.h_nspring_flag.assign(spring_flag, spring_flag + 6 * n_nodes);
+    m.xyz.upload(m.h_xyz.data(), 3 * n_nodes, st);
+    m.support.upload(m.h_support.data(), n_nodes, st);
+    m.enf_mask.upload(m.h_enf_mask.data(), n_nodes, st);
+    m.enf_val.upload(m.h_enf_val.data(), 6 * n_nodes, st);
+    m.nspring_k.upload(m.h_nspring_k.data(), 6 * n_nodes, st);
+    m.nspring_flag.upload(m.h_nspring_flag.data(), 6 * n_nodes, st);
+    PN_CUDA(cudaStreamSynchronize(st));
+    PN_API_END
+}
+
+static void check_conn(const Ctx *c, int64_t n, int nn, const int32_t *conn, const char *what) {
+    for (int64_t k = 0; k < n * nn; ++k)
+        if (conn[k] < 0 || conn[k] >= c->model.n_nodes) throw ArgError(std::string(what) + ": node index out of range");
+}
+
+int pn_set_springs(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *ks, const uint8_t *active) {
+    PN_API_BEGIN(ctx)
+    if (n < 0 || (n && (!ij || !ks || !active))) throw ArgError("pn_set_springs: null array");
+    check_conn(c, n, 2, ij, "pn_set_springs");
+    Model &m = c->model;
+    invalidate(c);
+    m.n_springs = n;
+    m.h_spring_ij.assign(ij, ij + 2 * n);
+    m.h_spring_active.assign(active, active + n);
+    m.spring_ij.upload(ij, 2 * n, c->stream);
+    m.spring_ks.upload(ks, n, c->stream);
+    m.spring_active.upload(active, n, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_set_members(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *props, const double *rotation_deg,
+                   const uint16_t *releases, const uint8_t *active) {
+    PN_API_BEGIN(ctx)
+    if (n < 0 || (n && (!ij || !props || !rotation_deg || !releases || !active))) throw ArgError("pn_set_members: null array");
+    check_conn(c, n, 2, ij, "pn_set_members");
+    Model &m = c->model;
+    invalidate(c);
+    m.n_members = n;
+    m.h_mem_ij.assign(ij, ij + 2 * n);
+    m.h_mem_active.assign(active, active + n);
+    m.mem_ij.upload(ij, 2 * n, c->stream);
+    m.mem_props.upload(props, 6 * n, c->stream);
+    m.mem_rot.upload(rotation_deg, n, c->stream);
+    m.mem_rel.upload(releases, n, c->stream);
+    m.mem_active.upload(active, n, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+static void set_shells(Ctx *c, bool quad, int64_t n, const int32_t *ijmn, const double *props) {
+    if (n < 0 || (n && (!ijmn || !props))) throw ArgError("pn_set_quads/plates: null array");
+    check_conn(c, n, 4, ijmn, "pn_set_quads/plates");
+    Model &m = c->model;
+    invalidate(c);
+    (quad ? m.n_quads : m.n_plates) = n;
+    (quad ? m.h_quad_ijmn : m.h_plate_ijmn).assign(ijmn, ijmn + 4 * n);
+    (quad ? m.quad_ijmn : m.plate_ijmn).upload(ijmn, 4 * n, c->stream);
+    (quad ? m.quad_props : m.plate_props).upload(props, 5 * n, c->stream);
+    // the membrane matrix is unsymmetric when kx_mod != ky_mod (Quad3D.py:517-519)
+    bool sym = true;
+    for (int64_t e = 0; e < n; ++e) if (props[5 * e + 3] != props[5 * e + 4]) sym = false;
+    if (quad) c->quad_symmetric = sym; else c->plate_symmetric = sym;
+    m.symmetric = c->quad_symmetric && c->plate_symmetric;
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+int pn_set_quads(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props) {
+    PN_API_BEGIN(ctx)
+    set_shells(c, true, n, ijmn, props);
+    PN_API_END
+}
+int pn_set_plates(pn_ctx *ctx, int64_t n, const int32_t *ijmn, const double *props) {
+    PN_API_BEGIN(ctx)
+    set_shells(c, false, n, ijmn, props);
+    PN_API_END
+}
+
+int pn_element_ke(pn_ctx *ctx, int kind, double *out) {
+    PN_API_BEGIN(ctx)
+    if (!out) throw ArgError("pn_element_ke: null output");
+    ensure_ev(c);
+    const Model &m = c->model;
+    int64_t off, cnt;
+    switch (kind) {
+    case PN_SPRING: off = c->ev_off_spring; cnt = 144 * m.n_springs; break;
+    case PN_MEMBER: off = c->ev_off_member; cnt = 144 * m.n_members; break;
+    case PN_QUAD: off = c->ev_off_quad; cnt = 576 * m.n_quads; break;
+    case PN_PLATE: off = c->ev_off_plate; cnt = 576 * m.n_plates; break;
+    default: throw ArgError("pn_element_ke: unknown element kind");
+    }
+    if (cnt) PN_CUDA(cudaMemcpyAsync(out, c->ev.ptr + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_member_kg(pn_ctx *ctx, const double *P, double *out) {
+    PN_API_BEGIN(ctx)
+    int64_t n = c->model.n_members;
+    if (n && (!P || !out)) throw ArgError("pn_member_kg: null array");
+    DevBuf<double> dP, dK;
+    dP.upload(P, n, c->stream);
+    dK.resize(144 * n);
+    launch_member_kg(c, dP.ptr, dK.ptr, c->stream);
+    download(dK, out, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_symbolic(pn_ctx *ctx, uint32_t flags) {
+    PN_API_BEGIN(ctx)
+    ensure_symbolic(c, flags);
+    PN_API_END
+}
+
+int pn_get_sizes(pn_ctx *ctx, pn_sizes *out) {
+    PN_API_BEGIN(ctx)
+    if (!out) throw ArgError("pn_get_sizes: null output");
+    if (!c->symbolic_ready) throw ArgError("pn_get_sizes: call pn_symbolic first");
+    out->n_dof = c->n_dof; out->nnz_coo = c->nnz_coo; out->nnz_csr = c->nnz_csr; out->n1 = c->n1; out->n2 = c->n2;
+    out->nnz11 = c->blk[0].nnz; out->nnz12 = c->blk[1].nnz; out->nnz21 = c->blk[2].nnz; out->nnz22 = c->blk[3].nnz;
+    PN_API_END
+}
+
+int pn_get_coo(pn_ctx *ctx, int32_t *row, int32_t *col, double *data) {
+    PN_API_BEGIN(ctx)
+    if (!c->symbolic_ready) throw ArgError("pn_get_coo: call pn_symbolic first");
+    DevBuf<int32_t> r, cc;
+    DevBuf<double> d;
+    r.resize(c->nnz_coo); cc.resize(c->nnz_coo); d.resize(c->nnz_coo);
+    export_coo(c, r.ptr, cc.ptr, d.ptr);
+    download(r, row, c->stream); download(cc, col, c->stream); download(d, data, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_get_pattern(pn_ctx *ctx, int32_t *indptr, int32_t *indices) {
+    PN_API_BEGIN(ctx)
+    if (!c->symbolic_ready) throw ArgError("pn_get_pattern: call pn_symbolic first");
+    download(c->indptr, indptr, c->stream);
+    download(c->indices, indices, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_get_partition(pn_ctx *ctx, int32_t *d1, int32_t *d2, double *d2_values) {
+    PN_API_BEGIN(ctx)
+    if (!c->symbolic_ready) throw ArgError("pn_get_partition: call pn_symbolic first");
+    download(c->d1, d1, c->stream);
+    download(c->d2, d2, c->stream);
+    download(c->d2_val, d2_values, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_get_block(pn_ctx *ctx, int block, int32_t *indptr, int32_t *indices, double *data) {
+    PN_API_BEGIN(ctx)
+    if (block < 0 || block > 3) throw ArgError("pn_get_block: block must be 0..3");
+    if (!c->symbolic_ready) throw ArgError("pn_get_block: call pn_symbolic first");
+    if (data && !c->vals_ready) throw ArgError("pn_get_block: call pn_assemble_ke first");
+    const CsrBlock &B = c->blk[block];
+    download(B.indptr, indptr, c->stream);
+    download(B.indices, indices, c->stream);
+    download(B.vals, data, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_assemble_ke(pn_ctx *ctx) {
+    PN_API_BEGIN(ctx)
+    if (c->symbolic_ready) compute_ev(c);      // numeric re-assembly on a fixed pattern
+    ensure_symbolic(c, c->symbolic_ready ? c->sym_flags : 0u);
+    assemble(c);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_get_csr_values(pn_ctx *ctx, double *data) {
+    PN_API_BEGIN(ctx)
+    if (!c->vals_ready) throw ArgError("pn_get_csr_values: call pn_assemble_ke first");
+    download(c->vals, data, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_check_nodal_stability(pn_ctx *ctx, int32_t *bad_dofs, int64_t cap, int64_t *n_bad) {
+    PN_API_BEGIN(ctx)
+    if (!c->vals_ready) throw ArgError("pn_check_nodal_stability: call pn_assemble_ke first");
+    std::vector<int32_t> tmp((size_t)std::max<int64_t>(cap, 1));
+    int64_t n = check_nodal_stability(c, tmp.data(), std::max<int64_t>(cap, 1));
+    if (n_bad) *n_bad = n;
+    if (bad_dofs) for (int64_t i = 0; i < std::min(n, cap); ++i) bad_dofs[i] = tmp[i];
+    if (n > 0) throw StatusError(PN_ERR_UNSTABLE_NODE, "Unstable node(s). See console output for details.");
+    PN_API_END
+}
+
+int pn_set_loads(pn_ctx *ctx, int32_t n_case,
+                 int64_t n_nodal, const int32_t *nl_dof, const int32_t *nl_case, const double *nl_val,
+                 int64_t n_mload, const int32_t *ml_member, const int32_t *ml_case, const int32_t *ml_kind,
+                 const double *ml_params,
+                 int64_t n_qp, const int32_t *qp_elem, const int32_t *qp_case, const double *qp_val,
+                 int64_t n_pp, const int32_t *pp_elem, const int32_t *pp_case, const double *pp_val) {
+    PN_API_BEGIN(ctx)
+    if (n_case < 0 || n_nodal < 0 || n_mload < 0 || n_qp < 0 || n_pp < 0) throw ArgError("pn_set_loads: negative count");
+    Loads &ld = c->loads;
+    const Model &m = c->model;
+    cudaStream_t st = c->stream;
+    ld.vectors_ready = false;
+    c->solved = c->solved_pdelta = false;
+    ld.n_case = n_case;
+    int64_t n_dof = 6 * m.n_nodes;
+
+    // duplicates of one (index, case) pair are summed in input (= model) order
+    auto unique_sum = [&](int64_t n, const int32_t *idx, const int32_t *cs, const double *val, int64_t idx_limit,
+                          const char *what, std::vector<int32_t> &oi, std::vector<int32_t> &oc, std::vector<double> &ov) {
+        std::vector<int64_t> order(n);
+        std::iota(order.begin(), order.end(), 0);
+        for (int64_t k = 0; k < n; ++k)
+            if (idx[k] < 0 || idx[k] >= idx_limit || cs[k] < 0 || cs[k] >= n_case)
+                throw ArgError(std::string(what) + ": index or case out of range");
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+            return cs[a] != cs[b] ? cs[a] < cs[b] : idx[a] < idx[b];
+        });
+        oi.clear(); oc.clear(); ov.clear();
+        for (int64_t q = 0; q < n; ++q) {
+            int64_t k = order[q];
+            if (!oi.empty() && oi.back() == idx[k] && oc.back() == cs[k]) ov.back() += val[k];
+            else { oi.push_back(idx[k]); oc.push_back(cs[k]); ov.push_back(val[k]); }
+        }
+    };
+    std::vector<int32_t> oi, oc;
+    std::vector<double> ov;
+    unique_sum(n_nodal, nl_dof, nl_case, nl_val, n_dof, "pn_set_loads(nodal)", oi, oc, ov);
+    ld.nl_dof.upload(oi.data(), (int64_t)oi.size(), st);
+    ld.nl_case.upload(oc.data(), (int64_t)oc.size(), st);
+    ld.nl_val.upload(ov.data(), (int64_t)ov.size(), st);
+    PN_CUDA(cudaStreamSynchronize(st));
+    unique_sum(n_qp, qp_elem, qp_case, qp_val, m.n_quads, "pn_set_loads(quad pressure)", oi, oc, ov);
+    ld.case_has_quad.assign(n_case, 0);
+    for (int32_t cs : oc) ld.case_has_quad[cs] = 1;
+    ld.qp_elem.upload(oi.data(), (int64_t)oi.size(), st);
+    ld.qp_case.upload(oc.data(), (int64_t)oc.size(), st);
+    ld.qp_val.upload(ov.data(), (int64_t)ov.size(), st);
+    PN_CUDA(cudaStreamSynchronize(st));
+    unique_sum(n_pp, pp_elem, pp_case, pp_val, m.n_plates, "pn_set_loads(plate pressure)", oi, oc, ov);
+    ld.case_has_plate.assign(n_case, 0);
+    for (int32_t cs : oc) ld.case_has_plate[cs] = 1;
+    ld.pp_elem.upload(oi.data(), (int64_t)oi.size(), st);
+    ld.pp_case.upload(oc.data(), (int64_t)oc.size(), st);
+    ld.pp_val.upload(ov.data(), (int64_t)ov.size(), st);
+    PN_CUDA(cudaStreamSynchronize(st));
+
+    // member loads grouped by (member, case), input order kept inside a group
+    {
+        std::vector<int64_t> order(n_mload);
+        std::iota(order.begin(), order.end(), 0);
+        for (int64_t k = 0; k < n_mload; ++k)
+            if (ml_member[k] < 0 || ml_member[k] >= m.n_members || ml_case[k] < 0 || ml_case[k] >= n_case ||
+                ml_kind[k] < 0 || ml_kind[k] > 17)
+                throw ArgError("pn_set_loads(member): member, case or kind out of range");
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+            return ml_member[a] != ml_member[b] ? ml_member[a] < ml_member[b] : ml_case[a] < ml_case[b];
+        });
+        std::vector<int32_t> kind(n_mload), gm, gc;
+        std::vector<double> par(4 * n_mload);
+        std::vector<int64_t> gs;
+        for (int64_t q = 0; q < n_mload; ++q) {
+            int64_t k = order[q];
+            kind[q] = ml_kind[k];
+            for (int t = 0; t < 4; ++t) par[4 * q + t] = ml_params[4 * k + t];
+            if (gm.empty() || gm.back() != ml_member[k] || gc.back() != ml_case[k]) {
+                gm.push_back(ml_member[k]); gc.push_back(ml_case[k]); gs.push_back(q);
+            }
+        }
+        gs.push_back(n_mload);
+        ld.n_mloads = n_mload;
+        ld.n_mgroups = (int64_t)gm.size();
+        ld.ml_kind.upload(kind.data(), n_mload, st);
+        ld.ml_params.upload(par.data(), 4 * n_mload, st);
+        ld.mg_member.upload(gm.data(), ld.n_mgroups, st);
+        ld.mg_case.upload(gc.data(), ld.n_mgroups, st);
+        ld.mg_start.upload(gs.data(), ld.n_mgroups + 1, st);
+        ld.mg_fer_local.resize(12 * ld.n_mgroups);
+        ld.mg_fer_global.resize(12 * ld.n_mgroups);
+        PN_CUDA(cudaStreamSynchronize(st));
+    }
+    PN_API_END
+}
+
+int pn_set_combos(pn_ctx *ctx, int32_t n_combo, const double *factors) {
+    PN_API_BEGIN(ctx)
+    Loads &ld = c->loads;
+    if (n_combo < 0 || (n_combo && ld.n_case && !factors)) throw ArgError("pn_set_combos: null factors");
+    ld.n_combo = n_combo;
+    ld.h_factors.assign(factors, factors + (int64_t)n_combo * ld.n_case);
+    ld.factors.upload(ld.h_factors.data(), (int64_t)ld.h_factors.size(), c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    c->solved = c->solved_pdelta = false;
+    PN_API_END
+}
+
+int pn_get_load_vector(pn_ctx *ctx, int32_t combo, int32_t which, double *out) {
+    PN_API_BEGIN(ctx)
+    Loads &ld = c->loads;
+    if (combo < 0 || combo >= ld.n_combo || (which != 0 && which != 1) || !out) throw ArgError("pn_get_load_vector: bad argument");
+    ensure_symbolic(c, c->symbolic_ready ? c->sym_flags : 0u);
+    ensure_loads(c);
+    int64_t n = c->n_dof;
+    std::vector<double> P((size_t)ld.n_case * n), G;
+    PN_CUDA(cudaMemcpyAsync(P.data(), ld.Pcase.ptr, sizeof(double) * P.size(), cudaMemcpyDeviceToHost, c->stream));
+    if (which == 1) {
+        G.resize(P.size());
+        PN_CUDA(cudaMemcpyAsync(G.data(), ld.Gcase.ptr, sizeof(double) * G.size(), cudaMemcpyDeviceToHost, c->stream));
+    }
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t d = 0; d < n; ++d) {
+        double acc = 0.0;
+        for (int cs = 0; cs < ld.n_case; ++cs) {
+            double v = which == 0 ? P[(size_t)cs * n + d] : P[(size_t)cs * n + d] - G[(size_t)cs * n + d];
+            acc = std::fma(ld.h_factors[(size_t)combo * ld.n_case + cs], v, acc);
+        }
+        out[d] = acc;
+    }
+    PN_API_END
+}
+
+int pn_solve_linear(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats) {
+    PN_API_BEGIN(ctx)
+    pn_solve_opts o = default_opts(opts);
+    Loads &ld = c->loads;
+    c->solved = c->solved_pdelta = false;
+    ensure_assembled(c, c->symbolic_ready ? c->sym_flags : 0u);
+    ensure_loads(c);
+    solve_linear_all(c, o);
+    c->solved = true;
+    if (D_out) download(c->D_all, D_out, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    reactions_out(c, false, Rxn_out);
+    (void)ld;
+    c->stats.kernel_launches = c->launches;
+    if (stats) *stats = c->stats;
+    PN_API_END
+}
+
+int pn_solve_pdelta(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, double *Rxn_out, pn_stats *stats) {
+    PN_API_BEGIN(ctx)
+    pn_solve_opts o = default_opts(opts);
+    Loads &ld = c->loads;
+    const Model &m = c->model;
+    cudaStream_t st = c->stream;
+    c->solved = c->solved_pdelta = false;
+    // Kg has no zero filter (FEModel3D.py:1859-1885): the pattern must hold every member block densely
+    ensure_assembled(c, PN_SYM_DENSE_MEMBER_BLOCKS);
+    ensure_loads(c);
+    solve_linear_all(c, o);                         // step 1 (Analysis.py:382-445)
+    int nc = ld.n_combo;
+    if (m.n_members && c->n1) {
+        const CsrBlock &K11 = c->blk[0], &K12 = c->blk[1];
+        DevBuf<double> ev2, memP, kg, valsj, vals11, vals12, kd2col, kd2all;
+        ev2.resize(c->ev_count);
+        PN_CUDA(cudaMemcpyAsync(ev2.ptr, c->ev.ptr, sizeof(double) * c->ev_count, cudaMemcpyDeviceToDevice, st));
+        memP.resize(m.n_members); kg.resize(144 * m.n_members); valsj.resize(c->nnz_csr);
+        vals12.resize(K12.nnz); kd2col.resize(c->n1);
+        int bs = batch_size(c, nc);
+        // also bound the per-combo K11 copies to ~8 GB
+        bs = (int)std::max<int64_t>(1, std::min<int64_t>(bs, (int64_t)(8.0e9 / (8.0 * std::max<int64_t>(K11.nnz, 1)))));
+        for (int j0 = 0; j0 < nc; j0 += bs) {
+            int s = std::min(bs, nc - j0);
+            vals11.resize((int64_t)s * K11.nnz);
+            kd2all.resize(c->n1 * s);
+            for (int j = 0; j < s; ++j) {          // step 2 matrices (FEModel3D.Kg :1826-1892, Analysis.py:395-402)
+                PhaseTimer tm(c, &c->stats.ms_scatter);
+                const double *D = c->D_all.ptr + (int64_t)(j0 + j) * c->n_dof;
+                launch_member_axial(c, D, memP.ptr, st);
+                launch_member_kg(c, memP.ptr, kg.ptr, st);
+                k_add<<<grid_for(144 * m.n_members, 256), 256, 0, st>>>(144 * m.n_members, c->ev.ptr + c->ev_off_member,
+                                                                         kg.ptr, ev2.ptr + c->ev_off_member);
+                scatter_add_values(c, ev2.ptr, valsj.ptr);
+                if (K11.nnz)
+                    k_gather_vals<<<grid_for(K11.nnz, 256), 256, 0, st>>>(K11.nnz, K11.src.ptr, valsj.ptr,
+                                                                          vals11.ptr + (int64_t)j * K11.nnz);
+                kd2col.zero(st);
+                if (K12.nnz) {
+                    k_gather_vals<<<grid_for(K12.nnz, 256), 256, 0, st>>>(K12.nnz, K12.src.ptr, valsj.ptr, vals12.ptr);
+                    spmv_plain(c, K12, vals12.ptr, c->d2_val.ptr, kd2col.ptr, st);
+                }
+                k_put_col<<<grid_for(c->n1, 256), 256, 0, st>>>(c->n1, s, j, kd2col.ptr, kd2all.ptr);
+                c->count_launch(4);
+            }
+            {
+                PhaseTimer tm(c, &c->stats.ms_rhs);
+                build_rhs(c, j0, s, kd2all.ptr);
+            }
+            run_solver(c, vals11.ptr, 1, s, o);
+            merge_displacements(c, j0, s);
+        }
+    }
+    c->solved = c->solved_pdelta = true;
+    if (D_out) download(c->D_all, D_out, st);
+    PN_CUDA(cudaStreamSynchronize(st));
+    reactions_out(c, true, Rxn_out);
+    c->stats.kernel_launches = c->launches;
+    if (stats) *stats = c->stats;
+    PN_API_END
+}
+
+int pn_get_kg_coo(pn_ctx *ctx, int32_t combo, int32_t first_step, int32_t *row, int32_t *col, double *data,
+                  int64_t *n_out) {
+    PN_API_BEGIN(ctx)
+    const Model &m = c->model;
+    if (!first_step && (!c->solved || combo < 0 || combo >= c->loads.n_combo))
+        throw ArgError("pn_get_kg_coo: combo has not been solved");
+    cudaStream_t st = c->stream;
+    DevBuf<double> memP, kg;
+    memP.resize(m.n_members); kg.resize(144 * m.n_members);
+    if (first_step) memP.zero(st);
+    else launch_member_axial(c, c->D_all.ptr + (int64_t)combo * c->n_dof, memP.ptr, st);
+    launch_member_kg(c, memP.ptr, kg.ptr, st);
+    std::vector<double> h(144 * (size_t)m.n_members);
+    download(kg, h.data(), st);
+    PN_CUDA(cudaStreamSynchronize(st));
+    int64_t o = 0;
+    for (int64_t e = 0; e < m.n_members; ++e) {
+        if (!m.h_mem_active[e]) continue;
+        for (int r = 0; r < 12; ++r)
+            for (int q = 0; q < 12; ++q) {
+                if (row) row[o] = m.h_mem_ij[2 * e + r / 6] * 6 + r % 6;
+                if (col) col[o] = m.h_mem_ij[2 * e + q / 6] * 6 + q % 6;
+                if (data) data[o] = h[(size_t)e * 144 + r * 12 + q];
+                ++o;
+            }
+    }
+    if (n_out) *n_out = o;
+    PN_API_END
+}
+
+int pn_set_displacements(pn_ctx *ctx, int32_t combo, const double *D) {
+    PN_API_BEGIN(ctx)
+    if (!c->solved || combo < 0 || combo >= c->loads.n_combo || !D) throw ArgError("pn_set_displacements: combo has not been solved");
+    PN_CUDA(cudaMemcpyAsync(c->D_all.ptr + (int64_t)combo * c->n_dof, D, sizeof(double) * c->n_dof, cudaMemcpyHostToDevice, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_reactions(pn_ctx *ctx, int32_t combo, int32_t pdelta, double *out) {
+    PN_API_BEGIN(ctx)
+    if (!c->solved || combo < 0 || combo >= c->loads.n_combo || !out) throw ArgError("pn_reactions: combo has not been solved");
+    PhaseTimer tm(c, &c->stats.ms_reactions);
+    build_incidence(c);
+    DevBuf<double> rx;
+    rx.resize(c->n_dof);
+    compute_reactions(c, combo, pdelta != 0, rx.ptr);
+    download(rx, out, c->stream);
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32_t pdelta, double *out) {
+    PN_API_BEGIN(ctx)
+    if (!c->solved || combo < 0 || combo >= c->loads.n_combo) throw ArgError("pn_element_forces: combo has not been solved");
+    if (!out) throw ArgError("pn_element_forces: null output");
+    const Model &m = c->model;
+    cudaStream_t st = c->stream;
+    build_incidence(c);
+    ensure_loads(c);
+    combine_fer(c, combo);
+    const double *D = c->D_all.ptr + (int64_t)combo * c->n_dof;
+    int64_t off, cnt;
+    const double *fer = nullptr;
+    switch (kind) {
+    case PN_SPRING: off = c->ef_off_spring; cnt = 12 * m.n_springs; break;
+    case PN_MEMBER: off = c->ef_off_member; cnt = 12 * m.n_members; fer = c->fer_combo.ptr + off; break;
+    case PN_QUAD: off = c->ef_off_quad; cnt = 24 * m.n_quads; fer = c->fer_combo.ptr + off; break;
+    case PN_PLATE: off = c->ef_off_plate; cnt = 24 * m.n_plates; fer = c->fer_combo.ptr + off; break;
+    default: throw ArgError("pn_element_forces: unknown element kind");
+    }
+    double *F = c->ef.ptr + off;
+    launch_element_forces(c, kind, D, fer, F, st);
+    if (kind == PN_MEMBER && pdelta) launch_member_pdelta_forces(c, D, F, st);
+    if (local) launch_forces_to_local(c, kind, F, st);
+    if (cnt) PN_CUDA(cudaMemcpyAsync(out, F, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    PN_CUDA(cudaStreamSynchronize(st));
+    PN_API_END
+}
+
+int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repeat, double *ms_out) {
+    PN_API_BEGIN(ctx)
+    if (!c->vals_ready) throw ArgError("pn_spmm_k11: call pn_assemble_ke first");
+    if (s < 1 || s > 256 || repeat < 1) throw ArgError("pn_spmm_k11: bad s / repeat");
+    cudaStream_t st = c->stream;
+    DevBuf<double> dX, dY;
+    int64_t n = c->n1 * s;
+    dX.resize(n); dY.resize(n);
+    if (X) PN_CUDA(cudaMemcpyAsync(dX.ptr, X, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    else {
+        std::vector<double> ones((size_t)n, 1.0);
+        PN_CUDA(cudaMemcpyAsync(dX.ptr, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        PN_CUDA(cudaStreamSynchronize(st));
+    }
+    spmm(c, c->blk[0], c->blk[0].vals.ptr, dX.ptr, dY.ptr, s, st);       // warm-up
+    PN_CUDA(cudaEventRecord(c->ev0, st));
+    for (int r = 0; r < repeat; ++r) spmm(c, c->blk[0], c->blk[0].vals.ptr, dX.ptr, dY.ptr, s, st);
+    PN_CUDA(cudaEventRecord(c->ev1, st));
+    PN_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    PN_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (ms_out) *ms_out = (double)ms / repeat;
+    c->stats.ms_spmm += ms;
+    c->stats.spmm_launches += repeat;
+    if (Y) PN_CUDA(cudaMemcpyAsync(Y, dY.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    PN_CUDA(cudaStreamSynchronize(st));
+    PN_API_END
+}
+
+int pn_get_stats(pn_ctx *ctx, pn_stats *out) {
+    PN_API_BEGIN(ctx)
+    if (!out) throw ArgError("pn_get_stats: null output");
+    c->stats.kernel_launches = c->launches;
+    *out = c->stats;
+    PN_API_END
+}
+
+int pn_reset_stats(pn_ctx *ctx) {
+    PN_API_BEGIN(ctx)
+    c->stats = pn_stats{};
+    c->launches = 0;
+    PN_API_END
+}
+
+}  // extern "C"

@@ -7,10 +7,12 @@
 
 #if defined(__CUDACC__)
 #define PN_HD __host__ __device__ __forceinline__
+#define PN_D __device__ __forceinline__
 #else
 // The element math headers are also compiled by g++ into tests/host_harness (test infrastructure
 // only: it lets the arithmetic be checked against the oracle on a box without a GPU).
 #define PN_HD inline
+#define PN_D inline
 #endif
 
 // Fused multiply-add used in the hot accumulation loops.  The library is compiled with

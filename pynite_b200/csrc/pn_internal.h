@@ -138,6 +138,7 @@ struct Ctx {
 
     Model model;
     Loads loads;
+    bool quad_symmetric = true, plate_symmetric = true;
 
     // element-value buffer: [node springs | springs*144 | members*144 | quads*576 | plates*576]
     DevBuf<double> ev;
@@ -215,14 +216,15 @@ void scatter_add_values(Ctx *c, const double *ev_dev, double *vals_dev);
 void gather_block_values(Ctx *c, const double *vals_dev);
 void build_incidence(Ctx *c);
 void build_load_vectors(Ctx *c);
-void build_rhs(Ctx *c);                      // B = factors * G restricted to D1 - K12 D2
-void merge_displacements(Ctx *c);            // X, D2 -> D_all
+void build_rhs(Ctx *c, int32_t combo0, int s, const double *kd2_percol);   // B = factors * G restricted to D1 - K12 D2
+void merge_displacements(Ctx *c, int32_t combo0, int s);   // X, D2 -> D_all[combo0 .. combo0+s)
+void export_coo(Ctx *c, int32_t *row_dev, int32_t *col_dev, double *data_dev);
 void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev /* [n_dof] */);
 void combine_fer(Ctx *c, int32_t combo);     // fer_combo = sum_case factor * fer_case
 int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap);
 // Y = A X for a CSR block, X/Y row-major with s columns
 void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st);
-void spmv_plain(Ctx *c, const CsrBlock &A, const double *x, double *y, cudaStream_t st);
+void spmv_plain(Ctx *c, const CsrBlock &A, const double *vals, const double *x, double *y, cudaStream_t st);
 
 // ---- pn_pcg.cu / pn_direct.cu ---------------------------------------------------------------------
 // Solve K11 X = B for all s columns; `vals11` may differ per column when per_column_vals != 0

@@ -6,6 +6,8 @@
 // runs once per topology; the numeric kernels that run per assembly / per iteration are written here.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "pn_internal.h"
 
 namespace pn {
@@ -338,6 +340,22 @@ void build_symbolic(Ctx *c, uint32_t flags) {
     c->incidence_ready = false;
 }
 
+// COO triplets in emission order (FEModel3D.py:1773-1791), for inspection / parity tests.
+__global__ void k_export_coo(EvLayout L, int64_t n, const uint32_t *__restrict__ emit, const double *__restrict__ ev,
+                             int32_t *__restrict__ row, int32_t *__restrict__ col, double *__restrict__ data) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int32_t r, cc; int kind; int64_t e;
+    ev_row_col(L, emit[k], r, cc, kind, e);
+    row[k] = r; col[k] = cc; data[k] = ev[emit[k]];
+}
+void export_coo(Ctx *c, int32_t *row_dev, int32_t *col_dev, double *data_dev) {
+    if (!c->nnz_coo) return;
+    k_export_coo<<<grid_for(c->nnz_coo, 256), 256, 0, c->stream>>>(make_layout(c), c->nnz_coo, c->coo_emit.ptr, c->ev.ptr,
+                                                                    row_dev, col_dev, data_dev);
+    c->count_launch();
+}
+
 // ------------------------------------------------------------------------------------------------
 // numeric COO -> CSR: each stored entry is the sum of its COO duplicates taken in emission order
 // (fixed at symbolic time by the stable sort), so the result is bit-reproducible run to run.
@@ -549,14 +567,14 @@ __global__ void k_spmv_rows(int64_t rows, const int32_t *__restrict__ indptr, co
     for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) acc = fma(vals[k], x[indices[k]], acc);
     y[r] = acc;
 }
-void spmv_plain(Ctx *c, const CsrBlock &A, const double *x, double *y, cudaStream_t st) {
+void spmv_plain(Ctx *c, const CsrBlock &A, const double *vals, const double *x, double *y, cudaStream_t st) {
     if (!A.rows) return;
-    k_spmv_rows<<<grid_for(A.rows, 128), 128, 0, st>>>(A.rows, A.indptr.ptr, A.indices.ptr, A.vals.ptr, x, y);
+    k_spmv_rows<<<grid_for(A.rows, 128), 128, 0, st>>>(A.rows, A.indptr.ptr, A.indices.ptr, vals, x, y);
     c->count_launch();
 }
 
 __global__ void k_build_rhs(int64_t n1, int s, int n_case, const int32_t *__restrict__ d1, const double *__restrict__ G,
-                            int64_t n_dof, const double *__restrict__ fac, const double *__restrict__ kd2,
+                            int64_t n_dof, const double *__restrict__ fac, const double *__restrict__ kd2, int kd2_percol,
                             double *__restrict__ B) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n1 * s) return;
@@ -564,21 +582,24 @@ __global__ void k_build_rhs(int64_t n1, int s, int n_case, const int32_t *__rest
     int64_t d = d1[i];
     double acc = 0.0;
     for (int cs = 0; cs < n_case; ++cs) acc = fma(fac[(int64_t)j * n_case + cs], G[(int64_t)cs * n_dof + d], acc);
-    B[t] = acc - kd2[i];
+    B[t] = acc - (kd2_percol ? kd2[t] : kd2[i]);
 }
 
-void build_rhs(Ctx *c) {
+// kd2_percol: optional [n1][s] array of per-combo K12 D2 products (P-Delta second step); null = use
+// the elastic K12 for every combo.
+void build_rhs(Ctx *c, int32_t combo0, int s, const double *kd2_percol) {
     cudaStream_t st = c->stream;
     Loads &ld = c->loads;
-    int s = ld.n_combo;
     c->B.resize(c->n1 * s);
     c->X.resize(c->n1 * s);
     c->kd2.resize(c->n1);
     c->kd2.zero(st);
-    if (c->n1 == 0) return;
-    if (c->n2) spmv_plain(c, c->blk[1], c->d2_val.ptr, c->kd2.ptr, st);
+    if (c->n1 == 0 || s == 0) return;
+    if (!kd2_percol && c->n2) spmv_plain(c, c->blk[1], c->blk[1].vals.ptr, c->d2_val.ptr, c->kd2.ptr, st);
     k_build_rhs<<<grid_for(c->n1 * s, 256), 256, 0, st>>>(c->n1, s, ld.n_case, c->d1.ptr, ld.Gcase.ptr, c->n_dof,
-                                                            ld.factors.ptr, c->kd2.ptr, c->B.ptr);
+                                                            ld.factors.ptr + (int64_t)combo0 * ld.n_case,
+                                                            kd2_percol ? kd2_percol : c->kd2.ptr, kd2_percol ? 1 : 0,
+                                                            c->B.ptr);
     c->count_launch();
 }
 
@@ -592,12 +613,10 @@ __global__ void k_merge(int64_t n_dof, int s, const int32_t *__restrict__ newidx
     int32_t ni = newidx[d];
     D[t] = ni >= 0 ? X[(int64_t)ni * s + j] : d2_val[-1 - ni];
 }
-void merge_displacements(Ctx *c) {
-    int s = c->loads.n_combo;
-    c->D_all.resize((int64_t)s * c->n_dof);
+void merge_displacements(Ctx *c, int32_t combo0, int s) {
     if (!c->n_dof || !s) return;
     k_merge<<<grid_for(c->n_dof * s, 256), 256, 0, c->stream>>>(c->n_dof, s, c->newidx.ptr, c->X.ptr, c->d2_val.ptr,
-                                                                 c->D_all.ptr);
+                                                                 c->D_all.ptr + (int64_t)combo0 * c->n_dof);
     c->count_launch();
 }
 

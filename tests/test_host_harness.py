@@ -1,0 +1,156 @@
+"""CPU checks of the CUDA library's element arithmetic and of the direct solver's symbolic analysis.
+
+The element-math headers (`pynite_b200/csrc/elem_*.cuh`) are plain host/device functions; compiled with g++
+(tests/host_harness, -ffp-contract=off like nvcc -fmad=false) they are compared with the golden element
+matrices the reference produced.  The multifrontal ordering / front maps (`pn_direct_symbolic.cpp`) are
+exercised by a sequential host emulation of the GPU factorisation and compared with scipy.
+Nothing here is a product path: the package never loads these libraries."""
+import ctypes as ct
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spla
+
+from oracle import model as om
+from tests.util import FIXTURES, load_fixture, rel_err
+
+HH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'host_harness')
+F64P = ct.POINTER(ct.c_double)
+I32P = ct.POINTER(ct.c_int32)
+I64P = ct.POINTER(ct.c_int64)
+
+
+@pytest.fixture(scope='module')
+def libs():
+    subprocess.run(['make', '-C', HH], check=True, capture_output=True)
+    return ct.CDLL(os.path.join(HH, 'libhost_harness.so')), ct.CDLL(os.path.join(HH, 'libdirect_host.so'))
+
+
+def _p(a):
+    return a.ctypes.data_as(F64P)
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_line_elements(libs, name):
+    hh, _ = libs
+    A, ref, _ = load_fixture(name)
+    out = np.empty(144)
+    for m in range(len(A.mem_rot)):
+        i, j = A.mem_ij[m]
+        pi, pj = np.ascontiguousarray(A.xyz[i]), np.ascontiguousarray(A.xyz[j])
+        pr = np.ascontiguousarray(A.mem_props[m])
+        hh.hh_line_matrix(_p(pi), _p(pj), _p(pr), ct.c_double(A.mem_rot[m]), ct.c_uint(int(A.mem_rel[m])), 0,
+                          ct.c_double(0.0), _p(out))
+        assert rel_err(out.reshape(12, 12), ref['member_Ke'][m]) < 1e-12, m
+        if 'member_Kg' in ref:
+            hh.hh_line_matrix(_p(pi), _p(pj), _p(pr), ct.c_double(A.mem_rot[m]), ct.c_uint(int(A.mem_rel[m])), 1,
+                              ct.c_double(ref['member_P'][m]), _p(out))
+            assert rel_err(out.reshape(12, 12), ref['member_Kg'][m]) < 1e-12, m
+    for s in range(len(A.spring_ks)):
+        i, j = A.spring_ij[s]
+        pi, pj = np.ascontiguousarray(A.xyz[i]), np.ascontiguousarray(A.xyz[j])
+        pr = np.array([A.spring_ks[s], 0, 0, 0, 0, 0.0])
+        hh.hh_line_matrix(_p(pi), _p(pj), _p(pr), ct.c_double(0.0), ct.c_uint(0), 2, ct.c_double(0.0), _p(out))
+        assert rel_err(out.reshape(12, 12), ref['spring_Ke'][s]) < 1e-12, s
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_shell_elements(libs, name):
+    hh, _ = libs
+    A, ref, _ = load_fixture(name)
+    out = np.empty(576)
+    for kind, conn, props, is_quad in (('quad', A.quad_ijmn, A.quad_props, 1), ('plate', A.plate_ijmn, A.plate_props, 0)):
+        for e in range(len(conn)):
+            pts = np.ascontiguousarray(A.xyz[conn[e]].reshape(-1))
+            pr = np.ascontiguousarray(props[e])
+            hh.hh_shell_matrix(_p(pts), _p(pr), is_quad, _p(out))
+            K, R = out.reshape(24, 24), ref[kind + '_Ke'][e]
+            assert rel_err(K, R) < 1e-12, (kind, e)
+            if name != 'skew_shell':
+                # exact-zero structure decides the COO pattern (FEModel3D.py:130)
+                assert np.array_equal(K != 0.0, R != 0.0), (kind, e)
+
+
+@pytest.mark.parametrize('name', ['portal_frame', 'continuous_beam', 'moment_frame'])
+def test_member_fer(libs, name):
+    hh, _ = libs
+    A, ref, _ = load_fixture(name)
+    out = np.empty(12)
+    for c in range(A.factors.shape[0]):
+        factors = om.combo_factors(A, c)
+        for m in range(len(A.mem_rot)):
+            sel = np.nonzero(A.ml_member == m)[0]
+            if not len(sel):
+                continue
+            i, j = A.mem_ij[m]
+            pi, pj = np.ascontiguousarray(A.xyz[i]), np.ascontiguousarray(A.xyz[j])
+            kinds = np.ascontiguousarray(A.ml_kind[sel].astype(np.int32))
+            params = np.ascontiguousarray(A.ml_params[sel])
+            fac = np.array([factors.get(int(A.ml_case[k]), 0.0) for k in sel])
+            hh.hh_member_fer(_p(pi), _p(pj), _p(np.ascontiguousarray(A.mem_props[m])), ct.c_double(A.mem_rot[m]),
+                             ct.c_uint(int(A.mem_rel[m])), len(sel), kinds.ctypes.data_as(I32P), _p(params), _p(fac), _p(out))
+            expect = om.member_fer_local(A, m, factors).reshape(-1)
+            assert np.abs(out - expect).max() <= 1e-11*max(1.0, np.abs(expect).max()), (c, m)
+
+
+@pytest.mark.parametrize('name', ['quad_mesh_xy', 'plate_mesh_xz', 'skew_shell', 'mat_foundation'])
+def test_shell_fer(libs, name):
+    hh, _ = libs
+    A, ref, _ = load_fixture(name)
+    out = np.empty(24)
+    n = A.n_dof
+    for c in range(A.factors.shape[0]):
+        factors = om.combo_factors(A, c)
+        FER = np.zeros(n)
+        for conn, props, is_quad, el, cs, val in ((A.quad_ijmn, A.quad_props, 1, A.qp_elem, A.qp_case, A.qp_val),
+                                                  (A.plate_ijmn, A.plate_props, 0, A.pp_elem, A.pp_case, A.pp_val)):
+            for e in range(len(conn)):
+                p = sum(factors.get(int(cs[k]), 0.0)*val[k] for k in np.nonzero(el == e)[0])
+                pts = np.ascontiguousarray(A.xyz[conn[e]].reshape(-1))
+                hh.hh_shell_fer(_p(pts), _p(np.ascontiguousarray(props[e])), is_quad, ct.c_double(p), _p(out))
+                dofs = (6*conn[e][:, None] + np.arange(6)[None, :]).reshape(-1)
+                np.add.at(FER, dofs, out)
+        assert rel_err(FER, ref['FER'][c]) < 1e-12
+
+
+def _vertex_graph(K11, A, d1):
+    """Vertex graph of free DOFs grouped by node, as pn_direct_symbolic.cpp::build_vertex_graph builds it."""
+    node_of = np.asarray(d1)//6
+    nodes, vstart = np.unique(node_of, return_index=True)
+    vstart = np.append(vstart, len(d1)).astype(np.int32)
+    vid = -np.ones(A.n_nodes, dtype=np.int64)
+    vid[nodes] = np.arange(len(nodes))
+    C = K11.tocoo()
+    va, vb = vid[node_of[C.row]], vid[node_of[C.col]]
+    keep = va != vb
+    G = sps.coo_matrix((np.ones(keep.sum()), (va[keep], vb[keep])), shape=(len(nodes), len(nodes))).tocsr()
+    G = ((G + G.T) > 0).astype(np.int8).tocsr()
+    G.sort_indices()
+    coords = np.ascontiguousarray(A.xyz[nodes].reshape(-1))
+    return vstart, coords, G.indptr.astype(np.int64), G.indices.astype(np.int32)
+
+
+@pytest.mark.parametrize('name,leaf', [('quad_mesh_xy', 2), ('moment_frame', 3), ('mat_foundation', 4), ('mixed_building', 2),
+                                       ('plate_mesh_xz', 1), ('pdelta_frame', 5)])
+def test_direct_symbolic_host(libs, name, leaf):
+    _, dh = libs
+    A, ref, _ = load_fixture(name)
+    d1, d2, _ = om.partition_D(A)
+    K11 = sps.csr_matrix((ref['K11_data'], ref['K11_indices'], ref['K11_indptr']), shape=(len(d1), len(d1)))
+    vstart, coords, adj_ptr, adj = _vertex_graph(K11, A, d1)
+    s = 3
+    rng = np.random.default_rng(0)
+    B = np.ascontiguousarray(rng.standard_normal((len(d1), s)))
+    X = np.empty_like(B)
+    stats = np.zeros(8)
+    rc = dh.hh_direct_solve(ct.c_int64(len(d1)), K11.indptr.ctypes.data_as(I32P), K11.indices.ctypes.data_as(I32P),
+                            _p(np.ascontiguousarray(K11.data)), ct.c_int32(len(vstart) - 1),
+                            vstart.ctypes.data_as(I32P), _p(coords), adj_ptr.ctypes.data_as(I64P),
+                            adj.ctypes.data_as(I32P), leaf, s, _p(B), _p(X), _p(stats))
+    assert rc == 0
+    Xs = spla.splu(K11.tocsc()).solve(B)
+    assert rel_err(X, Xs) < 1e-8
+    assert stats[2] >= 1 and stats[4] >= 1
