@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the stiffness-assembly + linear-solve path (BASELINE.json metric: DOF*combos/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 3 -- a 500x500 DKMQ quad plate (1 506 006 DOF, 250 000 quads,
+CSR nnz 29 540 014) with 64 load combinations per GPU, synthetic data.
+
+One *step* = one pass of the hot path over that model: batched element stiffness -> COO->CSR scatter-add ->
+K11/K12/K21/K22 partition -> right-hand sides for all combos -> numeric factorisation -> multi-RHS solve with
+iterative refinement -> displacement merge.  `value` times steps with the model resident in HBM (topology
+dependent symbolic data -- pattern, scatter map, elimination tree -- built once before the timed region, as it
+is reused across re-analyses of one topology).  `e2e` times the whole call sequence a host caller makes
+through the C ABI with HOST buffers every step: upload of the SoA arrays, symbolic phase, assembly, solve,
+reactions, and the device->host copies of D and the reactions (pinned memory).
+
+Multi-GPU: load combinations are independent given K, so ranks own disjoint sets of 64 combos (weak scaling,
+no data-path collective; NCCL only for the barrier / max-over-ranks timing).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'assembly+solve throughput, 1.5M-DOF quad plate x 64 load combos per GPU'
+UNIT = 'DOF*combos/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=int, default=500, help='quads per side (500 = BASELINE config 3)')
+    ap.add_argument('--combos', type=int, default=64, help='load combinations per GPU')
+    ap.add_argument('--solver', default='direct', choices=['direct', 'pcg'])
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--cpu-n', type=int, default=96, help='quads per side of the CPU-baseline sample')
+    ap.add_argument('--cpu-combos', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    n = args.n
+    return {'workload': f'BASELINE config 3: {n}x{n} DKMQ quad plate, perimeter pinned, {args.combos} load combos per GPU',
+            'n_dof': 6*(n + 1)*(n + 1), 'n_quads': n*n, 'combos_per_gpu': args.combos,
+            'combos_total': args.combos*world, 'solver': args.solver,
+            'sharding': 'load combinations across GPUs, K assembled and factorised per GPU, no data-path collective',
+            'l2': 'inputs larger than L2 (CSR values 236 MB, factor 8.5 GB per step); no explicit flush',
+            'symbolic': 'pattern / scatter map / elimination tree built once outside the timed region for `value`, inside for `e2e`'}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (numpy element loops + scipy tocsr/SuperLU)
+# ---------------------------------------------------------------------------------------------
+def cpu_port_step(n, n_combos):
+    """One pass of the reference algorithm (restated in oracle/) on an n x n quad plate with n_combos combos.
+    Returns (units, seconds, phase dict).  Phases are the ones BASELINE.md section 3 lists."""
+    from oracle import model as om
+    from pynite_b200 import synthetic
+    from scipy.sparse.linalg import spsolve
+    A = synthetic.quad_plate_arrays(n=n, n_combos=n_combos)
+    ph = {}
+    t0 = time.perf_counter()
+    K = om.ke_csr(A)
+    ph['Ke+tocsr'] = time.perf_counter() - t0
+    t = time.perf_counter()
+    d1, d2, D2 = om.partition_D(A)
+    K11, K12, _, _ = om.partition_matrix(K, d1, d2)
+    ph['partition'] = time.perf_counter() - t
+    ph['FER+P'] = ph['spsolve'] = ph['reactions'] = 0.0
+    for c in range(n_combos):
+        t = time.perf_counter()
+        P, FER = om.load_vectors(A, c)
+        ph['FER+P'] += time.perf_counter() - t
+        t = time.perf_counter()
+        rhs = np.subtract(np.subtract(P[d1, :], FER[d1, :]), K12.tocsr() @ D2)
+        D1 = spsolve(K11.tocsr(), rhs)          # one full SuperLU factorisation per combo, as the reference does
+        ph['spsolve'] += time.perf_counter() - t
+        t = time.perf_counter()
+        D = om._merge(A, D1, D2, d1, d2)
+        om.reactions(A, c, D)
+        ph['reactions'] += time.perf_counter() - t
+    total = time.perf_counter() - t0
+    return A.n_dof*n_combos, total, {k: round(v, 3) for k, v in ph.items()}
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path.  /root/reference (pure Python) does
+    not exist on the GPU box, so this times the oracle port of it; every step is a bounded sample."""
+    if rank != 0:
+        return
+    cfg = workload_config(args, world)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port_step(max(8, args.cpu_n//4), 1)
+    t_all, units = 0.0, 0
+    phases = None
+    for _ in range(args.steps):
+        u, t, phases = cpu_port_step(args.cpu_n, args.cpu_combos)
+        units += u
+        t_all += t
+    value = units/t_all
+    sample = (f'{args.cpu_n}x{args.cpu_n} quad plate ({6*(args.cpu_n + 1)**2} DOF) x {args.cpu_combos} combos per step: numpy element '
+              f'loops + scipy coo->csr + SuperLU spsolve per combo + reactions; phases of last step (s): {phases}')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3*t_all/args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for row in self.rows:
+            f = [x.strip() for x in row.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measure_fp64_gemm_peak(torch, dev):
+    """cuBLAS DGEMM burst on this GPU: the denominator for the FP64 dense kernels (MEASURED_PEAKS.json only holds
+    the HBM copy and the bf16 GEMM).  4096^3, best of 5, CUDA events on torch's stream."""
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2*4096**3/(best*1e-3)/1e12
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'MEASURED_PEAKS.json'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from pynite_b200 import synthetic
+    from pynite_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # every rank owns its own 64 combos of the same mesh (rank-specific factor table and point loads)
+    A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019 + rank)
+    eng = Engine(local_rank)
+    opts = eng.make_opts(solver=args.solver, check_stability=True, refine_steps=2, tol=1e-10, max_iter=500000)
+    units_per_step = A.n_dof*args.combos
+
+    # ---- device-resident arm -----------------------------------------------------------------
+    eng.set_model(A)
+    eng.set_loads(A)
+    eng.set_combos(A.factors)
+    sizes = eng.symbolic(0)
+    eng.assemble_ke()
+    eng.solve_linear(opts, reactions=False, download=False)          # builds the elimination tree (once per topology)
+    first_stats = eng.stats().as_dict()
+
+    def step():
+        eng.assemble_ke()
+        eng.solve_linear(opts, reactions=False, download=False)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    eng.reset_stats()
+    eng.profile_enable(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    eng.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = eng.timer_stop()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    prof = eng.profile()
+    eng.profile_enable(False)
+    st = eng.stats().as_dict()
+    ms = max_over_ranks(ms)
+    value = units_per_step*world*args.steps/(ms*1e-3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out, everything inside the timed region ---
+    n_dof = A.n_dof
+    D_host = torch.empty((args.combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
+    R_host = torch.empty((args.combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
+    in_fields = ['xyz', 'support', 'enf_mask', 'enf_val', 'nspring_k', 'nspring_flag', 'quad_ijmn', 'quad_props', 'nl_dof',
+                 'nl_case', 'nl_val', 'qp_elem', 'qp_case', 'qp_val', 'factors']
+    h2d = int(sum(np.asarray(getattr(A, f)).nbytes for f in in_fields))
+    d2h = int(D_host.nbytes + R_host.nbytes)
+
+    def e2e_step():
+        eng.set_model(A)
+        eng.set_loads(A)
+        eng.set_combos(A.factors)
+        eng.symbolic(0)
+        eng.assemble_ke()
+        eng.solve_linear(opts, reactions=True, D_out=D_host, R_out=R_host)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = units_per_step*world*args.e2e_steps/t_e2e
+    e2e_stats = eng.stats().as_dict()
+    checksum = float(np.abs(D_host).max())
+
+    # ---- per-kernel breakdown and rooflines ---------------------------------------------------------
+    hbm_peak, hbm_src = load_peaks()
+    f64_peak = measure_fp64_gemm_peak(torch, dev)
+    K = args.steps
+    total_kernel_ms = sum(v[0] for v in prof.values())
+    kern = {}
+    for name, (kms, n) in prof.items():
+        kern[name] = {'ms_per_step': kms/K, 'launches_per_step': n/K, 'share_of_kernel_time': kms/total_kernel_ms}
+    asm_bytes = A.quad_ijmn.shape[0]*152 + sizes.nnz_csr*8                     # 152 B per quad + 8 B per stored entry
+    asm_ms = (prof.get('element_ke', (0, 0))[0] + prof.get('scatter_add', (0, 0))[0])/K
+    rooflines = {}
+    if asm_ms > 0:
+        a = asm_bytes/(asm_ms*1e-3)/1e9
+        rooflines['assembly(element_ke+scatter_add)'] = {'bound': 'hbm', 'achieved': a, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': a/hbm_peak,
+                                                         'algorithmic_bytes': asm_bytes, 'ms': asm_ms}
+    if 'spmm' in prof:
+        s = args.combos
+        spmm_bytes = sizes.nnz11*12 + (sizes.n1 + 1)*4 + 2*sizes.n1*s*8
+        kms, n = prof['spmm']
+        a = spmm_bytes/(kms/n*1e-3)/1e9
+        rooflines['spmm(K11, %d rhs)' % s] = {'bound': 'hbm', 'achieved': a, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': a/hbm_peak,
+                                              'algorithmic_bytes': spmm_bytes, 'ms': kms/n}
+    if 'lu_update' in prof and first_stats.get('update_flops', 0) > 0:
+        kms, n = prof['lu_update']
+        a = first_stats['update_flops']*K/(kms*1e-3)/1e12
+        rooflines['lu_update(FP64 trailing GEMM)'] = {'bound': 'tensor', 'achieved': a, 'peak': f64_peak, 'unit': 'TFLOP/s', 'frac': a/f64_peak,
+                                                      'flops_per_step': first_stats['update_flops'], 'ms': kms/K,
+                                                      'peak_source': 'cuBLAS DGEMM 4096^3 burst measured in this run (FP64 is not in MEASURED_PEAKS.json)'}
+    if 'solve_update' in prof and first_stats.get('solve_flops', 0) > 0:
+        kms, n = prof['solve_update']
+        sweeps = 1 + opts.refine_steps
+        fl = first_stats['solve_flops']*args.combos*sweeps
+        a = fl*K/(kms*1e-3)/1e12
+        rooflines['solve_update(FP64 panel GEMM, %d rhs)' % args.combos] = {
+            'bound': 'tensor', 'achieved': a, 'peak': f64_peak, 'unit': 'TFLOP/s', 'frac': a/f64_peak, 'flops_per_step': fl, 'ms': kms/K,
+            'peak_source': 'cuBLAS DGEMM 4096^3 burst measured in this run'}
+    dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+    dom_key = next((k for k in rooflines if k.startswith(dominant or '~')), None)
+    if dom_key is None and rooflines:
+        dom_key = max(rooflines, key=lambda k: rooflines[k]['ms'])
+    roof = dict(rooflines[dom_key]) if dom_key else None
+    if roof is not None:
+        roof['kernel'] = dom_key
+        roof['traffic'] = None
+        roof['peak_is'] = ('measured (' + hbm_src + ')') if roof['bound'] == 'hbm' else roof.get('peak_source')
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms/args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(args, world),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': 1e3*t_e2e/args.e2e_steps, 'steps': args.e2e_steps,
+                    'includes': 'pn_set_* uploads, symbolic phase, elimination-tree analysis, assembly, solve, reactions, D and Rxn copies to pinned host memory'},
+            'gpu_launches': int(st['kernel_launches']), 'clocks': clocks,
+            'roofline': roof, 'rooflines': rooflines, 'kernels': kern,
+            'phases_ms_per_step': {k: st[k]/K for k in ('ms_elements', 'ms_scatter', 'ms_partition', 'ms_rhs', 'ms_factor', 'ms_solve')},
+            'solver_stats': {'factor_nnz': first_stats['factor_nnz'], 'factor_flops': first_stats['factor_flops'],
+                             'max_rel_residual': e2e_stats['max_rel_residual'], 'refine_steps': opts.refine_steps,
+                             'fp64_gemm_peak_tflops_measured': f64_peak},
+            'sizes': {'n_dof': int(sizes.n_dof), 'n1': int(sizes.n1), 'nnz_coo': int(sizes.nnz_coo), 'nnz_csr': int(sizes.nnz_csr),
+                      'nnz11': int(sizes.nnz11)},
+            'checksum_max_abs_D': checksum}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
+    if world == 1 and not args.no_cpu_baseline:
+        u, t, phases = cpu_port_step(args.cpu_n, args.cpu_combos)
+        line['cpu_baseline'] = {'value': u/t, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                                'sample': (f'{args.cpu_n}x{args.cpu_n} quad plate ({6*(args.cpu_n + 1)**2} DOF) x {args.cpu_combos} combos, {t:.1f} s: '
+                                           f'oracle port of the reference (numpy element loops, scipy coo->csr, SuperLU spsolve per combo, '
+                                           f'reactions); phases (s): {phases}; host cores visible: {os.cpu_count()}')}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -84,6 +84,8 @@ typedef struct pn_stats {
     double max_rel_residual; /* max over combos of ||K11 x - b|| / ||b||                            */
     int64_t factor_nnz;      /* stored entries of the direct factor                                */
     double factor_flops;
+    double update_flops;     /* flops of the trailing-matrix updates alone (2 bs rest^2 per block step)    */
+    double solve_flops;      /* flops of one forward+backward sweep for ONE right-hand side               */
 } pn_stats;
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
@@ -176,6 +178,16 @@ PN_EXPORT int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t lo
 PN_EXPORT int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repeat, double *ms_out);
 PN_EXPORT int pn_get_stats(pn_ctx *ctx, pn_stats *out);
 PN_EXPORT int pn_reset_stats(pn_ctx *ctx);
+/* Device time of a host-chosen region on the library's stream (CUDA events): start synchronises the stream
+ * and records, stop records, waits and returns the elapsed milliseconds.                              */
+PN_EXPORT int pn_timer_start(pn_ctx *ctx);
+PN_EXPORT int pn_timer_stop(pn_ctx *ctx, double *ms_out);
+/* Per-kernel timing: when enabled, every launch of the main kernels is bracketed by CUDA events on the
+ * library's stream; pn_profile_get returns the summed device time and launch count of one kernel slot.
+ * pn_profile_slot_name(slot) returns NULL past the last slot.                                          */
+PN_EXPORT int pn_profile_enable(pn_ctx *ctx, int on);
+PN_EXPORT int pn_profile_get(pn_ctx *ctx, int slot, double *ms, int64_t *launches);
+PN_EXPORT const char *pn_profile_slot_name(int slot);
 
 #ifdef __cplusplus
 }

@@ -168,9 +168,22 @@ def partition_matrix(K, d1, d2):
 
 
 # ---- loads -------------------------------------------------------------------------------------
+def _index_by(A, field):
+    """{element: [positions]} for a load table, built once per array object (keeps the element loops linear)."""
+    cache = A.__dict__.setdefault('_oracle_index', {})
+    arr = getattr(A, field)
+    hit = cache.get(field)
+    if hit is None or hit[0] is not arr:
+        table = {}
+        for k, e in enumerate(arr.tolist()):
+            table.setdefault(e, []).append(k)
+        cache[field] = hit = (arr, table)
+    return hit[1]
+
+
 def _member_loads(A, m):
     pts, dists = [], []
-    for k in np.nonzero(A.ml_member == m)[0]:
+    for k in _index_by(A, 'ml_member').get(m, ()):
         kind = int(A.ml_kind[k])
         p = A.ml_params[k]
         if kind < 12:
@@ -189,23 +202,24 @@ def member_fer_local(A, m, factors):
     return el.condense_vector(el.member_ke_unc(E, G, Ar, Iy, Iz, J, L), fu, rel)
 
 
-def _pressure(elem_ids, case_ids, vals, e, factors):
+def _pressure(A, field, case_ids, vals, e, factors):
     p = 0
+    rows = _index_by(A, field).get(e, ())
     for case, factor in factors.items():
-        for k in np.nonzero(elem_ids == e)[0]:
+        for k in rows:
             if int(case_ids[k]) == case:
                 p += factor*vals[k]
     return p
 
 
 def quad_fer_local(A, q, factors):
-    p = _pressure(A.qp_elem, A.qp_case, A.qp_val, q, factors)
+    p = _pressure(A, 'qp_elem', A.qp_case, A.qp_val, q, factors)
     pts = [A.xyz[k] for k in A.quad_ijmn[q]]
     return el.quad_fer(pts[0], pts[1], pts[2], pts[3], p)
 
 
 def plate_fer_local(A, e, factors):
-    p = _pressure(A.pp_elem, A.pp_case, A.pp_val, e, factors)
+    p = _pressure(A, 'pp_elem', A.pp_case, A.pp_val, e, factors)
     pts = [A.xyz[k] for k in A.plate_ijmn[e]]
     w = float(((pts[0] - pts[1])**2).sum()**0.5)
     h = float(((pts[0] - pts[3])**2).sum()**0.5)
@@ -227,15 +241,15 @@ def load_vectors(A, c):
             P[A.nl_dof[k], 0] += f*A.nl_val[k]
     FER = np.zeros((n, 1))
     for m in range(len(A.mem_rot)):
-        if np.any(A.ml_member == m):
+        if m in _index_by(A, 'ml_member'):
             T = el.block_diag_T(member_geometry(A, m)[1], 4)
             FER[_dofs(*A.mem_ij[m]), 0] += (np.linalg.inv(T) @ member_fer_local(A, m, factors)).reshape(-1)
     for e in range(len(A.plate_ijmn)):
-        if np.any(A.pp_elem == e):
+        if e in _index_by(A, 'pp_elem'):
             T = plate_Ke(A, e)[1]
             FER[_dofs(*A.plate_ijmn[e]), 0] += (np.linalg.inv(T) @ plate_fer_local(A, e, factors)).reshape(-1)
     for q in range(len(A.quad_ijmn)):
-        if np.any(A.qp_elem == q):
+        if q in _index_by(A, 'qp_elem'):
             T = quad_Ke(A, q)[1]
             FER[_dofs(*A.quad_ijmn[q]), 0] += (np.linalg.inv(T) @ quad_fer_local(A, q, factors)).reshape(-1)
     return P, FER

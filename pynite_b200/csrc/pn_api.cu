@@ -232,6 +232,22 @@ void solve_linear_all(Ctx *c, const pn_solve_opts &o) {
 
 }  // namespace
 
+namespace pn {
+void prof_flush(Ctx *c) {
+    Profiler &p = c->prof;
+    if (p.recs.empty()) { p.used = 0; return; }
+    cudaStreamSynchronize(c->stream);
+    for (const Profiler::Rec &r : p.recs) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.pool[r.e0], p.pool[r.e1]);
+        p.ms[r.slot] += ms;
+        p.n[r.slot] += 1;
+    }
+    p.recs.clear();
+    p.used = 0;
+}
+}  // namespace pn
+
 extern "C" {
 
 const char *pn_version(void) { return "pynite_b200 0.1 (sm_100a)"; }
@@ -264,6 +280,9 @@ void pn_destroy(pn_ctx *ctx) {
     pcg_release(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tm0) cudaEventDestroy(c->tm0);
+    if (c->tm1) cudaEventDestroy(c->tm1);
+    for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
     cudaStream_t st = c->stream;
     delete c;
     if (st) cudaStreamDestroy(st);
@@ -753,20 +772,18 @@ int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32
     cudaStream_t st = c->stream;
     build_incidence(c);
     ensure_loads(c);
-    combine_fer(c, combo);
     const double *D = c->D_all.ptr + (int64_t)combo * c->n_dof;
     int64_t off, cnt;
-    const double *fer = nullptr;
     switch (kind) {
     case PN_SPRING: off = c->ef_off_spring; cnt = 12 * m.n_springs; break;
-    case PN_MEMBER: off = c->ef_off_member; cnt = 12 * m.n_members; fer = c->fer_combo.ptr + off; break;
-    case PN_QUAD: off = c->ef_off_quad; cnt = 24 * m.n_quads; fer = c->fer_combo.ptr + off; break;
-    case PN_PLATE: off = c->ef_off_plate; cnt = 24 * m.n_plates; fer = c->fer_combo.ptr + off; break;
+    case PN_MEMBER: off = c->ef_off_member; cnt = 12 * m.n_members; break;
+    case PN_QUAD: off = c->ef_off_quad; cnt = 24 * m.n_quads; break;
+    case PN_PLATE: off = c->ef_off_plate; cnt = 24 * m.n_plates; break;
     default: throw ArgError("pn_element_forces: unknown element kind");
     }
     double *F = c->ef.ptr + off;
-    launch_element_forces(c, kind, D, fer, F, st);
-    if (kind == PN_MEMBER && pdelta) launch_member_pdelta_forces(c, D, F, st);
+    launch_element_forces(c, kind, D, combo, false, F, st);
+    if (kind == PN_MEMBER && pdelta) launch_member_pdelta_forces(c, D, false, F, st);
     if (local) launch_forces_to_local(c, kind, F, st);
     if (cnt) PN_CUDA(cudaMemcpyAsync(out, F, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
@@ -807,6 +824,49 @@ int pn_get_stats(pn_ctx *ctx, pn_stats *out) {
     if (!out) throw ArgError("pn_get_stats: null output");
     c->stats.kernel_launches = c->launches;
     *out = c->stats;
+    PN_API_END
+}
+
+static const char *kSlotNames[PS_COUNT] = {
+    "element_ke", "scatter_add", "gather_blocks", "build_rhs", "spmm", "front_assemble", "extend_add", "lu_diag",
+    "lu_panels", "lu_update", "copy_factors", "solve_gather_store", "solve_diag", "solve_update", "solve_misc",
+    "reactions", "pcg_vector", "merge_displacements"};
+
+const char *pn_profile_slot_name(int slot) { return (slot >= 0 && slot < PS_COUNT) ? kSlotNames[slot] : nullptr; }
+
+int pn_profile_enable(pn_ctx *ctx, int on) {
+    PN_API_BEGIN(ctx)
+    prof_flush(c);
+    for (int i = 0; i < PS_COUNT; ++i) { c->prof.ms[i] = 0; c->prof.n[i] = 0; }
+    c->prof.on = on != 0;
+    PN_API_END
+}
+
+int pn_profile_get(pn_ctx *ctx, int slot, double *ms, int64_t *launches) {
+    PN_API_BEGIN(ctx)
+    if (slot < 0 || slot >= PS_COUNT) throw ArgError("pn_profile_get: bad slot");
+    prof_flush(c);
+    if (ms) *ms = c->prof.ms[slot];
+    if (launches) *launches = c->prof.n[slot];
+    PN_API_END
+}
+
+int pn_timer_start(pn_ctx *ctx) {
+    PN_API_BEGIN(ctx)
+    if (!c->tm0) { PN_CUDA(cudaEventCreate(&c->tm0)); PN_CUDA(cudaEventCreate(&c->tm1)); }
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_CUDA(cudaEventRecord(c->tm0, c->stream));
+    PN_API_END
+}
+
+int pn_timer_stop(pn_ctx *ctx, double *ms_out) {
+    PN_API_BEGIN(ctx)
+    if (!c->tm0) throw ArgError("pn_timer_stop: pn_timer_start was not called");
+    PN_CUDA(cudaEventRecord(c->tm1, c->stream));
+    PN_CUDA(cudaEventSynchronize(c->tm1));
+    float ms = 0;
+    PN_CUDA(cudaEventElapsedTime(&ms, c->tm0, c->tm1));
+    if (ms_out) *ms_out = ms;
     PN_API_END
 }
 

@@ -472,6 +472,16 @@ static void analyse(Ctx *c) {
     d.analysed = true;
     c->stats.factor_nnz = S.factor_entries;
     c->stats.factor_flops = S.factor_flops;
+    double upd = 0.0;
+    for (const FrontSym &fs : S.fronts) {
+        int64_t n = fs.ns + fs.nb;
+        for (int kb = 0; kb < fs.ns; kb += NB) {
+            double bs = std::min(NB, fs.ns - kb), rest = (double)(n - kb) - bs;
+            upd += 2.0 * bs * rest * rest;
+        }
+    }
+    c->stats.update_flops = upd;
+    c->stats.solve_flops = 2.0 * (double)S.factor_entries;
 }
 
 static void factorise(Ctx *c, const double *vals11) {
@@ -484,35 +494,35 @@ static void factorise(Ctx *c, const double *vals11) {
         if (!nfl) continue;
         double *arena = d.arena[l & 1].ptr;
         PN_CUDA(cudaMemsetAsync(arena, 0, sizeof(double) * d.level_f_total[l], st));
-        k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
-                                                                  d.fronts.ptr, vals11, arena);
+        { ProfScope ps_(c, PS_FRONT_ASSEMBLE); k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
+                                                                  d.fronts.ptr, vals11, arena); }
         c->count_launch();
         if (l > 0) {
             int cfirst = d.level_ptr[l - 1], ncl = d.level_ptr[l] - cfirst;
             int64_t nbmax = d.level_max_nb[l - 1];
             unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((nbmax * nbmax + 255) / 256, 1), 1024);
             for (int r = 0; r < d.level_max_children[l - 1]; ++r) {
-                k_extend_add<<<dim3(ncl, gy), 256, 0, st>>>(cfirst, ncl, r, d.fronts.ptr, d.rel.ptr, d.arena[(l - 1) & 1].ptr,
-                                                             arena);
+                { ProfScope ps_(c, PS_EXTEND_ADD); k_extend_add<<<dim3(ncl, gy), 256, 0, st>>>(cfirst, ncl, r, d.fronts.ptr, d.rel.ptr, d.arena[(l - 1) & 1].ptr,
+                                                             arena); }
                 c->count_launch();
             }
         }
         int maxns = d.level_max_ns[l], maxn = d.level_max_n[l];
         for (int kb = 0; kb < maxns; kb += NB) {
-            k_lu_diag<<<nfl, 256, 0, st>>>(first, kb, d.fronts.ptr, arena, d.status.ptr);
+            { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 256, 0, st>>>(first, kb, d.fronts.ptr, arena, d.status.ptr); }
             int rest = maxn - kb - 1;
             if (rest > 0) {
                 int tiles = (rest + 127) / 128;
-                k_lu_panels<<<dim3(nfl, 2 * tiles), 128, 0, st>>>(first, kb, tiles, d.fronts.ptr, arena);
+                { ProfScope ps_(c, PS_LU_PANELS); k_lu_panels<<<dim3(nfl, 2 * tiles), 128, 0, st>>>(first, kb, tiles, d.fronts.ptr, arena); }
                 int gt = (rest + TILE - 1) / TILE;
-                k_lu_update<<<dim3(nfl, gt, gt), 256, 0, st>>>(first, kb, d.fronts.ptr, arena);
+                { ProfScope ps_(c, PS_LU_UPDATE); k_lu_update<<<dim3(nfl, gt, gt), 256, 0, st>>>(first, kb, d.fronts.ptr, arena); }
                 c->count_launch(2);
             }
             c->count_launch();
         }
         int64_t per = (int64_t)maxn * std::max(maxns, 1) * 2;
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((per + 255) / 256, 1), 2048);
-        k_copy_factors<<<dim3(nfl, gy), 256, 0, st>>>(first, d.fronts.ptr, arena, d.L.ptr, d.U.ptr);
+        { ProfScope ps_(c, PS_COPY_FACTORS); k_copy_factors<<<dim3(nfl, gy), 256, 0, st>>>(first, d.fronts.ptr, arena, d.L.ptr, d.U.ptr); }
         c->count_launch();
     }
     int status = 0;
@@ -541,29 +551,29 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
-        k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr.ptr, d.fidx.ptr, X, W);
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr.ptr, d.fidx.ptr, X, W); }
         c->count_launch();
         if (l > 0) {
             int cfirst = d.level_ptr[l - 1], ncl = d.level_ptr[l] - cfirst;
             unsigned gyc = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)d.level_max_nb[l - 1] * s + 255) / 256, 1), 1024);
             for (int r = 0; r < d.level_max_children[l - 1]; ++r) {
-                k_solve_extend_add<<<dim3(ncl, gyc), 256, 0, st>>>(cfirst, ncl, r, s, fr.ptr, d.rel.ptr,
-                                                                    d.warena[(l - 1) & 1].ptr, W);
+                { ProfScope ps_(c, PS_SOLVE_MISC); k_solve_extend_add<<<dim3(ncl, gyc), 256, 0, st>>>(cfirst, ncl, r, s, fr.ptr, d.rel.ptr,
+                                                                    d.warena[(l - 1) & 1].ptr, W); }
                 c->count_launch();
             }
         }
         for (int kb = 0; kb < maxns; kb += NB) {
-            k_solve_diag<<<dim3(nfl, (s + 127) / 128), 128, 0, st>>>(first, kb, s, 0, fr.ptr, d.L.ptr, W);
+            { ProfScope ps_(c, PS_SOLVE_DIAG); k_solve_diag<<<dim3(nfl, (s + 127) / 128), 128, 0, st>>>(first, kb, s, 0, fr.ptr, d.L.ptr, W); }
             int rest = maxn - kb - 1;
             if (rest > 0) {
-                k_solve_update<<<dim3(nfl, (rest + TILE - 1) / TILE, gz), 256, 0, st>>>(first, kb, s, 0, fr.ptr, d.L.ptr,
-                                                                                        d.U.ptr, W);
+                { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_update<<<dim3(nfl, (rest + TILE - 1) / TILE, gz), 256, 0, st>>>(first, kb, s, 0, fr.ptr, d.L.ptr,
+                                                                                        d.U.ptr, W); }
                 c->count_launch();
             }
             c->count_launch();
         }
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
-        k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr.ptr, d.fidx.ptr, W, X);
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr.ptr, d.fidx.ptr, W, X); }
         c->count_launch();
     }
     // backward sweep
@@ -573,23 +583,23 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
-        k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 1, fr.ptr, d.fidx.ptr, X, W);
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 1, fr.ptr, d.fidx.ptr, X, W); }
         c->count_launch();
         if (d.level_max_nb[l] > 0) {
-            k_solve_update<<<dim3(nfl, (maxns + TILE - 1) / TILE, gz), 256, 0, st>>>(first, 0, s, 2, fr.ptr, d.L.ptr, d.U.ptr, W);
+            { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_update<<<dim3(nfl, (maxns + TILE - 1) / TILE, gz), 256, 0, st>>>(first, 0, s, 2, fr.ptr, d.L.ptr, d.U.ptr, W); }
             c->count_launch();
         }
         int last_kb = ((maxns - 1) / NB) * NB;
         for (int kb = last_kb; kb >= 0; kb -= NB) {
-            k_solve_diag<<<dim3(nfl, (s + 127) / 128), 128, 0, st>>>(first, kb, s, 1, fr.ptr, d.L.ptr, W);
+            { ProfScope ps_(c, PS_SOLVE_DIAG); k_solve_diag<<<dim3(nfl, (s + 127) / 128), 128, 0, st>>>(first, kb, s, 1, fr.ptr, d.L.ptr, W); }
             c->count_launch();
             if (kb > 0) {
-                k_solve_update<<<dim3(nfl, (kb + TILE - 1) / TILE, gz), 256, 0, st>>>(first, kb, s, 1, fr.ptr, d.L.ptr, d.U.ptr, W);
+                { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_update<<<dim3(nfl, (kb + TILE - 1) / TILE, gz), 256, 0, st>>>(first, kb, s, 1, fr.ptr, d.L.ptr, d.U.ptr, W); }
                 c->count_launch();
             }
         }
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
-        k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr.ptr, d.fidx.ptr, W, X);
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr.ptr, d.fidx.ptr, W, X); }
         c->count_launch();
     }
     PN_CUDA(cudaStreamSynchronize(st));
@@ -637,9 +647,9 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
         for (int it = 0; it < refine; ++it) {
             spmm(c, c->blk[0], vals11, c->X.ptr, AX.ptr, s, st);
             c->stats.spmm_launches += 1;
-            k_residual<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, c->B.ptr, AX.ptr, R.ptr);
+            { ProfScope ps_(c, PS_SOLVE_MISC); k_residual<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, c->B.ptr, AX.ptr, R.ptr); }
             solve_inplace(c, R.ptr, s);
-            k_axpy1<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, R.ptr, c->X.ptr);
+            { ProfScope ps_(c, PS_SOLVE_MISC); k_axpy1<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, R.ptr, c->X.ptr); }
             c->count_launch(2);
             c->stats.iterations += 1;
         }
@@ -658,9 +668,9 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
             solve_inplace(c, d.col_out.ptr, 1);
             for (int it = 0; it < refine; ++it) {
                 spmm(c, A, vj, d.col_out.ptr, ax.ptr, 1, st);
-                k_residual<<<grid_for(n1, 256), 256, 0, st>>>(n1, d.col_in.ptr, ax.ptr, ax.ptr);
+                { ProfScope ps_(c, PS_SOLVE_MISC); k_residual<<<grid_for(n1, 256), 256, 0, st>>>(n1, d.col_in.ptr, ax.ptr, ax.ptr); }
                 solve_inplace(c, ax.ptr, 1);
-                k_axpy1<<<grid_for(n1, 256), 256, 0, st>>>(n1, ax.ptr, d.col_out.ptr);
+                { ProfScope ps_(c, PS_SOLVE_MISC); k_axpy1<<<grid_for(n1, 256), 256, 0, st>>>(n1, ax.ptr, d.col_out.ptr); }
                 c->count_launch(2);
             }
             k_set_col<<<grid_for(n1, 256), 256, 0, st>>>(n1, s, j, d.col_out.ptr, c->X.ptr);

@@ -254,14 +254,17 @@ __global__ void k_member_fer_to_global(int64_t n_groups, const int32_t *__restri
 // In local axes f = T F.  `fer` may be null (no loads on this element type).
 // ------------------------------------------------------------------------------------------------
 template <int ND>
-__global__ void k_element_forces(int64_t n, const int32_t *__restrict__ conn, const double *__restrict__ ke,
-                                 const double *__restrict__ D, const double *__restrict__ fer /* [n][ND] or null */,
+__global__ void k_element_forces(int64_t n, const int32_t *__restrict__ list /* element ids or null = all */,
+                                 const int32_t *__restrict__ conn, const double *__restrict__ ke,
+                                 const double *__restrict__ D, const double *__restrict__ fer_case /* or null */,
+                                 int n_case, const double *__restrict__ fac_row, int64_t case_stride,
                                  const uint8_t *__restrict__ active, double *__restrict__ out) {
-    // one warp per element row-block: thread = (element, row)
+    // thread = (element, row); the fixed-end term is combined from the per-case vectors on the fly
     int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t e = tid / ND;
+    int64_t q = tid / ND;
     int r = (int)(tid % ND);
-    if (e >= n) return;
+    if (q >= n) return;
+    int64_t e = list ? list[q] : q;
     constexpr int NN = ND / 6;
     if (active && !active[e]) { out[e * ND + r] = 0.0; return; }
     const double *row = ke + e * (int64_t)(ND * ND) + (int64_t)r * ND;
@@ -272,7 +275,11 @@ __global__ void k_element_forces(int64_t n, const int32_t *__restrict__ conn, co
 #pragma unroll
         for (int k = 0; k < 6; ++k) acc = fma(row[6 * a + k], D[6 * nd + k], acc);
     }
-    if (fer) acc += fer[e * ND + r];
+    if (fer_case) {
+        double f = 0.0;
+        for (int cs = 0; cs < n_case; ++cs) f = fma(fac_row[cs], fer_case[(int64_t)cs * case_stride + e * ND + r], f);
+        acc += f;
+    }
     out[e * ND + r] = acc;
 }
 
@@ -280,9 +287,11 @@ __global__ void k_element_forces(int64_t n, const int32_t *__restrict__ conn, co
 __global__ void k_member_pdelta_forces(int64_t n, const int32_t *__restrict__ ij, const double *__restrict__ props,
                                        const double *__restrict__ rot, const uint16_t *__restrict__ rel,
                                        const double *__restrict__ xyz, const double *__restrict__ D,
-                                       const uint8_t *__restrict__ active, double *__restrict__ F) {
-    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= n) return;
+                                       const uint8_t *__restrict__ active, const int32_t *__restrict__ list,
+                                       double *__restrict__ F) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int64_t e = list ? list[q] : q;
     if (active && !active[e]) return;
     int i = ij[2 * e], j = ij[2 * e + 1];
     double pi[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
@@ -349,26 +358,26 @@ void launch_element_ke(Ctx *c, cudaStream_t st) {
     const Model &m = c->model;
     double *ev = c->ev.ptr;
     if (m.n_springs) {
-        k_spring_ke<<<grid_for(m.n_springs, 64), 64, 0, st>>>(m.n_springs, m.spring_ij.ptr, m.spring_ks.ptr,
-                                                               m.xyz.ptr, ev + c->ev_off_spring);
+        { ProfScope ps_(c, PS_ELEM_KE); k_spring_ke<<<grid_for(m.n_springs, 64), 64, 0, st>>>(m.n_springs, m.spring_ij.ptr, m.spring_ks.ptr,
+                                                               m.xyz.ptr, ev + c->ev_off_spring); }
         c->count_launch();
     }
     if (m.n_members) {
-        k_member_matrix<<<grid_for(m.n_members, 64), 64, 0, st>>>(m.n_members, m.mem_ij.ptr, m.mem_props.ptr,
+        { ProfScope ps_(c, PS_ELEM_KE); k_member_matrix<<<grid_for(m.n_members, 64), 64, 0, st>>>(m.n_members, m.mem_ij.ptr, m.mem_props.ptr,
                                                                    m.mem_rot.ptr, m.mem_rel.ptr, m.xyz.ptr, 0, nullptr,
-                                                                   ev + c->ev_off_member);
+                                                                   ev + c->ev_off_member); }
         c->count_launch();
     }
     if (m.n_quads) {
-        k_shell_ke<true><<<grid_for(m.n_quads, SHELL_EPB), SHELL_TPB, 0, st>>>(m.n_quads, m.quad_ijmn.ptr,
+        { ProfScope ps_(c, PS_ELEM_KE); k_shell_ke<true><<<grid_for(m.n_quads, SHELL_EPB), SHELL_TPB, 0, st>>>(m.n_quads, m.quad_ijmn.ptr,
                                                                                 m.quad_props.ptr, m.xyz.ptr,
-                                                                                ev + c->ev_off_quad);
+                                                                                ev + c->ev_off_quad); }
         c->count_launch();
     }
     if (m.n_plates) {
-        k_shell_ke<false><<<grid_for(m.n_plates, SHELL_EPB), SHELL_TPB, 0, st>>>(m.n_plates, m.plate_ijmn.ptr,
+        { ProfScope ps_(c, PS_ELEM_KE); k_shell_ke<false><<<grid_for(m.n_plates, SHELL_EPB), SHELL_TPB, 0, st>>>(m.n_plates, m.plate_ijmn.ptr,
                                                                                   m.plate_props.ptr, m.xyz.ptr,
-                                                                                  ev + c->ev_off_plate);
+                                                                                  ev + c->ev_off_plate); }
         c->count_launch();
     }
 }
@@ -414,48 +423,69 @@ void launch_shell_fer(Ctx *c, bool quad, const double *pressure_dev, double *out
     c->count_launch();
 }
 
-void launch_element_forces(Ctx *c, int kind, const double *D_dev, const double *fer_dev, double *out_dev,
+// combo: fixed-end vectors are combined with that combo's factors; supported_only restricts the work to the
+// elements that touch a supported node (all that Analysis._calc_reactions :1081-1267 needs).
+void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo, bool supported_only, double *out_dev,
                            cudaStream_t st) {
     const Model &m = c->model;
+    const Loads &ld = c->loads;
     const double *ev = c->ev.ptr;
+    const double *fac = ld.factors.ptr + (int64_t)combo * ld.n_case;
+    const double *ferc = ld.fer_case.n ? ld.fer_case.ptr : nullptr;
+    int k = kind - 1;
+    const int32_t *list = supported_only ? c->sup_list[k].ptr : nullptr;
+    ProfScope ps_(c, PS_REACTIONS);
     switch (kind) {
-    case PN_SPRING:
-        if (m.n_springs) {
-            k_element_forces<12><<<grid_for(m.n_springs * 12, 96), 96, 0, st>>>(
-                m.n_springs, m.spring_ij.ptr, ev + c->ev_off_spring, D_dev, nullptr, m.spring_active.ptr, out_dev);
-            c->count_launch();
-        }
-        break;
-    case PN_MEMBER:
-        if (m.n_members) {
-            k_element_forces<12><<<grid_for(m.n_members * 12, 96), 96, 0, st>>>(
-                m.n_members, m.mem_ij.ptr, ev + c->ev_off_member, D_dev, fer_dev, m.mem_active.ptr, out_dev);
-            c->count_launch();
-        }
-        break;
-    case PN_QUAD:
-        if (m.n_quads) {
-            k_element_forces<24><<<grid_for(m.n_quads * 24, 96), 96, 0, st>>>(
-                m.n_quads, m.quad_ijmn.ptr, ev + c->ev_off_quad, D_dev, fer_dev, nullptr, out_dev);
-            c->count_launch();
-        }
-        break;
-    case PN_PLATE:
-        if (m.n_plates) {
-            k_element_forces<24><<<grid_for(m.n_plates * 24, 96), 96, 0, st>>>(
-                m.n_plates, m.plate_ijmn.ptr, ev + c->ev_off_plate, D_dev, fer_dev, nullptr, out_dev);
+    case PN_SPRING: {
+        int64_t n = supported_only ? c->sup_list[k].n : m.n_springs;
+        if (n) {
+            k_element_forces<12><<<grid_for(n * 12, 96), 96, 0, st>>>(n, list, m.spring_ij.ptr, ev + c->ev_off_spring, D_dev,
+                                                                       nullptr, 0, fac, 0, m.spring_active.ptr, out_dev);
             c->count_launch();
         }
         break;
     }
+    case PN_MEMBER: {
+        int64_t n = supported_only ? c->sup_list[k].n : m.n_members;
+        if (n) {
+            k_element_forces<12><<<grid_for(n * 12, 96), 96, 0, st>>>(
+                n, list, m.mem_ij.ptr, ev + c->ev_off_member, D_dev, ferc ? ferc + c->ef_off_member : nullptr, ld.n_case, fac,
+                c->ef_count, m.mem_active.ptr, out_dev);
+            c->count_launch();
+        }
+        break;
+    }
+    case PN_QUAD: {
+        int64_t n = supported_only ? c->sup_list[k].n : m.n_quads;
+        if (n) {
+            k_element_forces<24><<<grid_for(n * 24, 96), 96, 0, st>>>(
+                n, list, m.quad_ijmn.ptr, ev + c->ev_off_quad, D_dev, ferc ? ferc + c->ef_off_quad : nullptr, ld.n_case, fac,
+                c->ef_count, nullptr, out_dev);
+            c->count_launch();
+        }
+        break;
+    }
+    case PN_PLATE: {
+        int64_t n = supported_only ? c->sup_list[k].n : m.n_plates;
+        if (n) {
+            k_element_forces<24><<<grid_for(n * 24, 96), 96, 0, st>>>(
+                n, list, m.plate_ijmn.ptr, ev + c->ev_off_plate, D_dev, ferc ? ferc + c->ef_off_plate : nullptr, ld.n_case, fac,
+                c->ef_count, nullptr, out_dev);
+            c->count_launch();
+        }
+        break;
+    }
+    }
 }
 
-void launch_member_pdelta_forces(Ctx *c, const double *D_dev, double *F_dev, cudaStream_t st) {
+void launch_member_pdelta_forces(Ctx *c, const double *D_dev, bool supported_only, double *F_dev, cudaStream_t st) {
     const Model &m = c->model;
-    if (!m.n_members) return;
-    k_member_pdelta_forces<<<grid_for(m.n_members, 64), 64, 0, st>>>(m.n_members, m.mem_ij.ptr, m.mem_props.ptr,
-                                                                      m.mem_rot.ptr, m.mem_rel.ptr, m.xyz.ptr, D_dev,
-                                                                      m.mem_active.ptr, F_dev);
+    int64_t n = supported_only ? c->sup_list[PN_MEMBER - 1].n : m.n_members;
+    if (!n) return;
+    ProfScope ps_(c, PS_REACTIONS);
+    k_member_pdelta_forces<<<grid_for(n, 64), 64, 0, st>>>(n, m.mem_ij.ptr, m.mem_props.ptr, m.mem_rot.ptr, m.mem_rel.ptr,
+                                                            m.xyz.ptr, D_dev, m.mem_active.ptr,
+                                                            supported_only ? c->sup_list[PN_MEMBER - 1].ptr : nullptr, F_dev);
     c->count_launch();
 }
 

@@ -124,6 +124,23 @@ struct CsrBlock {
     DevBuf<double> vals;
 };
 
+// Per-kernel device timing (CUDA events on the context stream around individual launches), switched on by
+// pn_profile_enable: bench.py reads it to report each kernel's share of a step and its roofline fraction.
+enum ProfSlot {
+    PS_ELEM_KE = 0, PS_SCATTER, PS_GATHER_BLOCKS, PS_RHS, PS_SPMM, PS_FRONT_ASSEMBLE, PS_EXTEND_ADD, PS_LU_DIAG,
+    PS_LU_PANELS, PS_LU_UPDATE, PS_COPY_FACTORS, PS_SOLVE_GATHER, PS_SOLVE_DIAG, PS_SOLVE_UPDATE, PS_SOLVE_MISC,
+    PS_REACTIONS, PS_PCG_VECTOR, PS_MERGE, PS_COUNT
+};
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int slot; size_t e0, e1; };
+    std::vector<Rec> recs;
+    double ms[PS_COUNT] = {0};
+    int64_t n[PS_COUNT] = {0};
+};
+
 struct DirectSolver;   // pn_direct.cu
 struct PcgWork;        // pn_pcg.cu
 
@@ -168,6 +185,7 @@ struct Ctx {
     DevBuf<uint32_t> inc_src;      // ef positions sorted by global DOF (stable = emission order)
     DevBuf<uint32_t> inc_start;    // [n_dof + 1]
     bool incidence_ready = false;
+    DevBuf<int32_t> sup_list[4];   // per element kind: elements touching a supported node (reactions only need these)
 
     // solve state
     DevBuf<double> B, X;           // [n1][s] row-major
@@ -183,6 +201,37 @@ struct Ctx {
     PcgWork *pcg = nullptr;
 
     DevBuf<uint8_t> cub_tmp;       // scratch for cub device-wide primitives
+    Profiler prof;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // pn_timer_start / pn_timer_stop
+};
+
+void prof_flush(Ctx *c);
+struct ProfScope {
+    Ctx *c;
+    int slot;
+    size_t e0 = 0;
+    bool live;
+    static size_t grab(Ctx *c) {
+        Profiler &p = c->prof;
+        if (p.used == p.pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            p.pool.push_back(e);
+        }
+        return p.used++;
+    }
+    ProfScope(Ctx *ctx, int s) : c(ctx), slot(s), live(ctx->prof.on) {
+        if (!live) return;
+        if (c->prof.used > 60000) prof_flush(c);
+        e0 = grab(c);
+        cudaEventRecord(c->prof.pool[e0], c->stream);
+    }
+    ~ProfScope() {
+        if (!live) return;
+        size_t e1 = grab(c);
+        cudaEventRecord(c->prof.pool[e1], c->stream);
+        c->prof.recs.push_back({slot, e0, e1});
+    }
 };
 
 // RAII timer on the context stream
@@ -205,9 +254,9 @@ void launch_member_kg(Ctx *c, const double *P_dev, double *out_dev, cudaStream_t
 void launch_member_axial(Ctx *c, const double *D_dev, double *P_dev, cudaStream_t st);
 void launch_member_fer_groups(Ctx *c, cudaStream_t st);
 void launch_shell_fer(Ctx *c, bool quad, const double *pressure_dev, double *out_dev, cudaStream_t st);
-void launch_element_forces(Ctx *c, int kind, const double *D_dev, const double *fer_dev, double *out_dev,
+void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo, bool supported_only, double *out_dev,
                            cudaStream_t st);
-void launch_member_pdelta_forces(Ctx *c, const double *D_dev, double *F_dev, cudaStream_t st);
+void launch_member_pdelta_forces(Ctx *c, const double *D_dev, bool supported_only, double *F_dev, cudaStream_t st);
 void launch_forces_to_local(Ctx *c, int kind, double *F_dev, cudaStream_t st);
 
 // ---- pn_sparse.cu ---------------------------------------------------------------------------------
@@ -220,7 +269,6 @@ void build_rhs(Ctx *c, int32_t combo0, int s, const double *kd2_percol);   // B 
 void merge_displacements(Ctx *c, int32_t combo0, int s);   // X, D2 -> D_all[combo0 .. combo0+s)
 void export_coo(Ctx *c, int32_t *row_dev, int32_t *col_dev, double *data_dev);
 void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev /* [n_dof] */);
-void combine_fer(Ctx *c, int32_t combo);     // fer_combo = sum_case factor * fer_case
 int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap);
 // Y = A X for a CSR block, X/Y row-major with s columns
 void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st);

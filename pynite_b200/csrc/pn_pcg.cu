@@ -91,8 +91,8 @@ __global__ void k_spmm_percol(int64_t rows, int s, int64_t nnz, const int32_t *_
 static void apply_matrix(Ctx *c, const double *vals11, int percol, const double *X, double *Y, int s) {
     const CsrBlock &A = c->blk[0];
     if (percol) {
-        k_spmm_percol<<<grid_for(A.rows * s, 256), 256, 0, c->stream>>>(A.rows, s, A.nnz, A.indptr.ptr, A.indices.ptr,
-                                                                         vals11, X, Y);
+        { ProfScope ps_(c, PS_SPMM); k_spmm_percol<<<grid_for(A.rows * s, 256), 256, 0, c->stream>>>(A.rows, s, A.nnz, A.indptr.ptr, A.indices.ptr,
+                                                                         vals11, X, Y); }
         c->count_launch();
     } else {
         spmm(c, A, vals11, X, Y, s, c->stream);
@@ -203,8 +203,8 @@ void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, dou
     DevBuf<double> partial, out;
     partial.resize((int64_t)grid * s);
     out.resize(s);
-    k_dot_partial<<<grid, RED_TPB, 0, c->stream>>>(n, s, A, B, partial.ptr, 0, 1);
-    k_dot_final<<<grid_for(s, 128), 128, 0, c->stream>>>(grid, s, 1, partial.ptr, out.ptr, nullptr, nullptr);
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_partial<<<grid, RED_TPB, 0, c->stream>>>(n, s, A, B, partial.ptr, 0, 1); }
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final<<<grid_for(s, 128), 128, 0, c->stream>>>(grid, s, 1, partial.ptr, out.ptr, nullptr, nullptr); }
     c->count_launch(2);
     PN_CUDA(cudaMemcpyAsync(out_host, out.ptr, sizeof(double) * s, cudaMemcpyDeviceToHost, c->stream));
     PN_CUDA(cudaStreamSynchronize(c->stream));
@@ -246,10 +246,10 @@ void pcg_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solve_o
     c->X.zero(st);
     PN_CUDA(cudaMemcpyAsync(w.R.ptr, c->B.ptr, (size_t)(n1 * s) * sizeof(double), cudaMemcpyDeviceToDevice, st));
     // z = Minv r, rz = r.z, bb = r.r (x0 = 0)
-    k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr, w.AP.ptr,
-                                                  c->X.ptr, w.R.ptr, w.Z.ptr, w.partial.ptr, 1);
-    k_dot_final<<<grid_for(2 * s, 128), 128, 0, st>>>(w.red_grid, s, 2, w.partial.ptr, rz, bb, nullptr);
-    k_update_p<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, rz, rz_new, w.Z.ptr, w.P.ptr, 1);
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr, w.AP.ptr,
+                                                  c->X.ptr, w.R.ptr, w.Z.ptr, w.partial.ptr, 1); }
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final<<<grid_for(2 * s, 128), 128, 0, st>>>(w.red_grid, s, 2, w.partial.ptr, rz, bb, nullptr); }
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_update_p<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, rz, rz_new, w.Z.ptr, w.P.ptr, 1); }
     c->count_launch(3);
 
     std::vector<double> h_bb(s), h_rr(s);
@@ -263,13 +263,13 @@ void pcg_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solve_o
     const int check_every = 20;
     while (!converged && it < max_iter) {
         apply_matrix(c, vals11, percol, w.P.ptr, w.AP.ptr, s);
-        k_dot_partial<<<w.red_grid, RED_TPB, 0, st>>>(n1, s, w.P.ptr, w.AP.ptr, w.partial.ptr, 0, 1);
-        k_dot_final<<<grid_for(s, 128), 128, 0, st>>>(w.red_grid, s, 1, w.partial.ptr, pAp, nullptr, nullptr);
-        k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr,
-                                                      w.AP.ptr, c->X.ptr, w.R.ptr, w.Z.ptr, w.partial.ptr, 0);
-        k_dot_final<<<grid_for(2 * s, 128), 128, 0, st>>>(w.red_grid, s, 2, w.partial.ptr, rz_new, rr, nullptr);
-        k_update_p<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, rz, rz_new, w.Z.ptr, w.P.ptr, 0);
-        k_copy_s<<<1, 256, 0, st>>>(s, rz_new, rz);
+        { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_partial<<<w.red_grid, RED_TPB, 0, st>>>(n1, s, w.P.ptr, w.AP.ptr, w.partial.ptr, 0, 1); }
+        { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final<<<grid_for(s, 128), 128, 0, st>>>(w.red_grid, s, 1, w.partial.ptr, pAp, nullptr, nullptr); }
+        { ProfScope ps_(c, PS_PCG_VECTOR); k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr,
+                                                      w.AP.ptr, c->X.ptr, w.R.ptr, w.Z.ptr, w.partial.ptr, 0); }
+        { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final<<<grid_for(2 * s, 128), 128, 0, st>>>(w.red_grid, s, 2, w.partial.ptr, rz_new, rr, nullptr); }
+        { ProfScope ps_(c, PS_PCG_VECTOR); k_update_p<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, rz, rz_new, w.Z.ptr, w.P.ptr, 0); }
+        { ProfScope ps_(c, PS_PCG_VECTOR); k_copy_s<<<1, 256, 0, st>>>(s, rz_new, rz); }
         c->count_launch(6);
         ++it;
         if (it % check_every == 0 || it == max_iter) {

@@ -260,7 +260,7 @@ void gather_block_values(Ctx *c, const double *vals_dev) {
     for (int b = 0; b < 4; ++b) {
         CsrBlock &B = c->blk[b];
         if (B.nnz) {
-            k_gather_u32<<<grid_for(B.nnz, 256), 256, 0, c->stream>>>(B.nnz, B.src.ptr, vals_dev, B.vals.ptr);
+            { ProfScope ps_(c, PS_GATHER_BLOCKS); k_gather_u32<<<grid_for(B.nnz, 256), 256, 0, c->stream>>>(B.nnz, B.src.ptr, vals_dev, B.vals.ptr); }
             c->count_launch();
         }
     }
@@ -373,8 +373,8 @@ __global__ void k_scatter_add(int64_t nnz_csr, const uint32_t *__restrict__ seg_
 
 void scatter_add_values(Ctx *c, const double *ev_dev, double *vals_dev) {
     if (!c->nnz_csr) return;
-    k_scatter_add<<<grid_for(c->nnz_csr, 256), 256, 0, c->stream>>>(c->nnz_csr, c->seg_start.ptr, c->coo_src.ptr, ev_dev,
-                                                                     vals_dev);
+    { ProfScope ps_(c, PS_SCATTER); k_scatter_add<<<grid_for(c->nnz_csr, 256), 256, 0, c->stream>>>(c->nnz_csr, c->seg_start.ptr, c->coo_src.ptr, ev_dev,
+                                                                     vals_dev); }
     c->count_launch();
 }
 
@@ -471,7 +471,24 @@ void build_incidence(Ctx *c) {
     c->count_launch();
     PN_CUDA(cudaStreamSynchronize(st));
     c->ef.resize(c->ef_count);
-    c->fer_combo.resize(c->ef_count);
+    c->ef.zero(st);
+    // elements that touch a supported node, per kind (host scan of the connectivity, once per topology)
+    {
+        struct View { int64_t n; int nn; const std::vector<int32_t> *conn; };
+        View views[4] = {{m.n_springs, 2, &m.h_spring_ij}, {m.n_members, 2, &m.h_mem_ij},
+                         {m.n_quads, 4, &m.h_quad_ijmn}, {m.n_plates, 4, &m.h_plate_ijmn}};
+        for (int k = 0; k < 4; ++k) {
+            std::vector<int32_t> list;
+            const View &v = views[k];
+            for (int64_t e = 0; e < v.n; ++e) {
+                bool sup = false;
+                for (int a = 0; a < v.nn; ++a) sup = sup || m.h_support[(*v.conn)[v.nn * e + a]] != 0;
+                if (sup) list.push_back((int32_t)e);
+            }
+            c->sup_list[k].upload(list.data(), (int64_t)list.size(), st);
+            PN_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     c->incidence_ready = true;
 }
 
@@ -596,10 +613,10 @@ void build_rhs(Ctx *c, int32_t combo0, int s, const double *kd2_percol) {
     c->kd2.zero(st);
     if (c->n1 == 0 || s == 0) return;
     if (!kd2_percol && c->n2) spmv_plain(c, c->blk[1], c->blk[1].vals.ptr, c->d2_val.ptr, c->kd2.ptr, st);
-    k_build_rhs<<<grid_for(c->n1 * s, 256), 256, 0, st>>>(c->n1, s, ld.n_case, c->d1.ptr, ld.Gcase.ptr, c->n_dof,
+    { ProfScope ps_(c, PS_RHS); k_build_rhs<<<grid_for(c->n1 * s, 256), 256, 0, st>>>(c->n1, s, ld.n_case, c->d1.ptr, ld.Gcase.ptr, c->n_dof,
                                                             ld.factors.ptr + (int64_t)combo0 * ld.n_case,
                                                             kd2_percol ? kd2_percol : c->kd2.ptr, kd2_percol ? 1 : 0,
-                                                            c->B.ptr);
+                                                            c->B.ptr); }
     c->count_launch();
 }
 
@@ -615,30 +632,14 @@ __global__ void k_merge(int64_t n_dof, int s, const int32_t *__restrict__ newidx
 }
 void merge_displacements(Ctx *c, int32_t combo0, int s) {
     if (!c->n_dof || !s) return;
-    k_merge<<<grid_for(c->n_dof * s, 256), 256, 0, c->stream>>>(c->n_dof, s, c->newidx.ptr, c->X.ptr, c->d2_val.ptr,
-                                                                 c->D_all.ptr + (int64_t)combo0 * c->n_dof);
+    { ProfScope ps_(c, PS_MERGE); k_merge<<<grid_for(c->n_dof * s, 256), 256, 0, c->stream>>>(c->n_dof, s, c->newidx.ptr, c->X.ptr, c->d2_val.ptr,
+                                                                 c->D_all.ptr + (int64_t)combo0 * c->n_dof); }
     c->count_launch();
 }
 
 // ------------------------------------------------------------------------------------------------
 // reactions (Analysis._calc_reactions :1059-1313)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_combine_fer(int64_t n, int n_case, const double *__restrict__ fac_row, const double *__restrict__ fer_case,
-                              double *__restrict__ out) {
-    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    double acc = 0.0;
-    for (int cs = 0; cs < n_case; ++cs) acc = fma(fac_row[cs], fer_case[(int64_t)cs * n + q], acc);
-    out[q] = acc;
-}
-void combine_fer(Ctx *c, int32_t combo) {
-    Loads &ld = c->loads;
-    if (!c->ef_count) return;
-    k_combine_fer<<<grid_for(c->ef_count, 256), 256, 0, c->stream>>>(
-        c->ef_count, ld.n_case, ld.factors.ptr + (int64_t)combo * ld.n_case, ld.fer_case.ptr, c->fer_combo.ptr);
-    c->count_launch();
-}
-
 __global__ void k_reactions(int64_t n_dof, int n_case, const uint8_t *__restrict__ support,
                             const uint32_t *__restrict__ inc_start, const uint32_t *__restrict__ inc_src,
                             const double *__restrict__ ef, const double *__restrict__ fac_row,
@@ -664,13 +665,13 @@ void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev) {
     Loads &ld = c->loads;
     const Model &m = c->model;
     const double *D = c->D_all.ptr + (int64_t)combo * c->n_dof;
-    combine_fer(c, combo);
-    launch_element_forces(c, PN_SPRING, D, nullptr, c->ef.ptr + c->ef_off_spring, st);
-    launch_element_forces(c, PN_MEMBER, D, c->fer_combo.ptr + c->ef_off_member, c->ef.ptr + c->ef_off_member, st);
-    if (pdelta) launch_member_pdelta_forces(c, D, c->ef.ptr + c->ef_off_member, st);
-    launch_element_forces(c, PN_QUAD, D, c->fer_combo.ptr + c->ef_off_quad, c->ef.ptr + c->ef_off_quad, st);
-    launch_element_forces(c, PN_PLATE, D, c->fer_combo.ptr + c->ef_off_plate, c->ef.ptr + c->ef_off_plate, st);
+    launch_element_forces(c, PN_SPRING, D, combo, true, c->ef.ptr + c->ef_off_spring, st);
+    launch_element_forces(c, PN_MEMBER, D, combo, true, c->ef.ptr + c->ef_off_member, st);
+    if (pdelta) launch_member_pdelta_forces(c, D, true, c->ef.ptr + c->ef_off_member, st);
+    launch_element_forces(c, PN_QUAD, D, combo, true, c->ef.ptr + c->ef_off_quad, st);
+    launch_element_forces(c, PN_PLATE, D, combo, true, c->ef.ptr + c->ef_off_plate, st);
     if (c->n_dof) {
+        ProfScope ps_(c, PS_REACTIONS);
         k_reactions<<<grid_for(c->n_dof, 256), 256, 0, st>>>(c->n_dof, ld.n_case, m.support.ptr, c->inc_start.ptr,
                                                               c->inc_src.ptr, c->ef.ptr,
                                                               ld.factors.ptr + (int64_t)combo * ld.n_case, ld.Pcase.ptr,
@@ -713,7 +714,7 @@ static void spmm_dispatch_cpl(Ctx *c, const CsrBlock &A, const double *vals, con
                               cudaStream_t st) {
     int cpl = (s + G - 1) / G;
     unsigned grid = grid_for(A.rows * G, 256);
-#define PN_SPMM(CPL_) k_spmm<G, CPL_><<<grid, 256, 0, st>>>(A.rows, A.indptr.ptr, A.indices.ptr, vals, X, Y, s)
+#define PN_SPMM(CPL_) do { ProfScope ps_(c, PS_SPMM); k_spmm<G, CPL_><<<grid, 256, 0, st>>>(A.rows, A.indptr.ptr, A.indices.ptr, vals, X, Y, s); } while (0)
     if (cpl <= 1) PN_SPMM(1);
     else if (cpl <= 2) PN_SPMM(2);
     else if (cpl <= 4) PN_SPMM(4);

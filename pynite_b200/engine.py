@@ -62,7 +62,8 @@ class Stats(ct.Structure):
                 ('ms_partition', ct.c_double), ('ms_rhs', ct.c_double), ('ms_factor', ct.c_double),
                 ('ms_solve', ct.c_double), ('ms_reactions', ct.c_double), ('ms_spmm', ct.c_double),
                 ('spmm_launches', ct.c_int64), ('kernel_launches', ct.c_int64), ('iterations', ct.c_int64),
-                ('max_rel_residual', ct.c_double), ('factor_nnz', ct.c_int64), ('factor_flops', ct.c_double)]
+                ('max_rel_residual', ct.c_double), ('factor_nnz', ct.c_int64), ('factor_flops', ct.c_double),
+                ('update_flops', ct.c_double), ('solve_flops', ct.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -114,6 +115,11 @@ SIGNATURES = {
     'pn_spmm_k11': (ct.c_int, [_P, ct.c_int32, _F64P, _F64P, ct.c_int32, _F64P]),
     'pn_get_stats': (ct.c_int, [_P, ct.POINTER(Stats)]),
     'pn_reset_stats': (ct.c_int, [_P]),
+    'pn_timer_start': (ct.c_int, [_P]),
+    'pn_timer_stop': (ct.c_int, [_P, _F64P]),
+    'pn_profile_enable': (ct.c_int, [_P, ct.c_int]),
+    'pn_profile_get': (ct.c_int, [_P, ct.c_int, _F64P, ct.POINTER(ct.c_int64)]),
+    'pn_profile_slot_name': (ct.c_char_p, [ct.c_int]),
 }
 
 
@@ -333,20 +339,21 @@ class Engine:
         o.singular_tol = singular_tol
         return o
 
-    def _solve(self, fn, opts, want_reactions, D_out=None, R_out=None):
+    def _solve(self, fn, opts, want_reactions, D_out=None, R_out=None, download=True):
         n = self.n_dof
-        D = D_out if D_out is not None else np.empty((self.n_combo, n))
+        D = (D_out if D_out is not None else np.empty((self.n_combo, n))) if download else None
         R = (R_out if R_out is not None else np.empty((self.n_combo, n))) if want_reactions else None
         st = Stats()
         rc = fn(self._h, ct.byref(opts) if opts is not None else None, _ptr(D, _F64P), _ptr(R, _F64P), ct.byref(st))
         self._check(rc)
         return D, R, st
 
-    def solve_linear(self, opts=None, reactions=True, D_out=None, R_out=None):
-        return self._solve(self._lib.pn_solve_linear, opts, reactions, D_out, R_out)
+    def solve_linear(self, opts=None, reactions=True, D_out=None, R_out=None, download=True):
+        """download=False keeps the displacements on the device (no D2H copy); reactions imply a copy."""
+        return self._solve(self._lib.pn_solve_linear, opts, reactions, D_out, R_out, download)
 
-    def solve_pdelta(self, opts=None, reactions=True, D_out=None, R_out=None):
-        return self._solve(self._lib.pn_solve_pdelta, opts, reactions, D_out, R_out)
+    def solve_pdelta(self, opts=None, reactions=True, D_out=None, R_out=None, download=True):
+        return self._solve(self._lib.pn_solve_pdelta, opts, reactions, D_out, R_out, download)
 
     def kg_coo(self, combo, first_step):
         cap = 144*self.counts[PN_MEMBER]
@@ -390,6 +397,32 @@ class Engine:
         st = Stats()
         self._check(self._lib.pn_get_stats(self._h, ct.byref(st)))
         return st
+
+    def timer_start(self):
+        self._check(self._lib.pn_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ct.c_double(0)
+        self._check(self._lib.pn_timer_stop(self._h, ct.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.pn_profile_enable(self._h, 1 if on else 0))
+
+    def profile(self):
+        """{kernel slot: (summed device ms, launches)} since profile_enable(True)."""
+        out = {}
+        slot = 0
+        while True:
+            name = self._lib.pn_profile_slot_name(slot)
+            if not name:
+                break
+            ms, n = ct.c_double(0), ct.c_int64(0)
+            self._check(self._lib.pn_profile_get(self._h, slot, ct.byref(ms), ct.byref(n)))
+            if n.value:
+                out[name.decode()] = (ms.value, n.value)
+            slot += 1
+        return out
 
     def reset_stats(self):
         self._check(self._lib.pn_reset_stats(self._h))
