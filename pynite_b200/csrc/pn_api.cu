@@ -37,8 +37,7 @@ void invalidate(Ctx *c) {
     c->incidence_ready = false;
     c->solved = c->solved_pdelta = false;
     c->loads.vectors_ready = false;
-    direct_release(c);
-    pcg_release(c);
+    direct_invalidate(c);
 }
 
 template <typename T>
@@ -85,8 +84,7 @@ void ensure_ev(Ctx *c) { if (!c->ev_ready) compute_ev(c); }
 void ensure_symbolic(Ctx *c, uint32_t flags) {
     ensure_ev(c);
     if (c->symbolic_ready && c->sym_flags == flags) return;
-    direct_release(c);
-    pcg_release(c);
+    direct_invalidate(c);
     PhaseTimer tm(c, &c->stats.ms_symbolic);
     build_symbolic(c, flags);
     c->loads.vectors_ready = c->loads.vectors_ready && c->incidence_ready;
@@ -124,10 +122,6 @@ pn_solve_opts default_opts(const pn_solve_opts *o) {
     return r;
 }
 
-__global__ void k_sub(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t < n) out[t] = a[t] - b[t];
-}
 __global__ void k_add(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t < n) out[t] = a[t] + b[t];
@@ -140,35 +134,15 @@ __global__ void k_gather_vals(int64_t n, const uint32_t *__restrict__ src, const
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[src[i]];
 }
-__global__ void k_spmm_percol_api(int64_t rows, int s, int64_t nnz, const int32_t *__restrict__ indptr,
-                                  const int32_t *__restrict__ indices, const double *__restrict__ vals,
-                                  const double *__restrict__ X, double *__restrict__ Y) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= rows * s) return;
-    int64_t r = t / s; int j = (int)(t - r * s);
-    const double *v = vals + (int64_t)j * nnz;
-    double acc = 0.0;
-    for (int32_t k = indptr[r]; k < indptr[r + 1]; ++k) acc = fma(v[k], X[(int64_t)indices[k] * s + j], acc);
-    Y[t] = acc;
-}
-
 // Analysis._solve_unknown_disp :228-239: non-finite values or ||K x - b|| > tol ||b|| (||x|| > tol when
 // b = 0) mean a singular matrix.  Returns the largest relative residual.
 double residual_check(Ctx *c, const double *vals11, int percol, int s, const pn_solve_opts &o, bool raise) {
     int64_t n1 = c->n1;
     if (!n1 || !s) return 0.0;
     cudaStream_t st = c->stream;
-    DevBuf<double> AX;
+    DevBuf<double> &AX = c->work_ax;
     AX.resize(n1 * s);
-    if (percol) {
-        k_spmm_percol_api<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, c->blk[0].nnz, c->blk[0].indptr.ptr,
-                                                                  c->blk[0].indices.ptr, vals11, c->X.ptr, AX.ptr);
-        c->count_launch();
-    } else {
-        spmm(c, c->blk[0], vals11, c->X.ptr, AX.ptr, s, st);
-    }
-    k_sub<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, AX.ptr, c->B.ptr, AX.ptr);
-    c->count_launch();
+    residual_dd(c, c->blk[0], vals11, percol ? c->blk[0].nnz : 0, c->X.ptr, c->B.ptr, AX.ptr, s, st);
     std::vector<double> rr(s), bb(s), xx(s);
     column_dots(c, n1, s, AX.ptr, AX.ptr, rr.data());
     column_dots(c, n1, s, c->B.ptr, c->B.ptr, bb.data());
@@ -207,7 +181,7 @@ void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
     if (!Rxn_out) return;
     PhaseTimer tm(c, &c->stats.ms_reactions);
     build_incidence(c);
-    DevBuf<double> rx;
+    DevBuf<double> &rx = c->work_rx;
     int nc = c->loads.n_combo;
     rx.resize((int64_t)nc * c->n_dof);
     for (int j = 0; j < nc; ++j) compute_reactions(c, j, pdelta, rx.ptr + (int64_t)j * c->n_dof);

@@ -3,10 +3,22 @@
 //   ordering / fronts : pn_direct_symbolic.cpp (nested dissection of the node graph by coordinates)
 //   numeric           : level by level up the separator tree; every front is a dense row-major
 //                       (ns+nb)^2 matrix in a per-level arena.  Right-looking partial LU in block
-//                       steps of NB pivots: diagonal block (one CTA), row/column panels, rank-NB update
-//                       of the trailing matrix (tiled FP64 GEMM).  The trailing nb x nb block is the
-//                       update matrix, extend-added into the parent in a fixed child order
-//                       (deterministic, no atomics).
+//                       steps of NB = 64 pivots:
+//                         diag    one CTA factorises the NB x NB diagonal block in shared memory and
+//                                 inverts its two triangles (Linv, Uinv)
+//                         panels  U[k, rest] = Linv * F[k, rest],  L[rest, k] = F[rest, k] * Uinv   (GEMMs)
+//                         update  F[rest, rest] -= L[rest, k] * U[k, rest]                         (GEMM, rank NB)
+//                       All three GEMM shapes run through one FP64 register-tiled kernel body
+//                       (gemm_tile: 128 x 64 output tile per CTA, 8 x 4 outputs per thread, whole
+//                       K-chunk of 64 staged in 97 KB of shared memory, 2 CTAs per SM).
+//                       The trailing nb x nb block is the update matrix, extend-added into the
+//                       parent in a fixed child order (deterministic, no atomics).
+//   stored factor     : so that the solves are pure GEMMs with ONE launch per block step, the
+//                       permanent panels are pre-multiplied by the diagonal-block inverses:
+//                         Lp[r, k] = L[r, k] * Linv_kk  (r below block k),  Lp[r, k] = U[r, k] * Uinv_kk (r above)
+//                       With y_k = Linv_kk b_k the forward update b_r -= L[r,k] y_k equals
+//                       b_r -= Lp[r,k] b_k, i.e. it reads the *old* b_k and can run concurrently with
+//                       the diagonal solve; likewise backwards with Uinv.
 //   solve             : all right-hand sides at once; forward sweep passes update vectors up the
 //                       tree like the update matrices, backward sweep reads ancestors' results.
 //
@@ -18,20 +30,31 @@
 #include "pn_direct_symbolic.h"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 namespace pn {
 
 static inline unsigned grid_for(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
-constexpr int NB = 32;        // pivots per block step
-constexpr int TILE = 64;      // GEMM tile edge
-constexpr int KC = 16;        // GEMM k chunk
+constexpr int NB = 64;        // pivots per block step
+constexpr int BM = 128;       // GEMM tile rows
+constexpr int BN = 64;        // GEMM tile columns
+constexpr int BK = 64;        // GEMM k chunk (= NB: one chunk per rank-NB update)
+constexpr int SA_LD = BK + 4; // leading dimensions = 4 mod 16 doubles: the DMMA fragment loads of a half-warp hit 32 distinct banks
+constexpr int SB_LD = BN + 4;
+constexpr int GEMM_SMEM = (BM * SA_LD + BK * SB_LD) * (int)sizeof(double);   // 104 448 B, two CTAs per SM
+constexpr int DIAG_LD = NB + 1;
+constexpr int DIAG_SMEM = (3 * NB * DIAG_LD + 2 * NB) * (int)sizeof(double);  // 100 864 B
+constexpr int GB = 256;      // pivots per group: the trailing matrix is streamed once per group (rank-GB update)
 
 struct FrontDev {
     int64_t f_off;      // front matrix offset in its level arena
     int64_t w_off;      // solve workspace offset in its level arena ((ns+nb) x s)
-    int64_t l_off;      // permanent L panel: (ns+nb) x ns, ld = ns (holds L11\U11 on top)
+    int64_t l_off;      // permanent pre-multiplied panels: (ns+nb) x ns, ld = ns
     int64_t u_off;      // permanent U12: ns x nb, ld = nb
+    int64_t inv_off;    // diagonal-block inverses: per block step [Linv | Uinv], NB x NB each
     int64_t idx_off;    // into fidx / fpos
     int64_t rel_off;    // into rel
     int32_t ns, nb, parent, child_rank;
@@ -52,7 +75,11 @@ struct DirectSolver {
     DevBuf<uint8_t> ent_level;
     DevBuf<double> arena[2];
     DevBuf<double> warena[2];
-    DevBuf<double> L, U;
+    DevBuf<double> yarena;                    // per-front solved own rows of the level being processed
+    DevBuf<FrontDev> fronts_scaled;           // fronts with w_off scaled by the current number of right-hand sides
+    int fronts_s = 0;
+    DevBuf<double> L, U, inv;
+    bool attrs_set = false;
     DevBuf<int> status;                       // 0 ok, 1 zero / non-finite pivot, 2 entry outside front
     DevBuf<double> col_in, col_out;           // per-column solves (P-Delta)
     int64_t arena_cap = 0;
@@ -127,160 +154,334 @@ __global__ void k_extend_add(int first_child, int n_children, int rank, const Fr
     }
 }
 
-// LU of the diagonal block [kb, kb+bs) of every front in the level (no pivoting), in shared memory.
-__global__ void __launch_bounds__(256)
-k_lu_diag(int first, int kb, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int *__restrict__ status) {
-    __shared__ double D[NB][NB + 1];
-    FrontDev F = fronts[first + blockIdx.x];
-    if (kb >= F.ns) return;
-    int bs = min(NB, F.ns - kb);
-    int n = F.ns + F.nb;
-    double *A = arena + F.f_off + (int64_t)kb * n + kb;
-    int t = threadIdx.x;
-    for (int e = t; e < bs * bs; e += blockDim.x) D[e / bs][e % bs] = A[(int64_t)(e / bs) * n + e % bs];
-    __syncthreads();
-    for (int p = 0; p < bs; ++p) {
-        double piv = D[p][p];
-        if (t == 0 && (piv == 0.0 || !(fabs(piv) <= 1.7976931348623157e308))) atomicMax(status, 1);
-        __syncthreads();
-        for (int i = p + 1 + t; i < bs; i += blockDim.x) D[i][p] = D[i][p] / piv;
-        __syncthreads();
-        int rem = bs - p - 1;
-        for (int e = t; e < rem * rem; e += blockDim.x) {
-            int i = p + 1 + e / rem, j = p + 1 + e % rem;
-            D[i][j] = fma(-D[i][p], D[p][j], D[i][j]);
-        }
-        __syncthreads();
-    }
-    for (int e = t; e < bs * bs; e += blockDim.x) A[(int64_t)(e / bs) * n + e % bs] = D[e / bs][e % bs];
+extern __shared__ double pn_dyn_smem[];
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool pred) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int bytes = pred ? 8 : 0;                 // src-size 0: nothing is read, the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor path (DMMA.8x8x4).  Fragment layout (PTX ISA, m8n8k4 .f64):
+// a: row = lane/4, k = lane%4;  b: k = lane%4, col = lane/4;  c/d: row = lane/4, cols 2 (lane%4) + {0, 1}.
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Row panel U[kb:kb+bs, r0:n] = L_kk^-1 F[...] (thread per column) and column panel
-// L[r0:n, kb:kb+bs] = F[...] U_kk^-1 (thread per row).  grid.x = front, grid.y = tile of 128 columns
-// / rows; the first half of grid.y does the row panel, the second half the column panel.
-__global__ void __launch_bounds__(128)
-k_lu_panels(int first, int kb, int tiles, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
-    __shared__ double D[NB][NB + 1];
-    FrontDev F = fronts[first + blockIdx.x];
-    if (kb >= F.ns) return;
-    int bs = min(NB, F.ns - kb);
-    int n = F.ns + F.nb;
-    int r0 = kb + bs;
-    int rest = n - r0;
-    int tile = blockIdx.y % tiles;
-    bool col_panel = blockIdx.y >= tiles;
-    if (tile * 128 >= rest) return;
-    double *A = arena + F.f_off;
-    for (int e = threadIdx.x; e < bs * bs; e += blockDim.x) D[e / bs][e % bs] = A[(int64_t)(kb + e / bs) * n + kb + e % bs];
-    __syncthreads();
-    int q = tile * 128 + threadIdx.x;
-    if (q >= rest) return;
-    double v[NB];
-    if (!col_panel) {
-        int c = r0 + q;
-        for (int i = 0; i < bs; ++i) {
-            double acc = A[(int64_t)(kb + i) * n + c];
-            for (int j = 0; j < i; ++j) acc = fma(-D[i][j], v[j], acc);
-            v[i] = acc;
+// C[m x n] (op)= A[m x k] B[k x n], row-major with leading dimensions; one BM x BN tile per call,
+// 256 threads = 8 warps in a 4 x 2 grid, each warp owning a 32 x 32 block as 4 x 4 DMMA tiles
+// (tools/microbench/fp64_pipes.cu: DMMA 37.0 vs DFMA 36.7 TFLOP/s peak on B200 -- the tensor path is used
+// because a fragment needs 1/6 of the shared-memory bytes the FMA register tile needs, not for its peak).
+// mode 0: C -= A B;  mode 1: C = A B.
+// The C tile is read straight into the accumulators while the first operand slices are in flight; the operand
+// tiles stream through shared memory as a ring of four 16-wide k slices filled by cp.async.
+// In-place use (C aliasing A or B) is safe when the tile covers the aliased operand's full extent in the other
+// dimension: every global read is complete (wait_group 0 + barrier) before the first store.
+__device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+                                          int m, int n, int k, int tile_m, int tile_n, int mode) {
+    double(*sA)[SA_LD] = reinterpret_cast<double(*)[SA_LD]>(pn_dyn_smem);
+    double(*sB)[SB_LD] = reinterpret_cast<double(*)[SB_LD]>(pn_dyn_smem + BM * SA_LD);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+    const int row0 = tile_m * BM, col0 = tile_n * BN;
+    const int wrow = (warp >> 1) * 32, wcol = (warp & 1) * 32;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        int gr = row0 + wrow + 8 * mi + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int gc = col0 + wcol + 8 * ni + 2 * tg;
+            bool ok = mode == 0 && gr < m;
+            acc[mi][ni][0] = (ok && gc < n) ? C[(int64_t)gr * ldc + gc] : 0.0;
+            acc[mi][ni][1] = (ok && gc + 1 < n) ? C[(int64_t)gr * ldc + gc + 1] : 0.0;
         }
-        for (int i = 0; i < bs; ++i) A[(int64_t)(kb + i) * n + c] = v[i];
-    } else {
-        double *row = A + (int64_t)(r0 + q) * n + kb;
-        for (int j = 0; j < bs; ++j) {
-            double acc = row[j];
-            for (int i = 0; i < j; ++i) acc = fma(-v[i], D[i][j], acc);
-            v[j] = acc / D[j][j];
-        }
-        for (int j = 0; j < bs; ++j) row[j] = v[j];
     }
-}
-
-// C[m x n] -= A[m x k] B[k x n], all row-major with leading dimensions; 64x64 tile per CTA,
-// 256 threads, 4x4 outputs per thread, k staged through shared memory in chunks of KC.
-__device__ __forceinline__ void gemm_tile_sub(const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb,
-                                              double *__restrict__ C, int ldc, int m, int n, int k, int tile_m, int tile_n) {
-    __shared__ double sA[KC][TILE + 1];      // transposed: sA[kk][row]
-    __shared__ double sB[KC][TILE];
-    int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-    int row0 = tile_m * TILE, col0 = tile_n * TILE;
-    double acc[4][4];
+    const double sign = mode == 0 ? -1.0 : 1.0;
+    // k runs through a ring of four 16-wide slices of the shared tiles (slot = slice & 3): slice sl + 3 is in
+    // flight while slice sl is multiplied, one barrier per slice.
+    const int nsl = (k + 15) >> 4;
+    auto issue = [&](int sl) {
+        if (sl < nsl) {
+            const int slot = sl & 3, kbase = sl << 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i) {
+                int e = tid + 256 * i;
+                int r = e >> 4, kk = e & 15;
+                int gr = row0 + r;
+                bool ok = gr < m && kbase + kk < k;
+                cp_async8(&sA[r][16 * slot + kk], ok ? A + (int64_t)gr * lda + kbase + kk : A, ok);
+            }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    for (int k0 = 0; k0 < k; k0 += KC) {
-        for (int e = threadIdx.x; e < TILE * KC; e += 256) {
-            int r = e / KC, kk = e % KC;
-            int gr = row0 + r, gk = k0 + kk;
-            sA[kk][r] = (gr < m && gk < k) ? A[(int64_t)gr * lda + gk] : 0.0;
+            for (int i = 0; i < 4; ++i) {
+                int e = tid + 256 * i;
+                int kr = e >> 6, cc = e & 63;
+                int gc = col0 + cc;
+                bool ok = kbase + kr < k && gc < n;
+                cp_async8(&sB[16 * slot + kr][cc], ok ? B + (int64_t)(kbase + kr) * ldb + gc : B, ok);
+            }
         }
-        for (int e = threadIdx.x; e < KC * TILE; e += 256) {
-            int kk = e / TILE, cc = e % TILE;
-            int gk = k0 + kk, gc = col0 + cc;
-            sB[kk][cc] = (gk < k && gc < n) ? B[(int64_t)gk * ldb + gc] : 0.0;
-        }
+        cp_async_commit();
+    };
+    issue(0); issue(1); issue(2);
+    for (int sl = 0; sl < nsl; ++sl) {
+        cp_async_wait<2>();
         __syncthreads();
+        issue(sl + 3);
+        const int base = (sl & 3) << 4;
 #pragma unroll
-        for (int kk = 0; kk < KC; ++kk) {
+        for (int ks = 0; ks < 4; ++ks) {
+            const int kk = base + 4 * ks + tg;
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+            for (int mi = 0; mi < 4; ++mi) a[mi] = sign * sA[wrow + 8 * mi + g][kk];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx + 16 * j];
+            for (int ni = 0; ni < 4; ++ni) b[ni] = sB[kk][wcol + 8 * ni + g];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();          // the tiles may be refilled by the caller's next gemm_tile call
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int gr = row0 + ty * 4 + i;
+    for (int mi = 0; mi < 4; ++mi) {
+        int gr = row0 + wrow + 8 * mi + g;
         if (gr >= m) continue;
+        double *crow = C + (int64_t)gr * ldc;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int gc = col0 + tx + 16 * j;
-            if (gc < n) C[(int64_t)gr * ldc + gc] -= acc[i][j];
+        for (int ni = 0; ni < 4; ++ni) {
+            int gc = col0 + wcol + 8 * ni + 2 * tg;
+            if (gc < n) crow[gc] = acc[mi][ni][0];
+            if (gc + 1 < n) crow[gc + 1] = acc[mi][ni][1];
         }
     }
 }
 
-// trailing update of the partial LU: F[r0:, r0:] -= L[r0:, kb:kb+bs] U[kb:kb+bs, r0:]
-__global__ void __launch_bounds__(256)
-k_lu_update(int first, int kb, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
+// LU (no pivoting) of one NB x NB diagonal block held in shared memory, then the inverses of its unit-lower and
+// upper triangles.  Called by the first 128 threads of a CTA (4 warps); contains __syncthreads-free named barriers
+// only, so the other warps of the CTA may skip it.  S holds the block on entry (identity-padded past bs) and the
+// packed L\U factors on exit; Li / Ui receive the inverses.
+//   LU      : thread i owns row i in registers; step p: row p is published through shared memory, every thread
+//             below divides by the pivot and updates its row (one barrier per step, 64 FMAs in registers).
+//   inverse : threads 0..63 build column j of Linv, threads 64..127 column j of Uinv by substitution, x in
+//             registers, the triangular factor read from shared memory as warp-wide broadcasts.
+__device__ __forceinline__ void bar128() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+__device__ __forceinline__ void diag_block_factor(double (*S)[DIAG_LD], double (*Li)[DIAG_LD], double (*Ui)[DIAG_LD],
+                                                  double *rowbuf /* [2][NB] */, int *status) {
+    const int t = threadIdx.x;          // 0..127
+    double row[NB];
+    if (t < NB) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) row[j] = S[t][j];
+    }
+#pragma unroll
+    for (int p = 0; p < NB; ++p) {
+        double *R = rowbuf + (p & 1) * NB;
+        if (t == p) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (j >= p) R[j] = row[j];
+            double piv = row[p];
+            if (piv == 0.0 || !(fabs(piv) <= 1.7976931348623157e308)) atomicMax(status, 1);
+        }
+        bar128();
+        if (t < NB && t > p) {
+            double l = row[p] / R[p];
+            row[p] = l;
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (j > p) row[j] = fma(-l, R[j], row[j]);
+        }
+    }
+    if (t < NB) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) S[t][j] = row[j];
+    }
+    bar128();
+    if (t < NB) {
+        // column j = t of inverse(unit lower L):  x_j = 1,  x_i = -sum_{p=j..i-1} L[i][p] x_p
+        const int j = t;
+        double x[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int p = 0; p < NB; ++p)
+                if (p < i) acc = fma(S[i][p], (p >= j) ? x[p] : 0.0, acc);
+            x[i] = (i == j) ? 1.0 : ((i > j) ? -acc : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) Li[i][j] = x[i];
+    } else {
+        // column j of inverse(upper U):  x_j = 1/U_jj,  x_i = -(sum_{p=i+1..j} U[i][p] x_p) / U_ii
+        const int j = t - NB;
+        double x[NB];
+#pragma unroll
+        for (int i = NB - 1; i >= 0; --i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int p = NB - 1; p >= 0; --p)
+                if (p > i) acc = fma(S[i][p], (p <= j) ? x[p] : 0.0, acc);
+            double d = S[i][i];
+            x[i] = (i == j) ? 1.0 / d : ((i < j) ? -acc / d : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) Ui[i][j] = x[i];
+    }
+    bar128();
+}
+
+// Diagonal block [kb, kb+bs) of one front: load, factor + invert (first 128 threads), write back.  All threads of
+// the CTA must call it (it contains __syncthreads).
+__device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *arena, double *inv, int *status) {
+    double(*S)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem);
+    double(*Li)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem + NB * DIAG_LD);
+    double(*Ui)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem + 2 * NB * DIAG_LD);
+    double *rowbuf = pn_dyn_smem + 3 * NB * DIAG_LD;
+    const int bs = min(NB, F.ns - kb);
+    const int n = F.ns + F.nb;
+    double *A = arena + F.f_off + (int64_t)kb * n + kb;
+    const int t = threadIdx.x;
+    for (int e = t; e < NB * NB; e += blockDim.x) {
+        int i = e / NB, j = e % NB;
+        S[i][j] = (i < bs && j < bs) ? A[(int64_t)i * n + j] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (t < 128) diag_block_factor(S, Li, Ui, rowbuf, status);
+    __syncthreads();
+    for (int e = t; e < bs * bs; e += blockDim.x) A[(int64_t)(e / bs) * n + e % bs] = S[e / bs][e % bs];
+    double *out = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
+    for (int e = t; e < NB * NB; e += blockDim.x) {
+        out[e] = Li[e / NB][e % NB];
+        out[NB * NB + e] = Ui[e / NB][e % NB];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_lu_diag(int first, int kb, const FrontDev *__restrict__ fronts, double *__restrict__ arena, double *__restrict__ inv,
+          int *__restrict__ status) {
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
-    int bs = min(NB, F.ns - kb);
-    int n = F.ns + F.nb;
-    int r0 = kb + bs, rest = n - r0;
-    if ((int)blockIdx.y * TILE >= rest || (int)blockIdx.z * TILE >= rest) return;
-    double *A = arena + F.f_off;
-    gemm_tile_sub(A + (int64_t)r0 * n + kb, n, A + (int64_t)kb * n + r0, n, A + (int64_t)r0 * n + r0, n, rest, rest, bs,
-                  blockIdx.y, blockIdx.z);
+    diag_step(F, kb, arena, inv, status);
 }
 
-// copies the factor parts of every front of a level to permanent storage
-__global__ void k_copy_factors(int first, const FrontDev *__restrict__ fronts, const double *__restrict__ arena,
-                               double *__restrict__ L, double *__restrict__ U) {
+// Panels of block step kb as GEMMs with the diagonal inverses.  grid.x = front; grid.y < tiles_u: column
+// tile of the row panel U[k, rest] = Linv F[k, rest]; otherwise row tile of the column panel
+// L[rest, k] = F[rest, k] Uinv.  Both are in place (see gemm_tile).
+__global__ void __launch_bounds__(256, 2)
+k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts, double *__restrict__ arena,
+            const double *__restrict__ inv) {
+    FrontDev F = fronts[first + blockIdx.x];
+    if (kb >= F.ns) return;
+    const int bs = min(NB, F.ns - kb);
+    const int n = F.ns + F.nb;
+    const int r0 = kb + bs, rest = n - r0;
+    if (rest <= 0) return;
+    double *A = arena + F.f_off;
+    const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
+    const double *Uinv = Linv + NB * NB;
+    if ((int)blockIdx.y < tiles_u) {
+        int t = blockIdx.y;
+        if (t * BN >= rest) return;
+        double *P = A + (int64_t)kb * n + r0;
+        gemm_tile(Linv, NB, P, n, P, n, bs, rest, bs, 0, t, 1);
+    } else {
+        int t = blockIdx.y - tiles_u;
+        if (t * BM >= rest) return;
+        double *P = A + (int64_t)r0 * n + kb;
+        gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1);
+    }
+}
+
+// Block steps are grouped GB pivots at a time so that the (HBM-resident) trailing matrix is read and written once
+// per group instead of once per step.  Inside group [g0, ge), after the panels of step kb, only the strips the
+// remaining steps of the group will factor are updated (rank NB):
+//   (a) F[r0:n, r0:ge]  -= L[r0:n, kb:r0] U[kb:r0, r0:ge]      (r0 = kb + NB)
+//   (b) F[r0:ge, ge:n]  -= L[r0:ge, kb:r0] U[kb:r0, ge:n]
+// grid = (front, tile); tiles enumerate region (a) row-major, then region (b).
+__global__ void __launch_bounds__(256, 2)
+k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
+    FrontDev F = fronts[first + blockIdx.x];
+    const int ge = min(g0 + GB, F.ns);
+    const int r0 = kb + NB;
+    if (r0 >= ge) return;
+    const int n = F.ns + F.nb;
+    double *A = arena + F.f_off;
+    const int wa = ge - r0, ha = n - r0;
+    const int ta_n = (wa + BN - 1) / BN, ta_m = (ha + BM - 1) / BM;
+    const int hb = ge - r0, wb = n - ge;
+    const int tb_n = (wb + BN - 1) / BN, tb_m = (hb + BM - 1) / BM;
+    int t = blockIdx.y;
+    const double *Lp = A + (int64_t)r0 * n + kb;        // L[r0:, kb:r0]
+    if (t < ta_m * ta_n) {
+        gemm_tile(Lp, n, A + (int64_t)kb * n + r0, n, A + (int64_t)r0 * n + r0, n, ha, wa, NB, t / ta_n, t % ta_n, 0);
+        return;
+    }
+    t -= ta_m * ta_n;
+    if (t < tb_m * tb_n)
+        gemm_tile(Lp, n, A + (int64_t)kb * n + ge, n, A + (int64_t)r0 * n + ge, n, hb, wb, NB, t / tb_n, t % tb_n, 0);
+}
+
+// trailing update after group [g0, ge): F[ge:, ge:] -= L[ge:, g0:ge] U[g0:ge, ge:]   (rank ge - g0 <= GB)
+__global__ void __launch_bounds__(256, 2)
+k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
+    FrontDev F = fronts[first + blockIdx.x];
+    if (g0 >= F.ns) return;
+    const int ge = min(g0 + GB, F.ns);
+    const int n = F.ns + F.nb;
+    const int rest = n - ge;
+    if ((int)blockIdx.y * BM >= rest || (int)blockIdx.z * BN >= rest) return;
+    double *A = arena + F.f_off;
+    gemm_tile(A + (int64_t)ge * n + g0, n, A + (int64_t)g0 * n + ge, n, A + (int64_t)ge * n + ge, n, rest, rest, ge - g0, blockIdx.y,
+              blockIdx.z, 0);
+}
+
+// Permanent factor of a level: for block column k of every front, rows above the diagonal block hold
+// U[., k] Uinv_kk and rows below hold L[., k] Linv_kk (see the header comment).  grid = (front, block column,
+// row tile); a row tile index first enumerates the tiles above the diagonal block, then those below.
+__global__ void __launch_bounds__(256, 2)
+k_store_panels(int first, const FrontDev *__restrict__ fronts, const double *__restrict__ arena,
+               const double *__restrict__ inv, double *__restrict__ L) {
+    FrontDev F = fronts[first + blockIdx.x];
+    const int kb = blockIdx.y * NB;
+    if (kb >= F.ns) return;
+    const int bs = min(NB, F.ns - kb);
+    const int n = F.ns + F.nb;
+    const int up_rows = kb, lo_rows = n - kb - bs;
+    const int up_tiles = (up_rows + BM - 1) / BM, lo_tiles = (lo_rows + BM - 1) / BM;
+    int t = blockIdx.z;
+    const double *Linv = inv + F.inv_off + (int64_t)blockIdx.y * (2 * NB * NB);
+    const double *A = arena + F.f_off;
+    double *out = L + F.l_off;
+    if (t < up_tiles) {
+        gemm_tile(A + kb, n, Linv + NB * NB, NB, out + kb, F.ns, up_rows, bs, bs, t, 0, 1);
+    } else if (t - up_tiles < lo_tiles) {
+        int r0 = kb + bs;
+        gemm_tile(A + (int64_t)r0 * n + kb, n, Linv, NB, out + (int64_t)r0 * F.ns + kb, F.ns, lo_rows, bs, bs, t - up_tiles, 0, 1);
+    }
+}
+
+// U12 of every front of a level to permanent storage
+__global__ void k_copy_u12(int first, const FrontDev *__restrict__ fronts, const double *__restrict__ arena,
+                           double *__restrict__ U) {
     FrontDev F = fronts[first + blockIdx.x];
     int n = F.ns + F.nb;
-    int64_t totalL = (int64_t)n * F.ns, totalU = (int64_t)F.ns * F.nb;
+    int64_t total = (int64_t)F.ns * F.nb;
     const double *A = arena + F.f_off;
-    for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < totalL + totalU; t += (int64_t)gridDim.y * blockDim.x) {
-        if (t < totalL) {
-            int64_t r = t / F.ns; int cidx = (int)(t - r * F.ns);
-            L[F.l_off + t] = A[r * n + cidx];
-        } else {
-            int64_t u = t - totalL;
-            int64_t r = u / F.nb; int cidx = (int)(u - r * F.nb);
-            U[F.u_off + u] = A[r * n + F.ns + cidx];
-        }
+    for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.y * blockDim.x) {
+        int64_t r = t / F.nb; int cidx = (int)(t - r * F.nb);
+        U[F.u_off + t] = A[r * n + F.ns + cidx];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// solve kernels (W = per-front workspace (ns+nb) x s, row-major)
+// solve kernels (W = per-front workspace (ns+nb) x s, row-major; Y = solved own rows, same offsets)
 // ------------------------------------------------------------------------------------------------
 // mode 0 (forward): own rows <- X[fidx], boundary rows <- 0
 // mode 1 (backward): own rows <- X[fidx] (holds y), boundary rows <- X[fidx] (final x of ancestors)
@@ -297,12 +498,12 @@ __global__ void k_solve_gather(int first, int s, int mode, const FrontDev *__res
     }
 }
 __global__ void k_solve_store(int first, int s, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
-                              const double *__restrict__ W, double *__restrict__ X) {
+                              const double *__restrict__ Y, double *__restrict__ X) {
     FrontDev F = fronts[first + blockIdx.x];
     int64_t total = (int64_t)F.ns * s;
     for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.y * blockDim.x) {
         int r = (int)(t / s), j = (int)(t - (int64_t)r * s);
-        X[(int64_t)fidx[F.idx_off + r] * s + j] = W[F.w_off + t];
+        X[(int64_t)fidx[F.idx_off + r] * s + j] = Y[F.w_off + t];
     }
 }
 __global__ void k_solve_extend_add(int first_child, int n_children, int rank, int s, const FrontDev *__restrict__ fronts,
@@ -319,61 +520,43 @@ __global__ void k_solve_extend_add(int first_child, int n_children, int rank, in
         Wp[P.w_off + (int64_t)r[a] * s + j] += Wc[C.w_off + (int64_t)(C.ns + a) * s + j];
     }
 }
-// forward: w[kb:kb+bs] <- L_kk^-1 w[kb:kb+bs] (unit lower); backward: w[kb:kb+bs] <- U_kk^-1 w[kb:kb+bs]
-__global__ void __launch_bounds__(128)
-k_solve_diag(int first, int kb, int s, int backward, const FrontDev *__restrict__ fronts, const double *__restrict__ L,
-             double *__restrict__ W) {
-    __shared__ double D[NB][NB + 1];
+// One block step of a sweep for every front of a level; grid = (front, row tile, column tile of s).
+//   forward : tile 0: Y[k] = Linv_kk W[k];  tile t >= 1: W[r] -= Lp[r, k] W[k] for the rows below block k
+//   backward: tile 0: Y[k] = Uinv_kk W[k];  tile t >= 1: W[r] -= Lp[r, k] W[k] for the rows above block k
+// Every tile reads the same, unmodified W[k] (the solved block goes to Y), so one launch does both.
+__global__ void __launch_bounds__(256, 2)
+k_solve_step(int first, int kb, int s, int backward, const FrontDev *__restrict__ fronts, const double *__restrict__ L,
+             const double *__restrict__ inv, double *__restrict__ W, double *__restrict__ Y) {
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
-    int bs = min(NB, F.ns - kb);
-    const double *Lp = L + F.l_off + (int64_t)kb * F.ns + kb;
-    for (int e = threadIdx.x; e < bs * bs; e += blockDim.x) D[e / bs][e % bs] = Lp[(int64_t)(e / bs) * F.ns + e % bs];
-    __syncthreads();
-    int j = blockIdx.y * blockDim.x + threadIdx.x;
-    if (j >= s) return;
-    double *w = W + F.w_off + (int64_t)kb * s + j;
-    double v[NB];
-    if (!backward) {
-        for (int i = 0; i < bs; ++i) {
-            double acc = w[(int64_t)i * s];
-            for (int p = 0; p < i; ++p) acc = fma(-D[i][p], v[p], acc);
-            v[i] = acc;
-        }
-    } else {
-        for (int i = bs - 1; i >= 0; --i) {
-            double acc = w[(int64_t)i * s];
-            for (int p = i + 1; p < bs; ++p) acc = fma(-D[i][p], v[p], acc);
-            v[i] = acc / D[i][i];
-        }
-    }
-    for (int i = 0; i < bs; ++i) w[(int64_t)i * s] = v[i];
-}
-// mode 0: forward update   W[r0:n]  -= Lpanel[r0:n, kb:kb+bs] W[kb:kb+bs]
-// mode 1: backward update  W[0:kb]  -= U11[0:kb, kb:kb+bs]    W[kb:kb+bs]
-// mode 2: boundary update  W[0:ns]  -= U12[ns x nb]           W[ns:n]
-__global__ void __launch_bounds__(256)
-k_solve_update(int first, int kb, int s, int mode, const FrontDev *__restrict__ fronts, const double *__restrict__ L,
-               const double *__restrict__ U, double *__restrict__ W) {
-    FrontDev F = fronts[first + blockIdx.x];
-    int n = F.ns + F.nb;
+    const int bs = min(NB, F.ns - kb);
+    const int n = F.ns + F.nb;
+    if ((int)blockIdx.z * BN >= s) return;
     double *w = W + F.w_off;
-    if (mode == 2) {
-        if (F.nb == 0 || (int)blockIdx.y * TILE >= F.ns || (int)blockIdx.z * TILE >= s) return;
-        gemm_tile_sub(U + F.u_off, F.nb, w + (int64_t)F.ns * s, s, w, s, F.ns, s, F.nb, blockIdx.y, blockIdx.z);
+    const double *wk = w + (int64_t)kb * s;
+    const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
+    int t = blockIdx.y;
+    if (t == 0) {
+        gemm_tile(backward ? Linv + NB * NB : Linv, NB, wk, s, Y + F.w_off + (int64_t)kb * s, s, bs, s, bs, 0, blockIdx.z, 1);
         return;
     }
-    if (kb >= F.ns) return;
-    int bs = min(NB, F.ns - kb);
-    if (mode == 0) {
-        int r0 = kb + bs, rest = n - r0;
-        if ((int)blockIdx.y * TILE >= rest || (int)blockIdx.z * TILE >= s) return;
-        gemm_tile_sub(L + F.l_off + (int64_t)r0 * F.ns + kb, F.ns, w + (int64_t)kb * s, s, w + (int64_t)r0 * s, s, rest, s, bs,
-                      blockIdx.y, blockIdx.z);
+    --t;
+    if (!backward) {
+        const int r0 = kb + bs, rest = n - r0;
+        if (t * BM >= rest) return;
+        gemm_tile(L + F.l_off + (int64_t)r0 * F.ns + kb, F.ns, wk, s, w + (int64_t)r0 * s, s, rest, s, bs, t, blockIdx.z, 0);
     } else {
-        if ((int)blockIdx.y * TILE >= kb || (int)blockIdx.z * TILE >= s) return;
-        gemm_tile_sub(L + F.l_off + kb, F.ns, w + (int64_t)kb * s, s, w, s, kb, s, bs, blockIdx.y, blockIdx.z);
+        if (t * BM >= kb) return;
+        gemm_tile(L + F.l_off + kb, F.ns, wk, s, w, s, kb, s, bs, t, blockIdx.z, 0);
     }
+}
+// backward boundary update  W[0:ns] -= U12[ns x nb] W[ns:n]
+__global__ void __launch_bounds__(256, 2)
+k_solve_boundary(int first, int s, const FrontDev *__restrict__ fronts, const double *__restrict__ U, double *__restrict__ W) {
+    FrontDev F = fronts[first + blockIdx.x];
+    if (F.nb == 0 || (int)blockIdx.y * BM >= F.ns || (int)blockIdx.z * BN >= s) return;
+    double *w = W + F.w_off;
+    gemm_tile(U + F.u_off, F.nb, w + (int64_t)F.ns * s, s, w, s, F.ns, s, F.nb, blockIdx.y, blockIdx.z, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,7 +595,7 @@ static void analyse(Ctx *c) {
     d.level_max_children.assign(d.n_levels, 0);
     d.level_f_total.assign(d.n_levels, 0); d.level_n_total.assign(d.n_levels, 0);
     std::vector<uint8_t> front_level(nf);
-    int64_t l_total = 0, u_total = 0;
+    int64_t l_total = 0, u_total = 0, inv_total = 0;
     for (int l = 0; l < d.n_levels; ++l) {
         int64_t foff = 0, noff = 0;
         for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
@@ -427,6 +610,7 @@ static void analyse(Ctx *c) {
             F.w_off = noff; noff += n;             // scaled by s at solve time
             F.l_off = l_total; l_total += n * fs.ns;
             F.u_off = u_total; u_total += (int64_t)fs.ns * fs.nb;
+            F.inv_off = inv_total; inv_total += (int64_t)((fs.ns + NB - 1) / NB) * (2 * NB * NB);
             front_level[q] = (uint8_t)l;
             d.level_max_ns[l] = std::max(d.level_max_ns[l], fs.ns);
             d.level_max_nb[l] = std::max(d.level_max_nb[l], fs.nb);
@@ -447,7 +631,19 @@ static void analyse(Ctx *c) {
     d.dof_front_lm.upload(dof_front_lm.data(), (int64_t)dof_front_lm.size(), st);
     DevBuf<uint8_t> d_front_level;
     d_front_level.upload(front_level.data(), nf, st);
-    d.L.resize(l_total); d.U.resize(u_total);
+    d.L.resize(l_total); d.U.resize(u_total); d.inv.resize(inv_total);
+    d.L.zero(st);
+    d.fronts_s = 0;
+    if (!d.attrs_set) {
+        PN_CUDA(cudaFuncSetAttribute(k_lu_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_lu_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_lu_panels, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_lu_update, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_store_panels, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_solve_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        d.attrs_set = true;
+    }
     d.status.resize(1);
     d.status.zero(st);
     // per-entry destination maps
@@ -487,12 +683,16 @@ static void analyse(Ctx *c) {
 static void factorise(Ctx *c, const double *vals11) {
     DirectSolver &d = *c->direct;
     cudaStream_t st = c->stream;
+    static const bool debug_levels = getenv("PN_DEBUG_LEVELS") != nullptr;
+    cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
+    if (debug_levels) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); }
     const CsrBlock &A = c->blk[0];
     d.status.zero(st);
     for (int l = 0; l < d.n_levels; ++l) {
         int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
         if (!nfl) continue;
         double *arena = d.arena[l & 1].ptr;
+        if (debug_levels) cudaEventRecord(dbg0, st);
         PN_CUDA(cudaMemsetAsync(arena, 0, sizeof(double) * d.level_f_total[l], st));
         { ProfScope ps_(c, PS_FRONT_ASSEMBLE); k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
                                                                   d.fronts.ptr, vals11, arena); }
@@ -508,23 +708,58 @@ static void factorise(Ctx *c, const double *vals11) {
             }
         }
         int maxns = d.level_max_ns[l], maxn = d.level_max_n[l];
-        for (int kb = 0; kb < maxns; kb += NB) {
-            { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 256, 0, st>>>(first, kb, d.fronts.ptr, arena, d.status.ptr); }
-            int rest = maxn - kb - 1;
-            if (rest > 0) {
-                int tiles = (rest + 127) / 128;
-                { ProfScope ps_(c, PS_LU_PANELS); k_lu_panels<<<dim3(nfl, 2 * tiles), 128, 0, st>>>(first, kb, tiles, d.fronts.ptr, arena); }
-                int gt = (rest + TILE - 1) / TILE;
-                { ProfScope ps_(c, PS_LU_UPDATE); k_lu_update<<<dim3(nfl, gt, gt), 256, 0, st>>>(first, kb, d.fronts.ptr, arena); }
-                c->count_launch(2);
+        for (int g0 = 0; g0 < maxns; g0 += GB) {
+            int gend = std::min(g0 + GB, maxns);
+            for (int kb = g0; kb < gend; kb += NB) {
+                { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 128, DIAG_SMEM, st>>>(first, kb, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr); }
+                c->count_launch();
+                int rest = maxn - kb - 1;          // upper bound of the trailing size over the level's fronts
+                if (rest > 0) {
+                    int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
+                    { ProfScope ps_(c, PS_LU_PANELS); k_lu_panels<<<dim3(nfl, tiles_u + tiles_l), 256, GEMM_SMEM, st>>>(first, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr); }
+                    c->count_launch();
+                    if (kb + NB < gend) {
+                        int wa = gend - kb - NB;       // strips inside the group
+                        int tiles = ((rest + BM - 1) / BM) * ((wa + BN - 1) / BN) + ((wa + BM - 1) / BM) * tiles_u;
+                        { ProfScope ps_(c, PS_LU_PANELS); k_lu_strip<<<dim3(nfl, tiles), 256, GEMM_SMEM, st>>>(first, kb, g0, d.fronts.ptr, arena); }
+                        c->count_launch();
+                    }
+                }
             }
-            c->count_launch();
+            int rest = maxn - g0 - 1;
+            if (rest > 0) {
+                int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
+                { ProfScope ps_(c, PS_LU_UPDATE); k_lu_update<<<dim3(nfl, tiles_l, tiles_u), 256, GEMM_SMEM, st>>>(first, g0, d.fronts.ptr, arena); }
+                c->count_launch();
+            }
         }
-        int64_t per = (int64_t)maxn * std::max(maxns, 1) * 2;
-        unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((per + 255) / 256, 1), 2048);
-        { ProfScope ps_(c, PS_COPY_FACTORS); k_copy_factors<<<dim3(nfl, gy), 256, 0, st>>>(first, d.fronts.ptr, arena, d.L.ptr, d.U.ptr); }
-        c->count_launch();
+        {
+            ProfScope ps_(c, PS_COPY_FACTORS);
+            int steps = (maxns + NB - 1) / NB;
+            int row_tiles = (maxn + BM - 1) / BM + 1;
+            if (steps > 0) k_store_panels<<<dim3(nfl, steps, row_tiles), 256, GEMM_SMEM, st>>>(first, d.fronts.ptr, arena, d.inv.ptr, d.L.ptr);
+            if (d.level_max_nb[l] > 0) {
+                int64_t per = (int64_t)maxns * d.level_max_nb[l];
+                unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((per + 255) / 256, 1), 2048);
+                k_copy_u12<<<dim3(nfl, gy), 256, 0, st>>>(first, d.fronts.ptr, arena, d.U.ptr);
+            }
+            c->count_launch(2);
+        }
+        if (debug_levels) {
+            cudaEventRecord(dbg1, st);
+            cudaEventSynchronize(dbg1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, dbg0, dbg1);
+            double fl = 0;
+            for (int q = first; q < first + nfl; ++q) {
+                double ns = d.h_fronts[q].ns, nb = d.h_fronts[q].nb;
+                fl += 2.0 / 3.0 * ns * ns * ns + 2.0 * ns * ns * nb + 2.0 * ns * nb * nb;
+            }
+            fprintf(stderr, "[pn] level %2d: %6d fronts, max ns %5d, max n %5d, arena %8.1f MB, %8.3f ms, %7.2f GFLOP -> %6.2f TFLOP/s\n",
+                    l, nfl, maxns, maxn, d.level_f_total[l] * 8e-6, ms, fl * 1e-9, fl / (ms * 1e-3) * 1e-12);
+        }
     }
+    if (debug_levels) { cudaEventDestroy(dbg0); cudaEventDestroy(dbg1); }
     int status = 0;
     PN_CUDA(cudaMemcpyAsync(&status, d.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
@@ -537,13 +772,18 @@ static void solve_inplace(Ctx *c, double *X, int s) {
     cudaStream_t st = c->stream;
     int64_t wmax = 0;
     for (int l = 0; l < d.n_levels; ++l) wmax = std::max(wmax, d.level_n_total[l]);
-    d.warena[0].resize(wmax * s); d.warena[1].resize(wmax * s);
+    d.warena[0].resize(wmax * s); d.warena[1].resize(wmax * s); d.yarena.resize(wmax * s);
     // workspace offsets were stored per unit column; scale once per s
-    std::vector<FrontDev> hf = d.h_fronts;
-    for (auto &F : hf) F.w_off *= s;
-    DevBuf<FrontDev> fr;
-    fr.upload(hf.data(), (int64_t)hf.size(), st);
-    int gz = (s + TILE - 1) / TILE;
+    if (d.fronts_s != s) {
+        std::vector<FrontDev> hf = d.h_fronts;
+        for (auto &F : hf) F.w_off *= s;
+        d.fronts_scaled.upload(hf.data(), (int64_t)hf.size(), st);
+        PN_CUDA(cudaStreamSynchronize(st));
+        d.fronts_s = s;
+    }
+    const FrontDev *fr = d.fronts_scaled.ptr;
+    double *Y = d.yarena.ptr;
+    int gz = (s + BN - 1) / BN;
     // forward sweep
     for (int l = 0; l < d.n_levels; ++l) {
         int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
@@ -551,29 +791,25 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
-        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr.ptr, d.fidx.ptr, X, W); }
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr, d.fidx.ptr, X, W); }
         c->count_launch();
         if (l > 0) {
             int cfirst = d.level_ptr[l - 1], ncl = d.level_ptr[l] - cfirst;
             unsigned gyc = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)d.level_max_nb[l - 1] * s + 255) / 256, 1), 1024);
             for (int r = 0; r < d.level_max_children[l - 1]; ++r) {
-                { ProfScope ps_(c, PS_SOLVE_MISC); k_solve_extend_add<<<dim3(ncl, gyc), 256, 0, st>>>(cfirst, ncl, r, s, fr.ptr, d.rel.ptr,
+                { ProfScope ps_(c, PS_SOLVE_MISC); k_solve_extend_add<<<dim3(ncl, gyc), 256, 0, st>>>(cfirst, ncl, r, s, fr, d.rel.ptr,
                                                                     d.warena[(l - 1) & 1].ptr, W); }
                 c->count_launch();
             }
         }
         for (int kb = 0; kb < maxns; kb += NB) {
-            { ProfScope ps_(c, PS_SOLVE_DIAG); k_solve_diag<<<dim3(nfl, (s + 127) / 128), 128, 0, st>>>(first, kb, s, 0, fr.ptr, d.L.ptr, W); }
-            int rest = maxn - kb - 1;
-            if (rest > 0) {
-                { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_update<<<dim3(nfl, (rest + TILE - 1) / TILE, gz), 256, 0, st>>>(first, kb, s, 0, fr.ptr, d.L.ptr,
-                                                                                        d.U.ptr, W); }
-                c->count_launch();
-            }
+            int rest = std::max(maxn - kb - 1, 0);
+            int tiles = 1 + (rest + BM - 1) / BM;
+            { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_step<<<dim3(nfl, tiles, gz), 256, GEMM_SMEM, st>>>(first, kb, s, 0, fr, d.L.ptr, d.inv.ptr, W, Y); }
             c->count_launch();
         }
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
-        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr.ptr, d.fidx.ptr, W, X); }
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
         c->count_launch();
     }
     // backward sweep
@@ -583,26 +819,22 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
-        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 1, fr.ptr, d.fidx.ptr, X, W); }
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 1, fr, d.fidx.ptr, X, W); }
         c->count_launch();
         if (d.level_max_nb[l] > 0) {
-            { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_update<<<dim3(nfl, (maxns + TILE - 1) / TILE, gz), 256, 0, st>>>(first, 0, s, 2, fr.ptr, d.L.ptr, d.U.ptr, W); }
+            { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_boundary<<<dim3(nfl, (maxns + BM - 1) / BM, gz), 256, GEMM_SMEM, st>>>(first, s, fr, d.U.ptr, W); }
             c->count_launch();
         }
         int last_kb = ((maxns - 1) / NB) * NB;
         for (int kb = last_kb; kb >= 0; kb -= NB) {
-            { ProfScope ps_(c, PS_SOLVE_DIAG); k_solve_diag<<<dim3(nfl, (s + 127) / 128), 128, 0, st>>>(first, kb, s, 1, fr.ptr, d.L.ptr, W); }
+            int tiles = 1 + (kb + BM - 1) / BM;
+            { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_step<<<dim3(nfl, tiles, gz), 256, GEMM_SMEM, st>>>(first, kb, s, 1, fr, d.L.ptr, d.inv.ptr, W, Y); }
             c->count_launch();
-            if (kb > 0) {
-                { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_update<<<dim3(nfl, (kb + TILE - 1) / TILE, gz), 256, 0, st>>>(first, kb, s, 1, fr.ptr, d.L.ptr, d.U.ptr, W); }
-                c->count_launch();
-            }
         }
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
-        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr.ptr, d.fidx.ptr, W, X); }
+        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
         c->count_launch();
     }
-    PN_CUDA(cudaStreamSynchronize(st));
 }
 
 // ---- residual / refinement helpers ------------------------------------------------------------------
@@ -628,6 +860,14 @@ void direct_release(Ctx *c) {
     c->direct = nullptr;
 }
 
+// The model changed: the elimination tree must be rebuilt, but the (grow-only) device buffers are kept so
+// that re-analysing a model of the same size performs no cudaMalloc / cudaFree.
+void direct_invalidate(Ctx *c) {
+    if (!c->direct) return;
+    c->direct->analysed = false;
+    c->direct->fronts_s = 0;
+}
+
 void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solve_opts &o) {
     cudaStream_t st = c->stream;
     int64_t n1 = c->n1;
@@ -637,21 +877,33 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
     }
     DirectSolver &d = *c->direct;
     int refine = o.refine_steps >= 0 ? o.refine_steps : 1;
-    DevBuf<double> R, AX;
+    DevBuf<double> &R = c->work_r;
     if (!percol) {
         { PhaseTimer tm(c, &c->stats.ms_factor); factorise(c, vals11); }
         PhaseTimer tm(c, &c->stats.ms_solve);
         PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * n1 * s, cudaMemcpyDeviceToDevice, st));
         solve_inplace(c, c->X.ptr, s);
-        if (refine > 0) { R.resize(n1 * s); AX.resize(n1 * s); }
+        if (refine > 0) R.resize(n1 * s);
+        // Iterative refinement with a double-double residual: each correction d shrinks the forward error by
+        // rho ~ cond(K11) * 2^-53.  rho is estimated per column as |d| / |x| of the first correction; refinement
+        // stops as soon as the error predicted after applying d (rho * |d| / |x| = rho^2) is below 1e-11.
+        std::vector<double> dd(s), xx(s);
         for (int it = 0; it < refine; ++it) {
-            spmm(c, c->blk[0], vals11, c->X.ptr, AX.ptr, s, st);
+            residual_dd(c, c->blk[0], vals11, 0, c->X.ptr, c->B.ptr, R.ptr, s, st);
             c->stats.spmm_launches += 1;
-            { ProfScope ps_(c, PS_SOLVE_MISC); k_residual<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, c->B.ptr, AX.ptr, R.ptr); }
             solve_inplace(c, R.ptr, s);
+            column_dots(c, n1, s, R.ptr, R.ptr, dd.data());
+            column_dots(c, n1, s, c->X.ptr, c->X.ptr, xx.data());
             { ProfScope ps_(c, PS_SOLVE_MISC); k_axpy1<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, R.ptr, c->X.ptr); }
-            c->count_launch(2);
+            c->count_launch();
             c->stats.iterations += 1;
+            double worst = 0.0;
+            for (int j = 0; j < s; ++j) {
+                double rho = xx[j] > 0 ? std::sqrt(dd[j] / xx[j]) : (dd[j] > 0 ? 1.0 : 0.0);
+                if (!(rho == rho)) rho = 1.0;
+                worst = std::max(worst, rho);
+            }
+            if (worst * worst < 1e-11) break;
         }
     } else {
         // one matrix per column (P-Delta): factorise and solve column by column
@@ -667,11 +919,10 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
             PN_CUDA(cudaMemcpyAsync(d.col_out.ptr, d.col_in.ptr, sizeof(double) * n1, cudaMemcpyDeviceToDevice, st));
             solve_inplace(c, d.col_out.ptr, 1);
             for (int it = 0; it < refine; ++it) {
-                spmm(c, A, vj, d.col_out.ptr, ax.ptr, 1, st);
-                { ProfScope ps_(c, PS_SOLVE_MISC); k_residual<<<grid_for(n1, 256), 256, 0, st>>>(n1, d.col_in.ptr, ax.ptr, ax.ptr); }
+                residual_dd(c, A, vj, 0, d.col_out.ptr, d.col_in.ptr, ax.ptr, 1, st);
                 solve_inplace(c, ax.ptr, 1);
                 { ProfScope ps_(c, PS_SOLVE_MISC); k_axpy1<<<grid_for(n1, 256), 256, 0, st>>>(n1, ax.ptr, d.col_out.ptr); }
-                c->count_launch(2);
+                c->count_launch();
             }
             k_set_col<<<grid_for(n1, 256), 256, 0, st>>>(n1, s, j, d.col_out.ptr, c->X.ptr);
             c->count_launch(2);

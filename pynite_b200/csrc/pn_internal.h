@@ -201,6 +201,8 @@ struct Ctx {
     PcgWork *pcg = nullptr;
 
     DevBuf<uint8_t> cub_tmp;       // scratch for cub device-wide primitives
+    // persistent work arrays: a steady-state step performs no cudaMalloc / cudaFree
+    DevBuf<double> work_r, work_ax, work_rx, dots_partial, dots_out;
     Profiler prof;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // pn_timer_start / pn_timer_stop
 };
@@ -272,6 +274,8 @@ void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev /* [n
 int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap);
 // Y = A X for a CSR block, X/Y row-major with s columns
 void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st);
+void residual_dd(Ctx *c, const CsrBlock &A, const double *vals, int64_t vals_col_stride, const double *X, const double *B,
+                 double *R, int s, cudaStream_t st);
 void spmv_plain(Ctx *c, const CsrBlock &A, const double *vals, const double *x, double *y, cudaStream_t st);
 
 // ---- pn_pcg.cu / pn_direct.cu ---------------------------------------------------------------------
@@ -282,5 +286,6 @@ void pcg_release(Ctx *c);
 void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host);
 void direct_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
 void direct_release(Ctx *c);
+void direct_invalidate(Ctx *c);
 
 }  // namespace pn

@@ -200,7 +200,7 @@ __global__ void k_copy_s(int s, const double *__restrict__ a, double *__restrict
 void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host) {
     if (s > 256) throw ArgError("column_dots: at most 256 columns");
     const int grid = 148 * 4;
-    DevBuf<double> partial, out;
+    DevBuf<double> &partial = c->dots_partial, &out = c->dots_out;
     partial.resize((int64_t)grid * s);
     out.resize(s);
     { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_partial<<<grid, RED_TPB, 0, c->stream>>>(n, s, A, B, partial.ptr, 0, 1); }
