@@ -16,6 +16,7 @@ import numpy as np
 import scipy.sparse as sps
 
 from pynite_b200 import engine as _eng
+from pynite_b200 import sharding as _sh
 from pynite_b200.LoadCombo import LoadCombo
 from pynite_b200.flatten import NodeIndex, flatten_model
 
@@ -92,7 +93,8 @@ def identify_combos(model, combo_tags=None):
 
 def _engine(model):
     if model._engine is None:
-        model._engine = _eng.Engine(getattr(model, 'device', 0))
+        import os
+        model._engine = _eng.Engine(getattr(model, 'device', int(os.environ.get('LOCAL_RANK', '0'))))
     return model._engine
 
 
@@ -168,24 +170,37 @@ def run_linear(model, log, check_stability, check_statics, sparse, combo_tags):
     prepare_model(model)
     combo_list = identify_combos(model, combo_tags)
     first = list(model.load_combos.keys())[0]
-    A, eng = _upload(model, combo_list, first)
+    # One process per GPU (torch.distributed initialised by the caller): every rank assembles and factorises K
+    # and solves its own contiguous block of combos; results are all-gathered so each rank ends up with all.
+    rank, ws = _sh.world()
+    distribute = ws > 1 and getattr(model, 'distribute_combos', True)
+    local_list = [combo_list[i] for i in _sh.shard_combos(len(combo_list), rank, ws)] if distribute else combo_list
+    A, eng = _upload(model, local_list, first)
     t1 = time.perf_counter()
     eng.reset_stats()
-    model._run = RunState(A, [c.name for c in combo_list])
+    model._run = RunState(A, [c.name for c in local_list])
     # the reference keeps the P-Delta end-force branch alive until `solution` is reset
     model._run.pdelta = model.solution == 'P-Delta'
     _assemble(model, eng, check_stability, log)
-    if combo_list:
+    D = np.zeros((0, A.n_dof))
+    R = np.zeros((0, A.n_dof))
+    if local_list:
         if log:
-            print('- Solving ' + str(len(combo_list)) + ' load combination(s)')
+            print('- Solving ' + str(len(local_list)) + ' load combination(s)')
         try:
             D, R, st = eng.solve_linear(_opts(check_stability), reactions=not model._run.pdelta)
         except _eng.SingularMatrix:
             raise Exception(_eng.SINGULAR_MSG)
         if model._run.pdelta:
-            R = np.stack([eng.reactions(i, True).reshape(-1) for i in range(len(combo_list))])
-        _store(model, combo_list, D, R)
-        model.last_stats = eng.stats().as_dict()
+            R = np.stack([eng.reactions(i, True).reshape(-1) for i in range(len(local_list))])
+    model.last_stats = eng.stats().as_dict()
+    if distribute:
+        import torch.distributed as dist
+        dev = ('cuda:%d' % eng.device) if dist.get_backend() == 'nccl' else None
+        counts = [len(_sh.shard_combos(len(combo_list), r, ws)) for r in range(ws)]
+        D = _sh.all_gather_rows(D, counts, dev)
+        R = _sh.all_gather_rows(R, counts, dev)
+    _store(model, combo_list, D, R)
     t2 = time.perf_counter()
     if model.last_stats is not None:
         model.last_stats['host_prepare_s'] = t1 - t0
