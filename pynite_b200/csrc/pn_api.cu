@@ -87,11 +87,19 @@ void ensure_symbolic(Ctx *c, uint32_t flags) {
     direct_invalidate(c);
     PhaseTimer tm(c, &c->stats.ms_symbolic);
     build_symbolic(c, flags);
+    fast_assembly_build(c);
     c->loads.vectors_ready = c->loads.vectors_ready && c->incidence_ready;
 }
 
-void assemble(Ctx *c) {
+// refresh: recompute the element values from the device-resident model first (a numeric re-assembly)
+void assemble(Ctx *c, bool refresh) {
+    bool done = false;
     {
+        PhaseTimer tm(c, &c->stats.ms_scatter);
+        done = fast_assembly_run(c, c->vals.ptr);      // element classes + block gather: no COO value reaches HBM
+    }
+    if (!done) {
+        if (refresh) compute_ev(c);
         PhaseTimer tm(c, &c->stats.ms_scatter);
         scatter_add_values(c, c->ev.ptr, c->vals.ptr);
     }
@@ -104,7 +112,7 @@ void assemble(Ctx *c) {
 
 void ensure_assembled(Ctx *c, uint32_t flags) {
     ensure_symbolic(c, flags);
-    if (!c->vals_ready) assemble(c);
+    if (!c->vals_ready) assemble(c, false);
 }
 
 void ensure_loads(Ctx *c) {
@@ -252,6 +260,7 @@ void pn_destroy(pn_ctx *ctx) {
     cudaStreamSynchronize(c->stream);
     direct_release(c);
     pcg_release(c);
+    fast_assembly_release(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->tm0) cudaEventDestroy(c->tm0);
@@ -305,6 +314,7 @@ int pn_set_springs(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *ks, 
     m.n_springs = n;
     m.h_spring_ij.assign(ij, ij + 2 * n);
     m.h_spring_active.assign(active, active + n);
+    m.h_spring_ks.assign(ks, ks + n);
     m.spring_ij.upload(ij, 2 * n, c->stream);
     m.spring_ks.upload(ks, n, c->stream);
     m.spring_active.upload(active, n, c->stream);
@@ -322,6 +332,9 @@ int pn_set_members(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *prop
     m.n_members = n;
     m.h_mem_ij.assign(ij, ij + 2 * n);
     m.h_mem_active.assign(active, active + n);
+    m.h_mem_props.assign(props, props + 6 * n);
+    m.h_mem_rot.assign(rotation_deg, rotation_deg + n);
+    m.h_mem_rel.assign(releases, releases + n);
     m.mem_ij.upload(ij, 2 * n, c->stream);
     m.mem_props.upload(props, 6 * n, c->stream);
     m.mem_rot.upload(rotation_deg, n, c->stream);
@@ -338,6 +351,7 @@ static void set_shells(Ctx *c, bool quad, int64_t n, const int32_t *ijmn, const 
     invalidate(c);
     (quad ? m.n_quads : m.n_plates) = n;
     (quad ? m.h_quad_ijmn : m.h_plate_ijmn).assign(ijmn, ijmn + 4 * n);
+    (quad ? m.h_quad_props : m.h_plate_props).assign(props, props + 5 * n);
     (quad ? m.quad_ijmn : m.plate_ijmn).upload(ijmn, 4 * n, c->stream);
     (quad ? m.quad_props : m.plate_props).upload(props, 5 * n, c->stream);
     // the membrane matrix is unsymmetric when kx_mod != ky_mod (Quad3D.py:517-519)
@@ -451,9 +465,9 @@ int pn_get_block(pn_ctx *ctx, int block, int32_t *indptr, int32_t *indices, doub
 
 int pn_assemble_ke(pn_ctx *ctx) {
     PN_API_BEGIN(ctx)
-    if (c->symbolic_ready) compute_ev(c);      // numeric re-assembly on a fixed pattern
+    bool refresh = c->symbolic_ready;          // numeric re-assembly on a fixed pattern
     ensure_symbolic(c, c->symbolic_ready ? c->sym_flags : 0u);
-    assemble(c);
+    assemble(c, refresh);
     PN_CUDA(cudaStreamSynchronize(c->stream));
     PN_API_END
 }

@@ -354,32 +354,33 @@ __global__ void k_forces_to_local(int64_t n, const int32_t *__restrict__ conn, c
 // ------------------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
+void launch_element_ke_arrays(Ctx *c, const ElemInputs &in, double *out_spring, double *out_member, double *out_quad,
+                              double *out_plate, cudaStream_t st) {
+    if (in.n_springs) {
+        { ProfScope ps_(c, PS_ELEM_KE); k_spring_ke<<<grid_for(in.n_springs, 64), 64, 0, st>>>(in.n_springs, in.spring_ij, in.spring_ks, in.xyz, out_spring); }
+        c->count_launch();
+    }
+    if (in.n_members) {
+        { ProfScope ps_(c, PS_ELEM_KE); k_member_matrix<<<grid_for(in.n_members, 64), 64, 0, st>>>(in.n_members, in.mem_ij, in.mem_props, in.mem_rot, in.mem_rel, in.xyz, 0, nullptr, out_member); }
+        c->count_launch();
+    }
+    if (in.n_quads) {
+        { ProfScope ps_(c, PS_ELEM_KE); k_shell_ke<true><<<grid_for(in.n_quads, SHELL_EPB), SHELL_TPB, 0, st>>>(in.n_quads, in.quad_ijmn, in.quad_props, in.xyz, out_quad); }
+        c->count_launch();
+    }
+    if (in.n_plates) {
+        { ProfScope ps_(c, PS_ELEM_KE); k_shell_ke<false><<<grid_for(in.n_plates, SHELL_EPB), SHELL_TPB, 0, st>>>(in.n_plates, in.plate_ijmn, in.plate_props, in.xyz, out_plate); }
+        c->count_launch();
+    }
+}
+
 void launch_element_ke(Ctx *c, cudaStream_t st) {
     const Model &m = c->model;
+    ElemInputs in{m.n_springs, m.n_members, m.n_quads, m.n_plates, m.spring_ij.ptr, m.spring_ks.ptr, m.mem_ij.ptr,
+                  m.mem_props.ptr, m.mem_rot.ptr, m.mem_rel.ptr, m.quad_ijmn.ptr, m.quad_props.ptr, m.plate_ijmn.ptr,
+                  m.plate_props.ptr, m.xyz.ptr};
     double *ev = c->ev.ptr;
-    if (m.n_springs) {
-        { ProfScope ps_(c, PS_ELEM_KE); k_spring_ke<<<grid_for(m.n_springs, 64), 64, 0, st>>>(m.n_springs, m.spring_ij.ptr, m.spring_ks.ptr,
-                                                               m.xyz.ptr, ev + c->ev_off_spring); }
-        c->count_launch();
-    }
-    if (m.n_members) {
-        { ProfScope ps_(c, PS_ELEM_KE); k_member_matrix<<<grid_for(m.n_members, 64), 64, 0, st>>>(m.n_members, m.mem_ij.ptr, m.mem_props.ptr,
-                                                                   m.mem_rot.ptr, m.mem_rel.ptr, m.xyz.ptr, 0, nullptr,
-                                                                   ev + c->ev_off_member); }
-        c->count_launch();
-    }
-    if (m.n_quads) {
-        { ProfScope ps_(c, PS_ELEM_KE); k_shell_ke<true><<<grid_for(m.n_quads, SHELL_EPB), SHELL_TPB, 0, st>>>(m.n_quads, m.quad_ijmn.ptr,
-                                                                                m.quad_props.ptr, m.xyz.ptr,
-                                                                                ev + c->ev_off_quad); }
-        c->count_launch();
-    }
-    if (m.n_plates) {
-        { ProfScope ps_(c, PS_ELEM_KE); k_shell_ke<false><<<grid_for(m.n_plates, SHELL_EPB), SHELL_TPB, 0, st>>>(m.n_plates, m.plate_ijmn.ptr,
-                                                                                  m.plate_props.ptr, m.xyz.ptr,
-                                                                                  ev + c->ev_off_plate); }
-        c->count_launch();
-    }
+    launch_element_ke_arrays(c, in, ev + c->ev_off_spring, ev + c->ev_off_member, ev + c->ev_off_quad, ev + c->ev_off_plate, st);
 }
 
 void launch_member_kg(Ctx *c, const double *P_dev, double *out_dev, cudaStream_t st) {

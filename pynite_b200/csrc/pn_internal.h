@@ -87,6 +87,8 @@ struct Model {
     std::vector<uint8_t> h_support, h_enf_mask, h_nspring_flag, h_spring_active, h_mem_active;
     std::vector<double> h_enf_val, h_nspring_k, h_xyz;
     std::vector<int32_t> h_spring_ij, h_mem_ij, h_quad_ijmn, h_plate_ijmn;
+    std::vector<double> h_spring_ks, h_mem_props, h_mem_rot, h_quad_props, h_plate_props;
+    std::vector<uint16_t> h_mem_rel;
     bool symmetric = true;      // false when a shell has kx_mod != ky_mod (membrane matrix unsymmetric)
 };
 
@@ -142,6 +144,16 @@ struct Profiler {
 };
 
 struct DirectSolver;   // pn_direct.cu
+struct FastAssembly;   // pn_assemble.cu
+
+struct ElemInputs {
+    int64_t n_springs, n_members, n_quads, n_plates;
+    const int32_t *spring_ij; const double *spring_ks;
+    const int32_t *mem_ij; const double *mem_props, *mem_rot; const uint16_t *mem_rel;
+    const int32_t *quad_ijmn; const double *quad_props;
+    const int32_t *plate_ijmn; const double *plate_props;
+    const double *xyz;
+};
 struct PcgWork;        // pn_pcg.cu
 
 struct Ctx {
@@ -199,6 +211,7 @@ struct Ctx {
 
     DirectSolver *direct = nullptr;
     PcgWork *pcg = nullptr;
+    FastAssembly *fast = nullptr;
 
     DevBuf<uint8_t> cub_tmp;       // scratch for cub device-wide primitives
     // persistent work arrays: a steady-state step performs no cudaMalloc / cudaFree
@@ -252,6 +265,8 @@ struct PhaseTimer {
 
 // ---- pn_elements.cu -------------------------------------------------------------------------------
 void launch_element_ke(Ctx *c, cudaStream_t st);
+void launch_element_ke_arrays(Ctx *c, const ElemInputs &in, double *out_spring, double *out_member, double *out_quad,
+                              double *out_plate, cudaStream_t st);
 void launch_member_kg(Ctx *c, const double *P_dev, double *out_dev, cudaStream_t st);
 void launch_member_axial(Ctx *c, const double *D_dev, double *P_dev, cudaStream_t st);
 void launch_member_fer_groups(Ctx *c, cudaStream_t st);
@@ -277,6 +292,11 @@ void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double
 void residual_dd(Ctx *c, const CsrBlock &A, const double *vals, int64_t vals_col_stride, const double *X, const double *B,
                  double *R, int s, cudaStream_t st);
 void spmv_plain(Ctx *c, const CsrBlock &A, const double *vals, const double *x, double *y, cudaStream_t st);
+
+// ---- pn_assemble.cu -------------------------------------------------------------------------------
+void fast_assembly_build(Ctx *c);             // symbolic: element classes + block-gather maps (after build_symbolic)
+bool fast_assembly_run(Ctx *c, double *vals); // numeric: false when unavailable / a class check failed (caller falls back)
+void fast_assembly_release(Ctx *c);
 
 // ---- pn_pcg.cu / pn_direct.cu ---------------------------------------------------------------------
 // Solve K11 X = B for all s columns; `vals11` may differ per column when per_column_vals != 0

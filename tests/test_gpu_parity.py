@@ -87,6 +87,39 @@ def test_assembly_is_deterministic(eng, name):
     assert np.array_equal(v1, eng.csr_values())
 
 
+@pytest.mark.parametrize('name', FIXTURES + ['synthetic_plate', 'synthetic_frame', 'synthetic_mat'])
+def test_class_gather_assembly_equals_general_path(eng, name):
+    """The class-based block-gather assembly (pn_assemble.cu) must reproduce the general path (dense element
+    values + k_scatter_add) bit for bit: same addends in the same order."""
+    import os
+    from pynite_b200 import synthetic
+    if name == 'synthetic_plate':
+        A = synthetic.quad_plate_arrays(n=37, n_combos=2)
+    elif name == 'synthetic_frame':
+        A = synthetic.moment_frame_arrays(bays_x=4, bays_z=3, stories=5, n_combos=2)
+    elif name == 'synthetic_mat':
+        A = synthetic.quad_plate_arrays(n=23, n_combos=2, mat_springs=0.1)
+    else:
+        A, _, _ = load_fixture(name)
+    out = []
+    for disable in (True, False):
+        if disable:
+            os.environ['PN_DISABLE_FAST_ASSEMBLY'] = '1'
+        else:
+            os.environ.pop('PN_DISABLE_FAST_ASSEMBLY', None)
+        try:
+            _upload(eng, A)
+            eng.symbolic(0)
+            eng.assemble_ke()
+            v1 = eng.csr_values().copy()
+            eng.assemble_ke()                 # numeric re-assembly on the fixed pattern
+            assert np.array_equal(v1, eng.csr_values())
+            out.append(v1)
+        finally:
+            os.environ.pop('PN_DISABLE_FAST_ASSEMBLY', None)
+    assert np.array_equal(out[0], out[1])
+
+
 @pytest.mark.parametrize('name', FIXTURES)
 def test_load_vectors(eng, name):
     A, ref, _ = load_fixture(name)
