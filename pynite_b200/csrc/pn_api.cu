@@ -244,6 +244,9 @@ int pn_create(pn_ctx **out, int device_id) {
     Ctx *c = new Ctx();
     c->device = device_id;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         cudaGetLastError();
         delete c;
@@ -266,9 +269,12 @@ void pn_destroy(pn_ctx *ctx) {
     if (c->tm0) cudaEventDestroy(c->tm0);
     if (c->tm1) cudaEventDestroy(c->tm1);
     for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
-    cudaStream_t st = c->stream;
+    cudaStream_t st = c->stream, st2 = c->stream2;
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     if (st) cudaStreamDestroy(st);
+    if (st2) cudaStreamDestroy(st2);
 }
 
 const char *pn_last_error(pn_ctx *ctx) { return ctx ? C(ctx)->err.c_str() : "null context"; }
@@ -818,7 +824,7 @@ int pn_get_stats(pn_ctx *ctx, pn_stats *out) {
 static const char *kSlotNames[PS_COUNT] = {
     "element_ke", "scatter_add", "gather_blocks", "build_rhs", "spmm", "front_assemble", "extend_add", "lu_diag",
     "lu_panels", "lu_update", "copy_factors", "solve_gather_store", "solve_diag", "solve_update", "solve_misc",
-    "reactions", "pcg_vector", "merge_displacements"};
+    "reactions", "pcg_vector", "merge_displacements", "assembly_total"};
 
 const char *pn_profile_slot_name(int slot) { return (slot >= 0 && slot < PS_COUNT) ? kSlotNames[slot] : nullptr; }
 

@@ -21,6 +21,7 @@
 
 #include "elem_line.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -43,7 +44,16 @@ struct FastAssembly {
     DevBuf<uint16_t> rep_rel;
     DevBuf<uint32_t> node_pair_ptr, pair_cptr;
     DevBuf<Contrib> contrib;
-    DevBuf<uint16_t> slot_code;
+    DevBuf<uint16_t> slot_code, rowpair_code;
+    DevBuf<uint32_t> node_recipe, recipe_ptr, recipe_tuples, nsp_first;
+    DevBuf<uint16_t> recipe_tuples16;
+    DevBuf<double> recipe_vals;
+    int64_t recipe_slots = 0;
+    bool idx16 = false;
+    DevBuf<uint8_t> recipe_nsp;
+    int width = 0;
+    bool recipes = false;
+    int max_pairs = 0;
     DevBuf<int> flag;
 };
 
@@ -113,24 +123,21 @@ __global__ void k_verify_classes(int kind, int64_t n, const int32_t *__restrict_
     if (!same) atomicOr(flag, 1);
 }
 
-// One warp per node a: for each of its six rows the lanes walk the stored entries (coalesced), decode the
-// (node pair, column DOF) of each slot and sum the contributing element-class entries in emission order.
+// Generic (fallback) gather: one warp per node, one CSR slot per lane and iteration; used when a node has more
+// than GATHER_MAX_PAIRS neighbour nodes or more than GATHER_MAX_CONTRIB contributing (element, node) incidences.
 __global__ void __launch_bounds__(256)
-k_block_gather(int64_t n_nodes, const int32_t *__restrict__ indptr, const uint16_t *__restrict__ slot_code,
-               const uint32_t *__restrict__ node_pair_ptr, const uint32_t *__restrict__ pair_cptr,
-               const Contrib *__restrict__ contrib, const double *__restrict__ table, const double *__restrict__ nsp_val,
-               double *__restrict__ vals) {
+k_block_gather_slots(int64_t n_nodes, const int32_t *__restrict__ indptr, const uint16_t *__restrict__ slot_code,
+                     const uint32_t *__restrict__ node_pair_ptr, const uint32_t *__restrict__ pair_cptr,
+                     const Contrib *__restrict__ contrib, const double *__restrict__ table, const double *__restrict__ nsp_val,
+                     double *__restrict__ vals) {
     const int64_t a = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (a >= n_nodes) return;
     const uint32_t p0 = node_pair_ptr[a];
-    const int32_t kbeg = indptr[6 * a], kend = indptr[6 * a + 6];
-    // the six rows of a node are contiguous in the CSR arrays: walk them as one run; the row of a slot is found
-    // from the (at most six) row boundaries
     int32_t rb[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) rb[i] = indptr[6 * a + i];
-    for (int32_t k = kbeg + lane; k < kend; k += 32) {
+    for (int32_t k = rb[0] + lane; k < rb[6]; k += 32) {
         int i = 0;
 #pragma unroll
         for (int q = 1; q < 6; ++q) i += (k >= rb[q]) ? 1 : 0;
@@ -148,6 +155,70 @@ k_block_gather(int64_t n_nodes, const int32_t *__restrict__ indptr, const uint16
             }
         }
         vals[k] = acc;
+    }
+}
+
+// Main gather: node recipes.  Nodes whose slot-by-slot addend lists are identical (all interior nodes of a generated
+// mesh, all like joints of a regular frame) share one recipe: for every stored entry of the node's six CSR rows --
+// one contiguous run of the CSR arrays -- `width` class-table indices in emission order (padded with the index of a
+// 0.0) and an optional node-support-spring addend.  One warp per node, one slot per lane and iteration: coalesced
+// tuple reads (L1-resident for shared recipes), bank-parallel shared-memory table reads, coalesced stores.  Per node
+// only its recipe id (4 B) and CSR row start are read from HBM; the 8 B per stored entry are the output itself.
+constexpr int GATHER_WARPS = 8;
+constexpr int GATHER_NODES_PER_WARP = 4;
+
+// Step 1: the value of every recipe slot that has no support-spring addend, summed once per recipe (not once per
+// node): thread per recipe slot, addends in emission order.
+template <bool IDX16>
+__global__ void k_recipe_values(int64_t n_slots, const void *__restrict__ tuples, int width, const double *__restrict__ table,
+                                double *__restrict__ rvals) {
+    int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    double acc = 0.0;
+    for (int t = 0; t < width; ++t) {
+        uint32_t idx = IDX16 ? (uint32_t)reinterpret_cast<const uint16_t *>(tuples)[slot * width + t]
+                             : reinterpret_cast<const uint32_t *>(tuples)[slot * width + t];
+        acc += table[idx];
+    }
+    rvals[slot] = acc;
+}
+
+// Step 2: one warp per node streams its recipe's slot values into the node's CSR run (coalesced 8-byte loads from the
+// L1-resident recipe values, coalesced stores).  A slot with a support-spring addend is summed in full here, spring
+// first, because floating-point addition is not associative and the reference's order is spring, then elements
+// (FEModel3D.py:1587-1771).
+template <bool IDX16, bool HAS_NSP>
+__global__ void __launch_bounds__(32 * GATHER_WARPS)
+k_recipe_gather(int64_t n_nodes, const int32_t *__restrict__ indptr, const uint32_t *__restrict__ node_recipe,
+                const uint32_t *__restrict__ recipe_ptr, const double *__restrict__ rvals, const void *__restrict__ tuples,
+                const uint8_t *__restrict__ rnsp, int width, const uint32_t *__restrict__ nsp_first,
+                const double *__restrict__ nsp_val, const double *__restrict__ table, double *__restrict__ vals) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int rep = 0; rep < GATHER_NODES_PER_WARP; ++rep) {
+        const int64_t a = (blockIdx.x * (int64_t)GATHER_NODES_PER_WARP + rep) * GATHER_WARPS + w;
+        if (a >= n_nodes) break;
+        const int32_t k0 = indptr[6 * a], k1 = indptr[6 * a + 6];
+        const uint32_t r0 = recipe_ptr[node_recipe[a]];
+        const uint32_t nf = HAS_NSP ? nsp_first[a] : 0u;
+        for (int32_t k = k0 + lane; k < k1; k += 32) {
+            const uint32_t slot = r0 + (uint32_t)(k - k0);
+            double v = rvals[slot];
+            if (HAS_NSP) {
+                const uint32_t ns = rnsp[slot];
+                if (ns != 0xffu) {
+                    double acc = 0.0;
+                    acc += nsp_val[nf + ns];
+                    for (int t = 0; t < width; ++t) {
+                        uint32_t idx = IDX16 ? (uint32_t)reinterpret_cast<const uint16_t *>(tuples)[(size_t)slot * width + t]
+                                             : reinterpret_cast<const uint32_t *>(tuples)[(size_t)slot * width + t];
+                        acc += table[idx];
+                    }
+                    v = acc;
+                }
+            }
+            vals[k] = v;
+        }
     }
 }
 
@@ -221,7 +292,8 @@ void fast_assembly_build(Ctx *c) {
     for (int k = 0; k < 4; ++k) { f.table_off[k] = off; off += f.n_class[k] * blk[k]; }
     f.table_count = off;
     if (off >= (int64_t)0xffffffffu) return;
-    f.table.resize(off);
+    f.table.resize(off + 1);          // + one 0.0 that pads the recipe tuples
+    PN_CUDA(cudaMemsetAsync(f.table.ptr + off, 0, sizeof(double), st));
 
     std::vector<int32_t> h_indptr(c->n_dof + 1), h_indices(c->nnz_csr), h_nsp(c->n_nsp);
     PN_CUDA(cudaMemcpyAsync(h_indptr.data(), c->indptr.ptr, sizeof(int32_t) * (c->n_dof + 1), cudaMemcpyDeviceToHost, st));
@@ -235,12 +307,31 @@ void fast_assembly_build(Ctx *c) {
         views[k].cls = cls[k].data(); views[k].table_off = f.table_off[k];
     }
     AssemblySym sym;
-    build_assembly_sym(m.n_nodes, c->n_nsp, h_nsp.data(), views, h_indptr.data(), h_indices.data(), sym);
+    build_assembly_sym(m.n_nodes, c->n_nsp, h_nsp.data(), views, h_indptr.data(), h_indices.data(), (uint32_t)off, sym);
     if (!sym.ok) return;
     f.node_pair_ptr.upload(sym.node_pair_ptr.data(), (int64_t)sym.node_pair_ptr.size(), st);
     f.pair_cptr.upload(sym.pair_cptr.data(), (int64_t)sym.pair_cptr.size(), st);
     f.contrib.upload(sym.contrib.data(), (int64_t)sym.contrib.size(), st);
     f.slot_code.upload(sym.slot_code.data(), (int64_t)sym.slot_code.size(), st);
+    f.recipes = sym.recipes_ok;
+    f.width = sym.width;
+    if (f.recipes) {
+        f.node_recipe.upload(sym.node_recipe.data(), (int64_t)sym.node_recipe.size(), st);
+        f.recipe_ptr.upload(sym.recipe_ptr.data(), (int64_t)sym.recipe_ptr.size(), st);
+        f.idx16 = off + 1 < 65536;
+        if (f.idx16) {
+            std::vector<uint16_t> t16(sym.recipe_tuples.size());
+            for (size_t q = 0; q < t16.size(); ++q) t16[q] = (uint16_t)sym.recipe_tuples[q];
+            f.recipe_tuples16.upload(t16.data(), (int64_t)t16.size(), st);
+            PN_CUDA(cudaStreamSynchronize(st));
+        } else {
+            f.recipe_tuples.upload(sym.recipe_tuples.data(), (int64_t)sym.recipe_tuples.size(), st);
+        }
+        f.recipe_nsp.upload(sym.recipe_nsp.data(), (int64_t)sym.recipe_nsp.size(), st);
+        f.recipe_slots = (int64_t)sym.recipe_nsp.size();
+        f.recipe_vals.resize(f.recipe_slots);
+        f.nsp_first.upload(sym.nsp_first.data(), (int64_t)sym.nsp_first.size(), st);
+    }
     f.flag.resize(1);
     PN_CUDA(cudaStreamSynchronize(st));
     f.ready = true;
@@ -251,14 +342,19 @@ bool fast_assembly_run(Ctx *c, double *vals) {
     FastAssembly &f = *c->fast;
     const Model &m = c->model;
     cudaStream_t st = c->stream;
-    f.flag.zero(st);
+    ProfScope total_(c, PS_ASSEMBLY_TOTAL);
     {
-        ProfScope ps_(c, PS_ELEM_KE);
-        if (m.n_springs) k_verify_classes<<<grid_for(m.n_springs, 256), 256, 0, st>>>(0, m.n_springs, m.spring_ij.ptr, m.xyz.ptr, m.spring_ks.ptr, nullptr, nullptr, f.cls[0].ptr, f.rep_sig[0].ptr, f.flag.ptr);
-        if (m.n_members) k_verify_classes<<<grid_for(m.n_members, 256), 256, 0, st>>>(1, m.n_members, m.mem_ij.ptr, m.xyz.ptr, m.mem_props.ptr, m.mem_rot.ptr, m.mem_rel.ptr, f.cls[1].ptr, f.rep_sig[1].ptr, f.flag.ptr);
-        if (m.n_quads) k_verify_classes<<<grid_for(m.n_quads, 256), 256, 0, st>>>(2, m.n_quads, m.quad_ijmn.ptr, m.xyz.ptr, m.quad_props.ptr, nullptr, nullptr, f.cls[2].ptr, f.rep_sig[2].ptr, f.flag.ptr);
-        if (m.n_plates) k_verify_classes<<<grid_for(m.n_plates, 256), 256, 0, st>>>(3, m.n_plates, m.plate_ijmn.ptr, m.xyz.ptr, m.plate_props.ptr, nullptr, nullptr, f.cls[3].ptr, f.rep_sig[3].ptr, f.flag.ptr);
+        // class verification runs on the side stream, concurrently with the class table + gather on the main stream
+        cudaStream_t s2 = c->stream2;
+        PN_CUDA(cudaEventRecord(c->ev_fork, st));
+        PN_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+        f.flag.zero(s2);
+        if (m.n_springs) k_verify_classes<<<grid_for(m.n_springs, 128), 128, 0, s2>>>(0, m.n_springs, m.spring_ij.ptr, m.xyz.ptr, m.spring_ks.ptr, nullptr, nullptr, f.cls[0].ptr, f.rep_sig[0].ptr, f.flag.ptr);
+        if (m.n_members) k_verify_classes<<<grid_for(m.n_members, 128), 128, 0, s2>>>(1, m.n_members, m.mem_ij.ptr, m.xyz.ptr, m.mem_props.ptr, m.mem_rot.ptr, m.mem_rel.ptr, f.cls[1].ptr, f.rep_sig[1].ptr, f.flag.ptr);
+        if (m.n_quads) k_verify_classes<<<grid_for(m.n_quads, 128), 128, 0, s2>>>(2, m.n_quads, m.quad_ijmn.ptr, m.xyz.ptr, m.quad_props.ptr, nullptr, nullptr, f.cls[2].ptr, f.rep_sig[2].ptr, f.flag.ptr);
+        if (m.n_plates) k_verify_classes<<<grid_for(m.n_plates, 128), 128, 0, s2>>>(3, m.n_plates, m.plate_ijmn.ptr, m.xyz.ptr, m.plate_props.ptr, nullptr, nullptr, f.cls[3].ptr, f.rep_sig[3].ptr, f.flag.ptr);
         c->count_launch(4);
+        PN_CUDA(cudaEventRecord(c->ev_join, s2));
     }
     ElemInputs in{f.n_class[0], f.n_class[1], f.n_class[2], f.n_class[3], f.rep_conn[0].ptr, f.rep_props[0].ptr,
                   f.rep_conn[1].ptr, f.rep_props[1].ptr, f.rep_rot.ptr, f.rep_rel.ptr, f.rep_conn[2].ptr, f.rep_props[2].ptr,
@@ -267,10 +363,30 @@ bool fast_assembly_run(Ctx *c, double *vals) {
     launch_element_ke_arrays(c, in, t + f.table_off[0], t + f.table_off[1], t + f.table_off[2], t + f.table_off[3], st);
     if (m.n_nodes) {
         ProfScope ps_(c, PS_SCATTER);
-        k_block_gather<<<grid_for(m.n_nodes * 32, 256), 256, 0, st>>>(m.n_nodes, c->indptr.ptr, f.slot_code.ptr, f.node_pair_ptr.ptr,
-                                                                       f.pair_cptr.ptr, f.contrib.ptr, f.table.ptr, c->nsp_val.ptr, vals);
+        if (f.recipes) {
+            unsigned grid = grid_for(m.n_nodes, GATHER_WARPS * GATHER_NODES_PER_WARP);
+            const void *tp = f.idx16 ? (const void *)f.recipe_tuples16.ptr : (const void *)f.recipe_tuples.ptr;
+            if (f.idx16) k_recipe_values<true><<<grid_for(f.recipe_slots, 256), 256, 0, st>>>(f.recipe_slots, tp, f.width, f.table.ptr, f.recipe_vals.ptr);
+            else k_recipe_values<false><<<grid_for(f.recipe_slots, 256), 256, 0, st>>>(f.recipe_slots, tp, f.width, f.table.ptr, f.recipe_vals.ptr);
+            c->count_launch();
+#define PN_RG(I16, NSP) k_recipe_gather<I16, NSP><<<grid, 32 * GATHER_WARPS, 0, st>>>(                                      \
+    m.n_nodes, c->indptr.ptr, f.node_recipe.ptr, f.recipe_ptr.ptr, f.recipe_vals.ptr, tp, f.recipe_nsp.ptr, f.width, f.nsp_first.ptr, \
+    c->nsp_val.ptr, f.table.ptr, vals)
+            if (f.idx16 && c->n_nsp) PN_RG(true, true);
+            else if (f.idx16) PN_RG(true, false);
+            else if (c->n_nsp) PN_RG(false, true);
+            else PN_RG(false, false);
+#undef PN_RG
+        }
+        else
+            k_block_gather_slots<<<grid_for(m.n_nodes * 32, 256), 256, 0, st>>>(m.n_nodes, c->indptr.ptr, f.slot_code.ptr,
+                                                                                 f.node_pair_ptr.ptr, f.pair_cptr.ptr, f.contrib.ptr,
+                                                                                 f.table.ptr, c->nsp_val.ptr, vals);
         c->count_launch();
     }
+    PN_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+    total_.~ProfScope();
+    total_.live = false;
     int flag = 0;
     PN_CUDA(cudaMemcpyAsync(&flag, f.flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));

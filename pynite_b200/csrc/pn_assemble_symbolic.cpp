@@ -59,7 +59,7 @@ struct Inc {                 // one (element, local node) incidence of a node, e
 }  // namespace
 
 void build_assembly_sym(int64_t n_nodes, int64_t n_nsp, const int32_t *nsp_dof, const ElemView views[4], const int32_t *indptr,
-                        const int32_t *indices, AssemblySym &out) {
+                        const int32_t *indices, uint32_t zero_index, AssemblySym &out) {
     out = AssemblySym();
     // node -> incident elements, emission order
     std::vector<uint32_t> inc_ptr(n_nodes + 1, 0);
@@ -178,6 +178,7 @@ void build_assembly_sym(int64_t n_nodes, int64_t n_nsp, const int32_t *nsp_dof, 
     // pass 4: slot codes from the CSR pattern
     const int64_t nnz = indptr[6 * n_nodes];
     out.slot_code.assign(nnz, 0);
+    out.rowpair_code.assign((size_t)6 * P, 0);
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 2048) reduction(| : bad)
     for (int64_t a = 0; a < n_nodes; ++a) {
@@ -190,10 +191,125 @@ void build_assembly_sym(int64_t n_nodes, int64_t n_nsp, const int32_t *nsp_dof, 
                 while (p < p1 && pair_node[p] < nbn) ++p;
                 if (p >= p1 || pair_node[p] != nbn) { bad = 1; break; }
                 out.slot_code[k] = (uint16_t)(((p - p0) << 3) | (uint32_t)(indices[k] % 6));
+                uint16_t &rp = out.rowpair_code[(size_t)6 * p0 + (size_t)i * (p1 - p0) + (p - p0)];
+                if (!(rp & 63u)) {
+                    uint32_t off = (uint32_t)(k - indptr[r]);
+                    if (off > 1023u) { bad = 1; break; }
+                    rp = (uint16_t)(off << 6);
+                }
+                rp |= (uint16_t)(1u << (indices[k] % 6));
             }
         }
     }
     out.ok = !bad;
+    if (!out.ok) return;
+
+    // ---- node recipes ---------------------------------------------------------------------------------
+    int width = 0;
+    for (int64_t p = 0; p < P; ++p) {
+        int cnt = 0;
+        for (uint32_t q = out.pair_cptr[p]; q < out.pair_cptr[p + 1]; ++q) cnt += out.contrib[q].nd != 0;
+        width = std::max(width, cnt);
+    }
+    width = std::max(4, (width + 3) & ~3);        // tuples are read four indices at a time
+    if (width > 12) return;                       // recipes_ok stays false: the per-slot gather kernel is used
+    out.width = width;
+    out.nsp_first.assign(nsp_ptr.begin(), nsp_ptr.end() - 1);
+    // descriptor hash per node: pair count, per pair the contributions (support springs by local index), the
+    // row/pair codes and the six row lengths -- everything the slot-by-slot addend lists are a function of
+    std::vector<uint64_t> nh(n_nodes);
+    auto mix = [](uint64_t h, uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; return (h ^ x) * 1099511628211ull; };
+    auto contrib_word = [&](int64_t a, const Contrib &ct) -> uint64_t {
+        uint64_t base = ct.nd ? ct.base : (uint64_t)(ct.base - nsp_ptr[a]);
+        return (base << 24) | ((uint64_t)ct.la << 16) | ((uint64_t)ct.lb << 8) | ct.nd;
+    };
+#pragma omp parallel for schedule(dynamic, 2048)
+    for (int64_t a = 0; a < n_nodes; ++a) {
+        uint32_t p0 = out.node_pair_ptr[a], p1 = out.node_pair_ptr[a + 1];
+        uint64_t h = 1469598103934665603ull;
+        h = mix(h, p1 - p0);
+        for (uint32_t p = p0; p < p1; ++p) {
+            h = mix(h, out.pair_cptr[p + 1] - out.pair_cptr[p]);
+            for (uint32_t q = out.pair_cptr[p]; q < out.pair_cptr[p + 1]; ++q) h = mix(h, contrib_word(a, out.contrib[q]));
+        }
+        for (uint32_t t = 6 * p0; t < 6 * p1; ++t) h = mix(h, out.rowpair_code[t]);
+        for (int i = 0; i < 6; ++i) h = mix(h, (uint64_t)(indptr[6 * a + i + 1] - indptr[6 * a + i]));
+        nh[a] = h;
+    }
+    auto same_desc = [&](int64_t a, int64_t b) {
+        uint32_t pa = out.node_pair_ptr[a], pb = out.node_pair_ptr[b];
+        uint32_t na = out.node_pair_ptr[a + 1] - pa;
+        if (na != out.node_pair_ptr[b + 1] - pb) return false;
+        for (int i = 0; i < 6; ++i)
+            if (indptr[6 * a + i + 1] - indptr[6 * a + i] != indptr[6 * b + i + 1] - indptr[6 * b + i]) return false;
+        for (uint32_t u = 0; u < na; ++u) {
+            uint32_t ca = out.pair_cptr[pa + u], cb = out.pair_cptr[pb + u];
+            uint32_t nca = out.pair_cptr[pa + u + 1] - ca;
+            if (nca != out.pair_cptr[pb + u + 1] - cb) return false;
+            for (uint32_t q = 0; q < nca; ++q)
+                if (contrib_word(a, out.contrib[ca + q]) != contrib_word(b, out.contrib[cb + q])) return false;
+        }
+        for (uint32_t t = 0; t < 6 * na; ++t)
+            if (out.rowpair_code[6 * pa + t] != out.rowpair_code[6 * pb + t]) return false;
+        return true;
+    };
+    std::vector<int64_t> order(n_nodes);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return nh[x] != nh[y] ? nh[x] < nh[y] : x < y; });
+    out.node_recipe.assign(n_nodes, 0);
+    std::vector<int64_t> rec_rep;
+    {
+        int64_t q = 0;
+        while (q < n_nodes) {
+            int64_t r = q;
+            while (r < n_nodes && nh[order[r]] == nh[order[q]]) ++r;
+            std::vector<std::pair<int64_t, uint32_t>> run;          // (representative node, recipe id)
+            for (int64_t t = q; t < r; ++t) {
+                int64_t a = order[t];
+                int64_t hit = -1;
+                for (auto &rr : run)
+                    if (same_desc(rr.first, a)) { hit = rr.second; break; }
+                if (hit < 0) { hit = (int64_t)rec_rep.size(); rec_rep.push_back(a); run.push_back({a, (uint32_t)hit}); }
+                out.node_recipe[a] = (uint32_t)hit;
+            }
+            q = r;
+        }
+    }
+    const int64_t R = (int64_t)rec_rep.size();
+    out.recipe_ptr.assign(R + 1, 0);
+    for (int64_t r = 0; r < R; ++r) {
+        int64_t a = rec_rep[r];
+        out.recipe_ptr[r + 1] = out.recipe_ptr[r] + (uint32_t)(indptr[6 * a + 6] - indptr[6 * a]);
+    }
+    const int64_t S = out.recipe_ptr[R];
+    out.recipe_tuples.assign((size_t)S * width, zero_index);
+    out.recipe_nsp.assign(S, 0xff);
+    int bad2 = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(| : bad2)
+    for (int64_t r = 0; r < R; ++r) {
+        int64_t a = rec_rep[r];
+        uint32_t p0 = out.node_pair_ptr[a];
+        for (int i = 0; i < 6; ++i)
+            for (int32_t k = indptr[6 * a + i]; k < indptr[6 * a + i + 1]; ++k) {
+                int64_t slot = out.recipe_ptr[r] + (k - indptr[6 * a]);
+                uint32_t code = out.slot_code[k];
+                uint32_t p = p0 + (code >> 3);
+                int j = (int)(code & 7u), w = 0;
+                for (uint32_t q = out.pair_cptr[p]; q < out.pair_cptr[p + 1]; ++q) {
+                    const Contrib &ct = out.contrib[q];
+                    if (ct.nd == 0) {
+                        if ((int)ct.la == i && j == i) {
+                            uint32_t local = ct.base - nsp_ptr[a];
+                            if (local >= 0xff || out.recipe_nsp[slot] != 0xff) bad2 = 1;
+                            out.recipe_nsp[slot] = (uint8_t)local;
+                        }
+                    } else {
+                        out.recipe_tuples[(size_t)slot * width + w++] = ct.base + (uint32_t)((6 * ct.la + i) * ct.nd + 6 * ct.lb + j);
+                    }
+                }
+            }
+    }
+    out.recipes_ok = !bad2;
 }
 
 }  // namespace pn

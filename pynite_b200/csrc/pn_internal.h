@@ -131,7 +131,7 @@ struct CsrBlock {
 enum ProfSlot {
     PS_ELEM_KE = 0, PS_SCATTER, PS_GATHER_BLOCKS, PS_RHS, PS_SPMM, PS_FRONT_ASSEMBLE, PS_EXTEND_ADD, PS_LU_DIAG,
     PS_LU_PANELS, PS_LU_UPDATE, PS_COPY_FACTORS, PS_SOLVE_GATHER, PS_SOLVE_DIAG, PS_SOLVE_UPDATE, PS_SOLVE_MISC,
-    PS_REACTIONS, PS_PCG_VECTOR, PS_MERGE, PS_COUNT
+    PS_REACTIONS, PS_PCG_VECTOR, PS_MERGE, PS_ASSEMBLY_TOTAL, PS_COUNT
 };
 struct Profiler {
     bool on = false;
@@ -159,6 +159,8 @@ struct PcgWork;        // pn_pcg.cu
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // side stream: work that may overlap the main stream (class verification)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     pn_stats stats{};
