@@ -276,13 +276,22 @@ def run_ours(args, rank, local_rank, world):
     h2d = int(sum(np.asarray(getattr(A, f)).nbytes for f in in_fields))
     d2h = int(D_host.nbytes + R_host.nbytes)
 
+    e2e_phases = {}
+
     def e2e_step():
+        t = [time.perf_counter()]
         eng.set_model(A)
         eng.set_loads(A)
         eng.set_combos(A.factors)
+        t.append(time.perf_counter())
         eng.symbolic(0)
+        t.append(time.perf_counter())
         eng.assemble_ke()
+        t.append(time.perf_counter())
         eng.solve_linear(opts, reactions=True, D_out=D_host, R_out=R_host)
+        t.append(time.perf_counter())
+        for name, a, b in (('upload', 0, 1), ('symbolic', 1, 2), ('assemble', 2, 3), ('solve+reactions+download', 3, 4)):
+            e2e_phases[name] = round(1e3*(t[b] - t[a]), 2)
 
     e2e_step()
     barrier()
@@ -363,7 +372,8 @@ def run_ours(args, rank, local_rank, world):
             'ms_per_step': ms/args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(args, world),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': 1e3*t_e2e/args.e2e_steps, 'steps': args.e2e_steps,
+                    'ms_per_step': 1e3*t_e2e/args.e2e_steps, 'steps': args.e2e_steps, 'host_phases_ms_last_step': e2e_phases,
+                    'device_phases_ms_last_step': {k: round(v, 2) for k, v in e2e_stats.items() if k.startswith('ms_')},
                     'includes': 'pn_set_* uploads, symbolic phase, elimination-tree analysis, assembly, solve, reactions, D and Rxn copies to pinned host memory'},
             'gpu_launches': int(st['kernel_launches']), 'clocks': clocks,
             'roofline': roof, 'rooflines': rooflines, 'kernels': kern,
@@ -394,6 +404,10 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1; the host-side symbolic phases (ordering, class / recipe maps) are OpenMP
+        # loops, so give every rank its share of the host cores before the library (libgomp) is loaded
+        os.environ['OMP_NUM_THREADS'] = str(max(1, (os.cpu_count() or 1)//world))
     if args.impl == 'reference':
         run_reference(args, rank, world)
     else:

@@ -309,11 +309,13 @@ void fast_assembly_build(Ctx *c) {
     AssemblySym sym;
     build_assembly_sym(m.n_nodes, c->n_nsp, h_nsp.data(), views, h_indptr.data(), h_indices.data(), (uint32_t)off, sym);
     if (!sym.ok) return;
-    f.node_pair_ptr.upload(sym.node_pair_ptr.data(), (int64_t)sym.node_pair_ptr.size(), st);
-    f.pair_cptr.upload(sym.pair_cptr.data(), (int64_t)sym.pair_cptr.size(), st);
-    f.contrib.upload(sym.contrib.data(), (int64_t)sym.contrib.size(), st);
-    f.slot_code.upload(sym.slot_code.data(), (int64_t)sym.slot_code.size(), st);
     f.recipes = sym.recipes_ok;
+    if (!f.recipes) {        // the per-slot fallback kernel needs the pair / contribution tables on the device
+        f.node_pair_ptr.upload(sym.node_pair_ptr.data(), (int64_t)sym.node_pair_ptr.size(), st);
+        f.pair_cptr.upload(sym.pair_cptr.data(), (int64_t)sym.pair_cptr.size(), st);
+        f.contrib.upload(sym.contrib.data(), (int64_t)sym.contrib.size(), st);
+        f.slot_code.upload(sym.slot_code.data(), (int64_t)sym.slot_code.size(), st);
+    }
     f.width = sym.width;
     if (f.recipes) {
         f.node_recipe.upload(sym.node_recipe.data(), (int64_t)sym.node_recipe.size(), st);

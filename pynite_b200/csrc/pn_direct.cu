@@ -46,7 +46,7 @@ constexpr int SA_LD = BK + 4; // leading dimensions = 4 mod 16 doubles: the DMMA
 constexpr int SB_LD = BN + 4;
 constexpr int GEMM_SMEM = (BM * SA_LD + BK * SB_LD) * (int)sizeof(double);   // 104 448 B, two CTAs per SM
 constexpr int DIAG_LD = NB + 1;
-constexpr int DIAG_SMEM = (3 * NB * DIAG_LD + 2 * NB) * (int)sizeof(double);  // 100 864 B
+constexpr int DIAG_SMEM = (3 * NB * DIAG_LD + 2 * (NB + 1)) * (int)sizeof(double);  // 100 880 B
 constexpr int GB = 256;      // pivots per group: the trailing matrix is streamed once per group (rank-GB update)
 
 struct FrontDev {
@@ -136,7 +136,8 @@ __global__ void k_assemble_entries(int64_t nnz, int level, const uint8_t *__rest
 }
 
 // Adds the update matrix of every child with the given rank into its parent (one level up).
-// grid.x = child index within the child level, grid.y = tile over the nb x nb update matrix.
+// grid.x = child index within the child level, grid.y = row chunk of the nb x nb update matrix; a thread block walks
+// rows, threads walk columns (coalesced reads of the child row; the parent columns rel[b] are ascending runs).
 __global__ void k_extend_add(int first_child, int n_children, int rank, const FrontDev *__restrict__ fronts,
                              const int32_t *__restrict__ rel, const double *__restrict__ child_arena,
                              double *__restrict__ parent_arena) {
@@ -145,12 +146,12 @@ __global__ void k_extend_add(int first_child, int n_children, int rank, const Fr
     FrontDev C = fronts[first_child + ci];
     if (C.parent < 0 || C.child_rank != rank || C.nb == 0) return;
     FrontDev P = fronts[C.parent];
-    int nc = C.ns + C.nb, np = P.ns + P.nb;
+    const int nc = C.ns + C.nb, np = P.ns + P.nb;
     const int32_t *r = rel + C.rel_off;
-    int64_t total = (int64_t)C.nb * C.nb;
-    for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.y * blockDim.x) {
-        int a = (int)(t / C.nb), b = (int)(t - (int64_t)a * C.nb);
-        parent_arena[P.f_off + (int64_t)r[a] * np + r[b]] += child_arena[C.f_off + (int64_t)(C.ns + a) * nc + C.ns + b];
+    for (int a = blockIdx.y; a < C.nb; a += gridDim.y) {
+        const double *src = child_arena + C.f_off + (int64_t)(C.ns + a) * nc + C.ns;
+        double *dst = parent_arena + P.f_off + (int64_t)r[a] * np;
+        for (int b = threadIdx.x; b < C.nb; b += blockDim.x) dst[r[b]] += src[b];
     }
 }
 
@@ -282,17 +283,18 @@ __device__ __forceinline__ void diag_block_factor(double (*S)[DIAG_LD], double (
     }
 #pragma unroll
     for (int p = 0; p < NB; ++p) {
-        double *R = rowbuf + (p & 1) * NB;
+        double *R = rowbuf + (p & 1) * (NB + 1);
         if (t == p) {
 #pragma unroll
             for (int j = 0; j < NB; ++j)
                 if (j >= p) R[j] = row[j];
             double piv = row[p];
             if (piv == 0.0 || !(fabs(piv) <= 1.7976931348623157e308)) atomicMax(status, 1);
+            R[NB] = 1.0 / piv;           // one reciprocal per step on the critical path instead of 63 divisions
         }
         bar128();
         if (t < NB && t > p) {
-            double l = row[p] / R[p];
+            double l = row[p] * R[NB];
             row[p] = l;
 #pragma unroll
             for (int j = 0; j < NB; ++j)
@@ -304,17 +306,20 @@ __device__ __forceinline__ void diag_block_factor(double (*S)[DIAG_LD], double (
         for (int j = 0; j < NB; ++j) S[t][j] = row[j];
     }
     bar128();
+    // reciprocals of the U diagonal for the upper inverse
+    if (t < NB) rowbuf[t] = 1.0 / S[t][t];
+    bar128();
     if (t < NB) {
         // column j = t of inverse(unit lower L):  x_j = 1,  x_i = -sum_{p=j..i-1} L[i][p] x_p
         const int j = t;
         double x[NB];
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            double acc = 0.0;
+            double a0 = 0.0;
 #pragma unroll
             for (int p = 0; p < NB; ++p)
-                if (p < i) acc = fma(S[i][p], (p >= j) ? x[p] : 0.0, acc);
-            x[i] = (i == j) ? 1.0 : ((i > j) ? -acc : 0.0);
+                if (p < i) a0 = fma(S[i][p], (p >= j) ? x[p] : 0.0, a0);
+            x[i] = (i == j) ? 1.0 : ((i > j) ? -a0 : 0.0);
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) Li[i][j] = x[i];
@@ -324,12 +329,12 @@ __device__ __forceinline__ void diag_block_factor(double (*S)[DIAG_LD], double (
         double x[NB];
 #pragma unroll
         for (int i = NB - 1; i >= 0; --i) {
-            double acc = 0.0;
+            double a0 = 0.0;
 #pragma unroll
             for (int p = NB - 1; p >= 0; --p)
-                if (p > i) acc = fma(S[i][p], (p <= j) ? x[p] : 0.0, acc);
-            double d = S[i][i];
-            x[i] = (i == j) ? 1.0 / d : ((i < j) ? -acc / d : 0.0);
+                if (p > i) a0 = fma(S[i][p], (p <= j) ? x[p] : 0.0, a0);
+            double rd = rowbuf[i];
+            x[i] = (i == j) ? rd : ((i < j) ? -a0 * rd : 0.0);
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) Ui[i][j] = x[i];
@@ -581,7 +586,9 @@ static void analyse(Ctx *c) {
     std::vector<int64_t> adj_ptr;
     build_vertex_graph(m.n_nodes, newidx.data(), m.h_xyz.data(), conn, vstart, coords, adj_ptr, adj);
     int32_t nv = (int32_t)vstart.size() - 1;
-    direct_symbolic(c->n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), 24, d.sym);
+    int leaf = 24;
+    if (const char *e = getenv("PN_LEAF_SIZE")) leaf = std::max(1, atoi(e));
+    direct_symbolic(c->n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym);
     const DirectSym &S = d.sym;
 
     // level-major renumbering of fronts
@@ -700,7 +707,8 @@ static void factorise(Ctx *c, const double *vals11) {
         if (l > 0) {
             int cfirst = d.level_ptr[l - 1], ncl = d.level_ptr[l] - cfirst;
             int64_t nbmax = d.level_max_nb[l - 1];
-            unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((nbmax * nbmax + 255) / 256, 1), 1024);
+            // enough row chunks to fill the GPU when the level has few children, few when it has thousands
+            unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(nbmax, 1), std::max<int64_t>(1, 16384 / std::max(ncl, 1)));
             for (int r = 0; r < d.level_max_children[l - 1]; ++r) {
                 { ProfScope ps_(c, PS_EXTEND_ADD); k_extend_add<<<dim3(ncl, gy), 256, 0, st>>>(cfirst, ncl, r, d.fronts.ptr, d.rel.ptr, d.arena[(l - 1) & 1].ptr,
                                                              arena); }

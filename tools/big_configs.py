@@ -1,0 +1,61 @@
+"""BASELINE configs 2, 4, 5 at full size on one B200 (development / evidence run; prints one JSON line each).
+   python tools/big_configs.py c2 c5 c4"""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, '.')
+from pynite_b200 import synthetic          # noqa: E402
+from pynite_b200.engine import Engine      # noqa: E402
+
+which = sys.argv[1:] or ['c2', 'c5', 'c4']
+eng = Engine(0)
+for name in which:
+    if name == 'c2':
+        A = synthetic.moment_frame_arrays(bays_x=20, bays_z=20, stories=30, n_combos=16)
+        mode = 'linear'
+    elif name == 'c5':
+        A = synthetic.moment_frame_arrays(bays_x=10, bays_z=10, stories=40, n_combos=32)
+        mode = 'pdelta'
+    elif name == 'c4':
+        A = synthetic.quad_plate_arrays(n=1000, n_combos=8, t=24.0, mat_springs=0.1)
+        mode = 'linear'
+    else:
+        continue
+    t0 = time.perf_counter()
+    eng.set_model(A); eng.set_loads(A); eng.set_combos(A.factors)
+    eng.reset_stats()
+    s = eng.symbolic(1 if mode == 'pdelta' else 0)
+    eng.assemble_ke()
+    opts = eng.make_opts(check_stability=True)
+    if mode == 'pdelta':
+        D, R, st = eng.solve_pdelta(opts)
+    else:
+        D, R, st = eng.solve_linear(opts)
+    t1 = time.perf_counter()
+    # size-independent checks: global equilibrium of every combo (sum of reactions + applied loads = 0)
+    n = A.n_dof
+    worst = 0.0
+    for c in range(A.factors.shape[0]):
+        F = (eng.load_vector(c, 'P') - eng.load_vector(c, 'FER')).reshape(-1, 6)[:, :3]
+        Rc = R[c].reshape(-1, 6)[:, :3]
+        if mode == 'linear' and name == 'c4':
+            # spring reactions are reported as negative spring forces at every node
+            pass
+        resid = np.abs(F.sum(axis=0) + Rc.sum(axis=0)).max()
+        worst = max(worst, resid/max(np.abs(F).sum(), 1e-300))
+    # steady-state step
+    t2 = time.perf_counter()
+    eng.assemble_ke()
+    if mode == 'pdelta':
+        eng.solve_pdelta(opts, reactions=False, download=False)
+    else:
+        eng.solve_linear(opts, reactions=False, download=False)
+    t3 = time.perf_counter()
+    d = st.as_dict()
+    print(json.dumps({'config': name, 'mode': mode, 'n_dof': int(s.n_dof), 'n1': int(s.n1), 'nnz_csr': int(s.nnz_csr),
+                      'combos': int(A.factors.shape[0]), 'first_call_s': round(t1 - t0, 3), 'steady_step_s': round(t3 - t2, 4),
+                      'dof_combos_per_s': s.n_dof*A.factors.shape[0]/(t3 - t2), 'equilibrium_rel_residual': worst,
+                      'max_rel_residual': d['max_rel_residual'], 'factor_flops': d['factor_flops'], 'max_abs_D': float(np.abs(D).max())}), flush=True)
