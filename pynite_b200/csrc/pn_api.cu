@@ -10,6 +10,10 @@
 
 using namespace pn;
 
+namespace pn {
+thread_local cudaStream_t tls_stream = nullptr;
+}
+
 namespace {
 
 inline Ctx *C(pn_ctx *p) { return reinterpret_cast<Ctx *>(p); }
@@ -18,7 +22,8 @@ inline Ctx *C(pn_ctx *p) { return reinterpret_cast<Ctx *>(p); }
     if (!(ctx)) return PN_ERR_ARG;                                                                 \
     Ctx *c = C(ctx);                                                                               \
     try {                                                                                          \
-        PN_CUDA(cudaSetDevice(c->device));
+        PN_CUDA(cudaSetDevice(c->device));                                                         \
+        pn::tls_stream = c->stream;
 
 #define PN_API_END                                                                                 \
     }                                                                                              \
@@ -252,6 +257,14 @@ int pn_create(pn_ctx **out, int device_id) {
         delete c;
         return PN_ERR_CUDA;
     }
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = reinterpret_cast<pn_ctx *>(c);
     return PN_OK;
 }
@@ -260,6 +273,7 @@ void pn_destroy(pn_ctx *ctx) {
     if (!ctx) return;
     Ctx *c = C(ctx);
     cudaSetDevice(c->device);
+    pn::tls_stream = c->stream;
     cudaStreamSynchronize(c->stream);
     direct_release(c);
     pcg_release(c);
@@ -273,6 +287,8 @@ void pn_destroy(pn_ctx *ctx) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
+    if (st) cudaStreamSynchronize(st);
+    pn::tls_stream = nullptr;
     if (st) cudaStreamDestroy(st);
     if (st2) cudaStreamDestroy(st2);
 }

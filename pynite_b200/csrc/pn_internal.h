@@ -32,6 +32,12 @@ struct StatusError : std::runtime_error {
                                 " (" __FILE__ ":" + std::to_string(__LINE__) + ")");               \
     } while (0)
 
+// Stream every allocation / free of the current API call is ordered on (set by PN_API_BEGIN).  Device memory comes
+// from the device's default stream-ordered pool with an unlimited release threshold, so temporaries of the symbolic
+// phase are recycled without cudaMalloc / cudaFree round trips to the driver (those cost milliseconds each and, on a
+// busy host, occasionally hundreds).
+extern thread_local cudaStream_t tls_stream;
+
 template <typename T>
 struct DevBuf {
     T *ptr = nullptr;
@@ -42,17 +48,20 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (ptr) cudaFree(ptr);
+        if (ptr) {
+            if (tls_stream) cudaFreeAsync(ptr, tls_stream);
+            else cudaFree(ptr);
+        }
         ptr = nullptr;
         n = cap = 0;
     }
     // grow-only allocation; contents are undefined afterwards
     void resize(int64_t count) {
         if (count > cap) {
-            if (ptr) cudaFree(ptr);
-            ptr = nullptr;
-            cap = 0;
-            PN_CUDA(cudaMalloc((void **)&ptr, (size_t)(count > 0 ? count : 1) * sizeof(T)));
+            release();
+            size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+            if (tls_stream) PN_CUDA(cudaMallocAsync((void **)&ptr, bytes, tls_stream));
+            else PN_CUDA(cudaMalloc((void **)&ptr, bytes));
             cap = count > 0 ? count : 1;
         }
         n = count;
