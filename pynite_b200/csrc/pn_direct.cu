@@ -344,7 +344,7 @@ __device__ __forceinline__ void diag_block_factor(double (*S)[DIAG_LD], double (
 
 // Diagonal block [kb, kb+bs) of one front: load, factor + invert (first 128 threads), write back.  All threads of
 // the CTA must call it (it contains __syncthreads).
-__device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *arena, double *inv, int *status) {
+__device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *arena, double *inv, int *status, int sym) {
     double(*S)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem);
     double(*Li)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem + NB * DIAG_LD);
     double(*Ui)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem + 2 * NB * DIAG_LD);
@@ -355,7 +355,9 @@ __device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *are
     const int t = threadIdx.x;
     for (int e = t; e < NB * NB; e += blockDim.x) {
         int i = e / NB, j = e % NB;
-        S[i][j] = (i < bs && j < bs) ? A[(int64_t)i * n + j] : (i == j ? 1.0 : 0.0);
+        // symmetric mode: only the lower triangle of the front is maintained; mirror it
+        int si = (sym && j > i) ? j : i, sj = (sym && j > i) ? i : j;
+        S[i][j] = (i < bs && j < bs) ? A[(int64_t)si * n + sj] : (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
     if (t < 128) diag_block_factor(S, Li, Ui, rowbuf, status);
@@ -370,10 +372,10 @@ __device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *are
 
 __global__ void __launch_bounds__(128)
 k_lu_diag(int first, int kb, const FrontDev *__restrict__ fronts, double *__restrict__ arena, double *__restrict__ inv,
-          int *__restrict__ status) {
+          int *__restrict__ status, int sym) {
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
-    diag_step(F, kb, arena, inv, status);
+    diag_step(F, kb, arena, inv, status, sym);
 }
 
 // Panels of block step kb as GEMMs with the diagonal inverses.  grid.x = front; grid.y < tiles_u: column
@@ -381,7 +383,7 @@ k_lu_diag(int first, int kb, const FrontDev *__restrict__ fronts, double *__rest
 // L[rest, k] = F[rest, k] Uinv.  Both are in place (see gemm_tile).
 __global__ void __launch_bounds__(256, 2)
 k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts, double *__restrict__ arena,
-            const double *__restrict__ inv) {
+            const double *__restrict__ inv, int sym) {
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
     const int bs = min(NB, F.ns - kb);
@@ -392,6 +394,7 @@ k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts,
     const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
     const double *Uinv = Linv + NB * NB;
     if ((int)blockIdx.y < tiles_u) {
+        if (sym) return;                       // the row panel is the scaled transpose of the column panel
         int t = blockIdx.y;
         if (t * BN >= rest) return;
         double *P = A + (int64_t)kb * n + r0;
@@ -404,6 +407,32 @@ k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts,
     }
 }
 
+// Symmetric mode: U[k, c] = D_k L[c, k]^T (D_k = pivots of block k), so the row panel of step kb is the scaled
+// transpose of the column panel just computed.  grid = (front, 32-row tile of the column panel); block 32 x 8.
+__global__ void k_lu_transpose_panel(int first, int kb, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
+    __shared__ double tile[32][33];
+    FrontDev F = fronts[first + blockIdx.x];
+    if (kb >= F.ns) return;
+    const int bs = min(NB, F.ns - kb);
+    const int n = F.ns + F.nb;
+    const int r0 = kb + bs, rest = n - r0;
+    const int c0 = blockIdx.y * 32;
+    if (c0 >= rest) return;
+    double *A = arena + F.f_off;
+    for (int h = 0; h < bs; h += 32) {         // the panel is bs wide: two 32-column halves
+        for (int y = threadIdx.y; y < 32; y += 8) {
+            int row = c0 + y, col = h + threadIdx.x;
+            tile[y][threadIdx.x] = (row < rest && col < bs) ? A[(int64_t)(r0 + row) * n + kb + col] : 0.0;
+        }
+        __syncthreads();
+        for (int y = threadIdx.y; y < 32; y += 8) {
+            int pi = h + y, col = c0 + threadIdx.x;
+            if (pi < bs && col < rest) A[(int64_t)(kb + pi) * n + r0 + col] = A[(int64_t)(kb + pi) * n + kb + pi] * tile[threadIdx.x][y];
+        }
+        __syncthreads();
+    }
+}
+
 // Block steps are grouped GB pivots at a time so that the (HBM-resident) trailing matrix is read and written once
 // per group instead of once per step.  Inside group [g0, ge), after the panels of step kb, only the strips the
 // remaining steps of the group will factor are updated (rank NB):
@@ -411,7 +440,7 @@ k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts,
 //   (b) F[r0:ge, ge:n]  -= L[r0:ge, kb:r0] U[kb:r0, ge:n]
 // grid = (front, tile); tiles enumerate region (a) row-major, then region (b).
 __global__ void __launch_bounds__(256, 2)
-k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
+k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym) {
     FrontDev F = fronts[first + blockIdx.x];
     const int ge = min(g0 + GB, F.ns);
     const int r0 = kb + NB;
@@ -425,9 +454,11 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
     int t = blockIdx.y;
     const double *Lp = A + (int64_t)r0 * n + kb;        // L[r0:, kb:r0]
     if (t < ta_m * ta_n) {
+        if (sym && (t / ta_n + 1) * BM <= (t % ta_n) * BN) return;      // tile strictly above the diagonal
         gemm_tile(Lp, n, A + (int64_t)kb * n + r0, n, A + (int64_t)r0 * n + r0, n, ha, wa, NB, t / ta_n, t % ta_n, 0);
         return;
     }
+    if (sym) return;                           // region (b) is the upper side
     t -= ta_m * ta_n;
     if (t < tb_m * tb_n)
         gemm_tile(Lp, n, A + (int64_t)kb * n + ge, n, A + (int64_t)r0 * n + ge, n, hb, wb, NB, t / tb_n, t % tb_n, 0);
@@ -435,13 +466,14 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
 
 // trailing update after group [g0, ge): F[ge:, ge:] -= L[ge:, g0:ge] U[g0:ge, ge:]   (rank ge - g0 <= GB)
 __global__ void __launch_bounds__(256, 2)
-k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
+k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym) {
     FrontDev F = fronts[first + blockIdx.x];
     if (g0 >= F.ns) return;
     const int ge = min(g0 + GB, F.ns);
     const int n = F.ns + F.nb;
     const int rest = n - ge;
     if ((int)blockIdx.y * BM >= rest || (int)blockIdx.z * BN >= rest) return;
+    if (sym && ((int)blockIdx.y + 1) * BM <= (int)blockIdx.z * BN) return;      // tile strictly above the diagonal
     double *A = arena + F.f_off;
     gemm_tile(A + (int64_t)ge * n + g0, n, A + (int64_t)g0 * n + ge, n, A + (int64_t)ge * n + ge, n, rest, rest, ge - g0, blockIdx.y,
               blockIdx.z, 0);
@@ -690,6 +722,11 @@ static void analyse(Ctx *c) {
 static void factorise(Ctx *c, const double *vals11) {
     DirectSolver &d = *c->direct;
     cudaStream_t st = c->stream;
+    // K is symmetric up to rounding unless a shell has kx_mod != ky_mod: then only the lower triangle of every front
+    // is updated (half the trailing-update flops) and the row panels are scaled transposes of the column panels.
+    // The ~1e-16 relative asymmetry of the assembled values this ignores is removed by the refinement against K itself.
+    static const bool force_lu = getenv("PN_FORCE_UNSYMMETRIC") != nullptr;
+    const int sym = (c->model.symmetric && !force_lu) ? 1 : 0;
     static const bool debug_levels = getenv("PN_DEBUG_LEVELS") != nullptr;
     cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
     if (debug_levels) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); }
@@ -719,17 +756,18 @@ static void factorise(Ctx *c, const double *vals11) {
         for (int g0 = 0; g0 < maxns; g0 += GB) {
             int gend = std::min(g0 + GB, maxns);
             for (int kb = g0; kb < gend; kb += NB) {
-                { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 128, DIAG_SMEM, st>>>(first, kb, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr); }
+                { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 128, DIAG_SMEM, st>>>(first, kb, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr, sym); }
                 c->count_launch();
                 int rest = maxn - kb - 1;          // upper bound of the trailing size over the level's fronts
                 if (rest > 0) {
                     int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
-                    { ProfScope ps_(c, PS_LU_PANELS); k_lu_panels<<<dim3(nfl, tiles_u + tiles_l), 256, GEMM_SMEM, st>>>(first, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr); }
-                    c->count_launch();
+                    { ProfScope ps_(c, PS_LU_PANELS); k_lu_panels<<<dim3(nfl, tiles_u + tiles_l), 256, GEMM_SMEM, st>>>(first, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym);
+                      if (sym) k_lu_transpose_panel<<<dim3(nfl, (rest + 31) / 32), dim3(32, 8), 0, st>>>(first, kb, d.fronts.ptr, arena); }
+                    c->count_launch(1 + sym);
                     if (kb + NB < gend) {
                         int wa = gend - kb - NB;       // strips inside the group
                         int tiles = ((rest + BM - 1) / BM) * ((wa + BN - 1) / BN) + ((wa + BM - 1) / BM) * tiles_u;
-                        { ProfScope ps_(c, PS_LU_PANELS); k_lu_strip<<<dim3(nfl, tiles), 256, GEMM_SMEM, st>>>(first, kb, g0, d.fronts.ptr, arena); }
+                        { ProfScope ps_(c, PS_LU_PANELS); k_lu_strip<<<dim3(nfl, tiles), 256, GEMM_SMEM, st>>>(first, kb, g0, d.fronts.ptr, arena, sym); }
                         c->count_launch();
                     }
                 }
@@ -737,7 +775,7 @@ static void factorise(Ctx *c, const double *vals11) {
             int rest = maxn - g0 - 1;
             if (rest > 0) {
                 int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
-                { ProfScope ps_(c, PS_LU_UPDATE); k_lu_update<<<dim3(nfl, tiles_l, tiles_u), 256, GEMM_SMEM, st>>>(first, g0, d.fronts.ptr, arena); }
+                { ProfScope ps_(c, PS_LU_UPDATE); k_lu_update<<<dim3(nfl, tiles_l, tiles_u), 256, GEMM_SMEM, st>>>(first, g0, d.fronts.ptr, arena, sym); }
                 c->count_launch();
             }
         }
