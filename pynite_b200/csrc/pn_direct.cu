@@ -707,15 +707,27 @@ static void analyse(Ctx *c) {
     d.analysed = true;
     c->stats.factor_nnz = S.factor_entries;
     c->stats.factor_flops = S.factor_flops;
-    double upd = 0.0;
-    for (const FrontSym &fs : S.fronts) {
-        int64_t n = fs.ns + fs.nb;
-        for (int kb = 0; kb < fs.ns; kb += NB) {
-            double bs = std::min(NB, fs.ns - kb), rest = (double)(n - kb) - bs;
-            upd += 2.0 * bs * rest * rest;
+    // flops the trailing-update kernel really performs (tile-granular, clipped to the matrix): general mode = every
+    // tile of the trailing square per pivot group, symmetric mode = the tiles that touch or lie below the diagonal
+    {
+        static const bool force_lu = getenv("PN_FORCE_UNSYMMETRIC") != nullptr;
+        const bool sym = c->model.symmetric && !force_lu;
+        double upd = 0.0;
+        for (const FrontSym &fs : S.fronts) {
+            int64_t n = fs.ns + fs.nb;
+            for (int g0 = 0; g0 < fs.ns; g0 += GB) {
+                int ge = std::min(g0 + GB, fs.ns);
+                int64_t rest = n - ge;
+                double K = ge - g0;
+                for (int64_t r = 0; r < rest; r += BM) {
+                    int64_t rows = std::min<int64_t>(BM, rest - r);
+                    int64_t cmax = sym ? std::min<int64_t>(rest, ((r + BM + BN - 1) / BN) * BN) : rest;   // columns of computed tiles
+                    upd += 2.0 * K * (double)rows * (double)cmax;
+                }
+            }
         }
+        c->stats.update_flops = upd;
     }
-    c->stats.update_flops = upd;
     c->stats.solve_flops = 2.0 * (double)S.factor_entries;
 }
 

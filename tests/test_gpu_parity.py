@@ -307,3 +307,32 @@ def test_medium_quad_plate_properties():
     m2.load_combos['C4'].factors = dict(m.load_combos['C4'].factors)
     m2.analyze_linear()
     assert np.array_equal(m2._D['C3'], m._D['C3'])
+
+
+def test_full_size_config3_properties():
+    """BASELINE config 3 at full size (1 506 006 DOF) with 8 combos through the C ABI: size-independent properties.
+    The reference cannot run this size (O(N^2) helpers), so the checks are: bit-exact closed-form pattern
+    counts, linearity in the combo factors, global equilibrium of the reactions, the residual of the solve and
+    run-to-run determinism."""
+    from pynite_b200 import synthetic
+    from pynite_b200.engine import Engine
+    A = synthetic.quad_plate_arrays(n=500, n_combos=8)
+    A.factors[7] = A.factors[0] + 2.0*A.factors[1]
+    e = Engine(0)
+    try:
+        e.set_model(A); e.set_loads(A); e.set_combos(A.factors)
+        s = e.symbolic(0)
+        assert (s.n_dof, s.nnz_coo, s.nnz_csr) == (1506006, 53000000, 29540014)      # SURVEY 8 closed forms
+        e.assemble_ke()
+        D, R, st = e.solve_linear(e.make_opts())
+        assert st.max_rel_residual < 1e-6
+        assert rel_err(D[7], D[0] + 2.0*D[1]) < 1e-9
+        for c in (0, 3):
+            F = (e.load_vector(c, 'P') - e.load_vector(c, 'FER')).reshape(-1, 6)
+            Rc = R[c].reshape(-1, 6)
+            assert abs(F[:, 2].sum() + Rc[:, 2].sum()) < 1e-7*abs(F[:, 2]).sum()
+        e.assemble_ke()
+        D2, _, _ = e.solve_linear(e.make_opts(), reactions=False)
+        assert np.array_equal(D, D2)
+    finally:
+        e.close()
