@@ -102,6 +102,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cfg = workload_config(args, world)
+    # bounded sample: one step costs about 2.1e-3 * n^2 seconds (2 combos) on one host core; keep the whole
+    # --steps/--warmup run near two minutes
+    budget = 120.0/max(1, args.steps + min(args.warmup, 1))
+    args.cpu_n = int(max(16, min(args.cpu_n, (budget/2.1e-3)**0.5)))
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_port_step(max(8, args.cpu_n//4), 1)
     t_all, units = 0.0, 0
