@@ -356,7 +356,7 @@ def run_ours(args, rank, local_rank, world):
                                                       'peak_source': 'cuBLAS DGEMM 4096^3 burst measured in this run (FP64 is not in MEASURED_PEAKS.json)'}
     if 'solve_update' in prof and first_stats.get('solve_flops', 0) > 0:
         kms, n = prof['solve_update']
-        sweeps = 1 + opts.refine_steps
+        sweeps = 1 + st['iterations']/K          # the first solve plus the refinement corrections actually taken
         fl = first_stats['solve_flops']*args.combos*sweeps
         a = fl*K/(kms*1e-3)/1e12
         rooflines['solve_update(FP64 panel GEMM, %d rhs)' % args.combos] = {

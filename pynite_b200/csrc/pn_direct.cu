@@ -76,6 +76,7 @@ struct DirectSolver {
     DevBuf<double> arena[2];
     DevBuf<double> warena[2];
     DevBuf<double> yarena;                    // per-front solved own rows of the level being processed
+    DevBuf<int32_t> child_ptr, child_idx;     // children of every front (level-major ids, child-rank order)
     DevBuf<FrontDev> fronts_scaled;           // fronts with w_off scaled by the current number of right-hand sides
     int fronts_s = 0;
     DevBuf<double> L, U, inv;
@@ -587,6 +588,94 @@ k_solve_step(int first, int kb, int s, int backward, const FrontDev *__restrict_
         gemm_tile(L + F.l_off + kb, F.ns, wk, s, w, s, kb, s, bs, t, blockIdx.z, 0);
     }
 }
+// Whole forward / backward sweep of one front inside one CTA (levels with many fronts): gather from X, pull the
+// children's update vectors (forward), all block steps back to back, store.  The front's workspace is touched by
+// this CTA only, so between steps it stays in L2 and the level costs one launch instead of 2 + children + steps.
+constexpr int FUSED_SOLVE_MIN_FRONTS = 128;
+
+__global__ void __launch_bounds__(256, 2)
+k_front_forward(int first, int s, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
+                const int32_t *__restrict__ rel, const int32_t *__restrict__ child_ptr, const int32_t *__restrict__ child_idx,
+                const double *__restrict__ L, const double *__restrict__ inv, double *__restrict__ X, double *__restrict__ W,
+                const double *__restrict__ Wchild, double *__restrict__ Y) {
+    const int f = first + blockIdx.x;
+    FrontDev F = fronts[f];
+    const int n = F.ns + F.nb;
+    double *w = W + F.w_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < n; r += 8) {
+        const double *src = r < F.ns ? X + (int64_t)fidx[F.idx_off + r] * s : nullptr;
+        for (int j = lane; j < s; j += 32) w[(int64_t)r * s + j] = src ? src[j] : 0.0;
+    }
+    __syncthreads();
+    for (int ci = child_ptr[f]; ci < child_ptr[f + 1]; ++ci) {
+        FrontDev C = fronts[child_idx[ci]];
+        const int32_t *rc = rel + C.rel_off;
+        const double *wc = Wchild + C.w_off + (int64_t)C.ns * s;
+        for (int a = warp; a < C.nb; a += 8) {
+            double *dst = w + (int64_t)rc[a] * s;
+            for (int j = lane; j < s; j += 32) dst[j] += wc[(int64_t)a * s + j];
+        }
+        __syncthreads();
+    }
+    const int gz = (s + BN - 1) / BN;
+    double *y = Y + F.w_off;
+    for (int kb = 0; kb < F.ns; kb += NB) {
+        const int bs = min(NB, F.ns - kb);
+        const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
+        const double *wk = w + (int64_t)kb * s;
+        const int r0 = kb + bs, rest = n - r0;
+        for (int tn = 0; tn < gz; ++tn) {
+            gemm_tile(Linv, NB, wk, s, y + (int64_t)kb * s, s, bs, s, bs, 0, tn, 1);
+            for (int tm = 0; tm * BM < rest; ++tm)
+                gemm_tile(L + F.l_off + (int64_t)r0 * F.ns + kb, F.ns, wk, s, w + (int64_t)r0 * s, s, rest, s, bs, tm, tn, 0);
+        }
+        __syncthreads();
+    }
+    for (int r = warp; r < F.ns; r += 8) {
+        double *dst = X + (int64_t)fidx[F.idx_off + r] * s;
+        for (int j = lane; j < s; j += 32) dst[j] = y[(int64_t)r * s + j];
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_front_backward(int first, int s, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
+                 const double *__restrict__ L, const double *__restrict__ U, const double *__restrict__ inv,
+                 double *__restrict__ X, double *__restrict__ W, double *__restrict__ Y) {
+    FrontDev F = fronts[first + blockIdx.x];
+    const int n = F.ns + F.nb;
+    double *w = W + F.w_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < n; r += 8) {
+        const double *src = X + (int64_t)fidx[F.idx_off + r] * s;
+        for (int j = lane; j < s; j += 32) w[(int64_t)r * s + j] = src[j];
+    }
+    __syncthreads();
+    const int gz = (s + BN - 1) / BN;
+    if (F.nb) {
+        for (int tn = 0; tn < gz; ++tn)
+            for (int tm = 0; tm * BM < F.ns; ++tm)
+                gemm_tile(U + F.u_off, F.nb, w + (int64_t)F.ns * s, s, w, s, F.ns, s, F.nb, tm, tn, 0);
+        __syncthreads();
+    }
+    double *y = Y + F.w_off;
+    for (int kb = ((F.ns - 1) / NB) * NB; kb >= 0; kb -= NB) {
+        const int bs = min(NB, F.ns - kb);
+        const double *Uinv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB) + NB * NB;
+        const double *wk = w + (int64_t)kb * s;
+        for (int tn = 0; tn < gz; ++tn) {
+            gemm_tile(Uinv, NB, wk, s, y + (int64_t)kb * s, s, bs, s, bs, 0, tn, 1);
+            for (int tm = 0; tm * BM < kb; ++tm)
+                gemm_tile(L + F.l_off + kb, F.ns, wk, s, w, s, kb, s, bs, tm, tn, 0);
+        }
+        __syncthreads();
+    }
+    for (int r = warp; r < F.ns; r += 8) {
+        double *dst = X + (int64_t)fidx[F.idx_off + r] * s;
+        for (int j = lane; j < s; j += 32) dst[j] = y[(int64_t)r * s + j];
+    }
+}
+
 // backward boundary update  W[0:ns] -= U12[ns x nb] W[ns:n]
 __global__ void __launch_bounds__(256, 2)
 k_solve_boundary(int first, int s, const FrontDev *__restrict__ fronts, const double *__restrict__ U, double *__restrict__ W) {
@@ -660,6 +749,20 @@ static void analyse(Ctx *c) {
         d.level_f_total[l] = foff; d.level_n_total[l] = noff;
     }
     if (d.n_levels > 255) throw ArgError("direct solver: elimination tree too deep");
+    {
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> kids(nf);      // (child rank, child id), level-major ids
+        for (int q = 0; q < nf; ++q)
+            if (d.h_fronts[q].parent >= 0) kids[d.h_fronts[q].parent].push_back({d.h_fronts[q].child_rank, q});
+        std::vector<int32_t> cptr(nf + 1, 0), cidx;
+        for (int q = 0; q < nf; ++q) {
+            std::sort(kids[q].begin(), kids[q].end());
+            for (auto &kc : kids[q]) cidx.push_back(kc.second);
+            cptr[q + 1] = (int32_t)cidx.size();
+        }
+        d.child_ptr.upload(cptr.data(), nf + 1, st);
+        d.child_idx.upload(cidx.data(), (int64_t)cidx.size(), st);
+        PN_CUDA(cudaStreamSynchronize(st));
+    }
     d.fronts.upload(d.h_fronts.data(), nf, st);
     d.fidx.upload(S.fidx.data(), (int64_t)S.fidx.size(), st);
     d.fpos.upload(S.fpos.data(), (int64_t)S.fpos.size(), st);
@@ -680,6 +783,8 @@ static void analyse(Ctx *c) {
         PN_CUDA(cudaFuncSetAttribute(k_lu_update, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_store_panels, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_solve_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         d.attrs_set = true;
     }
@@ -842,12 +947,23 @@ static void solve_inplace(Ctx *c, double *X, int s) {
     const FrontDev *fr = d.fronts_scaled.ptr;
     double *Y = d.yarena.ptr;
     int gz = (s + BN - 1) / BN;
+    static const bool debug_levels = getenv("PN_DEBUG_LEVELS") != nullptr;
+    cudaEvent_t dbg[64];
+    if (debug_levels) for (int i = 0; i < 64; ++i) cudaEventCreate(&dbg[i]);
     // forward sweep
     for (int l = 0; l < d.n_levels; ++l) {
         int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
+        if (debug_levels && l < 31) cudaEventRecord(dbg[l], st);
         if (!nfl) continue;
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
+        if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
+            ProfScope ps_(c, PS_SOLVE_UPDATE);
+            k_front_forward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, d.L.ptr,
+                                                           d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr, Y);
+            c->count_launch();
+            continue;
+        }
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr, d.fidx.ptr, X, W); }
         c->count_launch();
@@ -870,12 +986,20 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
         c->count_launch();
     }
+    if (debug_levels) cudaEventRecord(dbg[31], st);
     // backward sweep
     for (int l = d.n_levels - 1; l >= 0; --l) {
         int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
+        if (debug_levels && l < 31) cudaEventRecord(dbg[32 + l + 1], st);
         if (!nfl) continue;
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
+        if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
+            ProfScope ps_(c, PS_SOLVE_UPDATE);
+            k_front_backward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X, W, Y);
+            c->count_launch();
+            continue;
+        }
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 1, fr, d.fidx.ptr, X, W); }
         c->count_launch();
@@ -892,6 +1016,18 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
         c->count_launch();
+    }
+    if (debug_levels) {
+        cudaEventRecord(dbg[32], st);
+        cudaEventSynchronize(dbg[32]);
+        for (int l = 0; l < d.n_levels && l < 31; ++l) {
+            float f = 0, b = 0;
+            cudaEventElapsedTime(&f, dbg[l], l + 1 < d.n_levels ? dbg[l + 1] : dbg[31]);
+            cudaEventElapsedTime(&b, dbg[32 + l + 1], dbg[32 + l]);
+            fprintf(stderr, "[pn] solve level %2d (s=%d): %6d fronts, forward %7.3f ms, backward %7.3f ms\n", l, s,
+                    d.level_ptr[l + 1] - d.level_ptr[l], f, b);
+        }
+        for (int i = 0; i < 64; ++i) cudaEventDestroy(dbg[i]);
     }
 }
 
