@@ -55,6 +55,15 @@ struct FastAssembly {
     bool recipes = false;
     int max_pairs = 0;
     DevBuf<int> flag;
+    // host-side staging kept across symbolic phases: pinned copies of the CSR pattern, and the symbolic maps (their
+    // vectors keep their capacity, so re-analysing a model of the same size does not page-fault 200 MB of fresh memory)
+    int32_t *h_indptr = nullptr, *h_indices = nullptr;
+    int64_t h_indptr_cap = 0, h_indices_cap = 0;
+    AssemblySym sym;
+    ~FastAssembly() {
+        if (h_indptr) cudaFreeHost(h_indptr);
+        if (h_indices) cudaFreeHost(h_indices);
+    }
 };
 
 // ---- signatures: every word the element kernels read, as raw bits ---------------------------------------
@@ -240,6 +249,7 @@ void fast_assembly_build(Ctx *c) {
     if (counts[0] + counts[1] + counts[2] + counts[3] == 0 && c->n_nsp == 0) return;
     if (getenv("PN_DISABLE_FAST_ASSEMBLY")) return;       // tests compare both paths bit for bit
 
+    HostTick tick("fast_assembly");
     std::vector<int32_t> cls[4], reps[4];
     int64_t total_elems = 0, total_classes = 0;
     for (int k = 0; k < 4; ++k) {
@@ -285,6 +295,7 @@ void fast_assembly_build(Ctx *c) {
         }
         PN_CUDA(cudaStreamSynchronize(st));      // host staging vectors go out of scope
     }
+    tick.lap("signatures + classes");
     // decline when the classes do not compress: the table would be as large as the dense element values
     if (total_elems > 4096 && total_classes * 4 > total_elems) return;
     const int64_t blk[4] = {144, 144, 576, 576};
@@ -295,19 +306,32 @@ void fast_assembly_build(Ctx *c) {
     f.table.resize(off + 1);          // + one 0.0 that pads the recipe tuples
     PN_CUDA(cudaMemsetAsync(f.table.ptr + off, 0, sizeof(double), st));
 
-    std::vector<int32_t> h_indptr(c->n_dof + 1), h_indices(c->nnz_csr), h_nsp(c->n_nsp);
-    PN_CUDA(cudaMemcpyAsync(h_indptr.data(), c->indptr.ptr, sizeof(int32_t) * (c->n_dof + 1), cudaMemcpyDeviceToHost, st));
-    if (c->nnz_csr) PN_CUDA(cudaMemcpyAsync(h_indices.data(), c->indices.ptr, sizeof(int32_t) * c->nnz_csr, cudaMemcpyDeviceToHost, st));
+    if (f.h_indptr_cap < c->n_dof + 1) {
+        if (f.h_indptr) cudaFreeHost(f.h_indptr);
+        f.h_indptr_cap = c->n_dof + 1;
+        PN_CUDA(cudaMallocHost((void **)&f.h_indptr, sizeof(int32_t) * f.h_indptr_cap));
+    }
+    if (f.h_indices_cap < std::max<int64_t>(c->nnz_csr, 1)) {
+        if (f.h_indices) cudaFreeHost(f.h_indices);
+        f.h_indices_cap = std::max<int64_t>(c->nnz_csr, 1);
+        PN_CUDA(cudaMallocHost((void **)&f.h_indices, sizeof(int32_t) * f.h_indices_cap));
+    }
+    int32_t *h_indptr = f.h_indptr, *h_indices = f.h_indices;
+    std::vector<int32_t> h_nsp(c->n_nsp);
+    PN_CUDA(cudaMemcpyAsync(h_indptr, c->indptr.ptr, sizeof(int32_t) * (c->n_dof + 1), cudaMemcpyDeviceToHost, st));
+    if (c->nnz_csr) PN_CUDA(cudaMemcpyAsync(h_indices, c->indices.ptr, sizeof(int32_t) * c->nnz_csr, cudaMemcpyDeviceToHost, st));
     if (c->n_nsp) PN_CUDA(cudaMemcpyAsync(h_nsp.data(), c->nsp_dof.ptr, sizeof(int32_t) * c->n_nsp, cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
+    tick.lap("pattern D2H");
     ElemView views[4];
     for (int k = 0; k < 4; ++k) {
         views[k].count = counts[k]; views[k].nn = nn[k]; views[k].conn = conn[k]->data();
         views[k].active = k == 0 ? m.h_spring_active.data() : (k == 1 ? m.h_mem_active.data() : nullptr);
         views[k].cls = cls[k].data(); views[k].table_off = f.table_off[k];
     }
-    AssemblySym sym;
-    build_assembly_sym(m.n_nodes, c->n_nsp, h_nsp.data(), views, h_indptr.data(), h_indices.data(), (uint32_t)off, sym);
+    AssemblySym &sym = f.sym;
+    build_assembly_sym(m.n_nodes, c->n_nsp, h_nsp.data(), views, h_indptr, h_indices, (uint32_t)off, sym);
+    tick.lap("build_assembly_sym (host)");
     if (!sym.ok) return;
     f.recipes = sym.recipes_ok;
     if (!f.recipes) {        // the per-slot fallback kernel needs the pair / contribution tables on the device
@@ -336,6 +360,7 @@ void fast_assembly_build(Ctx *c) {
     }
     f.flag.resize(1);
     PN_CUDA(cudaStreamSynchronize(st));
+    tick.lap("uploads");
     f.ready = true;
 }
 

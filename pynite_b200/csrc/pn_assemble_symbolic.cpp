@@ -60,7 +60,9 @@ struct Inc {                 // one (element, local node) incidence of a node, e
 
 void build_assembly_sym(int64_t n_nodes, int64_t n_nsp, const int32_t *nsp_dof, const ElemView views[4], const int32_t *indptr,
                         const int32_t *indices, uint32_t zero_index, AssemblySym &out) {
-    out = AssemblySym();
+    out.ok = false;
+    out.recipes_ok = false;
+    out.width = 0;
     // node -> incident elements, emission order
     std::vector<uint32_t> inc_ptr(n_nodes + 1, 0);
     for (int k = 0; k < 4; ++k) {
@@ -259,13 +261,22 @@ void build_assembly_sym(int64_t n_nodes, int64_t n_nsp, const int32_t *nsp_dof, 
     out.node_recipe.assign(n_nodes, 0);
     std::vector<int64_t> rec_rep;
     {
+        // runs of equal hash: every member is compared (in parallel) with the run's first node; the rare mismatches
+        // (hash collisions) are matched serially against the run's further representatives
+        std::vector<uint8_t> match(n_nodes, 0);
         int64_t q = 0;
         while (q < n_nodes) {
             int64_t r = q;
             while (r < n_nodes && nh[order[r]] == nh[order[q]]) ++r;
+            const int64_t rep0 = order[q];
+#pragma omp parallel for schedule(static) if (r - q > 4096)
+            for (int64_t t = q; t < r; ++t) match[t] = same_desc(rep0, order[t]) ? 1 : 0;
             std::vector<std::pair<int64_t, uint32_t>> run;          // (representative node, recipe id)
+            uint32_t id0 = (uint32_t)rec_rep.size();
+            rec_rep.push_back(rep0);
             for (int64_t t = q; t < r; ++t) {
                 int64_t a = order[t];
+                if (match[t]) { out.node_recipe[a] = id0; continue; }
                 int64_t hit = -1;
                 for (auto &rr : run)
                     if (same_desc(rr.first, a)) { hit = rr.second; break; }

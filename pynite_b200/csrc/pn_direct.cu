@@ -693,6 +693,7 @@ static void analyse(Ctx *c) {
     DirectSolver &d = *c->direct;
     cudaStream_t st = c->stream;
     const Model &m = c->model;
+    HostTick tick("direct analyse");
     // vertex graph from element connectivity (a superset of the K11 pattern)
     std::vector<int32_t> newidx(c->n_dof);
     PN_CUDA(cudaMemcpyAsync(newidx.data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, st));
@@ -706,11 +707,13 @@ static void analyse(Ctx *c) {
     std::vector<double> coords;
     std::vector<int64_t> adj_ptr;
     build_vertex_graph(m.n_nodes, newidx.data(), m.h_xyz.data(), conn, vstart, coords, adj_ptr, adj);
+    tick.lap("vertex graph");
     int32_t nv = (int32_t)vstart.size() - 1;
     int leaf = 24;
     if (const char *e = getenv("PN_LEAF_SIZE")) leaf = std::max(1, atoi(e));
     direct_symbolic(c->n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym);
     const DirectSym &S = d.sym;
+    tick.lap("nested dissection + fronts");
 
     // level-major renumbering of fronts
     int nf = (int)S.fronts.size();
@@ -771,7 +774,7 @@ static void analyse(Ctx *c) {
     std::vector<int32_t> dof_front_lm(S.dof_front.size());
     for (size_t i = 0; i < dof_front_lm.size(); ++i) dof_front_lm[i] = lm_of[S.dof_front[i]];
     d.dof_front_lm.upload(dof_front_lm.data(), (int64_t)dof_front_lm.size(), st);
-    DevBuf<uint8_t> d_front_level;
+    DevBuf<uint8_t> &d_front_level = c->sym_front_level;
     d_front_level.upload(front_level.data(), nf, st);
     d.L.resize(l_total); d.U.resize(u_total); d.inv.resize(inv_total);
     d.L.zero(st);
@@ -792,7 +795,7 @@ static void analyse(Ctx *c) {
     d.status.zero(st);
     // per-entry destination maps
     const CsrBlock &A = c->blk[0];
-    DevBuf<int32_t> ent_row;
+    DevBuf<int32_t> &ent_row = c->sym_ent_row;
     ent_row.resize(A.nnz);
     d.ent_front.resize(A.nnz); d.ent_dst.resize(A.nnz); d.ent_level.resize(A.nnz);
     if (A.nnz) {
@@ -810,6 +813,7 @@ static void analyse(Ctx *c) {
     for (int l = 0; l < d.n_levels; ++l) amax = std::max(amax, d.level_f_total[l]);
     d.arena[0].resize(amax); d.arena[1].resize(amax);
     d.analysed = true;
+    tick.lap("device maps + allocation");
     c->stats.factor_nnz = S.factor_entries;
     c->stats.factor_flops = S.factor_flops;
     // flops the trailing-update kernel really performs (tile-granular, clipped to the matrix): general mode = every

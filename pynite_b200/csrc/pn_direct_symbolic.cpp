@@ -2,6 +2,7 @@
 #include "pn_direct_symbolic.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <numeric>
 #include <stdexcept>
@@ -80,6 +81,21 @@ void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xy
 
 namespace {
 
+// Fronts of one subproblem in post-order (children before parents), parents as local indices (-1 = root of the
+// subproblem's forest).
+struct SubTree {
+    std::vector<std::vector<int32_t>> verts;
+    std::vector<int32_t> parent;
+    std::vector<int32_t> roots;
+    int32_t append(SubTree &&o) {            // returns the offset the other tree's fronts got
+        int32_t off = (int32_t)verts.size();
+        for (auto &v : o.verts) verts.push_back(std::move(v));
+        for (int32_t p : o.parent) parent.push_back(p < 0 ? -1 : p + off);
+        for (int32_t r : o.roots) roots.push_back(r + off);
+        return off;
+    }
+};
+
 struct Builder {
     int32_t nv;
     const int32_t *vstart;
@@ -87,23 +103,20 @@ struct Builder {
     const int64_t *adj_ptr;
     const int32_t *adj;
     int leaf_size;
-    std::vector<int32_t> region;          // scratch marker per vertex
-    int32_t next_region = 1;
-    // outputs at vertex level
-    std::vector<std::vector<int32_t>> front_verts;   // own vertices of each front (post-order ids)
-    std::vector<int32_t> parent;
+    std::vector<int32_t> region;          // marker per vertex; a vertex belongs to exactly one live subproblem
+    std::atomic<int32_t> next_region{1};
 
-    // Orders the vertex set `verts` and everything it induces; returns the ids of the fronts that are the
-    // roots of this set's elimination forest (to be attached to the caller's separator).
-    void dissect(std::vector<int32_t> &verts, std::vector<int32_t> &roots_out) {
+    // Orders the vertex set `verts` and everything it induces.  Large subproblems recurse as OpenMP tasks; the
+    // result does not depend on the schedule (sub-results are concatenated in a fixed order).
+    SubTree dissect(std::vector<int32_t> &verts) {
+        SubTree out;
         if ((int)verts.size() <= leaf_size) {
-            if (verts.empty()) return;
-            int32_t id = (int32_t)front_verts.size();
+            if (verts.empty()) return out;
             std::sort(verts.begin(), verts.end());
-            front_verts.push_back(verts);
-            parent.push_back(-1);
-            roots_out.push_back(id);
-            return;
+            out.verts.push_back(std::move(verts));
+            out.parent.push_back(-1);
+            out.roots.push_back(0);
+            return out;
         }
         // widest coordinate axis
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -131,7 +144,7 @@ struct Builder {
                 mid = it - verts.begin();
             }
         }
-        int32_t ra = next_region++, rb = next_region++;
+        int32_t ra = next_region.fetch_add(2), rb = ra + 1;
         for (size_t i = 0; i < verts.size(); ++i) region[verts[i]] = i < mid ? ra : rb;
         std::vector<int32_t> A, B, S;
         // separator = vertices of B touching A (B holds the median plane, which is the natural cut)
@@ -143,20 +156,29 @@ struct Builder {
                 if (region[adj[k]] == ra) { touches = true; break; }
             (touches ? S : B).push_back(v);
         }
+        const bool par = verts.size() > 16384;
         std::vector<int32_t>().swap(verts);
-        std::vector<int32_t> child_roots;
-        dissect(A, child_roots);
-        dissect(B, child_roots);
-        if (S.empty()) {          // A and B are disconnected: no separator, pass the forests up
-            roots_out.insert(roots_out.end(), child_roots.begin(), child_roots.end());
-            return;
+        SubTree ta, tb;
+        if (par) {
+#pragma omp task shared(ta, A)
+            ta = dissect(A);
+#pragma omp task shared(tb, B)
+            tb = dissect(B);
+#pragma omp taskwait
+        } else {
+            ta = dissect(A);
+            tb = dissect(B);
         }
-        int32_t id = (int32_t)front_verts.size();
+        out = std::move(ta);
+        out.append(std::move(tb));
+        if (S.empty()) return out;          // A and B are disconnected: no separator, pass the forests up
+        int32_t id = (int32_t)out.verts.size();
         std::sort(S.begin(), S.end());
-        front_verts.push_back(S);
-        parent.push_back(-1);
-        for (int32_t r : child_roots) parent[r] = id;
-        roots_out.push_back(id);
+        out.verts.push_back(std::move(S));
+        out.parent.push_back(-1);
+        for (int32_t r : out.roots) out.parent[r] = id;
+        out.roots.assign(1, id);
+        return out;
     }
 };
 
@@ -172,9 +194,13 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
     b.region.assign(nv, 0);
     std::vector<int32_t> all(nv);
     std::iota(all.begin(), all.end(), 0);
-    std::vector<int32_t> roots;
-    b.dissect(all, roots);
-    const int32_t nf = (int32_t)b.front_verts.size();
+    SubTree tree;
+#pragma omp parallel
+#pragma omp single
+    tree = b.dissect(all);
+    std::vector<std::vector<int32_t>> &front_verts = tree.verts;
+    std::vector<int32_t> &parent_of = tree.parent;
+    const int32_t nf = (int32_t)front_verts.size();
 
     // vertex elimination positions (post-order front ids = elimination order) and DOF positions
     std::vector<int32_t> vfront(nv), vorder(nv);      // vorder: rank of the vertex in elimination order
@@ -183,7 +209,7 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
     std::vector<int32_t> f_vbeg(nf + 1, 0);
     for (int32_t f = 0; f < nf; ++f) {
         f_vbeg[f] = (int32_t)vert_seq.size();
-        for (int32_t v : b.front_verts[f]) { vfront[v] = f; vorder[v] = (int32_t)vert_seq.size(); vert_seq.push_back(v); }
+        for (int32_t v : front_verts[f]) { vfront[v] = f; vorder[v] = (int32_t)vert_seq.size(); vert_seq.push_back(v); }
     }
     f_vbeg[nf] = (int32_t)vert_seq.size();
     if ((int32_t)vert_seq.size() != nv) throw std::runtime_error("direct_symbolic: vertices lost in dissection");
@@ -205,11 +231,11 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
     // boundary vertex sets, bottom-up (as vertex orders, ascending)
     std::vector<std::vector<int32_t>> bnd(nf);
     std::vector<std::vector<int32_t>> children(nf);
-    for (int32_t f = 0; f < nf; ++f) if (b.parent[f] >= 0) children[b.parent[f]].push_back(f);
+    for (int32_t f = 0; f < nf; ++f) if (parent_of[f] >= 0) children[parent_of[f]].push_back(f);
     for (int32_t f = 0; f < nf; ++f) {
         int32_t vend = f_vbeg[f + 1];
         std::vector<int32_t> cur;
-        for (int32_t v : b.front_verts[f])
+        for (int32_t v : front_verts[f])
             for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k) {
                 int32_t o = vorder[adj[k]];
                 if (o >= vend) cur.push_back(o);
@@ -225,19 +251,19 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         }
         bnd[f].swap(cur);
         // every boundary vertex must live in an ancestor; a root must have an empty boundary
-        if (b.parent[f] < 0 && !bnd[f].empty())
+        if (parent_of[f] < 0 && !bnd[f].empty())
             throw std::runtime_error("direct_symbolic: root front with a non-empty boundary");
     }
 
     // fronts, index lists
     out.fronts.resize(nf);
     std::vector<int32_t> depth(nf, 0);
-    for (int32_t f = nf - 1; f >= 0; --f) depth[f] = b.parent[f] < 0 ? 0 : depth[b.parent[f]] + 1;
+    for (int32_t f = nf - 1; f >= 0; --f) depth[f] = parent_of[f] < 0 ? 0 : depth[parent_of[f]] + 1;
     int32_t maxdepth = 0;
     int64_t total_idx = 0, total_rel = 0;
     for (int32_t f = 0; f < nf; ++f) {
         FrontSym &F = out.fronts[f];
-        F.parent = b.parent[f];
+        F.parent = parent_of[f];
         F.depth = depth[f];
         maxdepth = std::max(maxdepth, depth[f]);
         F.pos_start = vdofpos[f_vbeg[f]];

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -225,6 +228,14 @@ struct Ctx {
     FastAssembly *fast = nullptr;
 
     DevBuf<uint8_t> cub_tmp;       // scratch for cub device-wide primitives
+    // scratch of the symbolic phase, kept (grow-only) so that re-analysing a model of the same size allocates nothing
+    DevBuf<uint8_t> sym_flag, sym_known;
+    DevBuf<uint32_t> sym_pos, sym_head, sym_incl, sym_kpos, sym_k32a, sym_k32b, sym_k32c;
+    DevBuf<uint64_t> sym_key;
+    DevBuf<int32_t> sym_slot_row, sym_cnt, sym_ent_row, sym_bad;
+    DevBuf<uint8_t> sym_front_level;
+    DevBuf<int> sym_nb;
+    DevBuf<double> sym_press;
     // persistent work arrays: a steady-state step performs no cudaMalloc / cudaFree
     DevBuf<double> work_r, work_ax, work_rx, dots_partial, dots_out;
     Profiler prof;
@@ -257,6 +268,26 @@ struct ProfScope {
         size_t e1 = grab(c);
         cudaEventRecord(c->prof.pool[e1], c->stream);
         c->prof.recs.push_back({slot, e0, e1});
+    }
+};
+
+// Host wall-clock checkpoints of the symbolic phases, printed when PN_DEBUG_TIMING is set
+struct HostTick {
+    const char *tag;
+    bool on;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit HostTick(const char *t) : tag(t), on(getenv("PN_DEBUG_TIMING") != nullptr), t0(now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        double t = now();
+        fprintf(stderr, "[pn-time] %-18s %-28s %8.2f ms\n", tag, what, t - t0);
+        t0 = t;
     }
 };
 

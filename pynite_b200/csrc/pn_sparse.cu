@@ -215,8 +215,8 @@ __global__ void k_gather_u32(int64_t n, const uint32_t *__restrict__ src, const 
 static void build_partition(Ctx *c) {
     cudaStream_t st = c->stream;
     int64_t n = c->n_dof;
-    DevBuf<uint8_t> known;
-    DevBuf<uint32_t> kpos;
+    DevBuf<uint8_t> &known = c->sym_known;
+    DevBuf<uint32_t> &kpos = c->sym_kpos;
     known.resize(n); kpos.resize(n);
     k_known_flags<<<grid_for(n, 256), 256, 0, st>>>(n, c->model.support.ptr, c->model.enf_mask.ptr, known.ptr);
     c->count_launch();
@@ -234,7 +234,7 @@ static void build_partition(Ctx *c) {
         const DevBuf<int32_t> &rows = (b < 2) ? c->d1 : c->d2;
         int want_known = b & 1;
         B.rows = rows.n; B.cols = want_known ? c->n2 : c->n1;
-        DevBuf<int32_t> cnt;
+        DevBuf<int32_t> &cnt = c->sym_cnt;
         cnt.resize(B.rows + 1);
         cnt.zero(st);
         B.indptr.resize(B.rows + 1);
@@ -271,14 +271,15 @@ void gather_block_values(Ctx *c, const double *vals_dev) {
 // ------------------------------------------------------------------------------------------------
 void build_symbolic(Ctx *c, uint32_t flags) {
     cudaStream_t st = c->stream;
+    HostTick tick("build_symbolic");
     c->sym_flags = flags;
     c->n_dof = 6 * c->model.n_nodes;
     EvLayout L = make_layout(c);
     int64_t N = c->ev_count;
     if (N >= (int64_t)0xffffffffu) throw ArgError("model too large for 32-bit element-value positions");
 
-    DevBuf<uint8_t> flag;
-    DevBuf<uint32_t> pos;
+    DevBuf<uint8_t> &flag = c->sym_flag;
+    DevBuf<uint32_t> &pos = c->sym_pos;
     flag.resize(N); pos.resize(N);
     int64_t nnz_coo = 0;
     if (N) {
@@ -287,9 +288,10 @@ void build_symbolic(Ctx *c, uint32_t flags) {
         exclusive_scan_u8(c, flag.ptr, pos.ptr, N);
         nnz_coo = (int64_t)read_back(pos.ptr + N - 1, st) + read_back(flag.ptr + N - 1, st);
     }
+    tick.lap("entry flags + scan");
     c->nnz_coo = nnz_coo;
 
-    DevBuf<uint64_t> key_in;
+    DevBuf<uint64_t> &key_in = c->sym_key;
     key_in.resize(nnz_coo);
     c->coo_emit.resize(nnz_coo);
     c->coo_key.resize(nnz_coo);
@@ -297,6 +299,7 @@ void build_symbolic(Ctx *c, uint32_t flags) {
     if (nnz_coo) {
         k_emit_coo<<<grid_for(N, 256), 256, 0, st>>>(L, flag.ptr, pos.ptr, key_in.ptr, c->coo_emit.ptr);
         c->count_launch();
+        tick.lap("emit coo");
         // stable LSD radix sort: equal keys keep emission order, which fixes the summation order
         int end_bit = 32 + bits_for(c->n_dof);
         size_t bytes = 0;
@@ -307,10 +310,10 @@ void build_symbolic(Ctx *c, uint32_t flags) {
                                                 c->coo_src.ptr, (int)nnz_coo, 0, end_bit, st));
         c->count_launch(8);
     }
-    flag.release(); pos.release(); key_in.release();
+    tick.lap("flags + emit + sort");
 
-    DevBuf<uint32_t> head, incl;
-    DevBuf<int32_t> slot_row;
+    DevBuf<uint32_t> &head = c->sym_head, &incl = c->sym_incl;
+    DevBuf<int32_t> &slot_row = c->sym_slot_row;
     head.resize(nnz_coo); incl.resize(nnz_coo);
     int64_t nnz_csr = 0;
     if (nnz_coo) {
@@ -334,7 +337,9 @@ void build_symbolic(Ctx *c, uint32_t flags) {
     c->count_launch();
     PN_CUDA(cudaStreamSynchronize(st));
 
+    tick.lap("pattern");
     build_partition(c);
+    tick.lap("partition");
     c->symbolic_ready = true;
     c->vals_ready = false;
     c->incidence_ready = false;
@@ -395,8 +400,8 @@ __global__ void k_zero_diag(int64_t n_dof, const int32_t *__restrict__ indptr, c
 }
 
 int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap) {
-    DevBuf<int32_t> bad;
-    DevBuf<int> nb;
+    DevBuf<int32_t> &bad = c->sym_bad;
+    DevBuf<int> &nb = c->sym_nb;
     bad.resize(cap); nb.resize(1);
     nb.zero(c->stream);
     k_zero_diag<<<grid_for(c->n_dof, 256), 256, 0, c->stream>>>(c->n_dof, c->indptr.ptr, c->indices.ptr, c->vals.ptr,
@@ -451,7 +456,7 @@ void build_incidence(Ctx *c) {
     EfLayout L{c->ef_off_spring, c->ef_off_member, c->ef_off_quad, c->ef_off_plate, c->ef_count,
                m.spring_ij.ptr, m.mem_ij.ptr, m.quad_ijmn.ptr, m.plate_ijmn.ptr};
     int64_t n = c->ef_count;
-    DevBuf<uint32_t> key_in, key_out, val_in;
+    DevBuf<uint32_t> &key_in = c->sym_k32a, &key_out = c->sym_k32b, &val_in = c->sym_k32c;
     key_in.resize(n); key_out.resize(n); val_in.resize(n);
     c->inc_src.resize(n);
     c->inc_start.resize(c->n_dof + 1);
@@ -526,7 +531,9 @@ void build_load_vectors(Ctx *c) {
     cudaStream_t st = c->stream;
     Loads &ld = c->loads;
     const Model &m = c->model;
+    HostTick tick("load vectors");
     build_incidence(c);
+    tick.lap("incidence");
     int64_t n_dof = c->n_dof;
     int nc = ld.n_case;
     ld.Pcase.resize((int64_t)nc * n_dof);
@@ -551,7 +558,7 @@ void build_load_vectors(Ctx *c) {
         int64_t ne = quad ? m.n_quads : m.n_plates;
         DevBuf<double> &val = quad ? ld.qp_val : ld.pp_val;
         if (!ne || !val.n) continue;
-        DevBuf<double> press;
+        DevBuf<double> &press = c->sym_press;
         press.resize((int64_t)nc * ne);
         press.zero(st);
         k_scatter_triplets<<<grid_for(val.n, 256), 256, 0, st>>>(val.n, quad ? ld.qp_elem.ptr : ld.pp_elem.ptr,
@@ -565,11 +572,13 @@ void build_load_vectors(Ctx *c) {
                                  ld.fer_case.ptr + (int64_t)cs * c->ef_count + (quad ? c->ef_off_quad : c->ef_off_plate), st);
         PN_CUDA(cudaStreamSynchronize(st));
     }
+    tick.lap("P / FER per case");
     if (nc && n_dof) {
         k_case_vectors<<<grid_for(n_dof * nc, 256), 256, 0, st>>>(n_dof, nc, c->inc_start.ptr, c->inc_src.ptr,
                                                                    ld.Pcase.ptr, ld.fer_case.ptr, c->ef_count, ld.Gcase.ptr);
         c->count_launch();
     }
+    tick.lap("case vectors");
     ld.vectors_ready = true;
 }
 
