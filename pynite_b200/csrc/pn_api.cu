@@ -840,7 +840,7 @@ int pn_get_stats(pn_ctx *ctx, pn_stats *out) {
 static const char *kSlotNames[PS_COUNT] = {
     "element_ke", "scatter_add", "gather_blocks", "build_rhs", "spmm", "front_assemble", "extend_add", "lu_diag",
     "lu_panels", "lu_update", "copy_factors", "solve_gather_store", "solve_diag", "solve_update", "solve_misc",
-    "reactions", "pcg_vector", "merge_displacements", "assembly_total"};
+    "reactions", "pcg_vector", "merge_displacements", "assembly_total", "solve_front_fused"};
 
 const char *pn_profile_slot_name(int slot) { return (slot >= 0 && slot < PS_COUNT) ? kSlotNames[slot] : nullptr; }
 

@@ -82,6 +82,7 @@ struct DirectSolver {
     DevBuf<double> L, U, inv;
     bool attrs_set = false;
     DevBuf<int> status;                       // 0 ok, 1 zero / non-finite pivot, 2 entry outside front
+    bool shared_factor = false;               // the stored factor belongs to the matrix shared by all columns (Ke)
     DevBuf<double> col_in, col_out;           // per-column solves (P-Delta)
     int64_t arena_cap = 0;
 };
@@ -962,7 +963,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
         if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
-            ProfScope ps_(c, PS_SOLVE_UPDATE);
+            ProfScope ps_(c, PS_SOLVE_FUSED);
             k_front_forward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, d.L.ptr,
                                                            d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr, Y);
             c->count_launch();
@@ -999,7 +1000,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
         if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
-            ProfScope ps_(c, PS_SOLVE_UPDATE);
+            ProfScope ps_(c, PS_SOLVE_FUSED);
             k_front_backward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X, W, Y);
             c->count_launch();
             continue;
@@ -1063,6 +1064,7 @@ void direct_release(Ctx *c) {
 void direct_invalidate(Ctx *c) {
     if (!c->direct) return;
     c->direct->analysed = false;
+    c->direct->shared_factor = false;
     c->direct->fronts_s = 0;
 }
 
@@ -1078,6 +1080,7 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
     DevBuf<double> &R = c->work_r;
     if (!percol) {
         { PhaseTimer tm(c, &c->stats.ms_factor); factorise(c, vals11); }
+        d.shared_factor = true;
         PhaseTimer tm(c, &c->stats.ms_solve);
         PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * n1 * s, cudaMemcpyDeviceToDevice, st));
         solve_inplace(c, c->X.ptr, s);
@@ -1104,13 +1107,49 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
             if (worst * worst < 1e-11) break;
         }
     } else {
-        // one matrix per column (P-Delta): factorise and solve column by column
+        // One matrix per column (P-Delta: K_j = Ke + Kg(P_j), same pattern).  Kg is a small perturbation of Ke for
+        // loads below buckling, and the factor of Ke is still in place from step 1 of the procedure, so the columns
+        // are solved together by the stationary iteration  x <- x + Ke^-1 (b_j - K_j x)  with double-double
+        // residuals: one multi-right-hand-side sweep per iteration instead of one factorisation per combination.
+        // Contraction rate = spectral radius of Ke^-1 Kg (~ P / P_cr); if it is too slow the columns fall back to
+        // their own factorisations below.
+        if (d.shared_factor) {
+            PhaseTimer tm(c, &c->stats.ms_solve);
+            const CsrBlock &A = c->blk[0];
+            R.resize(n1 * s);
+            PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * n1 * s, cudaMemcpyDeviceToDevice, st));
+            solve_inplace(c, c->X.ptr, s);
+            std::vector<double> dd(s), xx(s);
+            double prev = 1e300;
+            bool converged = false;
+            for (int it = 0; it < 80; ++it) {
+                residual_dd(c, A, vals11, A.nnz, c->X.ptr, c->B.ptr, R.ptr, s, st);
+                c->stats.spmm_launches += 1;
+                solve_inplace(c, R.ptr, s);
+                column_dots(c, n1, s, R.ptr, R.ptr, dd.data());
+                column_dots(c, n1, s, c->X.ptr, c->X.ptr, xx.data());
+                { ProfScope ps_(c, PS_SOLVE_MISC); k_axpy1<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, R.ptr, c->X.ptr); }
+                c->count_launch();
+                c->stats.iterations += 1;
+                double worst = 0.0;
+                for (int j = 0; j < s; ++j) {
+                    double rho = xx[j] > 0 ? std::sqrt(dd[j] / xx[j]) : (dd[j] > 0 ? 1.0 : 0.0);
+                    if (!(rho == rho)) rho = 1e300;
+                    worst = std::max(worst, rho);
+                }
+                if (worst < 1e-12) { converged = true; break; }
+                if (it >= 6 && worst > 0.7 * prev) break;          // contracting too slowly (or diverging)
+                prev = worst;
+            }
+            if (converged) return;
+        }
         d.col_in.resize(n1); d.col_out.resize(n1);
         DevBuf<double> ax;
         ax.resize(n1);
         const CsrBlock &A = c->blk[0];
         for (int j = 0; j < s; ++j) {
             const double *vj = vals11 + (int64_t)j * A.nnz;
+            d.shared_factor = false;
             { PhaseTimer tm(c, &c->stats.ms_factor); factorise(c, vj); }
             PhaseTimer tm(c, &c->stats.ms_solve);
             k_get_col<<<grid_for(n1, 256), 256, 0, st>>>(n1, s, j, c->B.ptr, d.col_in.ptr);

@@ -336,3 +336,40 @@ def test_full_size_config3_properties():
         assert np.array_equal(D, D2)
     finally:
         e.close()
+
+
+def test_public_inspection_calls():
+    """`FEModel3D.Ke/Kg/FER/P/D` as stand-alone calls and after an analysis (`FEModel3D.py:1551, 1802, 2136, 2184, 2237`)."""
+    from pynite_b200 import FEModel3D
+    _, ref, _ = load_fixture('portal_frame')
+    m = models.portal_frame(FEModel3D)
+    K = m.Ke('1.4D')                       # before any analysis: the call prepares and uploads the model itself
+    assert K.shape == (42, 42)
+    Kr = sps.csr_matrix((ref['data'], ref['indices'], ref['indptr']), shape=(42, 42))
+    assert abs(K.tocsr() - Kr).max() < 1e-12*abs(Kr).max()
+    m.analyze_linear(check_statics=True)
+    for c, combo in enumerate(m.load_combos):
+        assert rel_err(m.FER(combo).reshape(-1), ref['FER'][c]) < 1e-11
+        assert rel_err(m.P(combo).reshape(-1), ref['P'][c]) < 1e-12
+        assert rel_err(m.D(combo).reshape(-1), ref['D'][c]) < TOL_D
+    _, refp, _ = load_fixture('pdelta_column')
+    p = models.pdelta_column(FEModel3D)
+    p.analyze_PDelta()
+    Kg = p.Kg('C1', first_step=False)
+    assert np.array_equal(Kg.row, refp['kg_row']) and np.array_equal(Kg.col, refp['kg_col'])
+    assert rel_err(Kg.data, refp['kg_data']) < TOL_PDELTA
+    # linear re-analysis of a model whose last solution was P-Delta keeps the P-Delta end-force branch (SURVEY H5)
+    p.analyze_linear()
+    assert p.solution == 'Linear'
+
+
+def test_load_stepping_is_linear_without_tc_features():
+    """`analyze(num_steps=k)` on a model with a directional support spring that stays active: the summed load steps
+    equal the one-step solution (`Analysis._first_order` :262-305)."""
+    from pynite_b200 import FEModel3D
+    m1 = models.braced_tc(FEModel3D)
+    m1.analyze()
+    m2 = models.braced_tc(FEModel3D)
+    m2.analyze(num_steps=1, max_iter=30)
+    for combo in m1.load_combos:
+        assert np.array_equal(m1._D[combo], m2._D[combo])

@@ -18,6 +18,7 @@ for name in which:
         mode = 'linear'
     elif name == 'c5':
         A = synthetic.moment_frame_arrays(bays_x=10, bays_z=10, stories=40, n_combos=32)
+        A.ml_params[:, :2] *= 0.25          # keep the 40-storey frame well below sway buckling (P/P_cr ~ 0.2)
         mode = 'pdelta'
     elif name == 'c4':
         A = synthetic.quad_plate_arrays(n=1000, n_combos=8, t=24.0, mat_springs=0.1)
