@@ -172,6 +172,28 @@ PN_EXPORT int pn_reactions(pn_ctx *ctx, int32_t combo, int32_t pdelta, double *o
  *      pdelta != 0 uses the (ke + kg(P)) branch of Member3D.f :886-891                             */
 PN_EXPORT int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32_t pdelta, double *out);
 
+/* ---- device-pointer building blocks for the domain-decomposed PCG --------------------------------
+ * pynite_b200/ddpcg.py runs one process per GPU; every rank holds the whole K11 (assembly is 0.1 ms), owns a
+ * node-aligned strip of rows, and drives the CG recurrence with these kernels, exchanging the halo rows of the search
+ * direction and all-reducing the dot products with torch.distributed (NCCL).  Every pointer below is a DEVICE pointer
+ * on the context's GPU; vectors are [n1][s] row-major.  pn_set_stream makes the library launch on the caller's CUDA
+ * stream (e.g. torch's current stream) so that its kernels are ordered with the caller's own work.               */
+/* reset != 0: back to the stream pn_create made; otherwise cuda_stream is used as is (0 = the legacy default stream) */
+PN_EXPORT int pn_set_stream(pn_ctx *ctx, void *cuda_stream, int reset);
+/* first K11 row of every node's free DOFs, [n_nodes + 1] (host array): strips are cut at node boundaries          */
+PN_EXPORT int pn_node_row_starts(pn_ctx *ctx, int64_t *row_start);
+/* Y[row0:row1] = K11[row0:row1, :] X                                                                            */
+PN_EXPORT int pn_dev_spmm_k11_rows(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, const double *X_dev, double *Y_dev);
+/* node-block (<= 6x6) Jacobi preconditioner of K11: setup once per assembly, then Z[rows of nodes node0..node1) = Minv R */
+PN_EXPORT int pn_dev_block_jacobi_setup(pn_ctx *ctx);
+PN_EXPORT int pn_dev_block_jacobi_nodes(pn_ctx *ctx, int32_t s, int64_t node0, int64_t node1, const double *R_dev, double *Z_dev);
+/* right-hand sides P1 - FER1 - K12 D2 (FEModel3D.py:2311) of combos [combo0, combo0 + s) into B_dev [n1][s]        */
+PN_EXPORT int pn_dev_get_rhs(pn_ctx *ctx, int32_t combo0, int32_t s, double *B_dev);
+/* stores solved free-DOF displacements X_dev [n1][s] of combos [combo0, combo0 + s) (Analysis._store_displacements
+ * :847): afterwards pn_reactions / pn_element_forces / pn_get_displacements work for those combos                 */
+PN_EXPORT int pn_dev_set_solution(pn_ctx *ctx, int32_t combo0, int32_t s, const double *X_dev);
+PN_EXPORT int pn_get_displacements(pn_ctx *ctx, int32_t combo, double *D_out);
+
 /* ---- building blocks exposed for measurement and tests ----------------------------------------
  * Y[n1][s] = K11 * X[n1][s] (row-major, s right-hand sides), repeated `repeat` times; returns the
  * average kernel time in ms through *ms_out (CUDA events on the launching stream).                */

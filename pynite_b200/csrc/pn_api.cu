@@ -257,6 +257,7 @@ int pn_create(pn_ctx **out, int device_id) {
         delete c;
         return PN_ERR_CUDA;
     }
+    c->own_stream = c->stream;
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
@@ -283,7 +284,7 @@ void pn_destroy(pn_ctx *ctx) {
     if (c->tm0) cudaEventDestroy(c->tm0);
     if (c->tm1) cudaEventDestroy(c->tm1);
     for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
-    cudaStream_t st = c->stream, st2 = c->stream2;
+    cudaStream_t st = c->own_stream, st2 = c->stream2;
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
@@ -826,6 +827,80 @@ int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repe
     c->stats.spmm_launches += repeat;
     if (Y) PN_CUDA(cudaMemcpyAsync(Y, dY.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
+    PN_API_END
+}
+
+int pn_set_stream(pn_ctx *ctx, void *cuda_stream, int reset) {
+    if (!ctx) return PN_ERR_ARG;
+    Ctx *c = C(ctx);
+    try {
+        PN_CUDA(cudaSetDevice(c->device));
+        PN_CUDA(cudaStreamSynchronize(c->stream));
+        c->stream = reset ? c->own_stream : reinterpret_cast<cudaStream_t>(cuda_stream);
+        pn::tls_stream = c->stream;
+    } catch (const std::exception &e) { c->err = e.what(); return PN_ERR_CUDA; }
+    return PN_OK;
+}
+
+int pn_node_row_starts(pn_ctx *ctx, int64_t *row_start) {
+    PN_API_BEGIN(ctx)
+    if (!c->symbolic_ready || !row_start) throw ArgError("pn_node_row_starts: call pn_symbolic first");
+    pcg_node_row_starts(c, row_start);
+    PN_API_END
+}
+
+int pn_dev_spmm_k11_rows(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, const double *X_dev, double *Y_dev) {
+    PN_API_BEGIN(ctx)
+    if (!c->vals_ready) throw ArgError("pn_dev_spmm_k11_rows: call pn_assemble_ke first");
+    if (s < 1 || s > 256 || row0 < 0 || row1 > c->n1 || row0 > row1 || !X_dev || !Y_dev) throw ArgError("pn_dev_spmm_k11_rows: bad argument");
+    spmm_rows(c, c->blk[0], c->blk[0].vals.ptr, X_dev, Y_dev, s, row0, row1, c->stream);
+    c->stats.spmm_launches += 1;
+    PN_API_END
+}
+
+int pn_dev_block_jacobi_setup(pn_ctx *ctx) {
+    PN_API_BEGIN(ctx)
+    if (!c->vals_ready) throw ArgError("pn_dev_block_jacobi_setup: call pn_assemble_ke first");
+    if (!c->model.symmetric) throw ArgError("pcg: the stiffness matrix is unsymmetric (a shell has kx_mod != ky_mod); use the direct solver");
+    pcg_setup_precond(c, c->blk[0].vals.ptr);
+    PN_API_END
+}
+
+int pn_dev_block_jacobi_nodes(pn_ctx *ctx, int32_t s, int64_t node0, int64_t node1, const double *R_dev, double *Z_dev) {
+    PN_API_BEGIN(ctx)
+    if (s < 1 || node0 < 0 || node1 > c->model.n_nodes || node0 > node1 || !R_dev || !Z_dev) throw ArgError("pn_dev_block_jacobi_nodes: bad argument");
+    pcg_apply_precond_nodes(c, s, node0, node1, R_dev, Z_dev);
+    PN_API_END
+}
+
+int pn_dev_get_rhs(pn_ctx *ctx, int32_t combo0, int32_t s, double *B_dev) {
+    PN_API_BEGIN(ctx)
+    if (combo0 < 0 || s < 1 || combo0 + s > c->loads.n_combo || !B_dev) throw ArgError("pn_dev_get_rhs: bad combo range");
+    ensure_assembled(c, c->symbolic_ready ? c->sym_flags : 0u);
+    ensure_loads(c);
+    build_rhs(c, combo0, s, nullptr);
+    PN_CUDA(cudaMemcpyAsync(B_dev, c->B.ptr, sizeof(double) * c->n1 * s, cudaMemcpyDeviceToDevice, c->stream));
+    PN_API_END
+}
+
+int pn_dev_set_solution(pn_ctx *ctx, int32_t combo0, int32_t s, const double *X_dev) {
+    PN_API_BEGIN(ctx)
+    if (combo0 < 0 || s < 1 || combo0 + s > c->loads.n_combo || !X_dev) throw ArgError("pn_dev_set_solution: bad combo range");
+    if (!c->vals_ready) throw ArgError("pn_dev_set_solution: call pn_assemble_ke first");
+    c->X.resize(c->n1 * s);
+    PN_CUDA(cudaMemcpyAsync(c->X.ptr, X_dev, sizeof(double) * c->n1 * s, cudaMemcpyDeviceToDevice, c->stream));
+    c->D_all.resize((int64_t)c->loads.n_combo * c->n_dof);
+    merge_displacements(c, combo0, s);
+    c->solved = true;
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+int pn_get_displacements(pn_ctx *ctx, int32_t combo, double *D_out) {
+    PN_API_BEGIN(ctx)
+    if (!c->solved || combo < 0 || combo >= c->loads.n_combo || !D_out) throw ArgError("pn_get_displacements: combo has not been solved");
+    PN_CUDA(cudaMemcpyAsync(D_out, c->D_all.ptr + (int64_t)combo * c->n_dof, sizeof(double) * c->n_dof, cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
     PN_API_END
 }
 

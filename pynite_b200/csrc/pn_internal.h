@@ -171,6 +171,7 @@ struct PcgWork;        // pn_pcg.cu
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;  // the stream created by pn_create (pn_set_stream may redirect `stream`)
     cudaStream_t stream2 = nullptr;     // side stream: work that may overlap the main stream (class verification)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -333,6 +334,8 @@ int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap);
 void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st);
 void residual_dd(Ctx *c, const CsrBlock &A, const double *vals, int64_t vals_col_stride, const double *X, const double *B,
                  double *R, int s, cudaStream_t st);
+void spmm_rows(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, int64_t row0, int64_t row1,
+               cudaStream_t st);
 void spmv_plain(Ctx *c, const CsrBlock &A, const double *vals, const double *x, double *y, cudaStream_t st);
 
 // ---- pn_assemble.cu -------------------------------------------------------------------------------
@@ -345,6 +348,9 @@ void fast_assembly_release(Ctx *c);
 // (P-Delta: one matrix per combo, same pattern): vals11 is then [s][nnz11].
 void pcg_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
 void pcg_release(Ctx *c);
+void pcg_setup_precond(Ctx *c, const double *vals11);
+void pcg_apply_precond_nodes(Ctx *c, int s, int64_t node0, int64_t node1, const double *R, double *Z);
+void pcg_node_row_starts(Ctx *c, int64_t *out_host);
 void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host);
 void direct_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
 void direct_release(Ctx *c);

@@ -210,6 +210,63 @@ void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, dou
     PN_CUDA(cudaStreamSynchronize(c->stream));
 }
 
+// Z[rows of node] = Minv_node R[rows of node] for nodes [node0, node1); thread = (node, column)
+__global__ void k_apply_minv(int64_t node0, int64_t n_range, int s, const int32_t *__restrict__ start, const uint8_t *__restrict__ size,
+                             const double *__restrict__ minv, const double *__restrict__ R, double *__restrict__ Z) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_range * s) return;
+    int64_t nd = node0 + t / s;
+    int j = (int)(t % s);
+    int nb = size[nd];
+    if (!nb) return;
+    int64_t i0 = start[nd];
+    double r[6];
+    for (int k = 0; k < nb; ++k) r[k] = R[(i0 + k) * s + j];
+    const double *m = minv + nd * 36;
+    for (int k = 0; k < nb; ++k) {
+        double z = 0.0;
+        for (int l = 0; l < nb; ++l) z = fma(m[k * 6 + l], r[l], z);
+        Z[(i0 + k) * s + j] = z;
+    }
+}
+
+void pcg_setup_precond(Ctx *c, const double *vals11) {
+    if (!c->pcg) c->pcg = new PcgWork();
+    PcgWork &w = *c->pcg;
+    cudaStream_t st = c->stream;
+    const CsrBlock &A = c->blk[0];
+    int64_t nn = c->model.n_nodes;
+    w.nb_start.resize(nn); w.nb_size.resize(nn); w.minv.resize(nn * 36);
+    k_node_blocks<<<grid_for(nn, 256), 256, 0, st>>>(nn, c->newidx.ptr, w.nb_start.ptr, w.nb_size.ptr);
+    k_block_inverse<<<grid_for(nn, 128), 128, 0, st>>>(nn, w.nb_start.ptr, w.nb_size.ptr, A.indptr.ptr, A.indices.ptr, vals11, w.minv.ptr);
+    c->count_launch(2);
+}
+
+void pcg_apply_precond_nodes(Ctx *c, int s, int64_t node0, int64_t node1, const double *R, double *Z) {
+    if (!c->pcg || !c->pcg->minv.n) throw ArgError("block-Jacobi preconditioner has not been set up");
+    if (node1 <= node0) return;
+    PcgWork &w = *c->pcg;
+    ProfScope ps_(c, PS_PCG_VECTOR);
+    k_apply_minv<<<grid_for((node1 - node0) * s, 256), 256, 0, c->stream>>>(node0, node1 - node0, s, w.nb_start.ptr, w.nb_size.ptr,
+                                                                              w.minv.ptr, R, Z);
+    c->count_launch();
+}
+
+// host array [n_nodes + 1]: first K11 row of every node (nodes without free DOFs repeat the next start)
+void pcg_node_row_starts(Ctx *c, int64_t *out_host) {
+    int64_t nn = c->model.n_nodes;
+    std::vector<int32_t> newidx(c->n_dof);
+    PN_CUDA(cudaMemcpyAsync(newidx.data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t next = c->n1;
+    out_host[nn] = c->n1;
+    for (int64_t nd = nn - 1; nd >= 0; --nd) {
+        for (int k = 5; k >= 0; --k)
+            if (newidx[6 * nd + k] >= 0) next = newidx[6 * nd + k];
+        out_host[nd] = next;
+    }
+}
+
 void pcg_release(Ctx *c) {
     delete c->pcg;
     c->pcg = nullptr;

@@ -797,6 +797,25 @@ static void spmm_dispatch_cpl(Ctx *c, const CsrBlock &A, const double *vals, con
     c->count_launch();
 }
 
+// rows [row0, row1) only: indptr values are absolute, so offsetting the row pointer and the output is enough
+void spmm_rows(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, int64_t row0, int64_t row1,
+               cudaStream_t st) {
+    if (row1 <= row0 || !s) return;
+    CsrBlock view;
+    view.rows = row1 - row0;
+    view.cols = A.cols;
+    view.nnz = A.nnz;
+    view.indptr.ptr = A.indptr.ptr + row0;      // non-owning view: detached again before it goes out of scope
+    view.indices.ptr = A.indices.ptr;
+    try {
+        spmm(c, view, vals, X, Y + row0 * s, s, st);
+    } catch (...) {
+        view.indptr.ptr = nullptr; view.indices.ptr = nullptr;
+        throw;
+    }
+    view.indptr.ptr = nullptr; view.indices.ptr = nullptr;
+}
+
 void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st) {
     if (!A.rows || !s) return;
     if (s == 1) spmm_dispatch_cpl<1>(c, A, vals, X, Y, s, st);

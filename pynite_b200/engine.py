@@ -112,6 +112,14 @@ SIGNATURES = {
     'pn_set_displacements': (ct.c_int, [_P, ct.c_int32, _F64P]),
     'pn_reactions': (ct.c_int, [_P, ct.c_int32, ct.c_int32, _F64P]),
     'pn_element_forces': (ct.c_int, [_P, ct.c_int, ct.c_int32, ct.c_int32, ct.c_int32, _F64P]),
+    'pn_set_stream': (ct.c_int, [_P, ct.c_void_p, ct.c_int]),
+    'pn_node_row_starts': (ct.c_int, [_P, ct.POINTER(ct.c_int64)]),
+    'pn_dev_spmm_k11_rows': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
+    'pn_dev_block_jacobi_setup': (ct.c_int, [_P]),
+    'pn_dev_block_jacobi_nodes': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
+    'pn_dev_get_rhs': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_void_p]),
+    'pn_dev_set_solution': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_void_p]),
+    'pn_get_displacements': (ct.c_int, [_P, ct.c_int32, _F64P]),
     'pn_spmm_k11': (ct.c_int, [_P, ct.c_int32, _F64P, _F64P, ct.c_int32, _F64P]),
     'pn_get_stats': (ct.c_int, [_P, ct.POINTER(Stats)]),
     'pn_reset_stats': (ct.c_int, [_P]),
@@ -392,6 +400,39 @@ class Engine:
         ms = ct.c_double(0)
         self._check(self._lib.pn_spmm_k11(self._h, s, None, None, repeat, ct.byref(ms)))
         return ms.value
+
+    # ---- device-pointer building blocks (domain-decomposed PCG, pynite_b200/ddpcg.py) -----------------------
+    def set_stream(self, cuda_stream):
+        """Launch on the caller's CUDA stream (integer handle, 0 = legacy default stream); None = the library's own."""
+        if cuda_stream is None:
+            self._check(self._lib.pn_set_stream(self._h, None, 1))
+        else:
+            self._check(self._lib.pn_set_stream(self._h, ct.c_void_p(cuda_stream), 0))
+
+    def node_row_starts(self, n_nodes):
+        out = np.empty(n_nodes + 1, dtype=np.int64)
+        self._check(self._lib.pn_node_row_starts(self._h, out.ctypes.data_as(ct.POINTER(ct.c_int64))))
+        return out
+
+    def dev_spmm_rows(self, s, row0, row1, x_ptr, y_ptr):
+        self._check(self._lib.pn_dev_spmm_k11_rows(self._h, s, row0, row1, ct.c_void_p(x_ptr), ct.c_void_p(y_ptr)))
+
+    def dev_block_jacobi_setup(self):
+        self._check(self._lib.pn_dev_block_jacobi_setup(self._h))
+
+    def dev_block_jacobi_nodes(self, s, node0, node1, r_ptr, z_ptr):
+        self._check(self._lib.pn_dev_block_jacobi_nodes(self._h, s, node0, node1, ct.c_void_p(r_ptr), ct.c_void_p(z_ptr)))
+
+    def dev_get_rhs(self, combo0, s, b_ptr):
+        self._check(self._lib.pn_dev_get_rhs(self._h, combo0, s, ct.c_void_p(b_ptr)))
+
+    def dev_set_solution(self, combo0, s, x_ptr):
+        self._check(self._lib.pn_dev_set_solution(self._h, combo0, s, ct.c_void_p(x_ptr)))
+
+    def displacements(self, combo):
+        out = np.empty(self.n_dof)
+        self._check(self._lib.pn_get_displacements(self._h, combo, _ptr(out, _F64P)))
+        return out
 
     def stats(self):
         st = Stats()

@@ -373,3 +373,46 @@ def test_load_stepping_is_linear_without_tc_features():
     m2.analyze(num_steps=1, max_iter=30)
     for combo in m1.load_combos:
         assert np.array_equal(m1._D[combo], m2._D[combo])
+
+
+def test_row_range_kernels_for_ddpcg(eng):
+    """The device-pointer building blocks of the domain-decomposed PCG (strip SpMM, node-range block-Jacobi, rhs /
+    solution hand-over) on one GPU: two strips processed one after the other must equal the whole-matrix result,
+    and a single-rank ddpcg.solve must reproduce the direct solver."""
+    import torch
+    from pynite_b200 import ddpcg
+    A, ref, _ = load_fixture('mat_foundation')
+    _upload(eng, A)
+    eng.symbolic(0)
+    eng.assemble_ke()
+    D_direct, _, _ = eng.solve_linear(eng.make_opts(), reactions=False)
+    ops = ddpcg.EngineOps(eng, A.n_nodes)
+    try:
+        n1 = ops.n1
+        K11 = sps.csr_matrix((ref['K11_data'], ref['K11_indices'], ref['K11_indptr']), shape=(n1, n1))
+        rng = np.random.default_rng(9)
+        Xh = rng.standard_normal((n1, 5))
+        X = torch.from_numpy(Xh).cuda()
+        Y = torch.zeros_like(X)
+        cut_node = A.n_nodes//2
+        cut = int(ops.node_row_start[cut_node])
+        ops.spmm_rows(0, cut, X, Y)
+        ops.spmm_rows(cut, n1, X, Y)
+        torch.cuda.synchronize()
+        assert rel_err(Y.cpu().numpy(), K11 @ Xh) < 1e-12
+        Z = torch.zeros_like(X)
+        ops.precond_nodes(0, cut_node, X, Z)
+        ops.precond_nodes(cut_node, A.n_nodes, X, Z)
+        torch.cuda.synchronize()
+        Zh = Z.cpu().numpy()
+        Ks = ((K11 + K11.T)*0.5).tocsr()
+        for nd in (0, cut_node, A.n_nodes - 1):
+            a, b = int(ops.node_row_start[nd]), int(ops.node_row_start[nd + 1])
+            if b > a:
+                assert rel_err(Zh[a:b], np.linalg.solve(Ks[a:b, a:b].toarray(), Xh[a:b])) < 1e-10
+        Xs, it, info = ddpcg.solve(ops, 0, A.factors.shape[0], tol=1e-12, max_iter=20000, check_every=10)
+        ops.set_solution(0, Xs)
+        for c in range(A.factors.shape[0]):
+            assert rel_err(eng.displacements(c), D_direct[c]) < 1e-8
+    finally:
+        eng.set_stream(None)
