@@ -187,6 +187,18 @@ PN_EXPORT int pn_dev_spmm_k11_rows(pn_ctx *ctx, int32_t s, int64_t row0, int64_t
 /* node-block (<= 6x6) Jacobi preconditioner of K11: setup once per assembly, then Z[rows of nodes node0..node1) = Minv R */
 PN_EXPORT int pn_dev_block_jacobi_setup(pn_ctx *ctx);
 PN_EXPORT int pn_dev_block_jacobi_nodes(pn_ctx *ctx, int32_t s, int64_t node0, int64_t node1, const double *R_dev, double *Z_dev);
+/* fused CG vector kernels on a strip; the per-column scalars (rz, pAp, ...) are DEVICE arrays of s doubles so the caller
+ * all-reduces them in place between the kernels:
+ *   pn_dev_cg_dots       out[j] = sum over rows [row0,row1) of A[i][j] B[i][j]
+ *   pn_dev_cg_update     x += alpha p, r -= alpha Ap with alpha = rz/pAp (skipped when first != 0), z = Minv r on nodes
+ *                        [node0,node1); out2[0:s] = local r.z, out2[s:2s] = local r.r
+ *   pn_dev_cg_direction  p = z + (rz_new/rz) p on rows [row0,row1)   (p = z when first != 0)                        */
+PN_EXPORT int pn_dev_cg_dots(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, const double *A_dev, const double *B_dev, double *out_dev);
+PN_EXPORT int pn_dev_cg_update(pn_ctx *ctx, int32_t s, int64_t node0, int64_t node1, int32_t first, const double *rz_dev,
+                               const double *pAp_dev, const double *P_dev, const double *AP_dev, double *X_dev, double *R_dev,
+                               double *Z_dev, double *out2_dev);
+PN_EXPORT int pn_dev_cg_direction(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, int32_t first, const double *rz_dev,
+                                  const double *rz_new_dev, const double *Z_dev, double *P_dev);
 /* right-hand sides P1 - FER1 - K12 D2 (FEModel3D.py:2311) of combos [combo0, combo0 + s) into B_dev [n1][s]        */
 PN_EXPORT int pn_dev_get_rhs(pn_ctx *ctx, int32_t combo0, int32_t s, double *B_dev);
 /* stores solved free-DOF displacements X_dev [n1][s] of combos [combo0, combo0 + s) (Analysis._store_displacements

@@ -873,6 +873,31 @@ int pn_dev_block_jacobi_nodes(pn_ctx *ctx, int32_t s, int64_t node0, int64_t nod
     PN_API_END
 }
 
+int pn_dev_cg_dots(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, const double *A_dev, const double *B_dev, double *out_dev) {
+    PN_API_BEGIN(ctx)
+    if (!c->pcg || s < 1 || row0 < 0 || row1 > c->n1 || row0 > row1 || !A_dev || !B_dev || !out_dev) throw ArgError("pn_dev_cg_dots: bad argument");
+    pcg_strip_dots(c, s, row0, row1, A_dev, B_dev, out_dev);
+    PN_API_END
+}
+
+int pn_dev_cg_update(pn_ctx *ctx, int32_t s, int64_t node0, int64_t node1, int32_t first, const double *rz_dev,
+                     const double *pAp_dev, const double *P_dev, const double *AP_dev, double *X_dev, double *R_dev,
+                     double *Z_dev, double *out2_dev) {
+    PN_API_BEGIN(ctx)
+    if (!c->pcg) throw ArgError("pn_dev_cg_update: call pn_dev_block_jacobi_setup first");
+    if (s < 1 || node0 < 0 || node1 > c->model.n_nodes || node0 > node1 || !X_dev || !R_dev || !Z_dev || !out2_dev) throw ArgError("pn_dev_cg_update: bad argument");
+    pcg_strip_update(c, s, node0, node1, first, rz_dev, pAp_dev, P_dev, AP_dev, X_dev, R_dev, Z_dev, out2_dev);
+    PN_API_END
+}
+
+int pn_dev_cg_direction(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, int32_t first, const double *rz_dev,
+                        const double *rz_new_dev, const double *Z_dev, double *P_dev) {
+    PN_API_BEGIN(ctx)
+    if (s < 1 || row0 < 0 || row1 > c->n1 || row0 > row1 || !Z_dev || !P_dev) throw ArgError("pn_dev_cg_direction: bad argument");
+    pcg_strip_direction(c, s, row0, row1, first, rz_dev, rz_new_dev, Z_dev, P_dev);
+    PN_API_END
+}
+
 int pn_dev_get_rhs(pn_ctx *ctx, int32_t combo0, int32_t s, double *B_dev) {
     PN_API_BEGIN(ctx)
     if (combo0 < 0 || s < 1 || combo0 + s > c->loads.n_combo || !B_dev) throw ArgError("pn_dev_get_rhs: bad combo range");

@@ -351,6 +351,11 @@ void pcg_release(Ctx *c);
 void pcg_setup_precond(Ctx *c, const double *vals11);
 void pcg_apply_precond_nodes(Ctx *c, int s, int64_t node0, int64_t node1, const double *R, double *Z);
 void pcg_node_row_starts(Ctx *c, int64_t *out_host);
+void pcg_strip_dots(Ctx *c, int s, int64_t row0, int64_t row1, const double *A, const double *B, double *out_dev);
+void pcg_strip_update(Ctx *c, int s, int64_t node0, int64_t node1, int first, const double *rz_dev, const double *pAp_dev,
+                      const double *P, const double *AP, double *X, double *R, double *Z, double *out2_dev);
+void pcg_strip_direction(Ctx *c, int s, int64_t row0, int64_t row1, int first, const double *rz_dev, const double *rz_new_dev,
+                         const double *Z, double *P);
 void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host);
 void direct_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
 void direct_release(Ctx *c);

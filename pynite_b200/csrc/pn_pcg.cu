@@ -134,7 +134,7 @@ __global__ void k_dot_final(int grid, int s, int n_which, const double *__restri
 
 // ---- fused: x += alpha p, r -= alpha Ap, z = Minv r, partial dots r.z and r.r ----------------------
 __global__ void __launch_bounds__(RED_TPB)
-k_update_xrz(int64_t n_nodes, int s, const int32_t *__restrict__ start, const uint8_t *__restrict__ size,
+k_update_xrz(int64_t node0, int64_t n_nodes, int s, const int32_t *__restrict__ start, const uint8_t *__restrict__ size,
              const double *__restrict__ minv, const double *__restrict__ rz, const double *__restrict__ pAp,
              const double *__restrict__ P, const double *__restrict__ AP, double *__restrict__ X, double *__restrict__ R,
              double *__restrict__ Z, double *__restrict__ partial, int first) {
@@ -146,7 +146,7 @@ k_update_xrz(int64_t n_nodes, int s, const int32_t *__restrict__ start, const ui
     if (nl < lanes) {
         double alpha = 0.0;
         if (!first) { double d = pAp[j]; alpha = d != 0.0 ? rz[j] / d : 0.0; }
-        for (int64_t nd = (int64_t)blockIdx.x * lanes + nl; nd < n_nodes; nd += (int64_t)gridDim.x * lanes) {
+        for (int64_t nd = node0 + (int64_t)blockIdx.x * lanes + nl; nd < n_nodes; nd += (int64_t)gridDim.x * lanes) {
             int nb = size[nd];
             if (!nb) continue;
             int64_t i0 = start[nd];
@@ -252,6 +252,41 @@ void pcg_apply_precond_nodes(Ctx *c, int s, int64_t node0, int64_t node1, const 
     c->count_launch();
 }
 
+// ---- fused CG vector kernels on a strip (domain-decomposed PCG): the scalars live in device memory so that the caller
+// can all-reduce them between the kernels without a host round trip
+void pcg_strip_dots(Ctx *c, int s, int64_t row0, int64_t row1, const double *A, const double *B, double *out_dev) {
+    PcgWork &w = *c->pcg;
+    if (s > 256) throw ArgError("pcg: at most 256 right-hand sides per call");
+    w.red_grid = 148 * 4;
+    w.partial.resize((int64_t)w.red_grid * 3 * s);
+    ProfScope ps_(c, PS_PCG_VECTOR);
+    k_dot_partial<<<w.red_grid, RED_TPB, 0, c->stream>>>(row1 - row0, s, A + row0 * s, B + row0 * s, w.partial.ptr, 0, 1);
+    k_dot_final<<<grid_for(s, 128), 128, 0, c->stream>>>(w.red_grid, s, 1, w.partial.ptr, out_dev, nullptr, nullptr);
+    c->count_launch(2);
+}
+// x += alpha p, r -= alpha Ap (alpha = rz / pAp per column; skipped when first), z = Minv r on nodes [node0, node1);
+// out2_dev[0:s] = local r.z, out2_dev[s:2s] = local r.r
+void pcg_strip_update(Ctx *c, int s, int64_t node0, int64_t node1, int first, const double *rz_dev, const double *pAp_dev,
+                      const double *P, const double *AP, double *X, double *R, double *Z, double *out2_dev) {
+    PcgWork &w = *c->pcg;
+    if (s > 256) throw ArgError("pcg: at most 256 right-hand sides per call");
+    w.red_grid = 148 * 4;
+    w.partial.resize((int64_t)w.red_grid * 3 * s);
+    ProfScope ps_(c, PS_PCG_VECTOR);
+    k_update_xrz<<<w.red_grid, RED_TPB, 0, c->stream>>>(node0, node1, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz_dev, pAp_dev, P,
+                                                         AP, X, R, Z, w.partial.ptr, first);
+    k_dot_final<<<grid_for(2 * s, 128), 128, 0, c->stream>>>(w.red_grid, s, 2, w.partial.ptr, out2_dev, out2_dev + s, nullptr);
+    c->count_launch(2);
+}
+// p = z + (rz_new / rz) p on rows [row0, row1)   (p = z when first)
+void pcg_strip_direction(Ctx *c, int s, int64_t row0, int64_t row1, int first, const double *rz_dev, const double *rz_new_dev,
+                         const double *Z, double *P) {
+    if (row1 <= row0) return;
+    ProfScope ps_(c, PS_PCG_VECTOR);
+    k_update_p<<<grid_for((row1 - row0) * s, 256), 256, 0, c->stream>>>(row1 - row0, s, rz_dev, rz_new_dev, Z + row0 * s, P + row0 * s, first);
+    c->count_launch();
+}
+
 // host array [n_nodes + 1]: first K11 row of every node (nodes without free DOFs repeat the next start)
 void pcg_node_row_starts(Ctx *c, int64_t *out_host) {
     int64_t nn = c->model.n_nodes;
@@ -303,7 +338,7 @@ void pcg_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solve_o
     c->X.zero(st);
     PN_CUDA(cudaMemcpyAsync(w.R.ptr, c->B.ptr, (size_t)(n1 * s) * sizeof(double), cudaMemcpyDeviceToDevice, st));
     // z = Minv r, rz = r.z, bb = r.r (x0 = 0)
-    { ProfScope ps_(c, PS_PCG_VECTOR); k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr, w.AP.ptr,
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(0, nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr, w.AP.ptr,
                                                   c->X.ptr, w.R.ptr, w.Z.ptr, w.partial.ptr, 1); }
     { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final<<<grid_for(2 * s, 128), 128, 0, st>>>(w.red_grid, s, 2, w.partial.ptr, rz, bb, nullptr); }
     { ProfScope ps_(c, PS_PCG_VECTOR); k_update_p<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, rz, rz_new, w.Z.ptr, w.P.ptr, 1); }
@@ -322,7 +357,7 @@ void pcg_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solve_o
         apply_matrix(c, vals11, percol, w.P.ptr, w.AP.ptr, s);
         { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_partial<<<w.red_grid, RED_TPB, 0, st>>>(n1, s, w.P.ptr, w.AP.ptr, w.partial.ptr, 0, 1); }
         { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final<<<grid_for(s, 128), 128, 0, st>>>(w.red_grid, s, 1, w.partial.ptr, pAp, nullptr, nullptr); }
-        { ProfScope ps_(c, PS_PCG_VECTOR); k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr,
+        { ProfScope ps_(c, PS_PCG_VECTOR); k_update_xrz<<<w.red_grid, RED_TPB, 0, st>>>(0, nn, s, w.nb_start.ptr, w.nb_size.ptr, w.minv.ptr, rz, pAp, w.P.ptr,
                                                       w.AP.ptr, c->X.ptr, w.R.ptr, w.Z.ptr, w.partial.ptr, 0); }
         { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final<<<grid_for(2 * s, 128), 128, 0, st>>>(w.red_grid, s, 2, w.partial.ptr, rz_new, rr, nullptr); }
         { ProfScope ps_(c, PS_PCG_VECTOR); k_update_p<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1, s, rz, rz_new, w.Z.ptr, w.P.ptr, 0); }

@@ -86,6 +86,17 @@ class EngineOps:
     def set_solution(self, combo0, X):
         self.eng.dev_set_solution(combo0, X.shape[1], X.data_ptr())
 
+    # fused strip kernels: the per-column scalars stay on the device and are all-reduced in place by the driver
+    def cg_dots(self, row0, row1, A, B, out):
+        self.eng.dev_cg_dots(A.shape[1], row0, row1, A.data_ptr(), B.data_ptr(), out.data_ptr())
+
+    def cg_update(self, node0, node1, first, rz, pAp, P, AP, X, R, Z, out2):
+        self.eng.dev_cg_update(X.shape[1], node0, node1, first, rz.data_ptr(), pAp.data_ptr(), P.data_ptr(), AP.data_ptr(),
+                               X.data_ptr(), R.data_ptr(), Z.data_ptr(), out2.data_ptr())
+
+    def cg_direction(self, row0, row1, first, rz, rz_new, Z, P):
+        self.eng.dev_cg_direction(Z.shape[1], row0, row1, first, rz.data_ptr(), rz_new.data_ptr(), Z.data_ptr(), P.data_ptr())
+
 
 def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None, log=None):
     """Solves K11 X = B for combos [combo0, combo0 + s) on all ranks of `group`; returns (X on every rank, iterations,
@@ -140,44 +151,74 @@ def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None
     P = torch.zeros_like(R)
     AP = torch.zeros_like(R)
     own = slice(r0, r1)
-    ops.precond_nodes(node0, node1, R, Z)
-    red = torch.stack([(R[own]*Z[own]).sum(0), (R[own]*R[own]).sum(0)])
-    allreduce(red)
-    rz, bb = red[0].clone(), red[1].clone()
-    P[own] = Z[own]
+    fused = hasattr(ops, 'cg_update')
     it = 0
     worst = 0.0
     best, stalled = float('inf'), 0
-    if float(bb.max()) == 0.0:
-        return X, 0, 0.0
-    while it < max_iter:
-        exchange(P)
-        ops.spmm_rows(r0, r1, P, AP)
-        pAp = allreduce((P[own]*AP[own]).sum(0))
-        alpha = torch.where(pAp != 0, rz/pAp, torch.zeros_like(rz))
-        X[own] += alpha*P[own]
-        R[own] -= alpha*AP[own]
+
+    def converged(rr, bb):
+        nonlocal worst, best, stalled
+        worst = float(torch.sqrt((rr/torch.where(bb > 0, bb, torch.ones_like(bb))).max()))
+        if log:
+            log(it, worst)
+        if not np.isfinite(worst) or worst <= tol:
+            return True
+        # the recurrence residual cannot drop below ~2^-53 cond(K11): stop when it has stopped improving
+        if worst < 0.99*best:
+            best, stalled = worst, 0
+        else:
+            stalled += 1
+        return stalled >= 8
+
+    if fused:
+        # five library kernels, one halo exchange and two all-reduces per iteration; no host round trip in between
+        rz = torch.zeros(s, dtype=torch.float64, device=dev)
+        pAp = torch.zeros(s, dtype=torch.float64, device=dev)
+        red = torch.zeros(2*s, dtype=torch.float64, device=dev)
+        ops.cg_update(node0, node1, True, rz, pAp, P, AP, X, R, Z, red)
+        allreduce(red)
+        rz.copy_(red[:s])
+        bb = red[s:].clone()
+        ops.cg_direction(r0, r1, True, rz, rz, Z, P)
+        if float(bb.max()) == 0.0:
+            return X, 0, {'iterations': 0, 'max_rel_residual': 0.0, 'rows_per_rank': [], 'halo_rows': halo_rows, 'halo_bytes_per_iteration': 0}
+        while it < max_iter:
+            exchange(P)
+            ops.spmm_rows(r0, r1, P, AP)
+            ops.cg_dots(r0, r1, P, AP, pAp)
+            allreduce(pAp)
+            ops.cg_update(node0, node1, False, rz, pAp, P, AP, X, R, Z, red)
+            allreduce(red)
+            ops.cg_direction(r0, r1, False, rz, red, Z, P)          # red[:s] = new r.z
+            rz.copy_(red[:s])
+            it += 1
+            if (it % check_every == 0 or it == max_iter) and converged(red[s:], bb):
+                break
+    else:
         ops.precond_nodes(node0, node1, R, Z)
         red = torch.stack([(R[own]*Z[own]).sum(0), (R[own]*R[own]).sum(0)])
         allreduce(red)
-        rz_new, rr = red[0], red[1]
-        beta = torch.where(rz != 0, rz_new/rz, torch.zeros_like(rz))
-        P[own] = Z[own] + beta*P[own]
-        rz = rz_new.clone()
-        it += 1
-        if it % check_every == 0 or it == max_iter:
-            worst = float(torch.sqrt((rr/torch.where(bb > 0, bb, torch.ones_like(bb))).max()))
-            if log:
-                log(it, worst)
-            if not np.isfinite(worst) or worst <= tol:
+        rz, bb = red[0].clone(), red[1].clone()
+        P[own] = Z[own]
+        if float(bb.max()) == 0.0:
+            return X, 0, {'iterations': 0, 'max_rel_residual': 0.0, 'rows_per_rank': [], 'halo_rows': halo_rows, 'halo_bytes_per_iteration': 0}
+        while it < max_iter:
+            exchange(P)
+            ops.spmm_rows(r0, r1, P, AP)
+            pAp = allreduce((P[own]*AP[own]).sum(0))
+            alpha = torch.where(pAp != 0, rz/pAp, torch.zeros_like(rz))
+            X[own] += alpha*P[own]
+            R[own] -= alpha*AP[own]
+            ops.precond_nodes(node0, node1, R, Z)
+            red = torch.stack([(R[own]*Z[own]).sum(0), (R[own]*R[own]).sum(0)])
+            allreduce(red)
+            rz_new, rr = red[0], red[1]
+            beta = torch.where(rz != 0, rz_new/rz, torch.zeros_like(rz))
+            P[own] = Z[own] + beta*P[own]
+            rz = rz_new.clone()
+            it += 1
+            if (it % check_every == 0 or it == max_iter) and converged(rr, bb):
                 break
-            # the recurrence residual cannot drop below ~2^-53 cond(K11): stop when it has stopped improving
-            if worst < 0.99*best:
-                best, stalled = worst, 0
-            else:
-                stalled += 1
-                if stalled >= 8:
-                    break
     # every rank ends up with the whole solution: all-gather of the strips (ragged -> padded)
     if distributed:
         hmax = max(row_cuts[q + 1] - row_cuts[q] for q in range(world))

@@ -117,6 +117,9 @@ SIGNATURES = {
     'pn_dev_spmm_k11_rows': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
     'pn_dev_block_jacobi_setup': (ct.c_int, [_P]),
     'pn_dev_block_jacobi_nodes': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
+    'pn_dev_cg_dots': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
+    'pn_dev_cg_update': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_int32] + [ct.c_void_p]*8),
+    'pn_dev_cg_direction': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_int32] + [ct.c_void_p]*4),
     'pn_dev_get_rhs': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_void_p]),
     'pn_dev_set_solution': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_void_p]),
     'pn_get_displacements': (ct.c_int, [_P, ct.c_int32, _F64P]),
@@ -422,6 +425,15 @@ class Engine:
 
     def dev_block_jacobi_nodes(self, s, node0, node1, r_ptr, z_ptr):
         self._check(self._lib.pn_dev_block_jacobi_nodes(self._h, s, node0, node1, ct.c_void_p(r_ptr), ct.c_void_p(z_ptr)))
+
+    def dev_cg_dots(self, s, row0, row1, a_ptr, b_ptr, out_ptr):
+        self._check(self._lib.pn_dev_cg_dots(self._h, s, row0, row1, ct.c_void_p(a_ptr), ct.c_void_p(b_ptr), ct.c_void_p(out_ptr)))
+
+    def dev_cg_update(self, s, node0, node1, first, rz, pAp, P, AP, X, R, Z, out2):
+        self._check(self._lib.pn_dev_cg_update(self._h, s, node0, node1, 1 if first else 0, *[ct.c_void_p(p) for p in (rz, pAp, P, AP, X, R, Z, out2)]))
+
+    def dev_cg_direction(self, s, row0, row1, first, rz, rz_new, Z, P):
+        self._check(self._lib.pn_dev_cg_direction(self._h, s, row0, row1, 1 if first else 0, *[ct.c_void_p(p) for p in (rz, rz_new, Z, P)]))
 
     def dev_get_rhs(self, combo0, s, b_ptr):
         self._check(self._lib.pn_dev_get_rhs(self._h, combo0, s, ct.c_void_p(b_ptr)))
