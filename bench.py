@@ -335,7 +335,7 @@ def run_ours(args, rank, local_rank, world):
             a = asm_bytes/(asm_ms*1e-3)/1e9
             rooflines['assembly(element_ke+scatter_add)'] = {'bound': 'hbm', 'achieved': a, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': a/hbm_peak,
                                                              'algorithmic_bytes': asm_bytes, 'ms': asm_ms}
-    for srhs in (1, 8):
+    for srhs in (1, 8, 64):
         sms = eng.spmm_k11_time(srhs, 20)
         sb = sizes.nnz11*12 + (sizes.n1 + 1)*4 + 2*sizes.n1*srhs*8
         a = sb/(sms*1e-3)/1e9

@@ -46,7 +46,7 @@ constexpr int SA_LD = BK + 4; // leading dimensions = 4 mod 16 doubles: the DMMA
 constexpr int SB_LD = BN + 4;
 constexpr int GEMM_SMEM = (BM * SA_LD + BK * SB_LD) * (int)sizeof(double);   // 104 448 B, two CTAs per SM
 constexpr int DIAG_LD = NB + 1;
-constexpr int DIAG_SMEM = (3 * NB * DIAG_LD + 2 * (NB + 1)) * (int)sizeof(double);  // 100 880 B
+constexpr int DIAG_SMEM = (3 * NB * DIAG_LD + 5 * NB + 2) * (int)sizeof(double);      // 102 416 B, two CTAs per SM
 constexpr int GB = 256;      // pivots per group: the trailing matrix is streamed once per group (rank-GB update)
 
 struct FrontDev {
@@ -142,7 +142,7 @@ __global__ void k_assemble_entries(int64_t nnz, int level, const uint8_t *__rest
 // rows, threads walk columns (coalesced reads of the child row; the parent columns rel[b] are ascending runs).
 __global__ void k_extend_add(int first_child, int n_children, int rank, const FrontDev *__restrict__ fronts,
                              const int32_t *__restrict__ rel, const double *__restrict__ child_arena,
-                             double *__restrict__ parent_arena) {
+                             double *__restrict__ parent_arena, int sym) {
     int ci = blockIdx.x;
     if (ci >= n_children) return;
     FrontDev C = fronts[first_child + ci];
@@ -153,7 +153,9 @@ __global__ void k_extend_add(int first_child, int n_children, int rank, const Fr
     for (int a = blockIdx.y; a < C.nb; a += gridDim.y) {
         const double *src = child_arena + C.f_off + (int64_t)(C.ns + a) * nc + C.ns;
         double *dst = parent_arena + P.f_off + (int64_t)r[a] * np;
-        for (int b = threadIdx.x; b < C.nb; b += blockDim.x) dst[r[b]] += src[b];
+        // symmetric mode maintains the lower triangle only (rel is ascending, so it maps into the parent's lower triangle)
+        const int bend = sym ? a + 1 : C.nb;
+        for (int b = threadIdx.x; b < bend; b += blockDim.x) dst[r[b]] += src[b];
     }
 }
 
@@ -265,119 +267,212 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
     }
 }
 
-// LU (no pivoting) of one NB x NB diagonal block held in shared memory, then the inverses of its unit-lower and
-// upper triangles.  Called by the first 128 threads of a CTA (4 warps); contains __syncthreads-free named barriers
-// only, so the other warps of the CTA may skip it.  S holds the block on entry (identity-padded past bs) and the
-// packed L\U factors on exit; Li / Ui receive the inverses.
-//   LU      : thread i owns row i in registers; step p: row p is published through shared memory, every thread
-//             below divides by the pivot and updates its row (one barrier per step, 64 FMAs in registers).
-//   inverse : threads 0..63 build column j of Linv, threads 64..127 column j of Uinv by substitution, x in
-//             registers, the triangular factor read from shared memory as warp-wide broadcasts.
-__device__ __forceinline__ void bar128() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
-
-__device__ __forceinline__ void diag_block_factor(double (*S)[DIAG_LD], double (*Li)[DIAG_LD], double (*Ui)[DIAG_LD],
-                                                  double *rowbuf /* [2][NB] */, int *status) {
-    const int t = threadIdx.x;          // 0..127
-    double row[NB];
-    if (t < NB) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j) row[j] = S[t][j];
-    }
-#pragma unroll
-    for (int p = 0; p < NB; ++p) {
-        double *R = rowbuf + (p & 1) * (NB + 1);
-        if (t == p) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-                if (j >= p) R[j] = row[j];
-            double piv = row[p];
-            if (piv == 0.0 || !(fabs(piv) <= 1.7976931348623157e308)) atomicMax(status, 1);
-            R[NB] = 1.0 / piv;           // one reciprocal per step on the critical path instead of 63 divisions
-        }
-        bar128();
-        if (t < NB && t > p) {
-            double l = row[p] * R[NB];
-            row[p] = l;
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-                if (j > p) row[j] = fma(-l, R[j], row[j]);
-        }
-    }
-    if (t < NB) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j) S[t][j] = row[j];
-    }
-    bar128();
-    // reciprocals of the U diagonal for the upper inverse
-    if (t < NB) rowbuf[t] = 1.0 / S[t][t];
-    bar128();
-    if (t < NB) {
-        // column j = t of inverse(unit lower L):  x_j = 1,  x_i = -sum_{p=j..i-1} L[i][p] x_p
-        const int j = t;
-        double x[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            double a0 = 0.0;
-#pragma unroll
-            for (int p = 0; p < NB; ++p)
-                if (p < i) a0 = fma(S[i][p], (p >= j) ? x[p] : 0.0, a0);
-            x[i] = (i == j) ? 1.0 : ((i > j) ? -a0 : 0.0);
-        }
-#pragma unroll
-        for (int i = 0; i < NB; ++i) Li[i][j] = x[i];
-    } else {
-        // column j of inverse(upper U):  x_j = 1/U_jj,  x_i = -(sum_{p=i+1..j} U[i][p] x_p) / U_ii
-        const int j = t - NB;
-        double x[NB];
-#pragma unroll
-        for (int i = NB - 1; i >= 0; --i) {
-            double a0 = 0.0;
-#pragma unroll
-            for (int p = NB - 1; p >= 0; --p)
-                if (p > i) a0 = fma(S[i][p], (p <= j) ? x[p] : 0.0, a0);
-            double rd = rowbuf[i];
-            x[i] = (i == j) ? rd : ((i < j) ? -a0 * rd : 0.0);
-        }
-#pragma unroll
-        for (int i = 0; i < NB; ++i) Ui[i][j] = x[i];
-    }
-    bar128();
+// LU (no pivoting) of one NB x NB diagonal block, then the inverses of its unit-lower and upper triangles.
+// The kernel sits on the critical path of every block step (one launch per 64 pivots, a single CTA per front on the
+// top levels), so it is organised for latency, not throughput:
+//   LU      : 256 threads as a 16 x 16 grid, each owning a 4 x 4 register tile.  Step p: the owners of row p and of
+//             column p publish them (and the pivot's reciprocal: MUFU seed + two Newton steps, not an IEEE division)
+//             through double-buffered shared memory, ONE barrier, then every thread updates its tile.
+//   inverse : the two 32 x 32 diagonal blocks of each triangle by substitution in axpy form (one warp per block, one
+//             lane per column, 32 accumulators in registers: the dependent chain is 32 steps long, all other FMAs
+//             are independent), then the off-diagonal blocks as two small GEMMs by all 256 threads:
+//               inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]],   inv([[A,C],[0,B]]) = [[Ai,-Ai C Bi],[0,Bi]].
+__device__ __forceinline__ double rcp_newton(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
 }
 
-// Diagonal block [kb, kb+bs) of one front: load, factor + invert (first 128 threads), write back.  All threads of
-// the CTA must call it (it contains __syncthreads).
-__device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *arena, double *inv, int *status, int sym) {
+// Diagonal block [kb, kb+bs) of one front: load, factor + invert, write back.  All 256 threads of the CTA call it.
+#define PN_CLK(i) do { if (clk && threadIdx.x == 0) clk[i] = clock64(); } while (0)
+__device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *arena, double *inv, int *status, int sym,
+                                          long long *clk = nullptr) {
+    PN_CLK(0);
     double(*S)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem);
     double(*Li)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem + NB * DIAG_LD);
     double(*Ui)[DIAG_LD] = reinterpret_cast<double(*)[DIAG_LD]>(pn_dyn_smem + 2 * NB * DIAG_LD);
-    double *rowbuf = pn_dyn_smem + 3 * NB * DIAG_LD;
+    double *rowb = pn_dyn_smem + 3 * NB * DIAG_LD;      // [2][NB]
+    double *colb = rowb + 2 * NB;                       // [2][NB]
+    double *rdiag = colb + 2 * NB;                      // [NB] reciprocal pivots
+    double *rcpb = rdiag + NB;                          // [2]
     const int bs = min(NB, F.ns - kb);
     const int n = F.ns + F.nb;
     double *A = arena + F.f_off + (int64_t)kb * n + kb;
-    const int t = threadIdx.x;
-    for (int e = t; e < NB * NB; e += blockDim.x) {
-        int i = e / NB, j = e % NB;
-        // symmetric mode: only the lower triangle of the front is maintained; mirror it
-        int si = (sym && j > i) ? j : i, sj = (sym && j > i) ? i : j;
-        S[i][j] = (i < bs && j < bs) ? A[(int64_t)si * n + sj] : (i == j ? 1.0 : 0.0);
+    // thread (ti, tj) owns rows ti + 16 r and columns tj + 16 c (cyclic: the published row / column and the smem and
+    // global accesses are contiguous across the lanes of a half-warp, and every thread stays busy until the end)
+    const int t = threadIdx.x, ti = t >> 4, tj = t & 15;
+    double a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ti + 16 * r, j = tj + 16 * c;
+            // symmetric mode: only the lower triangle of the front is maintained; mirror it
+            const int si = (sym && j > i) ? j : i, sj = (sym && j > i) ? i : j;
+            a[r][c] = (i < bs && j < bs) ? A[(int64_t)si * n + sj] : (i == j ? 1.0 : 0.0);
+        }
+    PN_CLK(1);
+#pragma unroll
+    for (int qb = 0; qb < 4; ++qb) {
+        for (int pp = 0; pp < 16; ++pp) {
+            const int p = 16 * qb + pp;
+            double *R = rowb + (pp & 1) * NB, *Cc = colb + (pp & 1) * NB;
+            if (ti == pp) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) R[tj + 16 * c] = a[qb][c];
+            }
+            if (tj == pp) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) Cc[ti + 16 * r] = a[r][qb];
+                if (ti == pp) {
+                    const double piv = a[qb][qb];
+                    if (piv == 0.0 || !(fabs(piv) <= 1.7976931348623157e308)) atomicMax(status, 1);
+                    const double rc = rcp_newton(piv);
+                    rcpb[pp & 1] = rc;
+                    rdiag[p] = rc;
+                }
+            }
+            __syncthreads();
+            // branch-free update: rows / columns that are not below / right of the pivot get a zero multiplier
+            const double rc = rcpb[pp & 1];
+            double l[4], u[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool act = (r > qb) || (r == qb && ti > pp);
+                l[r] = act ? Cc[ti + 16 * r] * rc : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool act = (c > qb) || (c == qb && tj > pp);
+                u[c] = act ? R[tj + 16 * c] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) a[r][c] = fma(-l[r], u[c], a[r][c]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool act = (tj == pp) && ((r > qb) || (r == qb && ti > pp));
+                a[r][qb] = act ? l[r] : a[r][qb];
+            }
+        }
+    }
+    PN_CLK(2);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ti + 16 * r, j = tj + 16 * c;
+            S[i][j] = a[r][c];
+            if (i < bs && j < bs) A[(int64_t)i * n + j] = a[r][c];
+        }
+    __syncthreads();
+    PN_CLK(3);
+    // ---- 32 x 32 diagonal blocks of the two inverses: warp 0/1 = Linv blocks, warp 2/3 = Uinv blocks ----
+    const int warp = t >> 5, lane = t & 31;
+    if (warp < 2) {
+        const int o = 32 * warp;
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const double xp = acc[p];
+#pragma unroll
+            for (int i = p + 1; i < 32; ++i) acc[i] = fma(-S[o + i][o + p], xp, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Li[o + i][o + lane] = acc[i];
+    } else if (warp < 4) {
+        const int o = 32 * (warp - 2);
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int p = 31; p >= 0; --p) {
+            const double xp = acc[p] * rdiag[o + p];
+            acc[p] = xp;
+#pragma unroll
+            for (int i = 0; i < p; ++i) acc[i] = fma(-S[o + i][o + p], xp, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Ui[o + i][o + lane] = acc[i];
     }
     __syncthreads();
-    if (t < 128) diag_block_factor(S, Li, Ui, rowbuf, status);
+    PN_CLK(4);
+    // ---- off-diagonal blocks: T = C Ai (lower) / C Bi (upper), then X = -Bi T / -Ai T ----
+    // thread = (matrix m, row group w of 8 rows, column lane): the B operand row is read contiguously across the
+    // lanes, the A operand as warp-wide broadcasts
+    const int m = t >> 7, r0 = 8 * ((t >> 5) & 3);
+    {
+        double acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+        if (m == 0) {
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const double bv = Li[k][lane];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = fma(S[32 + r0 + r][k], bv, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) Li[r0 + r][32 + lane] = acc[r];          // scratch: the (zero) upper-right block
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const double bv = Ui[32 + k][32 + lane];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = fma(S[r0 + r][32 + k], bv, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) Ui[32 + r0 + r][lane] = acc[r];          // scratch: the (zero) lower-left block
+        }
+    }
     __syncthreads();
-    for (int e = t; e < bs * bs; e += blockDim.x) A[(int64_t)(e / bs) * n + e % bs] = S[e / bs][e % bs];
+    {
+        double acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+        if (m == 0) {
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const double bv = Li[k][32 + lane];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = fma(-Li[32 + r0 + r][32 + k], bv, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) Li[32 + r0 + r][lane] = acc[r];
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const double bv = Ui[32 + k][lane];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = fma(-Ui[r0 + r][k], bv, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) Ui[r0 + r][32 + lane] = acc[r];
+        }
+    }
+    __syncthreads();
+    PN_CLK(5);
     double *out = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
     for (int e = t; e < NB * NB; e += blockDim.x) {
-        out[e] = Li[e / NB][e % NB];
-        out[NB * NB + e] = Ui[e / NB][e % NB];
+        const int i = e / NB, j = e % NB;
+        out[e] = (j > i) ? 0.0 : Li[i][j];               // the scratch blocks are not part of the result
+        out[NB * NB + e] = (j < i) ? 0.0 : Ui[i][j];
     }
+    PN_CLK(6);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 2)
 k_lu_diag(int first, int kb, const FrontDev *__restrict__ fronts, double *__restrict__ arena, double *__restrict__ inv,
-          int *__restrict__ status, int sym) {
+          int *__restrict__ status, int sym, long long *clk) {
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
-    diag_step(F, kb, arena, inv, status, sym);
+    diag_step(F, kb, arena, inv, status, sym, blockIdx.x == 0 ? clk : nullptr);
 }
 
 // Panels of block step kb as GEMMs with the diagonal inverses.  grid.x = front; grid.y < tiles_u: column
@@ -841,6 +936,44 @@ static void analyse(Ctx *c) {
     c->stats.solve_flops = 2.0 * (double)S.factor_entries;
 }
 
+// PN_DEBUG_LEVELS: device time of every launch class inside one level (events around each launch)
+struct LevelProf {
+    bool on;
+    cudaStream_t st;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls;
+    size_t used = 0;
+    static constexpr int NC = 8;
+    LevelProf(bool enable, cudaStream_t s) : on(enable), st(s) {}
+    void begin(int c) {
+        if (!on) return;
+        if (used + 2 > ev.size()) { ev.resize(used + 2); cudaEventCreate(&ev[used]); cudaEventCreate(&ev[used + 1]); }
+        cls.push_back(c);
+        cudaEventRecord(ev[used], st);
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(ev[used + 1], st);
+        used += 2;
+    }
+    void report(int level) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        double ms[NC] = {0}; int n[NC] = {0};
+        for (size_t i = 0; i < cls.size(); ++i) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+            ms[cls[i]] += t; n[cls[i]]++;
+        }
+        static const char *names[NC] = {"zero+assemble", "extend_add", "diag", "panels", "transpose", "strip", "update", "store"};
+        fprintf(stderr, "[pn]   level %2d kernels:", level);
+        for (int c = 0; c < NC; ++c) if (n[c]) fprintf(stderr, " %s %.3f ms/%d", names[c], ms[c], n[c]);
+        fprintf(stderr, "\n");
+        cls.clear(); used = 0;
+    }
+    ~LevelProf() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
 static void factorise(Ctx *c, const double *vals11) {
     DirectSolver &d = *c->direct;
     cudaStream_t st = c->stream;
@@ -852,6 +985,10 @@ static void factorise(Ctx *c, const double *vals11) {
     static const bool debug_levels = getenv("PN_DEBUG_LEVELS") != nullptr;
     cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
     if (debug_levels) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); }
+    static const bool debug_kernels = getenv("PN_DEBUG_LEVEL_KERNELS") != nullptr;
+    LevelProf lp(debug_levels && debug_kernels, st);
+    long long *dbg_clk = nullptr;
+    if (debug_levels && debug_kernels) cudaMalloc(&dbg_clk, 8 * sizeof(long long));
     const CsrBlock &A = c->blk[0];
     d.status.zero(st);
     for (int l = 0; l < d.n_levels; ++l) {
@@ -859,9 +996,11 @@ static void factorise(Ctx *c, const double *vals11) {
         if (!nfl) continue;
         double *arena = d.arena[l & 1].ptr;
         if (debug_levels) cudaEventRecord(dbg0, st);
+        lp.begin(0);
         PN_CUDA(cudaMemsetAsync(arena, 0, sizeof(double) * d.level_f_total[l], st));
         { ProfScope ps_(c, PS_FRONT_ASSEMBLE); k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
                                                                   d.fronts.ptr, vals11, arena); }
+        lp.end();
         c->count_launch();
         if (l > 0) {
             int cfirst = d.level_ptr[l - 1], ncl = d.level_ptr[l] - cfirst;
@@ -869,8 +1008,10 @@ static void factorise(Ctx *c, const double *vals11) {
             // enough row chunks to fill the GPU when the level has few children, few when it has thousands
             unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(nbmax, 1), std::max<int64_t>(1, 16384 / std::max(ncl, 1)));
             for (int r = 0; r < d.level_max_children[l - 1]; ++r) {
+                lp.begin(1);
                 { ProfScope ps_(c, PS_EXTEND_ADD); k_extend_add<<<dim3(ncl, gy), 256, 0, st>>>(cfirst, ncl, r, d.fronts.ptr, d.rel.ptr, d.arena[(l - 1) & 1].ptr,
-                                                             arena); }
+                                                             arena, sym); }
+                lp.end();
                 c->count_launch();
             }
         }
@@ -878,18 +1019,32 @@ static void factorise(Ctx *c, const double *vals11) {
         for (int g0 = 0; g0 < maxns; g0 += GB) {
             int gend = std::min(g0 + GB, maxns);
             for (int kb = g0; kb < gend; kb += NB) {
-                { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 128, DIAG_SMEM, st>>>(first, kb, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr, sym); }
+                lp.begin(2);
+                { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 256, DIAG_SMEM, st>>>(first, kb, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr, sym, dbg_clk); }
+                if (dbg_clk && kb == 0) {
+                    long long h[8];
+                    cudaMemcpyAsync(h, dbg_clk, sizeof(h), cudaMemcpyDeviceToHost, st);
+                    cudaStreamSynchronize(st);
+                    fprintf(stderr, "[pn]   level %2d diag clocks: load %lld  lu %lld  store %lld  inv32 %lld  gemm %lld  out %lld\n", l, h[1] - h[0],
+                            h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+                }
+                lp.end();
                 c->count_launch();
                 int rest = maxn - kb - 1;          // upper bound of the trailing size over the level's fronts
                 if (rest > 0) {
                     int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
+                    lp.begin(3);
                     { ProfScope ps_(c, PS_LU_PANELS); k_lu_panels<<<dim3(nfl, tiles_u + tiles_l), 256, GEMM_SMEM, st>>>(first, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym);
+                      lp.end(); lp.begin(4);
                       if (sym) k_lu_transpose_panel<<<dim3(nfl, (rest + 31) / 32), dim3(32, 8), 0, st>>>(first, kb, d.fronts.ptr, arena); }
+                    lp.end();
                     c->count_launch(1 + sym);
                     if (kb + NB < gend) {
                         int wa = gend - kb - NB;       // strips inside the group
                         int tiles = ((rest + BM - 1) / BM) * ((wa + BN - 1) / BN) + ((wa + BM - 1) / BM) * tiles_u;
+                        lp.begin(5);
                         { ProfScope ps_(c, PS_LU_PANELS); k_lu_strip<<<dim3(nfl, tiles), 256, GEMM_SMEM, st>>>(first, kb, g0, d.fronts.ptr, arena, sym); }
+                        lp.end();
                         c->count_launch();
                     }
                 }
@@ -897,11 +1052,14 @@ static void factorise(Ctx *c, const double *vals11) {
             int rest = maxn - g0 - 1;
             if (rest > 0) {
                 int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
+                lp.begin(6);
                 { ProfScope ps_(c, PS_LU_UPDATE); k_lu_update<<<dim3(nfl, tiles_l, tiles_u), 256, GEMM_SMEM, st>>>(first, g0, d.fronts.ptr, arena, sym); }
+                lp.end();
                 c->count_launch();
             }
         }
         {
+            lp.begin(7);
             ProfScope ps_(c, PS_COPY_FACTORS);
             int steps = (maxns + NB - 1) / NB;
             int row_tiles = (maxn + BM - 1) / BM + 1;
@@ -911,6 +1069,7 @@ static void factorise(Ctx *c, const double *vals11) {
                 unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((per + 255) / 256, 1), 2048);
                 k_copy_u12<<<dim3(nfl, gy), 256, 0, st>>>(first, d.fronts.ptr, arena, d.U.ptr);
             }
+            lp.end();
             c->count_launch(2);
         }
         if (debug_levels) {
@@ -925,9 +1084,11 @@ static void factorise(Ctx *c, const double *vals11) {
             }
             fprintf(stderr, "[pn] level %2d: %6d fronts, max ns %5d, max n %5d, arena %8.1f MB, %8.3f ms, %7.2f GFLOP -> %6.2f TFLOP/s\n",
                     l, nfl, maxns, maxn, d.level_f_total[l] * 8e-6, ms, fl * 1e-9, fl / (ms * 1e-3) * 1e-12);
+            lp.report(l);
         }
     }
     if (debug_levels) { cudaEventDestroy(dbg0); cudaEventDestroy(dbg1); }
+    if (dbg_clk) cudaFree(dbg_clk);
     int status = 0;
     PN_CUDA(cudaMemcpyAsync(&status, d.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
