@@ -84,6 +84,9 @@ struct DirectSolver {
     DevBuf<int> status;                       // 0 ok, 1 zero / non-finite pivot, 2 entry outside front
     bool shared_factor = false;               // the stored factor belongs to the matrix shared by all columns (Ke)
     DevBuf<double> col_in, col_out;           // per-column solves (P-Delta)
+    DevBuf<uint32_t> ll_flags;                // left-looking sweeps: one flag per (pivot block, column chunk)
+    uint32_t ll_epoch = 0;
+    int ll_grid = 0;                          // resident CTAs of k_ll_sweep (all units' owners must be co-resident)
     int64_t arena_cap = 0;
 };
 
@@ -194,39 +197,74 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
     const int row0 = tile_m * BM, col0 = tile_n * BN;
     const int wrow = (warp >> 1) * 32, wcol = (warp & 1) * 32;
     double acc[4][4][2];
+    const bool full_tile = row0 + BM <= m && col0 + BN <= n;
+    if (mode != 0) {
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-        int gr = row0 + wrow + 8 * mi + g;
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            int gc = col0 + wcol + 8 * ni + 2 * tg;
-            bool ok = mode == 0 && gr < m;
-            acc[mi][ni][0] = (ok && gc < n) ? C[(int64_t)gr * ldc + gc] : 0.0;
-            acc[mi][ni][1] = (ok && gc + 1 < n) ? C[(int64_t)gr * ldc + gc + 1] : 0.0;
+            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    } else if (full_tile) {
+        const double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 2 * tg;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                acc[mi][ni][0] = c0p[(int64_t)(8 * mi) * ldc + 8 * ni];
+                acc[mi][ni][1] = c0p[(int64_t)(8 * mi) * ldc + 8 * ni + 1];
+            }
+    } else {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            int gr = row0 + wrow + 8 * mi + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                int gc = col0 + wcol + 8 * ni + 2 * tg;
+                bool ok = gr < m;
+                acc[mi][ni][0] = (ok && gc < n) ? C[(int64_t)gr * ldc + gc] : 0.0;
+                acc[mi][ni][1] = (ok && gc + 1 < n) ? C[(int64_t)gr * ldc + gc + 1] : 0.0;
+            }
         }
     }
     const double sign = mode == 0 ? -1.0 : 1.0;
     // k runs through a ring of four 16-wide slices of the shared tiles (slot = slice & 3): slice sl + 3 is in
     // flight while slice sl is multiplied, one barrier per slice.
+    // The DMMA holds the issue port of its scheduler for its whole duration (tools/microbench/dmma_occupancy.cu:
+    // every other instruction costs ~0.85 cycles of tensor time, at any occupancy), so the copy loop issues as few
+    // instructions as it can while staying coalesced (16 consecutive lanes = 16 consecutive k of one A row / 64
+    // consecutive columns of one B row) and conflict-free in shared memory: per copy one 32-bit offset from a
+    // per-slice base (IMAD), one IMAD.WIDE, one LDGSTS; the row / column predicates are decided once per tile.
+    // Rows >= m of the A tile and columns >= n of the B tile only feed accumulators that are never stored, so in
+    // full slices their copies are clamped to a valid row / column instead of being predicated.
     const int nsl = (k + 15) >> 4;
+    const int ra = tid >> 4, ka = tid & 15;                 // A: rows ra + 16 i (i < 8), k column ka
+    const int kr = tid >> 6, cb = tid & 63;                 // B: k rows kr + 4 i (i < 4), column cb
+    const int a_last = m - 1 - row0;                        // last valid tile row
+    const int cbc = min(cb, n - 1 - col0);                  // clamped column
+    const uint32_t lda32 = (uint32_t)lda, ldb32 = (uint32_t)ldb;
+    const double *Abase = A + (int64_t)row0 * lda + ka;
+    const double *Bbase = B + col0 + cbc;
     auto issue = [&](int sl) {
         if (sl < nsl) {
             const int slot = sl & 3, kbase = sl << 4;
+            const double *sa = Abase + kbase;
+            const double *sb = Bbase + (int64_t)kbase * ldb;
+            double *ta = &sA[ra][16 * slot + ka], *tb = &sB[16 * slot + kr][cb];
+            if (kbase + 16 <= k) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int e = tid + 256 * i;
-                int r = e >> 4, kk = e & 15;
-                int gr = row0 + r;
-                bool ok = gr < m && kbase + kk < k;
-                cp_async8(&sA[r][16 * slot + kk], ok ? A + (int64_t)gr * lda + kbase + kk : A, ok);
-            }
+                for (int i = 0; i < 8; ++i) cp_async8(ta + 16 * i * SA_LD, sa + (uint32_t)min(ra + 16 * i, a_last) * lda32, true);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int e = tid + 256 * i;
-                int kr = e >> 6, cc = e & 63;
-                int gc = col0 + cc;
-                bool ok = kbase + kr < k && gc < n;
-                cp_async8(&sB[16 * slot + kr][cc], ok ? B + (int64_t)(kbase + kr) * ldb + gc : B, ok);
+                for (int i = 0; i < 4; ++i) cp_async8(tb + 4 * i * SB_LD, sb + (uint32_t)(kr + 4 * i) * ldb32, true);
+            } else {                                        // last, partial slice: zero-fill k >= k_valid
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool ok = kbase + ka < k;
+                    cp_async8(ta + 16 * i * SA_LD, ok ? sa + (uint32_t)min(ra + 16 * i, a_last) * lda32 : A, ok);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool ok = kbase + kr + 4 * i < k;
+                    cp_async8(tb + 4 * i * SB_LD, ok ? sb + (uint32_t)(kr + 4 * i) * ldb32 : B, ok);
+                }
             }
         }
         cp_async_commit();
@@ -253,6 +291,17 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
     }
     cp_async_wait<0>();
     __syncthreads();          // the tiles may be refilled by the caller's next gemm_tile call
+    if (full_tile) {
+        double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 2 * tg;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                c0p[(int64_t)(8 * mi) * ldc + 8 * ni] = acc[mi][ni][0];
+                c0p[(int64_t)(8 * mi) * ldc + 8 * ni + 1] = acc[mi][ni][1];
+            }
+        return;
+    }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         int gr = row0 + wrow + 8 * mi + g;
@@ -772,6 +821,415 @@ k_front_backward(int first, int s, const FrontDev *__restrict__ fronts, const in
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sweeps with the front's right-hand-side block resident in shared memory.
+// A CTA owns (front, chunk of CW right-hand-side columns): the (ns+nb) x CW block w lives in shared memory for the
+// whole sweep of the front, so the only global traffic is the gather from X / the children, ONE streaming pass over
+// the front's stored panels, and the result rows.  Warps own 16-row slabs of the panel; the DMMA A fragments are read
+// straight from global memory (every quad of lanes reads one full 32-byte sector) into registers, one 32-wide k
+// chunk ahead of the math; the B fragments (rows of w for the pivot block) and the accumulators come from shared
+// memory with leading dimension CW + 4 (conflict-free fragment loads, see gemm_tile).
+// Used for every level whose largest front fits (n + 32) * (CW + 4) * 8 bytes <= 227 KB for some CW in {32, 16, 8}.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_PAD_ROWS = 32;       // zeroed rows after the block: k chunks may run past the last valid row
+constexpr int SW_MAX_SMEM = 232448;   // 227 KB
+constexpr int SW_TWO_CTA_SMEM = 113 * 1024;
+
+// acc += (NEG ? -1 : 1) * A[0:16, 0:kc] * Bs[0:kc, 0:CW]   for one 16-row slab.  A: global, row-major, leading
+// dimension lda; rows >= rows_valid and columns >= kc read as zero.  Bs: shared, leading dimension CW + 4.
+template <int CW, bool NEG>
+__device__ __forceinline__ void slab_mma(double (&acc)[2][CW / 8][2], const double *__restrict__ A, int64_t lda, int rows_valid,
+                                         int kc, const double *Bs, int lane) {
+    constexpr int LDW = CW + 4, NT = CW / 8;
+    const int g = lane >> 2, tg = lane & 3;
+    const bool v0 = g < rows_valid, v1 = g + 8 < rows_valid;
+    const double *a0p = A + (int64_t)g * lda + tg;
+    const double *a1p = A + (int64_t)(g + 8) * lda + tg;
+    constexpr int KS = (CW >= 32) ? 4 : 8;          // k steps (of 4) per prefetched chunk: registers vs distance
+    constexpr int KCH = 4 * KS;
+    const int nch = (kc + KCH - 1) / KCH;
+    double cur[2][KS], nxt[2][KS];
+    auto load = [&](double (&d)[2][KS], int ch) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int k = KCH * ch + 4 * ks;
+            const bool kv = k + tg < kc;
+            d[0][ks] = (v0 && kv) ? __ldg(a0p + k) : 0.0;
+            d[1][ks] = (v1 && kv) ? __ldg(a1p + k) : 0.0;
+        }
+    };
+    load(cur, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) load(nxt, ch + 1);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const double *brow = Bs + (KCH * ch + 4 * ks + tg) * LDW + g;
+            double b[NT];
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) b[ni] = brow[8 * ni];
+            const double a0 = NEG ? -cur[0][ks] : cur[0][ks], a1 = NEG ? -cur[1][ks] : cur[1][ks];
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) {
+                dmma884(acc[0][ni][0], acc[0][ni][1], a0, b[ni]);
+                dmma884(acc[1][ni][0], acc[1][ni][1], a1, b[ni]);
+            }
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) { cur[0][ks] = nxt[0][ks]; cur[1][ks] = nxt[1][ks]; }
+    }
+}
+
+// accumulators <-> rows [r, r + 16) of the shared block (c fragment: row g / g + 8, columns 2 tg, 2 tg + 1 of every n tile)
+template <int CW>
+__device__ __forceinline__ void slab_load_c(double (&acc)[2][CW / 8][2], const double *w, int r, int n, int lane) {
+    constexpr int LDW = CW + 4, NT = CW / 8;
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        const int row = r + 8 * mi + g;
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            double2 v = row < n ? *reinterpret_cast<const double2 *>(w + row * LDW + 8 * ni + 2 * tg) : make_double2(0.0, 0.0);
+            acc[mi][ni][0] = v.x; acc[mi][ni][1] = v.y;
+        }
+    }
+}
+template <int CW>
+__device__ __forceinline__ void slab_store_c(const double (&acc)[2][CW / 8][2], double *w, int r, int n, int lane) {
+    constexpr int LDW = CW + 4, NT = CW / 8;
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        const int row = r + 8 * mi + g;
+        if (row >= n) continue;
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni)
+            *reinterpret_cast<double2 *>(w + row * LDW + 8 * ni + 2 * tg) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    }
+}
+// solved rows [i0, i0 + 16) of pivot block kb straight to X
+template <int CW>
+__device__ __forceinline__ void slab_store_x(const double (&acc)[2][CW / 8][2], double *__restrict__ X, const int32_t *__restrict__ fi,
+                                             int kb, int i0, int bs, int s, int c0, int lane) {
+    constexpr int NT = CW / 8;
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        const int i = i0 + 8 * mi + g;
+        if (i >= bs) continue;
+        double *dst = X + (int64_t)fi[kb + i] * s + c0;
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            const int col = 8 * ni + 2 * tg;
+            if (c0 + col < s) dst[col] = acc[mi][ni][0];
+            if (c0 + col + 1 < s) dst[col + 1] = acc[mi][ni][1];
+        }
+    }
+}
+
+// w[r][0:CW] = X[fi[r]][c0 : c0 + CW] for r < rows_x, zero for rows_x <= r < rows_all; four rows per thread in flight
+template <int CW>
+__device__ __noinline__ void sweep_gather(double *w, const double *__restrict__ X, const int32_t *__restrict__ fi, int rows_x,
+                                             int rows_all, int s, int c0, int tid) {
+    constexpr int LDW = CW + 4, RPP = 256 / CW;
+    const int j = tid % CW, a0 = tid / CW;
+    const bool cv = c0 + j < s;
+    for (int base = 0; base < rows_all; base += 4 * RPP) {
+        int32_t src[4];
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = base + q * RPP + a0;
+            src[q] = (cv && r < rows_x) ? fi[r] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = src[q] >= 0 ? X[(int64_t)src[q] * s + c0 + j] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = base + q * RPP + a0;
+            if (r < rows_all) w[r * LDW + j] = v[q];
+        }
+    }
+}
+
+// w[rc[a]][0:CW] += wc[a][0:CW] for the nb boundary rows of one child; four rows per thread in flight
+template <int CW>
+__device__ __noinline__ void sweep_add_child(double *w, const double *__restrict__ wc, const int32_t *__restrict__ rc, int nb, int s,
+                                             int c0, int tid) {
+    constexpr int LDW = CW + 4, RPP = 256 / CW;
+    const int j = tid % CW, a0 = tid / CW;
+    const bool cv = c0 + j < s;
+    for (int base = 0; base < nb; base += 4 * RPP) {
+        double v[4];
+        int dst[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int a = base + q * RPP + a0;
+            const bool ok = cv && a < nb;
+            dst[q] = ok ? rc[a] : -1;
+            v[q] = ok ? wc[(int64_t)a * s + j] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (dst[q] >= 0) w[dst[q] * LDW + j] += v[q];
+    }
+}
+
+template <int CW>
+__global__ void __launch_bounds__(256, 2)
+k_front_forward_sm(int first, int s, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
+                   const int32_t *__restrict__ rel, const int32_t *__restrict__ child_ptr, const int32_t *__restrict__ child_idx,
+                   const double *__restrict__ L, const double *__restrict__ inv, double *__restrict__ X,
+                   double *__restrict__ Wout, const double *__restrict__ Wchild) {
+    constexpr int LDW = CW + 4, NT = CW / 8;
+    double *w = pn_dyn_smem;
+    const int f = first + blockIdx.x;
+    const FrontDev F = fronts[f];
+    const int n = F.ns + F.nb, c0 = blockIdx.y * CW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t *fi = fidx + F.idx_off;
+    // own rows from X, boundary rows and the padding rows zero
+    sweep_gather<CW>(w, X, fi, F.ns, n + SW_PAD_ROWS, s, c0, tid);
+    __syncthreads();
+    // update vectors of the children, in child-rank order (fixed summation order)
+    for (int ci = child_ptr[f]; ci < child_ptr[f + 1]; ++ci) {
+        const FrontDev C = fronts[child_idx[ci]];
+        const int32_t *rc = rel + C.rel_off;
+        const double *wc = Wchild + C.w_off + (int64_t)C.ns * s + c0;
+        sweep_add_child<CW>(w, wc, rc, C.nb, s, c0, tid);
+        __syncthreads();
+    }
+    for (int kb = 0; kb < F.ns; kb += NB) {
+        const int bs = min(NB, F.ns - kb);
+        const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
+        const int r0 = kb + bs, rest = n - r0;
+        const int dslabs = (bs + 15) >> 4, nslabs = dslabs + ((rest + 15) >> 4);
+        const double *Bs = w + kb * LDW;
+        for (int sl = warp; sl < nslabs; sl += 8) {
+            double acc[2][NT][2];
+            if (sl < dslabs) {                 // y_k = Linv_kk w_k  -> X
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                slab_mma<CW, false>(acc, Linv + (int64_t)(16 * sl) * NB, NB, NB - 16 * sl, bs, Bs, lane);   // columns >= bs are zero
+                slab_store_x<CW>(acc, X, fi, kb, 16 * sl, bs, s, c0, lane);
+            } else {                           // w[r] -= Lp[r, k] w_k  (old w_k: the panel is pre-multiplied by Linv_kk)
+                const int r = r0 + 16 * (sl - dslabs);
+                slab_load_c<CW>(acc, w, r, n, lane);
+                slab_mma<CW, true>(acc, L + F.l_off + (int64_t)r * F.ns + kb, F.ns, n - r, bs, Bs, lane);
+                slab_store_c<CW>(acc, w, r, n, lane);
+            }
+        }
+        __syncthreads();
+    }
+    // update vector for the parent
+    double *wo = Wout + F.w_off + (int64_t)F.ns * s + c0;
+    for (int e = tid; e < F.nb * CW; e += 256) {
+        const int a = e / CW, j = e % CW;
+        if (c0 + j < s) wo[(int64_t)a * s + j] = w[(F.ns + a) * LDW + j];
+    }
+}
+
+template <int CW>
+__global__ void __launch_bounds__(256, 2)
+k_front_backward_sm(int first, int s, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
+                    const double *__restrict__ L, const double *__restrict__ U, const double *__restrict__ inv,
+                    double *__restrict__ X) {
+    constexpr int LDW = CW + 4, NT = CW / 8;
+    double *w = pn_dyn_smem;
+    const FrontDev F = fronts[first + blockIdx.x];
+    const int n = F.ns + F.nb, c0 = blockIdx.y * CW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t *fi = fidx + F.idx_off;
+    // own rows hold y, boundary rows the final x of the ancestors
+    sweep_gather<CW>(w, X, fi, n, n + SW_PAD_ROWS, s, c0, tid);
+    __syncthreads();
+    if (F.nb) {                                // w[0:ns] -= U12 w[ns:n]
+        const int nslabs = (F.ns + 15) >> 4;
+        for (int sl = warp; sl < nslabs; sl += 8) {
+            double acc[2][NT][2];
+            const int r = 16 * sl;
+            slab_load_c<CW>(acc, w, r, F.ns, lane);
+            slab_mma<CW, true>(acc, U + F.u_off + (int64_t)r * F.nb, F.nb, F.ns - r, F.nb, w + F.ns * LDW, lane);
+            slab_store_c<CW>(acc, w, r, F.ns, lane);
+        }
+        __syncthreads();
+    }
+    for (int kb = ((F.ns - 1) / NB) * NB; kb >= 0; kb -= NB) {
+        const int bs = min(NB, F.ns - kb);
+        const double *Uinv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB) + NB * NB;
+        const int dslabs = (bs + 15) >> 4, nslabs = dslabs + ((kb + 15) >> 4);
+        const double *Bs = w + kb * LDW;
+        for (int sl = warp; sl < nslabs; sl += 8) {
+            double acc[2][NT][2];
+            if (sl < dslabs) {                 // x_k = Uinv_kk w_k  -> X
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                slab_mma<CW, false>(acc, Uinv + (int64_t)(16 * sl) * NB, NB, NB - 16 * sl, bs, Bs, lane);   // columns >= bs are zero
+                slab_store_x<CW>(acc, X, fi, kb, 16 * sl, bs, s, c0, lane);
+            } else {                           // w[r] -= Lp[r, k] w_k for the rows above block k
+                const int r = 16 * (sl - dslabs);
+                slab_load_c<CW>(acc, w, r, kb, lane);
+                slab_mma<CW, true>(acc, L + F.l_off + (int64_t)r * F.ns + kb, F.ns, kb - r, bs, Bs, lane);
+                slab_store_c<CW>(acc, w, r, kb, lane);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Left-looking sweeps for the levels with few, large fronts (the per-step launches of the general path cost one
+// launch latency per 64 pivots: 47 dependent launches for a 3000-pivot root separator).
+// One persistent kernel per level and direction.  A unit = (64-row tile of a front, 32-column chunk of the right-hand
+// sides); the CTA that owns a unit keeps the tile in its accumulators and subtracts panel x w_k for EVERY earlier
+// pivot block k in one long k loop (the tile's rows of the stored panels are streamed exactly once, nothing is
+// read-modify-written), waiting for block k's rows through a per-block flag in global memory.  When its own rows are
+// final it publishes them (release store of the sweep's epoch number) and only then multiplies by the diagonal
+// inverse.  Units are numbered tile-major and every CTA takes units in increasing order with all CTAs resident, so
+// the lowest unfinished unit never waits on an unscheduled one.  Summation order is fixed (k ascending / descending).
+// ------------------------------------------------------------------------------------------------
+constexpr int LL_MAX_CHUNKS = 8;          // 32-column chunks: up to 256 right-hand sides
+__device__ __forceinline__ void flag_wait(const uint32_t *flag, uint32_t epoch, int lane) {
+    if (lane == 0) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v < epoch) __nanosleep(40);
+        } while (v < epoch);
+    }
+    __syncwarp();
+}
+
+// acc -= A[0:16, 0:kc] * Bg[0:kc, 0:16]  (A: global row-major, ld lda;  Bg: global row-major, ld ldb, read through
+// L2 only: the rows were written by another CTA of this kernel)
+__device__ __forceinline__ void slab_mma_g(double (&acc)[2][2][2], const double *__restrict__ A, int64_t lda, int rows_valid, int kc,
+                                           const double *Bg, int64_t ldb, int cols_valid, int lane, bool neg) {
+    const int g = lane >> 2, tg = lane & 3;
+    const bool v0 = g < rows_valid, v1 = g + 8 < rows_valid;
+    const bool c0v = g < cols_valid, c1v = g + 8 < cols_valid;
+    const double *a0p = A + (int64_t)g * lda + tg;
+    const double *a1p = A + (int64_t)(g + 8) * lda + tg;
+    const double *bp = Bg + (int64_t)tg * ldb + g;
+    for (int kb = 0; kb < kc; kb += 16) {
+        double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int k = kb + 4 * ks;
+            const bool kv = k + tg < kc;
+            a0[ks] = (v0 && kv) ? __ldg(a0p + k) : 0.0;
+            a1[ks] = (v1 && kv) ? __ldg(a1p + k) : 0.0;
+            b0[ks] = (c0v && kv) ? __ldcg(bp + (int64_t)k * ldb) : 0.0;
+            b1[ks] = (c1v && kv) ? __ldcg(bp + (int64_t)k * ldb + 8) : 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const double x0 = neg ? -a0[ks] : a0[ks], x1 = neg ? -a1[ks] : a1[ks];
+            dmma884(acc[0][0][0], acc[0][0][1], x0, b0[ks]);
+            dmma884(acc[0][1][0], acc[0][1][1], x0, b1[ks]);
+            dmma884(acc[1][0][0], acc[1][0][1], x1, b0[ks]);
+            dmma884(acc[1][1][0], acc[1][1][1], x1, b1[ks]);
+        }
+    }
+}
+
+// c fragments <-> 16 rows x 16 columns of a global row-major block (ld = s); rows / columns past the valid range skipped
+__device__ __forceinline__ void frag_load_g(double (&acc)[2][2][2], const double *P, int64_t ld, int rows_valid, int cols_valid, int lane) {
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = 8 * mi + g, cidx = 8 * ni + 2 * tg + e;
+                acc[mi][ni][e] = (r < rows_valid && cidx < cols_valid) ? __ldcg(P + (int64_t)r * ld + cidx) : 0.0;
+            }
+}
+__device__ __forceinline__ void frag_store_g(const double (&acc)[2][2][2], double *P, int64_t ld, int rows_valid, int cols_valid, int lane) {
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = 8 * mi + g, cidx = 8 * ni + 2 * tg + e;
+                if (r < rows_valid && cidx < cols_valid) __stcg(P + (int64_t)r * ld + cidx, acc[mi][ni][e]);
+            }
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_ll_sweep(int first, int nfl, int s, int H, int T, int backward, const FrontDev *__restrict__ fronts, const double *__restrict__ L,
+           const double *__restrict__ U, const double *__restrict__ inv, double *W, double *__restrict__ Y, uint32_t *flags,
+           uint32_t epoch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = warp >> 1, chh = warp & 1;             // 16-row group of the tile, 16-column half of the chunk
+    const int per_t = nfl * H;
+    for (int u = blockIdx.x; u < T * per_t; u += gridDim.x) {
+        const int tt = u / per_t, rem = u - tt * per_t, f = rem / H, h = rem - f * H;
+        const FrontDev F = fronts[first + f];
+        const int n = F.ns + F.nb, ntp = (F.ns + NB - 1) / NB, ntb = (F.nb + NB - 1) / NB;
+        int t;
+        if (!backward) { t = tt; if (t >= ntp + ntb) continue; }
+        else { t = ntp - 1 - tt; if (t < 0) continue; }
+        const bool piv = t < ntp;
+        const int r0 = piv ? NB * t : F.ns + NB * (t - ntp);
+        const int rows = min(NB, (piv ? F.ns : n) - r0);
+        const int c0 = 32 * h + 16 * chh, cv = s - c0;     // this warp's columns
+        double *w = W + F.w_off;
+        uint32_t *fl = flags + (F.inv_off / (2 * NB * NB)) * LL_MAX_CHUNKS + h;   // one flag per (pivot block, column chunk)
+        double acc[2][2][2];
+        const int wr = r0 + 16 * rg, rv = rows - 16 * rg;  // this warp's rows
+        frag_load_g(acc, w + (int64_t)wr * s + c0, s, rv, cv, lane);
+        const double *Lrow = L + F.l_off + (int64_t)wr * F.ns;
+        if (!backward) {
+            const int kend = piv ? t : ntp;
+            for (int k = 0; k < kend; ++k) {
+                flag_wait(fl + LL_MAX_CHUNKS * k, epoch, lane);
+                slab_mma_g(acc, Lrow + NB * k, F.ns, rv, min(NB, F.ns - NB * k), w + (int64_t)(NB * k) * s + c0, s, cv, lane, true);
+            }
+        } else {
+            if (F.nb) slab_mma_g(acc, U + F.u_off + (int64_t)wr * F.nb, F.nb, rv, F.nb, w + (int64_t)F.ns * s + c0, s, cv, lane, true);
+            for (int k = ntp - 1; k > t; --k) {
+                flag_wait(fl + LL_MAX_CHUNKS * k, epoch, lane);
+                slab_mma_g(acc, Lrow + NB * k, F.ns, rv, min(NB, F.ns - NB * k), w + (int64_t)(NB * k) * s + c0, s, cv, lane, true);
+            }
+        }
+        frag_store_g(acc, w + (int64_t)wr * s + c0, s, rv, cv, lane);
+        if (piv) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(fl + LL_MAX_CHUNKS * t), "r"(epoch) : "memory");
+            // solved rows: y_t = Linv_tt w_t (forward) / x_t = Uinv_tt w_t (backward); only this CTA's columns are needed
+            const double *Dinv = inv + F.inv_off + (int64_t)t * (2 * NB * NB) + (backward ? NB * NB : 0);
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            slab_mma_g(acc, Dinv + (int64_t)(16 * rg) * NB, NB, NB - 16 * rg, rows, w + (int64_t)r0 * s + c0, s, cv, lane, false);
+            frag_store_g(acc, Y + F.w_off + (int64_t)wr * s + c0, s, rv, cv, lane);
+        }
+    }
+}
+
+// Largest column chunk in {32, 16} whose block leaves room for two CTAs per SM (measured: with one CTA per SM, or
+// 8-column chunks, the per-step GEMM launches of the general path are faster); 8 only when there are <= 8
+// right-hand sides.  0 = the level uses the general path.
+static int sweep_chunk(int maxn, int s, size_t *smem) {
+    const int cand[3] = {32, 16, 8};
+    const int scap = std::max(8, ((s + 7) / 8) * 8);
+    for (int cw : cand) {
+        if (cw > scap || (cw == 8 && s > 8)) continue;
+        size_t need = (size_t)(maxn + SW_PAD_ROWS) * (cw + 4) * sizeof(double);
+        if (need <= (size_t)SW_TWO_CTA_SMEM) { *smem = need; return cw; }
+    }
+    return 0;
+}
+
 // backward boundary update  W[0:ns] -= U12[ns x nb] W[ns:n]
 __global__ void __launch_bounds__(256, 2)
 k_solve_boundary(int first, int s, const FrontDev *__restrict__ fronts, const double *__restrict__ U, double *__restrict__ W) {
@@ -873,6 +1331,16 @@ static void analyse(Ctx *c) {
     DevBuf<uint8_t> &d_front_level = c->sym_front_level;
     d_front_level.upload(front_level.data(), nf, st);
     d.L.resize(l_total); d.U.resize(u_total); d.inv.resize(inv_total);
+    d.ll_flags.resize(inv_total / (2 * NB * NB) * LL_MAX_CHUNKS + 1);
+    PN_CUDA(cudaMemsetAsync(d.ll_flags.ptr, 0, sizeof(uint32_t) * (inv_total / (2 * NB * NB) * LL_MAX_CHUNKS + 1), st));
+    d.ll_epoch = 0;
+    if (!d.ll_grid) {
+        int per_sm = 0, dev = 0, sms = 0;
+        PN_CUDA(cudaGetDevice(&dev));
+        PN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ll_sweep, 256, 0));
+        d.ll_grid = std::max(1, per_sm) * sms;
+    }
     d.L.zero(st);
     d.fronts_s = 0;
     if (!d.attrs_set) {
@@ -885,6 +1353,12 @@ static void analyse(Ctx *c) {
         PN_CUDA(cudaFuncSetAttribute(k_front_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_solve_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_backward_sm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_backward_sm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_backward_sm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         d.attrs_set = true;
     }
     d.status.resize(1);
@@ -1114,6 +1588,9 @@ static void solve_inplace(Ctx *c, double *X, int s) {
     double *Y = d.yarena.ptr;
     int gz = (s + BN - 1) / BN;
     static const bool debug_levels = getenv("PN_DEBUG_LEVELS") != nullptr;
+    static const bool no_sm_sweeps = getenv("PN_NO_SMEM_SWEEPS") != nullptr;
+    static const bool no_ll_sweeps = getenv("PN_NO_LL_SWEEPS") != nullptr;
+    const bool use_ll = !no_ll_sweeps && s <= 32 * LL_MAX_CHUNKS;
     cudaEvent_t dbg[64];
     if (debug_levels) for (int i = 0; i < 64; ++i) cudaEventCreate(&dbg[i]);
     // forward sweep
@@ -1123,6 +1600,18 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         if (!nfl) continue;
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
+        size_t sw_smem = 0;
+        const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
+        if (cw) {
+            ProfScope ps_(c, PS_SOLVE_FUSED);
+            dim3 grid(nfl, (s + cw - 1) / cw);
+#define PN_FWD(CW_) k_front_forward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, \
+                                                                    d.L.ptr, d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr)
+            if (cw == 32) PN_FWD(32); else if (cw == 16) PN_FWD(16); else PN_FWD(8);
+#undef PN_FWD
+            c->count_launch();
+            continue;
+        }
         if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
             ProfScope ps_(c, PS_SOLVE_FUSED);
             k_front_forward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, d.L.ptr,
@@ -1142,6 +1631,14 @@ static void solve_inplace(Ctx *c, double *X, int s) {
                 c->count_launch();
             }
         }
+        if (use_ll) {
+            const int H = (s + 31) / 32, T = (maxns + NB - 1) / NB + (d.level_max_nb[l] + NB - 1) / NB;
+            const int units = T * nfl * H;
+            ProfScope ps_(c, PS_SOLVE_UPDATE);
+            k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 0, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
+                                                                  d.ll_flags.ptr, ++d.ll_epoch);
+            c->count_launch();
+        } else
         for (int kb = 0; kb < maxns; kb += NB) {
             int rest = std::max(maxn - kb - 1, 0);
             int tiles = 1 + (rest + BM - 1) / BM;
@@ -1160,6 +1657,17 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         if (!nfl) continue;
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
+        size_t sw_smem = 0;
+        const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
+        if (cw) {
+            ProfScope ps_(c, PS_SOLVE_FUSED);
+            dim3 grid(nfl, (s + cw - 1) / cw);
+#define PN_BWD(CW_) k_front_backward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X)
+            if (cw == 32) PN_BWD(32); else if (cw == 16) PN_BWD(16); else PN_BWD(8);
+#undef PN_BWD
+            c->count_launch();
+            continue;
+        }
         if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
             ProfScope ps_(c, PS_SOLVE_FUSED);
             k_front_backward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X, W, Y);
@@ -1169,6 +1677,14 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 1, fr, d.fidx.ptr, X, W); }
         c->count_launch();
+        if (use_ll) {
+            const int H = (s + 31) / 32, T = (maxns + NB - 1) / NB;
+            const int units = T * nfl * H;
+            ProfScope ps_(c, PS_SOLVE_UPDATE);
+            k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 1, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
+                                                                  d.ll_flags.ptr, ++d.ll_epoch);
+            c->count_launch();
+        } else {
         if (d.level_max_nb[l] > 0) {
             { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_boundary<<<dim3(nfl, (maxns + BM - 1) / BM, gz), 256, GEMM_SMEM, st>>>(first, s, fr, d.U.ptr, W); }
             c->count_launch();
@@ -1178,6 +1694,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             int tiles = 1 + (kb + BM - 1) / BM;
             { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_step<<<dim3(nfl, tiles, gz), 256, GEMM_SMEM, st>>>(first, kb, s, 1, fr, d.L.ptr, d.inv.ptr, W, Y); }
             c->count_launch();
+        }
         }
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
