@@ -277,6 +277,13 @@ def run_ours(args, rank, local_rank, world):
     R_host = torch.empty((args.combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
     in_fields = ['xyz', 'support', 'enf_mask', 'enf_val', 'nspring_k', 'nspring_flag', 'quad_ijmn', 'quad_props', 'nl_dof',
                  'nl_case', 'nl_val', 'qp_elem', 'qp_case', 'qp_val', 'factors']
+    # the step's inputs live in pinned host memory (same values, page-locked copies of the arrays the builder produced)
+    for f in in_fields:
+        a = np.ascontiguousarray(getattr(A, f))
+        if a.size:
+            pinned = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True).numpy()
+            pinned[...] = a
+            setattr(A, f, pinned)
     h2d = int(sum(np.asarray(getattr(A, f)).nbytes for f in in_fields))
     d2h = int(D_host.nbytes + R_host.nbytes)
 

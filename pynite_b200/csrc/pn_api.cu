@@ -92,6 +92,7 @@ void ensure_symbolic(Ctx *c, uint32_t flags) {
     direct_invalidate(c);
     PhaseTimer tm(c, &c->stats.ms_symbolic);
     build_symbolic(c, flags);
+    direct_prefetch(c);
     fast_assembly_build(c);
     c->loads.vectors_ready = c->loads.vectors_ready && c->incidence_ready;
 }
@@ -307,18 +308,20 @@ int pn_set_nodes(pn_ctx *ctx, int64_t n_nodes, const double *xyz, const uint8_t 
     cudaStream_t st = c->stream;
     invalidate(c);
     m.n_nodes = n_nodes;
+    // uploads are issued from the caller's buffers first so that the DMA (full speed when they are pinned) runs while
+    // the host copies the analysis needs later (ordering, element classes) are made
+    m.xyz.upload(xyz, 3 * n_nodes, st);
+    m.support.upload(support_mask, n_nodes, st);
+    m.enf_mask.upload(enforced_mask, n_nodes, st);
+    m.enf_val.upload(enforced_val, 6 * n_nodes, st);
+    m.nspring_k.upload(spring_k, 6 * n_nodes, st);
+    m.nspring_flag.upload(spring_flag, 6 * n_nodes, st);
     m.h_xyz.assign(xyz, xyz + 3 * n_nodes);
     m.h_support.assign(support_mask, support_mask + n_nodes);
     m.h_enf_mask.assign(enforced_mask, enforced_mask + n_nodes);
     m.h_enf_val.assign(enforced_val, enforced_val + 6 * n_nodes);
     m.h_nspring_k.assign(spring_k, spring_k + 6 * n_nodes);
     m.h_nspring_flag.assign(spring_flag, spring_flag + 6 * n_nodes);
-    m.xyz.upload(m.h_xyz.data(), 3 * n_nodes, st);
-    m.support.upload(m.h_support.data(), n_nodes, st);
-    m.enf_mask.upload(m.h_enf_mask.data(), n_nodes, st);
-    m.enf_val.upload(m.h_enf_val.data(), 6 * n_nodes, st);
-    m.nspring_k.upload(m.h_nspring_k.data(), 6 * n_nodes, st);
-    m.nspring_flag.upload(m.h_nspring_flag.data(), 6 * n_nodes, st);
     PN_CUDA(cudaStreamSynchronize(st));
     PN_API_END
 }
@@ -373,10 +376,10 @@ static void set_shells(Ctx *c, bool quad, int64_t n, const int32_t *ijmn, const 
     Model &m = c->model;
     invalidate(c);
     (quad ? m.n_quads : m.n_plates) = n;
-    (quad ? m.h_quad_ijmn : m.h_plate_ijmn).assign(ijmn, ijmn + 4 * n);
-    (quad ? m.h_quad_props : m.h_plate_props).assign(props, props + 5 * n);
     (quad ? m.quad_ijmn : m.plate_ijmn).upload(ijmn, 4 * n, c->stream);
     (quad ? m.quad_props : m.plate_props).upload(props, 5 * n, c->stream);
+    (quad ? m.h_quad_ijmn : m.h_plate_ijmn).assign(ijmn, ijmn + 4 * n);
+    (quad ? m.h_quad_props : m.h_plate_props).assign(props, props + 5 * n);
     // the membrane matrix is unsymmetric when kx_mod != ky_mod (Quad3D.py:517-519)
     bool sym = true;
     for (int64_t e = 0; e < n; ++e) if (props[5 * e + 3] != props[5 * e + 4]) sym = false;
@@ -653,9 +656,15 @@ int pn_solve_linear(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, doubl
     ensure_loads(c);
     solve_linear_all(c, o);
     c->solved = true;
-    if (D_out) download(c->D_all, D_out, c->stream);
-    PN_CUDA(cudaStreamSynchronize(c->stream));
+    // the displacement download runs on the second stream while the reactions are computed
+    if (D_out) {
+        PN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        PN_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        download(c->D_all, D_out, c->stream2);
+    }
     reactions_out(c, false, Rxn_out);
+    PN_CUDA(cudaStreamSynchronize(c->stream2));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
     (void)ld;
     c->stats.kernel_launches = c->launches;
     if (stats) *stats = c->stats;

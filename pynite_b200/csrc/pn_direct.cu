@@ -31,6 +31,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <future>
+#include <memory>
 #include <cstdio>
 #include <cstdlib>
 
@@ -84,6 +86,8 @@ struct DirectSolver {
     DevBuf<int> status;                       // 0 ok, 1 zero / non-finite pivot, 2 entry outside front
     bool shared_factor = false;               // the stored factor belongs to the matrix shared by all columns (Ke)
     DevBuf<double> col_in, col_out;           // per-column solves (P-Delta)
+    std::future<void> host_future;            // host half of the analysis running ahead on a worker thread
+    bool host_prefetched = false;
     DevBuf<uint32_t> ll_flags;                // left-looking sweeps: one flag per (pivot block, column chunk)
     uint32_t ll_epoch = 0;
     int ll_grid = 0;                          // resident CTAs of k_ll_sweep (all units' owners must be co-resident)
@@ -1242,16 +1246,15 @@ k_solve_boundary(int first, int s, const FrontDev *__restrict__ fronts, const do
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
-static void analyse(Ctx *c) {
-    if (!c->direct) c->direct = new DirectSolver();
+// Host half of the analysis (vertex graph, nested dissection, fronts): needs only the model's connectivity and the
+// DOF partition, so direct_prefetch() starts it on a second host thread while the symbolic phase of the assembly
+// (element classes, node recipes: also host work) is still running.
+static void analyse_host(Ctx *c, const std::vector<int32_t> &newidx, bool timing) {
     DirectSolver &d = *c->direct;
-    cudaStream_t st = c->stream;
     const Model &m = c->model;
     HostTick tick("direct analyse");
+    tick.on = tick.on && timing;
     // vertex graph from element connectivity (a superset of the K11 pattern)
-    std::vector<int32_t> newidx(c->n_dof);
-    PN_CUDA(cudaMemcpyAsync(newidx.data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, st));
-    PN_CUDA(cudaStreamSynchronize(st));
     std::vector<ConnView> conn;
     conn.push_back({m.n_springs, 2, m.h_spring_ij.data(), m.h_spring_active.data()});
     conn.push_back({m.n_members, 2, m.h_mem_ij.data(), m.h_mem_active.data()});
@@ -1266,8 +1269,45 @@ static void analyse(Ctx *c) {
     int leaf = 24;
     if (const char *e = getenv("PN_LEAF_SIZE")) leaf = std::max(1, atoi(e));
     direct_symbolic(c->n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym);
-    const DirectSym &S = d.sym;
     tick.lap("nested dissection + fronts");
+}
+
+static void join_host_analysis(DirectSolver &d) {
+    if (d.host_future.valid()) d.host_future.get();      // rethrows what the worker threw
+}
+
+void direct_prefetch(Ctx *c) {
+    static const bool off = getenv("PN_NO_ANALYSIS_PREFETCH") != nullptr;
+    if (off || !c->n1) return;
+    if (!c->direct) c->direct = new DirectSolver();
+    DirectSolver &d = *c->direct;
+    try { join_host_analysis(d); } catch (...) {}
+    auto newidx = std::make_shared<std::vector<int32_t>>(c->n_dof);
+    PN_CUDA(cudaMemcpyAsync(newidx->data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    d.analysed = false;
+    d.host_prefetched = true;
+    d.host_future = std::async(std::launch::async, [c, newidx]() { analyse_host(c, *newidx, false); });
+}
+
+static void analyse(Ctx *c) {
+    if (!c->direct) c->direct = new DirectSolver();
+    DirectSolver &d = *c->direct;
+    cudaStream_t st = c->stream;
+    const Model &m = c->model;
+    (void)m;
+    HostTick tick("direct analyse");
+    if (d.host_prefetched) {
+        join_host_analysis(d);
+        d.host_prefetched = false;
+        tick.lap("join prefetched host analysis");
+    } else {
+        std::vector<int32_t> newidx(c->n_dof);
+        PN_CUDA(cudaMemcpyAsync(newidx.data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, st));
+        PN_CUDA(cudaStreamSynchronize(st));
+        analyse_host(c, newidx, true);
+    }
+    const DirectSym &S = d.sym;
 
     // level-major renumbering of fronts
     int nf = (int)S.fronts.size();
@@ -1733,6 +1773,7 @@ __global__ void k_set_col(int64_t n, int s, int j, const double *__restrict__ v,
 }
 
 void direct_release(Ctx *c) {
+    if (c->direct) { try { join_host_analysis(*c->direct); } catch (...) {} }
     delete c->direct;
     c->direct = nullptr;
 }
@@ -1741,6 +1782,8 @@ void direct_release(Ctx *c) {
 // that re-analysing a model of the same size performs no cudaMalloc / cudaFree.
 void direct_invalidate(Ctx *c) {
     if (!c->direct) return;
+    try { join_host_analysis(*c->direct); } catch (...) {}     // the worker reads the host copy of the model
+    c->direct->host_prefetched = false;
     c->direct->analysed = false;
     c->direct->shared_factor = false;
     c->direct->fronts_s = 0;

@@ -359,6 +359,7 @@ void pcg_strip_direction(Ctx *c, int s, int64_t row0, int64_t row1, int first, c
 void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host);
 void direct_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
 void direct_release(Ctx *c);
+void direct_prefetch(Ctx *c);     // start the host half of the analysis on a worker thread (after the DOF partition is known)
 void direct_invalidate(Ctx *c);
 
 }  // namespace pn
