@@ -93,13 +93,25 @@ void ensure_symbolic(Ctx *c, uint32_t flags) {
     PhaseTimer tm(c, &c->stats.ms_symbolic);
     build_symbolic(c, flags);
     direct_prefetch(c);
-    fast_assembly_build(c);
+    // The element-class / node-recipe maps of the streaming assembly cost ~60 ms of host work at 250 000 quads, the
+    // general path 3 ms of device time: they pay off from the second assembly of a pattern on (P-Delta, T/C
+    // iterations, repeated analyses), so they are built lazily by assemble() unless PN_EAGER_FAST_ASSEMBLY is set.
+    fast_assembly_invalidate(c);
+    c->n_assemblies = 0;
+    c->fast_build_tried = false;
+    static const bool eager = getenv("PN_EAGER_FAST_ASSEMBLY") != nullptr;
+    if (eager) { fast_assembly_build(c); c->fast_build_tried = true; }
     c->loads.vectors_ready = c->loads.vectors_ready && c->incidence_ready;
 }
 
 // refresh: recompute the element values from the device-resident model first (a numeric re-assembly)
 void assemble(Ctx *c, bool refresh) {
     bool done = false;
+    if (++c->n_assemblies >= 2 && !c->fast_build_tried) {
+        PhaseTimer tm(c, &c->stats.ms_symbolic);
+        fast_assembly_build(c);
+        c->fast_build_tried = true;
+    }
     {
         PhaseTimer tm(c, &c->stats.ms_scatter);
         done = fast_assembly_run(c, c->vals.ptr);      // element classes + block gather: no COO value reaches HBM
@@ -224,7 +236,7 @@ namespace pn {
 void prof_flush(Ctx *c) {
     Profiler &p = c->prof;
     if (p.recs.empty()) { p.used = 0; return; }
-    cudaStreamSynchronize(c->stream);
+    cudaDeviceSynchronize();            // scopes may have been recorded on the factorisation's side streams
     for (const Profiler::Rec &r : p.recs) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.pool[r.e0], p.pool[r.e1]);

@@ -236,6 +236,10 @@ void fast_assembly_release(Ctx *c) {
     c->fast = nullptr;
 }
 
+void fast_assembly_invalidate(Ctx *c) {
+    if (c->fast) c->fast->ready = false;
+}
+
 void fast_assembly_build(Ctx *c) {
     if (!c->fast) c->fast = new FastAssembly();
     FastAssembly &f = *c->fast;

@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cmath>
 #include <future>
+#include <omp.h>
 #include <memory>
 #include <cstdio>
 #include <cstdlib>
@@ -86,6 +87,20 @@ struct DirectSolver {
     DevBuf<int> status;                       // 0 ok, 1 zero / non-finite pivot, 2 entry outside front
     bool shared_factor = false;               // the stored factor belongs to the matrix shared by all columns (Ke)
     DevBuf<double> col_in, col_out;           // per-column solves (P-Delta)
+    cudaStream_t fstream[4] = {nullptr, nullptr, nullptr, nullptr};   // factorisation: chains of front groups side by side
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n_fstreams = 0, split_max_fronts = 1 << 30;
+    ~DirectSolver() {
+        for (int q = 0; q < 4; ++q) {
+            if (fstream[q]) cudaStreamDestroy(fstream[q]);
+            if (ev_join[q]) cudaEventDestroy(ev_join[q]);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+    }
+    std::vector<int32_t> g_vstart, g_adj;     // vertex graph of the last analysis (host)
+    std::vector<double> g_coords;
+    std::vector<int64_t> g_adj_ptr;
+    VertexGraphScratch g_scratch;
     std::future<void> host_future;            // host half of the analysis running ahead on a worker thread
     bool host_prefetched = false;
     DevBuf<uint32_t> ll_flags;                // left-looking sweeps: one flag per (pivot block, column chunk)
@@ -1253,17 +1268,18 @@ static void analyse_host(Ctx *c, const std::vector<int32_t> &newidx, bool timing
     DirectSolver &d = *c->direct;
     const Model &m = c->model;
     HostTick tick("direct analyse");
-    tick.on = tick.on && timing;
+    tick.sync = timing;                                   // worker thread: wall clock only
     // vertex graph from element connectivity (a superset of the K11 pattern)
     std::vector<ConnView> conn;
     conn.push_back({m.n_springs, 2, m.h_spring_ij.data(), m.h_spring_active.data()});
     conn.push_back({m.n_members, 2, m.h_mem_ij.data(), m.h_mem_active.data()});
     conn.push_back({m.n_quads, 4, m.h_quad_ijmn.data(), nullptr});
     conn.push_back({m.n_plates, 4, m.h_plate_ijmn.data(), nullptr});
-    std::vector<int32_t> vstart, adj;
-    std::vector<double> coords;
-    std::vector<int64_t> adj_ptr;
-    build_vertex_graph(m.n_nodes, newidx.data(), m.h_xyz.data(), conn, vstart, coords, adj_ptr, adj);
+    // the graph vectors and the builder's scratch live in the solver object: a re-analysis touches no fresh pages
+    std::vector<int32_t> &vstart = d.g_vstart, &adj = d.g_adj;
+    std::vector<double> &coords = d.g_coords;
+    std::vector<int64_t> &adj_ptr = d.g_adj_ptr;
+    build_vertex_graph(m.n_nodes, newidx.data(), m.h_xyz.data(), conn, vstart, coords, adj_ptr, adj, &d.g_scratch);
     tick.lap("vertex graph");
     int32_t nv = (int32_t)vstart.size() - 1;
     int leaf = 24;
@@ -1287,7 +1303,13 @@ void direct_prefetch(Ctx *c) {
     PN_CUDA(cudaStreamSynchronize(c->stream));
     d.analysed = false;
     d.host_prefetched = true;
-    d.host_future = std::async(std::launch::async, [c, newidx]() { analyse_host(c, *newidx, false); });
+    // the class / recipe maps of the assembly are built lazily (pn_api.cu), so the worker normally has the cores to itself
+    int wt = omp_get_max_threads();
+    if (const char *e = getenv("PN_PREFETCH_THREADS")) wt = std::max(1, atoi(e));
+    d.host_future = std::async(std::launch::async, [c, newidx, wt]() {
+        omp_set_num_threads(wt);
+        analyse_host(c, *newidx, false);
+    });
 }
 
 static void analyse(Ctx *c) {
@@ -1400,6 +1422,17 @@ static void analyse(Ctx *c) {
         PN_CUDA(cudaFuncSetAttribute(k_front_backward_sm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_backward_sm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         d.attrs_set = true;
+    }
+    if (!d.n_fstreams) {
+        int ns_ = 4;
+        if (const char *e = getenv("PN_FACTOR_STREAMS")) ns_ = std::min(4, std::max(1, atoi(e)));
+        if (const char *e = getenv("PN_FACTOR_SPLIT_MAX")) d.split_max_fronts = std::max(0, atoi(e));
+        for (int q = 0; q < ns_; ++q) {
+            PN_CUDA(cudaStreamCreateWithFlags(&d.fstream[q], cudaStreamNonBlocking));
+            PN_CUDA(cudaEventCreateWithFlags(&d.ev_join[q], cudaEventDisableTiming));
+        }
+        PN_CUDA(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+        d.n_fstreams = ns_;
     }
     d.status.resize(1);
     d.status.zero(st);
@@ -1530,46 +1563,66 @@ static void factorise(Ctx *c, const double *vals11) {
             }
         }
         int maxns = d.level_max_ns[l], maxn = d.level_max_n[l];
-        for (int g0 = 0; g0 < maxns; g0 += GB) {
-            int gend = std::min(g0 + GB, maxns);
-            for (int kb = g0; kb < gend; kb += NB) {
-                lp.begin(2);
-                { ProfScope ps_(c, PS_LU_DIAG); k_lu_diag<<<nfl, 256, DIAG_SMEM, st>>>(first, kb, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr, sym, dbg_clk); }
-                if (dbg_clk && kb == 0) {
-                    long long h[8];
-                    cudaMemcpyAsync(h, dbg_clk, sizeof(h), cudaMemcpyDeviceToHost, st);
-                    cudaStreamSynchronize(st);
-                    fprintf(stderr, "[pn]   level %2d diag clocks: load %lld  lu %lld  store %lld  inv32 %lld  gemm %lld  out %lld\n", l, h[1] - h[0],
-                            h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
-                }
-                lp.end();
-                c->count_launch();
-                int rest = maxn - kb - 1;          // upper bound of the trailing size over the level's fronts
-                if (rest > 0) {
-                    int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
-                    lp.begin(3);
-                    { ProfScope ps_(c, PS_LU_PANELS); k_lu_panels<<<dim3(nfl, tiles_u + tiles_l), 256, GEMM_SMEM, st>>>(first, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym);
-                      lp.end(); lp.begin(4);
-                      if (sym) k_lu_transpose_panel<<<dim3(nfl, (rest + 31) / 32), dim3(32, 8), 0, st>>>(first, kb, d.fronts.ptr, arena); }
+        // The block-step chain (diag -> panels -> strip per 64 pivots) of a level with few fronts keeps only a handful of
+        // CTAs busy, while the rank-256 updates are throughput work: such levels are cut into up to four groups of
+        // fronts whose chains run on separate streams, so that one group's chain overlaps the others' updates.
+        auto run_steps = [&](int f0_, int nf_, cudaStream_t sq) {
+            for (int g0 = 0; g0 < maxns; g0 += GB) {
+                int gend = std::min(g0 + GB, maxns);
+                for (int kb = g0; kb < gend; kb += NB) {
+                    lp.begin(2);
+                    { ProfScope ps_(c, PS_LU_DIAG, sq); k_lu_diag<<<nf_, 256, DIAG_SMEM, sq>>>(f0_, kb, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr, sym, dbg_clk); }
+                    if (dbg_clk && kb == 0) {
+                        long long h[8];
+                        cudaMemcpyAsync(h, dbg_clk, sizeof(h), cudaMemcpyDeviceToHost, sq);
+                        cudaStreamSynchronize(sq);
+                        fprintf(stderr, "[pn]   level %2d diag clocks: load %lld  lu %lld  store %lld  inv32 %lld  gemm %lld  out %lld\n", l, h[1] - h[0],
+                                h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+                    }
                     lp.end();
-                    c->count_launch(1 + sym);
-                    if (kb + NB < gend) {
-                        int wa = gend - kb - NB;       // strips inside the group
-                        int tiles = ((rest + BM - 1) / BM) * ((wa + BN - 1) / BN) + ((wa + BM - 1) / BM) * tiles_u;
-                        lp.begin(5);
-                        { ProfScope ps_(c, PS_LU_PANELS); k_lu_strip<<<dim3(nfl, tiles), 256, GEMM_SMEM, st>>>(first, kb, g0, d.fronts.ptr, arena, sym); }
+                    c->count_launch();
+                    int rest = maxn - kb - 1;          // upper bound of the trailing size over the level's fronts
+                    if (rest > 0) {
+                        int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
+                        lp.begin(3);
+                        { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_panels<<<dim3(nf_, tiles_u + tiles_l), 256, GEMM_SMEM, sq>>>(f0_, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym);
+                          lp.end(); lp.begin(4);
+                          if (sym) k_lu_transpose_panel<<<dim3(nf_, (rest + 31) / 32), dim3(32, 8), 0, sq>>>(f0_, kb, d.fronts.ptr, arena); }
                         lp.end();
-                        c->count_launch();
+                        c->count_launch(1 + sym);
+                        if (kb + NB < gend) {
+                            int wa = gend - kb - NB;       // strips inside the group
+                            int tiles = ((rest + BM - 1) / BM) * ((wa + BN - 1) / BN) + ((wa + BM - 1) / BM) * tiles_u;
+                            lp.begin(5);
+                            { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_strip<<<dim3(nf_, tiles), 256, GEMM_SMEM, sq>>>(f0_, kb, g0, d.fronts.ptr, arena, sym); }
+                            lp.end();
+                            c->count_launch();
+                        }
                     }
                 }
+                int rest = maxn - g0 - 1;
+                if (rest > 0) {
+                    int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
+                    lp.begin(6);
+                    { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<dim3(nf_, tiles_l, tiles_u), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym); }
+                    lp.end();
+                    c->count_launch();
+                }
             }
-            int rest = maxn - g0 - 1;
-            if (rest > 0) {
-                int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
-                lp.begin(6);
-                { ProfScope ps_(c, PS_LU_UPDATE); k_lu_update<<<dim3(nfl, tiles_l, tiles_u), 256, GEMM_SMEM, st>>>(first, g0, d.fronts.ptr, arena, sym); }
-                lp.end();
-                c->count_launch();
+        };
+        int nsplit = 1;
+        // (per-kernel profiling serialises the groups: overlapping kernels would be charged each other's time)
+        if (!lp.on && !c->prof.on && nfl >= 2 && nfl <= d.split_max_fronts) nsplit = std::min(nfl, d.n_fstreams);
+        if (nsplit == 1) {
+            run_steps(first, nfl, st);
+        } else {
+            PN_CUDA(cudaEventRecord(d.ev_fork, st));
+            for (int q = 0; q < nsplit; ++q) {
+                int a = first + (int)((int64_t)nfl * q / nsplit), b = first + (int)((int64_t)nfl * (q + 1) / nsplit);
+                PN_CUDA(cudaStreamWaitEvent(d.fstream[q], d.ev_fork, 0));
+                run_steps(a, b - a, d.fstream[q]);
+                PN_CUDA(cudaEventRecord(d.ev_join[q], d.fstream[q]));
+                PN_CUDA(cudaStreamWaitEvent(st, d.ev_join[q], 0));
             }
         }
         {

@@ -4,6 +4,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <numeric>
 #include <stdexcept>
 
@@ -11,9 +14,12 @@ namespace pn {
 
 void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xyz, const std::vector<ConnView> &conn,
                         std::vector<int32_t> &vstart, std::vector<double> &coords, std::vector<int64_t> &adj_ptr,
-                        std::vector<int32_t> &adj) {
+                        std::vector<int32_t> &adj, VertexGraphScratch *scratch) {
+    VertexGraphScratch local;
+    VertexGraphScratch &sc = scratch ? *scratch : local;
     // vertices = nodes with at least one free DOF, in node order, so K11 rows stay contiguous per vertex
-    std::vector<int32_t> vid(n_nodes, -1);
+    std::vector<int32_t> &vid = sc.vid;
+    vid.assign(n_nodes, -1);
     vstart.clear();
     coords.clear();
     int32_t nv = 0;
@@ -35,25 +41,35 @@ void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xy
         for (int64_t d = 0; d < 6 * n_nodes; ++d) if (newidx[d] >= 0) ++n1;
         vstart.push_back((int32_t)n1);
     }
-    // count, fill (with duplicates), then sort + unique per vertex
-    std::vector<int64_t> deg(nv + 1, 0);
-    for (const ConnView &cv : conn)
+    // count, fill (with duplicates, in any order: atomics), then sort + unique per vertex
+    std::vector<int64_t> &deg = sc.deg, &ptr = sc.ptr, &fill = sc.fill, &cnt = sc.cnt;
+    std::vector<int32_t> &raw = sc.raw;
+    deg.assign(nv + 1, 0);
+    for (const ConnView &cv : conn) {
+#pragma omp parallel for schedule(static)
         for (int64_t e = 0; e < cv.count; ++e) {
             if (cv.active && !cv.active[e]) continue;
             for (int a = 0; a < cv.nn; ++a) {
                 int32_t va = vid[cv.nodes[cv.nn * e + a]];
                 if (va < 0) continue;
+                int64_t add = 0;
                 for (int b = 0; b < cv.nn; ++b) {
                     int32_t vb = vid[cv.nodes[cv.nn * e + b]];
-                    if (vb >= 0 && vb != va) ++deg[va];
+                    if (vb >= 0 && vb != va) ++add;
+                }
+                if (add) {
+#pragma omp atomic
+                    deg[va] += add;
                 }
             }
         }
-    std::vector<int64_t> ptr(nv + 1, 0);
+    }
+    ptr.assign(nv + 1, 0);
     for (int32_t v = 0; v < nv; ++v) ptr[v + 1] = ptr[v] + deg[v];
-    std::vector<int32_t> raw(ptr[nv]);
-    std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
-    for (const ConnView &cv : conn)
+    raw.resize(ptr[nv]);
+    fill.assign(ptr.begin(), ptr.end() - 1);
+    for (const ConnView &cv : conn) {
+#pragma omp parallel for schedule(static)
         for (int64_t e = 0; e < cv.count; ++e) {
             if (cv.active && !cv.active[e]) continue;
             for (int a = 0; a < cv.nn; ++a) {
@@ -61,11 +77,17 @@ void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xy
                 if (va < 0) continue;
                 for (int b = 0; b < cv.nn; ++b) {
                     int32_t vb = vid[cv.nodes[cv.nn * e + b]];
-                    if (vb >= 0 && vb != va) raw[fill[va]++] = vb;
+                    if (vb >= 0 && vb != va) {
+                        int64_t at;
+#pragma omp atomic capture
+                        at = fill[va]++;
+                        raw[at] = vb;
+                    }
                 }
             }
         }
-    std::vector<int64_t> cnt(nv, 0);
+    }
+    cnt.assign(nv, 0);
 #pragma omp parallel for schedule(dynamic, 1024)
     for (int32_t v = 0; v < nv; ++v) {
         auto b = raw.begin() + ptr[v], e = raw.begin() + ptr[v + 1];
@@ -145,18 +167,34 @@ struct Builder {
             }
         }
         int32_t ra = next_region.fetch_add(2), rb = ra + 1;
-        for (size_t i = 0; i < verts.size(); ++i) region[verts[i]] = i < mid ? ra : rb;
+        const bool par = verts.size() > 16384;
+        const int64_t nvs = (int64_t)verts.size();
+        // the large subproblems near the root are few: their vertex loops are split into tasks as well
+#pragma omp taskloop grainsize(8192) if (par) default(shared)
+        for (int64_t i = 0; i < nvs; ++i) region[verts[i]] = i < (int64_t)mid ? ra : rb;
         std::vector<int32_t> A, B, S;
         // separator = vertices of B touching A (B holds the median plane, which is the natural cut)
-        for (size_t i = 0; i < verts.size(); ++i) {
+        std::vector<uint8_t> touch(par ? nvs : 0);
+        if (par) {
+#pragma omp taskloop grainsize(4096) default(shared)
+            for (int64_t i = (int64_t)mid; i < nvs; ++i) {
+                int32_t v = verts[i];
+                uint8_t t = 0;
+                for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k)
+                    if (region[adj[k]] == ra) { t = 1; break; }
+                touch[i] = t;
+            }
+        }
+        A.assign(verts.begin(), verts.begin() + mid);
+        for (size_t i = mid; i < verts.size(); ++i) {
             int32_t v = verts[i];
-            if (i < mid) { A.push_back(v); continue; }
             bool touches = false;
-            for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k)
-                if (region[adj[k]] == ra) { touches = true; break; }
+            if (par) touches = touch[i] != 0;
+            else
+                for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k)
+                    if (region[adj[k]] == ra) { touches = true; break; }
             (touches ? S : B).push_back(v);
         }
-        const bool par = verts.size() > 16384;
         std::vector<int32_t>().swap(verts);
         SubTree ta, tb;
         if (par) {
@@ -186,41 +224,63 @@ struct Builder {
 
 void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double *coords, const int64_t *adj_ptr,
                      const int32_t *adj, int leaf_size, DirectSym &out) {
-    out = DirectSym();
     out.n = n;
-    if (n == 0 || nv == 0) { out.level_ptr.assign(1, 0); return; }
+    out.max_children = 0; out.factor_entries = 0; out.factor_flops = 0; out.max_front = 0;
+    if (n == 0 || nv == 0) {
+        out.perm_pos.clear(); out.dof_front.clear(); out.fronts.clear(); out.fidx.clear(); out.fpos.clear(); out.rel.clear();
+        out.level_fronts.clear();
+        out.level_ptr.assign(1, 0);
+        return;
+    }
     Builder b;
     b.nv = nv; b.vstart = vstart; b.coords = coords; b.adj_ptr = adj_ptr; b.adj = adj; b.leaf_size = leaf_size;
+    b.region.swap(out.s_region);
     b.region.assign(nv, 0);
     std::vector<int32_t> all(nv);
     std::iota(all.begin(), all.end(), 0);
     SubTree tree;
+    const bool timing = getenv("PN_DEBUG_TIMING") != nullptr;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    double t0 = now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        double t = now();
+        fprintf(stderr, "[pn-time] direct_symbolic    %-28s %8.2f ms\n", what, t - t0);
+        t0 = t;
+    };
 #pragma omp parallel
 #pragma omp single
     tree = b.dissect(all);
+    lap("dissect");
     std::vector<std::vector<int32_t>> &front_verts = tree.verts;
     std::vector<int32_t> &parent_of = tree.parent;
     const int32_t nf = (int32_t)front_verts.size();
 
     // vertex elimination positions (post-order front ids = elimination order) and DOF positions
-    std::vector<int32_t> vfront(nv), vorder(nv);      // vorder: rank of the vertex in elimination order
-    std::vector<int32_t> vert_seq;                     // vertices in elimination order
+    b.region.swap(out.s_region);                       // keep the capacity for the next call
+    std::vector<int32_t> &vfront = out.s_vfront, &vorder = out.s_vorder;      // vorder: rank of the vertex in elimination order
+    vfront.resize(nv); vorder.resize(nv);
+    std::vector<int32_t> &vert_seq = out.s_vert_seq;   // vertices in elimination order
+    vert_seq.clear();
     vert_seq.reserve(nv);
-    std::vector<int32_t> f_vbeg(nf + 1, 0);
+    std::vector<int32_t> &f_vbeg = out.s_f_vbeg;
+    f_vbeg.assign(nf + 1, 0);
     for (int32_t f = 0; f < nf; ++f) {
         f_vbeg[f] = (int32_t)vert_seq.size();
         for (int32_t v : front_verts[f]) { vfront[v] = f; vorder[v] = (int32_t)vert_seq.size(); vert_seq.push_back(v); }
     }
     f_vbeg[nf] = (int32_t)vert_seq.size();
     if ((int32_t)vert_seq.size() != nv) throw std::runtime_error("direct_symbolic: vertices lost in dissection");
-    std::vector<int32_t> vdofpos(nv + 1, 0);           // DOF elimination position of vertex with order r
+    std::vector<int32_t> &vdofpos = out.s_vdofpos;     // DOF elimination position of vertex with order r
+    vdofpos.assign(nv + 1, 0);
     for (int32_t r = 0; r < nv; ++r) {
         int32_t v = vert_seq[r];
         vdofpos[r + 1] = vdofpos[r] + (vstart[v + 1] - vstart[v]);
     }
-    out.perm_pos.assign(n, -1);
-    out.dof_front.assign(n, -1);
-    for (int32_t r = 0; r < nv; ++r) {
+    out.perm_pos.resize(n);
+    out.dof_front.resize(n);
+#pragma omp parallel for schedule(static)
+    for (int32_t r = 0; r < nv; ++r) {            // every K11 row belongs to exactly one vertex
         int32_t v = vert_seq[r];
         for (int32_t k = 0; k < vstart[v + 1] - vstart[v]; ++k) {
             out.perm_pos[vstart[v] + k] = vdofpos[r] + k;
@@ -228,44 +288,59 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         }
     }
 
-    // boundary vertex sets, bottom-up (as vertex orders, ascending)
+    lap("orders");
+    // boundary vertex sets, bottom-up (as vertex orders, ascending); fronts of one depth are independent
     std::vector<std::vector<int32_t>> bnd(nf);
     std::vector<std::vector<int32_t>> children(nf);
     for (int32_t f = 0; f < nf; ++f) if (parent_of[f] >= 0) children[parent_of[f]].push_back(f);
-    for (int32_t f = 0; f < nf; ++f) {
-        int32_t vend = f_vbeg[f + 1];
-        std::vector<int32_t> cur;
-        for (int32_t v : front_verts[f])
-            for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k) {
-                int32_t o = vorder[adj[k]];
-                if (o >= vend) cur.push_back(o);
-            }
-        std::sort(cur.begin(), cur.end());
-        cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
-        for (int32_t c : children[f]) {
-            std::vector<int32_t> merged;
-            merged.reserve(cur.size() + bnd[c].size());
-            auto first = std::lower_bound(bnd[c].begin(), bnd[c].end(), vend);
-            std::set_union(cur.begin(), cur.end(), first, bnd[c].end(), std::back_inserter(merged));
-            cur.swap(merged);
-        }
-        bnd[f].swap(cur);
-        // every boundary vertex must live in an ancestor; a root must have an empty boundary
-        if (parent_of[f] < 0 && !bnd[f].empty())
-            throw std::runtime_error("direct_symbolic: root front with a non-empty boundary");
-    }
-
-    // fronts, index lists
-    out.fronts.resize(nf);
     std::vector<int32_t> depth(nf, 0);
-    for (int32_t f = nf - 1; f >= 0; --f) depth[f] = parent_of[f] < 0 ? 0 : depth[parent_of[f]] + 1;
     int32_t maxdepth = 0;
+    for (int32_t f = nf - 1; f >= 0; --f) {
+        depth[f] = parent_of[f] < 0 ? 0 : depth[parent_of[f]] + 1;
+        maxdepth = std::max(maxdepth, depth[f]);
+    }
+    std::vector<std::vector<int32_t>> by_depth(maxdepth + 1);
+    for (int32_t f = 0; f < nf; ++f) by_depth[depth[f]].push_back(f);
+    int bad_root = 0;
+    for (int32_t dd = maxdepth; dd >= 0; --dd) {
+        const std::vector<int32_t> &grp = by_depth[dd];
+#pragma omp parallel for schedule(dynamic, 16) if (grp.size() > 32)
+        for (int64_t q = 0; q < (int64_t)grp.size(); ++q) {
+            const int32_t f = grp[q];
+            int32_t vend = f_vbeg[f + 1];
+            std::vector<int32_t> cur;
+            for (int32_t v : front_verts[f])
+                for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k) {
+                    int32_t o = vorder[adj[k]];
+                    if (o >= vend) cur.push_back(o);
+                }
+            std::sort(cur.begin(), cur.end());
+            cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
+            for (int32_t c : children[f]) {
+                std::vector<int32_t> merged;
+                merged.reserve(cur.size() + bnd[c].size());
+                auto first = std::lower_bound(bnd[c].begin(), bnd[c].end(), vend);
+                std::set_union(cur.begin(), cur.end(), first, bnd[c].end(), std::back_inserter(merged));
+                cur.swap(merged);
+            }
+            bnd[f].swap(cur);
+            // every boundary vertex must live in an ancestor; a root must have an empty boundary
+            if (parent_of[f] < 0 && !bnd[f].empty()) {
+#pragma omp atomic write
+                bad_root = 1;
+            }
+        }
+    }
+    if (bad_root) throw std::runtime_error("direct_symbolic: root front with a non-empty boundary");
+
+    lap("boundary sets");
+    // fronts, index lists
+    out.fronts.assign(nf, FrontSym());
     int64_t total_idx = 0, total_rel = 0;
     for (int32_t f = 0; f < nf; ++f) {
         FrontSym &F = out.fronts[f];
         F.parent = parent_of[f];
         F.depth = depth[f];
-        maxdepth = std::max(maxdepth, depth[f]);
         F.pos_start = vdofpos[f_vbeg[f]];
         F.ns = vdofpos[f_vbeg[f + 1]] - vdofpos[f_vbeg[f]];
         int32_t nbd = 0;
@@ -285,12 +360,15 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         for (int32_t c : children[f]) out.fronts[c].child_rank = rank++;
         out.max_children = std::max(out.max_children, rank);
     }
+    lap("front sizes");
     // inverse of perm_pos for index lists in K11 numbering
-    std::vector<int32_t> pos_dof(n);
+    std::vector<int32_t> &pos_dof = out.s_pos_dof;
+    pos_dof.resize(n);
     for (int64_t d = 0; d < n; ++d) pos_dof[out.perm_pos[d]] = (int32_t)d;
     out.fpos.resize(total_idx);
     out.fidx.resize(total_idx);
     out.rel.resize(total_rel);
+    lap("alloc lists");
 #pragma omp parallel for schedule(dynamic, 64)
     for (int32_t f = 0; f < nf; ++f) {
         const FrontSym &F = out.fronts[f];
@@ -300,6 +378,7 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
             for (int32_t p = vdofpos[vo]; p < vdofpos[vo + 1]; ++p) out.fpos[o++] = p;
         for (int64_t k = F.idx_off; k < F.idx_off + F.ns + F.nb; ++k) out.fidx[k] = pos_dof[out.fpos[k]];
     }
+    lap("index lists");
     int bad_rel = 0;
 #pragma omp parallel for schedule(dynamic, 64)
     for (int32_t f = 0; f < nf; ++f) {
@@ -321,6 +400,7 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         }
     }
     if (bad_rel) throw std::runtime_error("direct_symbolic: child boundary not contained in parent front");
+    lap("rel maps");
     // levels: level = maxdepth - depth, so children sit exactly one level below their parent
     int32_t nl = maxdepth + 1;
     out.level_ptr.assign(nl + 1, 0);

@@ -32,6 +32,15 @@ struct DirectSym {
     int64_t factor_entries = 0;       // stored entries of L and U
     double factor_flops = 0;
     int64_t max_front = 0;            // largest ns + nb
+    // scratch of direct_symbolic, kept between calls: re-analysing a model of the same size then touches no fresh
+    // pages (the page faults of ~100 MB of new vectors were a third of the ordering time)
+    std::vector<int32_t> s_pos_dof, s_vfront, s_vorder, s_vert_seq, s_f_vbeg, s_vdofpos, s_region, s_all;
+};
+
+// scratch of build_vertex_graph, kept by the caller between calls for the same reason
+struct VertexGraphScratch {
+    std::vector<int32_t> vid, raw;
+    std::vector<int64_t> deg, ptr, fill, cnt;
 };
 
 // Vertex graph: vertex v owns K11 rows vstart[v] .. vstart[v+1]; coords[3 v ..]; adjacency in CSR
@@ -50,6 +59,6 @@ struct ConnView {
 };
 void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xyz, const std::vector<ConnView> &conn,
                         std::vector<int32_t> &vstart, std::vector<double> &coords, std::vector<int64_t> &adj_ptr,
-                        std::vector<int32_t> &adj);
+                        std::vector<int32_t> &adj, VertexGraphScratch *scratch = nullptr);
 
 }  // namespace pn

@@ -227,6 +227,8 @@ struct Ctx {
     DirectSolver *direct = nullptr;
     PcgWork *pcg = nullptr;
     FastAssembly *fast = nullptr;
+    int64_t n_assemblies = 0;       // numeric assemblies on the current pattern
+    bool fast_build_tried = false;  // the class / recipe maps are built lazily, at the second assembly
 
     DevBuf<uint8_t> cub_tmp;       // scratch for cub device-wide primitives
     // scratch of the symbolic phase, kept (grow-only) so that re-analysing a model of the same size allocates nothing
@@ -249,6 +251,7 @@ struct ProfScope {
     int slot;
     size_t e0 = 0;
     bool live;
+    cudaStream_t stream;
     static size_t grab(Ctx *c) {
         Profiler &p = c->prof;
         if (p.used == p.pool.size()) {
@@ -258,16 +261,17 @@ struct ProfScope {
         }
         return p.used++;
     }
-    ProfScope(Ctx *ctx, int s) : c(ctx), slot(s), live(ctx->prof.on) {
+    // `on`: the stream the timed launches go to (default: the context stream)
+    ProfScope(Ctx *ctx, int s, cudaStream_t on = nullptr) : c(ctx), slot(s), live(ctx->prof.on), stream(on ? on : ctx->stream) {
         if (!live) return;
         if (c->prof.used > 60000) prof_flush(c);
         e0 = grab(c);
-        cudaEventRecord(c->prof.pool[e0], c->stream);
+        cudaEventRecord(c->prof.pool[e0], stream);
     }
     ~ProfScope() {
         if (!live) return;
         size_t e1 = grab(c);
-        cudaEventRecord(c->prof.pool[e1], c->stream);
+        cudaEventRecord(c->prof.pool[e1], stream);
         c->prof.recs.push_back({slot, e0, e1});
     }
 };
@@ -276,6 +280,7 @@ struct ProfScope {
 struct HostTick {
     const char *tag;
     bool on;
+    bool sync = true;         // false on worker threads: wall clock only, no device synchronisation
     double t0;
     static double now() {
         timespec ts;
@@ -285,7 +290,7 @@ struct HostTick {
     explicit HostTick(const char *t) : tag(t), on(getenv("PN_DEBUG_TIMING") != nullptr), t0(now()) {}
     void lap(const char *what) {
         if (!on) return;
-        cudaDeviceSynchronize();
+        if (sync) cudaDeviceSynchronize();
         double t = now();
         fprintf(stderr, "[pn-time] %-18s %-28s %8.2f ms\n", tag, what, t - t0);
         t0 = t;
@@ -342,6 +347,7 @@ void spmv_plain(Ctx *c, const CsrBlock &A, const double *vals, const double *x, 
 void fast_assembly_build(Ctx *c);             // symbolic: element classes + block-gather maps (after build_symbolic)
 bool fast_assembly_run(Ctx *c, double *vals); // numeric: false when unavailable / a class check failed (caller falls back)
 void fast_assembly_release(Ctx *c);
+void fast_assembly_invalidate(Ctx *c);
 
 // ---- pn_pcg.cu / pn_direct.cu ---------------------------------------------------------------------
 // Solve K11 X = B for all s columns; `vals11` may differ per column when per_column_vals != 0
