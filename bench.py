@@ -292,7 +292,13 @@ def run_ours(args, rank, local_rank, world):
             pinned[...] = a
             setattr(A, f, pinned)
     h2d = int(sum(np.asarray(getattr(A, f)).nbytes for f in in_fields))
-    d2h = int(D_host.nbytes + R_host.nbytes)
+    # reactions cross PCIe as the rows of the DOFs that can carry one (supported, or with an active support spring) when
+    # those are few (pn_api.cu reactions_out); the host array is zero-filled and the rows scattered into it
+    sup_bits = np.unpackbits(np.asarray(A.support, dtype=np.uint8).reshape(-1, 1), axis=1, bitorder='little')[:, :6].reshape(-1)
+    nsf = np.asarray(A.nspring_flag, dtype=np.uint8).reshape(-1)
+    n_rxn = int(np.count_nonzero((sup_bits != 0) | (((nsf & 1) != 0) & ((nsf & 2) != 0))))
+    rxn_bytes = n_rxn*args.combos*8 if n_rxn*8 < n_dof else R_host.nbytes
+    d2h = int(D_host.nbytes + rxn_bytes)
 
     e2e_phases = {}
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <future>
 #include <numeric>
 
 #include "pn_internal.h"
@@ -36,6 +37,7 @@ inline Ctx *C(pn_ctx *p) { return reinterpret_cast<Ctx *>(p); }
 inline unsigned grid_for(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 void invalidate(Ctx *c) {
+    c->rxn_list_ready = false;
     c->ev_ready = false;
     c->symbolic_ready = false;
     c->vals_ready = false;
@@ -203,16 +205,68 @@ int batch_size(Ctx *c, int n_combo) {
     return std::max(s, 1);
 }
 
+// rows `dofs` of every combo's reaction vector: out[j][i] = R[j][dofs[i]]
+__global__ void k_gather_reaction_rows(int64_t nr, int nc, int64_t n_dof, const int32_t *__restrict__ dofs,
+                                       const double *__restrict__ R, double *__restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nr * nc) return;
+    int64_t j = t / nr, i = t - j * nr;
+    out[t] = R[j * n_dof + dofs[i]];
+}
+
+// Reactions are exactly zero except at supported DOFs and at DOFs with an active node support spring (k_reactions).
+// When those are few (a plate pinned on its perimeter: 6 000 of 1.5 M DOFs) only their rows cross PCIe; the host array
+// is zero-filled by a worker thread (OpenMP) while the device computes, then the rows are scattered into it.
 void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
     if (!Rxn_out) return;
     PhaseTimer tm(c, &c->stats.ms_reactions);
     build_incidence(c);
     DevBuf<double> &rx = c->work_rx;
-    int nc = c->loads.n_combo;
-    rx.resize((int64_t)nc * c->n_dof);
-    for (int j = 0; j < nc; ++j) compute_reactions(c, j, pdelta, rx.ptr + (int64_t)j * c->n_dof);
-    download(rx, Rxn_out, c->stream);
+    const int nc = c->loads.n_combo;
+    const int64_t n_dof = c->n_dof;
+    const Model &m = c->model;
+    if (!c->rxn_list_ready) {
+        c->h_rxn_dofs.clear();
+        for (int64_t d = 0; d < n_dof; ++d) {
+            const uint8_t f = m.h_nspring_flag[d];
+            if (((m.h_support[d / 6] >> (d % 6)) & 1u) || ((f & 1u) && (f & 2u))) c->h_rxn_dofs.push_back((int32_t)d);
+        }
+        c->rxn_dofs.upload(c->h_rxn_dofs.data(), (int64_t)c->h_rxn_dofs.size(), c->stream);
+        c->rxn_list_ready = true;
+    }
+    const int64_t nr = (int64_t)c->h_rxn_dofs.size();
+    static const bool full = getenv("PN_FULL_REACTION_DOWNLOAD") != nullptr;
+    const bool compact = !full && nr * 8 < n_dof;
+    std::future<void> zero;
+    if (compact)
+        zero = std::async(std::launch::async, [Rxn_out, nc, n_dof]() {
+            const int64_t total = (int64_t)nc * n_dof, chunk = 1 << 20;
+#pragma omp parallel for schedule(static)
+            for (int64_t b = 0; b < (total + chunk - 1) / chunk; ++b)
+                memset(Rxn_out + b * chunk, 0, sizeof(double) * (size_t)std::min(chunk, total - b * chunk));
+        });
+    rx.resize((int64_t)nc * n_dof);
+    for (int j = 0; j < nc; ++j) compute_reactions(c, j, pdelta, rx.ptr + (int64_t)j * n_dof);
+    if (!compact) {
+        download(rx, Rxn_out, c->stream);
+        PN_CUDA(cudaStreamSynchronize(c->stream));
+        return;
+    }
+    c->rxn_rows.resize(nr * nc);
+    c->h_rxn_rows.resize((size_t)(nr * nc));
+    if (nr) {
+        k_gather_reaction_rows<<<grid_for(nr * nc, 256), 256, 0, c->stream>>>(nr, nc, n_dof, c->rxn_dofs.ptr, rx.ptr, c->rxn_rows.ptr);
+        c->count_launch();
+        download(c->rxn_rows, c->h_rxn_rows.data(), c->stream);
+    }
     PN_CUDA(cudaStreamSynchronize(c->stream));
+    zero.get();
+    const int32_t *rd = c->h_rxn_dofs.data();
+    for (int j = 0; j < nc; ++j) {
+        double *dst = Rxn_out + (int64_t)j * n_dof;
+        const double *src = c->h_rxn_rows.data() + (int64_t)j * nr;
+        for (int64_t i = 0; i < nr; ++i) dst[rd[i]] = src[i];
+    }
 }
 
 void solve_linear_all(Ctx *c, const pn_solve_opts &o) {

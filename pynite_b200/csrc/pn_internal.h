@@ -241,6 +241,12 @@ struct Ctx {
     DevBuf<double> sym_press;
     // persistent work arrays: a steady-state step performs no cudaMalloc / cudaFree
     DevBuf<double> work_r, work_ax, work_rx, dots_partial, dots_out;
+    // DOFs whose reaction can be nonzero (supported, or with an active node support spring) and their rows
+    bool rxn_list_ready = false;
+    std::vector<int32_t> h_rxn_dofs;
+    DevBuf<int32_t> rxn_dofs;
+    DevBuf<double> rxn_rows;
+    std::vector<double> h_rxn_rows;
     Profiler prof;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // pn_timer_start / pn_timer_stop
 };
