@@ -117,6 +117,12 @@ PN_EXPORT int pn_member_kg(pn_ctx *ctx, const double *P, double *out);
 
 /* ---- symbolic phase: FEModel3D._build_dof_vector :66, _append_sparse_block :99 (zero filter),
  *      coo_matrix + tocsr pattern (:1791, :2279), Analysis._partition_D :1412, _partition :1508 -- */
+/* Optional hint, callable once every pn_set_nodes / pn_set_springs / pn_set_members / pn_set_quads / pn_set_plates call
+ * of a model has been made: starts the host half of the direct solver's analysis (node graph, nested dissection,
+ * fronts; the reference has no counterpart, SuperLU orders inside spsolve, Analysis.py:217) on a worker thread so
+ * that it overlaps the load upload and the symbolic phase.  pn_symbolic starts it itself if this was not called; a
+ * later pn_set_* call discards it. */
+PN_EXPORT int pn_prefetch_analysis(pn_ctx *ctx);
 PN_EXPORT int pn_symbolic(pn_ctx *ctx, uint32_t flags);
 PN_EXPORT int pn_get_sizes(pn_ctx *ctx, pn_sizes *out);
 PN_EXPORT int pn_get_coo(pn_ctx *ctx, int32_t *row, int32_t *col, double *data); /* emission order           */

@@ -91,7 +91,7 @@ void ensure_ev(Ctx *c) { if (!c->ev_ready) compute_ev(c); }
 void ensure_symbolic(Ctx *c, uint32_t flags) {
     ensure_ev(c);
     if (c->symbolic_ready && c->sym_flags == flags) return;
-    direct_invalidate(c);
+    direct_invalidate_pattern(c);
     PhaseTimer tm(c, &c->stats.ms_symbolic);
     build_symbolic(c, flags);
     direct_prefetch(c);
@@ -496,6 +496,12 @@ int pn_member_kg(pn_ctx *ctx, const double *P, double *out) {
     PN_API_END
 }
 
+int pn_prefetch_analysis(pn_ctx *ctx) {
+    PN_API_BEGIN(ctx)
+    direct_prefetch(c);
+    PN_API_END
+}
+
 int pn_symbolic(pn_ctx *ctx, uint32_t flags) {
     PN_API_BEGIN(ctx)
     ensure_symbolic(c, flags);
@@ -607,10 +613,11 @@ int pn_set_loads(pn_ctx *ctx, int32_t n_case,
         for (int64_t k = 0; k < n; ++k)
             if (idx[k] < 0 || idx[k] >= idx_limit || cs[k] < 0 || cs[k] >= n_case)
                 throw ArgError(std::string(what) + ": index or case out of range");
-        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-            return cs[a] != cs[b] ? cs[a] < cs[b] : idx[a] < idx[b];
-        });
+        auto less = [&](int64_t a, int64_t b) { return cs[a] != cs[b] ? cs[a] < cs[b] : idx[a] < idx[b]; };
+        if (!std::is_sorted(order.begin(), order.end(), less))      // generated input usually arrives grouped by case
+            std::stable_sort(order.begin(), order.end(), less);
         oi.clear(); oc.clear(); ov.clear();
+        oi.reserve(n); oc.reserve(n); ov.reserve(n);
         for (int64_t q = 0; q < n; ++q) {
             int64_t k = order[q];
             if (!oi.empty() && oi.back() == idx[k] && oc.back() == cs[k]) ov.back() += val[k];

@@ -102,7 +102,8 @@ struct DirectSolver {
     std::vector<int64_t> g_adj_ptr;
     VertexGraphScratch g_scratch;
     std::future<void> host_future;            // host half of the analysis running ahead on a worker thread
-    bool host_prefetched = false;
+    int host_state = 0;                       // 0 none, 1 worker running, 2 d.sym valid for the current model
+    int64_t prefetch_n1 = -1;
     DevBuf<uint32_t> ll_flags;                // left-looking sweeps: one flag per (pivot block, column chunk)
     uint32_t ll_epoch = 0;
     int ll_grid = 0;                          // resident CTAs of k_ll_sweep (all units' owners must be co-resident)
@@ -1264,7 +1265,7 @@ k_solve_boundary(int first, int s, const FrontDev *__restrict__ fronts, const do
 // Host half of the analysis (vertex graph, nested dissection, fronts): needs only the model's connectivity and the
 // DOF partition, so direct_prefetch() starts it on a second host thread while the symbolic phase of the assembly
 // (element classes, node recipes: also host work) is still running.
-static void analyse_host(Ctx *c, const std::vector<int32_t> &newidx, bool timing) {
+static void analyse_host(Ctx *c, const std::vector<int32_t> &newidx, bool timing, int64_t n1) {
     DirectSolver &d = *c->direct;
     const Model &m = c->model;
     HostTick tick("direct analyse");
@@ -1284,7 +1285,7 @@ static void analyse_host(Ctx *c, const std::vector<int32_t> &newidx, bool timing
     int32_t nv = (int32_t)vstart.size() - 1;
     int leaf = 24;
     if (const char *e = getenv("PN_LEAF_SIZE")) leaf = std::max(1, atoi(e));
-    direct_symbolic(c->n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym);
+    direct_symbolic(n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym);
     tick.lap("nested dissection + fronts");
 }
 
@@ -1292,23 +1293,34 @@ static void join_host_analysis(DirectSolver &d) {
     if (d.host_future.valid()) d.host_future.get();      // rethrows what the worker threw
 }
 
+// Starts the host half of the analysis on a worker thread.  The DOF partition is recomputed on the host from the
+// model's support / enforced-displacement masks (same rule as k_known_flags + k_partition_lists), so the worker needs
+// nothing from the device and can start as soon as the model arrays are set (pn_prefetch_analysis), well before the
+// symbolic phase.  A model change joins and discards it (direct_invalidate).
 void direct_prefetch(Ctx *c) {
     static const bool off = getenv("PN_NO_ANALYSIS_PREFETCH") != nullptr;
-    if (off || !c->n1) return;
+    const Model &m = c->model;
+    if (off || !m.n_nodes) return;
     if (!c->direct) c->direct = new DirectSolver();
     DirectSolver &d = *c->direct;
+    if (d.host_state != 0) return;                       // running, or done and still valid for this model
     try { join_host_analysis(d); } catch (...) {}
-    auto newidx = std::make_shared<std::vector<int32_t>>(c->n_dof);
-    PN_CUDA(cudaMemcpyAsync(newidx->data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, c->stream));
-    PN_CUDA(cudaStreamSynchronize(c->stream));
     d.analysed = false;
-    d.host_prefetched = true;
-    // the class / recipe maps of the assembly are built lazily (pn_api.cu), so the worker normally has the cores to itself
-    int wt = omp_get_max_threads();
-    if (const char *e = getenv("PN_PREFETCH_THREADS")) wt = std::max(1, atoi(e));
-    d.host_future = std::async(std::launch::async, [c, newidx, wt]() {
+    d.host_state = 1;
+    const int wt = omp_get_max_threads();
+    d.host_future = std::async(std::launch::async, [c, wt]() {
         omp_set_num_threads(wt);
-        analyse_host(c, *newidx, false);
+        const Model &mm = c->model;
+        const int64_t n_dof = 6 * mm.n_nodes;
+        std::vector<int32_t> newidx((size_t)n_dof);
+        int32_t fp = 0, kp = 0;
+        for (int64_t dd = 0; dd < n_dof; ++dd) {
+            const int64_t nd = dd / 6;
+            const bool known = ((mm.h_support[nd] | mm.h_enf_mask[nd]) >> (dd % 6)) & 1u;
+            newidx[dd] = known ? -1 - kp++ : fp++;
+        }
+        c->direct->prefetch_n1 = fp;
+        analyse_host(c, newidx, false, fp);
     });
 }
 
@@ -1319,15 +1331,18 @@ static void analyse(Ctx *c) {
     const Model &m = c->model;
     (void)m;
     HostTick tick("direct analyse");
-    if (d.host_prefetched) {
+    if (d.host_state == 1) {
+        d.host_state = 0;
         join_host_analysis(d);
-        d.host_prefetched = false;
+        if (d.prefetch_n1 == c->n1) d.host_state = 2;    // (always, unless the partition rule and its host copy diverge)
         tick.lap("join prefetched host analysis");
-    } else {
+    }
+    if (d.host_state != 2) {
         std::vector<int32_t> newidx(c->n_dof);
         PN_CUDA(cudaMemcpyAsync(newidx.data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, st));
         PN_CUDA(cudaStreamSynchronize(st));
-        analyse_host(c, newidx, true);
+        analyse_host(c, newidx, true, c->n1);
+        d.host_state = 2;
     }
     const DirectSym &S = d.sym;
 
@@ -1836,7 +1851,15 @@ void direct_release(Ctx *c) {
 void direct_invalidate(Ctx *c) {
     if (!c->direct) return;
     try { join_host_analysis(*c->direct); } catch (...) {}     // the worker reads the host copy of the model
-    c->direct->host_prefetched = false;
+    c->direct->host_state = 0;
+    c->direct->analysed = false;
+    c->direct->shared_factor = false;
+    c->direct->fronts_s = 0;
+}
+
+// The pattern was rebuilt for the same model (other symbolic flags): the device maps must be redone, the ordering stays.
+void direct_invalidate_pattern(Ctx *c) {
+    if (!c->direct) return;
     c->direct->analysed = false;
     c->direct->shared_factor = false;
     c->direct->fronts_s = 0;

@@ -373,5 +373,6 @@ void direct_solve(Ctx *c, const double *vals11, int per_column_vals, int s, cons
 void direct_release(Ctx *c);
 void direct_prefetch(Ctx *c);     // start the host half of the analysis on a worker thread (after the DOF partition is known)
 void direct_invalidate(Ctx *c);
+void direct_invalidate_pattern(Ctx *c);
 
 }  // namespace pn

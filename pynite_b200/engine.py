@@ -114,6 +114,7 @@ SIGNATURES = {
     'pn_element_forces': (ct.c_int, [_P, ct.c_int, ct.c_int32, ct.c_int32, ct.c_int32, _F64P]),
     'pn_set_stream': (ct.c_int, [_P, ct.c_void_p, ct.c_int]),
     'pn_node_row_starts': (ct.c_int, [_P, ct.POINTER(ct.c_int64)]),
+    'pn_prefetch_analysis': (ct.c_int, [_P]),
     'pn_dev_spmm_k11_rows': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
     'pn_dev_block_jacobi_setup': (ct.c_int, [_P]),
     'pn_dev_block_jacobi_nodes': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
@@ -224,6 +225,8 @@ class Engine:
         self.n_dof = 6*A.n_nodes
         self.counts = {PN_SPRING: len(A.spring_ks), PN_MEMBER: len(A.mem_rot),
                        PN_QUAD: len(A.quad_ijmn), PN_PLATE: len(A.plate_ijmn)}
+        # the model is complete: the ordering of the direct solver can start on a host worker thread
+        self._check(L.pn_prefetch_analysis(self._h))
 
     def set_nodes(self, A):
         self._check(self._lib.pn_set_nodes(self._h, A.n_nodes, _ptr(_c(A.xyz, np.float64), _F64P),
