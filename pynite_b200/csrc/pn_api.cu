@@ -496,6 +496,14 @@ int pn_member_kg(pn_ctx *ctx, const double *P, double *out) {
     PN_API_END
 }
 
+int pn_set_option(pn_ctx *ctx, const char *name, int64_t value) {
+    PN_API_BEGIN(ctx)
+    if (!name) throw ArgError("pn_set_option: null name");
+    if (!strcmp(name, "assembly_graph")) c->opt_assembly_graph = value != 0;
+    else throw ArgError(std::string("pn_set_option: unknown option ") + name);
+    PN_API_END
+}
+
 int pn_prefetch_analysis(pn_ctx *ctx) {
     PN_API_BEGIN(ctx)
     direct_prefetch(c);

@@ -60,7 +60,18 @@ struct FastAssembly {
     int32_t *h_indptr = nullptr, *h_indices = nullptr;
     int64_t h_indptr_cap = 0, h_indices_cap = 0;
     AssemblySym sym;
+    // the numeric assembly (verification on the side stream, class table, recipe values, gather) as one CUDA graph:
+    // four dependent launches of 5-50 us each lose ~10 us to launch gaps when issued one by one
+    cudaGraphExec_t graph_exec = nullptr;
+    double *graph_vals = nullptr;
+    cudaStream_t graph_stream = nullptr;
+    int graph_launches = 0;
+    void drop_graph() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+    }
     ~FastAssembly() {
+        drop_graph();
         if (h_indptr) cudaFreeHost(h_indptr);
         if (h_indices) cudaFreeHost(h_indices);
     }
@@ -237,13 +248,14 @@ void fast_assembly_release(Ctx *c) {
 }
 
 void fast_assembly_invalidate(Ctx *c) {
-    if (c->fast) c->fast->ready = false;
+    if (c->fast) { c->fast->ready = false; c->fast->drop_graph(); }
 }
 
 void fast_assembly_build(Ctx *c) {
     if (!c->fast) c->fast = new FastAssembly();
     FastAssembly &f = *c->fast;
     f.ready = false;
+    f.drop_graph();
     const Model &m = c->model;
     cudaStream_t st = c->stream;
     const int64_t counts[4] = {m.n_springs, m.n_members, m.n_quads, m.n_plates};
@@ -368,12 +380,10 @@ void fast_assembly_build(Ctx *c) {
     f.ready = true;
 }
 
-bool fast_assembly_run(Ctx *c, double *vals) {
-    if (!c->fast || !c->fast->ready) return false;
+static void fast_assembly_enqueue(Ctx *c, double *vals) {
     FastAssembly &f = *c->fast;
     const Model &m = c->model;
     cudaStream_t st = c->stream;
-    ProfScope total_(c, PS_ASSEMBLY_TOTAL);
     {
         // class verification runs on the side stream, concurrently with the class table + gather on the main stream
         cudaStream_t s2 = c->stream2;
@@ -416,12 +426,50 @@ bool fast_assembly_run(Ctx *c, double *vals) {
         c->count_launch();
     }
     PN_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
-    total_.~ProfScope();
-    total_.live = false;
+}
+
+bool fast_assembly_run(Ctx *c, double *vals) {
+    if (!c->fast || !c->fast->ready) return false;
+    FastAssembly &f = *c->fast;
+    cudaStream_t st = c->stream;
+    if (c->opt_assembly_graph) {
+        if (!f.graph_exec || f.graph_vals != vals || f.graph_stream != st) {
+            f.drop_graph();
+            const bool prof_was = c->prof.on;
+            const int64_t launches_before = c->launches;
+            c->prof.on = false;                            // events recorded inside a capture cannot be timed
+            cudaGraph_t g = nullptr;
+            PN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try {
+                fast_assembly_enqueue(c, vals);
+            } catch (...) {
+                cudaStreamEndCapture(st, &g);
+                if (g) cudaGraphDestroy(g);
+                c->prof.on = prof_was;
+                throw;
+            }
+            PN_CUDA(cudaStreamEndCapture(st, &g));
+            c->prof.on = prof_was;
+            f.graph_launches = (int)(c->launches - launches_before);
+            c->launches = launches_before;
+            PN_CUDA(cudaGraphInstantiate(&f.graph_exec, g, 0));
+            cudaGraphDestroy(g);
+            f.graph_vals = vals;
+            f.graph_stream = st;
+        }
+        {
+            ProfScope total_(c, PS_ASSEMBLY_TOTAL);
+            PN_CUDA(cudaGraphLaunch(f.graph_exec, st));
+        }
+        c->count_launch(f.graph_launches);
+    } else {
+        ProfScope total_(c, PS_ASSEMBLY_TOTAL);
+        fast_assembly_enqueue(c, vals);
+    }
     int flag = 0;
     PN_CUDA(cudaMemcpyAsync(&flag, f.flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
-    if (flag) { f.ready = false; return false; }      // coordinates / properties changed under a fixed class map
+    if (flag) { f.ready = false; f.drop_graph(); return false; }      // coordinates / properties changed under a fixed class map
     return true;
 }
 

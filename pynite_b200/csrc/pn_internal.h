@@ -227,6 +227,7 @@ struct Ctx {
     DirectSolver *direct = nullptr;
     PcgWork *pcg = nullptr;
     FastAssembly *fast = nullptr;
+    bool opt_assembly_graph = true; // pn_set_option("assembly_graph"): replay the numeric assembly as one CUDA graph
     int64_t n_assemblies = 0;       // numeric assemblies on the current pattern
     bool fast_build_tried = false;  // the class / recipe maps are built lazily, at the second assembly
 
