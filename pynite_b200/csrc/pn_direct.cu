@@ -633,16 +633,16 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
 // trailing update after group [g0, ge): F[ge:, ge:] -= L[ge:, g0:ge] U[g0:ge, ge:]   (rank ge - g0 <= GB)
 __global__ void __launch_bounds__(256, 2)
 k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym) {
-    FrontDev F = fronts[first + blockIdx.x];
+    FrontDev F = fronts[first + blockIdx.z];      // front slowest: the CTAs of one front run together, its panels stay in L2
     if (g0 >= F.ns) return;
     const int ge = min(g0 + GB, F.ns);
     const int n = F.ns + F.nb;
     const int rest = n - ge;
-    if ((int)blockIdx.y * BM >= rest || (int)blockIdx.z * BN >= rest) return;
-    if (sym && ((int)blockIdx.y + 1) * BM <= (int)blockIdx.z * BN) return;      // tile strictly above the diagonal
+    if ((int)blockIdx.y * BM >= rest || (int)blockIdx.x * BN >= rest) return;
+    if (sym && ((int)blockIdx.y + 1) * BM <= (int)blockIdx.x * BN) return;      // tile strictly above the diagonal
     double *A = arena + F.f_off;
     gemm_tile(A + (int64_t)ge * n + g0, n, A + (int64_t)g0 * n + ge, n, A + (int64_t)ge * n + ge, n, rest, rest, ge - g0, blockIdx.y,
-              blockIdx.z, 0);
+              blockIdx.x, 0);
 }
 
 // Permanent factor of a level: for block column k of every front, rows above the diagonal block hold
@@ -1619,7 +1619,7 @@ static void factorise(Ctx *c, const double *vals11) {
                 if (rest > 0) {
                     int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
                     lp.begin(6);
-                    { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<dim3(nf_, tiles_l, tiles_u), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym); }
+                    { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<dim3(tiles_u, tiles_l, nf_), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym); }
                     lp.end();
                     c->count_launch();
                 }
@@ -1720,7 +1720,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             c->count_launch();
             continue;
         }
-        if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
+        if (!use_ll && nfl >= FUSED_SOLVE_MIN_FRONTS) {     // fallback for more than 256 right-hand sides
             ProfScope ps_(c, PS_SOLVE_FUSED);
             k_front_forward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, d.L.ptr,
                                                            d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr, Y);
@@ -1776,7 +1776,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             c->count_launch();
             continue;
         }
-        if (nfl >= FUSED_SOLVE_MIN_FRONTS) {
+        if (!use_ll && nfl >= FUSED_SOLVE_MIN_FRONTS) {
             ProfScope ps_(c, PS_SOLVE_FUSED);
             k_front_backward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X, W, Y);
             c->count_launch();
