@@ -632,17 +632,20 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
 
 // trailing update after group [g0, ge): F[ge:, ge:] -= L[ge:, g0:ge] U[g0:ge, ge:]   (rank ge - g0 <= GB)
 __global__ void __launch_bounds__(256, 2)
-k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym) {
-    FrontDev F = fronts[first + blockIdx.z];      // front slowest: the CTAs of one front run together, its panels stay in L2
+k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym, int front_on_x) {
+    // front slowest (grid z) when the level has at most 65535 fronts: the CTAs of one front run together and its
+    // panels stay in L2; otherwise the front index needs the x dimension
+    const int tcol = front_on_x ? blockIdx.z : blockIdx.x;
+    FrontDev F = fronts[first + (front_on_x ? blockIdx.x : blockIdx.z)];
     if (g0 >= F.ns) return;
     const int ge = min(g0 + GB, F.ns);
     const int n = F.ns + F.nb;
     const int rest = n - ge;
-    if ((int)blockIdx.y * BM >= rest || (int)blockIdx.x * BN >= rest) return;
-    if (sym && ((int)blockIdx.y + 1) * BM <= (int)blockIdx.x * BN) return;      // tile strictly above the diagonal
+    if ((int)blockIdx.y * BM >= rest || tcol * BN >= rest) return;
+    if (sym && ((int)blockIdx.y + 1) * BM <= tcol * BN) return;      // tile strictly above the diagonal
     double *A = arena + F.f_off;
     gemm_tile(A + (int64_t)ge * n + g0, n, A + (int64_t)g0 * n + ge, n, A + (int64_t)ge * n + ge, n, rest, rest, ge - g0, blockIdx.y,
-              blockIdx.x, 0);
+              tcol, 0);
 }
 
 // Permanent factor of a level: for block column k of every front, rows above the diagonal block hold
@@ -997,15 +1000,16 @@ __device__ __noinline__ void sweep_add_child(double *w, const double *__restrict
 
 template <int CW>
 __global__ void __launch_bounds__(256, 2)
-k_front_forward_sm(int first, int s, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
+k_front_forward_sm(int first, int s, int H, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
                    const int32_t *__restrict__ rel, const int32_t *__restrict__ child_ptr, const int32_t *__restrict__ child_idx,
                    const double *__restrict__ L, const double *__restrict__ inv, double *__restrict__ X,
                    double *__restrict__ Wout, const double *__restrict__ Wchild) {
     constexpr int LDW = CW + 4, NT = CW / 8;
     double *w = pn_dyn_smem;
-    const int f = first + blockIdx.x;
+    // 1-D grid, column chunk fastest: the CTAs that stream the same front's panels are scheduled together (second read from L2)
+    const int f = first + blockIdx.x / H;
     const FrontDev F = fronts[f];
-    const int n = F.ns + F.nb, c0 = blockIdx.y * CW;
+    const int n = F.ns + F.nb, c0 = (blockIdx.x % H) * CW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t *fi = fidx + F.idx_off;
     // own rows from X, boundary rows and the padding rows zero
@@ -1053,13 +1057,13 @@ k_front_forward_sm(int first, int s, const FrontDev *__restrict__ fronts, const 
 
 template <int CW>
 __global__ void __launch_bounds__(256, 2)
-k_front_backward_sm(int first, int s, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
+k_front_backward_sm(int first, int s, int H, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
                     const double *__restrict__ L, const double *__restrict__ U, const double *__restrict__ inv,
                     double *__restrict__ X) {
     constexpr int LDW = CW + 4, NT = CW / 8;
     double *w = pn_dyn_smem;
-    const FrontDev F = fronts[first + blockIdx.x];
-    const int n = F.ns + F.nb, c0 = blockIdx.y * CW;
+    const FrontDev F = fronts[first + blockIdx.x / H];
+    const int n = F.ns + F.nb, c0 = (blockIdx.x % H) * CW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t *fi = fidx + F.idx_off;
     // own rows hold y, boundary rows the final x of the ancestors
@@ -1619,7 +1623,7 @@ static void factorise(Ctx *c, const double *vals11) {
                 if (rest > 0) {
                     int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
                     lp.begin(6);
-                    { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<dim3(tiles_u, tiles_l, nf_), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym); }
+                    { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<nf_ <= 65535 ? dim3(tiles_u, tiles_l, nf_) : dim3(nf_, tiles_l, tiles_u), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym, nf_ <= 65535 ? 0 : 1); }
                     lp.end();
                     c->count_launch();
                 }
@@ -1712,8 +1716,9 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
         if (cw) {
             ProfScope ps_(c, PS_SOLVE_FUSED);
-            dim3 grid(nfl, (s + cw - 1) / cw);
-#define PN_FWD(CW_) k_front_forward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, \
+            const int H = (s + cw - 1) / cw;
+            const unsigned grid = (unsigned)nfl * (unsigned)H;
+#define PN_FWD(CW_) k_front_forward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, \
                                                                     d.L.ptr, d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr)
             if (cw == 32) PN_FWD(32); else if (cw == 16) PN_FWD(16); else PN_FWD(8);
 #undef PN_FWD
@@ -1769,8 +1774,9 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
         if (cw) {
             ProfScope ps_(c, PS_SOLVE_FUSED);
-            dim3 grid(nfl, (s + cw - 1) / cw);
-#define PN_BWD(CW_) k_front_backward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X)
+            const int H = (s + cw - 1) / cw;
+            const unsigned grid = (unsigned)nfl * (unsigned)H;
+#define PN_BWD(CW_) k_front_backward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X)
             if (cw == 32) PN_BWD(32); else if (cw == 16) PN_BWD(16); else PN_BWD(8);
 #undef PN_BWD
             c->count_launch();

@@ -47,14 +47,16 @@ for name in which:
             pass
         resid = np.abs(F.sum(axis=0) + Rc.sum(axis=0)).max()
         worst = max(worst, resid/max(np.abs(F).sum(), 1e-300))
-    # steady-state step
-    t2 = time.perf_counter()
-    eng.assemble_ke()
-    if mode == 'pdelta':
-        eng.solve_pdelta(opts, reactions=False, download=False)
-    else:
-        eng.solve_linear(opts, reactions=False, download=False)
-    t3 = time.perf_counter()
+    # steady-state step: the second assembly of a pattern builds the class / recipe maps (lazy), so the step that
+    # is timed is the third one
+    for rep in range(2):
+        t2 = time.perf_counter()
+        eng.assemble_ke()
+        if mode == 'pdelta':
+            eng.solve_pdelta(opts, reactions=False, download=False)
+        else:
+            eng.solve_linear(opts, reactions=False, download=False)
+        t3 = time.perf_counter()
     d = st.as_dict()
     print(json.dumps({'config': name, 'mode': mode, 'n_dof': int(s.n_dof), 'n1': int(s.n1), 'nnz_csr': int(s.nnz_csr),
                       'combos': int(A.factors.shape[0]), 'first_call_s': round(t1 - t0, 3), 'steady_step_s': round(t3 - t2, 4),
