@@ -201,6 +201,45 @@ def test_spmm_matches_scipy(eng):
         assert ms > 0
 
 
+def test_compact_reaction_download_matches_oracle(eng):
+    """`reactions_out` moves only the rows of DOFs that can carry a reaction across PCIe when they are fewer than one in
+    eight and scatters them into a zero-filled host array: same numbers as the oracle, exact zeros elsewhere."""
+    from pynite_b200 import synthetic
+    A = synthetic.quad_plate_arrays(n=30, n_combos=3)
+    sup = np.unpackbits(np.asarray(A.support, dtype=np.uint8).reshape(-1, 1), axis=1, bitorder='little')[:, :6].reshape(-1)
+    assert 8*int(sup.sum()) < A.n_dof                   # the compact path is the one exercised here
+    _upload(eng, A)
+    R_host = np.full((3, A.n_dof), np.nan)              # must be overwritten completely
+    D, R, _ = eng.solve_linear(eng.make_opts(), R_out=R_host)
+    Do, Ro = om.solve_linear(A)
+    for c in range(3):
+        assert rel_err(D[c], Do[c].reshape(-1)) < TOL_D
+        assert rel_err(R[c], Ro[c].reshape(-1)) < TOL_D
+        assert np.all(R[c][sup == 0] == 0.0)
+
+
+def test_assembly_graph_equals_launch_by_launch(eng):
+    """The numeric class / recipe assembly replayed as one CUDA graph writes the same bits as the individual launches
+    and as the general path (first assembly of a pattern)."""
+    from pynite_b200 import synthetic
+    A = synthetic.quad_plate_arrays(n=41, n_combos=2, mat_springs=0.1)
+    _upload(eng, A)
+    eng.symbolic(0)
+    eng.assemble_ke()
+    v_general = eng.csr_values().copy()
+    eng.assemble_ke()                                   # second assembly: class / recipe maps, graph captured
+    v_graph = eng.csr_values().copy()
+    eng.assemble_ke()                                   # graph replay
+    assert np.array_equal(v_graph, eng.csr_values())
+    eng.set_option('assembly_graph', 0)
+    try:
+        eng.assemble_ke()
+        v_plain = eng.csr_values().copy()
+    finally:
+        eng.set_option('assembly_graph', 1)
+    assert np.array_equal(v_general, v_graph) and np.array_equal(v_graph, v_plain)
+
+
 def test_unstable_and_singular_detection(eng):
     """`Analysis._check_stability` (:111-168) and the residual check of `_solve_unknown_disp` (:228-239)."""
     from pynite_b200 import FEModel3D
