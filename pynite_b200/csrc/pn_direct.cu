@@ -160,6 +160,24 @@ __global__ void k_assemble_entries(int64_t nnz, int level, const uint8_t *__rest
     arena[fronts[ent_front[k]].f_off + ent_dst[k]] = vals[k];
 }
 
+// Symmetric mode reads the strict upper triangle of a front only where the transposed panels wrote it, so only the lower
+// triangle (with the diagonal) is zeroed before assembly: half the bytes of a memset of the whole arena.
+// grid = (front, row chunk); a warp per row, 16-byte stores.
+__global__ void k_zero_lower(int first, const FrontDev *__restrict__ fronts, double *__restrict__ arena) {
+    const FrontDev F = fronts[first + blockIdx.x];
+    const int n = F.ns + F.nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = blockIdx.y * nw + warp; r < n; r += gridDim.y * nw) {
+        double *row = arena + F.f_off + (int64_t)r * n;
+        // f_off + r n may be odd: peel to 16-byte alignment, then double2 stores
+        int c = 0;
+        if ((reinterpret_cast<uintptr_t>(row) & 15) != 0) { if (lane == 0) row[0] = 0.0; c = 1; }
+        const int end = r + 1;
+        for (int j = c + 2 * lane; j + 1 < end; j += 64) *reinterpret_cast<double2 *>(row + j) = make_double2(0.0, 0.0);
+        if (((end - c) & 1) && lane == 0) row[end - 1] = 0.0;
+    }
+}
+
 // Adds the update matrix of every child with the given rank into its parent (one level up).
 // grid.x = child index within the child level, grid.y = row chunk of the nb x nb update matrix; a thread block walks
 // rows, threads walk columns (coalesced reads of the child row; the parent columns rel[b] are ascending runs).
@@ -1563,7 +1581,13 @@ static void factorise(Ctx *c, const double *vals11) {
         double *arena = d.arena[l & 1].ptr;
         if (debug_levels) cudaEventRecord(dbg0, st);
         lp.begin(0);
-        PN_CUDA(cudaMemsetAsync(arena, 0, sizeof(double) * d.level_f_total[l], st));
+        if (sym) {
+            unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((d.level_max_n[l] + 7) / 8, 1), std::max<int64_t>(1, 32768 / std::max(nfl, 1)));
+            k_zero_lower<<<dim3(nfl, gy), 256, 0, st>>>(first, d.fronts.ptr, arena);
+            c->count_launch();
+        } else {
+            PN_CUDA(cudaMemsetAsync(arena, 0, sizeof(double) * d.level_f_total[l], st));
+        }
         { ProfScope ps_(c, PS_FRONT_ASSEMBLE); k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
                                                                   d.fronts.ptr, vals11, arena); }
         lp.end();
