@@ -227,8 +227,12 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // tiles stream through shared memory as a ring of four 16-wide k slices filled by cp.async.
 // In-place use (C aliasing A or B) is safe when the tile covers the aliased operand's full extent in the other
 // dimension: every global read is complete (wait_group 0 + barrier) before the first store.
+// Warps whose 32 x 32 block lies outside the matrix, or (lower_only: C is a symmetric trailing matrix of which only the
+// lower triangle is kept, rows and columns counted from the same origin) strictly above the diagonal, take part in the
+// copies and barriers but skip their fragment loads and DMMAs: on the small fronts of the bottom levels (trailing
+// blocks of 144 ... 1140 rows in 128 x 64 tiles) that removes more than half of the tensor work.
 __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
-                                          int m, int n, int k, int tile_m, int tile_n, int mode) {
+                                          int m, int n, int k, int tile_m, int tile_n, int mode, bool lower_only = false) {
     double(*sA)[SA_LD] = reinterpret_cast<double(*)[SA_LD]>(pn_dyn_smem);
     double(*sB)[SB_LD] = reinterpret_cast<double(*)[SB_LD]>(pn_dyn_smem + BM * SA_LD);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
@@ -236,7 +240,8 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
     const int wrow = (warp >> 1) * 32, wcol = (warp & 1) * 32;
     double acc[4][4][2];
     const bool full_tile = row0 + BM <= m && col0 + BN <= n;
-    if (mode != 0) {
+    const bool warp_on = row0 + wrow < m && col0 + wcol < n && !(lower_only && row0 + wrow + 31 < col0 + wcol);
+    if (mode != 0 || !warp_on) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -313,6 +318,7 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
         __syncthreads();
         issue(sl + 3);
         const int base = (sl & 3) << 4;
+        if (warp_on)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const int kk = base + 4 * ks + tg;
@@ -329,6 +335,7 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
     }
     cp_async_wait<0>();
     __syncthreads();          // the tiles may be refilled by the caller's next gemm_tile call
+    if (!warp_on) return;
     if (full_tile) {
         double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 2 * tg;
 #pragma unroll
@@ -639,7 +646,7 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
     const double *Lp = A + (int64_t)r0 * n + kb;        // L[r0:, kb:r0]
     if (t < ta_m * ta_n) {
         if (sym && (t / ta_n + 1) * BM <= (t % ta_n) * BN) return;      // tile strictly above the diagonal
-        gemm_tile(Lp, n, A + (int64_t)kb * n + r0, n, A + (int64_t)r0 * n + r0, n, ha, wa, NB, t / ta_n, t % ta_n, 0);
+        gemm_tile(Lp, n, A + (int64_t)kb * n + r0, n, A + (int64_t)r0 * n + r0, n, ha, wa, NB, t / ta_n, t % ta_n, 0, sym != 0);
         return;
     }
     if (sym) return;                           // region (b) is the upper side
@@ -663,7 +670,7 @@ k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__re
     if (sym && ((int)blockIdx.y + 1) * BM <= tcol * BN) return;      // tile strictly above the diagonal
     double *A = arena + F.f_off;
     gemm_tile(A + (int64_t)ge * n + g0, n, A + (int64_t)g0 * n + ge, n, A + (int64_t)ge * n + ge, n, rest, rest, ge - g0, blockIdx.y,
-              tcol, 0);
+              tcol, 0, sym != 0);
 }
 
 // Permanent factor of a level: for block column k of every front, rows above the diagonal block hold
@@ -1508,11 +1515,11 @@ static void analyse(Ctx *c) {
                 int ge = std::min(g0 + GB, fs.ns);
                 int64_t rest = n - ge;
                 double K = ge - g0;
-                for (int64_t r = 0; r < rest; r += BM) {
-                    int64_t rows = std::min<int64_t>(BM, rest - r);
-                    int64_t cmax = sym ? std::min<int64_t>(rest, ((r + BM + BN - 1) / BN) * BN) : rest;   // columns of computed tiles
-                    upd += 2.0 * K * (double)rows * (double)cmax;
-                }
+                // executed at the granularity of a warp's 32 x 32 block: blocks inside the matrix and, in symmetric
+                // mode, not strictly above the diagonal (gemm_tile's warp_on)
+                for (int64_t r = 0; r < rest; r += 32)
+                    for (int64_t cc = 0; cc < rest; cc += 32)
+                        if (!(sym && r + 31 < cc)) upd += 2.0 * K * 32.0 * 32.0;
             }
         }
         c->stats.update_flops = upd;
