@@ -232,7 +232,8 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // copies and barriers but skip their fragment loads and DMMAs: on the small fronts of the bottom levels (trailing
 // blocks of 144 ... 1140 rows in 128 x 64 tiles) that removes more than half of the tensor work.
 __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
-                                          int m, int n, int k, int tile_m, int tile_n, int mode, bool lower_only = false) {
+                                          int m, int n, int k, int tile_m, int tile_n, int mode, bool lower_only = false,
+                                          double *Ct = nullptr, int64_t ldct = 0, const double *ct_scale = nullptr, int64_t ct_scale_ld = 0) {
     double(*sA)[SA_LD] = reinterpret_cast<double(*)[SA_LD]>(pn_dyn_smem);
     double(*sB)[SB_LD] = reinterpret_cast<double(*)[SB_LD]>(pn_dyn_smem + BM * SA_LD);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
@@ -336,6 +337,25 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
     cp_async_wait<0>();
     __syncthreads();          // the tiles may be refilled by the caller's next gemm_tile call
     if (!warp_on) return;
+    if (Ct) {
+        // second, transposed and column-scaled copy of the result: Ct[col][row] = scale[col] * C[row][col] (the row
+        // panel U = D L^T of the symmetric factorisation, written from the accumulators instead of by a transpose
+        // kernel); the eight lanes that share a column write eight consecutive rows = one 64-byte segment
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gc = col0 + wcol + 8 * ni + 2 * tg + e;
+                if (gc >= n) continue;
+                const double sc = ct_scale[(int64_t)gc * ct_scale_ld];
+                double *dst = Ct + (int64_t)gc * ldct;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int gr = row0 + wrow + 8 * mi + g;
+                    if (gr < m) dst[gr] = sc * acc[mi][ni][e];
+                }
+            }
+    }
     if (full_tile) {
         double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 2 * tg;
 #pragma unroll
@@ -594,7 +614,10 @@ k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts,
         int t = blockIdx.y - tiles_u;
         if (t * BM >= rest) return;
         double *P = A + (int64_t)r0 * n + kb;
-        gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1);
+        if (sym)      // U[kb + j, r0 + i] = pivot_j * L[r0 + i, kb + j]
+            gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1, false, A + (int64_t)kb * n + r0, n, A + (int64_t)kb * n + kb, n + 1);
+        else
+            gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1);
     }
 }
 
@@ -1577,6 +1600,8 @@ static void factorise(Ctx *c, const double *vals11) {
     cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
     if (debug_levels) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); }
     static const bool debug_kernels = getenv("PN_DEBUG_LEVEL_KERNELS") != nullptr;
+    // symmetric mode: the row panels are written by the panel GEMM's epilogue; the stand-alone transpose kernel is kept for A/B runs
+    static const bool transpose_kernel = getenv("PN_TRANSPOSE_KERNEL") != nullptr;
     LevelProf lp(debug_levels && debug_kernels, st);
     long long *dbg_clk = nullptr;
     if (debug_levels && debug_kernels) cudaMalloc(&dbg_clk, 8 * sizeof(long long));
@@ -1637,9 +1662,9 @@ static void factorise(Ctx *c, const double *vals11) {
                         lp.begin(3);
                         { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_panels<<<dim3(nf_, tiles_u + tiles_l), 256, GEMM_SMEM, sq>>>(f0_, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym);
                           lp.end(); lp.begin(4);
-                          if (sym) k_lu_transpose_panel<<<dim3(nf_, (rest + 31) / 32), dim3(32, 8), 0, sq>>>(f0_, kb, d.fronts.ptr, arena); }
+                          if (sym && transpose_kernel) k_lu_transpose_panel<<<dim3(nf_, (rest + 31) / 32), dim3(32, 8), 0, sq>>>(f0_, kb, d.fronts.ptr, arena); }
                         lp.end();
-                        c->count_launch(1 + sym);
+                        c->count_launch(1 + (sym && transpose_kernel));
                         if (kb + NB < gend) {
                             int wa = gend - kb - NB;       // strips inside the group
                             int tiles = ((rest + BM - 1) / BM) * ((wa + BN - 1) / BN) + ((wa + BM - 1) / BM) * tiles_u;
