@@ -233,7 +233,8 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // blocks of 144 ... 1140 rows in 128 x 64 tiles) that removes more than half of the tensor work.
 __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
                                           int m, int n, int k, int tile_m, int tile_n, int mode, bool lower_only = false,
-                                          double *Ct = nullptr, int64_t ldct = 0, const double *ct_scale = nullptr, int64_t ct_scale_ld = 0) {
+                                          double *Ct = nullptr, int64_t ldct = 0, const double *ct_scale = nullptr, int64_t ct_scale_ld = 0,
+                                          double *Ct2 = nullptr, int64_t ldct2 = 0, int ct2_row0 = 0) {
     double(*sA)[SA_LD] = reinterpret_cast<double(*)[SA_LD]>(pn_dyn_smem);
     double(*sB)[SB_LD] = reinterpret_cast<double(*)[SB_LD]>(pn_dyn_smem + BM * SA_LD);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
@@ -349,10 +350,15 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
                 if (gc >= n) continue;
                 const double sc = ct_scale[(int64_t)gc * ct_scale_ld];
                 double *dst = Ct + (int64_t)gc * ldct;
+                double *dst2 = Ct2 ? Ct2 + (int64_t)gc * ldct2 - ct2_row0 : nullptr;   // rows >= ct2_row0 also go to the permanent U12
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi) {
                     const int gr = row0 + wrow + 8 * mi + g;
-                    if (gr < m) dst[gr] = sc * acc[mi][ni][e];
+                    if (gr < m) {
+                        const double v = sc * acc[mi][ni][e];
+                        dst[gr] = v;
+                        if (dst2 && gr >= ct2_row0) dst2[gr] = v;
+                    }
                 }
             }
     }
@@ -594,7 +600,7 @@ k_lu_diag(int first, int kb, const FrontDev *__restrict__ fronts, double *__rest
 // L[rest, k] = F[rest, k] Uinv.  Both are in place (see gemm_tile).
 __global__ void __launch_bounds__(256, 2)
 k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts, double *__restrict__ arena,
-            const double *__restrict__ inv, int sym) {
+            const double *__restrict__ inv, int sym, double *__restrict__ U12) {
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
     const int bs = min(NB, F.ns - kb);
@@ -615,7 +621,8 @@ k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts,
         if (t * BM >= rest) return;
         double *P = A + (int64_t)r0 * n + kb;
         if (sym)      // U[kb + j, r0 + i] = pivot_j * L[r0 + i, kb + j]
-            gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1, false, A + (int64_t)kb * n + r0, n, A + (int64_t)kb * n + kb, n + 1);
+            gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1, false, A + (int64_t)kb * n + r0, n, A + (int64_t)kb * n + kb, n + 1,
+                      F.nb ? U12 + F.u_off + (int64_t)kb * F.nb : nullptr, F.nb, F.ns - r0);
         else
             gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1);
     }
@@ -1660,7 +1667,7 @@ static void factorise(Ctx *c, const double *vals11) {
                     if (rest > 0) {
                         int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
                         lp.begin(3);
-                        { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_panels<<<dim3(nf_, tiles_u + tiles_l), 256, GEMM_SMEM, sq>>>(f0_, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym);
+                        { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_panels<<<dim3(nf_, tiles_u + tiles_l), 256, GEMM_SMEM, sq>>>(f0_, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym, d.U.ptr);
                           lp.end(); lp.begin(4);
                           if (sym && transpose_kernel) k_lu_transpose_panel<<<dim3(nf_, (rest + 31) / 32), dim3(32, 8), 0, sq>>>(f0_, kb, d.fronts.ptr, arena); }
                         lp.end();
@@ -1706,7 +1713,7 @@ static void factorise(Ctx *c, const double *vals11) {
             int steps = (maxns + NB - 1) / NB;
             int row_tiles = (maxn + BM - 1) / BM + 1;
             if (steps > 0) k_store_panels<<<dim3(nfl, steps, row_tiles), 256, GEMM_SMEM, st>>>(first, d.fronts.ptr, arena, d.inv.ptr, d.L.ptr);
-            if (d.level_max_nb[l] > 0) {
+            if (d.level_max_nb[l] > 0 && !(sym && !transpose_kernel)) {     // symmetric mode: written by the panel GEMMs
                 int64_t per = (int64_t)maxns * d.level_max_nb[l];
                 unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((per + 255) / 256, 1), 2048);
                 k_copy_u12<<<dim3(nfl, gy), 256, 0, st>>>(first, d.fronts.ptr, arena, d.U.ptr);
