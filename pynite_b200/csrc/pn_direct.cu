@@ -600,7 +600,7 @@ k_lu_diag(int first, int kb, const FrontDev *__restrict__ fronts, double *__rest
 // L[rest, k] = F[rest, k] Uinv.  Both are in place (see gemm_tile).
 __global__ void __launch_bounds__(256, 2)
 k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts, double *__restrict__ arena,
-            const double *__restrict__ inv, int sym, double *__restrict__ U12) {
+            const double *__restrict__ inv, int sym, double *__restrict__ U12, double *__restrict__ Lst) {
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
     const int bs = min(NB, F.ns - kb);
@@ -625,6 +625,10 @@ k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts,
                       F.nb ? U12 + F.u_off + (int64_t)kb * F.nb : nullptr, F.nb, F.ns - r0);
         else
             gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1);
+        // permanent, pre-multiplied copy of the tile for the sweeps: Lp[r, k] = L[r, k] Linv_kk, from the tile this CTA
+        // has just written (L1 / L2 hits) instead of a second pass over the arena at the end of the level
+        __syncthreads();
+        gemm_tile(P, n, Linv, NB, Lst + F.l_off + (int64_t)r0 * F.ns + kb, F.ns, rest, bs, bs, t, 0, 1);
     }
 }
 
@@ -720,12 +724,8 @@ k_store_panels(int first, const FrontDev *__restrict__ fronts, const double *__r
     const double *Linv = inv + F.inv_off + (int64_t)blockIdx.y * (2 * NB * NB);
     const double *A = arena + F.f_off;
     double *out = L + F.l_off;
-    if (t < up_tiles) {
-        gemm_tile(A + kb, n, Linv + NB * NB, NB, out + kb, F.ns, up_rows, bs, bs, t, 0, 1);
-    } else if (t - up_tiles < lo_tiles) {
-        int r0 = kb + bs;
-        gemm_tile(A + (int64_t)r0 * n + kb, n, Linv, NB, out + (int64_t)r0 * F.ns + kb, F.ns, lo_rows, bs, bs, t - up_tiles, 0, 1);
-    }
+    (void)lo_tiles;      // the rows below the diagonal block are stored by k_lu_panels
+    if (t < up_tiles) gemm_tile(A + kb, n, Linv + NB * NB, NB, out + kb, F.ns, up_rows, bs, bs, t, 0, 1);
 }
 
 // U12 of every front of a level to permanent storage
@@ -1667,7 +1667,7 @@ static void factorise(Ctx *c, const double *vals11) {
                     if (rest > 0) {
                         int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
                         lp.begin(3);
-                        { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_panels<<<dim3(nf_, tiles_u + tiles_l), 256, GEMM_SMEM, sq>>>(f0_, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym, d.U.ptr);
+                        { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_panels<<<dim3(nf_, tiles_u + tiles_l), 256, GEMM_SMEM, sq>>>(f0_, kb, tiles_u, d.fronts.ptr, arena, d.inv.ptr, sym, d.U.ptr, d.L.ptr);
                           lp.end(); lp.begin(4);
                           if (sym && transpose_kernel) k_lu_transpose_panel<<<dim3(nf_, (rest + 31) / 32), dim3(32, 8), 0, sq>>>(f0_, kb, d.fronts.ptr, arena); }
                         lp.end();
@@ -1711,8 +1711,8 @@ static void factorise(Ctx *c, const double *vals11) {
             lp.begin(7);
             ProfScope ps_(c, PS_COPY_FACTORS);
             int steps = (maxns + NB - 1) / NB;
-            int row_tiles = (maxn + BM - 1) / BM + 1;
-            if (steps > 0) k_store_panels<<<dim3(nfl, steps, row_tiles), 256, GEMM_SMEM, st>>>(first, d.fronts.ptr, arena, d.inv.ptr, d.L.ptr);
+            int row_tiles = (maxns + BM - 1) / BM;          // rows above the diagonal blocks only
+            if (steps > 1) k_store_panels<<<dim3(nfl, steps, row_tiles), 256, GEMM_SMEM, st>>>(first, d.fronts.ptr, arena, d.inv.ptr, d.L.ptr);
             if (d.level_max_nb[l] > 0 && !(sym && !transpose_kernel)) {     // symmetric mode: written by the panel GEMMs
                 int64_t per = (int64_t)maxns * d.level_max_nb[l];
                 unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>((per + 255) / 256, 1), 2048);
