@@ -34,8 +34,30 @@
 #include <future>
 #include <omp.h>
 #include <memory>
+#include <new>
 #include <cstdio>
 #include <cstdlib>
+
+// page-locked host memory for the index lists of the analysis (pn_direct_symbolic.h, PinnedAllocator); falls back to
+// pageable memory if the driver refuses (the uploads are then staged, nothing else changes)
+extern "C" void *pn_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0) bytes = 1;
+    if (cudaMallocHost(&p, bytes + 16) != cudaSuccess) {
+        cudaGetLastError();
+        p = malloc(bytes + 16);
+        if (!p) throw std::bad_alloc();
+        *static_cast<uint64_t *>(p) = 0;
+    } else {
+        *static_cast<uint64_t *>(p) = 1;
+    }
+    return static_cast<char *>(p) + 16;
+}
+extern "C" void pn_host_free(void *q) {
+    if (!q) return;
+    char *p = static_cast<char *>(q) - 16;
+    if (*reinterpret_cast<uint64_t *>(p) == 1) cudaFreeHost(p); else free(p);
+}
 
 namespace pn {
 
@@ -97,6 +119,7 @@ struct DirectSolver {
         }
         if (ev_fork) cudaEventDestroy(ev_fork);
     }
+    SymVec<int32_t> h_dof_front_lm;           // page-locked staging of dof_front in level-major numbering
     std::vector<int32_t> g_vstart, g_adj;     // vertex graph of the last analysis (host)
     std::vector<double> g_coords;
     std::vector<int64_t> g_adj_ptr;
@@ -1461,8 +1484,10 @@ static void analyse(Ctx *c) {
     d.fpos.upload(S.fpos.data(), (int64_t)S.fpos.size(), st);
     d.rel.upload(S.rel.data(), (int64_t)S.rel.size(), st);
     d.perm_pos.upload(S.perm_pos.data(), (int64_t)S.perm_pos.size(), st);
-    std::vector<int32_t> dof_front_lm(S.dof_front.size());
-    for (size_t i = 0; i < dof_front_lm.size(); ++i) dof_front_lm[i] = lm_of[S.dof_front[i]];
+    SymVec<int32_t> &dof_front_lm = d.h_dof_front_lm;
+    dof_front_lm.resize(S.dof_front.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)dof_front_lm.size(); ++i) dof_front_lm[i] = lm_of[S.dof_front[i]];
     d.dof_front_lm.upload(dof_front_lm.data(), (int64_t)dof_front_lm.size(), st);
     DevBuf<uint8_t> &d_front_level = c->sym_front_level;
     d_front_level.upload(front_level.data(), nf, st);
@@ -1477,7 +1502,8 @@ static void analyse(Ctx *c) {
         PN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ll_sweep, 256, 0));
         d.ll_grid = std::max(1, per_sm) * sms;
     }
-    d.L.zero(st);
+    // (L needs no zero fill: the sweeps read, per block column, only the rows below / above the diagonal block, and
+    // those are all written by k_lu_panels / k_store_panels; columns past a partial block are masked by the k count)
     d.fronts_s = 0;
     if (!d.attrs_set) {
         PN_CUDA(cudaFuncSetAttribute(k_lu_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));

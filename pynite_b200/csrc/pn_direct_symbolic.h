@@ -2,8 +2,35 @@
 // of the node graph from node coordinates, separator tree = supernodal elimination tree, front
 // index lists and extend-add maps.  See pn_direct.cu for the numeric multifrontal factorisation.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <vector>
+
+// The large index lists go to the device right after the analysis.  In the library build (PN_SYM_PINNED) their vectors
+// allocate page-locked host memory (pn_host_alloc / pn_host_free, defined in pn_direct.cu with cudaMallocHost), so the
+// uploads run at full PCIe speed without a staging copy; the vectors live in the solver object and keep their
+// capacity, so the allocation cost is paid once.  The host-only test harness uses plain std::allocator.
+#ifdef PN_SYM_PINNED
+extern "C" void *pn_host_alloc(size_t bytes);
+extern "C" void pn_host_free(void *p);
+namespace pn {
+template <typename T>
+struct PinnedAllocator {
+    using value_type = T;
+    PinnedAllocator() = default;
+    template <typename U> PinnedAllocator(const PinnedAllocator<U> &) {}
+    T *allocate(size_t n) { return static_cast<T *>(pn_host_alloc(n * sizeof(T))); }
+    void deallocate(T *p, size_t) { pn_host_free(p); }
+    template <typename U> bool operator==(const PinnedAllocator<U> &) const { return true; }
+    template <typename U> bool operator!=(const PinnedAllocator<U> &) const { return false; }
+};
+template <typename T> using SymVec = std::vector<T, PinnedAllocator<T>>;
+}  // namespace pn
+#else
+namespace pn {
+template <typename T> using SymVec = std::vector<T>;
+}
+#endif
 
 namespace pn {
 
@@ -20,12 +47,12 @@ struct FrontSym {
 
 struct DirectSym {
     int64_t n = 0;                    // order of K11
-    std::vector<int32_t> perm_pos;    // [n] elimination position of each K11 row
+    SymVec<int32_t> perm_pos;         // [n] elimination position of each K11 row
     std::vector<int32_t> dof_front;   // [n] front that eliminates each K11 row
     std::vector<FrontSym> fronts;     // post-order: children before parents
-    std::vector<int32_t> fidx;        // front index lists as K11 row numbers
-    std::vector<int32_t> fpos;        // the same lists as elimination positions (ascending per front)
-    std::vector<int32_t> rel;         // for each boundary DOF: its position in the parent's index list
+    SymVec<int32_t> fidx;             // front index lists as K11 row numbers
+    SymVec<int32_t> fpos;             // the same lists as elimination positions (ascending per front)
+    SymVec<int32_t> rel;              // for each boundary DOF: its position in the parent's index list
     std::vector<int32_t> level_ptr;   // level l holds fronts level_fronts[level_ptr[l] .. level_ptr[l+1])
     std::vector<int32_t> level_fronts;   // level 0 = deepest; every child is exactly one level below its parent
     int32_t max_children = 0;
