@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument('--n', type=int, default=500, help='quads per side (500 = BASELINE config 3)')
     ap.add_argument('--combos', type=int, default=64, help='load combinations per GPU')
     ap.add_argument('--solver', default='direct', choices=['direct', 'pcg'])
-    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--cpu-n', type=int, default=96, help='quads per side of the CPU-baseline sample')
     ap.add_argument('--cpu-combos', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')

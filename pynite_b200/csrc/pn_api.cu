@@ -47,6 +47,15 @@ void invalidate(Ctx *c) {
     direct_invalidate(c);
 }
 
+// host copy of a model array (the analysis reads these copies: ordering, element classes, symmetric-mode detection).
+// Deliberately serial: an OpenMP region on this thread would leave its team spinning on the cores the ordering
+// worker (pn_prefetch_analysis) is about to use (measured: e2e 157 -> 187 ms with a parallel copy).
+template <typename T>
+void host_copy(std::vector<T> &v, const T *src, int64_t n) {
+    v.resize((size_t)n);
+    if (n) memcpy(v.data(), src, (size_t)n * sizeof(T));
+}
+
 template <typename T>
 void download(const DevBuf<T> &b, T *host, cudaStream_t st) {
     if (host && b.n) PN_CUDA(cudaMemcpyAsync(host, b.ptr, (size_t)b.n * sizeof(T), cudaMemcpyDeviceToHost, st));
@@ -382,12 +391,12 @@ int pn_set_nodes(pn_ctx *ctx, int64_t n_nodes, const double *xyz, const uint8_t 
     m.enf_val.upload(enforced_val, 6 * n_nodes, st);
     m.nspring_k.upload(spring_k, 6 * n_nodes, st);
     m.nspring_flag.upload(spring_flag, 6 * n_nodes, st);
-    m.h_xyz.assign(xyz, xyz + 3 * n_nodes);
-    m.h_support.assign(support_mask, support_mask + n_nodes);
-    m.h_enf_mask.assign(enforced_mask, enforced_mask + n_nodes);
-    m.h_enf_val.assign(enforced_val, enforced_val + 6 * n_nodes);
-    m.h_nspring_k.assign(spring_k, spring_k + 6 * n_nodes);
-    m.h_nspring_flag.assign(spring_flag, spring_flag + 6 * n_nodes);
+    host_copy(m.h_xyz, xyz, (int64_t)(3 * n_nodes));
+    host_copy(m.h_support, support_mask, (int64_t)(n_nodes));
+    host_copy(m.h_enf_mask, enforced_mask, (int64_t)(n_nodes));
+    host_copy(m.h_enf_val, enforced_val, (int64_t)(6 * n_nodes));
+    host_copy(m.h_nspring_k, spring_k, (int64_t)(6 * n_nodes));
+    host_copy(m.h_nspring_flag, spring_flag, (int64_t)(6 * n_nodes));
     PN_CUDA(cudaStreamSynchronize(st));
     PN_API_END
 }
@@ -404,9 +413,9 @@ int pn_set_springs(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *ks, 
     Model &m = c->model;
     invalidate(c);
     m.n_springs = n;
-    m.h_spring_ij.assign(ij, ij + 2 * n);
-    m.h_spring_active.assign(active, active + n);
-    m.h_spring_ks.assign(ks, ks + n);
+    host_copy(m.h_spring_ij, ij, (int64_t)(2 * n));
+    host_copy(m.h_spring_active, active, (int64_t)(n));
+    host_copy(m.h_spring_ks, ks, (int64_t)(n));
     m.spring_ij.upload(ij, 2 * n, c->stream);
     m.spring_ks.upload(ks, n, c->stream);
     m.spring_active.upload(active, n, c->stream);
@@ -422,11 +431,11 @@ int pn_set_members(pn_ctx *ctx, int64_t n, const int32_t *ij, const double *prop
     Model &m = c->model;
     invalidate(c);
     m.n_members = n;
-    m.h_mem_ij.assign(ij, ij + 2 * n);
-    m.h_mem_active.assign(active, active + n);
-    m.h_mem_props.assign(props, props + 6 * n);
-    m.h_mem_rot.assign(rotation_deg, rotation_deg + n);
-    m.h_mem_rel.assign(releases, releases + n);
+    host_copy(m.h_mem_ij, ij, (int64_t)(2 * n));
+    host_copy(m.h_mem_active, active, (int64_t)(n));
+    host_copy(m.h_mem_props, props, (int64_t)(6 * n));
+    host_copy(m.h_mem_rot, rotation_deg, (int64_t)(n));
+    host_copy(m.h_mem_rel, releases, (int64_t)(n));
     m.mem_ij.upload(ij, 2 * n, c->stream);
     m.mem_props.upload(props, 6 * n, c->stream);
     m.mem_rot.upload(rotation_deg, n, c->stream);
@@ -444,8 +453,8 @@ static void set_shells(Ctx *c, bool quad, int64_t n, const int32_t *ijmn, const 
     (quad ? m.n_quads : m.n_plates) = n;
     (quad ? m.quad_ijmn : m.plate_ijmn).upload(ijmn, 4 * n, c->stream);
     (quad ? m.quad_props : m.plate_props).upload(props, 5 * n, c->stream);
-    (quad ? m.h_quad_ijmn : m.h_plate_ijmn).assign(ijmn, ijmn + 4 * n);
-    (quad ? m.h_quad_props : m.h_plate_props).assign(props, props + 5 * n);
+    host_copy((quad ? m.h_quad_ijmn : m.h_plate_ijmn), ijmn, (int64_t)(4 * n));
+    host_copy((quad ? m.h_quad_props : m.h_plate_props), props, (int64_t)(5 * n));
     // the membrane matrix is unsymmetric when kx_mod != ky_mod (Quad3D.py:517-519)
     bool sym = true;
     for (int64_t e = 0; e < n; ++e) if (props[5 * e + 3] != props[5 * e + 4]) sym = false;

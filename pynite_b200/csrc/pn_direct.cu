@@ -1368,6 +1368,18 @@ static void analyse_host(Ctx *c, const std::vector<int32_t> &newidx, bool timing
     int leaf = 24;
     if (const char *e = getenv("PN_LEAF_SIZE")) leaf = std::max(1, atoi(e));
     direct_symbolic(n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym);
+    {
+        // front of every K11 row in level-major numbering (page-locked: uploaded as is).  Done here, on the thread
+        // that already owns an OpenMP team: a parallel region on the caller's thread would leave a second team
+        // spinning on the cores.
+        const DirectSym &S = d.sym;
+        const int nf = (int)S.fronts.size();
+        std::vector<int32_t> lm_of(nf);
+        for (int q = 0; q < nf; ++q) lm_of[S.level_fronts[q]] = q;
+        d.h_dof_front_lm.resize(S.dof_front.size());
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)S.dof_front.size(); ++i) d.h_dof_front_lm[i] = lm_of[S.dof_front[i]];
+    }
     tick.lap("nested dissection + fronts");
 }
 
@@ -1484,11 +1496,7 @@ static void analyse(Ctx *c) {
     d.fpos.upload(S.fpos.data(), (int64_t)S.fpos.size(), st);
     d.rel.upload(S.rel.data(), (int64_t)S.rel.size(), st);
     d.perm_pos.upload(S.perm_pos.data(), (int64_t)S.perm_pos.size(), st);
-    SymVec<int32_t> &dof_front_lm = d.h_dof_front_lm;
-    dof_front_lm.resize(S.dof_front.size());
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < (int64_t)dof_front_lm.size(); ++i) dof_front_lm[i] = lm_of[S.dof_front[i]];
-    d.dof_front_lm.upload(dof_front_lm.data(), (int64_t)dof_front_lm.size(), st);
+    d.dof_front_lm.upload(d.h_dof_front_lm.data(), (int64_t)d.h_dof_front_lm.size(), st);     // filled by analyse_host
     DevBuf<uint8_t> &d_front_level = c->sym_front_level;
     d_front_level.upload(front_level.data(), nf, st);
     d.L.resize(l_total); d.U.resize(u_total); d.inv.resize(inv_total);
