@@ -154,10 +154,24 @@ struct Builder {
             double ca = coords[3 * a + axis], cb = coords[3 * b + axis];
             return ca < cb || (ca == cb && a < b);
         };
-        std::nth_element(verts.begin(), verts.begin() + mid, verts.end(), cmp);
-        // keep vertices with the same coordinate as the median on one side when possible, so that
-        // separators of structured meshes are straight lines / planes
-        {
+        // Large sets: the cut coordinate is the median of a fixed-stride sample (the exact median needs an nth_element
+        // over indirect keys, which was a third of the serial time at the top of the recursion); the set is then
+        // split by coordinate, so vertices sharing the cut coordinate stay on one side and the separators of
+        // structured meshes are straight lines / planes.  Small or degenerate sets take the exact path.
+        bool split_done = false;
+        if (verts.size() > 8192) {
+            const size_t ns = 2047, stride = verts.size() / ns;
+            double sample[2047];
+            for (size_t q = 0; q < ns; ++q) sample[q] = coords[3 * verts[q * stride] + axis];
+            std::nth_element(sample, sample + ns / 2, sample + ns);
+            const double cm = sample[ns / 2];
+            auto it = std::partition(verts.begin(), verts.end(), [&](int32_t v) { return coords[3 * v + axis] < cm; });
+            const size_t cut = it - verts.begin();
+            if (cut > verts.size() / 4 && cut < verts.size() - verts.size() / 4) { mid = cut; split_done = true; }
+        }
+        if (!split_done) {
+            std::nth_element(verts.begin(), verts.begin() + mid, verts.end(), cmp);
+            // keep vertices with the same coordinate as the median on one side when possible
             double cm = coords[3 * verts[mid] + axis];
             size_t lo_cnt = 0;
             for (int32_t v : verts) if (coords[3 * v + axis] < cm) ++lo_cnt;
