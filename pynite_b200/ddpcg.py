@@ -68,6 +68,10 @@ class EngineOps:
         self.n1 = int(self.node_row_start[-1])
         self.device = torch.device('cuda', engine.device)
 
+    def set_stream(self, stream):
+        """Attaches the library's launches to a torch stream (the capture stream while an iteration is recorded)."""
+        self.eng.set_stream(stream.cuda_stream)
+
     def pattern(self):
         indptr, indices, _ = self.eng.block(0, values=False)
         return indptr, indices
@@ -98,9 +102,13 @@ class EngineOps:
         self.eng.dev_cg_direction(Z.shape[1], row0, row1, first, rz.data_ptr(), rz_new.data_ptr(), Z.data_ptr(), P.data_ptr())
 
 
-def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None, log=None):
+def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None, log=None, graph=True):
     """Solves K11 X = B for combos [combo0, combo0 + s) on all ranks of `group`; returns (X on every rank, iterations,
-    max relative residual).  Works without torch.distributed initialised (world size 1)."""
+    max relative residual).  Works without torch.distributed initialised (world size 1).
+
+    graph: on CUDA, one iteration (halo exchange, five library kernels, two all-reduces) is recorded once as a CUDA
+    graph -- NCCL's sends, receives and all-reduces included -- and replayed; issued call by call from Python an
+    iteration costs ~1.8 ms of launch and binding latency whatever the strip size, which is what capped the scaling."""
     distributed = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
@@ -182,7 +190,7 @@ def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None
         ops.cg_direction(r0, r1, True, rz, rz, Z, P)
         if float(bb.max()) == 0.0:
             return X, 0, {'iterations': 0, 'max_rel_residual': 0.0, 'rows_per_rank': [], 'halo_rows': halo_rows, 'halo_bytes_per_iteration': 0}
-        while it < max_iter:
+        def iteration():
             exchange(P)
             ops.spmm_rows(r0, r1, P, AP)
             ops.cg_dots(r0, r1, P, AP, pAp)
@@ -191,6 +199,28 @@ def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None
             allreduce(red)
             ops.cg_direction(r0, r1, False, rz, red, Z, P)          # red[:s] = new r.z
             rz.copy_(red[:s])
+
+        replay = None
+        if graph and dev.type == 'cuda' and hasattr(ops, 'set_stream') and max_iter > 8:
+            for _ in range(3):                                      # eager iterations: communicators and work buffers exist
+                iteration()
+                it += 1
+            torch.cuda.synchronize(dev)
+            cs = torch.cuda.Stream(device=dev)
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            ops.set_stream(cs)                                      # the library records into the capture stream
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g, stream=cs):
+                    iteration()
+                replay = g.replay
+            finally:
+                ops.set_stream(torch.cuda.current_stream(dev))
+        while it < max_iter:
+            if replay is not None:
+                replay()
+            else:
+                iteration()
             it += 1
             if (it % check_every == 0 or it == max_iter) and converged(red[s:], bb):
                 break
