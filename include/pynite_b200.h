@@ -194,6 +194,9 @@ PN_EXPORT int pn_node_row_starts(pn_ctx *ctx, int64_t *row_start);
 /* Y[row0:row1] = K11[row0:row1, :] X                                                                            */
 PN_EXPORT int pn_dev_spmm_k11_rows(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, const double *X_dev, double *Y_dev);
 /* node-block (<= 6x6) Jacobi preconditioner of K11: setup once per assembly, then Z[rows of nodes node0..node1) = Minv R */
+/* Columns [lo, hi) referenced by rows [row0, row1) of K11: the halo a domain-decomposed strip needs (computed on the
+ * device; the pattern of a 6 M-DOF model is 0.5 GB and does not have to visit the host for this). */
+PN_EXPORT int pn_k11_col_range(pn_ctx *ctx, int64_t row0, int64_t row1, int64_t *lo, int64_t *hi);
 PN_EXPORT int pn_dev_block_jacobi_setup(pn_ctx *ctx);
 PN_EXPORT int pn_dev_block_jacobi_nodes(pn_ctx *ctx, int32_t s, int64_t node0, int64_t node1, const double *R_dev, double *Z_dev);
 /* fused CG vector kernels on a strip; the per-column scalars (rz, pAp, ...) are DEVICE arrays of s doubles so the caller

@@ -957,6 +957,36 @@ int pn_dev_spmm_k11_rows(pn_ctx *ctx, int32_t s, int64_t row0, int64_t row1, con
     PN_API_END
 }
 
+// smallest / largest column referenced by rows [row0, row1) of K11 (rows are sorted: first and last entry of each row)
+__global__ void k_row_col_range(int64_t row0, int64_t row1, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                int32_t *__restrict__ lohi) {
+    int64_t r = row0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= row1) return;
+    const int32_t a = indptr[r], b = indptr[r + 1];
+    if (b > a) {
+        atomicMin(lohi, indices[a]);
+        atomicMax(lohi + 1, indices[b - 1]);
+    }
+}
+
+int pn_k11_col_range(pn_ctx *ctx, int64_t row0, int64_t row1, int64_t *lo, int64_t *hi) {
+    PN_API_BEGIN(ctx)
+    if (!c->symbolic_ready || row0 < 0 || row1 > c->n1 || row0 > row1 || !lo || !hi) throw ArgError("pn_k11_col_range: bad argument");
+    const CsrBlock &A = c->blk[0];
+    DevBuf<int32_t> lohi;
+    int32_t h[2] = {INT32_MAX, -1};
+    lohi.upload(h, 2, c->stream);
+    if (row1 > row0) {
+        k_row_col_range<<<grid_for(row1 - row0, 256), 256, 0, c->stream>>>(row0, row1, A.indptr.ptr, A.indices.ptr, lohi.ptr);
+        c->count_launch();
+    }
+    PN_CUDA(cudaMemcpyAsync(h, lohi.ptr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    if (h[1] < 0) { *lo = row0; *hi = row1; }       // empty strip
+    else { *lo = h[0]; *hi = (int64_t)h[1] + 1; }
+    PN_API_END
+}
+
 int pn_dev_block_jacobi_setup(pn_ctx *ctx) {
     PN_API_BEGIN(ctx)
     if (!c->vals_ready) throw ArgError("pn_dev_block_jacobi_setup: call pn_assemble_ke first");

@@ -76,6 +76,10 @@ class EngineOps:
         indptr, indices, _ = self.eng.block(0, values=False)
         return indptr, indices
 
+    def col_range(self, row0, row1):
+        """Columns [lo, hi) a strip references, computed on the device."""
+        return self.eng.k11_col_range(row0, row1)
+
     def rhs(self, combo0, s):
         B = torch.empty((self.n1, s), dtype=torch.float64, device=self.device)
         self.eng.dev_get_rhs(combo0, s, B.data_ptr())
@@ -102,7 +106,7 @@ class EngineOps:
         self.eng.dev_cg_direction(Z.shape[1], row0, row1, first, rz.data_ptr(), rz_new.data_ptr(), Z.data_ptr(), P.data_ptr())
 
 
-def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None, log=None, graph=True):
+def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None, log=None, graph=True, profile=None):
     """Solves K11 X = B for combos [combo0, combo0 + s) on all ranks of `group`; returns (X on every rank, iterations,
     max relative residual).  Works without torch.distributed initialised (world size 1).
 
@@ -121,10 +125,13 @@ def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None
     dev = ops.device
 
     # columns my strip references -> halo plan
-    indptr, indices = ops.pattern()
-    mine = indices[indptr[r0]:indptr[r1]]
-    lo = int(mine.min()) if mine.size else r0
-    hi = int(mine.max()) + 1 if mine.size else r1
+    if hasattr(ops, 'col_range'):
+        lo, hi = ops.col_range(r0, r1)
+    else:
+        indptr, indices = ops.pattern()
+        mine = indices[indptr[r0]:indptr[r1]]
+        lo = int(mine.min()) if mine.size else r0
+        hi = int(mine.max()) + 1 if mine.size else r1
     if distributed:
         t = torch.tensor([lo, hi], dtype=torch.int64, device=dev)
         allt = [torch.empty_like(t) for _ in range(world)]
@@ -178,6 +185,10 @@ def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None
             stalled += 1
         return stalled >= 8
 
+    ev0 = ev1 = None
+    if dev.type == 'cuda':
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     if fused:
         # five library kernels, one halo exchange and two all-reduces per iteration; no host round trip in between
         rz = torch.zeros(s, dtype=torch.float64, device=dev)
@@ -249,6 +260,36 @@ def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None
             it += 1
             if (it % check_every == 0 or it == max_iter) and converged(rr, bb):
                 break
+    ms_loop = None
+    if ev0 is not None:
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        ms_loop = ev0.elapsed_time(ev1)
+    if profile is not None and fused and dev.type == 'cuda':
+        # diagnostic: the real closures of this solve, 50 repetitions each (the iterates are garbage afterwards: copies)
+        keep = [t.clone() for t in (X, R, Z, P, AP, rz, pAp, red)]
+
+        def timed(fn, reps=50):
+            fn()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([a.elapsed_time(b)/reps], dtype=torch.float64, device=dev)
+            allreduce_max = t.clone()
+            if distributed:
+                dist.all_reduce(allreduce_max, op=dist.ReduceOp.MAX, group=group)
+            return round(float(allreduce_max.item()), 4)
+
+        profile['exchange'] = timed(lambda: exchange(P))
+        profile['iteration_eager'] = timed(iteration)
+        if replay is not None:
+            profile['iteration_graph'] = timed(replay)
+        for t, k in zip((X, R, Z, P, AP, rz, pAp, red), keep):
+            t.copy_(k)
     # every rank ends up with the whole solution: all-gather of the strips (ragged -> padded)
     if distributed:
         hmax = max(row_cuts[q + 1] - row_cuts[q] for q in range(world))
@@ -259,5 +300,5 @@ def solve(ops, combo0, s, tol=1e-10, max_iter=200000, check_every=25, group=None
         for q in range(world):
             X[row_cuts[q]:row_cuts[q + 1]] = parts[q][:row_cuts[q + 1] - row_cuts[q]]
     info = {'iterations': it, 'max_rel_residual': worst, 'rows_per_rank': [row_cuts[q + 1] - row_cuts[q] for q in range(world)],
-            'halo_rows': halo_rows, 'halo_bytes_per_iteration': halo_rows*s*8}
+            'halo_rows': halo_rows, 'halo_bytes_per_iteration': halo_rows*s*8, 'ms_iteration_loop': ms_loop}
     return X, it, info

@@ -115,6 +115,7 @@ SIGNATURES = {
     'pn_set_stream': (ct.c_int, [_P, ct.c_void_p, ct.c_int]),
     'pn_node_row_starts': (ct.c_int, [_P, ct.POINTER(ct.c_int64)]),
     'pn_prefetch_analysis': (ct.c_int, [_P]),
+    'pn_k11_col_range': (ct.c_int, [_P, ct.c_int64, ct.c_int64, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64)]),
     'pn_set_option': (ct.c_int, [_P, ct.c_char_p, ct.c_int64]),
     'pn_dev_spmm_k11_rows': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
     'pn_dev_block_jacobi_setup': (ct.c_int, [_P]),
@@ -228,6 +229,11 @@ class Engine:
                        PN_QUAD: len(A.quad_ijmn), PN_PLATE: len(A.plate_ijmn)}
         # the model is complete: the ordering of the direct solver can start on a host worker thread
         self._check(L.pn_prefetch_analysis(self._h))
+
+    def k11_col_range(self, row0, row1):
+        lo, hi = ct.c_int64(0), ct.c_int64(0)
+        self._check(self._lib.pn_k11_col_range(self._h, row0, row1, ct.byref(lo), ct.byref(hi)))
+        return lo.value, hi.value
 
     def set_option(self, name, value):
         self._check(self._lib.pn_set_option(self._h, name.encode(), int(value)))

@@ -23,6 +23,8 @@ ap.add_argument('--tol', type=float, default=1e-8)
 ap.add_argument('--max-iter', type=int, default=20000)
 ap.add_argument('--ks', type=float, default=0.1)
 ap.add_argument('--check', action='store_true')
+ap.add_argument('--no-graph', action='store_true', help='issue every iteration call by call instead of replaying a CUDA graph')
+ap.add_argument('--profile', action='store_true', help='time the pieces of one iteration separately (100 repetitions each)')
 args = ap.parse_args()
 
 local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -47,7 +49,8 @@ if world > 1:
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 hist = []
 e0.record()
-X, it, info = ddpcg.solve(ops, 0, args.combos, tol=args.tol, max_iter=args.max_iter, check_every=50,
+prof_solve = {} if args.profile else None
+X, it, info = ddpcg.solve(ops, 0, args.combos, tol=args.tol, max_iter=args.max_iter, check_every=50, profile=prof_solve, graph=not args.no_graph,
                           log=(lambda k, w: hist.append((k, w))) if rank == 0 else None)
 e1.record()
 torch.cuda.synchronize()
@@ -58,14 +61,52 @@ if world > 1:
     ms = float(t.item())
 ops.set_solution(0, X)
 out = {'config': f'{args.n}x{args.n} quad mat on springs ks={args.ks}', 'n_gpus': world, 'n_dof': int(sizes.n_dof), 'n1': int(sizes.n1),
-       'nnz11': int(sizes.nnz11), 'combos': args.combos, 'iterations': it, 'ms_total': ms, 'ms_per_iteration': ms/max(it, 1),
+       'nnz11': int(sizes.nnz11), 'combos': args.combos, 'iterations': it, 'ms_total': ms, 'ms_iteration_loop': info.get('ms_iteration_loop'),
+       'ms_per_iteration': (info.get('ms_iteration_loop') or ms)/max(it, 1),
        'max_rel_residual': info['max_rel_residual'], 'rows_per_rank': info['rows_per_rank'],
        'halo_bytes_per_iteration_rank0': info['halo_bytes_per_iteration'],
-       'spmm_algorithmic_GBps_per_rank': ((sizes.nnz11*12 + 2*sizes.n1*args.combos*8)/world)/(ms/max(it, 1)*1e-3)/1e9,
+       'spmm_algorithmic_GBps_per_rank': ((sizes.nnz11*12 + 2*sizes.n1*args.combos*8)/world)/((info.get('ms_iteration_loop') or ms)/max(it, 1)*1e-3)/1e9,
        'residual_history_tail': hist[-3:]}
 if args.check:
     D = eng.displacements(0)
     out['max_rel_diff_vs_direct_combo0'] = float(np.abs(D - D_direct[0]).max()/np.abs(D_direct[0]).max())
+if args.profile:
+    # the pieces of one iteration on this rank's strip, each repeated 100 times between two events (max over ranks)
+    nrs = ops.node_row_start
+    ncut = ddpcg.strip_cuts(nrs, world)
+    node0, node1 = ncut[rank], ncut[rank + 1]
+    r0, r1 = int(nrs[node0]), int(nrs[node1])
+    sN = args.combos
+    dev = ops.device
+    Pv = torch.randn((ops.n1, sN), dtype=torch.float64, device=dev)
+    APv, Xv, Rv, Zv = (torch.zeros_like(Pv) for _ in range(4))
+    rz = torch.ones(sN, dtype=torch.float64, device=dev)
+    pAp = torch.ones(sN, dtype=torch.float64, device=dev)
+    red = torch.ones(2*sN, dtype=torch.float64, device=dev)
+
+    def timed(fn, reps=100):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)/reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return round(float(t.item()), 4)
+
+    out['profile_solve_ms'] = prof_solve
+    out['profile_ms'] = {
+        'spmm_rows': timed(lambda: ops.spmm_rows(r0, r1, Pv, APv)),
+        'cg_dots': timed(lambda: ops.cg_dots(r0, r1, Pv, APv, pAp)),
+        'cg_update': timed(lambda: ops.cg_update(node0, node1, False, rz, pAp, Pv, APv, Xv, Rv, Zv, red)),
+        'cg_direction': timed(lambda: ops.cg_direction(r0, r1, False, rz, red, Zv, Pv)),
+        'allreduce_x2': timed(lambda: (dist.all_reduce(pAp), dist.all_reduce(red))) if world > 1 else 0.0,
+    }
 if rank == 0:
     print(json.dumps(out), flush=True)
 eng.set_stream(None)
