@@ -688,8 +688,8 @@ __global__ void k_lu_transpose_panel(int first, int kb, const FrontDev *__restri
 //   (b) F[r0:ge, ge:n]  -= L[r0:ge, kb:r0] U[kb:r0, ge:n]
 // grid = (front, tile); tiles enumerate region (a) row-major, then region (b).
 __global__ void __launch_bounds__(256, 2)
-k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym) {
-    FrontDev F = fronts[first + blockIdx.x];
+k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym, int front_on_x) {
+    FrontDev F = fronts[first + (front_on_x ? blockIdx.x : blockIdx.y)];
     const int ge = min(g0 + GB, F.ns);
     const int r0 = kb + NB;
     if (r0 >= ge) return;
@@ -699,7 +699,7 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
     const int ta_n = (wa + BN - 1) / BN, ta_m = (ha + BM - 1) / BM;
     const int hb = ge - r0, wb = n - ge;
     const int tb_n = (wb + BN - 1) / BN, tb_m = (hb + BM - 1) / BM;
-    int t = blockIdx.y;
+    int t = front_on_x ? blockIdx.y : blockIdx.x;
     const double *Lp = A + (int64_t)r0 * n + kb;        // L[r0:, kb:r0]
     if (t < ta_m * ta_n) {
         if (sym && (t / ta_n + 1) * BM <= (t % ta_n) * BN) return;      // tile strictly above the diagonal
@@ -1710,7 +1710,7 @@ static void factorise(Ctx *c, const double *vals11) {
                             int wa = gend - kb - NB;       // strips inside the group
                             int tiles = ((rest + BM - 1) / BM) * ((wa + BN - 1) / BN) + ((wa + BM - 1) / BM) * tiles_u;
                             lp.begin(5);
-                            { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_strip<<<dim3(nf_, tiles), 256, GEMM_SMEM, sq>>>(f0_, kb, g0, d.fronts.ptr, arena, sym); }
+                            { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_strip<<<nf_ <= 65535 ? dim3(tiles, nf_) : dim3(nf_, tiles), 256, GEMM_SMEM, sq>>>(f0_, kb, g0, d.fronts.ptr, arena, sym, nf_ <= 65535 ? 0 : 1); }
                             lp.end();
                             c->count_launch();
                         }
