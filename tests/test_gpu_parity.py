@@ -218,6 +218,26 @@ def test_compact_reaction_download_matches_oracle(eng):
         assert np.all(R[c][sup == 0] == 0.0)
 
 
+def test_sweeps_with_odd_right_hand_side_counts(eng):
+    """The shared-memory and left-looking sweep kernels work on 8-, 16- and 32-column chunks: column counts that are
+    not multiples of the chunk (1, 3, 17, 33) on a model with several elimination levels, against the oracle."""
+    from pynite_b200 import synthetic
+    import copy
+    A = synthetic.quad_plate_arrays(n=40, n_combos=33)
+    _upload(eng, A)
+    picks = [0, 2, 16, 32]                      # the oracle solves these four combos only (it is a per-combo Python loop)
+    A4 = copy.copy(A)
+    A4.factors = A.factors[picks]
+    Do, _ = om.solve_linear(A4)
+    for k in (1, 3, 17, 33):
+        eng.set_combos(A.factors[:k])
+        D, _, st = eng.solve_linear(eng.make_opts(), reactions=False)
+        assert D.shape[0] == k
+        for q, c in enumerate(picks):
+            if c < k:
+                assert rel_err(D[c], Do[q].reshape(-1)) < TOL_D
+
+
 def test_assembly_graph_equals_launch_by_launch(eng):
     """The numeric class / recipe assembly replayed as one CUDA graph writes the same bits as the individual launches
     and as the general path (first assembly of a pattern)."""
