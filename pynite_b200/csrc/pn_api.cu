@@ -394,7 +394,6 @@ int pn_set_nodes(pn_ctx *ctx, int64_t n_nodes, const double *xyz, const uint8_t 
     host_copy(m.h_xyz, xyz, (int64_t)(3 * n_nodes));
     host_copy(m.h_support, support_mask, (int64_t)(n_nodes));
     host_copy(m.h_enf_mask, enforced_mask, (int64_t)(n_nodes));
-    host_copy(m.h_enf_val, enforced_val, (int64_t)(6 * n_nodes));
     host_copy(m.h_nspring_k, spring_k, (int64_t)(6 * n_nodes));
     host_copy(m.h_nspring_flag, spring_flag, (int64_t)(6 * n_nodes));
     PN_CUDA(cudaStreamSynchronize(st));

@@ -97,7 +97,7 @@ struct Model {
     DevBuf<double> quad_props, plate_props;
     // host copies needed by host-side logic
     std::vector<uint8_t> h_support, h_enf_mask, h_nspring_flag, h_spring_active, h_mem_active;
-    std::vector<double> h_enf_val, h_nspring_k, h_xyz;
+    std::vector<double> h_nspring_k, h_xyz;        // (enforced values are only needed on the device)
     std::vector<int32_t> h_spring_ij, h_mem_ij, h_quad_ijmn, h_plate_ijmn;
     std::vector<double> h_spring_ks, h_mem_props, h_mem_rot, h_quad_props, h_plate_props;
     std::vector<uint16_t> h_mem_rel;
