@@ -611,6 +611,42 @@ __global__ void k_build_rhs(int64_t n1, int s, int n_case, const int32_t *__rest
     B[t] = acc - (kd2_percol ? kd2[t] : kd2[i]);
 }
 
+// Same arithmetic (fma over the cases in ascending order: bit-identical), eight combinations per thread: the case
+// vector entries G[cs][d] are loaded once per eight outputs and the factor table sits in shared memory as [case][combo]
+// (the one-output-per-thread kernel above issued 16 loads per output and ran at 4 % of the HBM rate of its 0.9 GB).
+constexpr int RHS_JB = 8;
+__global__ void __launch_bounds__(256)
+k_build_rhs8(int64_t n1, int s, int n_case, const int32_t *__restrict__ d1, const double *__restrict__ G, int64_t n_dof,
+             const double *__restrict__ fac, const double *__restrict__ kd2, int kd2_percol, double *__restrict__ B) {
+    extern __shared__ double s_fac[];                      // [n_case][s]
+    for (int e = threadIdx.x; e < s * n_case; e += blockDim.x) {
+        const int j = e / n_case, cs = e - j * n_case;
+        s_fac[cs * s + j] = fac[e];
+    }
+    __syncthreads();
+    const int groups = (s + RHS_JB - 1) / RHS_JB;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n1 * groups) return;
+    const int64_t i = t / groups;
+    const int jj = (int)(t - i * groups);                  // this thread's combinations: jj, jj + groups, jj + 2 groups, ...
+    const int64_t d = d1[i];                               // (consecutive threads write consecutive columns of B)
+    double acc[RHS_JB];
+#pragma unroll
+    for (int q = 0; q < RHS_JB; ++q) acc[q] = 0.0;
+    for (int cs = 0; cs < n_case; ++cs) {
+        const double g = G[(int64_t)cs * n_dof + d];
+        const double *f = s_fac + cs * s + jj;
+#pragma unroll
+        for (int q = 0; q < RHS_JB; ++q)
+            if (jj + q * groups < s) acc[q] = fma(f[q * groups], g, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < RHS_JB; ++q) {
+        const int j = jj + q * groups;
+        if (j < s) B[i * s + j] = acc[q] - (kd2_percol ? kd2[i * s + j] : kd2[i]);
+    }
+}
+
 // kd2_percol: optional [n1][s] array of per-combo K12 D2 products (P-Delta second step); null = use
 // the elastic K12 for every combo.
 void build_rhs(Ctx *c, int32_t combo0, int s, const double *kd2_percol) {
@@ -622,10 +658,20 @@ void build_rhs(Ctx *c, int32_t combo0, int s, const double *kd2_percol) {
     c->kd2.zero(st);
     if (c->n1 == 0 || s == 0) return;
     if (!kd2_percol && c->n2) spmv_plain(c, c->blk[1], c->blk[1].vals.ptr, c->d2_val.ptr, c->kd2.ptr, st);
-    { ProfScope ps_(c, PS_RHS); k_build_rhs<<<grid_for(c->n1 * s, 256), 256, 0, st>>>(c->n1, s, ld.n_case, c->d1.ptr, ld.Gcase.ptr, c->n_dof,
-                                                            ld.factors.ptr + (int64_t)combo0 * ld.n_case,
-                                                            kd2_percol ? kd2_percol : c->kd2.ptr, kd2_percol ? 1 : 0,
-                                                            c->B.ptr); }
+    {
+        ProfScope ps_(c, PS_RHS);
+        const size_t fac_smem = (size_t)s * std::max(ld.n_case, 1) * sizeof(double);
+        if (fac_smem <= 40 * 1024) {
+            const int64_t work = c->n1 * ((s + RHS_JB - 1) / RHS_JB);
+            k_build_rhs8<<<grid_for(work, 256), 256, fac_smem, st>>>(c->n1, s, ld.n_case, c->d1.ptr, ld.Gcase.ptr, c->n_dof,
+                                                                     ld.factors.ptr + (int64_t)combo0 * ld.n_case,
+                                                                     kd2_percol ? kd2_percol : c->kd2.ptr, kd2_percol ? 1 : 0, c->B.ptr);
+        } else {
+            k_build_rhs<<<grid_for(c->n1 * s, 256), 256, 0, st>>>(c->n1, s, ld.n_case, c->d1.ptr, ld.Gcase.ptr, c->n_dof,
+                                                                  ld.factors.ptr + (int64_t)combo0 * ld.n_case,
+                                                                  kd2_percol ? kd2_percol : c->kd2.ptr, kd2_percol ? 1 : 0, c->B.ptr);
+        }
+    }
     c->count_launch();
 }
 
@@ -639,10 +685,43 @@ __global__ void k_merge(int64_t n_dof, int s, const int32_t *__restrict__ newidx
     int32_t ni = newidx[d];
     D[t] = ni >= 0 ? X[(int64_t)ni * s + j] : d2_val[-1 - ni];
 }
+// The same copy as a tiled transpose: X is [n1][s] (combination fastest), D is [s][n_dof] (DOF fastest); a block moves
+// 32 DOFs x 32 combinations through shared memory so that both sides are accessed in 256-byte runs (the direct kernel
+// above read X with a stride of s doubles: 1.9 ms for 1.5 GB at config 3).
+__global__ void __launch_bounds__(256)
+k_merge_tiled(int64_t n_dof, int s, const int32_t *__restrict__ newidx, const double *__restrict__ X,
+              const double *__restrict__ d2_val, double *__restrict__ D) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+    const int64_t d0 = (int64_t)blockIdx.x * 32;
+    for (int c0 = 0; c0 < s; c0 += 32) {
+        for (int dd = ty; dd < 32; dd += 8) {
+            const int64_t d = d0 + dd;
+            double v = 0.0;
+            if (d < n_dof && c0 + tx < s) {
+                const int32_t ni = newidx[d];
+                v = ni >= 0 ? X[(int64_t)ni * s + c0 + tx] : d2_val[-1 - ni];
+            }
+            tile[dd][tx] = v;
+        }
+        __syncthreads();
+        for (int jj = ty; jj < 32; jj += 8) {
+            const int j = c0 + jj;
+            if (j < s && d0 + tx < n_dof) D[(int64_t)j * n_dof + d0 + tx] = tile[tx][jj];
+        }
+        __syncthreads();
+    }
+}
+
 void merge_displacements(Ctx *c, int32_t combo0, int s) {
     if (!c->n_dof || !s) return;
-    { ProfScope ps_(c, PS_MERGE); k_merge<<<grid_for(c->n_dof * s, 256), 256, 0, c->stream>>>(c->n_dof, s, c->newidx.ptr, c->X.ptr, c->d2_val.ptr,
-                                                                 c->D_all.ptr + (int64_t)combo0 * c->n_dof); }
+    { ProfScope ps_(c, PS_MERGE);
+      if (s >= 8)
+          k_merge_tiled<<<grid_for(c->n_dof, 32), 256, 0, c->stream>>>(c->n_dof, s, c->newidx.ptr, c->X.ptr, c->d2_val.ptr,
+                                                                        c->D_all.ptr + (int64_t)combo0 * c->n_dof);
+      else
+          k_merge<<<grid_for(c->n_dof * s, 256), 256, 0, c->stream>>>(c->n_dof, s, c->newidx.ptr, c->X.ptr, c->d2_val.ptr,
+                                                                     c->D_all.ptr + (int64_t)combo0 * c->n_dof); }
     c->count_launch();
 }
 
