@@ -1797,8 +1797,9 @@ static void solve_inplace(Ctx *c, double *X, int s) {
     double *Y = d.yarena.ptr;
     int gz = (s + BN - 1) / BN;
     static const bool debug_levels = getenv("PN_DEBUG_LEVELS") != nullptr;
-    static const bool no_sm_sweeps = getenv("PN_NO_SMEM_SWEEPS") != nullptr;
-    static const bool no_ll_sweeps = getenv("PN_NO_LL_SWEEPS") != nullptr;
+    // (read on every call: the parity tests switch kernel families inside one process)
+    const bool no_sm_sweeps = getenv("PN_NO_SMEM_SWEEPS") != nullptr;
+    const bool no_ll_sweeps = getenv("PN_NO_LL_SWEEPS") != nullptr;
     const bool use_ll = !no_ll_sweeps && s <= 32 * LL_MAX_CHUNKS;
     cudaEvent_t dbg[64];
     if (debug_levels) for (int i = 0; i < 64; ++i) cudaEventCreate(&dbg[i]);

@@ -229,13 +229,22 @@ def test_sweeps_with_odd_right_hand_side_counts(eng):
     A4 = copy.copy(A)
     A4.factors = A.factors[picks]
     Do, _ = om.solve_linear(A4)
-    for k in (1, 3, 17, 33):
-        eng.set_combos(A.factors[:k])
-        D, _, st = eng.solve_linear(eng.make_opts(), reactions=False)
-        assert D.shape[0] == k
-        for q, c in enumerate(picks):
-            if c < k:
-                assert rel_err(D[c], Do[q].reshape(-1)) < TOL_D
+    import os
+    # three kernel families: shared-memory-resident sweeps (default for these front sizes), the left-looking persistent
+    # kernel on every level (what the large levels of a big model use), and the per-step GEMM fallback
+    for env in ({}, {'PN_NO_SMEM_SWEEPS': '1'}, {'PN_NO_SMEM_SWEEPS': '1', 'PN_NO_LL_SWEEPS': '1'}):
+        os.environ.update(env)
+        try:
+            for k in (1, 3, 17, 33):
+                eng.set_combos(A.factors[:k])
+                D, _, st = eng.solve_linear(eng.make_opts(), reactions=False)
+                assert D.shape[0] == k
+                for q, c in enumerate(picks):
+                    if c < k:
+                        assert rel_err(D[c], Do[q].reshape(-1)) < TOL_D, (env, k, c)
+        finally:
+            for name in env:
+                os.environ.pop(name, None)
 
 
 def test_assembly_graph_equals_launch_by_launch(eng):
