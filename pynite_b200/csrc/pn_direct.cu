@@ -1403,6 +1403,7 @@ void direct_prefetch(Ctx *c) {
     d.host_state = 1;
     const int wt = omp_get_max_threads();
     d.host_future = std::async(std::launch::async, [c, wt]() {
+        cudaSetDevice(c->device);          // the page-locked index lists are allocated from this thread
         omp_set_num_threads(wt);
         const Model &mm = c->model;
         const int64_t n_dof = 6 * mm.n_nodes;
