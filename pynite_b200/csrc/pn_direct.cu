@@ -1,26 +1,30 @@
 // Sparse direct solver for K11 X = B: multifrontal LU without pivoting on a symmetric pattern.
 //
-//   ordering / fronts : pn_direct_symbolic.cpp (nested dissection of the node graph by coordinates)
+//   ordering / fronts : pn_direct_symbolic.cpp (nested dissection of the node graph by coordinates), on a worker
+//                       thread from the moment the model arrays are set (direct_prefetch)
 //   numeric           : level by level up the separator tree; every front is a dense row-major
 //                       (ns+nb)^2 matrix in a per-level arena.  Right-looking partial LU in block
-//                       steps of NB = 64 pivots:
-//                         diag    one CTA factorises the NB x NB diagonal block in shared memory and
-//                                 inverts its two triangles (Linv, Uinv)
-//                         panels  U[k, rest] = Linv * F[k, rest],  L[rest, k] = F[rest, k] * Uinv   (GEMMs)
-//                         update  F[rest, rest] -= L[rest, k] * U[k, rest]                         (GEMM, rank NB)
-//                       All three GEMM shapes run through one FP64 register-tiled kernel body
-//                       (gemm_tile: 128 x 64 output tile per CTA, 8 x 4 outputs per thread, whole
-//                       K-chunk of 64 staged in 97 KB of shared memory, 2 CTAs per SM).
+//                       steps of NB = 64 pivots, grouped GB = 256 pivots at a time:
+//                         diag    k_lu_diag: LU of the NB x NB diagonal block + inverses of its triangles (Linv, Uinv)
+//                         panels  k_lu_panels: L[rest, k] = F[rest, k] Uinv (GEMM); in symmetric mode the same
+//                                 kernel writes the row panel U = D L^T, U12 and the pre-multiplied permanent panel
+//                                 from its accumulators; general mode: U[k, rest] = Linv F[k, rest] as a second GEMM
+//                         strip   k_lu_strip: rank-NB update of what the rest of the group needs
+//                         update  k_lu_update: F[rest, rest] -= L[rest, group] U[group, rest], once per group
+//                       All GEMM shapes run through gemm_tile (128 x 64 tile per CTA, DMMA.8x8x4, cp.async ring).
 //                       The trailing nb x nb block is the update matrix, extend-added into the
-//                       parent in a fixed child order (deterministic, no atomics).
-//   stored factor     : so that the solves are pure GEMMs with ONE launch per block step, the
-//                       permanent panels are pre-multiplied by the diagonal-block inverses:
+//                       parent in a fixed child order (deterministic, no atomics).  Levels with few fronts are cut
+//                       into groups of fronts on side streams.
+//   stored factor     : the permanent panels are pre-multiplied by the diagonal-block inverses:
 //                         Lp[r, k] = L[r, k] * Linv_kk  (r below block k),  Lp[r, k] = U[r, k] * Uinv_kk (r above)
 //                       With y_k = Linv_kk b_k the forward update b_r -= L[r,k] y_k equals
 //                       b_r -= Lp[r,k] b_k, i.e. it reads the *old* b_k and can run concurrently with
 //                       the diagonal solve; likewise backwards with Uinv.
 //   solve             : all right-hand sides at once; forward sweep passes update vectors up the
-//                       tree like the update matrices, backward sweep reads ancestors' results.
+//                       tree like the update matrices, backward sweep reads ancestors' results.  Per level one of
+//                         k_front_forward_sm / k_front_backward_sm  (front's right-hand-side block resident in shared memory),
+//                         k_ll_sweep                                 (left-looking persistent kernel with per-block flags),
+//                         k_solve_step + gather / extend-add / store (per-step GEMM launches: fallback, > 256 columns).
 //
 // LU (not Cholesky) because the reference's K is not exactly symmetric: B^T H B is summed in a fixed
 // order per element and the orthotropic membrane matrix is unsymmetric when kx_mod != ky_mod
