@@ -23,12 +23,14 @@ void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xy
     vstart.clear();
     coords.clear();
     int32_t nv = 0;
+    int64_t n1 = 0;
     for (int64_t nd = 0; nd < n_nodes; ++nd) {
         int32_t first = -1, cnt = 0;
         for (int k = 0; k < 6; ++k) {
             int32_t ni = newidx[6 * nd + k];
             if (ni >= 0) { if (first < 0) first = ni; ++cnt; }
         }
+        n1 += cnt;
         if (cnt) {
             vid[nd] = nv++;
             vstart.push_back(first);
@@ -36,11 +38,7 @@ void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xy
         }
     }
     // vstart needs an end sentinel: rows are contiguous and ascending over vertices
-    {
-        int64_t n1 = 0;
-        for (int64_t d = 0; d < 6 * n_nodes; ++d) if (newidx[d] >= 0) ++n1;
-        vstart.push_back((int32_t)n1);
-    }
+    vstart.push_back((int32_t)n1);
     // count, fill (with duplicates, in any order: atomics), then sort + unique per vertex
     std::vector<int64_t> &deg = sc.deg, &ptr = sc.ptr, &fill = sc.fill, &cnt = sc.cnt;
     std::vector<int32_t> &raw = sc.raw;
@@ -200,6 +198,7 @@ struct Builder {
             }
         }
         A.assign(verts.begin(), verts.begin() + mid);
+        if (par) { B.reserve(verts.size() - mid); S.reserve(4096); }
         for (size_t i = mid; i < verts.size(); ++i) {
             int32_t v = verts[i];
             bool touches = false;
