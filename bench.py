@@ -15,8 +15,16 @@ is reused across re-analyses of one topology).  `e2e` times the whole call seque
 through the C ABI with HOST buffers every step: upload of the SoA arrays, symbolic phase, assembly, solve,
 reactions, and the device->host copies of D and the reactions (pinned memory).
 
-Multi-GPU: load combinations are independent given K, so ranks own disjoint sets of 64 combos (weak scaling,
-no data-path collective; NCCL only for the barrier / max-over-ranks timing).
+Multi-GPU (`--gpus N`, one process per GPU under torchrun): BASELINE config 3 is "64 load combos sharded across
+1/2/4/8 GPUs", i.e. STRONG scaling -- the default: the 64 combinations are split across the ranks
+(`sharding.shard_combos`), every rank assembles and factorises K and solves its share; `value` = n_dof x 64 x steps
+/ max-over-ranks time.  `--scaling weak` gives every rank its own 64 combinations instead (N x the work).
+
+`--impl reference` and the in-arm `cpu_baseline` time the CPU restatement of the reference (oracle/, memoisation
+off: the reference recomputes every element) on a BOUNDED SAMPLE of the workload -- a smaller plate with 2 combos --
+and say so: the sample's real size is what `config` reports, `same_config` is false, and an extrapolation to
+config 3 (element phases linear in the element count, SuperLU with the exponent fitted from two sizes) is given
+separately and labelled as such.
 """
 import argparse
 import json
@@ -31,7 +39,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = 'assembly+solve throughput, 1.5M-DOF quad plate x 64 load combos per GPU'
+METRIC = 'assembly+solve throughput (DOF*combos/s), 1.5M-DOF quad plate x 64 load combos, 1/2/4/8 B200'
 UNIT = 'DOF*combos/s'
 
 
@@ -42,7 +50,8 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n', type=int, default=500, help='quads per side (500 = BASELINE config 3)')
-    ap.add_argument('--combos', type=int, default=64, help='load combinations per GPU')
+    ap.add_argument('--combos', type=int, default=64, help='load combinations: total (strong scaling) or per GPU (weak)')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--solver', default='direct', choices=['direct', 'pcg'])
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--cpu-n', type=int, default=96, help='quads per side of the CPU-baseline sample')
@@ -53,12 +62,24 @@ def parse_args():
 
 def workload_config(args, world):
     n = args.n
-    return {'workload': f'BASELINE config 3: {n}x{n} DKMQ quad plate, perimeter pinned, {args.combos} load combos per GPU',
-            'n_dof': 6*(n + 1)*(n + 1), 'n_quads': n*n, 'combos_per_gpu': args.combos,
-            'combos_total': args.combos*world, 'solver': args.solver,
-            'sharding': 'load combinations across GPUs, K assembled and factorised per GPU, no data-path collective',
+    total = args.combos if args.scaling == 'strong' else args.combos*world
+    per = [len(x) for x in combo_shards(args, world)]
+    return {'workload': f'BASELINE config 3: {n}x{n} DKMQ quad plate, perimeter pinned, {total} load combos in total',
+            'n_dof': 6*(n + 1)*(n + 1), 'n_quads': n*n, 'combos_total': total, 'combos_per_gpu': per, 'solver': args.solver,
+            'sharding': ('strong scaling: the combos are split across the GPUs; K is assembled and factorised on every GPU, '
+                         'no data-path collective' if args.scaling == 'strong' else
+                         'weak scaling: every GPU owns its own set of combos; no data-path collective'),
             'l2': 'inputs larger than L2 (CSR values 236 MB, factor 8.5 GB per step); no explicit flush',
             'symbolic': 'pattern / scatter map / elimination tree built once outside the timed region for `value`, inside for `e2e`'}
+
+
+def combo_shards(args, world):
+    """Combo indices owned by every rank.  strong: one table of `--combos` rows split with sharding.shard_combos;
+    weak: every rank has its own `--combos` rows."""
+    from pynite_b200 import sharding
+    if args.scaling == 'strong':
+        return [sharding.shard_combos(args.combos, r, world) for r in range(world)]
+    return [list(range(args.combos)) for _ in range(world)]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -66,60 +87,97 @@ def workload_config(args, world):
 # ---------------------------------------------------------------------------------------------
 def cpu_port_step(n, n_combos):
     """One pass of the reference algorithm (restated in oracle/) on an n x n quad plate with n_combos combos.
-    Returns (units, seconds, phase dict).  Phases are the ones BASELINE.md section 3 lists."""
+    Returns (units, seconds, phase dict).  Phases are the ones BASELINE.md section 3 lists.  The oracle's
+    memoisation is switched off: the reference evaluates every element and every element load separately."""
     from oracle import model as om
     from pynite_b200 import synthetic
     from scipy.sparse.linalg import spsolve
     A = synthetic.quad_plate_arrays(n=n, n_combos=n_combos)
     ph = {}
-    t0 = time.perf_counter()
-    K = om.ke_csr(A)
-    ph['Ke+tocsr'] = time.perf_counter() - t0
-    t = time.perf_counter()
-    d1, d2, D2 = om.partition_D(A)
-    K11, K12, _, _ = om.partition_matrix(K, d1, d2)
-    ph['partition'] = time.perf_counter() - t
-    ph['FER+P'] = ph['spsolve'] = ph['reactions'] = 0.0
-    for c in range(n_combos):
+    memo = om.MEMOISE
+    om.MEMOISE = False
+    try:
+        t0 = time.perf_counter()
+        K = om.ke_csr(A)
+        ph['Ke+tocsr'] = time.perf_counter() - t0
         t = time.perf_counter()
-        P, FER = om.load_vectors(A, c)
-        ph['FER+P'] += time.perf_counter() - t
-        t = time.perf_counter()
-        rhs = np.subtract(np.subtract(P[d1, :], FER[d1, :]), K12.tocsr() @ D2)
-        D1 = spsolve(K11.tocsr(), rhs)          # one full SuperLU factorisation per combo, as the reference does
-        ph['spsolve'] += time.perf_counter() - t
-        t = time.perf_counter()
-        D = om._merge(A, D1, D2, d1, d2)
-        om.reactions(A, c, D)
-        ph['reactions'] += time.perf_counter() - t
-    total = time.perf_counter() - t0
+        d1, d2, D2 = om.partition_D(A)
+        K11, K12, _, _ = om.partition_matrix(K, d1, d2)
+        ph['partition'] = time.perf_counter() - t
+        ph['FER+P'] = ph['spsolve'] = ph['reactions'] = 0.0
+        for c in range(n_combos):
+            t = time.perf_counter()
+            P, FER = om.load_vectors(A, c)
+            ph['FER+P'] += time.perf_counter() - t
+            t = time.perf_counter()
+            rhs = np.subtract(np.subtract(P[d1, :], FER[d1, :]), K12.tocsr() @ D2)
+            D1 = spsolve(K11.tocsr(), rhs)          # one full SuperLU factorisation per combo, as the reference does
+            ph['spsolve'] += time.perf_counter() - t
+            t = time.perf_counter()
+            D = om._merge(A, D1, D2, d1, d2)
+            om.reactions(A, c, D)
+            ph['reactions'] += time.perf_counter() - t
+        total = time.perf_counter() - t0
+    finally:
+        om.MEMOISE = memo
     return A.n_dof*n_combos, total, {k: round(v, 3) for k, v in ph.items()}
+
+
+def cpu_sample_n(args):
+    """Quads per side of the CPU sample, the same for `--impl reference` and for the in-arm `cpu_baseline`: one step
+    costs about 2.1e-3 n^2 seconds (2 combos, one host core); the `--steps/--warmup` run of the reference arm is kept
+    near two minutes."""
+    budget = 120.0/max(1, args.steps + 1)
+    return int(max(16, min(args.cpu_n, (budget/2.1e-3)**0.5)))
+
+
+def cpu_sample_record(n, combos, phases, seconds):
+    return (f'{n}x{n} quad plate ({6*(n + 1)**2} DOF, {n*n} quads) x {combos} combos per step, {seconds:.1f} s: oracle port of the '
+            f'reference (numpy element loops, scipy coo->csr, SuperLU spsolve per combo, reactions), one host core; '
+            f'phases of the last step (s): {phases}; host cores visible: {os.cpu_count()}')
+
+
+def extrapolate_to_config3(n, combos, phases, n_small, phases_small, target_n=500, target_combos=64):
+    """Config-3 time of the CPU path from the sample: element phases (Ke, FER, reactions, partition) scale with the
+    element count (and FER/reactions/spsolve with the combo count); SuperLU with the exponent fitted between the two
+    sample sizes.  An EXTRAPOLATION, labelled as such in the record."""
+    q, qs, qt = n*n, n_small*n_small, target_n*target_n
+    dof, dofs, doft = 6*(n + 1)**2, 6*(n_small + 1)**2, 6*(target_n + 1)**2
+    ps = max(phases_small['spsolve'], 1e-9)
+    expo = float(np.log(max(phases['spsolve'], 1e-9)/ps)/np.log(dof/dofs))
+    cs = target_combos/combos
+    t = (phases['Ke+tocsr'] + phases['partition'])*qt/q + (phases['FER+P'] + phases['reactions'])*qt/q*cs + \
+        phases['spsolve']*(doft/dof)**expo*cs
+    return {'value': doft*target_combos/t, 'unit': UNIT, 'seconds_per_step': t, 'spsolve_exponent_in_dof': expo,
+            'fitted_between': [f'{n_small}x{n_small}', f'{n}x{n}'], 'extrapolated': True,
+            'note': 'the reference itself cannot run config 3: _store_displacements / _calc_reactions are quadratic (SURVEY H4)'}
 
 
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's CPU implementation of the path.  /root/reference (pure Python) does
-    not exist on the GPU box, so this times the oracle port of it; every step is a bounded sample."""
+    not exist on the GPU box, so this times the oracle port of it; every step is a bounded sample, and the record
+    says which: `config` describes the SAMPLE that was timed, not config 3."""
     if rank != 0:
         return
-    cfg = workload_config(args, world)
-    # bounded sample: one step costs about 2.1e-3 * n^2 seconds (2 combos) on one host core; keep the whole
-    # --steps/--warmup run near two minutes
-    budget = 120.0/max(1, args.steps + min(args.warmup, 1))
-    args.cpu_n = int(max(16, min(args.cpu_n, (budget/2.1e-3)**0.5)))
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_port_step(max(8, args.cpu_n//4), 1)
+    n = cpu_sample_n(args)
+    n_small = max(12, n//2)
+    _, t_small, phases_small = cpu_port_step(n_small, args.cpu_combos)       # also the warm-up
     t_all, units = 0.0, 0
     phases = None
     for _ in range(args.steps):
-        u, t, phases = cpu_port_step(args.cpu_n, args.cpu_combos)
+        u, t, phases = cpu_port_step(n, args.cpu_combos)
         units += u
         t_all += t
     value = units/t_all
-    sample = (f'{args.cpu_n}x{args.cpu_n} quad plate ({6*(args.cpu_n + 1)**2} DOF) x {args.cpu_combos} combos per step: numpy element '
-              f'loops + scipy coo->csr + SuperLU spsolve per combo + reactions; phases of last step (s): {phases}')
+    sample = cpu_sample_record(n, args.cpu_combos, phases, t_all/args.steps)
+    cfg = {'workload': f'SAMPLE of BASELINE config 3: {n}x{n} DKMQ quad plate, perimeter pinned, {args.cpu_combos} load combos '
+                       f'(config 3 itself is 500x500 x 64 and does not finish on the CPU path)',
+           'n_dof': 6*(n + 1)**2, 'n_quads': n*n, 'combos_total': args.cpu_combos, 'sample': True,
+           'sample_of': workload_config(args, world)['workload']}
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3*t_all/args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'warmup': 1, 'ms_per_step': 1e3*t_all/args.steps, 'higher_is_better': True, 'scaling': args.scaling,
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'same_config': False, 'sample': True,
+            'extrapolated_config3': extrapolate_to_config3(n, args.cpu_combos, phases, n_small, phases_small),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -234,11 +292,19 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # every rank owns its own 64 combos of the same mesh (rank-specific factor table and point loads)
-    A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019 + rank)
+    shards = combo_shards(args, world)
+    if args.scaling == 'strong':
+        # one model, one table of --combos combinations; this rank solves rows shards[rank]
+        A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019)
+        A.factors = np.ascontiguousarray(A.factors[shards[rank]])
+        A.combo_names = [A.combo_names[i] for i in shards[rank]]
+    else:
+        # every rank owns its own --combos combinations of the same mesh (rank-specific factor table and point loads)
+        A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019 + rank)
+    my_combos = len(shards[rank])
     eng = Engine(local_rank)
     opts = eng.make_opts(solver=args.solver, check_stability=True, refine_steps=2, tol=1e-10, max_iter=500000)
-    units_per_step = A.n_dof*args.combos
+    units_per_step_all = A.n_dof*sum(len(x) for x in shards)      # whole job, all ranks
 
     # ---- device-resident arm -----------------------------------------------------------------
     eng.set_model(A)
@@ -288,12 +354,12 @@ def run_ours(args, rank, local_rank, world):
         if name in prof_asm and name not in prof:
             prof[name] = (prof_asm[name][0]*args.steps/5.0, prof_asm[name][1]*args.steps/5.0)
     ms = max_over_ranks(ms)
-    value = units_per_step*world*args.steps/(ms*1e-3)
+    value = units_per_step_all*args.steps/(ms*1e-3)
 
     # ---- end-to-end arm: host buffers in, host buffers out, everything inside the timed region ---
     n_dof = A.n_dof
-    D_host = torch.empty((args.combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
-    R_host = torch.empty((args.combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
+    D_host = torch.empty((my_combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
+    R_host = torch.empty((my_combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
     in_fields = ['xyz', 'support', 'enf_mask', 'enf_val', 'nspring_k', 'nspring_flag', 'quad_ijmn', 'quad_props', 'nl_dof',
                  'nl_case', 'nl_val', 'qp_elem', 'qp_case', 'qp_val', 'factors']
     # the step's inputs live in pinned host memory (same values, page-locked copies of the arrays the builder produced)
@@ -309,7 +375,7 @@ def run_ours(args, rank, local_rank, world):
     sup_bits = np.unpackbits(np.asarray(A.support, dtype=np.uint8).reshape(-1, 1), axis=1, bitorder='little')[:, :6].reshape(-1)
     nsf = np.asarray(A.nspring_flag, dtype=np.uint8).reshape(-1)
     n_rxn = int(np.count_nonzero((sup_bits != 0) | (((nsf & 1) != 0) & ((nsf & 2) != 0))))
-    rxn_bytes = n_rxn*args.combos*8 if n_rxn*8 < n_dof else R_host.nbytes
+    rxn_bytes = n_rxn*my_combos*8 if n_rxn*8 < n_dof else R_host.nbytes
     d2h = int(D_host.nbytes + rxn_bytes)
 
     e2e_phases = {}
@@ -336,7 +402,7 @@ def run_ours(args, rank, local_rank, world):
         e2e_step()
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = units_per_step*world*args.e2e_steps/t_e2e
+    e2e_value = units_per_step_all*args.e2e_steps/t_e2e
     e2e_stats = eng.stats().as_dict()
     checksum = float(np.abs(D_host).max())
 
@@ -374,7 +440,7 @@ def run_ours(args, rank, local_rank, world):
         rooflines['spmm(K11, %d rhs)' % srhs] = {'bound': 'hbm', 'achieved': a, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': a/hbm_peak,
                                                  'algorithmic_bytes': sb, 'ms': sms}
     if 'spmm' in prof:
-        s = args.combos
+        s = my_combos
         spmm_bytes = sizes.nnz11*12 + (sizes.n1 + 1)*4 + 2*sizes.n1*s*8
         kms, n = prof['spmm']
         a = spmm_bytes/(kms/n*1e-3)/1e9
@@ -392,9 +458,9 @@ def run_ours(args, rank, local_rank, world):
         kms = prof['solve_update'][0] + prof.get('solve_front_fused', (0.0, 0))[0]
         n = prof['solve_update'][1] + prof.get('solve_front_fused', (0.0, 0))[1]
         sweeps = 1 + st['iterations']/K          # the first solve plus the refinement corrections actually taken
-        fl = first_stats['solve_flops']*args.combos*sweeps
+        fl = first_stats['solve_flops']*my_combos*sweeps
         a = fl*K/(kms*1e-3)/1e12
-        rooflines['solve sweeps (solve_update + solve_front_fused, %d rhs)' % args.combos] = {
+        rooflines['solve sweeps (solve_update + solve_front_fused, %d rhs)' % my_combos] = {
             'bound': 'tensor', 'achieved': a, 'peak': f64_peak, 'unit': 'TFLOP/s', 'frac': a/f64_peak, 'flops_per_step': fl, 'ms': kms/K,
             'peak_source': 'cuBLAS DGEMM 4096^3 burst measured in this run'}
     dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
@@ -417,7 +483,7 @@ def run_ours(args, rank, local_rank, world):
         roof['peak_is'] = ('measured (' + hbm_src + ')') if roof['bound'] == 'hbm' else roof.get('peak_source')
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms/args.steps, 'ms_per_step_profiled_pass': ms_profiled/args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'ms_per_step': ms/args.steps, 'ms_per_step_profiled_pass': ms_profiled/args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(args, world),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': 1e3*t_e2e/args.e2e_steps, 'steps': args.e2e_steps, 'host_phases_ms_last_step': e2e_phases,
@@ -435,11 +501,10 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
-        u, t, phases = cpu_port_step(args.cpu_n, args.cpu_combos)
-        line['cpu_baseline'] = {'value': u/t, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-                                'sample': (f'{args.cpu_n}x{args.cpu_n} quad plate ({6*(args.cpu_n + 1)**2} DOF) x {args.cpu_combos} combos, {t:.1f} s: '
-                                           f'oracle port of the reference (numpy element loops, scipy coo->csr, SuperLU spsolve per combo, '
-                                           f'reactions); phases (s): {phases}; host cores visible: {os.cpu_count()}')}
+        n_cpu = cpu_sample_n(args)
+        u, t, phases = cpu_port_step(n_cpu, args.cpu_combos)
+        line['cpu_baseline'] = {'value': u/t, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample_is_config3': False,
+                                'sample': cpu_sample_record(n_cpu, args.cpu_combos, phases, t)}
     if rank == 0:
         print(json.dumps(line))
     eng.close()

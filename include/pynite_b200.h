@@ -48,7 +48,7 @@ enum pn_elem_kind { PN_SPRING = 1, PN_MEMBER = 2, PN_QUAD = 3, PN_PLATE = 4 };
                                           filter: FEModel3D.py:1859-1885); used by the P-Delta solve */
 
 /* solver selection for pn_solve_* */
-#define PN_SOLVER_DIRECT 0 /* sparse multifrontal LDL^T + FP64 iterative refinement                */
+#define PN_SOLVER_DIRECT 0 /* sparse multifrontal LU (no pivoting) + double-double refinement      */
 #define PN_SOLVER_PCG 1    /* node-block-Jacobi preconditioned CG, all right-hand sides at once    */
 
 typedef struct pn_sizes {
@@ -171,7 +171,9 @@ PN_EXPORT int pn_get_kg_coo(pn_ctx *ctx, int32_t combo, int32_t first_step, int3
                   int64_t *n_out);
 
 /* Analysis._sum_displacements :882-914 (load stepping in _first_order :262-305): overwrites the stored
- * displacement vector of a solved combo, so that element forces and reactions refer to the summed state */
+ * displacement vector of a combo, so that element forces and reactions refer to the summed state.  Also how
+ * displacements obtained elsewhere (another rank's share of the combinations) become resident: valid for any
+ * combo index of the current pn_set_combos table once the matrix is assembled.                         */
 PN_EXPORT int pn_set_displacements(pn_ctx *ctx, int32_t combo, const double *D);
 /* Analysis._calc_reactions :1059-1313 for one solved combo with the current element activity; out[6N] */
 PN_EXPORT int pn_reactions(pn_ctx *ctx, int32_t combo, int32_t pdelta, double *out);
@@ -180,6 +182,16 @@ PN_EXPORT int pn_reactions(pn_ctx *ctx, int32_t combo, int32_t pdelta, double *o
  *      Quad3D.f :713 / F :798, Plate3D.f :316 / F :403.  out[count][nd]; local != 0 -> local axes;
  *      pdelta != 0 uses the (ke + kg(P)) branch of Member3D.f :886-891                             */
 PN_EXPORT int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32_t pdelta, double *out);
+
+/* ---- internal forces / stresses of shells for solved combos: Quad3D.shear :1017, moment :1096, membrane :1173
+ *      (points = natural coordinates (xi, eta), values at the Gauss points extrapolated), Plate3D.shear :608,
+ *      moment :590, membrane :650 (points = local (x, y); the reference's plate methods ignore `local`).
+ *      Every element of `kind` (PN_QUAD / PN_PLATE), combos [combo0, combo0 + n_combo), n_pts points pts[n_pts][2]:
+ *      out[n_combo][count][n_pts][9] = Qx Qy 0 | Mx My Mxy | Sx Sy Txy  (local != 0)
+ *                                      Qx Qy Qz | Mx My Mxy | Sx Sy Sxy  (local == 0, quads: Quad3D.py:1069-1092,
+ *                                      1146-1171, 1214-1239)                                                        */
+PN_EXPORT int pn_shell_stresses(pn_ctx *ctx, int kind, int32_t combo0, int32_t n_combo, int32_t n_pts, const double *pts,
+                                int32_t local, double *out);
 
 /* ---- device-pointer building blocks for the domain-decomposed PCG --------------------------------
  * pynite_b200/ddpcg.py runs one process per GPU; every rank holds the whole K11 (assembly is 0.1 ms), owns a
@@ -224,6 +236,14 @@ PN_EXPORT int pn_get_displacements(pn_ctx *ctx, int32_t combo, double *D_out);
 PN_EXPORT int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repeat, double *ms_out);
 PN_EXPORT int pn_get_stats(pn_ctx *ctx, pn_stats *out);
 PN_EXPORT int pn_reset_stats(pn_ctx *ctx);
+/* Which kernel families the direct solver took since pn_reset_stats (no reference counterpart: SuperLU is a black box
+ * behind spsolve, Analysis.py:217).  Names: pn_counter_name(0..) until NULL -- "lu_update", "lu_update_later_groups"
+ * (fronts with more than 256 pivots), "lu_strip", "split_levels" (front groups on side streams), "sweep_smem",
+ * "sweep_ll", "sweep_step", "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches",
+ * "pdelta_fallback_columns".  The parity tests assert from these that a mid-size model exercises the
+ * kernels the full-size configurations run. */
+PN_EXPORT int pn_get_counter(pn_ctx *ctx, const char *name, int64_t *out);
+PN_EXPORT const char *pn_counter_name(int index);
 /* Device time of a host-chosen region on the library's stream (CUDA events): start synchronises the stream
  * and records, stop records, waits and returns the elapsed milliseconds.                              */
 PN_EXPORT int pn_timer_start(pn_ctx *ctx);

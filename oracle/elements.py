@@ -528,3 +528,116 @@ def plate_fer(width, height, pressure):
     f = np.zeros((24, 1))
     f[_bending_slots(), 0] = v
     return f
+
+
+# ------------------------------------------------------------------------------------------------
+# internal forces / stresses of shells (Quad3D.py:1017-1239, Plate3D.py:524-692)
+# ------------------------------------------------------------------------------------------------
+def _quad_bending_ops(xy, t, nu):
+    """B_b(r, s) and B_s(r, s) of the DKMQ element as closures over the element geometry (`Quad3D.py:288-438`)."""
+    Lk, Ck, Sk = _quad_edges(xy)
+    kappa = 5/6
+    phi = [2/(kappa*(1 - nu))*(t/L)**2 for L in Lk]
+    A_Dinv = -3/2*np.diag([1/(1 + p) for p in phi])
+    A_phiD = np.diag([p/(1 + p) for p in phi])
+    A_gam = np.diag([Lk[0]/2, Lk[1]/2, -Lk[2]/2, -Lk[3]/2])
+    A_u = _quad_Au(Lk, Ck, Sk)
+
+    def B_b(r, s):
+        Ji = inv(jacobian(xy, r, s))
+        dN = 0.25*np.array([[s - 1, -(s - 1), s + 1, -(s + 1)],
+                            [r - 1, -(r + 1), r + 1, -(r - 1)]])
+        Nxy = Ji @ dN
+        Bb = np.zeros((3, 12))
+        for a in range(4):
+            Bb[0, 3*a + 1] = Nxy[0, a]
+            Bb[1, 3*a + 2] = Nxy[1, a]
+            Bb[2, 3*a + 1] = Nxy[1, a]
+            Bb[2, 3*a + 2] = Nxy[0, a]
+        dP = np.array([[r*(s - 1), -0.5*(s - 1)*(s + 1), -r*(s + 1), 0.5*(s - 1)*(s + 1)],
+                       [0.5*(r - 1)*(r + 1), -s*(r + 1), -0.5*(r - 1)*(r + 1), s*(r - 1)]])
+        Pxy = Ji @ dP
+        BD = np.array([[Pxy[0, e]*Ck[e] for e in range(4)],
+                       [Pxy[1, e]*Sk[e] for e in range(4)],
+                       [Pxy[1, e]*Ck[e] + Pxy[0, e]*Sk[e] for e in range(4)]])
+        return np.add(Bb, BD @ A_Dinv @ A_u)
+
+    def B_s(r, s):
+        Ng = np.array([[1/2*(1 - s), 0, 1/2*(1 + s), 0],
+                       [0, 1/2*(1 + r), 0, 1/2*(1 - r)]])
+        return inv(jacobian(xy, r, s)) @ Ng @ A_gam @ A_phiD @ A_u
+    return B_b, B_s
+
+
+def _extrapolation_H(xi, eta):
+    """Bilinear functions at (xi, eta)/gp: Gauss-point values -> any point (`Quad3D.py:1050-1059`)."""
+    x, e = xi/GP, eta/GP
+    return 1/4*np.array([(1 - x)*(1 - e), (1 + x)*(1 - e), (1 + x)*(1 + e), (1 - x)*(1 + e)])
+
+
+def quad_stress(p1, p2, p3, p4, t, E, nu, kx_mod, ky_mod, d, xi, eta, local=True):
+    """(shear, moment, membrane) of a quad at natural coordinates (xi, eta) from its LOCAL displacement vector d
+    (24, 1) (`Quad3D.shear` :1017-1094, `moment` :1096-1171, `membrane` :1173-1239)."""
+    xy = quad_local_xy(p1, p2, p3, p4)
+    B_b, B_s = _quad_bending_ops(xy, t, nu)
+    db = np.array(d, dtype=float).reshape(24, 1).copy()
+    db[[3, 9, 15, 21], :] *= -1
+    db = db[[2, 4, 3, 8, 10, 9, 14, 16, 15, 20, 22, 21], :]
+    H = _extrapolation_H(xi, eta)
+    Hs = E*t*(5/6)/(2*(1 + nu))*np.eye(2)
+    Hb = E*t**3/(12*(1 - nu**2))*np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu)/2]])
+    q = [np.matmul(Hs, np.matmul(B_s(r, s), db)) for r, s in _GAUSS]
+    m = [np.matmul(Hb, np.matmul(B_b(r, s), db)) for r, s in _GAUSS]
+    dm = np.asarray(d, dtype=float).reshape(24, 1)[[0, 1, 6, 7, 12, 13, 18, 19], :]
+    C = membrane_C(E, nu, kx_mod, ky_mod)
+    sg = [np.matmul(C, np.matmul(membrane_B(xy, r, s), dm)) for r, s in _GAUSS]
+    Q = np.array([sum(H[g]*q[g][k] for g in range(4)) for k in range(2)]).reshape(2)
+    M = np.array([sum(H[g]*m[g][k] for g in range(4)) for k in range(3)]).reshape(3)
+    S = np.array([sum(H[g]*sg[g][k] for g in range(4)) for k in range(3)]).reshape(3)
+    if local:
+        return Q, M, S
+    R = shell_dircos(p1, p2, p4)
+    Qg = np.matmul(R.T, np.array([[Q[0], 0, 0], [0, Q[1], 0], [0, 0, 0]]))
+    Qo = np.array([Qg[0, 0], Qg[1, 1], Qg[2, 1]])
+    Mg = R @ np.array([[M[0], M[2], 0.0], [M[2], -M[1], 0.0], [0.0, 0.0, 0.0]]) @ R.T
+    Sg = R @ np.array([[S[0], S[2], 0.0], [S[2], S[1], 0.0], [0.0, 0.0, 0.0]]) @ R.T
+    return Qo, np.array([Mg[0, 0], Mg[1, 1], Mg[0, 1]]), np.array([Sg[0, 0], Sg[1, 1], Sg[0, 1]])
+
+
+def plate_C(width, height):
+    """Displacement coefficient matrix [C] of the rectangular plate (`Plate3D._C` :524-557)."""
+    rows = []
+    for x, y in ((0, 0), (width, 0), (width, height), (0, height)):
+        rows.append([1, x, y, x**2, x*y, y**2, x**3, x**2*y, x*y**2, y**3, x**3*y, x*y**3])
+        rows.append([0, 0, 1, 0, x, 2*y, 0, x**2, 2*x*y, 3*y**2, x**3, 3*x*y**2])
+        rows.append([0, -1, 0, -2*x, -y, 0, -3*x**2, -2*x*y, -y**2, 0, -3*x**2*y, -y**3])
+    return np.array(rows, dtype=float)
+
+
+def plate_stress(width, height, t, E, nu, kx_mod, ky_mod, d, x, y):
+    """(shear, moment, membrane) of a rectangular plate at local (x, y) from its LOCAL displacement vector
+    (`Plate3D._a` :573-588, `moment` :590-606, `shear` :608-648, `membrane` :650-692)."""
+    d = np.asarray(d, dtype=float).reshape(24, 1)
+    a = inv(plate_C(width, height)) @ d[[2, 3, 4, 8, 9, 10, 14, 15, 16, 20, 21, 22], :]
+    Ex, Ey, G = E*kx_mod, E*ky_mod, E/(2*(1 + nu))
+    Db = t**3/(12*(1 - nu*nu))*np.array([[Ex, nu*Ex, 0], [nu*Ey, Ey, 0], [0, 0, G]])
+    Qm = np.array([[0, 0, 0, -2, 0, 0, -6*x, -2*y, 0, 0, -6*x*y, 0],
+                   [0, 0, 0, 0, 0, -2, 0, 0, -2*x, -6*y, 0, -6*x*y],
+                   [0, 0, 0, 0, -2, 0, 0, -4*x, -4*y, 0, -6*x**2, -6*y**2]])
+    M = (-Db @ Qm @ a).reshape(3)
+    R1 = np.array([[0, 0, 0, 0, 0, 0, -6, 0, 0, 0, -6*y, 0],
+                   [0, 0, 0, 0, 0, 0, 0, 0, -2, 0, 0, -6*y],
+                   [0, 0, 0, 0, 0, 0, 0, -4, 0, 0, -12*x, 0]])
+    R2 = np.array([[0, 0, 0, 0, 0, 0, 0, -2, 0, 0, -6*x, 0],
+                   [0, 0, 0, 0, 0, 0, 0, 0, 0, -6, 0, -6*x],
+                   [0, 0, 0, 0, 0, 0, 0, 0, -4, 0, 0, -12*y]])
+    v1, v2 = (Db @ R1 @ a).reshape(3), (Db @ R2 @ a).reshape(3)
+    Q = np.array([v1[0] + v2[2], v2[1] + v1[2]])
+    r, s = -1 + 2*x/width, -1 + 2*y/height
+    H = _extrapolation_H(r, s)
+    xy = ((0, 0), (width, 0), (width, height), (0, height))
+    dm = d[[0, 1, 6, 7, 12, 13, 18, 19], :]
+    C = membrane_C(E, nu, kx_mod, ky_mod)
+    sg = [np.matmul(C, np.matmul(membrane_B(xy, rr, ss), dm)) for rr, ss in _GAUSS]
+    S = np.array([sum(H[g]*sg[g][k] for g in range(4)) for k in range(3)]).reshape(3)
+    return Q, M, S

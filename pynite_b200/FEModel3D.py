@@ -318,5 +318,8 @@ class FEModel3D:
     def _element_force(self, kind, elem_id, combo_name, local):
         return _analysis.element_force(self, kind, elem_id, combo_name, local)
 
+    def _shell_stress(self, kind, elem_id, combo_name, u, v, local):
+        return _analysis.shell_stress(self, kind, elem_id, combo_name, u, v, local)
+
     def _member_dircos(self, sub):
         return _analysis.member_dircos_host(sub)

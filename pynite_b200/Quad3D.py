@@ -3,9 +3,13 @@
 Data fields follow `Pynite/Quad3D.py:30-57` and `Pynite/Plate3D.py:16-72` (nodes i-j-m-n, thickness,
 E and nu copied from the material at construction, in-plane stiffness modifiers, pressure list).
 Stiffness, fixed-end forces and end forces (`Quad3D.py:107-950`, `Plate3D.py:77-522`) are computed by
-the sm_100a shell kernels (`csrc/elem_quad.cuh`, `csrc/elem_plate.cuh`).
+the sm_100a shell kernels (`csrc/elem_shell.cuh`); internal shears, moments and membrane stresses
+(`Quad3D.py:1017-1239`, `Plate3D.py:590-692`) by `csrc/elem_stress.cuh` / `pn_stress.cu`, batched over all
+elements of the kind for the requested combination and point.
 """
 from __future__ import annotations
+
+import numpy as np
 
 
 class _Shell4:
@@ -44,6 +48,20 @@ class Quad3D(_Shell4):
     _kind = 'quad'
     type = 'Quad'
 
+    # Results at natural coordinates (xi, eta), extrapolated from the Gauss points like the reference does.
+    def shear(self, xi=0.0, eta=0.0, local=True, combo_name='Combo 1'):
+        """[[Qx], [Qy]] per unit length (`Quad3D.py:1017-1094`); global: [[Qx], [Qy], [Qz]]."""
+        r = self.model._shell_stress('quad', self.ID, combo_name, xi, eta, local)
+        return r[0:2].reshape(2, 1).copy() if local else r[0:3].reshape(3, 1).copy()
+
+    def moment(self, xi=0.0, eta=0.0, local=True, combo_name='Combo 1'):
+        """[[Mx], [My], [Mxy]] per unit length (`Quad3D.py:1096-1171`)."""
+        return self.model._shell_stress('quad', self.ID, combo_name, xi, eta, local)[3:6].reshape(3, 1).copy()
+
+    def membrane(self, xi=0.0, eta=0.0, local=True, combo_name='Combo 1'):
+        """[[Sx], [Sy], [Txy]] (`Quad3D.py:1173-1239`)."""
+        return self.model._shell_stress('quad', self.ID, combo_name, xi, eta, local)[6:9].reshape(3, 1).copy()
+
     def __repr__(self):
         return (f"Quad3D(name={self.name!r}, i_node={self.i_node.name!r}, j_node={self.j_node.name!r}, "
                 f"m_node={self.m_node.name!r}, n_node={self.n_node.name!r})")
@@ -62,3 +80,13 @@ class Plate3D(_Shell4):
 
     def height(self):
         return self.i_node.distance(self.n_node)
+
+    # Results at local coordinates (x, y).  Like the reference's, these ignore `local` (`Plate3D.py:590-692`).
+    def moment(self, x, y, local=True, combo_name='Combo 1'):
+        return self.model._shell_stress('plate', self.ID, combo_name, x, y, True)[3:6].reshape(3, 1).copy()
+
+    def shear(self, x, y, local=True, combo_name='Combo 1'):
+        return self.model._shell_stress('plate', self.ID, combo_name, x, y, True)[0:2].reshape(2, 1).copy()
+
+    def membrane(self, x, y, local=True, combo_name='Combo 1'):
+        return self.model._shell_stress('plate', self.ID, combo_name, x, y, True)[6:9].reshape(3, 1).copy()

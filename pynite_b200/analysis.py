@@ -181,25 +181,43 @@ def run_linear(model, log, check_stability, check_statics, sparse, combo_tags):
     model._run = RunState(A, [c.name for c in local_list])
     # the reference keeps the P-Delta end-force branch alive until `solution` is reset
     model._run.pdelta = model.solution == 'P-Delta'
-    _assemble(model, eng, check_stability, log)
     D = np.zeros((0, A.n_dof))
     R = np.zeros((0, A.n_dof))
-    if local_list:
-        if log:
-            print('- Solving ' + str(len(local_list)) + ' load combination(s)')
-        try:
-            D, R, st = eng.solve_linear(_opts(check_stability), reactions=not model._run.pdelta)
-        except _eng.SingularMatrix:
-            raise Exception(_eng.SINGULAR_MSG)
-        if model._run.pdelta:
-            R = np.stack([eng.reactions(i, True).reshape(-1) for i in range(len(local_list))])
+    failure = None
+    try:
+        _assemble(model, eng, check_stability, log)
+        if local_list:
+            if log:
+                print('- Solving ' + str(len(local_list)) + ' load combination(s)')
+            try:
+                D, R, st = eng.solve_linear(_opts(check_stability), reactions=not model._run.pdelta)
+            except _eng.SingularMatrix:
+                raise Exception(_eng.SINGULAR_MSG)
+            if model._run.pdelta:
+                R = np.stack([eng.reactions(i, True).reshape(-1) for i in range(len(local_list))])
+    except Exception as err:              # noqa: BLE001 -- re-raised below, on every rank when distributed
+        if not distribute:
+            raise
+        failure = err
     model.last_stats = eng.stats().as_dict()
     if distribute:
         import torch.distributed as dist
         dev = ('cuda:%d' % eng.device) if dist.get_backend() == 'nccl' else None
+        # failure is collective: a rank that raised (singular matrix, unstable node) must not leave the others
+        # waiting in the all-gather, and a rank without combos of its own must still learn of it
+        if _sh.any_rank_failed(failure is not None, dev):
+            raise failure if failure is not None else Exception(_eng.SINGULAR_MSG)
         counts = [len(_sh.shard_combos(len(combo_list), r, ws)) for r in range(ws)]
         D = _sh.all_gather_rows(D, counts, dev)
         R = _sh.all_gather_rows(R, counts, dev)
+        # every rank holds K: make all combinations resident so that element forces, stresses and the statics check
+        # work for the ones solved elsewhere exactly as for the local ones
+        A_all = flatten_factors(model, combo_list, A)
+        eng.set_combos(A_all.factors)
+        for i in range(len(combo_list)):
+            eng.set_displacements(i, D[i])
+        model._run = RunState(A_all, [c.name for c in combo_list])
+        model._run.pdelta = model.solution == 'P-Delta'
     _store(model, combo_list, D, R)
     t2 = time.perf_counter()
     if model.last_stats is not None:
@@ -417,14 +435,38 @@ def run_pdelta(model, log, check_stability, max_iter, sparse, combo_tags):
 # ---------------------------------------------------------------------------------------------
 # inspection helpers behind FEModel3D.Ke / Kg / FER / P and the element objects
 # ---------------------------------------------------------------------------------------------
+def flatten_factors(model, combo_list, A):
+    """Copy of the flattened arrays `A` with the factor table of `combo_list` (same model, same load cases)."""
+    import copy
+    B = copy.copy(A)
+    B.factors = np.array([[c.factors.get(case, 0.0) for case in A.cases] for c in combo_list], dtype=float).reshape(
+        len(combo_list), len(A.cases))
+    B.combo_names = [c.name for c in combo_list]
+    return B
+
+
 def _fresh_engine_state(model, combo_name):
-    """Uploads the model for a stand-alone `Ke/Kg/FER/P` call when no analysis state matches."""
+    """Engine state for a stand-alone `Ke/Kg/FER/P` call.
+
+    Reuses the analysis state when it holds the combo.  Otherwise the model is uploaded to a *scratch* context when an
+    analysis exists (its displacements, saved end forces and P-Delta flag must stay readable: in the reference these
+    inspection calls never touch stored results), and to the main context when nothing has been analysed yet."""
     run = model._run
     if run is not None and model.solution is not None and combo_name in run.engine_combo:
         return run, _engine(model)
     if any(n.ID is None for n in model.nodes.values()) or model._run is None:
         prepare_model(model)
     combo = model.load_combos[combo_name]
+    if model._run is not None and model.solution is not None:
+        import os
+        if getattr(model, '_scratch_engine', None) is None:
+            model._scratch_engine = _eng.Engine(getattr(model, 'device', int(os.environ.get('LOCAL_RANK', '0'))))
+        eng = model._scratch_engine
+        A = flatten_model(model, [combo], combo_name)
+        eng.set_model(A)
+        eng.set_loads(A)
+        eng.set_combos(A.factors)
+        return RunState(A, [combo_name]), eng
     A, eng = _upload(model, [combo], combo_name)
     model._run = RunState(A, [combo_name])
     return model._run, eng
@@ -447,10 +489,10 @@ def global_Ke(model, combo_name, log, check_stability, sparse):
 def global_Kg(model, combo_name, log, sparse, first_step):
     _require_sparse(sparse)
     run = model._run
+    eng = _engine(model)
     if first_step or run is None or combo_name not in run.engine_combo:
         run, eng = _fresh_engine_state(model, combo_name)
-        first_step = True if model.solution is None else first_step
-    eng = _engine(model)
+        first_step = True if (model.solution is None or eng is not model._engine) else first_step
     row, col, data = eng.kg_coo(run.engine_combo[combo_name], first_step)
     n = run.arrays.n_dof
     return sps.coo_matrix((data, (row, col)), shape=(n, n))
@@ -469,12 +511,46 @@ def element_force(model, kind, elem_id, combo_name, local):
     key = (kind, combo_name, bool(local))
     if key not in run.force_cache:
         eng = _engine(model)
-        if combo_name in run.engine_combo:
-            run.force_cache[key] = eng.element_forces(kind, run.engine_combo[combo_name], local=local, pdelta=run.pdelta)
-        else:
-            F = getattr(run, 'saved', {})[combo_name][kind]
+        saved = getattr(run, 'saved', {})
+        if combo_name in saved:
+            # per-combination analyses keep every combo's end forces as computed with that combo's own element activity
+            F = saved[combo_name][kind]
             run.force_cache[key] = _rotate_saved(model, kind, F) if local else F
+        else:
+            j = _make_resident(model, combo_name)
+            run.force_cache[key] = eng.element_forces(kind, j, local=local, pdelta=run.pdelta)
     return run.force_cache[key][elem_id].reshape(-1, 1)
+
+
+def _make_resident(model, combo_name):
+    """Engine combo index whose stored displacements are those of `combo_name`.  After a per-combination analysis
+    (tension/compression-only, load stepping) only the last combination is resident: the requested one is brought
+    back with its factor row and its stored displacement vector (`pn_set_displacements`)."""
+    run = model._run
+    eng = _engine(model)
+    if combo_name in run.engine_combo:
+        return run.engine_combo[combo_name]
+    ci = run.combo_index[combo_name]
+    eng.set_combos(run.arrays.factors[ci:ci + 1])
+    eng.set_displacements(0, model._D[combo_name])
+    run.engine_combo = {combo_name: 0}
+    return 0
+
+
+def shell_stress(model, kind, elem_id, combo_name, u, v, local):
+    """(9,) results of one quad / plate at (u, v) for a solved combo: shears, moments, membrane stresses
+    (`Quad3D.shear/moment/membrane` :1017-1239, `Plate3D` :590-692).  One batched device call evaluates every element
+    of the kind at that point; the table is cached, so walking over the elements costs one launch."""
+    run = model._run
+    if run is None or combo_name not in model._D:
+        raise KeyError(f"load combination '{combo_name}' has not been analysed")
+    key = ('stress', kind, combo_name, float(u), float(v), bool(local))
+    if key not in run.force_cache:
+        j = _make_resident(model, combo_name)
+        if len(run.force_cache) > 64:
+            run.force_cache = {k: val for k, val in run.force_cache.items() if k[0] != 'stress'}
+        run.force_cache[key] = _engine(model).shell_stresses(kind, j, 1, [[u, v]], local)[0, :, 0, :]
+    return run.force_cache[key][elem_id]
 
 
 def _rotate_saved(model, kind, F):

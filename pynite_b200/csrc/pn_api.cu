@@ -854,9 +854,22 @@ int pn_get_kg_coo(pn_ctx *ctx, int32_t combo, int32_t first_step, int32_t *row, 
 
 int pn_set_displacements(pn_ctx *ctx, int32_t combo, const double *D) {
     PN_API_BEGIN(ctx)
-    if (!c->solved || combo < 0 || combo >= c->loads.n_combo || !D) throw ArgError("pn_set_displacements: combo has not been solved");
+    if (combo < 0 || combo >= c->loads.n_combo || !D) throw ArgError("pn_set_displacements: bad combo index");
+    if (!c->vals_ready) throw ArgError("pn_set_displacements: call pn_assemble_ke first");
+    // Also the way results computed elsewhere (another rank's share of the combinations, an earlier per-combination
+    // analysis) are made resident again for pn_reactions / pn_element_forces / pn_shell_stresses.
+    const int64_t need = (int64_t)c->loads.n_combo * c->n_dof;
+    if (c->D_all.n < need) {
+        DevBuf<double> grown;
+        grown.resize(need);
+        grown.zero(c->stream);
+        if (c->D_all.n && c->solved)
+            PN_CUDA(cudaMemcpyAsync(grown.ptr, c->D_all.ptr, sizeof(double) * c->D_all.n, cudaMemcpyDeviceToDevice, c->stream));
+        std::swap(grown.ptr, c->D_all.ptr); std::swap(grown.n, c->D_all.n); std::swap(grown.cap, c->D_all.cap);
+    }
     PN_CUDA(cudaMemcpyAsync(c->D_all.ptr + (int64_t)combo * c->n_dof, D, sizeof(double) * c->n_dof, cudaMemcpyHostToDevice, c->stream));
     PN_CUDA(cudaStreamSynchronize(c->stream));
+    c->solved = true;
     PN_API_END
 }
 
@@ -896,6 +909,32 @@ int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32
     if (local) launch_forces_to_local(c, kind, F, st);
     if (cnt) PN_CUDA(cudaMemcpyAsync(out, F, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
+    PN_API_END
+}
+
+int pn_shell_stresses(pn_ctx *ctx, int kind, int32_t combo0, int32_t n_combo, int32_t n_pts, const double *pts, int32_t local,
+                      double *out) {
+    PN_API_BEGIN(ctx)
+    if (kind != PN_QUAD && kind != PN_PLATE) throw ArgError("pn_shell_stresses: kind must be PN_QUAD or PN_PLATE");
+    if (!c->solved || combo0 < 0 || n_combo < 0 || combo0 + n_combo > c->loads.n_combo)
+        throw ArgError("pn_shell_stresses: combos have not been solved");
+    if (n_pts < 0 || (n_pts && !pts) || !out) throw ArgError("pn_shell_stresses: null array");
+    const int64_t n = kind == PN_QUAD ? c->model.n_quads : c->model.n_plates;
+    if (n && n_combo && n_pts) {
+        cudaStream_t st = c->stream;
+        DevBuf<double> dp, dout;
+        dp.upload(pts, 2 * (int64_t)n_pts, st);
+        // bounded device buffer: combos in batches of <= 2 GB of results
+        const int64_t per_combo = n * n_pts * 9;
+        const int step = (int)std::max<int64_t>(1, std::min<int64_t>(n_combo, (int64_t)(2.5e8 / (double)per_combo)));
+        dout.resize(per_combo * step);
+        for (int j0 = 0; j0 < n_combo; j0 += step) {
+            const int nj = std::min(step, n_combo - j0);
+            launch_shell_stress(c, kind == PN_QUAD, c->D_all.ptr + (int64_t)(combo0 + j0) * c->n_dof, nj, n_pts, dp.ptr, local, dout.ptr, st);
+            PN_CUDA(cudaMemcpyAsync(out + (int64_t)j0 * per_combo, dout.ptr, sizeof(double) * per_combo * nj, cudaMemcpyDeviceToHost, st));
+            PN_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     PN_API_END
 }
 
@@ -1112,6 +1151,22 @@ int pn_reset_stats(pn_ctx *ctx) {
     PN_API_BEGIN(ctx)
     c->stats = pn_stats{};
     c->launches = 0;
+    for (int i = 0; i < PC_COUNT; ++i) c->ctr[i] = 0;
+    PN_API_END
+}
+
+static const char *kCounterNames[PC_COUNT] = {
+    "lu_update", "lu_update_later_groups", "lu_strip", "split_levels", "sweep_smem", "sweep_ll", "sweep_step",
+    "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches", "pdelta_fallback_columns"};
+
+const char *pn_counter_name(int index) { return (index >= 0 && index < PC_COUNT) ? kCounterNames[index] : nullptr; }
+
+int pn_get_counter(pn_ctx *ctx, const char *name, int64_t *out) {
+    PN_API_BEGIN(ctx)
+    if (!name || !out) throw ArgError("pn_get_counter: null argument");
+    for (int i = 0; i < PC_COUNT; ++i)
+        if (!strcmp(name, kCounterNames[i])) { *out = c->ctr[i]; return PN_OK; }
+    throw ArgError(std::string("pn_get_counter: unknown counter ") + name);
     PN_API_END
 }
 

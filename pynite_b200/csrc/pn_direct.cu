@@ -1653,6 +1653,9 @@ static void factorise(Ctx *c, const double *vals11) {
     if (debug_levels && debug_kernels) cudaMalloc(&dbg_clk, 8 * sizeof(long long));
     const CsrBlock &A = c->blk[0];
     d.status.zero(st);
+    c->ctr[PC_FACTORISATIONS]++;
+    c->ctr[PC_LEVELS] = d.n_levels;
+    for (int l = 0; l < d.n_levels; ++l) c->ctr[PC_MAX_FRONT_NS] = std::max<int64_t>(c->ctr[PC_MAX_FRONT_NS], d.level_max_ns[l]);
     for (int l = 0; l < d.n_levels; ++l) {
         int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
         if (!nfl) continue;
@@ -1718,6 +1721,7 @@ static void factorise(Ctx *c, const double *vals11) {
                             { ProfScope ps_(c, PS_LU_PANELS, sq); k_lu_strip<<<nf_ <= 65535 ? dim3(tiles, nf_) : dim3(nf_, tiles), 256, GEMM_SMEM, sq>>>(f0_, kb, g0, d.fronts.ptr, arena, sym, nf_ <= 65535 ? 0 : 1); }
                             lp.end();
                             c->count_launch();
+                            c->ctr[PC_LU_STRIP]++;
                         }
                     }
                 }
@@ -1728,6 +1732,8 @@ static void factorise(Ctx *c, const double *vals11) {
                     { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<nf_ <= 65535 ? dim3(tiles_u, tiles_l, nf_) : dim3(nf_, tiles_l, tiles_u), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym, nf_ <= 65535 ? 0 : 1); }
                     lp.end();
                     c->count_launch();
+                    c->ctr[PC_LU_UPDATE]++;
+                    if (g0 > 0) c->ctr[PC_LU_UPDATE_LATER]++;
                 }
             }
         };
@@ -1737,6 +1743,7 @@ static void factorise(Ctx *c, const double *vals11) {
         if (nsplit == 1) {
             run_steps(first, nfl, st);
         } else {
+            c->ctr[PC_SPLIT_LEVELS]++;
             PN_CUDA(cudaEventRecord(d.ev_fork, st));
             for (int q = 0; q < nsplit; ++q) {
                 int a = first + (int)((int64_t)nfl * q / nsplit), b = first + (int)((int64_t)nfl * (q + 1) / nsplit);
@@ -1826,6 +1833,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             if (cw == 32) PN_FWD(32); else if (cw == 16) PN_FWD(16); else PN_FWD(8);
 #undef PN_FWD
             c->count_launch();
+            c->ctr[PC_SWEEP_SMEM]++;
             continue;
         }
         if (!use_ll && nfl >= FUSED_SOLVE_MIN_FRONTS) {     // fallback for more than 256 right-hand sides
@@ -1854,12 +1862,14 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 0, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
                                                                   d.ll_flags.ptr, ++d.ll_epoch);
             c->count_launch();
+            c->ctr[PC_SWEEP_LL]++;
         } else
         for (int kb = 0; kb < maxns; kb += NB) {
             int rest = std::max(maxn - kb - 1, 0);
             int tiles = 1 + (rest + BM - 1) / BM;
             { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_step<<<dim3(nfl, tiles, gz), 256, GEMM_SMEM, st>>>(first, kb, s, 0, fr, d.L.ptr, d.inv.ptr, W, Y); }
             c->count_launch();
+            c->ctr[PC_SWEEP_STEP]++;
         }
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
@@ -1883,6 +1893,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             if (cw == 32) PN_BWD(32); else if (cw == 16) PN_BWD(16); else PN_BWD(8);
 #undef PN_BWD
             c->count_launch();
+            c->ctr[PC_SWEEP_SMEM]++;
             continue;
         }
         if (!use_ll && nfl >= FUSED_SOLVE_MIN_FRONTS) {
@@ -1901,6 +1912,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 1, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
                                                                   d.ll_flags.ptr, ++d.ll_epoch);
             c->count_launch();
+            c->ctr[PC_SWEEP_LL]++;
         } else {
         if (d.level_max_nb[l] > 0) {
             { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_boundary<<<dim3(nfl, (maxns + BM - 1) / BM, gz), 256, GEMM_SMEM, st>>>(first, s, fr, d.U.ptr, W); }
@@ -1911,6 +1923,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
             int tiles = 1 + (kb + BM - 1) / BM;
             { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_step<<<dim3(nfl, tiles, gz), 256, GEMM_SMEM, st>>>(first, kb, s, 1, fr, d.L.ptr, d.inv.ptr, W, Y); }
             c->count_launch();
+            c->ctr[PC_SWEEP_STEP]++;
         }
         }
         unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
@@ -1947,6 +1960,131 @@ __global__ void k_get_col(int64_t n, int s, int j, const double *__restrict__ M,
 __global__ void k_set_col(int64_t n, int s, int j, const double *__restrict__ v, double *__restrict__ M) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) M[i * s + j] = v[i];
+}
+
+// ---- GMRES on K_j x_j = b_j for all columns at once, right-preconditioned with the stored factor (of Ke) -----------
+// Y[i][j] += alpha[j] X[i][j]  /  Y[i][j] = alpha[j] X[i][j]
+__global__ void k_col_axpy(int64_t n, int s, const double *__restrict__ alpha, const double *__restrict__ X, double *__restrict__ Y) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n * s) Y[t] = fma(alpha[t % s], X[t], Y[t]);
+}
+__global__ void k_col_scale(int64_t n, int s, const double *__restrict__ alpha, const double *__restrict__ X, double *__restrict__ Y) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n * s) Y[t] = alpha[t % s] * X[t];
+}
+
+static void gmres_columns(Ctx *c, const double *vals11, int s) {
+    cudaStream_t st = c->stream;
+    const CsrBlock &A = c->blk[0];
+    const int64_t n1 = c->n1, ns = n1 * s;
+    int m = (int)std::min<int64_t>(40, std::max<int64_t>(5, (int64_t)(4.0e9 / (8.0 * (double)std::max<int64_t>(ns, 1))) - 3));
+    DevBuf<double> V, W, Z, zero, alpha;
+    V.resize((int64_t)(m + 1) * ns); W.resize(ns); Z.resize(ns); zero.resize(ns); alpha.resize(s);
+    zero.zero(st);
+    std::vector<double> a(s), beta(s), bnorm(s), dots(s);
+    std::vector<std::vector<double>> H(s, std::vector<double>((size_t)(m + 1) * m, 0.0)), cs(s, std::vector<double>(m)),
+        sn(s, std::vector<double>(m)), g(s, std::vector<double>(m + 1));
+    auto put_alpha = [&]() {
+        PN_CUDA(cudaMemcpyAsync(alpha.ptr, a.data(), sizeof(double) * s, cudaMemcpyHostToDevice, st));
+        PN_CUDA(cudaStreamSynchronize(st));
+    };
+    const unsigned grid = grid_for(ns, 256);
+    // start from x = Ke^-1 b (the stationary iterate may have drifted along a divergent mode)
+    PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * ns, cudaMemcpyDeviceToDevice, st));
+    solve_inplace(c, c->X.ptr, s);
+    column_dots(c, n1, s, c->B.ptr, c->B.ptr, bnorm.data());
+    for (int j = 0; j < s; ++j) bnorm[j] = std::sqrt(bnorm[j]);
+    const double tol = 1e-13;
+    double worst = 0.0;
+    for (int cycle = 0; cycle < 12; ++cycle) {
+        residual_dd(c, A, vals11, A.nnz, c->X.ptr, c->B.ptr, W.ptr, s, st);
+        column_dots(c, n1, s, W.ptr, W.ptr, beta.data());
+        worst = 0.0;
+        for (int j = 0; j < s; ++j) {
+            beta[j] = std::sqrt(beta[j]);
+            if (!(beta[j] == beta[j])) beta[j] = INFINITY;
+            worst = std::max(worst, bnorm[j] > 0 ? beta[j] / bnorm[j] : beta[j]);
+        }
+        if (worst <= 1e-12) break;
+        if (!std::isfinite(worst)) break;
+        for (int j = 0; j < s; ++j) {
+            a[j] = beta[j] > 0 ? 1.0 / beta[j] : 0.0;
+            std::fill(g[j].begin(), g[j].end(), 0.0);
+            g[j][0] = beta[j];
+            std::fill(H[j].begin(), H[j].end(), 0.0);
+        }
+        put_alpha();
+        k_col_scale<<<grid, 256, 0, st>>>(n1, s, alpha.ptr, W.ptr, V.ptr);
+        c->count_launch();
+        int kdone = 0;
+        for (int k = 0; k < m; ++k) {
+            // w = K_j Ke^-1 v_k
+            PN_CUDA(cudaMemcpyAsync(Z.ptr, V.ptr + (int64_t)k * ns, sizeof(double) * ns, cudaMemcpyDeviceToDevice, st));
+            solve_inplace(c, Z.ptr, s);
+            residual_dd(c, A, vals11, A.nnz, Z.ptr, zero.ptr, W.ptr, s, st);       // W = -K z
+            for (int j = 0; j < s; ++j) a[j] = -1.0;
+            put_alpha();
+            k_col_scale<<<grid, 256, 0, st>>>(n1, s, alpha.ptr, W.ptr, W.ptr);
+            c->count_launch();
+            for (int i = 0; i <= k; ++i) {                                        // modified Gram-Schmidt
+                column_dots(c, n1, s, W.ptr, V.ptr + (int64_t)i * ns, dots.data());
+                for (int j = 0; j < s; ++j) { H[j][(size_t)i * m + k] = dots[j]; a[j] = -dots[j]; }
+                put_alpha();
+                k_col_axpy<<<grid, 256, 0, st>>>(n1, s, alpha.ptr, V.ptr + (int64_t)i * ns, W.ptr);
+                c->count_launch();
+            }
+            column_dots(c, n1, s, W.ptr, W.ptr, dots.data());
+            double est = 0.0;
+            for (int j = 0; j < s; ++j) {
+                const double hk1 = std::sqrt(dots[j]);
+                H[j][(size_t)(k + 1) * m + k] = hk1;
+                a[j] = hk1 > 1e-300 ? 1.0 / hk1 : 0.0;
+                // Givens rotations of column k
+                std::vector<double> &Hj = H[j];
+                for (int i = 0; i < k; ++i) {
+                    const double t0 = cs[j][i] * Hj[(size_t)i * m + k] + sn[j][i] * Hj[(size_t)(i + 1) * m + k];
+                    Hj[(size_t)(i + 1) * m + k] = -sn[j][i] * Hj[(size_t)i * m + k] + cs[j][i] * Hj[(size_t)(i + 1) * m + k];
+                    Hj[(size_t)i * m + k] = t0;
+                }
+                const double hkk = Hj[(size_t)k * m + k], r = std::hypot(hkk, hk1);
+                cs[j][k] = r > 0 ? hkk / r : 1.0;
+                sn[j][k] = r > 0 ? hk1 / r : 0.0;
+                Hj[(size_t)k * m + k] = r;
+                Hj[(size_t)(k + 1) * m + k] = 0.0;
+                g[j][k + 1] = -sn[j][k] * g[j][k];
+                g[j][k] = cs[j][k] * g[j][k];
+                est = std::max(est, bnorm[j] > 0 ? std::fabs(g[j][k + 1]) / bnorm[j] : std::fabs(g[j][k + 1]));
+            }
+            put_alpha();
+            k_col_scale<<<grid, 256, 0, st>>>(n1, s, alpha.ptr, W.ptr, V.ptr + (int64_t)(k + 1) * ns);
+            c->count_launch();
+            c->stats.iterations += 1;
+            kdone = k + 1;
+            if (est <= tol) break;
+        }
+        // x += Ke^-1 (V y),  H y = g
+        std::vector<std::vector<double>> y(s, std::vector<double>(kdone, 0.0));
+        for (int j = 0; j < s; ++j)
+            for (int i = kdone - 1; i >= 0; --i) {
+                double acc = g[j][i];
+                for (int q = i + 1; q < kdone; ++q) acc -= H[j][(size_t)i * m + q] * y[j][q];
+                const double dgn = H[j][(size_t)i * m + i];
+                y[j][i] = dgn != 0.0 ? acc / dgn : 0.0;
+            }
+        Z.zero(st);
+        for (int i = 0; i < kdone; ++i) {
+            for (int j = 0; j < s; ++j) a[j] = y[j][i];
+            put_alpha();
+            k_col_axpy<<<grid, 256, 0, st>>>(n1, s, alpha.ptr, V.ptr + (int64_t)i * ns, Z.ptr);
+            c->count_launch();
+        }
+        solve_inplace(c, Z.ptr, s);
+        k_axpy1<<<grid, 256, 0, st>>>(ns, Z.ptr, c->X.ptr);
+        c->count_launch();
+    }
+    c->ctr[PC_PDELTA_PERCOLUMN] += s;
+    if (!(worst <= 1e-8))
+        throw StatusError(PN_ERR_SINGULAR, "The stiffness matrix is singular, which indicates that the structure is unstable.");
 }
 
 void direct_release(Ctx *c) {
@@ -2047,7 +2185,17 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
                 if (it >= 6 && worst > 0.7 * prev) break;          // contracting too slowly (or diverging)
                 prev = worst;
             }
-            if (converged) return;
+            if (converged) { c->ctr[PC_PDELTA_STATIONARY]++; return; }
+            static const bool percol_lu = getenv("PN_PDELTA_PERCOLUMN_LU") != nullptr;
+            if (!percol_lu) {
+                // Contraction too slow: the load is near or above a buckling load of some mode (P / P_cr -> 1), where
+                // Ke + Kg is near-singular or indefinite.  An LU without pivoting must not be trusted there (the reference
+                // uses SuperLU with partial pivoting, Analysis.py:434), so the columns are finished by GMRES on K_j with the
+                // factor of Ke as right preconditioner: Ke^-1 K_j = I + Ke^-1 Kg has one outlying eigenvalue per
+                // buckling mode the load approaches, everything else clusters at 1.
+                gmres_columns(c, vals11, s);
+                return;
+            }
         }
         d.col_in.resize(n1); d.col_out.resize(n1);
         DevBuf<double> ax;
@@ -2056,6 +2204,7 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
         for (int j = 0; j < s; ++j) {
             const double *vj = vals11 + (int64_t)j * A.nnz;
             d.shared_factor = false;
+            c->ctr[PC_PDELTA_PERCOLUMN]++;
             { PhaseTimer tm(c, &c->stats.ms_factor); factorise(c, vj); }
             PhaseTimer tm(c, &c->stats.ms_solve);
             k_get_col<<<grid_for(n1, 256), 256, 0, st>>>(n1, s, j, c->B.ptr, d.col_in.ptr);

@@ -155,6 +155,22 @@ struct Profiler {
     int64_t n[PS_COUNT] = {0};
 };
 
+enum PathCounter {
+    PC_LU_UPDATE = 0,      // k_lu_update launches (rank <= 256 trailing update, one per pivot group)
+    PC_LU_UPDATE_LATER,    // ... of a second or later pivot group: fronts with more than 256 pivots
+    PC_LU_STRIP,           // k_lu_strip launches (rank-64 strips inside a pivot group)
+    PC_SPLIT_LEVELS,       // levels whose fronts ran as groups on the side streams
+    PC_SWEEP_SMEM,         // k_front_forward_sm / k_front_backward_sm launches
+    PC_SWEEP_LL,           // k_ll_sweep launches
+    PC_SWEEP_STEP,         // per-step GEMM sweep launches (fallback family)
+    PC_MAX_FRONT_NS,       // largest separator (pivots of one front)
+    PC_LEVELS,             // elimination-tree levels
+    PC_FACTORISATIONS,     // numeric factorisations
+    PC_PDELTA_STATIONARY,  // P-Delta batches solved by the stationary iteration on the elastic factor
+    PC_PDELTA_PERCOLUMN,   // P-Delta columns finished by preconditioned GMRES (or their own factorisation)
+    PC_COUNT
+};
+
 struct DirectSolver;   // pn_direct.cu
 struct FastAssembly;   // pn_assemble.cu
 
@@ -250,6 +266,9 @@ struct Ctx {
     std::vector<double> h_rxn_rows;
     Profiler prof;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // pn_timer_start / pn_timer_stop
+    // which kernel families the direct solver took since pn_reset_stats (pn_get_counter): the parity tests assert from
+    // these that a model is large enough to exercise the production paths of the big configurations
+    int64_t ctr[PC_COUNT] = {0};
 };
 
 void prof_flush(Ctx *c);
@@ -330,6 +349,10 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
                            cudaStream_t st);
 void launch_member_pdelta_forces(Ctx *c, const double *D_dev, bool supported_only, double *F_dev, cudaStream_t st);
 void launch_forces_to_local(Ctx *c, int kind, double *F_dev, cudaStream_t st);
+
+// ---- pn_stress.cu ---------------------------------------------------------------------------------
+void launch_shell_stress(Ctx *c, bool quad, const double *D_dev, int n_combo, int n_pts, const double *pts_dev, int local,
+                         double *out_dev, cudaStream_t st);
 
 // ---- pn_sparse.cu ---------------------------------------------------------------------------------
 void build_symbolic(Ctx *c, uint32_t flags);

@@ -112,6 +112,7 @@ SIGNATURES = {
     'pn_set_displacements': (ct.c_int, [_P, ct.c_int32, _F64P]),
     'pn_reactions': (ct.c_int, [_P, ct.c_int32, ct.c_int32, _F64P]),
     'pn_element_forces': (ct.c_int, [_P, ct.c_int, ct.c_int32, ct.c_int32, ct.c_int32, _F64P]),
+    'pn_shell_stresses': (ct.c_int, [_P, ct.c_int, ct.c_int32, ct.c_int32, ct.c_int32, _F64P, ct.c_int32, _F64P]),
     'pn_set_stream': (ct.c_int, [_P, ct.c_void_p, ct.c_int]),
     'pn_node_row_starts': (ct.c_int, [_P, ct.POINTER(ct.c_int64)]),
     'pn_prefetch_analysis': (ct.c_int, [_P]),
@@ -129,6 +130,8 @@ SIGNATURES = {
     'pn_spmm_k11': (ct.c_int, [_P, ct.c_int32, _F64P, _F64P, ct.c_int32, _F64P]),
     'pn_get_stats': (ct.c_int, [_P, ct.POINTER(Stats)]),
     'pn_reset_stats': (ct.c_int, [_P]),
+    'pn_get_counter': (ct.c_int, [_P, ct.c_char_p, ct.POINTER(ct.c_int64)]),
+    'pn_counter_name': (ct.c_char_p, [ct.c_int]),
     'pn_timer_start': (ct.c_int, [_P]),
     'pn_timer_stop': (ct.c_int, [_P, _F64P]),
     'pn_profile_enable': (ct.c_int, [_P, ct.c_int]),
@@ -405,6 +408,15 @@ class Engine:
                                                 _ptr(out, _F64P)))
         return out
 
+    def shell_stresses(self, kind, combo0, n_combo, pts, local=True):
+        """[n_combo][count][n_pts][9] internal shears / moments / membrane stresses of every quad or plate."""
+        kind = KIND.get(kind, kind)
+        pts = _c(pts, np.float64).reshape(-1, 2)
+        out = np.empty((n_combo, self.counts[kind], len(pts), 9))
+        self._check(self._lib.pn_shell_stresses(self._h, kind, combo0, n_combo, len(pts), _ptr(pts, _F64P), 1 if local else 0,
+                                                _ptr(out, _F64P)))
+        return out
+
     def spmm_k11(self, X, repeat=1):
         X = _c(X, np.float64)
         Y = np.empty_like(X)
@@ -492,3 +504,17 @@ class Engine:
 
     def reset_stats(self):
         self._check(self._lib.pn_reset_stats(self._h))
+
+    def counters(self):
+        """{name: count} of the direct solver's kernel families since `reset_stats` (`pn_get_counter`)."""
+        out = {}
+        i = 0
+        while True:
+            name = self._lib.pn_counter_name(i)
+            if not name:
+                break
+            v = ct.c_int64(0)
+            self._check(self._lib.pn_get_counter(self._h, name, ct.byref(v)))
+            out[name.decode()] = v.value
+            i += 1
+        return out

@@ -54,3 +54,16 @@ def max_over_ranks(x, device=None):
     t = torch.tensor([float(x)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def any_rank_failed(failed, device=None):
+    """Collective OR of a per-rank failure flag: every rank learns whether any rank raised, so that an exception on one
+    rank (singular matrix, unstable node) is raised everywhere instead of leaving the others blocked in a collective."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = world()
+    if ws == 1:
+        return bool(failed)
+    t = torch.tensor([1.0 if failed else 0.0], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(t.item() > 0)

@@ -53,6 +53,8 @@ def reference_run(build, mode):
             ref.analyze_linear(sparse=True)
         elif mode == 'tc':
             ref.analyze(sparse=True)
+        elif mode == 'tc_steps':
+            ref.analyze(sparse=True, **models.TC_STEPS_KW)
         else:
             ref.analyze_PDelta(sparse=True)
     return ref
@@ -106,6 +108,27 @@ def collect(ref, mode):
     out['ref_plate_F'] = np.array([[np.asarray(p.F(c)).reshape(-1) for p in ref.plates.values()]
                                    for c in combos]).reshape(len(combos), -1, 24)
     out['ref_sub_names'] = np.array([s.name for s in subs])
+    # internal shears / moments / membrane stresses (Quad3D.py:1017-1239, Plate3D.py:590-692) at the points of
+    # oracle.model.STRESS_POINTS (quads, natural coordinates) / PLATE_FRACTIONS (plates, fractions of width and height)
+    from oracle.model import STRESS_POINTS, PLATE_FRACTIONS
+
+    def nine(Q, M, S):
+        v = np.zeros(9)
+        Q, M, S = (np.asarray(x, dtype=float).reshape(-1) for x in (Q, M, S))
+        v[:len(Q)] = Q
+        v[3:6] = M
+        v[6:9] = S
+        return v
+    for loc, tag in ((True, 'local'), (False, 'global')):
+        out['ref_quad_stress_' + tag] = np.array(
+            [[[nine(q.shear(xi, eta, loc, c), q.moment(xi, eta, loc, c), q.membrane(xi, eta, loc, c))
+               for (xi, eta) in STRESS_POINTS] for q in ref.quads.values()] for c in combos]).reshape(
+            len(combos), len(ref.quads), len(STRESS_POINTS), 9)
+    out['ref_plate_stress'] = np.array(
+        [[[nine(p.shear(fx*p.width(), fy*p.height(), True, c), p.moment(fx*p.width(), fy*p.height(), True, c),
+                p.membrane(fx*p.width(), fy*p.height(), True, c))
+           for (fx, fy) in PLATE_FRACTIONS] for p in ref.plates.values()] for c in combos]).reshape(
+        len(combos), len(ref.plates), len(PLATE_FRACTIONS), 9)
     if mode == 'pdelta':
         Kg = ref.Kg(first, False, True, False)
         out['ref_kg_row'] = np.asarray(Kg.row, dtype=np.int64)
@@ -130,13 +153,13 @@ def flatten_pair(build, ref, mode):
     B = flatten_model(ref, list(ref.load_combos.values()))
     for f in ARRAY_FIELDS:
         a, b = getattr(A, f), getattr(B, f)
-        if mode == 'tc' and f in ('spring_active', 'mem_active', 'nspring_flag'):
+        if mode in ('tc', 'tc_steps') and f in ('spring_active', 'mem_active', 'nspring_flag'):
             continue
         if a.shape != b.shape or not np.array_equal(a, b):
             raise AssertionError(f'flattened field {f} differs between pynite_b200 and the reference object graph')
     assert A.cases == B.cases and A.combo_names == B.combo_names
     assert [s.name for s in A.sub_members] == [s.name for s in B.sub_members]
-    src = B if mode == 'tc' else A
+    src = B if mode in ('tc', 'tc_steps') else A
     out = {'in_' + f: getattr(src, f) for f in ARRAY_FIELDS}
     out['in_n_nodes'] = np.array(A.n_nodes)
     out['in_cases'] = np.array(A.cases)

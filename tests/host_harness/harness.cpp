@@ -4,6 +4,7 @@
 // Nothing in the product package loads this library.
 #include "../../pynite_b200/csrc/elem_line.cuh"
 #include "../../pynite_b200/csrc/elem_shell.cuh"
+#include "../../pynite_b200/csrc/elem_stress.cuh"
 
 extern "C" {
 
@@ -102,6 +103,65 @@ void hh_shell_fer(const double *pts, const double *props, int is_quad, double pr
         }
         pn_rot_to_global(R, tl, out24 + 6*a);
         pn_rot_to_global(R, rl, out24 + 6*a + 3);
+    }
+}
+
+// Internal shears / moments / membrane stresses of one shell (sequential restatement of k_shell_stress in
+// pynite_b200/csrc/pn_stress.cu): D24 = global displacements of the four nodes, pts[n_pts][2], out[n_pts][9].
+void hh_shell_stress(const double *pts12, const double *props, int is_quad, const double *D24, int n_pts, const double *pts,
+                     int local, double *out) {
+    double p[4][3];
+    for (int a = 0; a < 4; ++a) for (int k = 0; k < 3; ++k) p[a][k] = pts12[3*a+k];
+    double R[9];
+    pn_shell_dircos(p[0], p[1], p[3], R);
+    PnShellMat mat;
+    pn_shell_material(props, mat);
+    PnShellGeom G;
+    double width = 0, height = 0, cinv[144];
+    if (is_quad) {
+        pn_quad_local_xy(p, G.xl, G.yl);
+        pn_quad_edges(G, props[0], props[2]);
+    } else {
+        double d;
+        d = 0; for (int k = 0; k < 3; ++k) d += (p[0][k]-p[1][k])*(p[0][k]-p[1][k]); width = sqrt(d);
+        d = 0; for (int k = 0; k < 3; ++k) d += (p[0][k]-p[3][k])*(p[0][k]-p[3][k]); height = sqrt(d);
+        G.xl[0] = 0; G.yl[0] = 0; G.xl[1] = width; G.yl[1] = 0; G.xl[2] = width; G.yl[2] = height; G.xl[3] = 0; G.yl[3] = height;
+        double pw[7], ph[7];
+        pn_plate_powers(width, pw);
+        pn_plate_powers(height, ph);
+        for (int k = 0; k < 144; ++k) cinv[k] = pn_plate_cinv_entry(k, pw, ph);
+    }
+    PnGpNode rec[16];
+    for (int t = 0; t < 16; ++t) pn_shell_gp_node(G, t >> 2, t & 3, is_quad != 0, rec[t]);
+    double d[24];
+    for (int a = 0; a < 4; ++a) {
+        double tr[3] = {D24[6*a], D24[6*a+1], D24[6*a+2]}, ro[3] = {D24[6*a+3], D24[6*a+4], D24[6*a+5]};
+        pn_rot_to_local(R, tr, d + 6*a);
+        pn_rot_to_local(R, ro, d + 6*a + 3);
+    }
+    double V[4][8], a12[12];
+    pn_shell_gp_values(rec, mat, d, is_quad != 0, V);
+    if (!is_quad)
+        for (int i = 0; i < 12; ++i) {
+            double acc = 0.0;
+            for (int q = 0; q < 12; ++q) acc = fma(cinv[12*i + q], d[6*(q/3) + 2 + q % 3], acc);
+            a12[i] = acc;
+        }
+    for (int q = 0; q < n_pts; ++q) {
+        const double u = pts[2*q], v = pts[2*q+1];
+        double loc[8], res[9];
+        if (is_quad) {
+            pn_shell_extrapolate(V, u, v, 0, 8, loc);
+            if (local) { res[0] = loc[0]; res[1] = loc[1]; res[2] = 0.0; for (int k = 2; k < 8; ++k) res[k+1] = loc[k]; }
+            else pn_quad_stress_global(R, loc, res);
+        } else {
+            pn_shell_extrapolate(V, -1 + 2*u/width, -1 + 2*v/height, 5, 8, loc);
+            double b5[5];
+            pn_plate_bending_results(props, a12, u, v, b5);
+            res[0] = b5[0]; res[1] = b5[1]; res[2] = 0.0; res[3] = b5[2]; res[4] = b5[3]; res[5] = b5[4];
+            res[6] = loc[5]; res[7] = loc[6]; res[8] = loc[7];
+        }
+        for (int k = 0; k < 9; ++k) out[9*q + k] = res[k];
     }
 }
 }

@@ -282,6 +282,26 @@ def pdelta_column(FE):
     return m
 
 
+def pdelta_near_buckling(FE):
+    """The cantilever of `pdelta_column` loaded to 0.6 ... 0.95 of its in-plane Euler load (P_cr = pi^2 E Iz / (4 L^2)
+    = 633 kip for bending about z): Ke + Kg is close to singular in plane and already indefinite out of plane
+    (weak-axis P_cr = 229 kip), which is where an unpivoted factorisation of Ke + Kg must not be trusted."""
+    m = FE()
+    m.add_material('Steel', 29000.0, 11200.0, 0.3, 2.836e-4)
+    m.add_section('W14', 26.5, 362.0, 999.0, 5.45)
+    n = 7
+    for i in range(n):
+        m.add_node('N' + str(i + 1), 0, i*28.0*12/(n - 1), 0)
+    m.add_member('M1', 'N1', 'N' + str(n), 'Steel', 'W14')
+    m.def_support('N1', True, True, True, True, True, True)
+    m.add_node_load('N' + str(n), 'FX', 1.0, case='H')
+    m.add_node_load('N' + str(n), 'FZ', 0.05, case='H')
+    m.add_node_load('N' + str(n), 'FY', -100.0, case='P')
+    for i, p in enumerate((1.2, 3.8, 5.0, 5.7, 6.0)):
+        m.add_load_combo('C' + str(i + 1), {'H': 1.0, 'P': p})
+    return m
+
+
 def braced_tc(FE):
     """Braced bay with tension-only diagonals, a compression-only node support spring and a tension-only
     spring element: exercises `_check_TC_convergence` (`Analysis.py:917-1056`)."""
@@ -415,6 +435,34 @@ def big_quad_plate(FE, n=500, n_combos=64, a=12.0, t=8.0, seed=20261019):
     return m
 
 
+def tc_load_steps(FE):
+    """Propped cantilever whose prop is a compression-only support spring that engages only once the tip has moved
+    by more than the spring tolerance, plus a tension-only tie: with `analyze(num_steps=4, spring_tolerance=0.05)`
+    the spring flips in the middle of the load stepping (`Analysis._first_order` :262-305 undo / redo branches)."""
+    m = FE()
+    m.add_material('Steel', 29000.0, 11200.0, 0.3, 2.836e-4)
+    m.add_section('Beam', 10.0, 100.0, 150.0, 5.0)
+    m.add_node('A', 0, 0, 0)
+    m.add_node('B', 120, 0, 0)
+    m.add_node('C', 240, 0, 0)
+    m.add_node('T', 240, 60, 0)
+    m.def_support('A', True, True, True, True, True, True)
+    m.def_support('T', True, True, True, True, True, True)
+    m.add_member('AB', 'A', 'B', 'Steel', 'Beam')
+    m.add_member('BC', 'B', 'C', 'Steel', 'Beam')
+    m.def_support_spring('C', 'DY', 1.0, '-')
+    m.def_support_spring('B', 'DY', 8.0, '+')
+    m.add_spring('TIE', 'C', 'T', 4.0, tension_only=True)
+    m.add_node_load('C', 'FY', -6.0, case='G')
+    m.add_node_load('B', 'FY', -3.0, case='G')
+    m.add_member_dist_load('AB', 'Fy', -0.01, -0.01, case='G')
+    m.add_node_load('C', 'FY', 5.0, case='U')
+    m.add_load_combo('G', {'G': 1.0})
+    m.add_load_combo('G+U', {'G': 1.0, 'U': 1.6})
+    m.add_load_combo('0.5G', {'G': 0.5})
+    return m
+
+
 SMALL_MODELS = {
     'space_frame': (space_frame, 'tc'),
     'portal_frame': (portal_frame, 'linear'),
@@ -429,4 +477,10 @@ SMALL_MODELS = {
     'pdelta_column': (pdelta_column, 'pdelta'),
     'pdelta_frame': (lambda FE: moment_frame(FE, bays_x=2, bays_z=1, stories=4, interior=1, n_combos=4), 'pdelta'),
     'braced_tc': (braced_tc, 'tc'),
+    'pdelta_near_buckling': (pdelta_near_buckling, 'pdelta'),
+    'tc_load_steps': (tc_load_steps, 'tc_steps'),
 }
+
+# keyword arguments of `analyze` for the load-stepping fixture (mode 'tc_steps')
+TC_STEPS_KW = dict(num_steps=4, spring_tolerance=0.2, member_tolerance=0.0)
+

@@ -77,6 +77,39 @@ def test_shell_elements(libs, name):
                 assert np.array_equal(K != 0.0, R != 0.0), (kind, e)
 
 
+@pytest.mark.parametrize('name', ['quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz', 'skew_shell', 'mat_foundation',
+                                  'mixed_building'])
+def test_shell_stress_math(libs, name):
+    """`elem_stress.cuh` (what `k_shell_stress` evaluates per element and combo) against the values the reference's
+    `Quad3D.shear/moment/membrane` and `Plate3D.shear/moment/membrane` returned, from the reference's displacements."""
+    hh, _ = libs
+    A, ref, _ = load_fixture(name)
+    # (compared over all combos at once: a combo of pure uniform settlement has shears that are rounding noise)
+    for kind, conn, props, is_quad in (('quad', A.quad_ijmn, A.quad_props, 1), ('plate', A.plate_ijmn, A.plate_props, 0)):
+        if not len(conn):
+            continue
+        variants = ((1, 'quad_stress_local'), (0, 'quad_stress_global')) if is_quad else ((1, 'plate_stress'),)
+        for local, key in variants:
+            got = np.empty_like(ref[key])
+            for c in range(A.factors.shape[0]):
+                D = ref['D'][c]
+                for e in range(len(conn)):
+                    p4 = A.xyz[conn[e]]
+                    if is_quad:
+                        pts = np.array(om.STRESS_POINTS, dtype=float)
+                    else:
+                        w = np.linalg.norm(p4[0] - p4[1]); h = np.linalg.norm(p4[0] - p4[3])
+                        pts = np.array(om.PLATE_FRACTIONS, dtype=float)*np.array([w, h])
+                    pts = np.ascontiguousarray(pts)
+                    D24 = np.ascontiguousarray(D.reshape(-1, 6)[conn[e]].reshape(-1))
+                    out = np.empty((len(pts), 9))
+                    hh.hh_shell_stress(_p(np.ascontiguousarray(p4.reshape(-1))), _p(np.ascontiguousarray(props[e])), is_quad,
+                                       _p(D24), len(pts), _p(pts), local, _p(out))
+                    got[c, e] = out
+            for k0, k1 in ((0, 3), (3, 6), (6, 9)):
+                assert rel_err(got[..., k0:k1], ref[key][..., k0:k1]) < 1e-9, (key, k0)
+
+
 @pytest.mark.parametrize('name', ['portal_frame', 'continuous_beam', 'moment_frame'])
 def test_member_fer(libs, name):
     hh, _ = libs

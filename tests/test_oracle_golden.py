@@ -5,9 +5,10 @@ import pytest
 import scipy.sparse as sps
 
 from oracle import model as om
-from tests.util import FIXTURES, GENERAL_ORIENTATION, compare_general_pattern, load_fixture, rel_err
+from tests.util import (FIXTURES, GENERAL_ORIENTATION, PDELTA_FIXTURES, TC_FIXTURES, compare_general_pattern, load_fixture,
+                        rel_err)
 
-LINEARISH = [f for f in FIXTURES if f != 'braced_tc']
+LINEARISH = [f for f in FIXTURES if f not in TC_FIXTURES]
 
 
 @pytest.mark.parametrize('name', FIXTURES)
@@ -75,7 +76,7 @@ def test_solve_linear(name):
         assert rel_err(R[c].reshape(-1), ref['Rxn'][c]) < 1e-9
 
 
-@pytest.mark.parametrize('name', ['pdelta_column', 'pdelta_frame'])
+@pytest.mark.parametrize('name', PDELTA_FIXTURES)
 def test_solve_pdelta(name):
     A, ref, _ = load_fixture(name)
     D, R = om.solve_pdelta(A)
@@ -98,3 +99,49 @@ def test_textbook_space_frame():
     expected = np.array([7.098e-5, -0.014, -2.352e-3, -3.996e-3, 1.78e-5, -1.033e-4])
     assert np.allclose(got, expected, rtol=2e-3)
     assert ref['indptr'].shape == (25,) and ref['data'].shape == (108,) and ref['coo_data'].shape == (120,)
+
+
+@pytest.mark.parametrize('name', ['quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz', 'skew_shell', 'mat_foundation',
+                                  'mixed_building'])
+def test_shell_stresses(name):
+    """Internal shears / moments / membrane stresses of quads and plates (`Quad3D.py:1017-1239`, `Plate3D.py:590-692`)
+    from the reference's own displacement vectors, against what the reference's methods returned."""
+    A, ref, _ = load_fixture(name)
+    nc = A.factors.shape[0]
+    # (compared over all combos at once: a combo of pure uniform settlement has shears that are rounding noise)
+    if len(A.quad_ijmn):
+        for local, tag in ((True, 'local'), (False, 'global')):
+            got = np.array([om.shell_stresses(A, ref['D'][c], 'quad', om.STRESS_POINTS, local) for c in range(nc)])
+            for k0, k1 in ((0, 3), (3, 6), (6, 9)):
+                assert rel_err(got[..., k0:k1], ref['quad_stress_' + tag][..., k0:k1]) < 1e-10, (tag, k0)
+    if len(A.plate_ijmn):
+        got = np.array([om.shell_stresses(A, ref['D'][c], 'plate', om.PLATE_FRACTIONS) for c in range(nc)])
+        for k0, k1 in ((0, 3), (3, 6), (6, 9)):
+            assert rel_err(got[..., k0:k1], ref['plate_stress'][..., k0:k1]) < 1e-9, k0
+
+
+def test_memoised_oracle_is_bit_identical():
+    """The oracle caches per-element results under the bits of the difference vectors the reference's routines read
+    (oracle/model.py header): with and without the cache every output must be identical, on a generated mesh (all
+    hits), on a jittered one (no hits) and on a frame with releases / rolls / interior nodes."""
+    from pynite_b200 import synthetic
+    cases = [synthetic.quad_plate_arrays(n=9, n_combos=2), synthetic.quad_plate_arrays(n=7, n_combos=2, mat_springs=0.1),
+             synthetic.moment_frame_arrays(bays_x=2, bays_z=2, stories=3, n_combos=2), load_fixture('portal_frame')[0],
+             load_fixture('mixed_building')[0]]
+    J = synthetic.quad_plate_arrays(n=8, n_combos=2)
+    J.xyz = J.xyz + np.random.default_rng(3).uniform(-0.1, 0.1, size=J.xyz.shape)*np.array([1.0, 1.0, 0.0])
+    cases.append(J)
+    for A in cases:
+        res = []
+        for memo in (False, True):
+            om.MEMOISE = memo
+            om._MEMO.clear()
+            try:
+                r, c, d = om.assemble_coo(A)
+                D, R = om.solve_linear(A)
+                P, F = om.load_vectors(A, 1)
+            finally:
+                om.MEMOISE = True
+            res.append((r, c, d, np.array(D), np.array(R), P, F))
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
