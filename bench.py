@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument('--n', type=int, default=500, help='quads per side (500 = BASELINE config 3)')
     ap.add_argument('--combos', type=int, default=64, help='load combinations: total (strong scaling) or per GPU (weak)')
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
+    ap.add_argument('--dist', default='subtree', choices=['subtree', 'combos'],
+                    help='strong scaling on N > 1 GPUs: subtree = elimination tree split across the GPUs, all combos on '
+                         'every GPU (pn_set_distributed); combos = combos split, K factorised on every GPU')
     ap.add_argument('--solver', default='direct', choices=['direct', 'pcg'])
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--cpu-n', type=int, default=96, help='quads per side of the CPU-baseline sample')
@@ -64,13 +67,24 @@ def workload_config(args, world):
     n = args.n
     total = args.combos if args.scaling == 'strong' else args.combos*world
     per = [len(x) for x in combo_shards(args, world)]
+    subtree = subtree_mode(args, world)
+    if subtree:
+        sharding = ('strong scaling, subtree-to-GPU multifrontal: every GPU assembles K, factorises and sweeps the subtrees '
+                    'below its share of the cut level for all combos, the levels above the cut are replicated; three NCCL '
+                    'all-gathers per factor + solve (update matrices, update vectors, solved rows)')
+    elif args.scaling == 'strong':
+        sharding = 'strong scaling: the combos are split across the GPUs; K is assembled and factorised on every GPU, no data-path collective'
+    else:
+        sharding = 'weak scaling: every GPU owns its own set of combos; no data-path collective'
     return {'workload': f'BASELINE config 3: {n}x{n} DKMQ quad plate, perimeter pinned, {total} load combos in total',
-            'n_dof': 6*(n + 1)*(n + 1), 'n_quads': n*n, 'combos_total': total, 'combos_per_gpu': per, 'solver': args.solver,
-            'sharding': ('strong scaling: the combos are split across the GPUs; K is assembled and factorised on every GPU, '
-                         'no data-path collective' if args.scaling == 'strong' else
-                         'weak scaling: every GPU owns its own set of combos; no data-path collective'),
+            'n_dof': 6*(n + 1)*(n + 1), 'n_quads': n*n, 'combos_total': total,
+            'combos_per_gpu': [total]*world if subtree else per, 'solver': args.solver, 'sharding': sharding,
             'l2': 'inputs larger than L2 (CSR values 236 MB, factor 8.5 GB per step); no explicit flush',
             'symbolic': 'pattern / scatter map / elimination tree built once outside the timed region for `value`, inside for `e2e`'}
+
+
+def subtree_mode(args, world):
+    return world > 1 and args.scaling == 'strong' and args.dist == 'subtree' and args.solver == 'direct'
 
 
 def combo_shards(args, world):
@@ -293,7 +307,11 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     shards = combo_shards(args, world)
-    if args.scaling == 'strong':
+    subtree = subtree_mode(args, world)
+    if subtree:
+        # one model, all combinations on every rank; the elimination tree is what is split (pn_set_distributed)
+        A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019)
+    elif args.scaling == 'strong':
         # one model, one table of --combos combinations; this rank solves rows shards[rank]
         A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019)
         A.factors = np.ascontiguousarray(A.factors[shards[rank]])
@@ -301,8 +319,11 @@ def run_ours(args, rank, local_rank, world):
     else:
         # every rank owns its own --combos combinations of the same mesh (rank-specific factor table and point loads)
         A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019 + rank)
-    my_combos = len(shards[rank])
+    my_combos = args.combos if subtree else len(shards[rank])
     eng = Engine(local_rank)
+    if subtree:
+        from pynite_b200 import distsolve
+        distsolve.attach(eng)
     opts = eng.make_opts(solver=args.solver, check_stability=True, refine_steps=2, tol=1e-10, max_iter=500000)
     units_per_step_all = A.n_dof*sum(len(x) for x in shards)      # whole job, all ranks
 
@@ -358,8 +379,9 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- end-to-end arm: host buffers in, host buffers out, everything inside the timed region ---
     n_dof = A.n_dof
-    D_host = torch.empty((my_combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
-    R_host = torch.empty((my_combos, n_dof), dtype=torch.float64, pin_memory=True).numpy()
+    n_out = len(shards[rank]) if subtree else my_combos          # combos this rank delivers to its host
+    D_host = torch.empty((n_out, n_dof), dtype=torch.float64, pin_memory=True).numpy()
+    R_host = torch.empty((n_out, n_dof), dtype=torch.float64, pin_memory=True).numpy()
     in_fields = ['xyz', 'support', 'enf_mask', 'enf_val', 'nspring_k', 'nspring_flag', 'quad_ijmn', 'quad_props', 'nl_dof',
                  'nl_case', 'nl_val', 'qp_elem', 'qp_case', 'qp_val', 'factors']
     # the step's inputs live in pinned host memory (same values, page-locked copies of the arrays the builder produced)
@@ -375,7 +397,7 @@ def run_ours(args, rank, local_rank, world):
     sup_bits = np.unpackbits(np.asarray(A.support, dtype=np.uint8).reshape(-1, 1), axis=1, bitorder='little')[:, :6].reshape(-1)
     nsf = np.asarray(A.nspring_flag, dtype=np.uint8).reshape(-1)
     n_rxn = int(np.count_nonzero((sup_bits != 0) | (((nsf & 1) != 0) & ((nsf & 2) != 0))))
-    rxn_bytes = n_rxn*my_combos*8 if n_rxn*8 < n_dof else R_host.nbytes
+    rxn_bytes = R_host.nbytes if subtree else (n_rxn*my_combos*8 if n_rxn*8 < n_dof else R_host.nbytes)
     d2h = int(D_host.nbytes + rxn_bytes)
 
     e2e_phases = {}
@@ -390,7 +412,14 @@ def run_ours(args, rank, local_rank, world):
         t.append(time.perf_counter())
         eng.assemble_ke()
         t.append(time.perf_counter())
-        eng.solve_linear(opts, reactions=True, D_out=D_host, R_out=R_host)
+        if subtree:
+            # all ranks hold all of X after the solve; each delivers its share of the combinations to its host
+            eng.solve_linear(opts, reactions=False, download=False)
+            for k, cj in enumerate(shards[rank]):
+                eng.displacements(cj, out=D_host[k])
+                eng.reactions(cj, out=R_host[k])
+        else:
+            eng.solve_linear(opts, reactions=True, D_out=D_host, R_out=R_host)
         t.append(time.perf_counter())
         for name, a, b in (('upload', 0, 1), ('symbolic', 1, 2), ('assemble', 2, 3), ('solve+reactions+download', 3, 4)):
             e2e_phases[name] = round(1e3*(t[b] - t[a]), 2)

@@ -183,6 +183,24 @@ PN_EXPORT int pn_reactions(pn_ctx *ctx, int32_t combo, int32_t pdelta, double *o
  *      pdelta != 0 uses the (ke + kg(P)) branch of Member3D.f :886-891                             */
 PN_EXPORT int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32_t pdelta, double *out);
 
+/* ---- tension/compression-only iteration on the device: Analysis._check_TC_convergence :917-1056 -----------------
+ * pn_set_tc_modes: per two-node spring and per sub-member, bit0 = tension-only, bit1 = compression-only
+ *   (Spring3D.py:25-43, Member3D.py:37-105); group_start[n_groups + 1] = sub-member range of every physical member
+ *   (a physical member is deactivated as a whole, Analysis.py:1017-1047).  Node support springs carry their
+ *   direction in spring_flag bits 2 ('+') and 3 ('-') of pn_set_nodes.
+ * pn_tc_update: for the solved combo `combo` (displacements as stored / set by pn_set_displacements) switches node
+ *   support springs with a direction on or off, deactivates springs and members whose axial force has the wrong sign
+ *   (member extremes: Member3D.max_axial / min_axial), all in kernels; *n_changed = number of state changes, 0 =
+ *   converged.  When anything changed the model's activity flags are updated in place (no re-upload) and the next
+ *   pn_symbolic / pn_assemble_ke / pn_solve_* re-assembles with them.
+ * pn_tc_reset: every spring and member active again (start of a new combination, Analysis.py:68-79); node support
+ *   springs keep their state, as in the reference.  pn_get_activity: current flags (any pointer may be NULL).    */
+PN_EXPORT int pn_set_tc_modes(pn_ctx *ctx, const uint8_t *spring_mode, const uint8_t *member_mode, int64_t n_groups,
+                              const int64_t *group_start);
+PN_EXPORT int pn_tc_update(pn_ctx *ctx, int32_t combo, int32_t pdelta, double spring_tol, double member_tol, int64_t *n_changed);
+PN_EXPORT int pn_tc_reset(pn_ctx *ctx);
+PN_EXPORT int pn_get_activity(pn_ctx *ctx, uint8_t *nspring_flag, uint8_t *spring_active, uint8_t *member_active);
+
 /* ---- internal forces / stresses of shells for solved combos: Quad3D.shear :1017, moment :1096, membrane :1173
  *      (points = natural coordinates (xi, eta), values at the Gauss points extrapolated), Plate3D.shear :608,
  *      moment :590, membrane :650 (points = local (x, y); the reference's plate methods ignore `local`).
@@ -192,6 +210,24 @@ PN_EXPORT int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t lo
  *                                      1146-1171, 1214-1239)                                                        */
 PN_EXPORT int pn_shell_stresses(pn_ctx *ctx, int kind, int32_t combo0, int32_t n_combo, int32_t n_pts, const double *pts,
                                 int32_t local, double *out);
+
+/* ---- multi-GPU direct solve: subtree-to-GPU multifrontal (one pn_ctx per GPU / rank) -------------------
+ * Every rank holds the whole model and K.  The elimination tree is cut at the highest level that has at least `world`
+ * fronts: rank r factorises and sweeps the subtrees below its share of that level for ALL right-hand sides; the
+ * levels above the cut are factorised and swept by every rank (replicated).  Three exchanges per factor + solve, each
+ * an all-gather of equal-size segments:
+ *   (1) the update matrices of the subtree roots (after the local factorisation),
+ *   (2) the update vectors of the subtree roots (after the local forward sweep),
+ *   (3) the solved rows of every subtree (after the local backward sweep), so that every rank ends with all of X.
+ * The library packs its segment into a device buffer it owns and calls `allgather(user, send, recv, seg_doubles)`:
+ * the callee must all-gather send[0 : seg] of every rank into recv[r * seg : (r + 1) * seg] (r = 0 .. world-1) on every
+ * rank and return 0 once the data is visible to work submitted afterwards on the library's stream (pn_set_stream) --
+ * e.g. ncclAllGather on that stream, or torch.distributed.all_gather_into_tensor as pynite_b200/distsolve.py does.
+ * Both pointers are DEVICE pointers.  world <= 1 (or a NULL callback) switches the mode off.  A model whose tree has
+ * fewer than `world` fronts on every level is solved replicated, without exchanges.
+ * Results are bit-identical to the single-GPU solve (same kernels, same summation order).                        */
+typedef int (*pn_allgather_fn)(void *user, const double *send_dev, double *recv_dev, int64_t seg_doubles);
+PN_EXPORT int pn_set_distributed(pn_ctx *ctx, int32_t rank, int32_t world, pn_allgather_fn allgather, void *user);
 
 /* ---- device-pointer building blocks for the domain-decomposed PCG --------------------------------
  * pynite_b200/ddpcg.py runs one process per GPU; every rank holds the whole K11 (assembly is 0.1 ms), owns a
@@ -240,7 +276,7 @@ PN_EXPORT int pn_reset_stats(pn_ctx *ctx);
  * behind spsolve, Analysis.py:217).  Names: pn_counter_name(0..) until NULL -- "lu_update", "lu_update_later_groups"
  * (fronts with more than 256 pivots), "lu_strip", "split_levels" (front groups on side streams), "sweep_smem",
  * "sweep_ll", "sweep_step", "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches",
- * "pdelta_fallback_columns".  The parity tests assert from these that a mid-size model exercises the
+ * "pdelta_fallback_columns", "dist_exchanges", "dist_cut_level".  The parity tests assert from these that a mid-size model exercises the
  * kernels the full-size configurations run. */
 PN_EXPORT int pn_get_counter(pn_ctx *ctx, const char *name, int64_t *out);
 PN_EXPORT const char *pn_counter_name(int index);

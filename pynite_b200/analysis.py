@@ -232,73 +232,42 @@ def run_linear(model, log, check_stability, check_statics, sparse, combo_tags):
     model.solution = 'Linear'
 
 
-def _tc_converged(model, combo_name, log, spring_tolerance, member_tolerance):
-    """`Analysis._check_TC_convergence` (:917-1056)."""
-    convergence = True
-    if log:
-        print('- Checking for tension/compression-only support spring convergence')
-    for node in model.nodes.values():
-        for d in _DOFS:
-            spring = getattr(node, 'spring_' + d)
-            if spring[1] is not None:
-                displacement = getattr(node, d)[combo_name]
-                should_be_active = ((spring[1] == '-' and displacement <= -spring_tolerance) or
-                                    (spring[1] == '+' and displacement >= spring_tolerance))
-                if spring[2] != should_be_active:
-                    spring[2] = should_be_active
-                    convergence = False
-    if log:
-        print('- Checking for tension/compression-only spring convergence')
-    for spring in model.springs.values():
-        if spring.active[combo_name] == True:   # noqa: E712
-            if spring.tension_only and spring.axial(combo_name) > spring_tolerance:
-                if log:
-                    print(f'- Deactivating spring {spring.name}')
-                spring.active[combo_name] = False
-                convergence = False
-            elif spring.comp_only and spring.axial(combo_name) < -spring_tolerance:
-                if log:
-                    print(f'- Deactivating spring {spring.name}')
-                spring.active[combo_name] = False
-                convergence = False
-    if log:
-        print('- Checking for tension/compression-only member convergence')
-    for phys_member in model.members.values():
-        if phys_member.active[combo_name] == True:   # noqa: E712
-            deactivate = False
-            if phys_member.tension_only and phys_member.max_axial(combo_name) > member_tolerance:
-                deactivate = True
-            elif phys_member.comp_only and phys_member.min_axial(combo_name) < -member_tolerance:
-                deactivate = True
-            if deactivate:
-                if log:
-                    print(f'- Deactivating member {phys_member.name}')
-                phys_member.active[combo_name] = False
-                for sub in phys_member.sub_members.values():
-                    sub.active[combo_name] = False
-                convergence = False
-        for sub in phys_member.sub_members.values():
-            sub._solved_combo = None
-    return convergence
-
-
-def _refresh_activity(model, eng, A, combo_name):
-    """Re-reads the flags `_check_TC_convergence` may have flipped and uploads them."""
-    nodes = list(model.nodes.values())
-    for k, d in enumerate(_DOFS):
-        for i, nd in enumerate(nodes):
-            sp = getattr(nd, 'spring_' + d)
-            if sp[0] is not None:
-                A.nspring_flag[i, k] = (A.nspring_flag[i, k] & ~np.uint8(2)) | (2 if sp[2] == True else 0)   # noqa: E712
-    A.spring_active[:] = [1 if s.active.get(combo_name, True) == True else 0 for s in model.springs.values()]   # noqa: E712
-    act = []
+def _set_tc_modes(model, eng, A):
+    """Element modes for `pn_tc_update`: bit0 tension-only, bit1 compression-only; physical members as sub-member ranges."""
+    smode = np.array([(1 if s.tension_only else 0) | (2 if s.comp_only else 0) for s in model.springs.values()], dtype=np.uint8)
+    mmode, starts = [], [0]
     for pm in model.members.values():
-        on = 1 if pm.active.get(combo_name, True) == True else 0   # noqa: E712
-        act.extend([on]*len(pm.sub_members))
-    A.mem_active[:] = act
-    eng.set_nodes(A)
-    eng.set_springs(A)
-    eng.set_members(A)
+        md = (1 if pm.tension_only else 0) | (2 if pm.comp_only else 0)
+        mmode.extend([md]*len(pm.sub_members))
+        starts.append(len(mmode))
+    eng.set_tc_modes(smode, np.array(mmode, dtype=np.uint8), np.array(starts, dtype=np.int64))
+
+
+def _mirror_activity(model, combo_name, flags, log, before=None):
+    """Writes the device's activity flags back into the objects the reference keeps them in (`Node3D.spring_D*[2]`,
+    `Spring3D.active[combo]`, `PhysMember.active[combo]` and its sub-members), touching only the elements that can
+    change state.  With `log` the deactivations since `before` are printed like `_check_TC_convergence` does."""
+    nsf, sa, ma = flags
+    nodes = list(model.nodes.values())
+    for i, k in zip(*np.nonzero(nsf & 12)):
+        getattr(nodes[int(i)], 'spring_' + _DOFS[int(k)])[2] = bool(nsf[i, k] & 2)
+    for i, spring in enumerate(model.springs.values()):
+        if spring.tension_only or spring.comp_only:
+            on = bool(sa[i])
+            if log and before is not None and before[1][i] and not on:
+                print(f'- Deactivating spring {spring.name}')
+            spring.active[combo_name] = on
+    k = 0
+    for pm in model.members.values():
+        nsub = len(pm.sub_members)
+        if (pm.tension_only or pm.comp_only) and nsub:
+            on = bool(ma[k])
+            if log and before is not None and before[2][k] and not on:
+                print(f'- Deactivating member {pm.name}')
+            pm.active[combo_name] = on
+            for sub in pm.sub_members.values():
+                sub.active[combo_name] = on
+        k += nsub
 
 
 def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_tolerance, member_tolerance,
@@ -307,6 +276,7 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
     A, eng = _upload(model, combo_list, combo_list[0].name if combo_list else None)
     model._run = RunState(A, [c.name for c in combo_list])
     model._run.pdelta = pdelta
+    _set_tc_modes(model, eng, A)
     n = A.n_dof
     flags = _eng.PN_SYM_DENSE_MEMBER_BLOCKS if pdelta else 0
     for ci, combo in enumerate(combo_list):
@@ -314,6 +284,8 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
             print('')
             print('- Analyzing load combination ' + combo.name)
         eng.set_combos(A.factors[ci:ci + 1])
+        if ci > 0:
+            eng.tc_reset()          # springs / members start every combination active; node support springs keep their state
         model._run.engine_combo = {combo.name: 0}
         model._run.force_cache = {}
         total = np.zeros((n, 1))
@@ -329,7 +301,6 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
                 if log:
                     print(f'- Analyzing load step #{load_step}' if not pdelta else
                           '- Beginning tension/compression-only iteration #' + str(iter_count))
-                _refresh_activity(model, eng, A, combo.name)
                 _assemble(model, eng, check_stability, log, flags)
                 try:
                     if pdelta:
@@ -345,7 +316,13 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
                 model._D[combo.name] = total
                 eng.set_displacements(0, total)
                 model._run.force_cache = {}
-                converged = _tc_converged(model, combo.name, log, spring_tolerance, member_tolerance)
+                # `_check_TC_convergence` (:917-1056) in kernels: flags, displacements and end forces stay on the device
+                if log:
+                    print('- Checking for tension/compression-only support spring, spring and member convergence')
+                before = eng.activity(A.n_nodes) if log else None
+                converged = eng.tc_update(0, pdelta, spring_tolerance, member_tolerance) == 0
+                if log and not converged:
+                    _mirror_activity(model, combo.name, eng.activity(A.n_nodes), True, before)
                 if not converged:
                     if log:
                         print(f'- Undoing load step #{load_step} due to failed convergence.')
@@ -354,6 +331,7 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
                 else:
                     load_step += 1
                 iter_count += 1
+        _mirror_activity(model, combo.name, eng.activity(A.n_nodes), False)
         # reactions with this combo's final element activity (`_calc_reactions`, :1059-1313)
         model._Rxn[combo.name] = eng.reactions(0, pdelta)
         # element end forces must stay readable after the engine moves on to the next combo

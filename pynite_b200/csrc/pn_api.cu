@@ -938,6 +938,91 @@ int pn_shell_stresses(pn_ctx *ctx, int kind, int32_t combo0, int32_t n_combo, in
     PN_API_END
 }
 
+int pn_set_tc_modes(pn_ctx *ctx, const uint8_t *spring_mode, const uint8_t *member_mode, int64_t n_groups,
+                    const int64_t *group_start) {
+    PN_API_BEGIN(ctx)
+    const Model &m = c->model;
+    if ((m.n_springs && !spring_mode) || (m.n_members && (!member_mode || !group_start))) throw ArgError("pn_set_tc_modes: null array");
+    if (m.n_members && (n_groups < 1 || group_start[0] != 0 || group_start[n_groups] != m.n_members))
+        throw ArgError("pn_set_tc_modes: group_start must cover all sub-members");
+    c->tc_spring_mode.upload(spring_mode, m.n_springs, c->stream);
+    c->tc_member_mode.upload(member_mode, m.n_members, c->stream);
+    c->tc_n_groups = m.n_members ? n_groups : 0;
+    c->tc_group_start.upload(group_start, m.n_members ? n_groups + 1 : 0, c->stream);
+    c->tc_any_member_mode = false;
+    for (int64_t e = 0; e < m.n_members; ++e) if (member_mode[e]) c->tc_any_member_mode = true;
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    PN_API_END
+}
+
+// the activity flags changed on the device: refresh the host copies and drop what depends on them
+static void tc_sync_activity(Ctx *c, bool elements_changed) {
+    Model &m = c->model;
+    cudaStream_t st = c->stream;
+    if (m.nspring_flag.n) PN_CUDA(cudaMemcpyAsync(m.h_nspring_flag.data(), m.nspring_flag.ptr, m.nspring_flag.n, cudaMemcpyDeviceToHost, st));
+    if (m.n_springs) PN_CUDA(cudaMemcpyAsync(m.h_spring_active.data(), m.spring_active.ptr, m.n_springs, cudaMemcpyDeviceToHost, st));
+    if (m.n_members) PN_CUDA(cudaMemcpyAsync(m.h_mem_active.data(), m.mem_active.ptr, m.n_members, cudaMemcpyDeviceToHost, st));
+    PN_CUDA(cudaStreamSynchronize(st));
+    if (elements_changed) { invalidate(c); return; }
+    // only node support springs switched: the element graph (and with it the ordering of the direct solver) is unchanged
+    c->rxn_list_ready = false;
+    c->ev_ready = false;
+    c->symbolic_ready = false;
+    c->vals_ready = false;
+    c->solved = c->solved_pdelta = false;
+}
+
+int pn_tc_update(pn_ctx *ctx, int32_t combo, int32_t pdelta, double spring_tol, double member_tol, int64_t *n_changed) {
+    PN_API_BEGIN(ctx)
+    if (!c->solved || combo < 0 || combo >= c->loads.n_combo || !n_changed) throw ArgError("pn_tc_update: combo has not been solved");
+    build_incidence(c);
+    ensure_loads(c);
+    Model &m = c->model;
+    // element flags before, to tell element deactivations from node-spring switches
+    std::vector<uint8_t> s0 = m.h_spring_active, m0 = m.h_mem_active;
+    const int64_t n = tc_update(c, combo, pdelta != 0, spring_tol, member_tol);
+    *n_changed = n;
+    if (n > 0) {
+        tc_sync_activity(c, false);
+        if (s0 != m.h_spring_active || m0 != m.h_mem_active) invalidate(c);
+    }
+    PN_API_END
+}
+
+int pn_tc_reset(pn_ctx *ctx) {
+    PN_API_BEGIN(ctx)
+    Model &m = c->model;
+    bool any = false;
+    for (uint8_t a : m.h_spring_active) if (!a) any = true;
+    for (uint8_t a : m.h_mem_active) if (!a) any = true;
+    if (any) {
+        tc_reset_elements(c);
+        tc_sync_activity(c, true);
+    }
+    PN_API_END
+}
+
+int pn_get_activity(pn_ctx *ctx, uint8_t *nspring_flag, uint8_t *spring_active, uint8_t *member_active) {
+    PN_API_BEGIN(ctx)
+    const Model &m = c->model;
+    if (nspring_flag && !m.h_nspring_flag.empty()) memcpy(nspring_flag, m.h_nspring_flag.data(), m.h_nspring_flag.size());
+    if (spring_active && m.n_springs) memcpy(spring_active, m.h_spring_active.data(), (size_t)m.n_springs);
+    if (member_active && m.n_members) memcpy(member_active, m.h_mem_active.data(), (size_t)m.n_members);
+    PN_API_END
+}
+
+int pn_set_distributed(pn_ctx *ctx, int32_t rank, int32_t world, pn_allgather_fn allgather, void *user) {
+    PN_API_BEGIN(ctx)
+    if (world > 1 && (rank < 0 || rank >= world)) throw ArgError("pn_set_distributed: rank out of range");
+    if (world > 1 && !allgather) throw ArgError("pn_set_distributed: null all-gather callback");
+    c->dist_rank = world > 1 ? rank : 0;
+    c->dist_world = world > 1 ? world : 1;
+    c->dist_allgather = world > 1 ? allgather : nullptr;
+    c->dist_user = user;
+    direct_set_distributed(c);
+    PN_API_END
+}
+
 int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repeat, double *ms_out) {
     PN_API_BEGIN(ctx)
     if (!c->vals_ready) throw ArgError("pn_spmm_k11: call pn_assemble_ke first");
@@ -1157,7 +1242,8 @@ int pn_reset_stats(pn_ctx *ctx) {
 
 static const char *kCounterNames[PC_COUNT] = {
     "lu_update", "lu_update_later_groups", "lu_strip", "split_levels", "sweep_smem", "sweep_ll", "sweep_step",
-    "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches", "pdelta_fallback_columns"};
+    "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches", "pdelta_fallback_columns",
+    "dist_exchanges", "dist_cut_level"};
 
 const char *pn_counter_name(int index) { return (index >= 0 && index < PC_COUNT) ? kCounterNames[index] : nullptr; }
 

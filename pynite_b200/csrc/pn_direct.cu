@@ -89,8 +89,28 @@ struct FrontDev {
     int32_t ns, nb, parent, child_rank;
 };
 
+// Subtree-to-GPU distribution of the elimination tree (pn_set_distributed).  Fronts are level-major and, inside a level,
+// in post-order, so the fronts of one subtree form a contiguous run on every level: rank r owns fronts [lo[l], hi[l]) of
+// every level l <= cut and everything above the cut is replicated.
+struct DistPlan {
+    bool active = false;                      // world > 1 and the tree is wide enough
+    int cut = -1;                             // level of the subtree roots
+    std::vector<int32_t> lo, hi;              // [n_levels] this rank's front range per level (all fronts above the cut)
+    std::vector<int32_t> cut_lo, cut_hi;      // [world] ranges of the cut level per rank
+    std::vector<int64_t> um_off;              // per cut-level front (index inside the level): offset of its update matrix in its owner's segment
+    std::vector<int64_t> uv_off;              // ... of its update-vector rows (to be scaled by s)
+    int64_t um_seg = 0, uv_seg = 0;           // segment sizes (doubles; uv in rows)
+    std::vector<int64_t> pos_lo, pos_hi;      // [world] elimination-position range whose solved rows the rank owns
+    int64_t x_seg = 0;                        // max rows of a rank's range
+    DevBuf<int64_t> d_um_off, d_uv_off;
+    DevBuf<int32_t> d_cut_owner;
+    DevBuf<double> send, recv;
+};
+
 struct DirectSolver {
     DirectSym sym;
+    DistPlan dist;
+    DevBuf<int32_t> pos_dof;                  // K11 row at every elimination position
     bool analysed = false;
     int n_levels = 0;
     std::vector<int32_t> level_ptr;           // fronts are stored level-major on the device
@@ -178,13 +198,55 @@ __global__ void k_entry_maps(int64_t nnz, const int32_t *__restrict__ ent_row, c
 // ------------------------------------------------------------------------------------------------
 // numeric factorisation kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void k_assemble_entries(int64_t nnz, int level, const uint8_t *__restrict__ ent_level,
+__global__ void k_assemble_entries(int64_t nnz, int level, int f_lo, int f_hi, const uint8_t *__restrict__ ent_level,
                                    const int32_t *__restrict__ ent_front, const uint32_t *__restrict__ ent_dst,
                                    const FrontDev *__restrict__ fronts, const double *__restrict__ vals,
                                    double *__restrict__ arena) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= nnz || ent_level[k] != level) return;
-    arena[fronts[ent_front[k]].f_off + ent_dst[k]] = vals[k];
+    const int f = ent_front[k];
+    if (f < f_lo || f >= f_hi) return;         // (subtree-to-GPU: fronts of other ranks' subtrees)
+    arena[fronts[f].f_off + ent_dst[k]] = vals[k];
+}
+
+// ---- subtree-to-GPU exchanges (DistPlan) ---------------------------------------------------------------------------
+// update matrix (trailing nb x nb block, row-major with ld = n) of cut-level fronts <-> contiguous nb x nb segments.
+// grid = (front of the range, row chunk).  pack: arena -> buf;  unpack: buf -> arena.
+__global__ void k_dist_um(int first, const FrontDev *__restrict__ fronts, int cut_first, const int64_t *__restrict__ um_off,
+                          double *__restrict__ arena, double *__restrict__ buf, int unpack, int sym) {
+    const int q = first + blockIdx.x;
+    const FrontDev F = fronts[q];
+    const int n = F.ns + F.nb;
+    double *seg = buf + um_off[q - cut_first];
+    for (int a = blockIdx.y; a < F.nb; a += gridDim.y) {
+        double *row = arena + F.f_off + (int64_t)(F.ns + a) * n + F.ns;
+        double *srow = seg + (int64_t)a * F.nb;
+        const int bend = sym ? a + 1 : F.nb;       // symmetric mode keeps the lower triangle only
+        if (unpack) for (int b = threadIdx.x; b < bend; b += blockDim.x) row[b] = srow[b];
+        else        for (int b = threadIdx.x; b < bend; b += blockDim.x) srow[b] = row[b];
+    }
+}
+// update vectors: rows [ns, n) x s of the fronts' solve workspaces <-> contiguous segments
+__global__ void k_dist_uv(int first, int s, const FrontDev *__restrict__ fronts /* w_off scaled by s */, int cut_first,
+                          const int64_t *__restrict__ uv_off, double *__restrict__ W, double *__restrict__ buf, int unpack) {
+    const int q = first + blockIdx.x;
+    const FrontDev F = fronts[q];
+    double *w = W + F.w_off + (int64_t)F.ns * s;
+    double *seg = buf + uv_off[q - cut_first] * s;
+    const int64_t total = (int64_t)F.nb * s;
+    for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.y * blockDim.x) {
+        if (unpack) w[t] = seg[t]; else seg[t] = w[t];
+    }
+}
+// solved rows by elimination position: X[pos_dof[p]] <-> buf[p - p0], p in [p0, p1)
+__global__ void k_dist_x(int64_t p0, int64_t p1, int s, const int32_t *__restrict__ pos_dof, double *__restrict__ X,
+                         double *__restrict__ buf, int unpack) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (p1 - p0) * s) return;
+    const int64_t p = p0 + t / s;
+    const int j = (int)(t % s);
+    double *x = X + (int64_t)pos_dof[p] * s + j;
+    if (unpack) *x = buf[t]; else buf[t] = *x;
 }
 
 // Symmetric mode reads the strict upper triangle of a front only where the transposed panels wrote it, so only the lower
@@ -1423,6 +1485,8 @@ void direct_prefetch(Ctx *c) {
     });
 }
 
+static void build_dist_plan(Ctx *c);
+
 static void analyse(Ctx *c) {
     if (!c->direct) c->direct = new DirectSolver();
     DirectSolver &d = *c->direct;
@@ -1568,27 +1632,33 @@ static void analyse(Ctx *c) {
     int64_t amax = 0;
     for (int l = 0; l < d.n_levels; ++l) amax = std::max(amax, d.level_f_total[l]);
     d.arena[0].resize(amax); d.arena[1].resize(amax);
+    build_dist_plan(c);
     d.analysed = true;
     tick.lap("device maps + allocation");
     c->stats.factor_nnz = S.factor_entries;
     c->stats.factor_flops = S.factor_flops;
-    // flops the trailing-update kernel really performs (tile-granular, clipped to the matrix): general mode = every
-    // tile of the trailing square per pivot group, symmetric mode = the tiles that touch or lie below the diagonal
+    // flops the trailing-update kernel really performs on THIS rank (tile-granular, clipped to the matrix): general
+    // mode = every tile of the trailing square per pivot group, symmetric mode = the tiles that touch or lie below the
+    // diagonal; with a subtree-to-GPU plan only the fronts this rank factorises
     {
         static const bool force_lu = getenv("PN_FORCE_UNSYMMETRIC") != nullptr;
         const bool sym = c->model.symmetric && !force_lu;
         double upd = 0.0;
-        for (const FrontSym &fs : S.fronts) {
-            int64_t n = fs.ns + fs.nb;
-            for (int g0 = 0; g0 < fs.ns; g0 += GB) {
-                int ge = std::min(g0 + GB, fs.ns);
-                int64_t rest = n - ge;
-                double K = ge - g0;
-                // executed at the granularity of a warp's 32 x 32 block: blocks inside the matrix and, in symmetric
-                // mode, not strictly above the diagonal (gemm_tile's warp_on)
-                for (int64_t r = 0; r < rest; r += 32)
-                    for (int64_t cc = 0; cc < rest; cc += 32)
-                        if (!(sym && r + 31 < cc)) upd += 2.0 * K * 32.0 * 32.0;
+        for (int l = 0; l < d.n_levels; ++l) {
+            const int q0 = d.dist.active ? d.dist.lo[l] : d.level_ptr[l], q1 = d.dist.active ? d.dist.hi[l] : d.level_ptr[l + 1];
+            for (int q = q0; q < q1; ++q) {
+                const FrontDev &fs = d.h_fronts[q];
+                int64_t n = fs.ns + fs.nb;
+                for (int g0 = 0; g0 < fs.ns; g0 += GB) {
+                    int ge = std::min(g0 + GB, fs.ns);
+                    int64_t rest = n - ge;
+                    double K = ge - g0;
+                    // executed at the granularity of a warp's 32 x 32 block: blocks inside the matrix and, in symmetric
+                    // mode, not strictly above the diagonal (gemm_tile's warp_on)
+                    for (int64_t r = 0; r < rest; r += 32)
+                        for (int64_t cc = 0; cc < rest; cc += 32)
+                            if (!(sym && r + 31 < cc)) upd += 2.0 * K * 32.0 * 32.0;
+                }
             }
         }
         c->stats.update_flops = upd;
@@ -1634,6 +1704,161 @@ struct LevelProf {
     ~LevelProf() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
+// Subtree-to-GPU plan for the current tree (see DistPlan).  Level-major ids; parent ids are level-major as well.
+static void build_dist_plan(Ctx *c) {
+    DirectSolver &d = *c->direct;
+    DistPlan &P = d.dist;
+    const int world = c->dist_world, rank = c->dist_rank;
+    const int nl = d.n_levels;
+    P.active = false;
+    P.cut = -1;
+    P.lo.assign(nl, 0); P.hi.assign(nl, 0);
+    for (int l = 0; l < nl; ++l) { P.lo[l] = d.level_ptr[l]; P.hi[l] = d.level_ptr[l + 1]; }
+    c->ctr[PC_DIST_CUT_LEVEL] = -1;
+    if (world <= 1 || !c->dist_allgather || nl < 2) return;
+    int cut = -1;
+    for (int l = nl - 1; l >= 0; --l)
+        if (d.level_ptr[l + 1] - d.level_ptr[l] >= world) { cut = l; break; }
+    if (const char *e = getenv("PN_DIST_CUT_BELOW")) cut = std::max(0, cut - atoi(e));     // experiments: deeper cut
+    if (cut < 0 || cut >= nl - 1) return;              // too narrow (or every level is below the cut): replicated solve
+    const int cf = d.level_ptr[cut], nc = d.level_ptr[cut + 1] - cf;
+    // cost of every subtree: factorisation flops of its fronts (ancestor at the cut level by walking levels downwards)
+    const int nf = (int)d.h_fronts.size();
+    std::vector<int32_t> anc(nf, -1);
+    std::vector<double> cost(nc, 0.0);
+    for (int q = cf; q < cf + nc; ++q) anc[q] = q;
+    for (int l = cut - 1; l >= 0; --l)
+        for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
+            const int p = d.h_fronts[q].parent;
+            anc[q] = p >= 0 ? anc[p] : -1;
+        }
+    for (int l = 0; l <= cut; ++l)
+        for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
+            if (anc[q] < 0) continue;
+            const double ns = d.h_fronts[q].ns, nb = d.h_fronts[q].nb;
+            cost[anc[q] - cf] += 2.0 / 3.0 * ns * ns * ns + 2.0 * ns * ns * nb + 2.0 * ns * nb * nb + 1e4;
+        }
+    // contiguous blocks of the cut level, balanced by cost, at least one front per rank
+    P.cut_lo.assign(world, 0); P.cut_hi.assign(world, 0);
+    {
+        double total = 0.0;
+        for (double v : cost) total += v;
+        int q = 0;
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) {
+            P.cut_lo[r] = cf + q;
+            const int must_leave = world - 1 - r;          // one front at least for every later rank
+            acc += cost[q]; ++q;
+            while (q < nc - must_leave && acc + 0.5 * cost[q] <= total * (r + 1) / world) { acc += cost[q]; ++q; }
+            if (r == world - 1) q = nc;
+            P.cut_hi[r] = cf + q;
+        }
+    }
+    // per-level ranges of this rank: fronts whose cut ancestor is in [cut_lo[rank], cut_hi[rank]); contiguous per level
+    for (int l = 0; l <= cut; ++l) {
+        int lo = -1, hi = -1;
+        for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
+            const bool mine = anc[q] >= P.cut_lo[rank] && anc[q] < P.cut_hi[rank];
+            if (mine) { if (lo < 0) lo = q; hi = q + 1; }
+            else if (anc[q] < 0) throw ArgError("direct solver: a front below the cut level has no ancestor on it");
+        }
+        if (lo < 0) { lo = hi = d.level_ptr[l]; }
+        for (int q = lo; q < hi; ++q)
+            if (!(anc[q] >= P.cut_lo[rank] && anc[q] < P.cut_hi[rank])) throw ArgError("direct solver: a subtree is not contiguous on its level");
+        P.lo[l] = lo; P.hi[l] = hi;
+    }
+    // exchange layouts
+    P.um_off.assign(nc, 0); P.uv_off.assign(nc, 0);
+    P.um_seg = 0; P.uv_seg = 0;
+    std::vector<int32_t> owner(nc, 0);
+    for (int r = 0; r < world; ++r) {
+        int64_t um = 0, uv = 0;
+        for (int q = P.cut_lo[r]; q < P.cut_hi[r]; ++q) {
+            const int64_t nb = d.h_fronts[q].nb;
+            P.um_off[q - cf] = um; um += nb * nb;
+            P.uv_off[q - cf] = uv; uv += nb;
+            owner[q - cf] = r;
+        }
+        P.um_seg = std::max(P.um_seg, um);
+        P.uv_seg = std::max(P.uv_seg, uv);
+    }
+    // elimination-position range of every rank: from the first pivot of the first front of its first subtree to the last
+    // pivot of its last subtree root (top-level fronts that fall inside are replicated anyway)
+    const DirectSym &S = d.sym;
+    P.pos_lo.assign(world, 0); P.pos_hi.assign(world, 0);
+    P.x_seg = 0;
+    {
+        std::vector<int64_t> first_pos(nc, INT64_MAX), last_pos(nc, 0);
+        for (int l = 0; l <= cut; ++l)
+            for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
+                const FrontSym &fs = S.fronts[S.level_fronts[q]];
+                const int a = anc[q] - cf;
+                first_pos[a] = std::min<int64_t>(first_pos[a], fs.pos_start);
+                last_pos[a] = std::max<int64_t>(last_pos[a], (int64_t)fs.pos_start + fs.ns);
+            }
+        for (int r = 0; r < world; ++r) {
+            int64_t lo = INT64_MAX, hi = 0;
+            for (int q = P.cut_lo[r]; q < P.cut_hi[r]; ++q) { lo = std::min(lo, first_pos[q - cf]); hi = std::max(hi, last_pos[q - cf]); }
+            if (lo > hi) lo = hi = 0;
+            P.pos_lo[r] = lo; P.pos_hi[r] = hi;
+            P.x_seg = std::max(P.x_seg, hi - lo);
+        }
+        for (int r = 0; r + 1 < world; ++r)
+            if (P.pos_hi[r] > P.pos_lo[r + 1]) throw ArgError("direct solver: subtree position ranges overlap");
+    }
+    cudaStream_t st = c->stream;
+    P.d_um_off.upload(P.um_off.data(), nc, st);
+    P.d_uv_off.upload(P.uv_off.data(), nc, st);
+    P.d_cut_owner.upload(owner.data(), nc, st);
+    d.pos_dof.upload(S.s_pos_dof.data(), (int64_t)S.s_pos_dof.size(), st);
+    PN_CUDA(cudaStreamSynchronize(st));
+    P.cut = cut;
+    P.active = true;
+    c->ctr[PC_DIST_CUT_LEVEL] = cut;
+}
+
+// all-gather of `seg` doubles per rank through the caller's collective; the library's stream is idle on both sides
+static void dist_allgather(Ctx *c, int64_t seg) {
+    DistPlan &P = c->direct->dist;
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    const int rc = c->dist_allgather(c->dist_user, P.send.ptr, P.recv.ptr, seg);
+    if (rc != 0) throw StatusError(PN_ERR_CUDA, "pn_set_distributed: the all-gather callback failed");
+    c->ctr[PC_DIST_EXCHANGES]++;
+}
+
+void direct_set_distributed(Ctx *c) {
+    if (!c->direct) return;
+    c->direct->analysed = false;          // the plan is rebuilt with the device maps at the next solve
+    c->direct->shared_factor = false;
+    c->direct->fronts_s = 0;
+}
+
+// After the local factorisation of the cut level: every rank receives the update matrices of all subtree roots into the
+// cut level's arena, where the extend-add of the first replicated level expects them.
+static void exchange_update_matrices(Ctx *c, int sym) {
+    DirectSolver &d = *c->direct;
+    DistPlan &P = d.dist;
+    cudaStream_t st = c->stream;
+    const int world = c->dist_world, rank = c->dist_rank;
+    const int cf = d.level_ptr[P.cut];
+    double *arena = d.arena[P.cut & 1].ptr;
+    P.send.resize(std::max<int64_t>(P.um_seg, 1));
+    P.recv.resize(std::max<int64_t>(P.um_seg, 1) * world);
+    const int mine = P.cut_hi[rank] - P.cut_lo[rank];
+    const unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(d.level_max_nb[P.cut], 1), 4096);
+    if (mine > 0) {
+        k_dist_um<<<dim3(mine, gy), 256, 0, st>>>(P.cut_lo[rank], d.fronts.ptr, cf, P.d_um_off.ptr, arena, P.send.ptr, 0, sym);
+        c->count_launch();
+    }
+    dist_allgather(c, P.um_seg);
+    for (int r = 0; r < world; ++r) {
+        const int cnt = P.cut_hi[r] - P.cut_lo[r];
+        if (r == rank || cnt <= 0) continue;
+        k_dist_um<<<dim3(cnt, gy), 256, 0, st>>>(P.cut_lo[r], d.fronts.ptr, cf, P.d_um_off.ptr, arena, P.recv.ptr + (int64_t)r * P.um_seg, 1, sym);
+        c->count_launch();
+    }
+}
+
 static void factorise(Ctx *c, const double *vals11) {
     DirectSolver &d = *c->direct;
     cudaStream_t st = c->stream;
@@ -1656,8 +1881,11 @@ static void factorise(Ctx *c, const double *vals11) {
     c->ctr[PC_FACTORISATIONS]++;
     c->ctr[PC_LEVELS] = d.n_levels;
     for (int l = 0; l < d.n_levels; ++l) c->ctr[PC_MAX_FRONT_NS] = std::max<int64_t>(c->ctr[PC_MAX_FRONT_NS], d.level_max_ns[l]);
+    const DistPlan &DP = d.dist;
     for (int l = 0; l < d.n_levels; ++l) {
-        int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
+        // subtree-to-GPU: below and on the cut level only this rank's subtrees, above it every front (replicated)
+        int first = DP.active ? DP.lo[l] : d.level_ptr[l], nfl = (DP.active ? DP.hi[l] : d.level_ptr[l + 1]) - first;
+        if (DP.active && l == DP.cut + 1) exchange_update_matrices(c, sym);
         if (!nfl) continue;
         double *arena = d.arena[l & 1].ptr;
         if (debug_levels) cudaEventRecord(dbg0, st);
@@ -1669,16 +1897,19 @@ static void factorise(Ctx *c, const double *vals11) {
         } else {
             PN_CUDA(cudaMemsetAsync(arena, 0, sizeof(double) * d.level_f_total[l], st));
         }
-        { ProfScope ps_(c, PS_FRONT_ASSEMBLE); k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
+        { ProfScope ps_(c, PS_FRONT_ASSEMBLE); k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, first, first + nfl, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
                                                                   d.fronts.ptr, vals11, arena); }
         lp.end();
         c->count_launch();
         if (l > 0) {
-            int cfirst = d.level_ptr[l - 1], ncl = d.level_ptr[l] - cfirst;
+            // children: this rank's range of the level below (all of it above the cut, where the update matrices of the
+            // other ranks' subtree roots have just been received)
+            int cfirst = (DP.active && l - 1 <= DP.cut && l <= DP.cut) ? DP.lo[l - 1] : d.level_ptr[l - 1];
+            int ncl = ((DP.active && l - 1 <= DP.cut && l <= DP.cut) ? DP.hi[l - 1] : d.level_ptr[l]) - cfirst;
             int64_t nbmax = d.level_max_nb[l - 1];
             // enough row chunks to fill the GPU when the level has few children, few when it has thousands
             unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(nbmax, 1), std::max<int64_t>(1, 16384 / std::max(ncl, 1)));
-            for (int r = 0; r < d.level_max_children[l - 1]; ++r) {
+            for (int r = 0; r < d.level_max_children[l - 1] && ncl > 0; ++r) {
                 lp.begin(1);
                 { ProfScope ps_(c, PS_EXTEND_ADD); k_extend_add<<<dim3(ncl, gy), 256, 0, st>>>(cfirst, ncl, r, d.fronts.ptr, d.rel.ptr, d.arena[(l - 1) & 1].ptr,
                                                              arena, sym); }
@@ -1790,6 +2021,56 @@ static void factorise(Ctx *c, const double *vals11) {
     if (status == 1) throw StatusError(PN_ERR_SINGULAR, "zero or non-finite pivot in the stiffness factorisation");
 }
 
+// After the local forward sweep of the cut level: the update vectors (boundary rows of the subtree roots' workspaces)
+// of all ranks, into the cut level's workspace arena where the first replicated level pulls them from.
+static void exchange_update_vectors(Ctx *c, int s, const FrontDev *fr) {
+    DirectSolver &d = *c->direct;
+    DistPlan &P = d.dist;
+    cudaStream_t st = c->stream;
+    const int world = c->dist_world, rank = c->dist_rank;
+    const int cf = d.level_ptr[P.cut];
+    double *W = d.warena[P.cut & 1].ptr;
+    const int64_t seg = std::max<int64_t>(P.uv_seg, 1) * s;
+    P.send.resize(seg);
+    P.recv.resize(seg * world);
+    const unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)d.level_max_nb[P.cut] * s + 255) / 256, 1), 1024);
+    const int mine = P.cut_hi[rank] - P.cut_lo[rank];
+    if (mine > 0) {
+        k_dist_uv<<<dim3(mine, gy), 256, 0, st>>>(P.cut_lo[rank], s, fr, cf, P.d_uv_off.ptr, W, P.send.ptr, 0);
+        c->count_launch();
+    }
+    dist_allgather(c, seg);
+    for (int r = 0; r < world; ++r) {
+        const int cnt = P.cut_hi[r] - P.cut_lo[r];
+        if (r == rank || cnt <= 0) continue;
+        k_dist_uv<<<dim3(cnt, gy), 256, 0, st>>>(P.cut_lo[r], s, fr, cf, P.d_uv_off.ptr, W, P.recv.ptr + (int64_t)r * seg, 1);
+        c->count_launch();
+    }
+}
+
+// After the backward sweep: every rank's solved rows (its range of elimination positions) to every rank.
+static void exchange_solved_rows(Ctx *c, double *X, int s) {
+    DirectSolver &d = *c->direct;
+    DistPlan &P = d.dist;
+    cudaStream_t st = c->stream;
+    const int world = c->dist_world, rank = c->dist_rank;
+    const int64_t seg = std::max<int64_t>(P.x_seg, 1) * s;
+    P.send.resize(seg);
+    P.recv.resize(seg * world);
+    const int64_t mine = (P.pos_hi[rank] - P.pos_lo[rank]) * s;
+    if (mine > 0) {
+        k_dist_x<<<grid_for(mine, 256), 256, 0, st>>>(P.pos_lo[rank], P.pos_hi[rank], s, d.pos_dof.ptr, X, P.send.ptr, 0);
+        c->count_launch();
+    }
+    dist_allgather(c, seg);
+    for (int r = 0; r < world; ++r) {
+        const int64_t cnt = (P.pos_hi[r] - P.pos_lo[r]) * s;
+        if (r == rank || cnt <= 0) continue;
+        k_dist_x<<<grid_for(cnt, 256), 256, 0, st>>>(P.pos_lo[r], P.pos_hi[r], s, d.pos_dof.ptr, X, P.recv.ptr + (int64_t)r * seg, 1);
+        c->count_launch();
+    }
+}
+
 // solves in place: X holds the right-hand sides on entry ([n1][s] row-major)
 static void solve_inplace(Ctx *c, double *X, int s) {
     DirectSolver &d = *c->direct;
@@ -1815,10 +2096,12 @@ static void solve_inplace(Ctx *c, double *X, int s) {
     const bool use_ll = !no_ll_sweeps && s <= 32 * LL_MAX_CHUNKS;
     cudaEvent_t dbg[64];
     if (debug_levels) for (int i = 0; i < 64; ++i) cudaEventCreate(&dbg[i]);
-    // forward sweep
+    const DistPlan &DP = d.dist;
+    // forward sweep (subtree-to-GPU: own subtrees up to the cut level, then every front)
     for (int l = 0; l < d.n_levels; ++l) {
-        int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
+        int first = DP.active ? DP.lo[l] : d.level_ptr[l], nfl = (DP.active ? DP.hi[l] : d.level_ptr[l + 1]) - first;
         if (debug_levels && l < 31) cudaEventRecord(dbg[l], st);
+        if (DP.active && l == DP.cut + 1) exchange_update_vectors(c, s, fr);
         if (!nfl) continue;
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
@@ -1847,9 +2130,10 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr, d.fidx.ptr, X, W); }
         c->count_launch();
         if (l > 0) {
-            int cfirst = d.level_ptr[l - 1], ncl = d.level_ptr[l] - cfirst;
+            const bool own_children = DP.active && l <= DP.cut;
+            int cfirst = own_children ? DP.lo[l - 1] : d.level_ptr[l - 1], ncl = (own_children ? DP.hi[l - 1] : d.level_ptr[l]) - cfirst;
             unsigned gyc = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)d.level_max_nb[l - 1] * s + 255) / 256, 1), 1024);
-            for (int r = 0; r < d.level_max_children[l - 1]; ++r) {
+            for (int r = 0; r < d.level_max_children[l - 1] && ncl > 0; ++r) {
                 { ProfScope ps_(c, PS_SOLVE_MISC); k_solve_extend_add<<<dim3(ncl, gyc), 256, 0, st>>>(cfirst, ncl, r, s, fr, d.rel.ptr,
                                                                     d.warena[(l - 1) & 1].ptr, W); }
                 c->count_launch();
@@ -1878,7 +2162,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
     if (debug_levels) cudaEventRecord(dbg[31], st);
     // backward sweep
     for (int l = d.n_levels - 1; l >= 0; --l) {
-        int first = d.level_ptr[l], nfl = d.level_ptr[l + 1] - first;
+        int first = DP.active ? DP.lo[l] : d.level_ptr[l], nfl = (DP.active ? DP.hi[l] : d.level_ptr[l + 1]) - first;
         if (debug_levels && l < 31) cudaEventRecord(dbg[32 + l + 1], st);
         if (!nfl) continue;
         double *W = d.warena[l & 1].ptr;
@@ -1930,6 +2214,7 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
         c->count_launch();
     }
+    if (DP.active) exchange_solved_rows(c, X, s);
     if (debug_levels) {
         cudaEventRecord(dbg[32], st);
         cudaEventSynchronize(dbg[32]);

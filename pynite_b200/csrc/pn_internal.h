@@ -168,6 +168,8 @@ enum PathCounter {
     PC_FACTORISATIONS,     // numeric factorisations
     PC_PDELTA_STATIONARY,  // P-Delta batches solved by the stationary iteration on the elastic factor
     PC_PDELTA_PERCOLUMN,   // P-Delta columns finished by preconditioned GMRES (or their own factorisation)
+    PC_DIST_EXCHANGES,     // all-gathers of the subtree-to-GPU solve (update matrices, update vectors, solved rows)
+    PC_DIST_CUT_LEVEL,     // level of the subtree roots (-1: not distributed)
     PC_COUNT
 };
 
@@ -269,6 +271,15 @@ struct Ctx {
     // which kernel families the direct solver took since pn_reset_stats (pn_get_counter): the parity tests assert from
     // these that a model is large enough to exercise the production paths of the big configurations
     int64_t ctr[PC_COUNT] = {0};
+    // tension/compression-only element modes (pn_set_tc_modes): bit0 tension-only, bit1 compression-only
+    DevBuf<uint8_t> tc_spring_mode, tc_member_mode;
+    DevBuf<int64_t> tc_group_start;      // sub-member range of every physical member
+    int64_t tc_n_groups = 0;
+    bool tc_any_member_mode = false;
+    // multi-GPU direct solve (pn_set_distributed): this context is rank `dist_rank` of `dist_world`
+    int dist_rank = 0, dist_world = 1;
+    pn_allgather_fn dist_allgather = nullptr;
+    void *dist_user = nullptr;
 };
 
 void prof_flush(Ctx *c);
@@ -350,6 +361,10 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
 void launch_member_pdelta_forces(Ctx *c, const double *D_dev, bool supported_only, double *F_dev, cudaStream_t st);
 void launch_forces_to_local(Ctx *c, int kind, double *F_dev, cudaStream_t st);
 
+// ---- pn_tc.cu -------------------------------------------------------------------------------------
+int64_t tc_update(Ctx *c, int32_t combo, bool pdelta, double spring_tol, double member_tol);
+void tc_reset_elements(Ctx *c);
+
 // ---- pn_stress.cu ---------------------------------------------------------------------------------
 void launch_shell_stress(Ctx *c, bool quad, const double *D_dev, int n_combo, int n_pts, const double *pts_dev, int local,
                          double *out_dev, cudaStream_t st);
@@ -398,5 +413,6 @@ void direct_release(Ctx *c);
 void direct_prefetch(Ctx *c);     // start the host half of the analysis on a worker thread (after the DOF partition is known)
 void direct_invalidate(Ctx *c);
 void direct_invalidate_pattern(Ctx *c);
+void direct_set_distributed(Ctx *c);   // the rank / world / callback in the context changed
 
 }  // namespace pn

@@ -112,7 +112,12 @@ SIGNATURES = {
     'pn_set_displacements': (ct.c_int, [_P, ct.c_int32, _F64P]),
     'pn_reactions': (ct.c_int, [_P, ct.c_int32, ct.c_int32, _F64P]),
     'pn_element_forces': (ct.c_int, [_P, ct.c_int, ct.c_int32, ct.c_int32, ct.c_int32, _F64P]),
+    'pn_set_tc_modes': (ct.c_int, [_P, _U8P, _U8P, ct.c_int64, ct.POINTER(ct.c_int64)]),
+    'pn_tc_update': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_double, ct.c_double, ct.POINTER(ct.c_int64)]),
+    'pn_tc_reset': (ct.c_int, [_P]),
+    'pn_get_activity': (ct.c_int, [_P, _U8P, _U8P, _U8P]),
     'pn_shell_stresses': (ct.c_int, [_P, ct.c_int, ct.c_int32, ct.c_int32, ct.c_int32, _F64P, ct.c_int32, _F64P]),
+    'pn_set_distributed': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_void_p, ct.c_void_p]),
     'pn_set_stream': (ct.c_int, [_P, ct.c_void_p, ct.c_int]),
     'pn_node_row_starts': (ct.c_int, [_P, ct.POINTER(ct.c_int64)]),
     'pn_prefetch_analysis': (ct.c_int, [_P]),
@@ -396,8 +401,8 @@ class Engine:
         D = _c(D, np.float64).reshape(-1)
         self._check(self._lib.pn_set_displacements(self._h, combo, _ptr(D, _F64P)))
 
-    def reactions(self, combo, pdelta=False):
-        out = np.empty((self.n_dof, 1))
+    def reactions(self, combo, pdelta=False, out=None):
+        out = np.empty((self.n_dof, 1)) if out is None else out
         self._check(self._lib.pn_reactions(self._h, combo, 1 if pdelta else 0, _ptr(out, _F64P)))
         return out
 
@@ -407,6 +412,29 @@ class Engine:
         self._check(self._lib.pn_element_forces(self._h, kind, combo, 1 if local else 0, 1 if pdelta else 0,
                                                 _ptr(out, _F64P)))
         return out
+
+    # ---- tension/compression-only iteration on the device ----------------------------------------------
+    def set_tc_modes(self, spring_mode, member_mode, group_start):
+        sm, mm = _c(spring_mode, np.uint8), _c(member_mode, np.uint8)
+        gs = _c(group_start, np.int64)
+        self._check(self._lib.pn_set_tc_modes(self._h, _ptr(sm, _U8P), _ptr(mm, _U8P), max(len(gs) - 1, 0),
+                                              gs.ctypes.data_as(ct.POINTER(ct.c_int64))))
+
+    def tc_update(self, combo, pdelta, spring_tol, member_tol):
+        """Number of activity changes `Analysis._check_TC_convergence` would make for the resident combo (0 = converged)."""
+        n = ct.c_int64(0)
+        self._check(self._lib.pn_tc_update(self._h, combo, 1 if pdelta else 0, float(spring_tol), float(member_tol), ct.byref(n)))
+        return n.value
+
+    def tc_reset(self):
+        self._check(self._lib.pn_tc_reset(self._h))
+
+    def activity(self, n_nodes):
+        nsf = np.empty((n_nodes, 6), dtype=np.uint8)
+        sa = np.empty(self.counts[PN_SPRING], dtype=np.uint8)
+        ma = np.empty(self.counts[PN_MEMBER], dtype=np.uint8)
+        self._check(self._lib.pn_get_activity(self._h, _ptr(nsf, _U8P), _ptr(sa, _U8P), _ptr(ma, _U8P)))
+        return nsf, sa, ma
 
     def shell_stresses(self, kind, combo0, n_combo, pts, local=True):
         """[n_combo][count][n_pts][9] internal shears / moments / membrane stresses of every quad or plate."""
@@ -466,8 +494,8 @@ class Engine:
     def dev_set_solution(self, combo0, s, x_ptr):
         self._check(self._lib.pn_dev_set_solution(self._h, combo0, s, ct.c_void_p(x_ptr)))
 
-    def displacements(self, combo):
-        out = np.empty(self.n_dof)
+    def displacements(self, combo, out=None):
+        out = np.empty(self.n_dof) if out is None else out
         self._check(self._lib.pn_get_displacements(self._h, combo, _ptr(out, _F64P)))
         return out
 

@@ -363,6 +363,35 @@ def mat_foundation(FE, nx=6, ny=5, a=12.0, t=24.0, ks=0.1):
     return m
 
 
+def mat_tc(FE, nx=6, ny=5, a=12.0, t=10.0, ks=0.1):
+    """Mat foundation on COMPRESSION-ONLY Winkler springs (`MatFoundation.py:136` uses direction '-'), loaded so that
+    one side lifts off: the tension/compression-only iteration has to switch a band of support springs off, and a second
+    combination switches some of them back on."""
+    m = FE()
+    m.add_material('Conc', 3605.0, 1540.6, 0.17, 8.68e-5)
+    N = _grid_nodes(m, nx, ny, a, a, 'XZ')
+    k = 1
+    for r in range(ny):
+        for c in range(nx):
+            name = m.add_quad('Q' + str(k), N[(c, r)], N[(c + 1, r)], N[(c + 1, r + 1)], N[(c, r + 1)], t, 'Conc')
+            m.add_quad_surface_pressure(name, 0.0004, case='D')
+            k += 1
+    for r in range(ny + 1):
+        for c in range(nx + 1):
+            trib = a*a*(0.5 if r in (0, ny) else 1.0)*(0.5 if c in (0, nx) else 1.0)
+            m.def_support_spring(N[(c, r)], 'DY', ks*trib, '-')
+    m.def_support(N[(0, 0)], True, False, True, False, False, False)
+    m.def_support(N[(nx, 0)], False, False, True, False, False, False)
+    for r in range(ny + 1):
+        m.add_node_load(N[(0, r)], 'FY', -6.0, case='C')         # heavy wall along one edge
+        m.add_node_load(N[(nx, r)], 'FY', 1.0, case='U')         # uplift along the opposite edge
+    m.add_node_load(N[(nx//2, ny//2)], 'FY', -30.0, case='C')
+    m.add_load_combo('D+C', {'D': 1.0, 'C': 1.0})
+    m.add_load_combo('D+C+U', {'D': 1.0, 'C': 1.0, 'U': 1.0})
+    m.add_load_combo('D', {'D': 1.4})
+    return m
+
+
 def mixed_building(FE):
     """One-storey frame carrying a quad slab and a plate wall: all four element kinds in one matrix."""
     m = FE()
@@ -479,6 +508,7 @@ SMALL_MODELS = {
     'braced_tc': (braced_tc, 'tc'),
     'pdelta_near_buckling': (pdelta_near_buckling, 'pdelta'),
     'tc_load_steps': (tc_load_steps, 'tc_steps'),
+    'mat_tc': (mat_tc, 'tc'),
 }
 
 # keyword arguments of `analyze` for the load-stepping fixture (mode 'tc_steps')

@@ -8,12 +8,12 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 FIXTURES = ['space_frame', 'portal_frame', 'continuous_beam', 'quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz',
             'skew_shell', 'moment_frame', 'mat_foundation', 'mixed_building', 'pdelta_column', 'pdelta_frame',
-            'braced_tc', 'pdelta_near_buckling', 'tc_load_steps']
+            'braced_tc', 'pdelta_near_buckling', 'tc_load_steps', 'mat_tc']
 
 
 # fixtures whose stored displacements come from the tension/compression-only iteration (input arrays carry the
 # reference's final element activity; a plain linear solve of them is not what the reference stored)
-TC_FIXTURES = ('braced_tc', 'tc_load_steps')
+TC_FIXTURES = ('braced_tc', 'tc_load_steps', 'mat_tc')
 PDELTA_FIXTURES = ('pdelta_column', 'pdelta_frame', 'pdelta_near_buckling')
 
 
