@@ -200,6 +200,11 @@ PN_EXPORT int pn_set_tc_modes(pn_ctx *ctx, const uint8_t *spring_mode, const uin
 PN_EXPORT int pn_tc_update(pn_ctx *ctx, int32_t combo, int32_t pdelta, double spring_tol, double member_tol, int64_t *n_changed);
 PN_EXPORT int pn_tc_reset(pn_ctx *ctx);
 PN_EXPORT int pn_get_activity(pn_ctx *ctx, uint8_t *nspring_flag, uint8_t *spring_active, uint8_t *member_active);
+/* Overwrites the activity flags (any pointer may be NULL = unchanged) without touching stored displacements or load
+ * vectors: Analysis._calc_reactions :1059-1313 runs after ALL combinations and sees every element's per-combination
+ * `active[combo]` but the node support springs as the LAST combination left them; this call reproduces that state
+ * before pn_reactions / pn_element_forces.  The matrix has to be re-assembled before the next solve.                */
+PN_EXPORT int pn_set_activity(pn_ctx *ctx, const uint8_t *nspring_flag, const uint8_t *spring_active, const uint8_t *member_active);
 
 /* ---- internal forces / stresses of shells for solved combos: Quad3D.shear :1017, moment :1096, membrane :1173
  *      (points = natural coordinates (xi, eta), values at the Gauss points extrapolated), Plate3D.shear :608,
@@ -276,7 +281,7 @@ PN_EXPORT int pn_reset_stats(pn_ctx *ctx);
  * behind spsolve, Analysis.py:217).  Names: pn_counter_name(0..) until NULL -- "lu_update", "lu_update_later_groups"
  * (fronts with more than 256 pivots), "lu_strip", "split_levels" (front groups on side streams), "sweep_smem",
  * "sweep_ll", "sweep_step", "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches",
- * "pdelta_fallback_columns", "dist_exchanges", "dist_cut_level".  The parity tests assert from these that a mid-size model exercises the
+ * "pdelta_fallback_columns", "factor_fused_levels", "dist_exchanges", "dist_cut_level".  The parity tests assert from these that a mid-size model exercises the
  * kernels the full-size configurations run. */
 PN_EXPORT int pn_get_counter(pn_ctx *ctx, const char *name, int64_t *out);
 PN_EXPORT const char *pn_counter_name(int index);

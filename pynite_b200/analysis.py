@@ -278,6 +278,7 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
     model._run.pdelta = pdelta
     _set_tc_modes(model, eng, A)
     n = A.n_dof
+    end_flags = {}
     flags = _eng.PN_SYM_DENSE_MEMBER_BLOCKS if pdelta else 0
     for ci, combo in enumerate(combo_list):
         if log:
@@ -331,13 +332,28 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
                 else:
                     load_step += 1
                 iter_count += 1
-        _mirror_activity(model, combo.name, eng.activity(A.n_nodes), False)
+        end_flags[combo.name] = eng.activity(A.n_nodes)
+        _mirror_activity(model, combo.name, end_flags[combo.name], False)
         # reactions with this combo's final element activity (`_calc_reactions`, :1059-1313)
         model._Rxn[combo.name] = eng.reactions(0, pdelta)
         # element end forces must stay readable after the engine moves on to the next combo
         model._run.saved = getattr(model._run, 'saved', {})
         model._run.saved[combo.name] = {kind: eng.element_forces(kind, 0, local=False, pdelta=pdelta)
                                         for kind in ('spring', 'member', 'quad', 'plate')}
+    # The reference computes reactions after ALL combinations (`_calc_reactions` at the end of `analyze`): every
+    # element contributes with its own per-combination activity, but the node support springs with the state the LAST
+    # combination left them in.  Combinations whose support springs ended differently are recomputed with that state.
+    if combo_list:
+        final_nsf = end_flags[combo_list[-1].name][0]
+        for ci, combo in enumerate(combo_list[:-1]):
+            nsf, sa, ma = end_flags[combo.name]
+            if np.array_equal(nsf, final_nsf):
+                continue
+            eng.set_activity(final_nsf, sa, ma)
+            eng.set_combos(A.factors[ci:ci + 1])
+            eng.set_displacements(0, model._D[combo.name])
+            model._Rxn[combo.name] = eng.reactions(0, pdelta)
+            model._run.engine_combo = {combo.name: 0}
     model.last_stats = eng.stats().as_dict()
 
 

@@ -855,7 +855,7 @@ int pn_get_kg_coo(pn_ctx *ctx, int32_t combo, int32_t first_step, int32_t *row, 
 int pn_set_displacements(pn_ctx *ctx, int32_t combo, const double *D) {
     PN_API_BEGIN(ctx)
     if (combo < 0 || combo >= c->loads.n_combo || !D) throw ArgError("pn_set_displacements: bad combo index");
-    if (!c->vals_ready) throw ArgError("pn_set_displacements: call pn_assemble_ke first");
+    if (!c->n_dof || c->n_dof != 6 * c->model.n_nodes) throw ArgError("pn_set_displacements: call pn_symbolic first");
     // Also the way results computed elsewhere (another rank's share of the combinations, an earlier per-combination
     // analysis) are made resident again for pn_reactions / pn_element_forces / pn_shell_stresses.
     const int64_t need = (int64_t)c->loads.n_combo * c->n_dof;
@@ -877,7 +877,9 @@ int pn_reactions(pn_ctx *ctx, int32_t combo, int32_t pdelta, double *out) {
     PN_API_BEGIN(ctx)
     if (!c->solved || combo < 0 || combo >= c->loads.n_combo || !out) throw ArgError("pn_reactions: combo has not been solved");
     PhaseTimer tm(c, &c->stats.ms_reactions);
+    ensure_ev(c);
     build_incidence(c);
+    ensure_loads(c);
     DevBuf<double> rx;
     rx.resize(c->n_dof);
     compute_reactions(c, combo, pdelta != 0, rx.ptr);
@@ -892,6 +894,7 @@ int pn_element_forces(pn_ctx *ctx, int kind, int32_t combo, int32_t local, int32
     if (!out) throw ArgError("pn_element_forces: null output");
     const Model &m = c->model;
     cudaStream_t st = c->stream;
+    ensure_ev(c);
     build_incidence(c);
     ensure_loads(c);
     const double *D = c->D_all.ptr + (int64_t)combo * c->n_dof;
@@ -975,6 +978,7 @@ static void tc_sync_activity(Ctx *c, bool elements_changed) {
 int pn_tc_update(pn_ctx *ctx, int32_t combo, int32_t pdelta, double spring_tol, double member_tol, int64_t *n_changed) {
     PN_API_BEGIN(ctx)
     if (!c->solved || combo < 0 || combo >= c->loads.n_combo || !n_changed) throw ArgError("pn_tc_update: combo has not been solved");
+    ensure_ev(c);
     build_incidence(c);
     ensure_loads(c);
     Model &m = c->model;
@@ -999,6 +1003,35 @@ int pn_tc_reset(pn_ctx *ctx) {
         tc_reset_elements(c);
         tc_sync_activity(c, true);
     }
+    PN_API_END
+}
+
+int pn_set_activity(pn_ctx *ctx, const uint8_t *nspring_flag, const uint8_t *spring_active, const uint8_t *member_active) {
+    PN_API_BEGIN(ctx)
+    Model &m = c->model;
+    cudaStream_t st = c->stream;
+    bool elements = false;
+    if (nspring_flag && m.n_nodes) {
+        memcpy(m.h_nspring_flag.data(), nspring_flag, (size_t)(6 * m.n_nodes));
+        m.nspring_flag.upload(nspring_flag, 6 * m.n_nodes, st);
+    }
+    if (spring_active && m.n_springs) {
+        elements = elements || memcmp(m.h_spring_active.data(), spring_active, (size_t)m.n_springs) != 0;
+        memcpy(m.h_spring_active.data(), spring_active, (size_t)m.n_springs);
+        m.spring_active.upload(spring_active, m.n_springs, st);
+    }
+    if (member_active && m.n_members) {
+        elements = elements || memcmp(m.h_mem_active.data(), member_active, (size_t)m.n_members) != 0;
+        memcpy(m.h_mem_active.data(), member_active, (size_t)m.n_members);
+        m.mem_active.upload(member_active, m.n_members, st);
+    }
+    PN_CUDA(cudaStreamSynchronize(st));
+    // stored displacements and load vectors stay valid (pn_reactions / pn_element_forces with this activity); the matrix does not
+    c->rxn_list_ready = false;
+    c->ev_ready = false;
+    c->symbolic_ready = false;
+    c->vals_ready = false;
+    if (elements) direct_invalidate(c);
     PN_API_END
 }
 
@@ -1192,7 +1225,7 @@ int pn_get_stats(pn_ctx *ctx, pn_stats *out) {
 static const char *kSlotNames[PS_COUNT] = {
     "element_ke", "scatter_add", "gather_blocks", "build_rhs", "spmm", "front_assemble", "extend_add", "lu_diag",
     "lu_panels", "lu_update", "copy_factors", "solve_gather_store", "solve_diag", "solve_update", "solve_misc",
-    "reactions", "pcg_vector", "merge_displacements", "assembly_total", "solve_front_fused"};
+    "reactions", "pcg_vector", "merge_displacements", "assembly_total", "solve_front_fused", "factor_front_fused"};
 
 const char *pn_profile_slot_name(int slot) { return (slot >= 0 && slot < PS_COUNT) ? kSlotNames[slot] : nullptr; }
 
@@ -1243,7 +1276,7 @@ int pn_reset_stats(pn_ctx *ctx) {
 static const char *kCounterNames[PC_COUNT] = {
     "lu_update", "lu_update_later_groups", "lu_strip", "split_levels", "sweep_smem", "sweep_ll", "sweep_step",
     "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches", "pdelta_fallback_columns",
-    "dist_exchanges", "dist_cut_level"};
+    "factor_fused_levels", "dist_exchanges", "dist_cut_level"};
 
 const char *pn_counter_name(int index) { return (index >= 0 && index < PC_COUNT) ? kCounterNames[index] : nullptr; }
 

@@ -747,6 +747,104 @@ __global__ void k_lu_transpose_panel(int first, int kb, const FrontDev *__restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Whole factorisation of one front inside one CTA, for the levels with many small fronts (the bottom of the tree:
+// 8192 ... 512 fronts of 270 ... 666 rows in config 3).  The level-synchronous path launches diag / panels / strip /
+// update / store kernels per 64 pivots over ALL fronts of the level, and every launch streams the level's arena
+// (gigabytes) through HBM for GEMMs that are all prologue and epilogue.  Here a CTA walks the block steps of its own
+// front back to back with the same device functions (diag_step, gemm_tile): the front (<= 0.6 ... 3.5 MB, lower
+// triangle only in symmetric mode) stays in L2 between steps, there are no launch gaps or inter-kernel dependencies, and
+// the grid of thousands of independent CTAs keeps every SM busy.  Same arithmetic in the same order as the per-step
+// kernels, so the factor is bit-identical to theirs.
+// ------------------------------------------------------------------------------------------------
+constexpr int FUSED_FACTOR_SMEM = GEMM_SMEM > DIAG_SMEM ? GEMM_SMEM : DIAG_SMEM;
+// a level takes the one-CTA-per-front kernel when it has at least this many fronts (about two CTAs per SM)
+static int fused_factor_min() {
+    static const int v = getenv("PN_FUSED_FACTOR_MIN") ? atoi(getenv("PN_FUSED_FACTOR_MIN")) : 256;
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_front_factor_fused(int first, const FrontDev *__restrict__ fronts, double *__restrict__ arena, double *__restrict__ inv,
+                     int *__restrict__ status, int sym, double *__restrict__ U12, double *__restrict__ Lst) {
+    const FrontDev F = fronts[first + blockIdx.x];
+    const int n = F.ns + F.nb;
+    double *A = arena + F.f_off;
+    for (int g0 = 0; g0 < F.ns; g0 += GB) {
+        const int ge = min(g0 + GB, F.ns);
+        for (int kb = g0; kb < ge; kb += NB) {
+            diag_step(F, kb, arena, inv, status, sym);
+            __syncthreads();
+            const int bs = min(NB, F.ns - kb);
+            const int r0 = kb + bs, rest = n - r0;
+            if (rest <= 0) continue;
+            const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
+            const double *Uinv = Linv + NB * NB;
+            // panels (k_lu_panels)
+            if (!sym) {
+                double *P = A + (int64_t)kb * n + r0;
+                for (int t = 0; t * BN < rest; ++t) gemm_tile(Linv, NB, P, n, P, n, bs, rest, bs, 0, t, 1);
+            }
+            {
+                double *P = A + (int64_t)r0 * n + kb;
+                for (int t = 0; t * BM < rest; ++t) {
+                    if (sym)
+                        gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1, false, A + (int64_t)kb * n + r0, n, A + (int64_t)kb * n + kb, n + 1,
+                                  F.nb ? U12 + F.u_off + (int64_t)kb * F.nb : nullptr, F.nb, F.ns - r0);
+                    else
+                        gemm_tile(P, n, Uinv, NB, P, n, rest, bs, bs, t, 0, 1);
+                    __syncthreads();
+                    gemm_tile(P, n, Linv, NB, Lst + F.l_off + (int64_t)r0 * F.ns + kb, F.ns, rest, bs, bs, t, 0, 1);
+                }
+            }
+            __syncthreads();
+            // strips the rest of the group needs (k_lu_strip)
+            if (kb + NB < ge) {
+                const int q0 = kb + NB;
+                const int wa = ge - q0, ha = n - q0;
+                const int ta_n = (wa + BN - 1) / BN, ta_m = (ha + BM - 1) / BM;
+                const double *Lp = A + (int64_t)q0 * n + kb;
+                for (int t = 0; t < ta_m * ta_n; ++t) {
+                    if (sym && (t / ta_n + 1) * BM <= (t % ta_n) * BN) continue;
+                    gemm_tile(Lp, n, A + (int64_t)kb * n + q0, n, A + (int64_t)q0 * n + q0, n, ha, wa, NB, t / ta_n, t % ta_n, 0, sym != 0);
+                }
+                if (!sym) {
+                    const int hb = ge - q0, wb = n - ge;
+                    const int tb_n = (wb + BN - 1) / BN, tb_m = (hb + BM - 1) / BM;
+                    for (int t = 0; t < tb_m * tb_n; ++t)
+                        gemm_tile(Lp, n, A + (int64_t)kb * n + ge, n, A + (int64_t)q0 * n + ge, n, hb, wb, NB, t / tb_n, t % tb_n, 0);
+                }
+                __syncthreads();
+            }
+        }
+        // trailing update of the group (k_lu_update)
+        const int rest = n - ge;
+        if (rest > 0) {
+            const int tn_ = (rest + BN - 1) / BN, tm_ = (rest + BM - 1) / BM;
+            for (int tm = 0; tm < tm_; ++tm)
+                for (int tn = 0; tn < tn_; ++tn) {
+                    if (sym && (tm + 1) * BM <= tn * BN) continue;
+                    gemm_tile(A + (int64_t)ge * n + g0, n, A + (int64_t)g0 * n + ge, n, A + (int64_t)ge * n + ge, n, rest, rest, ge - g0, tm, tn, 0,
+                              sym != 0);
+                }
+            __syncthreads();
+        }
+    }
+    // permanent panels above the diagonal blocks (k_store_panels) and, in general mode, U12 (k_copy_u12)
+    for (int kb = NB; kb < F.ns; kb += NB) {
+        const int bs = min(NB, F.ns - kb);
+        const double *Uinv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB) + NB * NB;
+        for (int t = 0; t * BM < kb; ++t) gemm_tile(A + kb, n, Uinv, NB, Lst + F.l_off + kb, F.ns, kb, bs, bs, t, 0, 1);
+    }
+    if (!sym && F.nb) {
+        const int64_t total = (int64_t)F.ns * F.nb;
+        for (int64_t t = threadIdx.x; t < total; t += blockDim.x) {
+            const int64_t r = t / F.nb;
+            U12[F.u_off + t] = A[r * n + F.ns + (t - r * F.nb)];
+        }
+    }
+}
+
 // Block steps are grouped GB pivots at a time so that the (HBM-resident) trailing matrix is read and written once
 // per group instead of once per step.  Inside group [g0, ge), after the panels of step kb, only the strips the
 // remaining steps of the group will factor are updated (rank NB):
@@ -1585,6 +1683,7 @@ static void analyse(Ctx *c) {
     if (!d.attrs_set) {
         PN_CUDA(cudaFuncSetAttribute(k_lu_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_lu_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_factor_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_FACTOR_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_lu_panels, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_lu_update, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_store_panels, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
@@ -1637,7 +1736,7 @@ static void analyse(Ctx *c) {
     tick.lap("device maps + allocation");
     c->stats.factor_nnz = S.factor_entries;
     c->stats.factor_flops = S.factor_flops;
-    // flops the trailing-update kernel really performs on THIS rank (tile-granular, clipped to the matrix): general
+    // flops the trailing-update kernel (k_lu_update) really performs on THIS rank (tile-granular, clipped to the matrix): general
     // mode = every tile of the trailing square per pivot group, symmetric mode = the tiles that touch or lie below the
     // diagonal; with a subtree-to-GPU plan only the fronts this rank factorises
     {
@@ -1646,6 +1745,7 @@ static void analyse(Ctx *c) {
         double upd = 0.0;
         for (int l = 0; l < d.n_levels; ++l) {
             const int q0 = d.dist.active ? d.dist.lo[l] : d.level_ptr[l], q1 = d.dist.active ? d.dist.hi[l] : d.level_ptr[l + 1];
+            if (q1 - q0 >= fused_factor_min()) continue;       // factorised by k_front_factor_fused, not by k_lu_update
             for (int q = q0; q < q1; ++q) {
                 const FrontDev &fs = d.h_fronts[q];
                 int64_t n = fs.ns + fs.nb;
@@ -1968,6 +2068,21 @@ static void factorise(Ctx *c, const double *vals11) {
                 }
             }
         };
+        // levels with many fronts: one CTA per front does all block steps (k_front_factor_fused)
+        if (nfl >= fused_factor_min() && !lp.on) {
+            { ProfScope ps_(c, PS_FACTOR_FUSED); k_front_factor_fused<<<nfl, 256, FUSED_FACTOR_SMEM, st>>>(first, d.fronts.ptr, arena, d.inv.ptr, d.status.ptr, sym, d.U.ptr, d.L.ptr); }
+            c->count_launch();
+            c->ctr[PC_FACTOR_FUSED]++;
+            if (debug_levels) {
+                cudaEventRecord(dbg1, st);
+                cudaEventSynchronize(dbg1);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, dbg0, dbg1);
+                fprintf(stderr, "[pn] level %2d: %6d fronts, max ns %5d, max n %5d, arena %8.1f MB, %8.3f ms (fused per-front kernel)\n", l, nfl,
+                        d.level_max_ns[l], d.level_max_n[l], d.level_f_total[l] * 8e-6, ms);
+            }
+            continue;
+        }
         int nsplit = 1;
         // (per-kernel profiling serialises the groups: overlapping kernels would be charged each other's time)
         if (!lp.on && !c->prof.on && nfl >= 2 && nfl <= d.split_max_fronts) nsplit = std::min(nfl, d.n_fstreams);

@@ -143,7 +143,7 @@ struct CsrBlock {
 enum ProfSlot {
     PS_ELEM_KE = 0, PS_SCATTER, PS_GATHER_BLOCKS, PS_RHS, PS_SPMM, PS_FRONT_ASSEMBLE, PS_EXTEND_ADD, PS_LU_DIAG,
     PS_LU_PANELS, PS_LU_UPDATE, PS_COPY_FACTORS, PS_SOLVE_GATHER, PS_SOLVE_DIAG, PS_SOLVE_UPDATE, PS_SOLVE_MISC,
-    PS_REACTIONS, PS_PCG_VECTOR, PS_MERGE, PS_ASSEMBLY_TOTAL, PS_SOLVE_FUSED, PS_COUNT
+    PS_REACTIONS, PS_PCG_VECTOR, PS_MERGE, PS_ASSEMBLY_TOTAL, PS_SOLVE_FUSED, PS_FACTOR_FUSED, PS_COUNT
 };
 struct Profiler {
     bool on = false;
@@ -168,6 +168,7 @@ enum PathCounter {
     PC_FACTORISATIONS,     // numeric factorisations
     PC_PDELTA_STATIONARY,  // P-Delta batches solved by the stationary iteration on the elastic factor
     PC_PDELTA_PERCOLUMN,   // P-Delta columns finished by preconditioned GMRES (or their own factorisation)
+    PC_FACTOR_FUSED,       // levels factorised by the one-CTA-per-front kernel
     PC_DIST_EXCHANGES,     // all-gathers of the subtree-to-GPU solve (update matrices, update vectors, solved rows)
     PC_DIST_CUT_LEVEL,     // level of the subtree roots (-1: not distributed)
     PC_COUNT

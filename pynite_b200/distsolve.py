@@ -107,12 +107,12 @@ class LocalGroup:
                 self.sends[rank] = _tensor(send_ptr, seg, device)
                 self.gpu.release()
                 try:
-                    self.barrier.wait(timeout=300)
+                    self.barrier.wait(timeout=90)
                     recv = _tensor(recv_ptr, seg*world, device)
                     for r in range(world):
                         recv[r*seg:(r + 1)*seg].copy_(self.sends[r])
                     torch.cuda.synchronize(device)
-                    self.barrier.wait(timeout=300)
+                    self.barrier.wait(timeout=90)
                 finally:
                     self.gpu.acquire()
                 return 0

@@ -116,6 +116,7 @@ SIGNATURES = {
     'pn_tc_update': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_double, ct.c_double, ct.POINTER(ct.c_int64)]),
     'pn_tc_reset': (ct.c_int, [_P]),
     'pn_get_activity': (ct.c_int, [_P, _U8P, _U8P, _U8P]),
+    'pn_set_activity': (ct.c_int, [_P, _U8P, _U8P, _U8P]),
     'pn_shell_stresses': (ct.c_int, [_P, ct.c_int, ct.c_int32, ct.c_int32, ct.c_int32, _F64P, ct.c_int32, _F64P]),
     'pn_set_distributed': (ct.c_int, [_P, ct.c_int32, ct.c_int32, ct.c_void_p, ct.c_void_p]),
     'pn_set_stream': (ct.c_int, [_P, ct.c_void_p, ct.c_int]),
@@ -435,6 +436,10 @@ class Engine:
         ma = np.empty(self.counts[PN_MEMBER], dtype=np.uint8)
         self._check(self._lib.pn_get_activity(self._h, _ptr(nsf, _U8P), _ptr(sa, _U8P), _ptr(ma, _U8P)))
         return nsf, sa, ma
+
+    def set_activity(self, nspring_flag=None, spring_active=None, member_active=None):
+        a = [None if x is None else _c(x, np.uint8) for x in (nspring_flag, spring_active, member_active)]
+        self._check(self._lib.pn_set_activity(self._h, _ptr(a[0], _U8P), _ptr(a[1], _U8P), _ptr(a[2], _U8P)))
 
     def shell_stresses(self, kind, combo0, n_combo, pts, local=True):
         """[n_combo][count][n_pts][9] internal shears / moments / membrane stresses of every quad or plate."""

@@ -860,3 +860,34 @@ def test_tc_iteration_mat_config4_shape_properties():
     F = (eng.load_vector(jj, 'P') - eng.load_vector(jj, 'FER')).reshape(-1, 6)
     assert abs(F[:, 1].sum() + R[:, 1].sum()) < 1e-8*np.abs(F[:, 1]).sum()
     assert j == 1
+
+
+def test_config3_through_the_public_api():
+    """BASELINE config 3 at full size (251 001 nodes, 250 000 quads) built with `add_node / add_quad /
+    add_quad_surface_pressure / add_node_load / add_load_combo` and solved with `analyze_linear` -- the drop-in path, not
+    the vectorised array builder: same displacements as the array path bit for bit, host pre-pass time printed."""
+    import time
+    from pynite_b200 import FEModel3D, synthetic
+    from pynite_b200.engine import Engine
+    t0 = time.perf_counter()
+    m = models.big_quad_plate(FEModel3D, n=500, n_combos=4)
+    t1 = time.perf_counter()
+    m.analyze_linear(check_stability=True)
+    t2 = time.perf_counter()
+    st = m.last_stats
+    print(f'config 3 through FEModel3D: build {t1 - t0:.1f} s, analyze_linear {t2 - t1:.1f} s '
+          f'(host prepare + flatten {st["host_prepare_s"]:.1f} s, upload + device {st["device_total_s"]:.2f} s)')
+    assert m._run.arrays.n_dof == 1506006
+    A = synthetic.quad_plate_arrays(n=500, n_combos=4)
+    e = Engine(0)
+    try:
+        _upload(e, A)
+        D, R, _ = e.solve_linear(e.make_opts())
+    finally:
+        e.close()
+    for c, combo in enumerate(m.load_combos):
+        assert np.array_equal(m._D[combo].reshape(-1), D[c]), combo
+        assert np.array_equal(m._Rxn[combo].reshape(-1), R[c]), combo
+    nd = m.nodes['N125751']                       # centre node
+    assert nd.DZ['C1'] == m._D['C1'][nd.ID*6 + 2, 0] and nd.DZ['C1'] < 0
+    assert t2 - t0 < 120

@@ -42,12 +42,16 @@ def _worker(rank, ws, port, n_combo, n_dof, out):
         expect = np.array([[c*1000.0 + k for k in range(n_dof)] for c in range(n_combo)])
         ok = full.shape == expect.shape and np.array_equal(full, expect)
         tmax = sharding.max_over_ranks(10.0 + rank)
-        out[rank] = (ok, tmax)
+        # a failure on one rank (singular matrix, unstable node) must be seen by every rank, also by a rank that has no
+        # combos of its own (world size larger than the combo count)
+        seen_fail = sharding.any_rank_failed(rank == 1)
+        seen_ok = sharding.any_rank_failed(False)
+        out[rank] = (ok and seen_fail and not seen_ok, tmax)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n_combo', [5, 64])
+@pytest.mark.parametrize('n_combo', [1, 5, 64])
 def test_two_rank_gather(n_combo):
     ws = 2
     mgr = mp.Manager()
