@@ -118,7 +118,9 @@ PN_EXPORT int pn_member_kg(pn_ctx *ctx, const double *P, double *out);
 /* ---- symbolic phase: FEModel3D._build_dof_vector :66, _append_sparse_block :99 (zero filter),
  *      coo_matrix + tocsr pattern (:1791, :2279), Analysis._partition_D :1412, _partition :1508 -- */
 /* Tuning switches (no effect on results).  "assembly_graph" (default 1): the numeric class/recipe assembly is replayed
- * as one CUDA graph; 0 issues its launches one by one so that pn_profile_enable can time them individually. */
+ * as one CUDA graph; 0 issues its launches one by one so that pn_profile_enable can time them individually.
+ * "spmm_grouped" (default 1): K11 SpMM (pn_spmm_k11, PCG) with the rows of one node sharing every X-row load; 0 = one
+ * lane group per row (kept for A/B measurements; same bits). */
 PN_EXPORT int pn_set_option(pn_ctx *ctx, const char *name, int64_t value);
 /* Optional hint, callable once every pn_set_nodes / pn_set_springs / pn_set_members / pn_set_quads / pn_set_plates call
  * of a model has been made: starts the host half of the direct solver's analysis (node graph, nested dissection,

@@ -343,6 +343,7 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
     # The reference computes reactions after ALL combinations (`_calc_reactions` at the end of `analyze`): every
     # element contributes with its own per-combination activity, but the node support springs with the state the LAST
     # combination left them in.  Combinations whose support springs ended differently are recomputed with that state.
+    model._run.end_flags = end_flags
     if combo_list:
         final_nsf = end_flags[combo_list[-1].name][0]
         for ci, combo in enumerate(combo_list[:-1]):

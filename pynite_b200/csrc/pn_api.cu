@@ -508,6 +508,7 @@ int pn_set_option(pn_ctx *ctx, const char *name, int64_t value) {
     PN_API_BEGIN(ctx)
     if (!name) throw ArgError("pn_set_option: null name");
     if (!strcmp(name, "assembly_graph")) c->opt_assembly_graph = value != 0;
+    else if (!strcmp(name, "spmm_grouped")) c->opt_spmm_grouped = value != 0;
     else throw ArgError(std::string("pn_set_option: unknown option ") + name);
     PN_API_END
 }
@@ -1070,9 +1071,13 @@ int pn_spmm_k11(pn_ctx *ctx, int32_t s, const double *X, double *Y, int32_t repe
         PN_CUDA(cudaMemcpyAsync(dX.ptr, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
         PN_CUDA(cudaStreamSynchronize(st));
     }
-    spmm(c, c->blk[0], c->blk[0].vals.ptr, dX.ptr, dY.ptr, s, st);       // warm-up
+    auto apply = [&]() {
+        if (c->opt_spmm_grouped) spmm_k11_grouped(c, c->blk[0].vals.ptr, dX.ptr, dY.ptr, s, st);
+        else spmm(c, c->blk[0], c->blk[0].vals.ptr, dX.ptr, dY.ptr, s, st);
+    };
+    apply();                                                             // warm-up
     PN_CUDA(cudaEventRecord(c->ev0, st));
-    for (int r = 0; r < repeat; ++r) spmm(c, c->blk[0], c->blk[0].vals.ptr, dX.ptr, dY.ptr, s, st);
+    for (int r = 0; r < repeat; ++r) apply();
     PN_CUDA(cudaEventRecord(c->ev1, st));
     PN_CUDA(cudaEventSynchronize(c->ev1));
     float ms = 0;

@@ -1631,9 +1631,7 @@ static void analyse(Ctx *c) {
             int64_t n = fs.ns + fs.nb;
             F.f_off = foff; foff += n * n;
             F.w_off = noff; noff += n;             // scaled by s at solve time
-            F.l_off = l_total; l_total += n * fs.ns;
-            F.u_off = u_total; u_total += (int64_t)fs.ns * fs.nb;
-            F.inv_off = inv_total; inv_total += (int64_t)((fs.ns + NB - 1) / NB) * (2 * NB * NB);
+            F.l_off = F.u_off = F.inv_off = 0;     // assigned below, for the fronts this rank factorises
             front_level[q] = (uint8_t)l;
             d.level_max_ns[l] = std::max(d.level_max_ns[l], fs.ns);
             d.level_max_nb[l] = std::max(d.level_max_nb[l], fs.nb);
@@ -1644,6 +1642,19 @@ static void analyse(Ctx *c) {
         d.level_f_total[l] = foff; d.level_n_total[l] = noff;
     }
     if (d.n_levels > 255) throw ArgError("direct solver: elimination tree too deep");
+    // Subtree-to-GPU plan first: the permanent factor (panels, U12, diagonal inverses) is stored only for the fronts
+    // this rank factorises -- its subtrees and the replicated top -- so N GPUs hold an N times larger bottom of the tree.
+    build_dist_plan(c);
+    for (int l = 0; l < d.n_levels; ++l) {
+        const int q0 = d.dist.active ? d.dist.lo[l] : d.level_ptr[l], q1 = d.dist.active ? d.dist.hi[l] : d.level_ptr[l + 1];
+        for (int q = q0; q < q1; ++q) {
+            FrontDev &F = d.h_fronts[q];
+            const int64_t n = F.ns + F.nb;
+            F.l_off = l_total; l_total += n * F.ns;
+            F.u_off = u_total; u_total += (int64_t)F.ns * F.nb;
+            F.inv_off = inv_total; inv_total += (int64_t)((F.ns + NB - 1) / NB) * (2 * NB * NB);
+        }
+    }
     {
         std::vector<std::vector<std::pair<int32_t, int32_t>>> kids(nf);      // (child rank, child id), level-major ids
         for (int q = 0; q < nf; ++q)
@@ -1731,7 +1742,6 @@ static void analyse(Ctx *c) {
     int64_t amax = 0;
     for (int l = 0; l < d.n_levels; ++l) amax = std::max(amax, d.level_f_total[l]);
     d.arena[0].resize(amax); d.arena[1].resize(amax);
-    build_dist_plan(c);
     d.analysed = true;
     tick.lap("device maps + allocation");
     c->stats.factor_nnz = S.factor_entries;

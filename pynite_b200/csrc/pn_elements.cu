@@ -258,7 +258,7 @@ __global__ void k_element_forces(int64_t n, const int32_t *__restrict__ list /* 
                                  const int32_t *__restrict__ conn, const double *__restrict__ ke,
                                  const double *__restrict__ D, const double *__restrict__ fer_case /* or null */,
                                  int n_case, const double *__restrict__ fac_row, int64_t case_stride,
-                                 const uint8_t *__restrict__ active, double *__restrict__ out) {
+                                 const uint8_t *__restrict__ active, int inactive_quirk, double *__restrict__ out) {
     // thread = (element, row); the fixed-end term is combined from the per-case vectors on the fly
     int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t q = tid / ND;
@@ -266,14 +266,18 @@ __global__ void k_element_forces(int64_t n, const int32_t *__restrict__ list /* 
     if (q >= n) return;
     int64_t e = list ? list[q] : q;
     constexpr int NN = ND / 6;
-    if (active && !active[e]) { out[e * ND + r] = 0.0; return; }
+    // Inactive springs / members: excluded from the reactions (Analysis.py:1100, 1139).  Their own F() / f() in the
+    // reference still evaluate ke (T D) + fer with only the GLOBAL DX of both nodes dropped from D (Spring3D.D :222-225,
+    // Member3D.D :1110-1112) -- reproduced when `inactive_quirk` is set (the user-facing end forces).
+    const bool off = active && !active[e];
+    if (off && !inactive_quirk) { out[e * ND + r] = 0.0; return; }
     const double *row = ke + e * (int64_t)(ND * ND) + (int64_t)r * ND;
     double acc = 0.0;
 #pragma unroll
     for (int a = 0; a < NN; ++a) {
         int64_t nd = conn[NN * e + a];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) acc = fma(row[6 * a + k], D[6 * nd + k], acc);
+        for (int k = 0; k < 6; ++k) acc = fma(row[6 * a + k], (off && k == 0) ? 0.0 : D[6 * nd + k], acc);
     }
     if (fer_case) {
         double f = 0.0;
@@ -441,7 +445,7 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
         int64_t n = supported_only ? c->sup_list[k].n : m.n_springs;
         if (n) {
             k_element_forces<12><<<grid_for(n * 12, 96), 96, 0, st>>>(n, list, m.spring_ij.ptr, ev + c->ev_off_spring, D_dev,
-                                                                       nullptr, 0, fac, 0, m.spring_active.ptr, out_dev);
+                                                                       nullptr, 0, fac, 0, m.spring_active.ptr, supported_only ? 0 : 1, out_dev);
             c->count_launch();
         }
         break;
@@ -451,7 +455,7 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
         if (n) {
             k_element_forces<12><<<grid_for(n * 12, 96), 96, 0, st>>>(
                 n, list, m.mem_ij.ptr, ev + c->ev_off_member, D_dev, ferc ? ferc + c->ef_off_member : nullptr, ld.n_case, fac,
-                c->ef_count, m.mem_active.ptr, out_dev);
+                c->ef_count, m.mem_active.ptr, supported_only ? 0 : 1, out_dev);
             c->count_launch();
         }
         break;
@@ -461,7 +465,7 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
         if (n) {
             k_element_forces<24><<<grid_for(n * 24, 96), 96, 0, st>>>(
                 n, list, m.quad_ijmn.ptr, ev + c->ev_off_quad, D_dev, ferc ? ferc + c->ef_off_quad : nullptr, ld.n_case, fac,
-                c->ef_count, nullptr, out_dev);
+                c->ef_count, nullptr, 0, out_dev);
             c->count_launch();
         }
         break;
@@ -471,7 +475,7 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
         if (n) {
             k_element_forces<24><<<grid_for(n * 24, 96), 96, 0, st>>>(
                 n, list, m.plate_ijmn.ptr, ev + c->ev_off_plate, D_dev, ferc ? ferc + c->ef_off_plate : nullptr, ld.n_case, fac,
-                c->ef_count, nullptr, out_dev);
+                c->ef_count, nullptr, 0, out_dev);
             c->count_launch();
         }
         break;

@@ -225,6 +225,11 @@ struct Ctx {
     DevBuf<int32_t> d1, d2, newidx; // newidx[dof] >= 0: position in d1; < 0: -1 - position in d2
     DevBuf<double> d2_val;
     CsrBlock blk[4];               // K11, K12, K21, K22
+    // K11 rows grouped by node (the free DOFs of a node are consecutive rows): row_group[g] .. row_group[g + 1];
+    // built lazily from the host masks, used by the node-grouped SpMM (one X-row load per node pair)
+    DevBuf<int32_t> row_group;
+    int64_t n_row_groups = 0;
+    bool row_groups_ready = false;
 
     // element-force buffer layout [springs*12 | members*12 | quads*24 | plates*24] and DOF incidence
     int64_t ef_count = 0, ef_off_spring = 0, ef_off_member = 0, ef_off_quad = 0, ef_off_plate = 0;
@@ -246,6 +251,7 @@ struct Ctx {
     DirectSolver *direct = nullptr;
     PcgWork *pcg = nullptr;
     FastAssembly *fast = nullptr;
+    bool opt_spmm_grouped = true;   // pn_set_option("spmm_grouped"): K11 SpMM with the rows of a node sharing their X-row loads
     bool opt_assembly_graph = true; // pn_set_option("assembly_graph"): replay the numeric assembly as one CUDA graph
     int64_t n_assemblies = 0;       // numeric assemblies on the current pattern
     bool fast_build_tried = false;  // the class / recipe maps are built lazily, at the second assembly
@@ -387,6 +393,7 @@ void residual_dd(Ctx *c, const CsrBlock &A, const double *vals, int64_t vals_col
                  double *R, int s, cudaStream_t st);
 void spmm_rows(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, int64_t row0, int64_t row1,
                cudaStream_t st);
+void spmm_k11_grouped(Ctx *c, const double *vals, const double *X, double *Y, int s, cudaStream_t st);
 void spmv_plain(Ctx *c, const CsrBlock &A, const double *vals, const double *x, double *y, cudaStream_t st);
 
 // ---- pn_assemble.cu -------------------------------------------------------------------------------

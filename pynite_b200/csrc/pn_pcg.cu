@@ -94,6 +94,8 @@ static void apply_matrix(Ctx *c, const double *vals11, int percol, const double 
         { ProfScope ps_(c, PS_SPMM); k_spmm_percol<<<grid_for(A.rows * s, 256), 256, 0, c->stream>>>(A.rows, s, A.nnz, A.indptr.ptr, A.indices.ptr,
                                                                          vals11, X, Y); }
         c->count_launch();
+    } else if (c->opt_spmm_grouped) {
+        spmm_k11_grouped(c, vals11, X, Y, s, c->stream);
     } else {
         spmm(c, A, vals11, X, Y, s, c->stream);
     }
