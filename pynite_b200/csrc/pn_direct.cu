@@ -758,9 +758,11 @@ __global__ void k_lu_transpose_panel(int first, int kb, const FrontDev *__restri
 // kernels, so the factor is bit-identical to theirs.
 // ------------------------------------------------------------------------------------------------
 constexpr int FUSED_FACTOR_SMEM = GEMM_SMEM > DIAG_SMEM ? GEMM_SMEM : DIAG_SMEM;
-// a level takes the one-CTA-per-front kernel when it has at least this many fronts (about two CTAs per SM)
+// a level takes the one-CTA-per-front kernel when it has at least this many fronts.  Measured on config 3 (B200,
+// profiles/r2_fused_factor_ab.md): 8192 fronts 10.6 -> 9.9 ms, 4096 fronts 3.0 -> 2.9 ms, but 512 fronts 2.5 -> 3.0 ms and
+// 256 fronts 3.2 -> 4.5 ms (a single CTA per 1000-row front is a long serial chain), hence the threshold.
 static int fused_factor_min() {
-    static const int v = getenv("PN_FUSED_FACTOR_MIN") ? atoi(getenv("PN_FUSED_FACTOR_MIN")) : 256;
+    static const int v = getenv("PN_FUSED_FACTOR_MIN") ? atoi(getenv("PN_FUSED_FACTOR_MIN")) : 4096;
     return v;
 }
 

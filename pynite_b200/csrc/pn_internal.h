@@ -251,7 +251,7 @@ struct Ctx {
     DirectSolver *direct = nullptr;
     PcgWork *pcg = nullptr;
     FastAssembly *fast = nullptr;
-    bool opt_spmm_grouped = true;   // pn_set_option("spmm_grouped"): K11 SpMM with the rows of a node sharing their X-row loads
+    bool opt_spmm_grouped = false;  // pn_set_option("spmm_grouped"): K11 SpMM with the rows of a node sharing their X-row loads
     bool opt_assembly_graph = true; // pn_set_option("assembly_graph"): replay the numeric assembly as one CUDA graph
     int64_t n_assemblies = 0;       // numeric assemblies on the current pattern
     bool fast_build_tried = false;  // the class / recipe maps are built lazily, at the second assembly
