@@ -132,6 +132,8 @@ struct DirectSolver {
     bool attrs_set = false;
     DevBuf<int> status;                       // 0 ok, 1 zero / non-finite pivot, 2 entry outside front
     bool shared_factor = false;               // the stored factor belongs to the matrix shared by all columns (Ke)
+    int64_t factor_epoch = -1;                // Ctx::assembly_epoch the stored factor was computed from
+    const double *factor_vals = nullptr;
     DevBuf<double> col_in, col_out;           // per-column solves (P-Delta)
     cudaStream_t fstream[4] = {nullptr, nullptr, nullptr, nullptr};   // factorisation: chains of front groups side by side
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -2535,7 +2537,13 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
     int refine = o.refine_steps >= 0 ? o.refine_steps : 1;
     DevBuf<double> &R = c->work_r;
     if (!percol) {
-        { PhaseTimer tm(c, &c->stats.ms_factor); factorise(c, vals11); }
+        // one factorisation per assembled matrix: later batches of right-hand sides reuse it
+        if (!(d.shared_factor && d.factor_epoch == c->assembly_epoch && d.factor_vals == vals11)) {
+            d.shared_factor = false;
+            { PhaseTimer tm(c, &c->stats.ms_factor); factorise(c, vals11); }
+            d.factor_epoch = c->assembly_epoch;
+            d.factor_vals = vals11;
+        }
         d.shared_factor = true;
         PhaseTimer tm(c, &c->stats.ms_solve);
         PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * n1 * s, cudaMemcpyDeviceToDevice, st));

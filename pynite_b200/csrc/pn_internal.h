@@ -254,6 +254,7 @@ struct Ctx {
     bool opt_spmm_grouped = false;  // pn_set_option("spmm_grouped"): K11 SpMM with the rows of a node sharing their X-row loads
     bool opt_assembly_graph = true; // pn_set_option("assembly_graph"): replay the numeric assembly as one CUDA graph
     int64_t n_assemblies = 0;       // numeric assemblies on the current pattern
+    int64_t assembly_epoch = 0;     // incremented by every numeric assembly: the direct solver reuses a factor of the same epoch
     bool fast_build_tried = false;  // the class / recipe maps are built lazily, at the second assembly
 
     DevBuf<uint8_t> cub_tmp;       // scratch for cub device-wide primitives
