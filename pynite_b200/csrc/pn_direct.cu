@@ -70,12 +70,16 @@ static inline unsigned grid_for(int64_t n, int tpb) { return (unsigned)((n + tpb
 constexpr int NB = 64;        // pivots per block step
 constexpr int BM = 128;       // GEMM tile rows
 constexpr int BN = 64;        // GEMM tile columns
-constexpr int BK = 64;        // GEMM k chunk (= NB: one chunk per rank-NB update)
-constexpr int SA_LD = BK + 4; // leading dimensions = 4 mod 16 doubles: the DMMA fragment loads of a half-warp hit 32 distinct banks
-constexpr int SB_LD = BN + 4;
-constexpr int GEMM_SMEM = (BM * SA_LD + BK * SB_LD) * (int)sizeof(double);   // 104 448 B, two CTAs per SM
+constexpr int GEMM_SLICES = 3;             // ring of 16-wide k slices in shared memory
+constexpr int BK = 16 * GEMM_SLICES;
+constexpr int SA_LD = BK + 8; // = 8 (mod 16) doubles, SB_LD = 2 (mod 8): conflict-free 16-byte fragment loads (see gemm_tile)
+constexpr int SB_LD = BN + 2;
+constexpr int GEMM_SMEM = (BM * SA_LD + BK * SB_LD) * (int)sizeof(double);   // 82 688 B, two CTAs per SM
 constexpr int DIAG_LD = NB + 1;
 constexpr int DIAG_SMEM = (3 * NB * DIAG_LD + 5 * NB + 2) * (int)sizeof(double);      // 102 416 B, two CTAs per SM
+// leading dimension of a front matrix in its arena: n rounded up to even, so that every row starts 16-byte aligned
+// (16-byte cp.async / vector loads in gemm_tile)
+__host__ __device__ __forceinline__ int front_ld(int n) { return (n + 1) & ~1; }
 constexpr int GB = 256;      // pivots per group: the trailing matrix is streamed once per group (rank-GB update)
 
 struct FrontDev {
@@ -193,7 +197,7 @@ __global__ void k_entry_maps(int64_t nnz, const int32_t *__restrict__ ent_row, c
     int li = front_find(list, n, pi), lj = front_find(list, n, pj);
     if (li < 0 || lj < 0) { atomicMax(status, 2); li = lj = 0; }
     ent_front[k] = f;
-    ent_dst[k] = (uint32_t)li * (uint32_t)n + (uint32_t)lj;
+    ent_dst[k] = (uint32_t)li * (uint32_t)front_ld(n) + (uint32_t)lj;
     ent_level[k] = front_level[f];
 }
 
@@ -221,7 +225,7 @@ __global__ void k_dist_um(int first, const FrontDev *__restrict__ fronts, int cu
     const int n = F.ns + F.nb;
     double *seg = buf + um_off[q - cut_first];
     for (int a = blockIdx.y; a < F.nb; a += gridDim.y) {
-        double *row = arena + F.f_off + (int64_t)(F.ns + a) * n + F.ns;
+        double *row = arena + F.f_off + (int64_t)(F.ns + a) * front_ld(n) + F.ns;
         double *srow = seg + (int64_t)a * F.nb;
         const int bend = sym ? a + 1 : F.nb;       // symmetric mode keeps the lower triangle only
         if (unpack) for (int b = threadIdx.x; b < bend; b += blockDim.x) row[b] = srow[b];
@@ -259,8 +263,9 @@ __global__ void k_zero_lower(int first, const FrontDev *__restrict__ fronts, dou
     const int n = F.ns + F.nb;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int r = blockIdx.y * nw + warp; r < n; r += gridDim.y * nw) {
-        double *row = arena + F.f_off + (int64_t)r * n;
-        // f_off + r n may be odd: peel to 16-byte alignment, then double2 stores
+        double *row = arena + F.f_off + (int64_t)r * front_ld(n);
+        // (kept general: peels if a row start is not 16-byte aligned)
+        // f_off + r ld may be odd: peel to 16-byte alignment, then double2 stores
         int c = 0;
         if ((reinterpret_cast<uintptr_t>(row) & 15) != 0) { if (lane == 0) row[0] = 0.0; c = 1; }
         const int end = r + 1;
@@ -280,7 +285,7 @@ __global__ void k_extend_add(int first_child, int n_children, int rank, const Fr
     FrontDev C = fronts[first_child + ci];
     if (C.parent < 0 || C.child_rank != rank || C.nb == 0) return;
     FrontDev P = fronts[C.parent];
-    const int nc = C.ns + C.nb, np = P.ns + P.nb;
+    const int nc = front_ld(C.ns + C.nb), np = front_ld(P.ns + P.nb);     // leading dimensions
     const int32_t *r = rel + C.rel_off;
     for (int a = blockIdx.y; a < C.nb; a += gridDim.y) {
         const double *src = child_arena + C.f_off + (int64_t)(C.ns + a) * nc + C.ns;
@@ -298,6 +303,11 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, 
     int bytes = pred ? 8 : 0;                 // src-size 0: nothing is read, the 8 bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes));
 }
+// 16-byte copy (SASS LDGSTS.E.BYPASS.128); the first `bytes` (0, 8 or 16) come from global memory, the rest is zero-filled
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc, int bytes) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -314,8 +324,19 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // (tools/microbench/fp64_pipes.cu: DMMA 37.0 vs DFMA 36.7 TFLOP/s peak on B200 -- the tensor path is used
 // because a fragment needs 1/6 of the shared-memory bytes the FMA register tile needs, not for its peak).
 // mode 0: C -= A B;  mode 1: C = A B.
-// The C tile is read straight into the accumulators while the first operand slices are in flight; the operand
-// tiles stream through shared memory as a ring of four 16-wide k slices filled by cp.async.
+// Round-2 layout (tools/microbench/gemm_variants.cu, profiles/r2_gemm_variants.md: 22 -> 27 TFLOP/s on the rank-256
+// update of the 4 500-row fronts; the ablation there puts the remaining distance to the 33 TFLOP/s of the same loop
+// without copies on the global -> shared copies):
+//   * operands stream through a ring of three 16-wide k slices filled by 16-byte cp.async (SASS LDGSTS.E.BYPASS.128)
+//     when the leading dimensions are even and the operand origins 16-byte aligned, by 8-byte copies otherwise;
+//   * fragments are read with 16-byte shared loads: the DMMA contracts over the k index held by lane%4, and WHICH four
+//     k of a slice those are is free as long as A and B agree, so lane tg takes k = 8 kp + 2 tg + e for two consecutive
+//     DMMAs (e = 0, 1): one LDS.128 of A[row][8 kp + 2 tg .. +1] feeds both.  Likewise the 8 columns of a DMMA tile need
+//     not be adjacent: tile ni = 2 np + e2 holds columns 16 np + 2 g + e2, so one LDS.128 of B[k][16 np + 2 g .. +1] feeds
+//     tiles 2 np and 2 np + 1, and a lane's accumulators of a tile pair are the four consecutive columns 16 np + 4 tg + {0..3}
+//     (32-byte global loads / stores of C).  Shared leading dimensions: A = 8 (mod 16) doubles, B = 2 (mod 8): the eight
+//     16-byte accesses of a quarter-warp fall into eight different bank groups;
+//   * mode 0 keeps -C in the accumulators (negated on load and on store: exact), so the loop has no sign multiply.
 // In-place use (C aliasing A or B) is safe when the tile covers the aliased operand's full extent in the other
 // dimension: every global read is complete (wait_group 0 + barrier) before the first store.
 // Warps whose 32 x 32 block lies outside the matrix, or (lower_only: C is a symmetric trailing matrix of which only the
@@ -326,118 +347,173 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
                                           int m, int n, int k, int tile_m, int tile_n, int mode, bool lower_only = false,
                                           double *Ct = nullptr, int64_t ldct = 0, const double *ct_scale = nullptr, int64_t ct_scale_ld = 0,
                                           double *Ct2 = nullptr, int64_t ldct2 = 0, int ct2_row0 = 0) {
-    double(*sA)[SA_LD] = reinterpret_cast<double(*)[SA_LD]>(pn_dyn_smem);
-    double(*sB)[SB_LD] = reinterpret_cast<double(*)[SB_LD]>(pn_dyn_smem + BM * SA_LD);
+    double *sA = pn_dyn_smem;                      // [BM][SA_LD]
+    double *sB = pn_dyn_smem + BM * SA_LD;         // [BK][SB_LD]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
     const int row0 = tile_m * BM, col0 = tile_n * BN;
     const int wrow = (warp >> 1) * 32, wcol = (warp & 1) * 32;
+    // acc[mi][2 np + e2][e1] = (mode 0: minus) C[row0 + wrow + 8 mi + g][col0 + wcol + 16 np + 4 tg + 2 e1 + e2]
     double acc[4][4][2];
-    const bool full_tile = row0 + BM <= m && col0 + BN <= n;
     const bool warp_on = row0 + wrow < m && col0 + wcol < n && !(lower_only && row0 + wrow + 31 < col0 + wcol);
+    const bool full_tile = row0 + BM <= m && col0 + BN <= n;
+    const bool c16 = full_tile && (ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
     if (mode != 0 || !warp_on) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    } else if (full_tile) {
-        const double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 2 * tg;
+    } else if (c16) {
+        const double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 4 * tg;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                acc[mi][ni][0] = c0p[(int64_t)(8 * mi) * ldc + 8 * ni];
-                acc[mi][ni][1] = c0p[(int64_t)(8 * mi) * ldc + 8 * ni + 1];
+            for (int np = 0; np < 2; ++np) {
+                const double2 lo = *reinterpret_cast<const double2 *>(c0p + (int64_t)(8 * mi) * ldc + 16 * np);
+                const double2 hi = *reinterpret_cast<const double2 *>(c0p + (int64_t)(8 * mi) * ldc + 16 * np + 2);
+                acc[mi][2 * np][0] = -lo.x; acc[mi][2 * np + 1][0] = -lo.y;
+                acc[mi][2 * np][1] = -hi.x; acc[mi][2 * np + 1][1] = -hi.y;
             }
     } else {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
-            int gr = row0 + wrow + 8 * mi + g;
+            const int gr = row0 + wrow + 8 * mi + g;
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                int gc = col0 + wcol + 8 * ni + 2 * tg;
-                bool ok = gr < m;
-                acc[mi][ni][0] = (ok && gc < n) ? C[(int64_t)gr * ldc + gc] : 0.0;
-                acc[mi][ni][1] = (ok && gc + 1 < n) ? C[(int64_t)gr * ldc + gc + 1] : 0.0;
-            }
+            for (int np = 0; np < 2; ++np)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gc = col0 + wcol + 16 * np + 4 * tg + q;
+                    acc[mi][2 * np + (q & 1)][q >> 1] = (gr < m && gc < n) ? -C[(int64_t)gr * ldc + gc] : 0.0;
+                }
         }
     }
-    const double sign = mode == 0 ? -1.0 : 1.0;
-    // k runs through a ring of four 16-wide slices of the shared tiles (slot = slice & 3): slice sl + 3 is in
-    // flight while slice sl is multiplied, one barrier per slice.
+    // k runs through a ring of GEMM_SLICES 16-wide slices of the shared tiles: slices sl + 1, sl + 2 are in flight while
+    // slice sl is multiplied, one barrier per slice.
     // The DMMA holds the issue port of its scheduler for its whole duration (tools/microbench/dmma_occupancy.cu:
     // every other instruction costs ~0.85 cycles of tensor time, at any occupancy), so the copy loop issues as few
-    // instructions as it can while staying coalesced (16 consecutive lanes = 16 consecutive k of one A row / 64
-    // consecutive columns of one B row) and conflict-free in shared memory: per copy one 32-bit offset from a
-    // per-slice base (IMAD), one IMAD.WIDE, one LDGSTS; the row / column predicates are decided once per tile.
+    // instructions as it can: per copy one 32-bit offset from a per-slice base (IMAD), one IMAD.WIDE, one LDGSTS; the
+    // row / column predicates are decided once per tile.
     // Rows >= m of the A tile and columns >= n of the B tile only feed accumulators that are never stored, so in
     // full slices their copies are clamped to a valid row / column instead of being predicated.
     const int nsl = (k + 15) >> 4;
-    const int ra = tid >> 4, ka = tid & 15;                 // A: rows ra + 16 i (i < 8), k column ka
-    const int kr = tid >> 6, cb = tid & 63;                 // B: k rows kr + 4 i (i < 4), column cb
     const int a_last = m - 1 - row0;                        // last valid tile row
-    const int cbc = min(cb, n - 1 - col0);                  // clamped column
+    const int ncol = n - col0;                              // valid columns of the B tile
     const uint32_t lda32 = (uint32_t)lda, ldb32 = (uint32_t)ldb;
-    const double *Abase = A + (int64_t)row0 * lda + ka;
+    const bool a16 = (lda & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    const bool b16 = (ldb & 1) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+    // 16-byte copies.  A slice: 128 rows x 8 chunks, rows ra + 32 i (i < 4), k offset ca;  B slice: 16 k rows x 32 chunks,
+    // k rows kr + 8 i (i < 2), column cb (clamped to the last valid chunk, of which `bbytes` are inside the matrix)
+    const int ra = tid >> 3, ca = (tid & 7) * 2;
+    const int kr = tid >> 5, cb = (tid & 31) * 2;
+    const int cbc = min(cb, (ncol - 1) & ~1);
+    const int bbytes = min(16, (ncol - cbc) * 8);
+    const double *Abase = A + (int64_t)row0 * lda + ca;
     const double *Bbase = B + col0 + cbc;
+    auto issue_a16 = [&](int slot, int kbase) {
+        const double *sa = Abase + kbase;
+        double *ta = sA + ra * SA_LD + 16 * slot + ca;
+        if (kbase + 16 <= k) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async16(ta + 32 * i * SA_LD, sa + (uint32_t)min(ra + 32 * i, a_last) * lda32, 16);
+        } else {                                            // last, partial slice: zero-fill k >= k_valid
+            const int ab = max(0, min(16, (k - kbase - ca) * 8));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async16(ta + 32 * i * SA_LD, ab ? sa + (uint32_t)min(ra + 32 * i, a_last) * lda32 : A, ab);
+        }
+    };
+    auto issue_b16 = [&](int slot, int kbase) {
+        const double *sb = Bbase + (int64_t)kbase * ldb;
+        double *tb = sB + (16 * slot + kr) * SB_LD + cb;
+        if (kbase + 16 <= k) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) cp_async16(tb + 8 * i * SB_LD, sb + (uint32_t)(kr + 8 * i) * ldb32, bbytes);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool ok = kbase + kr + 8 * i < k;
+                cp_async16(tb + 8 * i * SB_LD, ok ? sb + (uint32_t)(kr + 8 * i) * ldb32 : B, ok ? bbytes : 0);
+            }
+        }
+    };
+    // 8-byte copies into the same layout (odd leading dimension or origin): A rows ra8 + 16 i (i < 8), k column ka8;
+    // B k rows kr8 + 4 i (i < 4), column cb8
+    const int ra8 = tid >> 4, ka8 = tid & 15, kr8 = tid >> 6, cb8 = tid & 63;
+    const int cbc8 = min(cb8, ncol - 1);
+    auto issue_a8 = [&](int slot, int kbase) {
+        const bool oka = kbase + ka8 < k;
+        const double *sa = A + (int64_t)row0 * lda + kbase + ka8;
+        double *ta = sA + ra8 * SA_LD + 16 * slot + ka8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async8(ta + 16 * i * SA_LD, oka ? sa + (uint32_t)min(ra8 + 16 * i, a_last) * lda32 : A, oka);
+    };
+    auto issue_b8 = [&](int slot, int kbase) {
+        const double *sb = B + col0 + cbc8 + (int64_t)kbase * ldb;
+        double *tb = sB + (16 * slot + kr8) * SB_LD + cb8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = kbase + kr8 + 4 * i < k;
+            cp_async8(tb + 4 * i * SB_LD, ok ? sb + (uint32_t)(kr8 + 4 * i) * ldb32 : B, ok);
+        }
+    };
     auto issue = [&](int sl) {
         if (sl < nsl) {
-            const int slot = sl & 3, kbase = sl << 4;
-            const double *sa = Abase + kbase;
-            const double *sb = Bbase + (int64_t)kbase * ldb;
-            double *ta = &sA[ra][16 * slot + ka], *tb = &sB[16 * slot + kr][cb];
-            if (kbase + 16 <= k) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cp_async8(ta + 16 * i * SA_LD, sa + (uint32_t)min(ra + 16 * i, a_last) * lda32, true);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) cp_async8(tb + 4 * i * SB_LD, sb + (uint32_t)(kr + 4 * i) * ldb32, true);
-            } else {                                        // last, partial slice: zero-fill k >= k_valid
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool ok = kbase + ka < k;
-                    cp_async8(ta + 16 * i * SA_LD, ok ? sa + (uint32_t)min(ra + 16 * i, a_last) * lda32 : A, ok);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const bool ok = kbase + kr + 4 * i < k;
-                    cp_async8(tb + 4 * i * SB_LD, ok ? sb + (uint32_t)(kr + 4 * i) * ldb32 : B, ok);
-                }
-            }
+            const int slot = sl % GEMM_SLICES, kbase = sl << 4;
+            if (a16) issue_a16(slot, kbase); else issue_a8(slot, kbase);
+            if (b16) issue_b16(slot, kbase); else issue_b8(slot, kbase);
         }
         cp_async_commit();
     };
-    issue(0); issue(1); issue(2);
+#pragma unroll
+    for (int i = 0; i < GEMM_SLICES - 1; ++i) issue(i);
     for (int sl = 0; sl < nsl; ++sl) {
-        cp_async_wait<2>();
+        cp_async_wait<GEMM_SLICES - 2>();
         __syncthreads();
-        issue(sl + 3);
-        const int base = (sl & 3) << 4;
+        issue(sl + GEMM_SLICES - 1);
+        const int base = (sl % GEMM_SLICES) << 4;
         if (warp_on)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const int kk = base + 4 * ks + tg;
-            double a[4], b[4];
+        for (int kp = 0; kp < 2; ++kp) {
+            double2 a[4], b[2][2];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = sign * sA[wrow + 8 * mi + g][kk];
+            for (int mi = 0; mi < 4; ++mi) a[mi] = *reinterpret_cast<const double2 *>(sA + (wrow + 8 * mi + g) * SA_LD + base + 8 * kp + 2 * tg);
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = sB[kk][wcol + 8 * ni + g];
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int np = 0; np < 2; ++np)
+                    b[e][np] = *reinterpret_cast<const double2 *>(sB + (base + 8 * kp + 2 * tg + e) * SB_LD + wcol + 16 * np + 2 * g);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int np = 0; np < 2; ++np) {
+                    dmma884(acc[mi][2 * np][0], acc[mi][2 * np][1], a[mi].x, b[0][np].x);
+                    dmma884(acc[mi][2 * np + 1][0], acc[mi][2 * np + 1][1], a[mi].x, b[0][np].y);
+                }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    dmma884(acc[mi][2 * np][0], acc[mi][2 * np][1], a[mi].y, b[1][np].x);
+                    dmma884(acc[mi][2 * np + 1][0], acc[mi][2 * np + 1][1], a[mi].y, b[1][np].y);
+                }
         }
     }
     cp_async_wait<0>();
     __syncthreads();          // the tiles may be refilled by the caller's next gemm_tile call
     if (!warp_on) return;
+    if (mode == 0) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = -acc[mi][ni][0]; acc[mi][ni][1] = -acc[mi][ni][1]; }
+    }
     if (Ct) {
         // second, transposed and column-scaled copy of the result: Ct[col][row] = scale[col] * C[row][col] (the row
         // panel U = D L^T of the symmetric factorisation, written from the accumulators instead of by a transpose
         // kernel); the eight lanes that share a column write eight consecutive rows = one 64-byte segment
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
+        for (int np = 0; np < 2; ++np)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int gc = col0 + wcol + 8 * ni + 2 * tg + e;
+            for (int q = 0; q < 4; ++q) {
+                const int gc = col0 + wcol + 16 * np + 4 * tg + q;
                 if (gc >= n) continue;
                 const double sc = ct_scale[(int64_t)gc * ct_scale_ld];
                 double *dst = Ct + (int64_t)gc * ldct;
@@ -446,35 +522,36 @@ __device__ __forceinline__ void gemm_tile(const double *A, int64_t lda, const do
                 for (int mi = 0; mi < 4; ++mi) {
                     const int gr = row0 + wrow + 8 * mi + g;
                     if (gr < m) {
-                        const double v = sc * acc[mi][ni][e];
+                        const double v = sc * acc[mi][2 * np + (q & 1)][q >> 1];
                         dst[gr] = v;
                         if (dst2 && gr >= ct2_row0) dst2[gr] = v;
                     }
                 }
             }
     }
-    if (full_tile) {
-        double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 2 * tg;
+    if (c16) {
+        double *c0p = C + (int64_t)(row0 + wrow + g) * ldc + col0 + wcol + 4 * tg;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                c0p[(int64_t)(8 * mi) * ldc + 8 * ni] = acc[mi][ni][0];
-                c0p[(int64_t)(8 * mi) * ldc + 8 * ni + 1] = acc[mi][ni][1];
+            for (int np = 0; np < 2; ++np) {
+                *reinterpret_cast<double2 *>(c0p + (int64_t)(8 * mi) * ldc + 16 * np) = make_double2(acc[mi][2 * np][0], acc[mi][2 * np + 1][0]);
+                *reinterpret_cast<double2 *>(c0p + (int64_t)(8 * mi) * ldc + 16 * np + 2) = make_double2(acc[mi][2 * np][1], acc[mi][2 * np + 1][1]);
             }
         return;
     }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
-        int gr = row0 + wrow + 8 * mi + g;
+        const int gr = row0 + wrow + 8 * mi + g;
         if (gr >= m) continue;
         double *crow = C + (int64_t)gr * ldc;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            int gc = col0 + wcol + 8 * ni + 2 * tg;
-            if (gc < n) crow[gc] = acc[mi][ni][0];
-            if (gc + 1 < n) crow[gc + 1] = acc[mi][ni][1];
-        }
+        for (int np = 0; np < 2; ++np)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gc = col0 + wcol + 16 * np + 4 * tg + q;
+                if (gc < n) crow[gc] = acc[mi][2 * np + (q & 1)][q >> 1];
+            }
     }
 }
 
@@ -510,7 +587,7 @@ __device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *are
     double *rdiag = colb + 2 * NB;                      // [NB] reciprocal pivots
     double *rcpb = rdiag + NB;                          // [2]
     const int bs = min(NB, F.ns - kb);
-    const int n = F.ns + F.nb;
+    const int n = front_ld(F.ns + F.nb);       // leading dimension of the front
     double *A = arena + F.f_off + (int64_t)kb * n + kb;
     // thread (ti, tj) owns rows ti + 16 r and columns tj + 16 c (cyclic: the published row / column and the smem and
     // global accesses are contiguous across the lanes of a half-warp, and every thread stays busy until the end)
@@ -695,8 +772,8 @@ k_lu_panels(int first, int kb, int tiles_u, const FrontDev *__restrict__ fronts,
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
     const int bs = min(NB, F.ns - kb);
-    const int n = F.ns + F.nb;
-    const int r0 = kb + bs, rest = n - r0;
+    const int nn = F.ns + F.nb, n = front_ld(nn);       // n = leading dimension from here on
+    const int r0 = kb + bs, rest = nn - r0;
     if (rest <= 0) return;
     double *A = arena + F.f_off;
     const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
@@ -730,8 +807,8 @@ __global__ void k_lu_transpose_panel(int first, int kb, const FrontDev *__restri
     FrontDev F = fronts[first + blockIdx.x];
     if (kb >= F.ns) return;
     const int bs = min(NB, F.ns - kb);
-    const int n = F.ns + F.nb;
-    const int r0 = kb + bs, rest = n - r0;
+    const int nn = F.ns + F.nb, n = front_ld(nn);
+    const int r0 = kb + bs, rest = nn - r0;
     const int c0 = blockIdx.y * 32;
     if (c0 >= rest) return;
     double *A = arena + F.f_off;
@@ -772,7 +849,7 @@ __global__ void __launch_bounds__(256, 2)
 k_front_factor_fused(int first, const FrontDev *__restrict__ fronts, double *__restrict__ arena, double *__restrict__ inv,
                      int *__restrict__ status, int sym, double *__restrict__ U12, double *__restrict__ Lst) {
     const FrontDev F = fronts[first + blockIdx.x];
-    const int n = F.ns + F.nb;
+    const int nn = F.ns + F.nb, n = front_ld(nn);       // n = leading dimension, nn = rows
     double *A = arena + F.f_off;
     for (int g0 = 0; g0 < F.ns; g0 += GB) {
         const int ge = min(g0 + GB, F.ns);
@@ -780,7 +857,7 @@ k_front_factor_fused(int first, const FrontDev *__restrict__ fronts, double *__r
             diag_step(F, kb, arena, inv, status, sym);
             __syncthreads();
             const int bs = min(NB, F.ns - kb);
-            const int r0 = kb + bs, rest = n - r0;
+            const int r0 = kb + bs, rest = nn - r0;
             if (rest <= 0) continue;
             const double *Linv = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
             const double *Uinv = Linv + NB * NB;
@@ -805,7 +882,7 @@ k_front_factor_fused(int first, const FrontDev *__restrict__ fronts, double *__r
             // strips the rest of the group needs (k_lu_strip)
             if (kb + NB < ge) {
                 const int q0 = kb + NB;
-                const int wa = ge - q0, ha = n - q0;
+                const int wa = ge - q0, ha = nn - q0;
                 const int ta_n = (wa + BN - 1) / BN, ta_m = (ha + BM - 1) / BM;
                 const double *Lp = A + (int64_t)q0 * n + kb;
                 for (int t = 0; t < ta_m * ta_n; ++t) {
@@ -813,7 +890,7 @@ k_front_factor_fused(int first, const FrontDev *__restrict__ fronts, double *__r
                     gemm_tile(Lp, n, A + (int64_t)kb * n + q0, n, A + (int64_t)q0 * n + q0, n, ha, wa, NB, t / ta_n, t % ta_n, 0, sym != 0);
                 }
                 if (!sym) {
-                    const int hb = ge - q0, wb = n - ge;
+                    const int hb = ge - q0, wb = nn - ge;
                     const int tb_n = (wb + BN - 1) / BN, tb_m = (hb + BM - 1) / BM;
                     for (int t = 0; t < tb_m * tb_n; ++t)
                         gemm_tile(Lp, n, A + (int64_t)kb * n + ge, n, A + (int64_t)q0 * n + ge, n, hb, wb, NB, t / tb_n, t % tb_n, 0);
@@ -822,7 +899,7 @@ k_front_factor_fused(int first, const FrontDev *__restrict__ fronts, double *__r
             }
         }
         // trailing update of the group (k_lu_update)
-        const int rest = n - ge;
+        const int rest = nn - ge;
         if (rest > 0) {
             const int tn_ = (rest + BN - 1) / BN, tm_ = (rest + BM - 1) / BM;
             for (int tm = 0; tm < tm_; ++tm)
@@ -861,11 +938,11 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
     const int ge = min(g0 + GB, F.ns);
     const int r0 = kb + NB;
     if (r0 >= ge) return;
-    const int n = F.ns + F.nb;
+    const int nn = F.ns + F.nb, n = front_ld(nn);       // n = leading dimension, nn = rows
     double *A = arena + F.f_off;
-    const int wa = ge - r0, ha = n - r0;
+    const int wa = ge - r0, ha = nn - r0;
     const int ta_n = (wa + BN - 1) / BN, ta_m = (ha + BM - 1) / BM;
-    const int hb = ge - r0, wb = n - ge;
+    const int hb = ge - r0, wb = nn - ge;
     const int tb_n = (wb + BN - 1) / BN, tb_m = (hb + BM - 1) / BM;
     int t = front_on_x ? blockIdx.y : blockIdx.x;
     const double *Lp = A + (int64_t)r0 * n + kb;        // L[r0:, kb:r0]
@@ -889,8 +966,8 @@ k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__re
     FrontDev F = fronts[first + (front_on_x ? blockIdx.x : blockIdx.z)];
     if (g0 >= F.ns) return;
     const int ge = min(g0 + GB, F.ns);
-    const int n = F.ns + F.nb;
-    const int rest = n - ge;
+    const int nn = F.ns + F.nb, n = front_ld(nn);       // n = leading dimension, nn = rows
+    const int rest = nn - ge;
     if ((int)blockIdx.y * BM >= rest || tcol * BN >= rest) return;
     if (sym && ((int)blockIdx.y + 1) * BM <= tcol * BN) return;      // tile strictly above the diagonal
     double *A = arena + F.f_off;
@@ -908,8 +985,8 @@ k_store_panels(int first, const FrontDev *__restrict__ fronts, const double *__r
     const int kb = blockIdx.y * NB;
     if (kb >= F.ns) return;
     const int bs = min(NB, F.ns - kb);
-    const int n = F.ns + F.nb;
-    const int up_rows = kb, lo_rows = n - kb - bs;
+    const int nn = F.ns + F.nb, n = front_ld(nn);
+    const int up_rows = kb, lo_rows = nn - kb - bs;
     const int up_tiles = (up_rows + BM - 1) / BM, lo_tiles = (lo_rows + BM - 1) / BM;
     int t = blockIdx.z;
     const double *Linv = inv + F.inv_off + (int64_t)blockIdx.y * (2 * NB * NB);
@@ -923,7 +1000,7 @@ k_store_panels(int first, const FrontDev *__restrict__ fronts, const double *__r
 __global__ void k_copy_u12(int first, const FrontDev *__restrict__ fronts, const double *__restrict__ arena,
                            double *__restrict__ U) {
     FrontDev F = fronts[first + blockIdx.x];
-    int n = F.ns + F.nb;
+    int n = front_ld(F.ns + F.nb);
     int64_t total = (int64_t)F.ns * F.nb;
     const double *A = arena + F.f_off;
     for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.y * blockDim.x) {
@@ -1633,7 +1710,7 @@ static void analyse(Ctx *c) {
             F.child_rank = fs.child_rank;
             F.idx_off = fs.idx_off; F.rel_off = fs.rel_off;
             int64_t n = fs.ns + fs.nb;
-            F.f_off = foff; foff += n * n;
+            F.f_off = foff; foff += n * front_ld((int)n);
             F.w_off = noff; noff += n;             // scaled by s at solve time
             F.l_off = F.u_off = F.inv_off = 0;     // assigned below, for the fronts this rank factorises
             front_level[q] = (uint8_t)l;
