@@ -4,10 +4,64 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <future>
+#include <mutex>
 #include <numeric>
+#include <omp.h>
+#include <thread>
+#include <unistd.h>
 
 #include "pn_internal.h"
+
+namespace pn {
+struct HostWorker {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::packaged_task<void()>> q;
+    pid_t pid;
+    HostWorker() : pid(getpid()) { std::thread([this] { run(); }).detach(); }
+    void run() {
+        for (;;) {
+            std::packaged_task<void()> t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !q.empty(); });
+                t = std::move(q.front());
+                q.pop_front();
+            }
+            t();                              // exceptions travel through the task's future
+        }
+    }
+};
+
+// OpenMP threads of the host-worker jobs: pn_set_option("host_threads") when set (several processes sharing the cores
+// of one box: one rank per GPU), else one less than the OpenMP default -- the caller's thread is busy with the uploads
+// and the symbolic phase while the ordering runs, and a team as wide as the machine then waits at every barrier for the
+// member that shares its core (measured on the 16-core box: ordering 42 ms with 16 threads beside the caller, 23 ms alone).
+int host_worker_threads(const Ctx *c) {
+    if (c->opt_host_threads > 0) return c->opt_host_threads;
+    return std::max(1, omp_get_max_threads() - 1);
+}
+
+std::future<void> host_worker_submit(std::function<void()> job) {
+    // never destroyed: the thread sleeps on its condition variable until the process exits.  A forked child gets its own
+    // worker (threads do not survive fork).
+    static std::mutex guard;
+    static HostWorker *w = nullptr;
+    std::packaged_task<void()> t(std::move(job));
+    std::future<void> f = t.get_future();
+    std::lock_guard<std::mutex> g(guard);
+    if (!w || w->pid != getpid()) w = new HostWorker();
+    {
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->q.push_back(std::move(t));
+    }
+    w->cv.notify_one();
+    return f;
+}
+}  // namespace pn
 
 using namespace pn;
 
@@ -215,68 +269,87 @@ int batch_size(Ctx *c, int n_combo) {
     return std::max(s, 1);
 }
 
-// rows `dofs` of every combo's reaction vector: out[j][i] = R[j][dofs[i]]
-__global__ void k_gather_reaction_rows(int64_t nr, int nc, int64_t n_dof, const int32_t *__restrict__ dofs,
-                                       const double *__restrict__ R, double *__restrict__ out) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= nr * nc) return;
-    int64_t j = t / nr, i = t - j * nr;
-    out[t] = R[j * n_dof + dofs[i]];
-}
-
 // Reactions are exactly zero except at supported DOFs and at DOFs with an active node support spring (k_reactions).
-// When those are few (a plate pinned on its perimeter: 6 000 of 1.5 M DOFs) only their rows cross PCIe; the host array
-// is zero-filled by a worker thread (OpenMP) while the device computes, then the rows are scattered into it.
-void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
-    if (!Rxn_out) return;
-    PhaseTimer tm(c, &c->stats.ms_reactions);
-    build_incidence(c);
-    DevBuf<double> &rx = c->work_rx;
-    const int nc = c->loads.n_combo;
+// When those are few (a plate pinned on its perimeter: 6 000 of 1.5 M DOFs) only their rows are computed and cross PCIe;
+// the host array is zero-filled by the host worker (OpenMP) while the device factorises (reactions_prepare, called at the
+// start of the solve), then the rows are scattered into it.
+static bool reactions_compact(Ctx *c) {
     const int64_t n_dof = c->n_dof;
     const Model &m = c->model;
     if (!c->rxn_list_ready) {
         c->h_rxn_dofs.clear();
-        for (int64_t d = 0; d < n_dof; ++d) {
-            const uint8_t f = m.h_nspring_flag[d];
-            if (((m.h_support[d / 6] >> (d % 6)) & 1u) || ((f & 1u) && (f & 2u))) c->h_rxn_dofs.push_back((int32_t)d);
+        const uint8_t *flag = m.h_nspring_flag.data();
+        const uint8_t *sup = m.h_support.data();
+        for (int64_t nd = 0; nd < m.n_nodes; ++nd) {
+            const uint8_t su = sup[nd];
+            for (int k = 0; k < 6; ++k) {
+                const uint8_t f = flag[6 * nd + k];
+                if (((su >> k) & 1u) || ((f & 1u) && (f & 2u))) c->h_rxn_dofs.push_back((int32_t)(6 * nd + k));
+            }
         }
         c->rxn_dofs.upload(c->h_rxn_dofs.data(), (int64_t)c->h_rxn_dofs.size(), c->stream);
         c->rxn_list_ready = true;
     }
-    const int64_t nr = (int64_t)c->h_rxn_dofs.size();
     static const bool full = getenv("PN_FULL_REACTION_DOWNLOAD") != nullptr;
-    const bool compact = !full && nr * 8 < n_dof;
-    std::future<void> zero;
-    if (compact)
-        zero = std::async(std::launch::async, [Rxn_out, nc, n_dof]() {
-            const int64_t total = (int64_t)nc * n_dof, chunk = 1 << 20;
-#pragma omp parallel for schedule(static)
-            for (int64_t b = 0; b < (total + chunk - 1) / chunk; ++b)
-                memset(Rxn_out + b * chunk, 0, sizeof(double) * (size_t)std::min(chunk, total - b * chunk));
-        });
-    rx.resize((int64_t)nc * n_dof);
-    for (int j = 0; j < nc; ++j) compute_reactions(c, j, pdelta, rx.ptr + (int64_t)j * n_dof);
+    return !full && (int64_t)c->h_rxn_dofs.size() * 8 < n_dof;
+}
+
+// Starts the zero fill of the caller's reaction array on the host worker.  The job queues behind the ordering of the
+// direct solver (same worker, FIFO), i.e. it runs while the device factorises and its threads do not compete with the
+// ordering, which is on the critical path.
+void reactions_prepare(Ctx *c, double *Rxn_out) {
+    c->rxn_zero = std::future<void>();
+    if (!Rxn_out || !reactions_compact(c)) return;
+    const int nc = c->loads.n_combo;
+    const int64_t n_dof = c->n_dof;
+    const int wt = host_worker_threads(c);
+    c->rxn_zero = host_worker_submit([Rxn_out, nc, n_dof, wt]() {
+        const int64_t total = (int64_t)nc * n_dof, chunk = 1 << 20;
+#pragma omp parallel for schedule(static) num_threads(wt)
+        for (int64_t b = 0; b < (total + chunk - 1) / chunk; ++b)
+            memset(Rxn_out + b * chunk, 0, sizeof(double) * (size_t)std::min(chunk, total - b * chunk));
+    });
+}
+
+void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
+    if (!Rxn_out) return;
+    PhaseTimer tm(c, &c->stats.ms_reactions);
+    HostTick tick("reactions_out");
+    tick.sync = false;
+    build_incidence(c);
+    tick.lap("incidence");
+    const int nc = c->loads.n_combo;
+    const int64_t n_dof = c->n_dof;
+    const bool compact = reactions_compact(c);
+    const int64_t nr = (int64_t)c->h_rxn_dofs.size();
     if (!compact) {
+        DevBuf<double> &rx = c->work_rx;
+        rx.resize((int64_t)nc * n_dof);
+        compute_reactions_batch(c, 0, nc, pdelta, nullptr, 0, rx.ptr);
         download(rx, Rxn_out, c->stream);
         PN_CUDA(cudaStreamSynchronize(c->stream));
         return;
     }
+    if (!c->rxn_zero.valid()) reactions_prepare(c, Rxn_out);        // (callers that did not announce the array)
     c->rxn_rows.resize(nr * nc);
     c->h_rxn_rows.resize((size_t)(nr * nc));
     if (nr) {
-        k_gather_reaction_rows<<<grid_for(nr * nc, 256), 256, 0, c->stream>>>(nr, nc, n_dof, c->rxn_dofs.ptr, rx.ptr, c->rxn_rows.ptr);
-        c->count_launch();
+        compute_reactions_batch(c, 0, nc, pdelta, c->rxn_dofs.ptr, nr, c->rxn_rows.ptr);
         download(c->rxn_rows, c->h_rxn_rows.data(), c->stream);
     }
+    tick.lap("launches enqueued");
     PN_CUDA(cudaStreamSynchronize(c->stream));
-    zero.get();
+    tick.lap("stream sync");
+    c->rxn_zero.get();
+    c->rxn_zero = std::future<void>();
+    tick.lap("wait for zero fill");
     const int32_t *rd = c->h_rxn_dofs.data();
     for (int j = 0; j < nc; ++j) {
         double *dst = Rxn_out + (int64_t)j * n_dof;
         const double *src = c->h_rxn_rows.data() + (int64_t)j * nr;
         for (int64_t i = 0; i < nr; ++i) dst[rd[i]] = src[i];
     }
+    tick.lap("scatter rows");
 }
 
 // D_out != null: the displacements of a finished batch are copied to the host on the second stream while the next batch
@@ -521,6 +594,7 @@ int pn_set_option(pn_ctx *ctx, const char *name, int64_t value) {
     if (!name) throw ArgError("pn_set_option: null name");
     if (!strcmp(name, "assembly_graph")) c->opt_assembly_graph = value != 0;
     else if (!strcmp(name, "spmm_grouped")) c->opt_spmm_grouped = value != 0;
+    else if (!strcmp(name, "host_threads")) c->opt_host_threads = (int)std::max<int64_t>(0, value);
     else throw ArgError(std::string("pn_set_option: unknown option ") + name);
     PN_API_END
 }
@@ -637,14 +711,23 @@ int pn_set_loads(pn_ctx *ctx, int32_t n_case,
     // duplicates of one (index, case) pair are summed in input (= model) order
     auto unique_sum = [&](int64_t n, const int32_t *idx, const int32_t *cs, const double *val, int64_t idx_limit,
                           const char *what, std::vector<int32_t> &oi, std::vector<int32_t> &oc, std::vector<double> &ov) {
-        std::vector<int64_t> order(n);
-        std::iota(order.begin(), order.end(), 0);
         for (int64_t k = 0; k < n; ++k)
             if (idx[k] < 0 || idx[k] >= idx_limit || cs[k] < 0 || cs[k] >= n_case)
                 throw ArgError(std::string(what) + ": index or case out of range");
-        auto less = [&](int64_t a, int64_t b) { return cs[a] != cs[b] ? cs[a] < cs[b] : idx[a] < idx[b]; };
-        if (!std::is_sorted(order.begin(), order.end(), less))      // generated input usually arrives grouped by case
-            std::stable_sort(order.begin(), order.end(), less);
+        // (case, index) order by a stable counting sort on the case, then a comparison sort only inside the cases whose
+        // indices do not already ascend (generated input arrives element-major: linear time)
+        std::vector<int64_t> order(n), start((size_t)n_case + 1, 0);
+        for (int64_t k = 0; k < n; ++k) ++start[cs[k] + 1];
+        for (int32_t q = 0; q < n_case; ++q) start[q + 1] += start[q];
+        {
+            std::vector<int64_t> fill(start.begin(), start.end() - 1);
+            for (int64_t k = 0; k < n; ++k) order[fill[cs[k]]++] = k;
+        }
+        for (int32_t q = 0; q < n_case; ++q) {
+            auto b = order.begin() + start[q], e = order.begin() + start[q + 1];
+            auto less = [&](int64_t a, int64_t bb) { return idx[a] < idx[bb]; };
+            if (!std::is_sorted(b, e, less)) std::stable_sort(b, e, less);
+        }
         oi.clear(); oc.clear(); ov.clear();
         oi.reserve(n); oc.reserve(n); ov.reserve(n);
         for (int64_t q = 0; q < n; ++q) {
@@ -754,13 +837,20 @@ int pn_solve_linear(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, doubl
     pn_solve_opts o = default_opts(opts);
     Loads &ld = c->loads;
     c->solved = c->solved_pdelta = false;
+    HostTick tick("pn_solve_linear");
+    tick.sync = false;
     ensure_assembled(c, c->symbolic_ready ? c->sym_flags : 0u);
     ensure_loads(c);
+    tick.lap("assembled + load vectors");
+    reactions_prepare(c, Rxn_out);
     solve_linear_all(c, o, D_out);      // (the displacement download runs on the second stream, batch by batch)
+    tick.lap("solve_linear_all");
     c->solved = true;
     reactions_out(c, false, Rxn_out);
+    tick.lap("reactions_out");
     PN_CUDA(cudaStreamSynchronize(c->stream2));
     PN_CUDA(cudaStreamSynchronize(c->stream));
+    tick.lap("final syncs (D download)");
     (void)ld;
     c->stats.kernel_launches = c->launches;
     if (stats) *stats = c->stats;

@@ -1646,8 +1646,8 @@ void direct_prefetch(Ctx *c) {
     try { join_host_analysis(d); } catch (...) {}
     d.analysed = false;
     d.host_state = 1;
-    const int wt = omp_get_max_threads();
-    d.host_future = std::async(std::launch::async, [c, wt]() {
+    const int wt = host_worker_threads(c);
+    d.host_future = host_worker_submit([c, wt]() {
         cudaSetDevice(c->device);          // the page-locked index lists are allocated from this thread
         omp_set_num_threads(wt);
         const Model &mm = c->model;

@@ -258,8 +258,13 @@ __global__ void k_element_forces(int64_t n, const int32_t *__restrict__ list /* 
                                  const int32_t *__restrict__ conn, const double *__restrict__ ke,
                                  const double *__restrict__ D, const double *__restrict__ fer_case /* or null */,
                                  int n_case, const double *__restrict__ fac_row, int64_t case_stride,
-                                 const uint8_t *__restrict__ active, int inactive_quirk, double *__restrict__ out) {
-    // thread = (element, row); the fixed-end term is combined from the per-case vectors on the fly
+                                 const uint8_t *__restrict__ active, int inactive_quirk, double *__restrict__ out,
+                                 int64_t d_stride, int64_t out_stride) {
+    // thread = (element, row); the fixed-end term is combined from the per-case vectors on the fly.
+    // grid.y = combination of a batch: D, the factor row and the output advance by their strides.
+    D += blockIdx.y * d_stride;
+    fac_row += blockIdx.y * (int64_t)n_case;
+    out += blockIdx.y * out_stride;
     int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t q = tid / ND;
     int r = (int)(tid % ND);
@@ -431,7 +436,11 @@ void launch_shell_fer(Ctx *c, bool quad, const double *pressure_dev, double *out
 // combo: fixed-end vectors are combined with that combo's factors; supported_only restricts the work to the
 // elements that touch a supported node (all that Analysis._calc_reactions :1081-1267 needs).
 void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo, bool supported_only, double *out_dev,
-                           cudaStream_t st) {
+                           cudaStream_t st, int n_batch, int64_t out_stride) {
+    // n_batch > 1: combinations combo .. combo + n_batch - 1 in one launch; D_dev is combo's vector inside D_all
+    // (stride n_dof), out_dev its output block (stride out_stride)
+    const int64_t d_stride = c->n_dof;
+    const unsigned gy = (unsigned)std::max(n_batch, 1);
     const Model &m = c->model;
     const Loads &ld = c->loads;
     const double *ev = c->ev.ptr;
@@ -444,8 +453,9 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
     case PN_SPRING: {
         int64_t n = supported_only ? c->sup_list[k].n : m.n_springs;
         if (n) {
-            k_element_forces<12><<<grid_for(n * 12, 96), 96, 0, st>>>(n, list, m.spring_ij.ptr, ev + c->ev_off_spring, D_dev,
-                                                                       nullptr, 0, fac, 0, m.spring_active.ptr, supported_only ? 0 : 1, out_dev);
+            k_element_forces<12><<<dim3(grid_for(n * 12, 96), gy), 96, 0, st>>>(n, list, m.spring_ij.ptr, ev + c->ev_off_spring, D_dev,
+                                                                       nullptr, ld.n_case, fac, 0, m.spring_active.ptr, supported_only ? 0 : 1, out_dev,
+                                                                       d_stride, out_stride);
             c->count_launch();
         }
         break;
@@ -453,9 +463,9 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
     case PN_MEMBER: {
         int64_t n = supported_only ? c->sup_list[k].n : m.n_members;
         if (n) {
-            k_element_forces<12><<<grid_for(n * 12, 96), 96, 0, st>>>(
+            k_element_forces<12><<<dim3(grid_for(n * 12, 96), gy), 96, 0, st>>>(
                 n, list, m.mem_ij.ptr, ev + c->ev_off_member, D_dev, ferc ? ferc + c->ef_off_member : nullptr, ld.n_case, fac,
-                c->ef_count, m.mem_active.ptr, supported_only ? 0 : 1, out_dev);
+                c->ef_count, m.mem_active.ptr, supported_only ? 0 : 1, out_dev, d_stride, out_stride);
             c->count_launch();
         }
         break;
@@ -463,9 +473,9 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
     case PN_QUAD: {
         int64_t n = supported_only ? c->sup_list[k].n : m.n_quads;
         if (n) {
-            k_element_forces<24><<<grid_for(n * 24, 96), 96, 0, st>>>(
+            k_element_forces<24><<<dim3(grid_for(n * 24, 96), gy), 96, 0, st>>>(
                 n, list, m.quad_ijmn.ptr, ev + c->ev_off_quad, D_dev, ferc ? ferc + c->ef_off_quad : nullptr, ld.n_case, fac,
-                c->ef_count, nullptr, 0, out_dev);
+                c->ef_count, nullptr, 0, out_dev, d_stride, out_stride);
             c->count_launch();
         }
         break;
@@ -473,9 +483,9 @@ void launch_element_forces(Ctx *c, int kind, const double *D_dev, int32_t combo,
     case PN_PLATE: {
         int64_t n = supported_only ? c->sup_list[k].n : m.n_plates;
         if (n) {
-            k_element_forces<24><<<grid_for(n * 24, 96), 96, 0, st>>>(
+            k_element_forces<24><<<dim3(grid_for(n * 24, 96), gy), 96, 0, st>>>(
                 n, list, m.plate_ijmn.ptr, ev + c->ev_off_plate, D_dev, ferc ? ferc + c->ef_off_plate : nullptr, ld.n_case, fac,
-                c->ef_count, nullptr, 0, out_dev);
+                c->ef_count, nullptr, 0, out_dev, d_stride, out_stride);
             c->count_launch();
         }
         break;

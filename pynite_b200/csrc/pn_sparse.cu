@@ -730,13 +730,20 @@ void merge_displacements(Ctx *c, int32_t combo0, int s) {
 // ------------------------------------------------------------------------------------------------
 // reactions (Analysis._calc_reactions :1059-1313)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_reactions(int64_t n_dof, int n_case, const uint8_t *__restrict__ support,
+// thread = (row i, combination blockIdx.y of the batch); rows = null: every DOF (i = d), else the listed DOFs
+__global__ void k_reactions(int64_t n_rows, const int32_t *__restrict__ rows, int64_t n_dof, int n_case,
+                            const uint8_t *__restrict__ support,
                             const uint32_t *__restrict__ inc_start, const uint32_t *__restrict__ inc_src,
-                            const double *__restrict__ ef, const double *__restrict__ fac_row,
+                            const double *__restrict__ ef, int64_t ef_stride, const double *__restrict__ fac_row,
                             const double *__restrict__ Pcase, const uint8_t *__restrict__ nsp_flag,
                             const double *__restrict__ nsp_k, const double *__restrict__ D, double *__restrict__ R) {
-    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (d >= n_dof) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t d = rows ? rows[i] : i;
+    ef += blockIdx.y * ef_stride;
+    fac_row += blockIdx.y * (int64_t)n_case;
+    D += blockIdx.y * n_dof;
+    R += blockIdx.y * n_rows;
     uint8_t sup = support[d / 6];
     double r = 0.0;
     if ((sup >> (d % 6)) & 1u) {
@@ -747,7 +754,7 @@ __global__ void k_reactions(int64_t n_dof, int n_case, const uint8_t *__restrict
     }
     uint8_t f = nsp_flag[d];
     if ((f & 1u) && (f & 2u)) r -= nsp_k[d] * D[d];
-    R[d] = r;
+    R[i] = r;
 }
 
 void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev) {
@@ -762,11 +769,44 @@ void compute_reactions(Ctx *c, int32_t combo, bool pdelta, double *rxn_dev) {
     launch_element_forces(c, PN_PLATE, D, combo, true, c->ef.ptr + c->ef_off_plate, st);
     if (c->n_dof) {
         ProfScope ps_(c, PS_REACTIONS);
-        k_reactions<<<grid_for(c->n_dof, 256), 256, 0, st>>>(c->n_dof, ld.n_case, m.support.ptr, c->inc_start.ptr,
-                                                              c->inc_src.ptr, c->ef.ptr,
+        k_reactions<<<grid_for(c->n_dof, 256), 256, 0, st>>>(c->n_dof, nullptr, c->n_dof, ld.n_case, m.support.ptr, c->inc_start.ptr,
+                                                              c->inc_src.ptr, c->ef.ptr, 0,
                                                               ld.factors.ptr + (int64_t)combo * ld.n_case, ld.Pcase.ptr,
                                                               m.nspring_flag.ptr, m.nspring_k.ptr, D, rxn_dev);
         c->count_launch();
+    }
+}
+
+void compute_reactions_batch(Ctx *c, int32_t combo0, int n_batch, bool pdelta, const int32_t *rows_dev, int64_t n_rows,
+                             double *out_dev) {
+    if (n_batch <= 0 || !c->n_dof) return;
+    cudaStream_t st = c->stream;
+    Loads &ld = c->loads;
+    const Model &m = c->model;
+    const int64_t nr = rows_dev ? n_rows : c->n_dof;
+    // element end forces of up to `chunk` combinations at a time (<= 2 GB of scratch)
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(n_batch, (int64_t)(2.0e9 / (8.0 * (double)std::max<int64_t>(c->ef_count, 1)))));
+    c->ef_batch.resize((int64_t)chunk * c->ef_count);
+    for (int j0 = 0; j0 < n_batch; j0 += chunk) {
+        const int nb = std::min(chunk, n_batch - j0);
+        const int32_t combo = combo0 + j0;
+        const double *D = c->D_all.ptr + (int64_t)combo * c->n_dof;
+        double *ef = c->ef_batch.ptr;
+        launch_element_forces(c, PN_SPRING, D, combo, true, ef + c->ef_off_spring, st, nb, c->ef_count);
+        launch_element_forces(c, PN_MEMBER, D, combo, true, ef + c->ef_off_member, st, nb, c->ef_count);
+        if (pdelta)
+            for (int j = 0; j < nb; ++j)
+                launch_member_pdelta_forces(c, D + (int64_t)j * c->n_dof, true, ef + (int64_t)j * c->ef_count + c->ef_off_member, st);
+        launch_element_forces(c, PN_QUAD, D, combo, true, ef + c->ef_off_quad, st, nb, c->ef_count);
+        launch_element_forces(c, PN_PLATE, D, combo, true, ef + c->ef_off_plate, st, nb, c->ef_count);
+        if (nr) {
+            ProfScope ps_(c, PS_REACTIONS);
+            k_reactions<<<dim3(grid_for(nr, 256), nb), 256, 0, st>>>(nr, rows_dev, c->n_dof, ld.n_case, m.support.ptr, c->inc_start.ptr,
+                                                                     c->inc_src.ptr, ef, c->ef_count,
+                                                                     ld.factors.ptr + (int64_t)combo * ld.n_case, ld.Pcase.ptr,
+                                                                     m.nspring_flag.ptr, m.nspring_k.ptr, D, out_dev + (int64_t)j0 * nr);
+            c->count_launch();
+        }
     }
 }
 

@@ -192,6 +192,11 @@ class Engine:
         self._h = h
         self.device = device
         self._keep = []          # arrays whose memory must outlive a call
+        # one process per GPU (torchrun): the ranks of a box share its cores, and torchrun pins OMP_NUM_THREADS to 1, which
+        # would leave the ordering of the direct solver single-threaded.  Give every rank its share, less the caller's thread.
+        local_world = int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1)
+        if local_world > 1:
+            self.set_option('host_threads', max(1, (os.cpu_count() or 1)//local_world - 1))
 
     def close(self):
         if getattr(self, '_h', None):
