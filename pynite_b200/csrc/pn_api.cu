@@ -353,14 +353,16 @@ void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
 }
 
 // D_out != null: the displacements of a finished batch are copied to the host on the second stream while the next batch
-// is solved (774 MB take ~30 ms over PCIe for config 3: with two batches half of that hides behind the second solve; the
-// factorisation is done once, see DirectSolver::factor_epoch).
+// is solved (the factorisation is done once, see DirectSolver::factor_epoch).  PN_DOWNLOAD_OVERLAP=1 additionally cuts a
+// single batch of >= 32 combinations in two so that half of the copy hides behind the second solve.  Measured on config 3
+// (774 MB = 13.5 ms at 57 GB/s): two solves of 32 columns cost 38 ms against 31 ms for one of 64, which is more than the
+// 7 ms of copy they hide (e2e 146.4 ms split, 143.0 ms unsplit), so it is off by default.
 void solve_linear_all(Ctx *c, const pn_solve_opts &o, double *D_out = nullptr) {
     int nc = c->loads.n_combo;
     c->D_all.resize((int64_t)nc * c->n_dof);
     int bs = batch_size(c, nc);
-    static const bool no_split = getenv("PN_NO_DOWNLOAD_OVERLAP") != nullptr;
-    if (D_out && !no_split && nc >= 32 && bs >= nc && o.solver == PN_SOLVER_DIRECT) bs = (nc + 1) / 2;
+    static const bool split = getenv("PN_DOWNLOAD_OVERLAP") != nullptr;
+    if (D_out && split && nc >= 32 && bs >= nc && o.solver == PN_SOLVER_DIRECT) bs = (nc + 1) / 2;
     for (int j0 = 0; j0 < nc; j0 += bs) {
         int s = std::min(bs, nc - j0);
         {
@@ -1377,7 +1379,7 @@ int pn_reset_stats(pn_ctx *ctx) {
 static const char *kCounterNames[PC_COUNT] = {
     "lu_update", "lu_update_later_groups", "lu_strip", "split_levels", "sweep_smem", "sweep_ll", "sweep_step",
     "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches", "pdelta_fallback_columns",
-    "factor_fused_levels", "dist_exchanges", "dist_cut_level"};
+    "factor_fused_levels", "dist_exchanges", "dist_cut_level", "sweep_overlapped"};
 
 const char *pn_counter_name(int index) { return (index >= 0 && index < PC_COUNT) ? kCounterNames[index] : nullptr; }
 

@@ -142,7 +142,13 @@ struct DirectSolver {
     cudaStream_t fstream[4] = {nullptr, nullptr, nullptr, nullptr};   // factorisation: chains of front groups side by side
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int n_fstreams = 0, split_max_fronts = 1 << 30;
+    // forward sweep of the first solve running one level behind the factorisation on its own (low-priority) stream
+    cudaStream_t sstream = nullptr;
+    cudaEvent_t ev_level[64] = {}, ev_sweep = nullptr;
     ~DirectSolver() {
+        if (sstream) cudaStreamDestroy(sstream);
+        for (int q = 0; q < 64; ++q) if (ev_level[q]) cudaEventDestroy(ev_level[q]);
+        if (ev_sweep) cudaEventDestroy(ev_sweep);
         for (int q = 0; q < 4; ++q) {
             if (fstream[q]) cudaStreamDestroy(fstream[q]);
             if (ev_join[q]) cudaEventDestroy(ev_join[q]);
@@ -2050,7 +2056,7 @@ static void exchange_update_matrices(Ctx *c, int sym) {
     }
 }
 
-static void factorise(Ctx *c, const double *vals11) {
+static void factorise(Ctx *c, const double *vals11, const std::function<void(int)> *level_done = nullptr) {
     DirectSolver &d = *c->direct;
     cudaStream_t st = c->stream;
     // K is symmetric up to rounding unless a shell has kx_mod != ky_mod: then only the lower triangle of every front
@@ -2077,7 +2083,7 @@ static void factorise(Ctx *c, const double *vals11) {
         // subtree-to-GPU: below and on the cut level only this rank's subtrees, above it every front (replicated)
         int first = DP.active ? DP.lo[l] : d.level_ptr[l], nfl = (DP.active ? DP.hi[l] : d.level_ptr[l + 1]) - first;
         if (DP.active && l == DP.cut + 1) exchange_update_matrices(c, sym);
-        if (!nfl) continue;
+        if (!nfl) { if (level_done) (*level_done)(l); continue; }
         double *arena = d.arena[l & 1].ptr;
         if (debug_levels) cudaEventRecord(dbg0, st);
         lp.begin(0);
@@ -2172,6 +2178,7 @@ static void factorise(Ctx *c, const double *vals11) {
                 fprintf(stderr, "[pn] level %2d: %6d fronts, max ns %5d, max n %5d, arena %8.1f MB, %8.3f ms (fused per-front kernel)\n", l, nfl,
                         d.level_max_ns[l], d.level_max_n[l], d.level_f_total[l] * 8e-6, ms);
             }
+            if (level_done) (*level_done)(l);
             continue;
         }
         int nsplit = 1;
@@ -2218,6 +2225,7 @@ static void factorise(Ctx *c, const double *vals11) {
                     l, nfl, maxns, maxn, d.level_f_total[l] * 8e-6, ms, fl * 1e-9, fl / (ms * 1e-3) * 1e-12);
             lp.report(l);
         }
+        if (level_done) (*level_done)(l);
     }
     if (debug_levels) { cudaEventDestroy(dbg0); cudaEventDestroy(dbg1); }
     if (dbg_clk) cudaFree(dbg_clk);
@@ -2277,14 +2285,13 @@ static void exchange_solved_rows(Ctx *c, double *X, int s) {
     }
 }
 
-// solves in place: X holds the right-hand sides on entry ([n1][s] row-major)
-static void solve_inplace(Ctx *c, double *X, int s) {
+// workspaces and the per-s copy of the front table (workspace offsets were stored per unit column)
+static void solve_prepare(Ctx *c, int s) {
     DirectSolver &d = *c->direct;
     cudaStream_t st = c->stream;
     int64_t wmax = 0;
     for (int l = 0; l < d.n_levels; ++l) wmax = std::max(wmax, d.level_n_total[l]);
     d.warena[0].resize(wmax * s); d.warena[1].resize(wmax * s); d.yarena.resize(wmax * s);
-    // workspace offsets were stored per unit column; scale once per s
     if (d.fronts_s != s) {
         std::vector<FrontDev> hf = d.h_fronts;
         for (auto &F : hf) F.w_off *= s;
@@ -2292,6 +2299,85 @@ static void solve_inplace(Ctx *c, double *X, int s) {
         PN_CUDA(cudaStreamSynchronize(st));
         d.fronts_s = s;
     }
+}
+
+// forward sweep of level l on stream st (the caller has run solve_prepare and, subtree-to-GPU, the exchange before the
+// first replicated level)
+static void solve_forward_level(Ctx *c, double *X, int s, int l, cudaStream_t st) {
+    DirectSolver &d = *c->direct;
+    const FrontDev *fr = d.fronts_scaled.ptr;
+    double *Y = d.yarena.ptr;
+    const int gz = (s + BN - 1) / BN;
+    // (read on every call: the parity tests switch kernel families inside one process)
+    const bool no_sm_sweeps = getenv("PN_NO_SMEM_SWEEPS") != nullptr;
+    const bool no_ll_sweeps = getenv("PN_NO_LL_SWEEPS") != nullptr;
+    const bool use_ll = !no_ll_sweeps && s <= 32 * LL_MAX_CHUNKS;
+    const DistPlan &DP = d.dist;
+    int first = DP.active ? DP.lo[l] : d.level_ptr[l], nfl = (DP.active ? DP.hi[l] : d.level_ptr[l + 1]) - first;
+    if (!nfl) return;
+    double *W = d.warena[l & 1].ptr;
+    int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
+    size_t sw_smem = 0;
+    const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
+    if (cw) {
+        ProfScope ps_(c, PS_SOLVE_FUSED);
+        const int H = (s + cw - 1) / cw;
+        const unsigned grid = (unsigned)nfl * (unsigned)H;
+#define PN_FWD(CW_) k_front_forward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, \
+                                                                d.L.ptr, d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr)
+        if (cw == 32) PN_FWD(32); else if (cw == 16) PN_FWD(16); else PN_FWD(8);
+#undef PN_FWD
+        c->count_launch();
+        c->ctr[PC_SWEEP_SMEM]++;
+        return;
+    }
+    if (!use_ll && nfl >= FUSED_SOLVE_MIN_FRONTS) {     // fallback for more than 256 right-hand sides
+        ProfScope ps_(c, PS_SOLVE_FUSED);
+        k_front_forward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, d.L.ptr,
+                                                       d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr, Y);
+        c->count_launch();
+        return;
+    }
+    unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
+    { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr, d.fidx.ptr, X, W); }
+    c->count_launch();
+    if (l > 0) {
+        const bool own_children = DP.active && l <= DP.cut;
+        int cfirst = own_children ? DP.lo[l - 1] : d.level_ptr[l - 1], ncl = (own_children ? DP.hi[l - 1] : d.level_ptr[l]) - cfirst;
+        unsigned gyc = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)d.level_max_nb[l - 1] * s + 255) / 256, 1), 1024);
+        for (int r = 0; r < d.level_max_children[l - 1] && ncl > 0; ++r) {
+            { ProfScope ps_(c, PS_SOLVE_MISC); k_solve_extend_add<<<dim3(ncl, gyc), 256, 0, st>>>(cfirst, ncl, r, s, fr, d.rel.ptr,
+                                                                d.warena[(l - 1) & 1].ptr, W); }
+            c->count_launch();
+        }
+    }
+    if (use_ll) {
+        const int H = (s + 31) / 32, T = (maxns + NB - 1) / NB + (d.level_max_nb[l] + NB - 1) / NB;
+        const int units = T * nfl * H;
+        ProfScope ps_(c, PS_SOLVE_UPDATE);
+        k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 0, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
+                                                              d.ll_flags.ptr, ++d.ll_epoch);
+        c->count_launch();
+        c->ctr[PC_SWEEP_LL]++;
+    } else
+    for (int kb = 0; kb < maxns; kb += NB) {
+        int rest = std::max(maxn - kb - 1, 0);
+        int tiles = 1 + (rest + BM - 1) / BM;
+        { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_step<<<dim3(nfl, tiles, gz), 256, GEMM_SMEM, st>>>(first, kb, s, 0, fr, d.L.ptr, d.inv.ptr, W, Y); }
+        c->count_launch();
+        c->ctr[PC_SWEEP_STEP]++;
+    }
+    unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
+    { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
+    c->count_launch();
+}
+
+// solves in place: X holds the right-hand sides on entry ([n1][s] row-major).  forward_done: the forward sweep has
+// already been issued (direct_solve runs it behind the factorisation).
+static void solve_inplace(Ctx *c, double *X, int s, bool forward_done = false) {
+    DirectSolver &d = *c->direct;
+    cudaStream_t st = c->stream;
+    solve_prepare(c, s);
     const FrontDev *fr = d.fronts_scaled.ptr;
     double *Y = d.yarena.ptr;
     int gz = (s + BN - 1) / BN;
@@ -2305,65 +2391,10 @@ static void solve_inplace(Ctx *c, double *X, int s) {
     const DistPlan &DP = d.dist;
     // forward sweep (subtree-to-GPU: own subtrees up to the cut level, then every front)
     for (int l = 0; l < d.n_levels; ++l) {
-        int first = DP.active ? DP.lo[l] : d.level_ptr[l], nfl = (DP.active ? DP.hi[l] : d.level_ptr[l + 1]) - first;
         if (debug_levels && l < 31) cudaEventRecord(dbg[l], st);
+        if (forward_done) continue;
         if (DP.active && l == DP.cut + 1) exchange_update_vectors(c, s, fr);
-        if (!nfl) continue;
-        double *W = d.warena[l & 1].ptr;
-        int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
-        size_t sw_smem = 0;
-        const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
-        if (cw) {
-            ProfScope ps_(c, PS_SOLVE_FUSED);
-            const int H = (s + cw - 1) / cw;
-            const unsigned grid = (unsigned)nfl * (unsigned)H;
-#define PN_FWD(CW_) k_front_forward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, \
-                                                                    d.L.ptr, d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr)
-            if (cw == 32) PN_FWD(32); else if (cw == 16) PN_FWD(16); else PN_FWD(8);
-#undef PN_FWD
-            c->count_launch();
-            c->ctr[PC_SWEEP_SMEM]++;
-            continue;
-        }
-        if (!use_ll && nfl >= FUSED_SOLVE_MIN_FRONTS) {     // fallback for more than 256 right-hand sides
-            ProfScope ps_(c, PS_SOLVE_FUSED);
-            k_front_forward<<<nfl, 256, GEMM_SMEM, st>>>(first, s, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, d.L.ptr,
-                                                           d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr, Y);
-            c->count_launch();
-            continue;
-        }
-        unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxn * s + 255) / 256, 1), 1024);
-        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_gather<<<dim3(nfl, gy), 256, 0, st>>>(first, s, 0, fr, d.fidx.ptr, X, W); }
-        c->count_launch();
-        if (l > 0) {
-            const bool own_children = DP.active && l <= DP.cut;
-            int cfirst = own_children ? DP.lo[l - 1] : d.level_ptr[l - 1], ncl = (own_children ? DP.hi[l - 1] : d.level_ptr[l]) - cfirst;
-            unsigned gyc = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)d.level_max_nb[l - 1] * s + 255) / 256, 1), 1024);
-            for (int r = 0; r < d.level_max_children[l - 1] && ncl > 0; ++r) {
-                { ProfScope ps_(c, PS_SOLVE_MISC); k_solve_extend_add<<<dim3(ncl, gyc), 256, 0, st>>>(cfirst, ncl, r, s, fr, d.rel.ptr,
-                                                                    d.warena[(l - 1) & 1].ptr, W); }
-                c->count_launch();
-            }
-        }
-        if (use_ll) {
-            const int H = (s + 31) / 32, T = (maxns + NB - 1) / NB + (d.level_max_nb[l] + NB - 1) / NB;
-            const int units = T * nfl * H;
-            ProfScope ps_(c, PS_SOLVE_UPDATE);
-            k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 0, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
-                                                                  d.ll_flags.ptr, ++d.ll_epoch);
-            c->count_launch();
-            c->ctr[PC_SWEEP_LL]++;
-        } else
-        for (int kb = 0; kb < maxns; kb += NB) {
-            int rest = std::max(maxn - kb - 1, 0);
-            int tiles = 1 + (rest + BM - 1) / BM;
-            { ProfScope ps_(c, PS_SOLVE_UPDATE); k_solve_step<<<dim3(nfl, tiles, gz), 256, GEMM_SMEM, st>>>(first, kb, s, 0, fr, d.L.ptr, d.inv.ptr, W, Y); }
-            c->count_launch();
-            c->ctr[PC_SWEEP_STEP]++;
-        }
-        unsigned gys = (unsigned)std::min<int64_t>(std::max<int64_t>(((int64_t)maxns * s + 255) / 256, 1), 1024);
-        { ProfScope ps_(c, PS_SOLVE_GATHER); k_solve_store<<<dim3(nfl, gys), 256, 0, st>>>(first, s, fr, d.fidx.ptr, Y, X); }
-        c->count_launch();
+        solve_forward_level(c, X, s, l, st);
     }
     if (debug_levels) cudaEventRecord(dbg[31], st);
     // backward sweep
@@ -2615,16 +2646,52 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
     DevBuf<double> &R = c->work_r;
     if (!percol) {
         // one factorisation per assembled matrix: later batches of right-hand sides reuse it
+        bool forward_done = false;
         if (!(d.shared_factor && d.factor_epoch == c->assembly_epoch && d.factor_vals == vals11)) {
             d.shared_factor = false;
-            { PhaseTimer tm(c, &c->stats.ms_factor); factorise(c, vals11); }
+            // The forward sweep of level l needs the factor of levels <= l only, and the top of the tree is factorised
+            // by latency-bound chains of block steps (root separator: one front, 47 dependent steps).  PN_SWEEP_OVERLAP=1
+            // runs the first forward sweep one level behind the factorisation on its own low-priority stream.
+            // Measured on config 3 (profiles/r2_dropped_experiments.md): factor 54.9 -> 61.0 ms, solve 31.3 -> 24.3 ms,
+            // step 90.0 -> 89.6 ms -- the persistent sweep kernels hold the SM slots the block-step chain needs, so the
+            // chain is delayed by as much as the sweep saves.  Off by default.
+            static const bool want_overlap = getenv("PN_SWEEP_OVERLAP") != nullptr, debug_levels = getenv("PN_DEBUG_LEVELS") != nullptr;
+            const bool overlap = want_overlap && !debug_levels && !d.dist.active && !c->prof.on && d.n_levels <= 64 && d.n_levels >= 3;
+            PhaseTimer tm(c, &c->stats.ms_factor);
+            if (overlap) {
+                if (!d.sstream) {
+                    int lo = 0, hi = 0;
+                    cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = numerically largest = lowest priority
+                    PN_CUDA(cudaStreamCreateWithPriority(&d.sstream, cudaStreamNonBlocking, lo));
+                    PN_CUDA(cudaEventCreateWithFlags(&d.ev_sweep, cudaEventDisableTiming));
+                }
+                solve_prepare(c, s);
+                PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * n1 * s, cudaMemcpyDeviceToDevice, st));
+                double *Xp = c->X.ptr;
+                std::function<void(int)> hook = [&, Xp](int l) {
+                    if (!d.ev_level[l]) PN_CUDA(cudaEventCreateWithFlags(&d.ev_level[l], cudaEventDisableTiming));
+                    PN_CUDA(cudaEventRecord(d.ev_level[l], st));
+                    PN_CUDA(cudaStreamWaitEvent(d.sstream, d.ev_level[l], 0));
+                    solve_forward_level(c, Xp, s, l, d.sstream);
+                };
+                // (a singular matrix throws out of factorise after the sweeps were queued: they run on garbage and
+                // are harmless; the stream is drained before anything else uses the workspaces)
+                try { factorise(c, vals11, &hook); }
+                catch (...) { cudaStreamSynchronize(d.sstream); throw; }
+                PN_CUDA(cudaEventRecord(d.ev_sweep, d.sstream));
+                PN_CUDA(cudaStreamWaitEvent(st, d.ev_sweep, 0));
+                forward_done = true;
+                c->ctr[PC_SWEEP_OVERLAPPED]++;
+            } else {
+                factorise(c, vals11);
+            }
             d.factor_epoch = c->assembly_epoch;
             d.factor_vals = vals11;
         }
         d.shared_factor = true;
         PhaseTimer tm(c, &c->stats.ms_solve);
-        PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * n1 * s, cudaMemcpyDeviceToDevice, st));
-        solve_inplace(c, c->X.ptr, s);
+        if (!forward_done) PN_CUDA(cudaMemcpyAsync(c->X.ptr, c->B.ptr, sizeof(double) * n1 * s, cudaMemcpyDeviceToDevice, st));
+        solve_inplace(c, c->X.ptr, s, forward_done);
         if (refine > 0) R.resize(n1 * s);
         // Iterative refinement with a double-double residual: each correction d shrinks the forward error by
         // rho ~ cond(K11) * 2^-53.  rho is estimated per column as |d| / |x| of the first correction; refinement

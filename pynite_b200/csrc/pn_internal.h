@@ -173,6 +173,7 @@ enum PathCounter {
     PC_FACTOR_FUSED,       // levels factorised by the one-CTA-per-front kernel
     PC_DIST_EXCHANGES,     // all-gathers of the subtree-to-GPU solve (update matrices, update vectors, solved rows)
     PC_DIST_CUT_LEVEL,     // level of the subtree roots (-1: not distributed)
+    PC_SWEEP_OVERLAPPED,   // factorisations whose first forward sweep ran behind them on the side stream
     PC_COUNT
 };
 
