@@ -141,6 +141,9 @@ struct DirectSolver {
     DevBuf<double> col_in, col_out;           // per-column solves (P-Delta)
     cudaStream_t fstream[4] = {nullptr, nullptr, nullptr, nullptr};   // factorisation: chains of front groups side by side
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    // look-ahead: the part of a group's trailing update that the next group does not need runs on its own stream
+    cudaStream_t ustream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_prio[4] = {nullptr, nullptr, nullptr, nullptr}, ev_rem[4] = {nullptr, nullptr, nullptr, nullptr};
     int n_fstreams = 0, split_max_fronts = 1 << 30;
     // forward sweep of the first solve running one level behind the factorisation on its own (low-priority) stream
     cudaStream_t sstream = nullptr;
@@ -151,7 +154,10 @@ struct DirectSolver {
         if (ev_sweep) cudaEventDestroy(ev_sweep);
         for (int q = 0; q < 4; ++q) {
             if (fstream[q]) cudaStreamDestroy(fstream[q]);
+            if (ustream[q]) cudaStreamDestroy(ustream[q]);
             if (ev_join[q]) cudaEventDestroy(ev_join[q]);
+            if (ev_prio[q]) cudaEventDestroy(ev_prio[q]);
+            if (ev_rem[q]) cudaEventDestroy(ev_rem[q]);
         }
         if (ev_fork) cudaEventDestroy(ev_fork);
     }
@@ -965,10 +971,11 @@ k_lu_strip(int first, int kb, int g0, const FrontDev *__restrict__ fronts, doubl
 
 // trailing update after group [g0, ge): F[ge:, ge:] -= L[ge:, g0:ge] U[g0:ge, ge:]   (rank ge - g0 <= GB)
 __global__ void __launch_bounds__(256, 2)
-k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym, int front_on_x) {
+k_lu_update(int first, int g0, const FrontDev *__restrict__ fronts, double *__restrict__ arena, int sym, int front_on_x, int tn0) {
     // front slowest (grid z) when the level has at most 65535 fronts: the CTAs of one front run together and its
-    // panels stay in L2; otherwise the front index needs the x dimension
-    const int tcol = front_on_x ? blockIdx.z : blockIdx.x;
+    // panels stay in L2; otherwise the front index needs the x dimension.  tn0 = first column tile of this launch
+    // (look-ahead: the next group's columns and the remainder are separate launches).
+    const int tcol = tn0 + (front_on_x ? blockIdx.z : blockIdx.x);
     FrontDev F = fronts[first + (front_on_x ? blockIdx.x : blockIdx.z)];
     if (g0 >= F.ns) return;
     const int ge = min(g0 + GB, F.ns);
@@ -1801,9 +1808,20 @@ static void analyse(Ctx *c) {
         int ns_ = 4;
         if (const char *e = getenv("PN_FACTOR_STREAMS")) ns_ = std::min(4, std::max(1, atoi(e)));
         if (const char *e = getenv("PN_FACTOR_SPLIT_MAX")) d.split_max_fronts = std::max(0, atoi(e));
+        // the chains of block steps are latency-bound: their CTAs go first whenever SM slots free up; the remainder updates
+        // of the look-ahead schedule are throughput work and take what is left
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // hi = numerically smallest = most urgent
+        static const bool flat_prio = getenv("PN_FLAT_STREAM_PRIORITY") != nullptr;
+        if (flat_prio) prio_lo = prio_hi = 0;
         for (int q = 0; q < ns_; ++q) {
-            PN_CUDA(cudaStreamCreateWithFlags(&d.fstream[q], cudaStreamNonBlocking));
+            PN_CUDA(cudaStreamCreateWithPriority(&d.fstream[q], cudaStreamNonBlocking, prio_hi));
             PN_CUDA(cudaEventCreateWithFlags(&d.ev_join[q], cudaEventDisableTiming));
+        }
+        for (int q = 0; q < 4; ++q) {
+            PN_CUDA(cudaStreamCreateWithPriority(&d.ustream[q], cudaStreamNonBlocking, prio_lo));
+            PN_CUDA(cudaEventCreateWithFlags(&d.ev_prio[q], cudaEventDisableTiming));
+            PN_CUDA(cudaEventCreateWithFlags(&d.ev_rem[q], cudaEventDisableTiming));
         }
         PN_CUDA(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
         d.n_fstreams = ns_;
@@ -2118,7 +2136,18 @@ static void factorise(Ctx *c, const double *vals11, const std::function<void(int
         // The block-step chain (diag -> panels -> strip per 64 pivots) of a level with few fronts keeps only a handful of
         // CTAs busy, while the rank-256 updates are throughput work: such levels are cut into up to four groups of
         // fronts whose chains run on separate streams, so that one group's chain overlaps the others' updates.
-        auto run_steps = [&](int f0_, int nf_, cudaStream_t sq) {
+        // Look-ahead (symmetric mode, few fronts, more than one pivot group): only the next group's 256 columns of the
+        // trailing update sit on the chain of block steps; the remainder (columns further right) runs on a second stream
+        // while the next group's diag -> panels -> strip chain proceeds.  Every entry still receives its updates in
+        // group order (the remainder stream is in order, and the next priority update waits for the previous remainder),
+        // so the factor is bit-identical to the serial schedule.
+        static const bool no_lookahead = getenv("PN_NO_LOOKAHEAD") != nullptr;
+        static const int la_max_fronts = getenv("PN_LOOKAHEAD_MAX_FRONTS") ? atoi(getenv("PN_LOOKAHEAD_MAX_FRONTS")) : 16;
+        auto run_steps = [&](int f0_, int nf_, cudaStream_t sq, int lane) {
+            const bool la = sym && !no_lookahead && !lp.on && !c->prof.on && maxns > GB && nf_ <= la_max_fronts;
+            cudaStream_t su = d.ustream[lane];
+            bool rem_pending = false;
+            if (la) c->ctr[PC_LOOKAHEAD]++;
             for (int g0 = 0; g0 < maxns; g0 += GB) {
                 int gend = std::min(g0 + GB, maxns);
                 for (int kb = g0; kb < gend; kb += NB) {
@@ -2156,14 +2185,29 @@ static void factorise(Ctx *c, const double *vals11, const std::function<void(int
                 int rest = maxn - g0 - 1;
                 if (rest > 0) {
                     int tiles_u = (rest + BN - 1) / BN, tiles_l = (rest + BM - 1) / BM;
-                    lp.begin(6);
-                    { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<nf_ <= 65535 ? dim3(tiles_u, tiles_l, nf_) : dim3(nf_, tiles_l, tiles_u), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym, nf_ <= 65535 ? 0 : 1); }
-                    lp.end();
-                    c->count_launch();
+                    const int prio = GB / BN;          // column tiles of the next group
+                    if (la && gend < maxns && tiles_u > prio) {
+                        // (the previous group's remainder wrote the columns this priority update continues on)
+                        if (rem_pending) PN_CUDA(cudaStreamWaitEvent(sq, d.ev_rem[lane], 0));
+                        k_lu_update<<<dim3(prio, tiles_l, nf_), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym, 0, 0);
+                        PN_CUDA(cudaEventRecord(d.ev_prio[lane], sq));
+                        PN_CUDA(cudaStreamWaitEvent(su, d.ev_prio[lane], 0));
+                        k_lu_update<<<dim3(tiles_u - prio, tiles_l, nf_), 256, GEMM_SMEM, su>>>(f0_, g0, d.fronts.ptr, arena, sym, 0, prio);
+                        PN_CUDA(cudaEventRecord(d.ev_rem[lane], su));
+                        rem_pending = true;
+                        c->count_launch(2);
+                    } else {
+                        if (rem_pending) { PN_CUDA(cudaStreamWaitEvent(sq, d.ev_rem[lane], 0)); rem_pending = false; }
+                        lp.begin(6);
+                        { ProfScope ps_(c, PS_LU_UPDATE, sq); k_lu_update<<<nf_ <= 65535 ? dim3(tiles_u, tiles_l, nf_) : dim3(nf_, tiles_l, tiles_u), 256, GEMM_SMEM, sq>>>(f0_, g0, d.fronts.ptr, arena, sym, nf_ <= 65535 ? 0 : 1, 0); }
+                        lp.end();
+                        c->count_launch();
+                    }
                     c->ctr[PC_LU_UPDATE]++;
                     if (g0 > 0) c->ctr[PC_LU_UPDATE_LATER]++;
                 }
             }
+            if (rem_pending) PN_CUDA(cudaStreamWaitEvent(sq, d.ev_rem[lane], 0));
         };
         // levels with many fronts: one CTA per front does all block steps (k_front_factor_fused)
         if (nfl >= fused_factor_min() && !lp.on) {
@@ -2185,14 +2229,14 @@ static void factorise(Ctx *c, const double *vals11, const std::function<void(int
         // (per-kernel profiling serialises the groups: overlapping kernels would be charged each other's time)
         if (!lp.on && !c->prof.on && nfl >= 2 && nfl <= d.split_max_fronts) nsplit = std::min(nfl, d.n_fstreams);
         if (nsplit == 1) {
-            run_steps(first, nfl, st);
+            run_steps(first, nfl, st, 0);
         } else {
             c->ctr[PC_SPLIT_LEVELS]++;
             PN_CUDA(cudaEventRecord(d.ev_fork, st));
             for (int q = 0; q < nsplit; ++q) {
                 int a = first + (int)((int64_t)nfl * q / nsplit), b = first + (int)((int64_t)nfl * (q + 1) / nsplit);
                 PN_CUDA(cudaStreamWaitEvent(d.fstream[q], d.ev_fork, 0));
-                run_steps(a, b - a, d.fstream[q]);
+                run_steps(a, b - a, d.fstream[q], q);
                 PN_CUDA(cudaEventRecord(d.ev_join[q], d.fstream[q]));
                 PN_CUDA(cudaStreamWaitEvent(st, d.ev_join[q], 0));
             }

@@ -174,6 +174,7 @@ enum PathCounter {
     PC_DIST_EXCHANGES,     // all-gathers of the subtree-to-GPU solve (update matrices, update vectors, solved rows)
     PC_DIST_CUT_LEVEL,     // level of the subtree roots (-1: not distributed)
     PC_SWEEP_OVERLAPPED,   // factorisations whose first forward sweep ran behind them on the side stream
+    PC_LOOKAHEAD,          // front groups factorised with the look-ahead schedule (trailing update split in two streams)
     PC_COUNT
 };
 

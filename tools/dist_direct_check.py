@@ -1,6 +1,6 @@
 """Multi-GPU check of the subtree-to-GPU direct solve (pn_set_distributed) over NCCL.  Launch with torchrun:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
-        tools/dist_direct_check.py [--n 160] [--combos 8]
+        tools/dist_direct_check.py [--mesh 160] [--combos 8]
 Every rank solves the model alone first, then distributed; the two must be bit-identical on every rank.  Prints the
 timing of both (device events) and the exchange counters."""
 import argparse
@@ -16,7 +16,7 @@ from pynite_b200 import distsolve, synthetic       # noqa: E402
 from pynite_b200.engine import Engine              # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--n', type=int, default=160)
+ap.add_argument('--mesh', dest='n', type=int, default=160)
 ap.add_argument('--combos', type=int, default=8)
 ap.add_argument('--steps', type=int, default=3)
 args = ap.parse_args()
