@@ -283,7 +283,7 @@ PN_EXPORT int pn_reset_stats(pn_ctx *ctx);
  * behind spsolve, Analysis.py:217).  Names: pn_counter_name(0..) until NULL -- "lu_update", "lu_update_later_groups"
  * (fronts with more than 256 pivots), "lu_strip", "split_levels" (front groups on side streams), "sweep_smem",
  * "sweep_ll", "sweep_step", "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches",
- * "pdelta_fallback_columns", "factor_fused_levels", "dist_exchanges", "dist_cut_level", "sweep_overlapped", "lookahead_groups".  The parity tests assert from these that a mid-size model exercises the
+ * "pdelta_fallback_columns", "factor_fused_levels", "dist_exchanges", "dist_cut_level", "sweep_overlapped", "lookahead_groups", "sweep_ll_gemm".  The parity tests assert from these that a mid-size model exercises the
  * kernels the full-size configurations run. */
 PN_EXPORT int pn_get_counter(pn_ctx *ctx, const char *name, int64_t *out);
 PN_EXPORT const char *pn_counter_name(int index);

@@ -1379,7 +1379,7 @@ int pn_reset_stats(pn_ctx *ctx) {
 static const char *kCounterNames[PC_COUNT] = {
     "lu_update", "lu_update_later_groups", "lu_strip", "split_levels", "sweep_smem", "sweep_ll", "sweep_step",
     "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches", "pdelta_fallback_columns",
-    "factor_fused_levels", "dist_exchanges", "dist_cut_level", "sweep_overlapped", "lookahead_groups"};
+    "factor_fused_levels", "dist_exchanges", "dist_cut_level", "sweep_overlapped", "lookahead_groups", "sweep_ll_gemm"};
 
 const char *pn_counter_name(int index) { return (index >= 0 && index < PC_COUNT) ? kCounterNames[index] : nullptr; }
 

@@ -1525,7 +1525,10 @@ __device__ __forceinline__ void frag_store_g(const double (&acc)[2][2][2], doubl
 __global__ void __launch_bounds__(256, 2)
 k_ll_sweep(int first, int nfl, int s, int H, int T, int backward, const FrontDev *__restrict__ fronts, const double *__restrict__ L,
            const double *__restrict__ U, const double *__restrict__ inv, double *W, double *__restrict__ Y, uint32_t *flags,
-           uint32_t epoch) {
+           uint32_t epoch, int pivots_only) {
+    // pivots_only: the boundary rows are handled by full-size GEMM tiles in separate launches -- forward: after this
+    // kernel (k_solve_forward_boundary), so only the pivot tiles are swept here; backward: before it (k_solve_boundary),
+    // so the U12 term is already in the workspace
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rg = warp >> 1, chh = warp & 1;             // 16-row group of the tile, 16-column half of the chunk
     const int per_t = nfl * H;
@@ -1534,7 +1537,7 @@ k_ll_sweep(int first, int nfl, int s, int H, int T, int backward, const FrontDev
         const FrontDev F = fronts[first + f];
         const int n = F.ns + F.nb, ntp = (F.ns + NB - 1) / NB, ntb = (F.nb + NB - 1) / NB;
         int t;
-        if (!backward) { t = tt; if (t >= ntp + ntb) continue; }
+        if (!backward) { t = tt; if (t >= ntp + ntb || (pivots_only && t >= ntp)) continue; }
         else { t = ntp - 1 - tt; if (t < 0) continue; }
         const bool piv = t < ntp;
         const int r0 = piv ? NB * t : F.ns + NB * (t - ntp);
@@ -1553,7 +1556,7 @@ k_ll_sweep(int first, int nfl, int s, int H, int T, int backward, const FrontDev
                 slab_mma_g(acc, Lrow + NB * k, F.ns, rv, min(NB, F.ns - NB * k), w + (int64_t)(NB * k) * s + c0, s, cv, lane, true);
             }
         } else {
-            if (F.nb) slab_mma_g(acc, U + F.u_off + (int64_t)wr * F.nb, F.nb, rv, F.nb, w + (int64_t)F.ns * s + c0, s, cv, lane, true);
+            if (F.nb && !pivots_only) slab_mma_g(acc, U + F.u_off + (int64_t)wr * F.nb, F.nb, rv, F.nb, w + (int64_t)F.ns * s + c0, s, cv, lane, true);
             for (int k = ntp - 1; k > t; --k) {
                 flag_wait(fl + LL_MAX_CHUNKS * k, epoch, lane);
                 slab_mma_g(acc, Lrow + NB * k, F.ns, rv, min(NB, F.ns - NB * k), w + (int64_t)(NB * k) * s + c0, s, cv, lane, true);
@@ -1597,6 +1600,16 @@ k_solve_boundary(int first, int s, const FrontDev *__restrict__ fronts, const do
     if (F.nb == 0 || (int)blockIdx.y * BM >= F.ns || (int)blockIdx.z * BN >= s) return;
     double *w = W + F.w_off;
     gemm_tile(U + F.u_off, F.nb, w + (int64_t)F.ns * s, s, w, s, F.ns, s, F.nb, blockIdx.y, blockIdx.z, 0);
+}
+
+// forward boundary update  W[ns:n] -= Lp[ns:n, 0:ns] W[0:ns]  (all pivot blocks of the front are final; the stored panels
+// are pre-multiplied, so the right-hand side is the accumulated, unsolved W[0:ns])
+__global__ void __launch_bounds__(256, 2)
+k_solve_forward_boundary(int first, int s, const FrontDev *__restrict__ fronts, const double *__restrict__ L, double *__restrict__ W) {
+    FrontDev F = fronts[first + blockIdx.x];
+    if (F.nb == 0 || (int)blockIdx.y * BM >= F.nb || (int)blockIdx.z * BN >= s) return;
+    double *w = W + F.w_off;
+    gemm_tile(L + F.l_off + (int64_t)F.ns * F.ns, F.ns, w, s, w + (int64_t)F.ns * s, s, F.nb, s, F.ns, blockIdx.y, blockIdx.z, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1796,6 +1809,7 @@ static void analyse(Ctx *c) {
         PN_CUDA(cudaFuncSetAttribute(k_front_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_solve_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_solve_forward_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
@@ -2329,6 +2343,16 @@ static void exchange_solved_rows(Ctx *c, double *X, int s) {
     }
 }
 
+// k_ll_sweep levels: boundary rows by gemm_tile launches (PN_LL_GEMM_BOUNDARY=0 restores the all-in-one sweep kernel)
+static bool ll_gemm_boundary() {
+    static const bool v = !(getenv("PN_LL_GEMM_BOUNDARY") && atoi(getenv("PN_LL_GEMM_BOUNDARY")) == 0);
+    return v;
+}
+static int ll_gemm_min_tiles() {
+    static const int v = getenv("PN_LL_GEMM_MIN_TILES") ? atoi(getenv("PN_LL_GEMM_MIN_TILES")) : 128;   // measured on config 3: below ~128 tiles of 128 x 64 the long-K tiles leave most SMs idle
+    return v;
+}
+
 // workspaces and the per-s copy of the front table (workspace offsets were stored per unit column)
 static void solve_prepare(Ctx *c, int s) {
     DirectSolver &d = *c->direct;
@@ -2396,13 +2420,23 @@ static void solve_forward_level(Ctx *c, double *X, int s, int l, cudaStream_t st
         }
     }
     if (use_ll) {
-        const int H = (s + 31) / 32, T = (maxns + NB - 1) / NB + (d.level_max_nb[l] + NB - 1) / NB;
+        // boundary rows as full 128 x 64 GEMM tiles (K = all pivots of the front) after the flag-synchronised sweep of the
+        // pivot tiles; the 16 x 16-per-warp tiles of k_ll_sweep are kept for the boundary only when the level has too few
+        // boundary tiles to fill the GPU with 128-row tiles
+        const int64_t gemm_tiles = (int64_t)nfl * ((d.level_max_nb[l] + BM - 1) / BM) * gz;
+        const bool split = ll_gemm_boundary() && d.level_max_nb[l] > 0 && gemm_tiles >= ll_gemm_min_tiles();
+        const int H = (s + 31) / 32, T = (maxns + NB - 1) / NB + (split ? 0 : (d.level_max_nb[l] + NB - 1) / NB);
         const int units = T * nfl * H;
         ProfScope ps_(c, PS_SOLVE_UPDATE);
         k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 0, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
-                                                              d.ll_flags.ptr, ++d.ll_epoch);
+                                                              d.ll_flags.ptr, ++d.ll_epoch, split ? 1 : 0);
         c->count_launch();
         c->ctr[PC_SWEEP_LL]++;
+        if (split) {
+            k_solve_forward_boundary<<<dim3(nfl, (d.level_max_nb[l] + BM - 1) / BM, gz), 256, GEMM_SMEM, st>>>(first, s, fr, d.L.ptr, W);
+            c->count_launch();
+            c->ctr[PC_SWEEP_LL_GEMM]++;
+        }
     } else
     for (int kb = 0; kb < maxns; kb += NB) {
         int rest = std::max(maxn - kb - 1, 0);
@@ -2473,9 +2507,16 @@ static void solve_inplace(Ctx *c, double *X, int s, bool forward_done = false) {
         if (use_ll) {
             const int H = (s + 31) / 32, T = (maxns + NB - 1) / NB;
             const int units = T * nfl * H;
+            const int64_t gemm_tiles = (int64_t)nfl * ((maxns + BM - 1) / BM) * gz;
+            const bool split = ll_gemm_boundary() && d.level_max_nb[l] > 0 && gemm_tiles >= ll_gemm_min_tiles();
             ProfScope ps_(c, PS_SOLVE_UPDATE);
+            if (split) {         // W[0:ns] -= U12 W[ns:n] as full GEMM tiles (K = nb), then the sweep of the pivot tiles
+                k_solve_boundary<<<dim3(nfl, (maxns + BM - 1) / BM, gz), 256, GEMM_SMEM, st>>>(first, s, fr, d.U.ptr, W);
+                c->count_launch();
+                c->ctr[PC_SWEEP_LL_GEMM]++;
+            }
             k_ll_sweep<<<std::min(units, d.ll_grid), 256, 0, st>>>(first, nfl, s, H, T, 1, fr, d.L.ptr, d.U.ptr, d.inv.ptr, W, Y,
-                                                                  d.ll_flags.ptr, ++d.ll_epoch);
+                                                                  d.ll_flags.ptr, ++d.ll_epoch, split ? 1 : 0);
             c->count_launch();
             c->ctr[PC_SWEEP_LL]++;
         } else {

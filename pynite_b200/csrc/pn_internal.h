@@ -175,6 +175,7 @@ enum PathCounter {
     PC_DIST_CUT_LEVEL,     // level of the subtree roots (-1: not distributed)
     PC_SWEEP_OVERLAPPED,   // factorisations whose first forward sweep ran behind them on the side stream
     PC_LOOKAHEAD,          // front groups factorised with the look-ahead schedule (trailing update split in two streams)
+    PC_SWEEP_LL_GEMM,      // boundary-row GEMM launches beside k_ll_sweep (k_solve_forward_boundary / k_solve_boundary)
     PC_COUNT
 };
 
