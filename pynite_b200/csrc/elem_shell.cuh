@@ -71,20 +71,21 @@ PN_HD void pn_quad_local_xy(const double p[4][3], double *xl, double *yl) {
     yl[3] = v14[0] * ya[0] + v14[1] * ya[1] + v14[2] * ya[2];
 }
 
-// Edge data for the DKMQ formulation (L_k :143, dir_cos :157, phi_k :179).
-PN_HD void pn_quad_edges(PnShellGeom &g, double t, double nu) {
+// Edge data for the DKMQ formulation (L_k :143, dir_cos :157, phi_k :179), one edge / all four.
+PN_HD void pn_quad_edge(PnShellGeom &g, int k, double t, double nu) {
     const double kappa = 5.0 / 6.0;
-    for (int k = 0; k < 4; ++k) {
-        int b = (k + 1) & 3;
-        double dx = g.xl[b] - g.xl[k], dy = g.yl[b] - g.yl[k];
-        double L = sqrt(dx * dx + dy * dy);
-        g.Lk[k] = L; g.Ck[k] = dx / L; g.Sk[k] = dy / L;
-        double r = t / L;
-        double phi = 2 / (kappa * (1 - nu)) * (r * r);
-        g.aD[k] = -1.5 * (1 / (1 + phi));
-        double ag = (k < 2) ? L / 2 : -L / 2;
-        g.gS[k] = ag * (phi / (1 + phi));
-    }
+    int b = (k + 1) & 3;
+    double dx = g.xl[b] - g.xl[k], dy = g.yl[b] - g.yl[k];
+    double L = sqrt(dx * dx + dy * dy);
+    g.Lk[k] = L; g.Ck[k] = dx / L; g.Sk[k] = dy / L;
+    double r = t / L;
+    double phi = 2 / (kappa * (1 - nu)) * (r * r);
+    g.aD[k] = -1.5 * (1 / (1 + phi));
+    double ag = (k < 2) ? L / 2 : -L / 2;
+    g.gS[k] = ag * (phi / (1 + phi));
+}
+PN_HD void pn_quad_edges(PnShellGeom &g, double t, double nu) {
+    for (int k = 0; k < 4; ++k) pn_quad_edge(g, k, t, nu);
 }
 
 // Jacobian of the bilinear map at (r, s): J = [[x_r, y_r], [x_s, y_s]] (Quad3D.J :276-286).

@@ -147,6 +147,7 @@ void compute_ev(Ctx *c) {
         PN_CUDA(cudaMemcpyAsync(c->ev.ptr, c->nsp_val.ptr, sizeof(double) * c->n_nsp, cudaMemcpyDeviceToDevice, c->stream));
     launch_element_ke(c, c->stream);
     c->ev_ready = true;
+    c->ev_assemblies = 0;
 }
 
 void ensure_ev(Ctx *c) { if (!c->ev_ready) compute_ev(c); }
@@ -182,7 +183,10 @@ void assemble(Ctx *c, bool refresh) {
         done = fast_assembly_run(c, c->vals.ptr);      // element classes + block gather: no COO value reaches HBM
     }
     if (!done) {
-        if (refresh) compute_ev(c);
+        // a re-assembly recomputes the element values, except when they were computed for this very model a moment
+        // ago (by the symbolic phase of the same analysis) and no assembly has consumed them yet
+        if (refresh && c->ev_assemblies > 0) compute_ev(c);
+        ++c->ev_assemblies;
         PhaseTimer tm(c, &c->stats.ms_scatter);
         scatter_add_values(c, c->ev.ptr, c->vals.ptr);
     }

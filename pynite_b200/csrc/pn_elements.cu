@@ -118,74 +118,115 @@ __global__ void k_member_fer_groups(int64_t n_groups, const int32_t *__restrict_
 // ------------------------------------------------------------------------------------------------
 constexpr int SHELL_TPB = 128;               // 8 elements per block
 constexpr int SHELL_EPB = SHELL_TPB / 16;
+constexpr int SHELL_OUT_LD = 580;            // 576 + 4: the two elements of a warp start 8 banks apart
 
+// Per-element data every one of the 16 threads needs: computed ONCE per element by three of them (local
+// coordinates, triad, material) and four more (one DKMQ edge each) instead of redundantly by all 16 -- the square
+// roots and divisions in here were half of the kernel's FP64 instructions.
+struct ShellShared {
+    PnShellGeom G;
+    PnShellMat mat;
+    double R[9];
+    double width, height;
+    double diag[4];
+};
+
+// The 16 threads of an element sit in one half warp, so every hand-over through shared memory below needs a
+// __syncwarp() only.  The finished 24x24 block is staged in shared memory (in the space of the stage-B records,
+// which are dead by then) and leaves as 128-byte contiguous stores.
 template <bool QUAD>
-__global__ void __launch_bounds__(SHELL_TPB)
+__global__ void __launch_bounds__(SHELL_TPB, 4)
 k_shell_ke(int64_t n, const int32_t *__restrict__ ijmn, const double *__restrict__ props,
            const double *__restrict__ xyz, double *__restrict__ out) {
-    __shared__ PnGpNode s_rec[SHELL_EPB][4][4];
-    __shared__ double s_diag[SHELL_EPB][4];
+    __shared__ double s_buf[SHELL_EPB][SHELL_OUT_LD];      // stage-B records (16 x 18 doubles), later the output block
+    __shared__ ShellShared s_el[SHELL_EPB];
+    static_assert(sizeof(PnGpNode) * 16 <= sizeof(double) * SHELL_OUT_LD, "stage-B records must fit the staging buffer");
     const int le = threadIdx.x >> 4, t = threadIdx.x & 15;
     int64_t e = blockIdx.x * (int64_t)SHELL_EPB + le;
     const bool valid = e < n;
-    if (!valid) e = n - 1;                    // keep every thread alive for the barriers
+    if (!valid) e = n - 1;                    // keep every thread alive for the warp-level hand-overs
+    ShellShared &S = s_el[le];
+    PnGpNode *s_rec = reinterpret_cast<PnGpNode *>(s_buf[le]);      // [gauss point][node]
 
-    // stage A (redundant per thread; loads are warp-broadcast): geometry, triad, material
-    double p[4][3];
+    // stage A: one thread each for the local corner coordinates, the triad and the material
+    if (t < 3) {
+        double p[4][3];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        int64_t nd = ijmn[4 * e + a];
-        p[a][0] = xyz[3 * nd]; p[a][1] = xyz[3 * nd + 1]; p[a][2] = xyz[3 * nd + 2];
-    }
-    double pr[5];
+        for (int a = 0; a < 4; ++a) {
+            int64_t nd = ijmn[4 * e + a];
+            p[a][0] = xyz[3 * nd]; p[a][1] = xyz[3 * nd + 1]; p[a][2] = xyz[3 * nd + 2];
+        }
+        if (t == 0) {
+            if (QUAD) {
+                pn_quad_local_xy(p, S.G.xl, S.G.yl);
+            } else {
+                // Plate3D.width/height :77-87 -- the plate is treated as a width x height rectangle
+                double width = sqrt((p[0][0] - p[1][0]) * (p[0][0] - p[1][0]) + (p[0][1] - p[1][1]) * (p[0][1] - p[1][1]) +
+                                    (p[0][2] - p[1][2]) * (p[0][2] - p[1][2]));
+                double height = sqrt((p[0][0] - p[3][0]) * (p[0][0] - p[3][0]) + (p[0][1] - p[3][1]) * (p[0][1] - p[3][1]) +
+                                     (p[0][2] - p[3][2]) * (p[0][2] - p[3][2]));
+                S.width = width; S.height = height;
+                S.G.xl[0] = 0; S.G.yl[0] = 0; S.G.xl[1] = width; S.G.yl[1] = 0;
+                S.G.xl[2] = width; S.G.yl[2] = height; S.G.xl[3] = 0; S.G.yl[3] = height;
+            }
+        } else if (t == 1) {
+            pn_shell_dircos(p[0], p[1], p[3], S.R);
+        } else {
+            double pr[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) pr[k] = props[5 * e + k];
-    PnShellGeom G;
-    double width = 0.0, height = 0.0;
-    if (QUAD) {
-        pn_quad_local_xy(p, G.xl, G.yl);
-        pn_quad_edges(G, pr[0], pr[2]);
-    } else {
-        // Plate3D.width/height :77-87 -- the plate is treated as a width x height rectangle
-        width = sqrt((p[0][0] - p[1][0]) * (p[0][0] - p[1][0]) + (p[0][1] - p[1][1]) * (p[0][1] - p[1][1]) +
-                     (p[0][2] - p[1][2]) * (p[0][2] - p[1][2]));
-        height = sqrt((p[0][0] - p[3][0]) * (p[0][0] - p[3][0]) + (p[0][1] - p[3][1]) * (p[0][1] - p[3][1]) +
-                      (p[0][2] - p[3][2]) * (p[0][2] - p[3][2]));
-        G.xl[0] = 0; G.yl[0] = 0; G.xl[1] = width; G.yl[1] = 0;
-        G.xl[2] = width; G.yl[2] = height; G.xl[3] = 0; G.yl[3] = height;
+            for (int k = 0; k < 5; ++k) pr[k] = props[5 * e + k];
+            pn_shell_material(pr, S.mat);
+        }
     }
+    __syncwarp();
+    if (QUAD && t < 4) pn_quad_edge(S.G, t, props[5 * e], props[5 * e + 2]);
+    __syncwarp();
 
     // stage B: (gauss point, node)
-    pn_shell_gp_node(G, t >> 2, t & 3, QUAD, s_rec[le][t >> 2][t & 3]);
-    __syncthreads();
+    {
+        PnGpNode rec;
+        pn_shell_gp_node(S.G, t >> 2, t & 3, QUAD, rec);      // edge data indexed at run time: straight from shared memory
+        s_rec[t] = rec;
+    }
+    __syncwarp();
 
     // stage C: (node a, node b)
     const int a = t >> 2, b = t & 3;
-    PnShellMat mat;
-    pn_shell_material(pr, mat);
+    const PnShellMat mat = S.mat;
     double kb[9], km[4];
     {
         PnGpNode A[4], B[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { A[g] = s_rec[le][g][a]; B[g] = s_rec[le][g][b]; }
+        for (int g = 0; g < 4; ++g) { A[g] = s_rec[4 * g + a]; B[g] = s_rec[4 * g + b]; }
         pn_quad_pair(A, B, mat, kb, km);
     }
-    if (!QUAD) pn_plate_pair_bending(a, b, width, height, pr, kb);
-    if (a == b) s_diag[le][a] = fmin(fabs(kb[4]), fabs(kb[8]));
-    __syncthreads();
+    if (!QUAD) {
+        double pr[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) pr[k] = props[5 * e + k];
+        pn_plate_pair_bending(a, b, S.width, S.height, pr, kb);
+    }
+    if (a == b) S.diag[a] = fmin(fabs(kb[4]), fabs(kb[8]));
+    __syncwarp();                                // also: every thread has read its stage-B records
     // drilling stiffness: smallest rotational diagonal / 1000 (Quad3D.py:577-579, Plate3D.py:262-264)
-    double k_rz = fmin(fmin(s_diag[le][0], s_diag[le][1]), fmin(s_diag[le][2], s_diag[le][3])) / 1000;
+    double k_rz = fmin(fmin(S.diag[0], S.diag[1]), fmin(S.diag[2], S.diag[3])) / 1000;
 
     double K[36], Kg[36], R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = S.R[k];
     pn_shell_local_block(kb, km, QUAD, a == b, k_rz, K);
-    pn_shell_dircos(p[0], p[1], p[3], R);
     pn_shell_rotate_block(R, K, Kg);
+    double *so = s_buf[le] + (6 * a) * 24 + 6 * b;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) so[i * 24 + j] = Kg[6 * i + j];
+    __syncwarp();
     if (valid) {
-        double *o = out + e * 576 + (6 * a) * 24 + 6 * b;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j < 6; ++j) o[i * 24 + j] = Kg[6 * i + j];
+        double *o = out + e * 576 + t;
+        const double *si = s_buf[le] + t;
+#pragma unroll 6
+        for (int k = 0; k < 36; ++k) o[16 * k] = si[16 * k];
     }
 }
 

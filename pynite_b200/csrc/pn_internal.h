@@ -215,6 +215,7 @@ struct Ctx {
     DevBuf<int32_t> nsp_dof;       // global DOF of each active node support spring, model order
     DevBuf<double> nsp_val;
     bool ev_ready = false;
+    int ev_assemblies = 0;          // assemblies that consumed the current element values (see assemble())
 
     // symbolic results
     bool symbolic_ready = false;

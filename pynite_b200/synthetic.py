@@ -40,12 +40,16 @@ def _empty_common(A, N):
     A.sub_owner = np.zeros(0, dtype=np.int32)
 
 
-def quad_plate_arrays(n=500, n_combos=64, a=12.0, t=8.0, E=3605.0, nu=0.17, seed=20261019, mat_springs=None):
+def quad_plate_arrays(n=500, n_combos=64, a=12.0, t=8.0, E=3605.0, nu=0.17, seed=20261019, mat_springs=None, jitter=0.0):
     """BASELINE config 3: n x n DKMQ quads in the XY plane, perimeter pinned.
 
     `mat_springs` = ks (kci) switches to the config-4 shape instead: the mesh lies in the XZ plane, every
     node carries a DY Winkler spring ks*tributary area (`MatFoundation.py:121-136`, linear springs), and
-    only two corner nodes are restrained in-plane."""
+    only two corner nodes are restrained in-plane.
+
+    `jitter` > 0 moves every node in the plane of the mesh by U(-jitter, jitter) in both directions (own random
+    stream): no two quads are bit-identical any more, which is what the general-geometry assembly path is measured
+    on (the generated meshes of the BASELINE configs collapse to a handful of element classes)."""
     A = ModelArrays()
     N = (n + 1)*(n + 1)
     _empty_common(A, N)
@@ -54,6 +58,10 @@ def quad_plate_arrays(n=500, n_combos=64, a=12.0, t=8.0, E=3605.0, nu=0.17, seed
     xyz = np.zeros((N, 3))
     xyz[:, 0] = c*a
     xyz[:, 2 if mat_springs is not None else 1] = r*a
+    if jitter:
+        jr = np.random.default_rng(seed + 7919)
+        xyz[:, 0] += jr.uniform(-jitter, jitter, N)
+        xyz[:, 2 if mat_springs is not None else 1] += jr.uniform(-jitter, jitter, N)
     A.xyz = xyz
     support = np.zeros(N, dtype=np.uint8)
     if mat_springs is None:
