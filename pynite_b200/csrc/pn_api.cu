@@ -238,11 +238,20 @@ double residual_check(Ctx *c, const double *vals11, int percol, int s, const pn_
     cudaStream_t st = c->stream;
     DevBuf<double> &AX = c->work_ax;
     AX.resize(n1 * s);
-    residual_dd(c, c->blk[0], vals11, percol ? c->blk[0].nnz : 0, c->X.ptr, c->B.ptr, AX.ptr, s, st);
+    // subtree-to-GPU solve: X is replicated, so every rank takes 1/world of the rows and the squared norms are summed
+    int64_t r0 = 0, r1 = n1;
+    if (o.solver != PN_SOLVER_PCG) direct_dist_row_share(c, n1, &r0, &r1);
+    residual_dd(c, c->blk[0], vals11, percol ? c->blk[0].nnz : 0, c->X.ptr, c->B.ptr, AX.ptr, s, st, nullptr, r0, r1 - r0);
     std::vector<double> rr(s), bb(s), xx(s);
-    column_dots(c, n1, s, AX.ptr, AX.ptr, rr.data());
-    column_dots(c, n1, s, c->B.ptr, c->B.ptr, bb.data());
-    column_dots(c, n1, s, c->X.ptr, c->X.ptr, xx.data());
+    column_dots(c, r1 - r0, s, AX.ptr + r0 * s, AX.ptr + r0 * s, rr.data());
+    column_dots(c, r1 - r0, s, c->B.ptr + r0 * s, c->B.ptr + r0 * s, bb.data());
+    column_dots(c, r1 - r0, s, c->X.ptr + r0 * s, c->X.ptr + r0 * s, xx.data());
+    if (r1 - r0 != n1) {
+        std::vector<double> all((size_t)3 * s);
+        for (int j = 0; j < s; ++j) { all[j] = rr[j]; all[s + j] = bb[j]; all[2 * s + j] = xx[j]; }
+        direct_dist_sum(c, all.data(), 3 * s);
+        for (int j = 0; j < s; ++j) { rr[j] = all[j]; bb[j] = all[s + j]; xx[j] = all[2 * s + j]; }
+    }
     double worst = 0.0;
     for (int j = 0; j < s; ++j) {
         bool finite = std::isfinite(rr[j]) && std::isfinite(xx[j]);

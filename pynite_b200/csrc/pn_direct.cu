@@ -30,6 +30,8 @@
 // order per element and the orthotropic membrane matrix is unsymmetric when kx_mod != ky_mod
 // (Quad3D.py:517-519).  K11 is positive definite for a stable structure, so no pivoting is needed;
 // a zero / non-finite pivot is reported as PN_ERR_SINGULAR (Analysis.py:172, 238-239).
+#include <cub/cub.cuh>
+
 #include "pn_internal.h"
 #include "pn_direct_symbolic.h"
 
@@ -104,11 +106,17 @@ struct DistPlan {
     std::vector<int64_t> um_off;              // per cut-level front (index inside the level): offset of its update matrix in its owner's segment
     std::vector<int64_t> uv_off;              // ... of its update-vector rows (to be scaled by s)
     int64_t um_seg = 0, uv_seg = 0;           // segment sizes (doubles; uv in rows)
+    bool um_tri = false;                      // symmetric mode: update matrices travel as packed lower triangles
     std::vector<int64_t> pos_lo, pos_hi;      // [world] elimination-position range whose solved rows the rank owns
     int64_t x_seg = 0;                        // max rows of a rank's range
     DevBuf<int64_t> d_um_off, d_uv_off;
     DevBuf<int32_t> d_cut_owner;
     DevBuf<double> send, recv;
+    // K11 rows this rank's sweeps read from a right-hand side: the pivots of its own subtrees and of every front above
+    // the cut.  The refinement residual is computed on these rows only (all other rows of the array are overwritten by
+    // the solve: they arrive with the other ranks' solved rows).
+    DevBuf<int32_t> res_rows;
+    int64_t n_res_rows = 0;
 };
 
 struct DirectSolver {
@@ -123,9 +131,15 @@ struct DirectSolver {
     std::vector<FrontDev> h_fronts;           // level-major
     DevBuf<FrontDev> fronts;
     DevBuf<int32_t> fidx, fpos, rel, perm_pos, dof_front_lm;   // dof_front in level-major numbering
-    DevBuf<int32_t> ent_front;                // per K11 entry: owning front (level-major id)
+    // K11 entries grouped by owning front (level-major id, so also by level): front f is assembled from entries
+    // [front_eptr[f], front_eptr[f+1]) -- a level (or a rank's range of it) touches its own entries only
+    DevBuf<int32_t> ent_front;                // per grouped entry: owning front
     DevBuf<uint32_t> ent_dst;                 // offset inside the front matrix
-    DevBuf<uint8_t> ent_level;
+    DevBuf<uint32_t> ent_src;                 // position in the K11 value array
+    std::vector<int64_t> front_eptr;          // [n_fronts + 1] (host)
+    DevBuf<int32_t> ent_front_raw;            // scratch of the grouping, kept so that a re-analysis allocates nothing
+    DevBuf<uint32_t> ent_dst_raw, ent_iota;
+    DevBuf<int64_t> d_front_eptr;
     DevBuf<double> arena[2];
     DevBuf<double> warena[2];
     DevBuf<double> yarena;                    // per-front solved own rows of the level being processed
@@ -196,8 +210,7 @@ __device__ __forceinline__ int front_find(const int32_t *__restrict__ list, int 
 __global__ void k_entry_maps(int64_t nnz, const int32_t *__restrict__ ent_row, const int32_t *__restrict__ indices,
                              const int32_t *__restrict__ perm_pos, const int32_t *__restrict__ dof_front,
                              const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fpos,
-                             const uint8_t *__restrict__ front_level, int32_t *__restrict__ ent_front,
-                             uint32_t *__restrict__ ent_dst, uint8_t *__restrict__ ent_level, int *__restrict__ status) {
+                             int32_t *__restrict__ ent_front, uint32_t *__restrict__ ent_dst, int *__restrict__ status) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     int32_t i = ent_row[k], j = indices[k];
@@ -210,21 +223,37 @@ __global__ void k_entry_maps(int64_t nnz, const int32_t *__restrict__ ent_row, c
     if (li < 0 || lj < 0) { atomicMax(status, 2); li = lj = 0; }
     ent_front[k] = f;
     ent_dst[k] = (uint32_t)li * (uint32_t)front_ld(n) + (uint32_t)lj;
-    ent_level[k] = front_level[f];
 }
 
 // ------------------------------------------------------------------------------------------------
 // numeric factorisation kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void k_assemble_entries(int64_t nnz, int level, int f_lo, int f_hi, const uint8_t *__restrict__ ent_level,
-                                   const int32_t *__restrict__ ent_front, const uint32_t *__restrict__ ent_dst,
-                                   const FrontDev *__restrict__ fronts, const double *__restrict__ vals,
-                                   double *__restrict__ arena) {
+// entries [k0, k1) of the front-grouped entry list: one store each (every K11 entry has its own destination)
+__global__ void k_assemble_entries(int64_t k0, int64_t k1, const int32_t *__restrict__ ent_front, const uint32_t *__restrict__ ent_dst,
+                                   const uint32_t *__restrict__ ent_src, const FrontDev *__restrict__ fronts,
+                                   const double *__restrict__ vals, double *__restrict__ arena) {
+    int64_t k = k0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    arena[fronts[ent_front[k]].f_off + ent_dst[k]] = vals[ent_src[k]];
+}
+__global__ void k_iota_u32(int64_t n, uint32_t *__restrict__ out) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= nnz || ent_level[k] != level) return;
-    const int f = ent_front[k];
-    if (f < f_lo || f >= f_hi) return;         // (subtree-to-GPU: fronts of other ranks' subtrees)
-    arena[fronts[f].f_off + ent_dst[k]] = vals[k];
+    if (k < n) out[k] = (uint32_t)k;
+}
+__global__ void k_gather_by_u32(int64_t n, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ in, uint32_t *__restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[perm[k]];
+}
+// eptr[f] = first position of the sorted front list with value >= f, f = 0 .. nf
+__global__ void k_front_entry_ptr(int nf, int64_t n, const int32_t *__restrict__ sorted_front, int64_t *__restrict__ eptr) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > nf) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (sorted_front[mid] < f) lo = mid + 1; else hi = mid;
+    }
+    eptr[f] = lo;
 }
 
 // ---- subtree-to-GPU exchanges (DistPlan) ---------------------------------------------------------------------------
@@ -238,7 +267,7 @@ __global__ void k_dist_um(int first, const FrontDev *__restrict__ fronts, int cu
     double *seg = buf + um_off[q - cut_first];
     for (int a = blockIdx.y; a < F.nb; a += gridDim.y) {
         double *row = arena + F.f_off + (int64_t)(F.ns + a) * front_ld(n) + F.ns;
-        double *srow = seg + (int64_t)a * F.nb;
+        double *srow = seg + (sym ? (int64_t)a * (a + 1) / 2 : (int64_t)a * F.nb);
         const int bend = sym ? a + 1 : F.nb;       // symmetric mode keeps the lower triangle only
         if (unpack) for (int b = threadIdx.x; b < bend; b += blockDim.x) row[b] = srow[b];
         else        for (int b = threadIdx.x; b < bend; b += blockDim.x) srow[b] = row[b];
@@ -1782,8 +1811,6 @@ static void analyse(Ctx *c) {
     d.rel.upload(S.rel.data(), (int64_t)S.rel.size(), st);
     d.perm_pos.upload(S.perm_pos.data(), (int64_t)S.perm_pos.size(), st);
     d.dof_front_lm.upload(d.h_dof_front_lm.data(), (int64_t)d.h_dof_front_lm.size(), st);     // filled by analyse_host
-    DevBuf<uint8_t> &d_front_level = c->sym_front_level;
-    d_front_level.upload(front_level.data(), nf, st);
     d.L.resize(l_total); d.U.resize(u_total); d.inv.resize(inv_total);
     d.ll_flags.resize(inv_total / (2 * NB * NB) * LL_MAX_CHUNKS + 1);
     PN_CUDA(cudaMemsetAsync(d.ll_flags.ptr, 0, sizeof(uint32_t) * (inv_total / (2 * NB * NB) * LL_MAX_CHUNKS + 1), st));
@@ -1846,13 +1873,30 @@ static void analyse(Ctx *c) {
     const CsrBlock &A = c->blk[0];
     DevBuf<int32_t> &ent_row = c->sym_ent_row;
     ent_row.resize(A.nnz);
-    d.ent_front.resize(A.nnz); d.ent_dst.resize(A.nnz); d.ent_level.resize(A.nnz);
+    d.ent_front.resize(A.nnz); d.ent_dst.resize(A.nnz); d.ent_src.resize(A.nnz);
+    d.front_eptr.assign((size_t)nf + 1, 0);
     if (A.nnz) {
+        // destination of every entry in K11 order, then a stable sort by owning front (fronts are level-major)
+        DevBuf<int32_t> &front_raw = d.ent_front_raw;
+        DevBuf<uint32_t> &dst_raw = d.ent_dst_raw, &iota = d.ent_iota;
+        DevBuf<int64_t> &eptr = d.d_front_eptr;
+        front_raw.resize(A.nnz); dst_raw.resize(A.nnz); iota.resize(A.nnz); eptr.resize(nf + 1);
         k_entry_rows<<<grid_for(A.rows, 128), 128, 0, st>>>(A.rows, A.indptr.ptr, ent_row.ptr);
         k_entry_maps<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, ent_row.ptr, A.indices.ptr, d.perm_pos.ptr,
-                                                            d.dof_front_lm.ptr, d.fronts.ptr, d.fpos.ptr, d_front_level.ptr,
-                                                            d.ent_front.ptr, d.ent_dst.ptr, d.ent_level.ptr, d.status.ptr);
-        c->count_launch(2);
+                                                            d.dof_front_lm.ptr, d.fronts.ptr, d.fpos.ptr,
+                                                            front_raw.ptr, dst_raw.ptr, d.status.ptr);
+        k_iota_u32<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, iota.ptr);
+        int end_bit = 1;
+        while ((1 << end_bit) <= nf && end_bit < 31) ++end_bit;
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, front_raw.ptr, d.ent_front.ptr, iota.ptr, d.ent_src.ptr, (int)A.nnz, 0, end_bit, st);
+        c->cub_tmp.resize((int64_t)bytes);
+        PN_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.ptr, bytes, front_raw.ptr, d.ent_front.ptr, iota.ptr, d.ent_src.ptr, (int)A.nnz, 0, end_bit, st));
+        k_gather_by_u32<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, d.ent_src.ptr, dst_raw.ptr, d.ent_dst.ptr);
+        k_front_entry_ptr<<<grid_for(nf + 1, 128), 128, 0, st>>>(nf, A.nnz, d.ent_front.ptr, eptr.ptr);
+        PN_CUDA(cudaMemcpyAsync(d.front_eptr.data(), eptr.ptr, sizeof(int64_t) * (nf + 1), cudaMemcpyDeviceToHost, st));
+        c->count_launch(9);
+        PN_CUDA(cudaStreamSynchronize(st));
     }
     int status = 0;
     PN_CUDA(cudaMemcpyAsync(&status, d.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1999,12 +2043,13 @@ static void build_dist_plan(Ctx *c) {
     // exchange layouts
     P.um_off.assign(nc, 0); P.uv_off.assign(nc, 0);
     P.um_seg = 0; P.uv_seg = 0;
+    P.um_tri = c->model.symmetric && getenv("PN_FORCE_UNSYMMETRIC") == nullptr;       // as factorise() decides `sym`
     std::vector<int32_t> owner(nc, 0);
     for (int r = 0; r < world; ++r) {
         int64_t um = 0, uv = 0;
         for (int q = P.cut_lo[r]; q < P.cut_hi[r]; ++q) {
             const int64_t nb = d.h_fronts[q].nb;
-            P.um_off[q - cf] = um; um += nb * nb;
+            P.um_off[q - cf] = um; um += P.um_tri ? nb * (nb + 1) / 2 : nb * nb;
             P.uv_off[q - cf] = uv; uv += nb;
             owner[q - cf] = r;
         }
@@ -2036,6 +2081,18 @@ static void build_dist_plan(Ctx *c) {
             if (P.pos_hi[r] > P.pos_lo[r + 1]) throw ArgError("direct solver: subtree position ranges overlap");
     }
     cudaStream_t st = c->stream;
+    {
+        std::vector<int32_t> rows;
+        rows.reserve((size_t)(P.pos_hi[rank] - P.pos_lo[rank]) + 16384);
+        for (int l = 0; l < nl; ++l)
+            for (int q = (l <= cut ? P.lo[l] : d.level_ptr[l]); q < (l <= cut ? P.hi[l] : d.level_ptr[l + 1]); ++q) {
+                const FrontSym &fs = S.fronts[S.level_fronts[q]];
+                for (int64_t pp = fs.pos_start; pp < (int64_t)fs.pos_start + fs.ns; ++pp) rows.push_back(S.s_pos_dof[(size_t)pp]);
+            }
+        std::sort(rows.begin(), rows.end());
+        P.n_res_rows = (int64_t)rows.size();
+        P.res_rows.upload(rows.data(), P.n_res_rows, st);
+    }
     P.d_um_off.upload(P.um_off.data(), nc, st);
     P.d_uv_off.upload(P.uv_off.data(), nc, st);
     P.d_cut_owner.upload(owner.data(), nc, st);
@@ -2055,6 +2112,36 @@ static void dist_allgather(Ctx *c, int64_t seg) {
     c->ctr[PC_DIST_EXCHANGES]++;
 }
 
+// Sum over the ranks of n host doubles (every rank ends with the same values: the all-gather order is fixed).
+// Returns false when this context is not part of a distributed solve.
+bool direct_dist_sum(Ctx *c, double *vals, int n) {
+    if (!c->direct || !c->direct->dist.active || c->dist_world <= 1) return false;
+    DistPlan &P = c->direct->dist;
+    const int world = c->dist_world;
+    P.send.resize(std::max<int64_t>(P.send.n, n));
+    P.recv.resize(std::max<int64_t>(P.recv.n, (int64_t)n * world));
+    PN_CUDA(cudaMemcpyAsync(P.send.ptr, vals, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    dist_allgather(c, n);
+    std::vector<double> all((size_t)n * world);
+    PN_CUDA(cudaMemcpyAsync(all.data(), P.recv.ptr, sizeof(double) * n * world, cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) acc += all[(size_t)r * n + j];
+        vals[j] = acc;
+    }
+    return true;
+}
+
+// rows [*r0, *r1) of K11 whose part of a residual norm this rank computes (the whole range when not distributed)
+void direct_dist_row_share(Ctx *c, int64_t n1, int64_t *r0, int64_t *r1) {
+    *r0 = 0; *r1 = n1;
+    if (!c->direct || !c->direct->dist.active || c->dist_world <= 1) return;
+    const int64_t per = (n1 + c->dist_world - 1) / c->dist_world;
+    *r0 = std::min<int64_t>(n1, per * c->dist_rank);
+    *r1 = std::min<int64_t>(n1, *r0 + per);
+}
+
 void direct_set_distributed(Ctx *c) {
     if (!c->direct) return;
     c->direct->analysed = false;          // the plan is rebuilt with the device maps at the next solve
@@ -2071,6 +2158,7 @@ static void exchange_update_matrices(Ctx *c, int sym) {
     const int world = c->dist_world, rank = c->dist_rank;
     const int cf = d.level_ptr[P.cut];
     double *arena = d.arena[P.cut & 1].ptr;
+    if ((sym != 0) != P.um_tri) throw ArgError("direct solver: the exchange layout was planned for the other symmetry mode");
     P.send.resize(std::max<int64_t>(P.um_seg, 1));
     P.recv.resize(std::max<int64_t>(P.um_seg, 1) * world);
     const int mine = P.cut_hi[rank] - P.cut_lo[rank];
@@ -2105,7 +2193,6 @@ static void factorise(Ctx *c, const double *vals11, const std::function<void(int
     LevelProf lp(debug_levels && debug_kernels, st);
     long long *dbg_clk = nullptr;
     if (debug_levels && debug_kernels) cudaMalloc(&dbg_clk, 8 * sizeof(long long));
-    const CsrBlock &A = c->blk[0];
     d.status.zero(st);
     c->ctr[PC_FACTORISATIONS]++;
     c->ctr[PC_LEVELS] = d.n_levels;
@@ -2126,8 +2213,13 @@ static void factorise(Ctx *c, const double *vals11, const std::function<void(int
         } else {
             PN_CUDA(cudaMemsetAsync(arena, 0, sizeof(double) * d.level_f_total[l], st));
         }
-        { ProfScope ps_(c, PS_FRONT_ASSEMBLE); k_assemble_entries<<<grid_for(A.nnz, 256), 256, 0, st>>>(A.nnz, l, first, first + nfl, d.ent_level.ptr, d.ent_front.ptr, d.ent_dst.ptr,
-                                                                  d.fronts.ptr, vals11, arena); }
+        {
+            const int64_t k0 = d.front_eptr[first], k1 = d.front_eptr[first + nfl];
+            if (k1 > k0) {
+                ProfScope ps_(c, PS_FRONT_ASSEMBLE);
+                k_assemble_entries<<<grid_for(k1 - k0, 256), 256, 0, st>>>(k0, k1, d.ent_front.ptr, d.ent_dst.ptr, d.ent_src.ptr, d.fronts.ptr, vals11, arena);
+            }
+        }
         lp.end();
         c->count_launch();
         if (l > 0) {
@@ -2719,6 +2811,21 @@ void direct_invalidate_pattern(Ctx *c) {
     c->direct->fronts_s = 0;
 }
 
+// |d|^2 and |x|^2 per column for the refinement's contraction estimate.  Distributed solve: both arrays are replicated,
+// every rank reduces its share of the rows and the partial sums are added across the ranks.
+static void refinement_norms(Ctx *c, int64_t n1, int s, const double *Dv, const double *Xv, double *dd, double *xx) {
+    int64_t r0 = 0, r1 = n1;
+    direct_dist_row_share(c, n1, &r0, &r1);
+    column_dots(c, r1 - r0, s, Dv + r0 * s, Dv + r0 * s, dd);
+    column_dots(c, r1 - r0, s, Xv + r0 * s, Xv + r0 * s, xx);
+    if (r1 - r0 != n1) {
+        std::vector<double> both((size_t)2 * s);
+        for (int j = 0; j < s; ++j) { both[j] = dd[j]; both[s + j] = xx[j]; }
+        direct_dist_sum(c, both.data(), 2 * s);
+        for (int j = 0; j < s; ++j) { dd[j] = both[j]; xx[j] = both[s + j]; }
+    }
+}
+
 void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solve_opts &o) {
     cudaStream_t st = c->stream;
     int64_t n1 = c->n1;
@@ -2783,11 +2890,11 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
         // stops as soon as the error predicted after applying d (rho * |d| / |x| = rho^2) is below 1e-11.
         std::vector<double> dd(s), xx(s);
         for (int it = 0; it < refine; ++it) {
-            residual_dd(c, c->blk[0], vals11, 0, c->X.ptr, c->B.ptr, R.ptr, s, st);
+            if (d.dist.active) residual_dd(c, c->blk[0], vals11, 0, c->X.ptr, c->B.ptr, R.ptr, s, st, d.dist.res_rows.ptr, 0, d.dist.n_res_rows);
+            else residual_dd(c, c->blk[0], vals11, 0, c->X.ptr, c->B.ptr, R.ptr, s, st);
             c->stats.spmm_launches += 1;
             solve_inplace(c, R.ptr, s);
-            column_dots(c, n1, s, R.ptr, R.ptr, dd.data());
-            column_dots(c, n1, s, c->X.ptr, c->X.ptr, xx.data());
+            refinement_norms(c, n1, s, R.ptr, c->X.ptr, dd.data(), xx.data());
             { ProfScope ps_(c, PS_SOLVE_MISC); k_axpy1<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, R.ptr, c->X.ptr); }
             c->count_launch();
             c->stats.iterations += 1;
@@ -2816,11 +2923,11 @@ void direct_solve(Ctx *c, const double *vals11, int percol, int s, const pn_solv
             double prev = 1e300;
             bool converged = false;
             for (int it = 0; it < 80; ++it) {
-                residual_dd(c, A, vals11, A.nnz, c->X.ptr, c->B.ptr, R.ptr, s, st);
+                if (d.dist.active) residual_dd(c, A, vals11, A.nnz, c->X.ptr, c->B.ptr, R.ptr, s, st, d.dist.res_rows.ptr, 0, d.dist.n_res_rows);
+                else residual_dd(c, A, vals11, A.nnz, c->X.ptr, c->B.ptr, R.ptr, s, st);
                 c->stats.spmm_launches += 1;
                 solve_inplace(c, R.ptr, s);
-                column_dots(c, n1, s, R.ptr, R.ptr, dd.data());
-                column_dots(c, n1, s, c->X.ptr, c->X.ptr, xx.data());
+                refinement_norms(c, n1, s, R.ptr, c->X.ptr, dd.data(), xx.data());
                 { ProfScope ps_(c, PS_SOLVE_MISC); k_axpy1<<<grid_for(n1 * s, 256), 256, 0, st>>>(n1 * s, R.ptr, c->X.ptr); }
                 c->count_launch();
                 c->stats.iterations += 1;

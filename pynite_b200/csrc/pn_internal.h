@@ -271,7 +271,6 @@ struct Ctx {
     DevBuf<uint32_t> sym_pos, sym_head, sym_incl, sym_kpos, sym_k32a, sym_k32b, sym_k32c;
     DevBuf<uint64_t> sym_key;
     DevBuf<int32_t> sym_slot_row, sym_cnt, sym_ent_row, sym_bad;
-    DevBuf<uint8_t> sym_front_level;
     DevBuf<int> sym_nb;
     DevBuf<double> sym_press;
     // persistent work arrays: a steady-state step performs no cudaMalloc / cudaFree
@@ -410,7 +409,7 @@ int64_t check_nodal_stability(Ctx *c, int32_t *bad_host, int64_t cap);
 // Y = A X for a CSR block, X/Y row-major with s columns
 void spmm(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, cudaStream_t st);
 void residual_dd(Ctx *c, const CsrBlock &A, const double *vals, int64_t vals_col_stride, const double *X, const double *B,
-                 double *R, int s, cudaStream_t st);
+                 double *R, int s, cudaStream_t st, const int32_t *rowlist = nullptr, int64_t row0 = 0, int64_t n_rows = -1);
 void spmm_rows(Ctx *c, const CsrBlock &A, const double *vals, const double *X, double *Y, int s, int64_t row0, int64_t row1,
                cudaStream_t st);
 void spmm_k11_grouped(Ctx *c, const double *vals, const double *X, double *Y, int s, cudaStream_t st);
@@ -441,6 +440,9 @@ void direct_release(Ctx *c);
 void direct_prefetch(Ctx *c);     // start the host half of the analysis on a worker thread (after the DOF partition is known)
 void direct_invalidate(Ctx *c);
 void direct_invalidate_pattern(Ctx *c);
-void direct_set_distributed(Ctx *c);   // the rank / world / callback in the context changed
+void direct_set_distributed(Ctx *c);
+bool direct_dist_sum(Ctx *c, double *vals, int n);                            // sum of host values over the ranks of a distributed solve
+void direct_dist_row_share(Ctx *c, int64_t n1, int64_t *r0, int64_t *r1);     // this rank's share of the rows for residual norms
+   // the rank / world / callback in the context changed
 
 }  // namespace pn

@@ -951,11 +951,12 @@ template <int G, int CPL>
 __global__ void __launch_bounds__(256)
 k_residual_dd(int64_t rows, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
               const double *__restrict__ vals, const double *__restrict__ X, const double *__restrict__ B,
-              double *__restrict__ R, int s, int64_t vals_col_stride) {
+              double *__restrict__ R, int s, int64_t vals_col_stride, const int32_t *__restrict__ rowlist, int64_t row0) {
     int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t r = gid / G;
     int lane = (int)(gid % G);
     if (r >= rows) return;
+    r = rowlist ? (int64_t)rowlist[r] : r + row0;          // a subset of the rows (subtree-to-GPU solve), or a row range
     double hi[CPL], lo[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) { hi[c] = (lane + c * G < s) ? B[r * s + lane + c * G] : 0.0; lo[c] = 0.0; }
@@ -983,10 +984,11 @@ k_residual_dd(int64_t rows, const int32_t *__restrict__ indptr, const int32_t *_
 
 template <int G>
 static void residual_dispatch_cpl(Ctx *c, const CsrBlock &A, const double *vals, int64_t stride, const double *X,
-                                  const double *B, double *R, int s, cudaStream_t st) {
+                                  const double *B, double *R, int s, cudaStream_t st, const int32_t *rowlist, int64_t row0,
+                                  int64_t n_rows) {
     int cpl = (s + G - 1) / G;
-    unsigned grid = grid_for(A.rows * G, 256);
-#define PN_RES(CPL_) do { ProfScope ps_(c, PS_SPMM); k_residual_dd<G, CPL_><<<grid, 256, 0, st>>>(A.rows, A.indptr.ptr, A.indices.ptr, vals, X, B, R, s, stride); } while (0)
+    unsigned grid = grid_for(n_rows * G, 256);
+#define PN_RES(CPL_) do { ProfScope ps_(c, PS_SPMM); k_residual_dd<G, CPL_><<<grid, 256, 0, st>>>(n_rows, A.indptr.ptr, A.indices.ptr, vals, X, B, R, s, stride, rowlist, row0); } while (0)
     if (cpl <= 1) PN_RES(1);
     else if (cpl <= 2) PN_RES(2);
     else if (cpl <= 4) PN_RES(4);
@@ -996,16 +998,21 @@ static void residual_dispatch_cpl(Ctx *c, const CsrBlock &A, const double *vals,
     c->count_launch();
 }
 
-// vals_col_stride = 0: one matrix for all columns; = nnz: vals is [s][nnz] (one matrix per column, P-Delta)
+// vals_col_stride = 0: one matrix for all columns; = nnz: vals is [s][nnz] (one matrix per column, P-Delta).
+// rowlist (n_rows entries) restricts the residual to those rows, otherwise rows [row0, row0 + n_rows) (n_rows < 0: all);
+// R keeps the full [rows][s] layout either way.
 void residual_dd(Ctx *c, const CsrBlock &A, const double *vals, int64_t vals_col_stride, const double *X, const double *B,
-                 double *R, int s, cudaStream_t st) {
-    if (!A.rows || !s) return;
-    if (s == 1) residual_dispatch_cpl<1>(c, A, vals, vals_col_stride, X, B, R, s, st);
-    else if (s == 2) residual_dispatch_cpl<2>(c, A, vals, vals_col_stride, X, B, R, s, st);
-    else if (s <= 4) residual_dispatch_cpl<4>(c, A, vals, vals_col_stride, X, B, R, s, st);
-    else if (s <= 8) residual_dispatch_cpl<8>(c, A, vals, vals_col_stride, X, B, R, s, st);
-    else if (s <= 16) residual_dispatch_cpl<16>(c, A, vals, vals_col_stride, X, B, R, s, st);
-    else residual_dispatch_cpl<32>(c, A, vals, vals_col_stride, X, B, R, s, st);
+                 double *R, int s, cudaStream_t st, const int32_t *rowlist, int64_t row0, int64_t n_rows) {
+    if (n_rows < 0) { rowlist = nullptr; row0 = 0; n_rows = A.rows; }
+    if (!A.rows || !s || !n_rows) return;
+#define PN_RESG(G_) residual_dispatch_cpl<G_>(c, A, vals, vals_col_stride, X, B, R, s, st, rowlist, row0, n_rows)
+    if (s == 1) PN_RESG(1);
+    else if (s == 2) PN_RESG(2);
+    else if (s <= 4) PN_RESG(4);
+    else if (s <= 8) PN_RESG(8);
+    else if (s <= 16) PN_RESG(16);
+    else PN_RESG(32);
+#undef PN_RESG
 }
 
 template <int G>
