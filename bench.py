@@ -56,6 +56,8 @@ def parse_args():
                     help='strong scaling on N > 1 GPUs: subtree = elimination tree split across the GPUs, all combos on '
                          'every GPU (pn_set_distributed); combos = combos split, K factorised on every GPU')
     ap.add_argument('--solver', default='direct', choices=['direct', 'pcg'])
+    ap.add_argument('--dof-classes', type=int, default=1, choices=[0, 1],
+                    help='pn_set_option("dof_classes"): 1 = membrane / bending / drilling fronts (default), 0 = node-based ordering (A/B)')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--cpu-n', type=int, default=96, help='quads per side of the CPU-baseline sample')
     ap.add_argument('--cpu-combos', type=int, default=2)
@@ -80,7 +82,10 @@ def workload_config(args, world):
     return {'workload': f'BASELINE config 3: {n}x{n} DKMQ quad plate, perimeter pinned, {total} load combos in total',
             'n_dof': 6*(n + 1)*(n + 1), 'n_quads': n*n, 'combos_total': total,
             'combos_per_gpu': [total]*world if subtree else per, 'solver': args.solver, 'sharding': sharding,
-            'l2': 'inputs larger than L2 (CSR values 236 MB, factor 8.5 GB per step); no explicit flush',
+            'ordering': ('nested dissection of the node graph, one front per separator and DOF-type class (membrane / bending / '
+                         'drilling never meet in a stored entry of a flat plate; verified on the device)' if args.dof_classes
+                         else 'nested dissection of the node graph, one front per separator (--dof-classes 0)'),
+            'l2': 'inputs larger than L2 (CSR values 236 MB, factor 3.6 GB per step); no explicit flush',
             'symbolic': 'pattern / scatter map / elimination tree built once outside the timed region for `value`, inside for `e2e`'}
 
 
@@ -358,6 +363,7 @@ def run_ours(args, rank, local_rank, world):
         A = synthetic.quad_plate_arrays(n=args.n, n_combos=args.combos, seed=20261019 + rank)
     my_combos = args.combos if subtree else len(shards[rank])
     eng = Engine(local_rank)
+    eng.set_option('dof_classes', args.dof_classes)
     if subtree:
         from pynite_b200 import distsolve
         distsolve.attach(eng)
@@ -561,6 +567,7 @@ def run_ours(args, rank, local_rank, world):
             'roofline': roof, 'rooflines': rooflines, 'kernels': kern,
             'phases_ms_per_step': {k: st[k]/K for k in ('ms_elements', 'ms_scatter', 'ms_partition', 'ms_rhs', 'ms_factor', 'ms_solve')},
             'solver_stats': {'factor_nnz': first_stats['factor_nnz'], 'factor_flops': first_stats['factor_flops'],
+                             'counters': eng.counters(),
                              'max_rel_residual': e2e_stats['max_rel_residual'], 'refine_steps': opts.refine_steps,
                              'fp64_gemm_peak_tflops_measured': f64_peak},
             'sizes': {'n_dof': int(sizes.n_dof), 'n1': int(sizes.n1), 'nnz_coo': int(sizes.nnz_coo), 'nnz_csr': int(sizes.nnz_csr),

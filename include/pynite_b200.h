@@ -119,8 +119,16 @@ PN_EXPORT int pn_member_kg(pn_ctx *ctx, const double *P, double *out);
  *      coo_matrix + tocsr pattern (:1791, :2279), Analysis._partition_D :1412, _partition :1508 -- */
 /* Tuning switches (no effect on results).  "assembly_graph" (default 1): the numeric class/recipe assembly is replayed
  * as one CUDA graph; 0 issues its launches one by one so that pn_profile_enable can time them individually.
- * "spmm_grouped" (default 1): K11 SpMM (pn_spmm_k11, PCG) with the rows of one node sharing every X-row load; 0 = one
- * lane group per row (kept for A/B measurements; same bits). */
+ * "spmm_grouped" (default 0): K11 SpMM (pn_spmm_k11, PCG) with the rows of one node sharing every X-row load; 0 = one
+ * lane group per row (same bits; the grouped kernel measured slower and is kept for A/B runs).
+ * "dof_classes" (default 1): ordering of the direct solver.  The reference stores no exact zeros (FEModel3D.py:130),
+ * so K11 of a flat shell model in an axis plane is reducible -- membrane translations, the bending triple and the drilling
+ * rotation never meet in a stored entry -- and SuperLU's column ordering inside spsolve (Analysis.py:217) works on
+ * that scalar graph.  1 = the classes are predicted from the element list, every separator of the node dissection
+ * yields one front per class, and the prediction is verified against the assembled pattern (rejected -> node-based
+ * ordering, counter "dof_class_rejects"); 0 = node-based ordering only; 2 = self-test (a prediction that must be
+ * rejected).  Same solution up to rounding; counter "dof_classes" reports the number of classes in use.
+ * "host_threads": OpenMP threads of the host worker (ordering, result zero fill). */
 PN_EXPORT int pn_set_option(pn_ctx *ctx, const char *name, int64_t value);
 /* Optional hint, callable once every pn_set_nodes / pn_set_springs / pn_set_members / pn_set_quads / pn_set_plates call
  * of a model has been made: starts the host half of the direct solver's analysis (node graph, nested dissection,

@@ -610,6 +610,10 @@ int pn_set_option(pn_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "assembly_graph")) c->opt_assembly_graph = value != 0;
     else if (!strcmp(name, "spmm_grouped")) c->opt_spmm_grouped = value != 0;
     else if (!strcmp(name, "host_threads")) c->opt_host_threads = (int)std::max<int64_t>(0, value);
+    else if (!strcmp(name, "dof_classes")) {
+        if (value < 0 || value > 2) throw ArgError("pn_set_option: dof_classes takes 0 (off), 1 (predict and verify) or 2 (self-test)");
+        if ((int)value != c->opt_dof_classes) { c->opt_dof_classes = (int)value; direct_invalidate(c); }
+    }
     else throw ArgError(std::string("pn_set_option: unknown option ") + name);
     PN_API_END
 }
@@ -1392,7 +1396,8 @@ int pn_reset_stats(pn_ctx *ctx) {
 static const char *kCounterNames[PC_COUNT] = {
     "lu_update", "lu_update_later_groups", "lu_strip", "split_levels", "sweep_smem", "sweep_ll", "sweep_step",
     "max_front_pivots", "levels", "factorisations", "pdelta_stationary_batches", "pdelta_fallback_columns",
-    "factor_fused_levels", "dist_exchanges", "dist_cut_level", "sweep_overlapped", "lookahead_groups", "sweep_ll_gemm"};
+    "factor_fused_levels", "dist_exchanges", "dist_cut_level", "sweep_overlapped", "lookahead_groups", "sweep_ll_gemm",
+    "dof_classes", "dof_class_rejects"};
 
 const char *pn_counter_name(int index) { return (index >= 0 && index < PC_COUNT) ? kCounterNames[index] : nullptr; }
 

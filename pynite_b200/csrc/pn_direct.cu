@@ -177,6 +177,9 @@ struct DirectSolver {
     }
     SymVec<int32_t> h_dof_front_lm;           // page-locked staging of dof_front in level-major numbering
     std::vector<int32_t> g_vstart, g_adj;     // vertex graph of the last analysis (host)
+    std::vector<uint8_t> g_row_class;         // DOF-type class of every K11 row when the DOF types fall into classes
+    int n_classes = 1;                        // DOF-type classes of the current ordering (pn_direct_symbolic.h, DofClasses)
+    bool classes_rejected = false;            // the assembled pattern joined two predicted classes: one class from now on
     std::vector<double> g_coords;
     std::vector<int64_t> g_adj_ptr;
     VertexGraphScratch g_scratch;
@@ -1662,12 +1665,32 @@ static void analyse_host(Ctx *c, const std::vector<int32_t> &newidx, bool timing
     std::vector<int32_t> &vstart = d.g_vstart, &adj = d.g_adj;
     std::vector<double> &coords = d.g_coords;
     std::vector<int64_t> &adj_ptr = d.g_adj_ptr;
+    // DOF-type classes predicted from the element list (flat shell models in an axis plane: membrane / bending /
+    // drilling never meet in a stored entry); k_entry_maps verifies the prediction against the assembled pattern
+    static const bool no_classes = getenv("PN_NO_DOF_CLASSES") != nullptr;
+    DofClasses cls;
+    if (!no_classes && !d.classes_rejected && c->opt_dof_classes == 1) {
+        std::vector<ConnView> shells(conn.begin() + 2, conn.end());
+        cls = predict_dof_classes(m.h_xyz.data(), shells, m.n_springs + m.n_members);
+    } else if (!d.classes_rejected && c->opt_dof_classes == 2) {
+        cls.n = 6;                                        // self-test of the verification: no model decouples like this
+        for (int k = 0; k < 6; ++k) cls.of_type[k] = (uint8_t)k;
+    }
+    d.n_classes = cls.n;
     build_vertex_graph(m.n_nodes, newidx.data(), m.h_xyz.data(), conn, vstart, coords, adj_ptr, adj, &d.g_scratch);
     tick.lap("vertex graph");
     int32_t nv = (int32_t)vstart.size() - 1;
     int leaf = 24;
     if (const char *e = getenv("PN_LEAF_SIZE")) leaf = std::max(1, atoi(e));
-    direct_symbolic(n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym);
+    if (cls.n > 1) {
+        d.g_row_class.resize((size_t)n1);
+        const int64_t n_dof = 6 * m.n_nodes;
+#pragma omp parallel for schedule(static)
+        for (int64_t dd = 0; dd < n_dof; ++dd)
+            if (newidx[dd] >= 0) d.g_row_class[newidx[dd]] = cls.of_type[dd % 6];
+    }
+    direct_symbolic(n1, nv, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, d.sym,
+                    cls.n > 1 ? d.g_row_class.data() : nullptr, cls.n, cls.diagonal);
     {
         // front of every K11 row in level-major numbering (page-locked: uploaded as is).  Done here, on the thread
         // that already owns an OpenMP team: a parallel region on the caller's thread would leave a second team
@@ -1901,7 +1924,16 @@ static void analyse(Ctx *c) {
     int status = 0;
     PN_CUDA(cudaMemcpyAsync(&status, d.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
+    if (status == 2 && d.n_classes > 1) {
+        // an assembled entry joins two of the predicted DOF-type classes: order again with one class (node-based)
+        d.classes_rejected = true;
+        d.host_state = 0;
+        c->ctr[PC_DOF_CLASS_REJECTS]++;
+        analyse(c);
+        return;
+    }
     if (status == 2) throw ArgError("direct solver: a K11 entry falls outside its front (symbolic analysis bug)");
+    c->ctr[PC_DOF_CLASSES] = d.n_classes;
     int64_t amax = 0;
     for (int l = 0; l < d.n_levels; ++l) amax = std::max(amax, d.level_f_total[l]);
     d.arena[0].resize(amax); d.arena[1].resize(amax);
@@ -1989,44 +2021,77 @@ static void build_dist_plan(Ctx *c) {
     for (int l = 0; l < nl; ++l) { P.lo[l] = d.level_ptr[l]; P.hi[l] = d.level_ptr[l + 1]; }
     c->ctr[PC_DIST_CUT_LEVEL] = -1;
     if (world <= 1 || !c->dist_allgather || nl < 2) return;
-    int cut = -1;
-    for (int l = nl - 1; l >= 0; --l)
-        if (d.level_ptr[l + 1] - d.level_ptr[l] >= world) { cut = l; break; }
-    if (const char *e = getenv("PN_DIST_CUT_BELOW")) cut = std::max(0, cut - atoi(e));     // experiments: deeper cut
-    if (cut < 0 || cut >= nl - 1) return;              // too narrow (or every level is below the cut): replicated solve
-    const int cf = d.level_ptr[cut], nc = d.level_ptr[cut + 1] - cf;
-    // cost of every subtree: factorisation flops of its fronts (ancestor at the cut level by walking levels downwards)
+    // Cut level.  Everything above it is replicated on every rank, everything on and below it is shared out as whole
+    // subtrees in contiguous, cost-balanced blocks of the cut level's fronts.  Candidates run from the highest level
+    // with at least `world` fronts down to the first one with 8 x world fronts; the one with the smallest
+    // (largest rank share + replicated part) in factorisation flops is taken: a higher cut replicates less but may
+    // balance badly (fronts of different DOF-type classes on one level differ by a factor of three in cost).
     const int nf = (int)d.h_fronts.size();
+    auto front_cost = [&](int q) {
+        const double ns = d.h_fronts[q].ns, nb = d.h_fronts[q].nb;
+        return 2.0 / 3.0 * ns * ns * ns + 2.0 * ns * ns * nb + 2.0 * ns * nb * nb + 1e4;
+    };
+    std::vector<double> level_cost(nl, 0.0);
+    for (int l = 0; l < nl; ++l)
+        for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) level_cost[l] += front_cost(q);
     std::vector<int32_t> anc(nf, -1);
-    std::vector<double> cost(nc, 0.0);
-    for (int q = cf; q < cf + nc; ++q) anc[q] = q;
-    for (int l = cut - 1; l >= 0; --l)
-        for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
-            const int p = d.h_fronts[q].parent;
-            anc[q] = p >= 0 ? anc[p] : -1;
-        }
-    for (int l = 0; l <= cut; ++l)
-        for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
-            if (anc[q] < 0) continue;
-            const double ns = d.h_fronts[q].ns, nb = d.h_fronts[q].nb;
-            cost[anc[q] - cf] += 2.0 / 3.0 * ns * ns * ns + 2.0 * ns * ns * nb + 2.0 * ns * nb * nb + 1e4;
-        }
-    // contiguous blocks of the cut level, balanced by cost, at least one front per rank
-    P.cut_lo.assign(world, 0); P.cut_hi.assign(world, 0);
-    {
-        double total = 0.0;
+    std::vector<double> cost;
+    auto subtree_costs = [&](int cut_) {            // fills anc (ancestor on the cut level) and cost (per cut front)
+        const int cf_ = d.level_ptr[cut_], nc_ = d.level_ptr[cut_ + 1] - cf_;
+        std::fill(anc.begin(), anc.end(), -1);
+        cost.assign(nc_, 0.0);
+        for (int q = cf_; q < cf_ + nc_; ++q) anc[q] = q;
+        for (int l = cut_ - 1; l >= 0; --l)
+            for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
+                const int p = d.h_fronts[q].parent;
+                anc[q] = p >= 0 ? anc[p] : -1;
+            }
+        for (int l = 0; l <= cut_; ++l)
+            for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q)
+                if (anc[q] >= 0) cost[anc[q] - cf_] += front_cost(q);
+    };
+    // contiguous blocks of the cut level, balanced by cost, at least one front per rank; returns the largest share
+    auto share_out = [&](int cut_, std::vector<int32_t> &lo_, std::vector<int32_t> &hi_) {
+        const int cf_ = d.level_ptr[cut_], nc_ = d.level_ptr[cut_ + 1] - cf_;
+        lo_.assign(world, 0); hi_.assign(world, 0);
+        double total = 0.0, worst = 0.0;
         for (double v : cost) total += v;
         int q = 0;
         double acc = 0.0;
         for (int r = 0; r < world; ++r) {
-            P.cut_lo[r] = cf + q;
+            lo_[r] = cf_ + q;
             const int must_leave = world - 1 - r;          // one front at least for every later rank
+            const double before = acc;
             acc += cost[q]; ++q;
-            while (q < nc - must_leave && acc + 0.5 * cost[q] <= total * (r + 1) / world) { acc += cost[q]; ++q; }
-            if (r == world - 1) q = nc;
-            P.cut_hi[r] = cf + q;
+            while (q < nc_ - must_leave && acc + 0.5 * cost[q] <= total * (r + 1) / world) { acc += cost[q]; ++q; }
+            if (r == world - 1) { while (q < nc_) { acc += cost[q]; ++q; } }
+            hi_[r] = cf_ + q;
+            worst = std::max(worst, acc - before);
+        }
+        return worst;
+    };
+    int cut = -1;
+    {
+        int top = -1;
+        for (int l = nl - 2; l >= 0; --l)
+            if (d.level_ptr[l + 1] - d.level_ptr[l] >= world) { top = l; break; }
+        if (top < 0) return;                            // too narrow: replicated solve
+        double best = 0.0, above = 0.0;
+        for (int l = nl - 1; l > top; --l) above += level_cost[l];
+        std::vector<int32_t> lo_, hi_;
+        for (int l = top; l >= 0; --l) {
+            subtree_costs(l);
+            const double obj = share_out(l, lo_, hi_) + above;
+            if (cut < 0 || obj < best) { cut = l; best = obj; }
+            if (d.level_ptr[l + 1] - d.level_ptr[l] >= 8 * world) break;
+            above += level_cost[l];
         }
     }
+    if (const char *e = getenv("PN_DIST_CUT_BELOW")) cut = std::max(0, cut - atoi(e));     // experiments: deeper cut
+    if (cut < 0 || cut >= nl - 1) return;
+    const int cf = d.level_ptr[cut], nc = d.level_ptr[cut + 1] - cf;
+    subtree_costs(cut);
+    share_out(cut, P.cut_lo, P.cut_hi);
     // per-level ranges of this rank: fronts whose cut ancestor is in [cut_lo[rank], cut_hi[rank]); contiguous per level
     for (int l = 0; l <= cut; ++l) {
         int lo = -1, hi = -1;
@@ -2196,6 +2261,7 @@ static void factorise(Ctx *c, const double *vals11, const std::function<void(int
     d.status.zero(st);
     c->ctr[PC_FACTORISATIONS]++;
     c->ctr[PC_LEVELS] = d.n_levels;
+    c->ctr[PC_DOF_CLASSES] = d.n_classes;
     for (int l = 0; l < d.n_levels; ++l) c->ctr[PC_MAX_FRONT_NS] = std::max<int64_t>(c->ctr[PC_MAX_FRONT_NS], d.level_max_ns[l]);
     const DistPlan &DP = d.dist;
     for (int l = 0; l < d.n_levels; ++l) {
@@ -2798,6 +2864,7 @@ void direct_invalidate(Ctx *c) {
     if (!c->direct) return;
     try { join_host_analysis(*c->direct); } catch (...) {}     // the worker reads the host copy of the model
     c->direct->host_state = 0;
+    c->direct->classes_rejected = false;
     c->direct->analysed = false;
     c->direct->shared_factor = false;
     c->direct->fronts_s = 0;

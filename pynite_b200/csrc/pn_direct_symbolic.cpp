@@ -12,6 +12,59 @@
 
 namespace pn {
 
+DofClasses predict_dof_classes(const double *xyz, const std::vector<ConnView> &shells, int64_t n_line_elements) {
+    DofClasses out;
+    if (n_line_elements > 0) return out;
+    // planes met: bit g = some shell has all four nodes at one coordinate g (bitwise equal: the element triad is then
+    // built from differences that are exact zeros along g); bit 3 = a shell in general position
+    unsigned planes = 0;
+    int64_t total = 0;
+    for (const ConnView &cv : shells) {
+        total += cv.count;
+        unsigned local = 0;
+#pragma omp parallel for schedule(static) reduction(| : local)
+        for (int64_t e = 0; e < cv.count; ++e) {
+            if (cv.active && !cv.active[e]) continue;
+            const int32_t *nd = cv.nodes + cv.nn * e;
+            int g = -1, hits = 0;
+            for (int k = 0; k < 3; ++k) {
+                bool same = true;
+                for (int a = 1; a < cv.nn; ++a) same = same && xyz[3 * (int64_t)nd[a] + k] == xyz[3 * (int64_t)nd[0] + k];
+                if (same) { g = k; ++hits; }
+            }
+            local |= hits == 1 ? 1u << g : 8u;
+        }
+        planes |= local;
+    }
+    if (!total || (planes & 8u)) return out;
+    int parent[6] = {0, 1, 2, 3, 4, 5};
+    auto find = [&](int a) { while (parent[a] != a) a = parent[a]; return a; };
+    auto join = [&](int a, int b) { a = find(a); b = find(b); if (a != b) parent[std::max(a, b)] = std::min(a, b); };
+    for (int g = 0; g < 3; ++g) {
+        if (!(planes >> g & 1u)) continue;
+        const int h1 = (g + 1) % 3, h2 = (g + 2) % 3;
+        join(h1, h2);                          // membrane
+        join(g, 3 + h1); join(g, 3 + h2);      // bending: normal translation + in-plane rotations
+    }                                          // (drilling rotation 3 + g: diagonal only)
+    int id[6], n = 0;
+    for (int k = 0; k < 6; ++k) id[k] = -1;
+    for (int k = 0; k < 6; ++k) {
+        const int r = find(k);
+        if (id[r] < 0) id[r] = n++;
+        out.of_type[k] = (uint8_t)id[r];
+    }
+    out.n = n;
+    // a class made of drilling rotations only: every member is the normal rotation of a plane that was met and was
+    // joined to nothing
+    for (int c = 0; c < n; ++c) {
+        bool only_drilling = true;
+        for (int k = 0; k < 6; ++k)
+            if (out.of_type[k] == c && !(k >= 3 && (planes >> (k - 3) & 1u))) only_drilling = false;
+        out.diagonal[c] = only_drilling ? 1 : 0;
+    }
+    return out;
+}
+
 void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xyz, const std::vector<ConnView> &conn,
                         std::vector<int32_t> &vstart, std::vector<double> &coords, std::vector<int64_t> &adj_ptr,
                         std::vector<int32_t> &adj, VertexGraphScratch *scratch) {
@@ -235,8 +288,72 @@ struct Builder {
 
 }  // namespace
 
+// Joins a forest into a set of trees of one height.  Roots of the tallest trees stay roots (they share the top level);
+// every shorter tree has an empty boundary at its root, so giving that root a parent adds nothing to the parent's
+// matrix -- the link only says on which level, and (subtree-to-GPU solve) on which rank, the tree is processed.  A tree
+// of height h hangs from a front of a tallest tree at depth H - 1 - h, so that its leaves land on the bottom level;
+// candidates of that depth are taken round-robin, those with the fewest children first.  Returns the post-order
+// (new id -> old id) and rewrites `parent` in new ids.
+static std::vector<int32_t> join_forest(std::vector<int32_t> &parent) {
+    const int32_t nf = (int32_t)parent.size();
+    std::vector<int32_t> depth(nf, 0), root_of(nf, 0), height(nf, 0), nchild(nf, 0);
+    for (int32_t f = nf - 1; f >= 0; --f) {           // parents have larger ids
+        const int32_t p = parent[f];
+        depth[f] = p < 0 ? 0 : depth[p] + 1;
+        root_of[f] = p < 0 ? f : root_of[p];
+        if (p >= 0) ++nchild[p];
+    }
+    int32_t H = 0;
+    for (int32_t f = 0; f < nf; ++f) {
+        height[root_of[f]] = std::max(height[root_of[f]], depth[f] + 1);
+        H = std::max(H, depth[f] + 1);
+    }
+    std::vector<std::vector<int32_t>> cand(H);
+    for (int pass = 0; pass <= 2; ++pass)
+        for (int32_t f = 0; f < nf; ++f)
+            if (height[root_of[f]] == H && std::min(nchild[f], 2) == pass) cand[depth[f]].push_back(f);
+    std::vector<size_t> next(H, 0);
+    for (int32_t f = 0; f < nf; ++f) {
+        if (parent[f] >= 0 || height[f] == H) continue;
+        const int32_t dp = std::max(0, H - 1 - height[f]);
+        parent[f] = cand[dp][next[dp]++ % cand[dp].size()];
+    }
+    // post-order renumbering (roots and children in ascending old id: the result depends on the input only)
+    std::vector<int32_t> cptr(nf + 1, 0), cidx(nf);
+    for (int32_t f = 0; f < nf; ++f) if (parent[f] >= 0) ++cptr[parent[f] + 1];
+    for (int32_t f = 0; f < nf; ++f) cptr[f + 1] += cptr[f];
+    {
+        std::vector<int32_t> fillp(cptr.begin(), cptr.end() - 1);
+        for (int32_t f = 0; f < nf; ++f) if (parent[f] >= 0) cidx[fillp[parent[f]]++] = f;
+    }
+    std::vector<int32_t> new_id(nf, -1), order;
+    order.reserve(nf);
+    std::vector<std::pair<int32_t, int32_t>> stack;     // (front, next child slot)
+    for (int32_t r = 0; r < nf; ++r) {
+        if (parent[r] >= 0) continue;
+        stack.push_back({r, cptr[r]});
+        while (!stack.empty()) {
+            auto &top = stack.back();
+            if (top.second < cptr[top.first + 1]) {
+                const int32_t ch = cidx[top.second++];
+                stack.push_back({ch, cptr[ch]});
+            } else {
+                new_id[top.first] = (int32_t)order.size();
+                order.push_back(top.first);
+                stack.pop_back();
+            }
+        }
+    }
+    if ((int32_t)order.size() != nf) throw std::runtime_error("direct_symbolic: forest join lost fronts");
+    std::vector<int32_t> np(nf);
+    for (int32_t q = 0; q < nf; ++q) np[q] = parent[order[q]] < 0 ? -1 : new_id[parent[order[q]]];
+    parent.swap(np);
+    return order;
+}
+
 void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double *coords, const int64_t *adj_ptr,
-                     const int32_t *adj, int leaf_size, DirectSym &out) {
+                     const int32_t *adj, int leaf_size, DirectSym &out, const uint8_t *row_class, int n_classes,
+                     const uint8_t *class_diagonal) {
     out.n = n;
     out.max_children = 0; out.factor_entries = 0; out.factor_flops = 0; out.max_front = 0;
     if (n == 0 || nv == 0) {
@@ -245,13 +362,7 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         out.level_ptr.assign(1, 0);
         return;
     }
-    Builder b;
-    b.nv = nv; b.vstart = vstart; b.coords = coords; b.adj_ptr = adj_ptr; b.adj = adj; b.leaf_size = leaf_size;
-    b.region.swap(out.s_region);
-    b.region.assign(nv, 0);
-    std::vector<int32_t> all(nv);
-    std::iota(all.begin(), all.end(), 0);
-    SubTree tree;
+    const int C = (row_class && n_classes > 1) ? n_classes : 1;
     const bool timing = getenv("PN_DEBUG_TIMING") != nullptr;
     auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     double t0 = now();
@@ -261,15 +372,39 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         fprintf(stderr, "[pn-time] direct_symbolic    %-28s %8.2f ms\n", what, t - t0);
         t0 = t;
     };
+    // rows of every (vertex, class); with classes the leaves are scaled so that the largest class keeps about
+    // 6 * leaf_size pivots per leaf
+    std::vector<uint8_t> vc_cnt;
+    int leaf_nodes = leaf_size;
+    if (C > 1) {
+        vc_cnt.assign((size_t)nv * C, 0);
+        std::vector<int64_t> rows_c(C, 0);
+#pragma omp parallel for schedule(static)
+        for (int32_t v = 0; v < nv; ++v)
+            for (int32_t r = vstart[v]; r < vstart[v + 1]; ++r) ++vc_cnt[(size_t)v * C + row_class[r]];
+        for (int64_t r = 0; r < n; ++r) ++rows_c[row_class[r]];
+        int64_t big = 1;
+        for (int c = 0; c < C; ++c) big = std::max(big, rows_c[c]);
+        leaf_nodes = (int)std::max<int64_t>(leaf_size, (6 * (int64_t)leaf_size * nv + big / 2) / big);
+    }
+    auto cnt_of = [&](int32_t v, int c) -> int32_t { return C > 1 ? vc_cnt[(size_t)v * C + c] : vstart[v + 1] - vstart[v]; };
+
+    Builder b;
+    b.nv = nv; b.vstart = vstart; b.coords = coords; b.adj_ptr = adj_ptr; b.adj = adj; b.leaf_size = leaf_nodes;
+    b.region.swap(out.s_region);
+    b.region.assign(nv, 0);
+    std::vector<int32_t> all(nv);
+    std::iota(all.begin(), all.end(), 0);
+    SubTree tree;
 #pragma omp parallel
 #pragma omp single
     tree = b.dissect(all);
     lap("dissect");
     std::vector<std::vector<int32_t>> &front_verts = tree.verts;
-    std::vector<int32_t> &parent_of = tree.parent;
-    const int32_t nf = (int32_t)front_verts.size();
+    std::vector<int32_t> &nparent = tree.parent;
+    const int32_t nf0 = (int32_t)front_verts.size();       // fronts of the node tree
 
-    // vertex elimination positions (post-order front ids = elimination order) and DOF positions
+    // node level: elimination order of the vertices (post-order front ids = elimination order)
     b.region.swap(out.s_region);                       // keep the capacity for the next call
     std::vector<int32_t> &vfront = out.s_vfront, &vorder = out.s_vorder;      // vorder: rank of the vertex in elimination order
     vfront.resize(nv); vorder.resize(nv);
@@ -277,33 +412,153 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
     vert_seq.clear();
     vert_seq.reserve(nv);
     std::vector<int32_t> &f_vbeg = out.s_f_vbeg;
-    f_vbeg.assign(nf + 1, 0);
-    for (int32_t f = 0; f < nf; ++f) {
+    f_vbeg.assign(nf0 + 1, 0);
+    for (int32_t f = 0; f < nf0; ++f) {
         f_vbeg[f] = (int32_t)vert_seq.size();
         for (int32_t v : front_verts[f]) { vfront[v] = f; vorder[v] = (int32_t)vert_seq.size(); vert_seq.push_back(v); }
     }
-    f_vbeg[nf] = (int32_t)vert_seq.size();
+    f_vbeg[nf0] = (int32_t)vert_seq.size();
     if ((int32_t)vert_seq.size() != nv) throw std::runtime_error("direct_symbolic: vertices lost in dissection");
-    std::vector<int32_t> &vdofpos = out.s_vdofpos;     // DOF elimination position of vertex with order r
-    vdofpos.assign(nv + 1, 0);
-    for (int32_t r = 0; r < nv; ++r) {
-        int32_t v = vert_seq[r];
-        vdofpos[r + 1] = vdofpos[r] + (vstart[v + 1] - vstart[v]);
+    lap("orders");
+
+    // boundary vertex sets of the node tree, bottom-up (as vertex orders, ascending); fronts of one depth are independent
+    std::vector<std::vector<int32_t>> bnd(nf0);
+    {
+        std::vector<std::vector<int32_t>> children(nf0);
+        for (int32_t f = 0; f < nf0; ++f) if (nparent[f] >= 0) children[nparent[f]].push_back(f);
+        std::vector<int32_t> depth(nf0, 0);
+        int32_t maxdepth = 0;
+        for (int32_t f = nf0 - 1; f >= 0; --f) {
+            depth[f] = nparent[f] < 0 ? 0 : depth[nparent[f]] + 1;
+            maxdepth = std::max(maxdepth, depth[f]);
+        }
+        std::vector<std::vector<int32_t>> by_depth(maxdepth + 1);
+        for (int32_t f = 0; f < nf0; ++f) by_depth[depth[f]].push_back(f);
+        int bad_root = 0;
+        for (int32_t dd = maxdepth; dd >= 0; --dd) {
+            const std::vector<int32_t> &grp = by_depth[dd];
+#pragma omp parallel for schedule(dynamic, 16) if (grp.size() > 32)
+            for (int64_t q = 0; q < (int64_t)grp.size(); ++q) {
+                const int32_t f = grp[q];
+                int32_t vend = f_vbeg[f + 1];
+                std::vector<int32_t> cur;
+                for (int32_t v : front_verts[f])
+                    for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k) {
+                        int32_t o = vorder[adj[k]];
+                        if (o >= vend) cur.push_back(o);
+                    }
+                std::sort(cur.begin(), cur.end());
+                cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
+                for (int32_t c : children[f]) {
+                    std::vector<int32_t> merged;
+                    merged.reserve(cur.size() + bnd[c].size());
+                    auto first = std::lower_bound(bnd[c].begin(), bnd[c].end(), vend);
+                    std::set_union(cur.begin(), cur.end(), first, bnd[c].end(), std::back_inserter(merged));
+                    cur.swap(merged);
+                }
+                bnd[f].swap(cur);
+                // every boundary vertex must live in an ancestor; a root must have an empty boundary
+                if (nparent[f] < 0 && !bnd[f].empty()) {
+#pragma omp atomic write
+                    bad_root = 1;
+                }
+            }
+        }
+        if (bad_root) throw std::runtime_error("direct_symbolic: root front with a non-empty boundary");
     }
+    lap("boundary sets");
+
+    // ---- fronts = (node front, class) pairs that own at least one pivot, in node-front order (children before parents
+    // within every class); the rows of a diagonal class become runs of 6 * leaf_size pivots without boundary -------------
+    struct ClassFront { int32_t node_front, cls, run; };      // run >= 0: index into diag_runs instead of a node front
+    std::vector<ClassFront> cf;
+    std::vector<int32_t> parent_of;
+    std::vector<std::vector<int32_t>> diag_runs;              // rows (K11 numbering) of each run
+    std::vector<int32_t> order;                               // final front id -> index into cf
+    if (C == 1) {
+        cf.resize(nf0);
+        for (int32_t f = 0; f < nf0; ++f) cf[f] = {f, 0, -1};
+        parent_of = nparent;
+        order.resize(nf0);
+        std::iota(order.begin(), order.end(), 0);
+    } else {
+        std::vector<uint8_t> diag(C, 0);
+        for (int c = 0; c < C; ++c) diag[c] = class_diagonal ? class_diagonal[c] : 0;
+        std::vector<int32_t> cf_id((size_t)nf0 * C, -1);
+        std::vector<uint8_t> owns((size_t)nf0 * C, 0);
+#pragma omp parallel for schedule(static)
+        for (int32_t f = 0; f < nf0; ++f)
+            for (int32_t v : front_verts[f])
+                for (int c = 0; c < C; ++c)
+                    if (!diag[c] && vc_cnt[(size_t)v * C + c]) owns[(size_t)f * C + c] = 1;
+        for (int32_t f = 0; f < nf0; ++f)
+            for (int c = 0; c < C; ++c)
+                if (owns[(size_t)f * C + c]) { cf_id[(size_t)f * C + c] = (int32_t)cf.size(); cf.push_back({f, c, -1}); }
+        parent_of.assign(cf.size(), -1);
+        for (size_t q = 0; q < cf.size(); ++q) {
+            int32_t p = nparent[cf[q].node_front];
+            while (p >= 0 && cf_id[(size_t)p * C + cf[q].cls] < 0) p = nparent[p];
+            parent_of[q] = p < 0 ? -1 : cf_id[(size_t)p * C + cf[q].cls];
+        }
+        const int64_t run_len = 6 * (int64_t)leaf_size;
+        for (int c = 0; c < C; ++c) {
+            if (!diag[c]) continue;
+            std::vector<int32_t> cur;
+            for (int64_t r = 0; r < n; ++r) {
+                if (row_class[r] != c) continue;
+                cur.push_back((int32_t)r);
+                if ((int64_t)cur.size() == run_len) {
+                    cf.push_back({-1, c, (int32_t)diag_runs.size()});
+                    parent_of.push_back(-1);
+                    diag_runs.push_back(std::move(cur));
+                    cur.clear();
+                }
+            }
+            if (!cur.empty()) {
+                cf.push_back({-1, c, (int32_t)diag_runs.size()});
+                parent_of.push_back(-1);
+                diag_runs.push_back(std::move(cur));
+            }
+        }
+        order = join_forest(parent_of);
+    }
+    const int32_t nf = (int32_t)cf.size();
+    lap("class fronts");
+
+    // pivots per front, elimination positions
+    std::vector<int32_t> ns_of(nf), pos_start(nf + 1, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t q = 0; q < nf; ++q) {
+        const ClassFront &F = cf[order[q]];
+        int32_t ns = 0;
+        if (F.run >= 0) ns = (int32_t)diag_runs[F.run].size();
+        else for (int32_t v : front_verts[F.node_front]) ns += cnt_of(v, F.cls);
+        ns_of[q] = ns;
+    }
+    for (int32_t q = 0; q < nf; ++q) pos_start[q + 1] = pos_start[q] + ns_of[q];
+    if (pos_start[nf] != n) throw std::runtime_error("direct_symbolic: rows lost in the class expansion");
     out.perm_pos.resize(n);
     out.dof_front.resize(n);
-#pragma omp parallel for schedule(static)
-    for (int32_t r = 0; r < nv; ++r) {            // every K11 row belongs to exactly one vertex
-        int32_t v = vert_seq[r];
-        for (int32_t k = 0; k < vstart[v + 1] - vstart[v]; ++k) {
-            out.perm_pos[vstart[v] + k] = vdofpos[r] + k;
-            out.dof_front[vstart[v] + k] = vfront[v];
+    std::vector<int32_t> &vcpos = out.s_vdofpos;       // position of the first row of (vertex, class)
+    vcpos.assign((size_t)nv * C, -1);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t q = 0; q < nf; ++q) {
+        const ClassFront &F = cf[order[q]];
+        int32_t pos = pos_start[q];
+        if (F.run >= 0) {
+            for (int32_t r : diag_runs[F.run]) { out.perm_pos[r] = pos++; out.dof_front[r] = q; }
+            continue;
+        }
+        for (int32_t v : front_verts[F.node_front]) {
+            if (!cnt_of(v, F.cls)) continue;
+            vcpos[(size_t)v * C + F.cls] = pos;
+            for (int32_t r = vstart[v]; r < vstart[v + 1]; ++r)
+                if (C == 1 || row_class[r] == F.cls) { out.perm_pos[r] = pos++; out.dof_front[r] = q; }
         }
     }
+    lap("positions");
 
-    lap("orders");
-    // boundary vertex sets, bottom-up (as vertex orders, ascending); fronts of one depth are independent
-    std::vector<std::vector<int32_t>> bnd(nf);
+    // fronts, index lists
     std::vector<std::vector<int32_t>> children(nf);
     for (int32_t f = 0; f < nf; ++f) if (parent_of[f] >= 0) children[parent_of[f]].push_back(f);
     std::vector<int32_t> depth(nf, 0);
@@ -312,53 +567,24 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         depth[f] = parent_of[f] < 0 ? 0 : depth[parent_of[f]] + 1;
         maxdepth = std::max(maxdepth, depth[f]);
     }
-    std::vector<std::vector<int32_t>> by_depth(maxdepth + 1);
-    for (int32_t f = 0; f < nf; ++f) by_depth[depth[f]].push_back(f);
-    int bad_root = 0;
-    for (int32_t dd = maxdepth; dd >= 0; --dd) {
-        const std::vector<int32_t> &grp = by_depth[dd];
-#pragma omp parallel for schedule(dynamic, 16) if (grp.size() > 32)
-        for (int64_t q = 0; q < (int64_t)grp.size(); ++q) {
-            const int32_t f = grp[q];
-            int32_t vend = f_vbeg[f + 1];
-            std::vector<int32_t> cur;
-            for (int32_t v : front_verts[f])
-                for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k) {
-                    int32_t o = vorder[adj[k]];
-                    if (o >= vend) cur.push_back(o);
-                }
-            std::sort(cur.begin(), cur.end());
-            cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
-            for (int32_t c : children[f]) {
-                std::vector<int32_t> merged;
-                merged.reserve(cur.size() + bnd[c].size());
-                auto first = std::lower_bound(bnd[c].begin(), bnd[c].end(), vend);
-                std::set_union(cur.begin(), cur.end(), first, bnd[c].end(), std::back_inserter(merged));
-                cur.swap(merged);
-            }
-            bnd[f].swap(cur);
-            // every boundary vertex must live in an ancestor; a root must have an empty boundary
-            if (parent_of[f] < 0 && !bnd[f].empty()) {
-#pragma omp atomic write
-                bad_root = 1;
-            }
-        }
-    }
-    if (bad_root) throw std::runtime_error("direct_symbolic: root front with a non-empty boundary");
-
-    lap("boundary sets");
-    // fronts, index lists
     out.fronts.assign(nf, FrontSym());
+    std::vector<int32_t> nb_of(nf, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t q = 0; q < nf; ++q) {
+        const ClassFront &F = cf[order[q]];
+        if (F.run >= 0) continue;
+        int32_t nbd = 0;
+        for (int32_t o : bnd[F.node_front]) nbd += cnt_of(vert_seq[o], F.cls);
+        nb_of[q] = nbd;
+    }
     int64_t total_idx = 0, total_rel = 0;
     for (int32_t f = 0; f < nf; ++f) {
         FrontSym &F = out.fronts[f];
         F.parent = parent_of[f];
         F.depth = depth[f];
-        F.pos_start = vdofpos[f_vbeg[f]];
-        F.ns = vdofpos[f_vbeg[f + 1]] - vdofpos[f_vbeg[f]];
-        int32_t nbd = 0;
-        for (int32_t o : bnd[f]) nbd += vdofpos[o + 1] - vdofpos[o];
-        F.nb = nbd;
+        F.pos_start = pos_start[f];
+        F.ns = ns_of[f];
+        F.nb = nb_of[f];
         F.idx_off = total_idx;
         F.rel_off = total_rel;
         total_idx += F.ns + F.nb;
@@ -385,10 +611,15 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
 #pragma omp parallel for schedule(dynamic, 64)
     for (int32_t f = 0; f < nf; ++f) {
         const FrontSym &F = out.fronts[f];
+        const ClassFront &K = cf[order[f]];
         int64_t o = F.idx_off;
         for (int32_t k = 0; k < F.ns; ++k) out.fpos[o++] = F.pos_start + k;
-        for (int32_t vo : bnd[f])
-            for (int32_t p = vdofpos[vo]; p < vdofpos[vo + 1]; ++p) out.fpos[o++] = p;
+        if (K.run < 0)
+            for (int32_t vo : bnd[K.node_front]) {
+                const int32_t v = vert_seq[vo], cnt = cnt_of(v, K.cls);
+                const int32_t p0 = vcpos[(size_t)v * C + K.cls];
+                for (int32_t k = 0; k < cnt; ++k) out.fpos[o++] = p0 + k;
+            }
         for (int64_t k = F.idx_off; k < F.idx_off + F.ns + F.nb; ++k) out.fidx[k] = pos_dof[out.fpos[k]];
     }
     lap("index lists");

@@ -70,10 +70,40 @@ struct VertexGraphScratch {
     std::vector<int64_t> deg, ptr, fill, cnt;
 };
 
-// Vertex graph: vertex v owns K11 rows vstart[v] .. vstart[v+1]; coords[3 v ..]; adjacency in CSR
-// (no self loops needed; symmetric).  leaf_size = vertices per leaf region.
+// DOF-type classes.  The reference stores no exact zeros (`FEModel3D.py:130`), so K11 of a flat shell model in an
+// axis plane is reducible: membrane translations, the bending triple (normal translation + the two in-plane
+// rotations) and the drilling rotation never meet in a stored entry.  A graph-based ordering of the scalar matrix
+// (COLAMD inside the reference's `spsolve`, `Analysis.py:217`) sees that by itself; a node-based dissection does not,
+// and factorises fronts that are block diagonal as dense ones (6^3 = 216 against 3^3 + 2^3 = 35 per node triple).  `of_type[k]` is the class of global
+// DOF type k (DX DY DZ RX RY RZ); every separator / leaf of the node dissection then yields one front per class.
+struct DofClasses {
+    int n = 1;
+    uint8_t of_type[6] = {0, 0, 0, 0, 0, 0};
+    // 1: the class holds only drilling rotations (`Quad3D.py:617`, `Plate3D.py:307`: a weak spring on the diagonal),
+    // which couple to nothing -- its rows are cut into leaves without boundary
+    uint8_t diagonal[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct ConnView;
+// Classes predicted from the element list alone (so the ordering can start before anything is assembled): shells that
+// lie in a plane normal to global axis g couple {the two in-plane translations}, {translation g + the two in-plane
+// rotations} and {rotation g} separately, whatever their in-plane orientation; a shell in general position, or any
+// line element, couples everything (one class).  The prediction is verified against the assembled pattern on the
+// device (k_entry_maps flags an entry that joins two classes) and the analysis is redone with one class if it fails.
+DofClasses predict_dof_classes(const double *xyz, const std::vector<ConnView> &shells, int64_t n_line_elements);
+
+// Vertex graph: vertex v (a node with free DOFs) owns K11 rows vstart[v] .. vstart[v+1]; coords[3 v ..]; adjacency in
+// CSR (no self loops needed; symmetric).  leaf_size = vertices per leaf region.
+// With `row_class` (class of every K11 row, n_classes > 1) the node graph is still dissected once, and every separator
+// / leaf then yields one front per class that has pivots there: pivots and boundary of (front, class) are the rows of
+// that class at the front's vertices / boundary vertices, its parent is the nearest ancestor that owns pivots of the
+// class.  The rows of a diagonal class become runs of 6 * leaf_size pivots without boundary.  The resulting forest is
+// joined (join_forest in the .cpp): roots of the tallest trees share the top level, a shorter tree hangs, as an extra
+// child without update matrix, from a front at the depth that puts its leaves on the bottom level.  Leaves are scaled
+// so that the largest class keeps about 6 * leaf_size pivots per leaf.
 void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double *coords, const int64_t *adj_ptr,
-                     const int32_t *adj, int leaf_size, DirectSym &out);
+                     const int32_t *adj, int leaf_size, DirectSym &out, const uint8_t *row_class = nullptr,
+                     int n_classes = 1, const uint8_t *class_diagonal = nullptr);
 
 // Builds the vertex graph of the free DOFs from element connectivity.
 // newidx[dof] >= 0 gives the K11 row of a free DOF.  `conn` lists for each element kind are

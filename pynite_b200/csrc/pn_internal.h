@@ -176,6 +176,8 @@ enum PathCounter {
     PC_SWEEP_OVERLAPPED,   // factorisations whose first forward sweep ran behind them on the side stream
     PC_LOOKAHEAD,          // front groups factorised with the look-ahead schedule (trailing update split in two streams)
     PC_SWEEP_LL_GEMM,      // boundary-row GEMM launches beside k_ll_sweep (k_solve_forward_boundary / k_solve_boundary)
+    PC_DOF_CLASSES,        // DOF-type classes the ordering dissected separately (1: node-based dissection)
+    PC_DOF_CLASS_REJECTS,  // analyses redone with one class because an assembled entry joined two predicted classes
     PC_COUNT
 };
 
@@ -259,6 +261,10 @@ struct Ctx {
     PcgWork *pcg = nullptr;
     FastAssembly *fast = nullptr;
     int opt_host_threads = 0;       // pn_set_option("host_threads"): OpenMP threads of the host-worker jobs (0 = default)
+    // pn_set_option("dof_classes"): 1 = the ordering of the direct solver treats DOF-type classes that never meet in a
+    // stored entry as separate problems (predicted from the element list, verified against the assembled pattern);
+    // 0 = node-based dissection only; 2 = self-test: predicts one class per DOF type, which the verification must reject
+    int opt_dof_classes = 1;
     bool opt_spmm_grouped = false;  // pn_set_option("spmm_grouped"): K11 SpMM with the rows of a node sharing their X-row loads
     bool opt_assembly_graph = true; // pn_set_option("assembly_graph"): replay the numeric assembly as one CUDA graph
     int64_t n_assemblies = 0;       // numeric assemblies on the current pattern

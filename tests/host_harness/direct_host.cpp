@@ -19,10 +19,11 @@ extern "C" {
 // stats[4] = #levels
 int hh_direct_solve(int64_t n, const int32_t *indptr, const int32_t *indices, const double *vals, int32_t nv,
                     const int32_t *vstart, const double *coords, const int64_t *adj_ptr, const int32_t *adj, int leaf,
-                    int s, const double *B, double *X, double *stats) {
+                    int s, const double *B, double *X, double *stats, const uint8_t *row_class, int n_classes,
+                    const uint8_t *class_diagonal) {
     DirectSym S;
     try {
-        direct_symbolic(n, nv, vstart, coords, adj_ptr, adj, leaf, S);
+        direct_symbolic(n, nv, vstart, coords, adj_ptr, adj, leaf, S, row_class, n_classes, class_diagonal);
     } catch (std::exception &e) {
         fprintf(stderr, "symbolic failed: %s\n", e.what());
         return -1;
@@ -136,6 +137,29 @@ int hh_direct_solve(int64_t n, const int32_t *indptr, const int32_t *indices, co
                 for (int j = 0; j < s; ++j) Y[(size_t)S.fidx[fs.idx_off + a] * s + j] = w[(size_t)a * s + j];
         }
     memcpy(X, Y.data(), sizeof(double) * n * s);
+    // every child exactly one level below its parent, one root, subtrees contiguous in front order
+    {
+        std::vector<int> level_of(nf, -1);
+        for (int l = 0; l < nl; ++l)
+            for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) level_of[S.level_fronts[q]] = l;
+        int roots = 0;
+        for (int f = 0; f < nf; ++f) {
+            const FrontSym &fs = S.fronts[f];
+            if (fs.parent < 0) { ++roots; continue; }
+            if (fs.parent <= f || level_of[fs.parent] != level_of[f] + 1) return -4;
+        }
+        stats[5] = roots;
+        stats[6] = S.max_children;
+    }
     return 0;
+}
+
+// The DOF-type classes predicted from the shell lists (the library's own predict_dof_classes).
+int hh_predict_classes(const double *xyz, int64_t n_quads, const int32_t *quads, int64_t n_plates, const int32_t *plates,
+                       int64_t n_line, uint8_t *of_type, uint8_t *diagonal) {
+    std::vector<ConnView> shells = {{n_quads, 4, quads, nullptr}, {n_plates, 4, plates, nullptr}};
+    DofClasses cls = predict_dof_classes(xyz, shells, n_line);
+    for (int k = 0; k < 6; ++k) { of_type[k] = cls.of_type[k]; diagonal[k] = cls.diagonal[k]; }
+    return cls.n;
 }
 }

@@ -589,6 +589,7 @@ def test_midsize_plate_150_against_oracle(eng):
     D, R, st = eng.solve_linear(eng.make_opts())
     ctr = eng.counters()
     _production_paths_taken(ctr, want_later_groups=True)
+    assert ctr['dof_classes'] == 3 and ctr['dof_class_rejects'] == 0, ctr      # membrane / bending / drilling fronts
     K = om.ke_csr(A)
     indptr, indices = eng.pattern()
     assert np.array_equal(indptr, K.indptr) and np.array_equal(indices, K.indices)
@@ -599,6 +600,76 @@ def test_midsize_plate_150_against_oracle(eng):
     for c in range(2):
         assert errs[c] < TOL_D, errs
         assert rel_err(R[c], Ro[c].reshape(-1)) < TOL_D
+
+
+@pytest.mark.parametrize('case', ['plate_xy', 'plate_yz', 'mat', 'frame'])
+def test_dof_class_ordering_equals_node_ordering(eng, case):
+    """`pn_set_option("dof_classes")`: the class-split ordering (1, default), the node-based ordering (0) and a prediction
+    the device verification has to reject (2) give the same displacements and reactions; flat shell models use three
+    classes, a frame keeps one."""
+    from pynite_b200 import synthetic
+    if case == 'plate_xy':
+        A = synthetic.quad_plate_arrays(n=72, n_combos=3)
+    elif case == 'mat':
+        A = synthetic.quad_plate_arrays(n=60, n_combos=2, mat_springs=0.1)
+    elif case == 'frame':
+        A = synthetic.moment_frame_arrays(bays_x=4, bays_z=3, stories=6, n_combos=2)
+    else:
+        A, _, _ = load_fixture('quad_mesh_yz_ortho')
+    out = {}
+    try:
+        for mode in (1, 0, 2):
+            eng.set_option('dof_classes', mode)
+            _upload(eng, A)
+            eng.reset_stats()
+            D, R, st = eng.solve_linear(eng.make_opts())
+            out[mode] = (D, R, eng.counters(), st.max_rel_residual)
+    finally:
+        eng.set_option('dof_classes', 1)
+    shells = case != 'frame'
+    assert out[1][2]['dof_classes'] == (3 if shells else 1), out[1][2]
+    assert out[0][2]['dof_classes'] == 1 and out[0][2]['dof_class_rejects'] == 0
+    assert out[2][2]['dof_classes'] == 1 and out[2][2]['dof_class_rejects'] == 1, out[2][2]
+    for mode in (0, 2):
+        assert rel_err(out[mode][0], out[1][0]) < 1e-10 and rel_err(out[mode][1], out[1][1]) < 1e-9, (mode, case)
+    assert np.array_equal(out[0][0], out[2][0])          # the rejected prediction falls back to exactly the node ordering
+    if shells:
+        Do, Ro = om.solve_linear(A)
+        for c in range(len(Do)):
+            assert rel_err(out[1][0][c], Do[c].reshape(-1)) < TOL_D
+
+
+def test_subtree_distributed_solve_on_eight_ranks():
+    """The class-split tree (two roots on the top level, cost-balanced cut) shared out over 8 ranks, against one rank."""
+    from pynite_b200 import distsolve, synthetic
+    from pynite_b200.engine import Engine
+    A = synthetic.quad_plate_arrays(n=96, n_combos=3)
+    e0 = Engine(0)
+    try:
+        _upload(e0, A)
+        D0, R0, _ = e0.solve_linear(e0.make_opts())
+    finally:
+        e0.close()
+    world = 8
+    group = distsolve.LocalGroup(world)
+    engines = [Engine(0) for _ in range(world)]
+
+    def rank_fn(r):
+        e = engines[r]
+        group.attach(e, r)
+        _upload(e, A)
+        e.reset_stats()
+        D, R, st = e.solve_linear(e.make_opts())
+        return D, R, e.counters()
+    try:
+        out = group.run(rank_fn)
+    finally:
+        for e in engines:
+            e.close()
+    assert not group.errors
+    for r, (D, R, ctr) in enumerate(out):
+        assert ctr['dist_cut_level'] >= 0 and ctr['dof_classes'] == 3, ctr
+        assert np.array_equal(D, D0) and np.array_equal(R, R0), r
 
 
 def test_midsize_plate_256_against_spsolve_and_refined_splu(eng):

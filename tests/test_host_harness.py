@@ -185,8 +185,60 @@ def test_direct_symbolic_host(libs, name, leaf):
     rc = dh.hh_direct_solve(ct.c_int64(len(d1)), K11.indptr.ctypes.data_as(I32P), K11.indices.ctypes.data_as(I32P),
                             _p(np.ascontiguousarray(K11.data)), ct.c_int32(len(vstart) - 1),
                             vstart.ctypes.data_as(I32P), _p(coords), adj_ptr.ctypes.data_as(I64P),
-                            adj.ctypes.data_as(I32P), leaf, s, _p(B), _p(X), _p(stats))
+                            adj.ctypes.data_as(I32P), leaf, s, _p(B), _p(X), _p(stats), None, 1, None)
     assert rc == 0
     Xs = spla.splu(K11.tocsc()).solve(B)
     assert rel_err(X, Xs) < 1e-8
     assert stats[2] >= 1 and stats[4] >= 1
+
+
+@pytest.mark.parametrize('name,leaf,expect', [('quad_mesh_xy', 1, 3), ('quad_mesh_yz_ortho', 1, 3), ('plate_mesh_xz', 2, 3),
+                                              ('mat_foundation', 1, 3), ('skew_shell', 2, 1), ('mixed_building', 2, 1)])
+def test_direct_symbolic_dof_classes(libs, name, leaf, expect):
+    """DOF-type classes (pn_direct_symbolic.h, DofClasses): a flat shell model in an axis plane is ordered as three
+    independent problems (membrane, bending, drilling) on one node dissection; models with line elements or shells in
+    general position keep one class.  The library's own predictor, the host multifrontal emulation on the resulting
+    tree against SuperLU, and -- the property the device verifies with k_entry_maps -- no stored K11 entry joins two
+    classes."""
+    _, dh = libs
+    A, ref, _ = load_fixture(name)
+    d1, d2, _ = om.partition_D(A)
+    n1 = len(d1)
+    K11 = sps.csr_matrix((ref['K11_data'], ref['K11_indices'], ref['K11_indptr']), shape=(n1, n1))
+    n_line = len(A.spring_ij.reshape(-1, 2)) + len(A.mem_ij.reshape(-1, 2))
+    quads = np.ascontiguousarray(A.quad_ijmn.reshape(-1, 4).astype(np.int32))
+    plates = np.ascontiguousarray(A.plate_ijmn.reshape(-1, 4).astype(np.int32))
+    xyz = np.ascontiguousarray(A.xyz, dtype=np.float64)
+    of_type = np.zeros(6, dtype=np.uint8)
+    diagonal = np.zeros(6, dtype=np.uint8)
+    U8P = ct.POINTER(ct.c_uint8)
+    ncls = dh.hh_predict_classes(_p(xyz), ct.c_int64(len(quads)), quads.ctypes.data_as(I32P), ct.c_int64(len(plates)),
+                                 plates.ctypes.data_as(I32P), ct.c_int64(n_line), of_type.ctypes.data_as(U8P),
+                                 diagonal.ctypes.data_as(U8P))
+    assert ncls == expect
+    if ncls == 1:
+        return
+    assert diagonal[:ncls].sum() == 1
+    # no stored entry joins two classes; a diagonal class has no off-diagonal entry at all
+    row_class = np.ascontiguousarray(of_type[np.asarray(d1) % 6])
+    C = K11.tocoo()
+    assert np.array_equal(row_class[C.row], row_class[C.col])
+    off = C.row != C.col
+    assert not diagonal[row_class[C.row[off]]].any()
+    vstart, coords, adj_ptr, adj = _vertex_graph(K11, A, d1)
+    s = 3
+    rng = np.random.default_rng(1)
+    B = np.ascontiguousarray(rng.standard_normal((n1, s)))
+    X = np.empty_like(B)
+    out = []
+    for args in ((row_class.ctypes.data_as(U8P), ncls, diagonal.ctypes.data_as(U8P)), (None, 1, None)):
+        stats = np.zeros(8)
+        rc = dh.hh_direct_solve(ct.c_int64(n1), K11.indptr.ctypes.data_as(I32P), K11.indices.ctypes.data_as(I32P),
+                                _p(np.ascontiguousarray(K11.data)), ct.c_int32(len(vstart) - 1), vstart.ctypes.data_as(I32P),
+                                _p(coords), adj_ptr.ctypes.data_as(I64P), adj.ctypes.data_as(I32P), leaf, s, _p(B), _p(X),
+                                _p(stats), *args)
+        assert rc == 0
+        assert rel_err(X, spla.splu(K11.tocsc()).solve(B)) < 1e-8
+        out.append(stats.copy())
+    # fewer factor entries and flops than the node-based ordering of the same matrix
+    assert out[0][0] < out[1][0] and out[0][1] < out[1][1]

@@ -4,6 +4,7 @@
 #include "pn_direct_symbolic.h"
 #include <chrono>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 using namespace pn;
 int main(int argc, char **argv) {
@@ -29,16 +30,34 @@ int main(int argc, char **argv) {
     std::vector<int64_t> adj_ptr;
     VertexGraphScratch scratch;
     DirectSym S;
+    std::vector<uint8_t> row_class(next);
+    const bool use_classes = argc > 2 && atoi(argv[2]) != 0;      // second argument 1: DOF-type classes (DofClasses)
+    const int leaf = argc > 3 ? atoi(argv[3]) : 24;
     for (int rep = 0; rep < 5; ++rep) {
         auto t0 = std::chrono::steady_clock::now();
         std::vector<ConnView> conn = {{(int64_t)n * n, 4, quads.data(), nullptr}};
+        DofClasses cls;
+        if (use_classes) cls = predict_dof_classes(xyz.data(), conn, 0);
         build_vertex_graph(nn, newidx.data(), xyz.data(), conn, vstart, coords, adj_ptr, adj, &scratch);
         auto t1 = std::chrono::steady_clock::now();
-        direct_symbolic(next, (int32_t)vstart.size() - 1, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), 24, S);
+        if (cls.n > 1)
+            for (int64_t dd = 0; dd < 6 * nn; ++dd) if (newidx[dd] >= 0) row_class[newidx[dd]] = cls.of_type[dd % 6];
+        direct_symbolic(next, (int32_t)vstart.size() - 1, vstart.data(), coords.data(), adj_ptr.data(), adj.data(), leaf, S,
+                        cls.n > 1 ? row_class.data() : nullptr, cls.n, cls.diagonal);
         auto t2 = std::chrono::steady_clock::now();
-        printf("vertex graph %.1f ms, direct_symbolic %.1f ms, fronts %zu, factor entries %lld\n",
-               std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
-               S.fronts.size(), (long long)S.factor_entries);
+        printf("classes %d, vertex graph %.1f ms, direct_symbolic %.1f ms, fronts %zu, levels %zu, factor entries %lld, flops %.3e, max children %d\n",
+               cls.n, std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
+               S.fronts.size(), S.level_ptr.size() - 1, (long long)S.factor_entries, S.factor_flops, S.max_children);
+    }
+    for (size_t l = 0; l + 1 < S.level_ptr.size(); ++l) {
+        int mx_ns = 0, mx_n = 0; double fl = 0;
+        for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+            const FrontSym &f = S.fronts[S.level_fronts[q]];
+            mx_ns = std::max(mx_ns, f.ns); mx_n = std::max(mx_n, f.ns + f.nb);
+            double ns = f.ns, nb = f.nb;
+            fl += 2.0 / 3.0 * ns * ns * ns + 2.0 * ns * ns * nb + 2.0 * ns * nb * nb;
+        }
+        printf("level %2zu: %6d fronts, max ns %5d, max n %5d, %8.2f GFLOP (LU)\n", l, S.level_ptr[l + 1] - S.level_ptr[l], mx_ns, mx_n, fl * 1e-9);
     }
     return 0;
 }
