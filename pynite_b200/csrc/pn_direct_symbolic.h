@@ -97,7 +97,7 @@ DofClasses predict_dof_classes(const double *xyz, const std::vector<ConnView> &s
 // With `row_class` (class of every K11 row, n_classes > 1) the node graph is still dissected once, and every separator
 // / leaf then yields one front per class that has pivots there: pivots and boundary of (front, class) are the rows of
 // that class at the front's vertices / boundary vertices, its parent is the nearest ancestor that owns pivots of the
-// class.  The rows of a diagonal class become runs of 6 * leaf_size pivots without boundary.  The resulting forest is
+// class.  The rows of a diagonal class become runs of 2 * leaf_size pivots without boundary.  The resulting forest is
 // joined (join_forest in the .cpp): roots of the tallest trees share the top level, a shorter tree hangs, as an extra
 // child without update matrix, from a front at the depth that puts its leaves on the bottom level.  Leaves are scaled
 // so that the largest class keeps about 6 * leaf_size pivots per leaf.

@@ -571,25 +571,32 @@ def _refined_splu(K11, rhs):
     return x
 
 
-def _production_paths_taken(ctr, want_later_groups):
+def _production_paths_taken(ctr, want_later_groups, want_ll=True):
     assert ctr['lu_update'] > 0 and ctr['lu_strip'] > 0, ctr
     assert ctr['split_levels'] > 0, ctr
-    assert ctr['sweep_smem'] > 0 and ctr['sweep_ll'] > 0, ctr
+    assert ctr['sweep_smem'] > 0 and (ctr['sweep_ll'] > 0 or not want_ll), ctr
     if want_later_groups:
         assert ctr['lu_update_later_groups'] > 0 and ctr['max_front_pivots'] > 256, ctr
 
 
-def test_midsize_plate_150_against_oracle(eng):
+@pytest.mark.parametrize('classes', [1, 0])
+def test_midsize_plate_150_against_oracle(eng, classes):
     """BASELINE config 3 shape at 150 x 150 quads (136 806 DOF), 2 combos: pattern bit-exact, values 1e-12,
-    displacements and reactions against the oracle's raw `spsolve` (what the reference calls, `Analysis.py:217`)."""
+    displacements and reactions against the oracle's raw `spsolve` (what the reference calls, `Analysis.py:217`).
+    With the class-split ordering (default: membrane / bending / drilling fronts; every level then fits the
+    shared-memory sweeps at this size) and with the node-based ordering (left-looking sweeps on the top levels)."""
     from pynite_b200 import synthetic
     A = synthetic.quad_plate_arrays(n=150, n_combos=2)
-    _upload(eng, A)
-    eng.reset_stats()
-    D, R, st = eng.solve_linear(eng.make_opts())
+    eng.set_option('dof_classes', classes)
+    try:
+        _upload(eng, A)
+        eng.reset_stats()
+        D, R, st = eng.solve_linear(eng.make_opts())
+    finally:
+        eng.set_option('dof_classes', 1)
     ctr = eng.counters()
-    _production_paths_taken(ctr, want_later_groups=True)
-    assert ctr['dof_classes'] == 3 and ctr['dof_class_rejects'] == 0, ctr      # membrane / bending / drilling fronts
+    _production_paths_taken(ctr, want_later_groups=True, want_ll=not classes)
+    assert ctr['dof_classes'] == (3 if classes else 1) and ctr['dof_class_rejects'] == 0, ctr
     K = om.ke_csr(A)
     indptr, indices = eng.pattern()
     assert np.array_equal(indptr, K.indptr) and np.array_equal(indices, K.indices)
@@ -685,7 +692,9 @@ def test_midsize_plate_256_against_spsolve_and_refined_splu(eng):
     eng.reset_stats()
     D, R, st = eng.solve_linear(eng.make_opts())
     ctr = eng.counters()
-    _production_paths_taken(ctr, want_later_groups=True)
+    # (class-split ordering: the largest front has 768 pivots and every level still fits the shared-memory sweeps; the
+    # left-looking sweeps are covered by the node-ordering run at 150 x 150 and by the full-size config 3 test)
+    _production_paths_taken(ctr, want_later_groups=True, want_ll=False)
     d1, d2, D2 = om.partition_D(A)
     K11, K12, _, _ = om.partition_matrix(om.ke_csr(A), d1, d2)
     P, FER = om.load_vectors(A, 0)
@@ -727,7 +736,8 @@ def test_midsize_mat_on_springs_against_oracle(eng, solver):
     eng.reset_stats()
     D, R, st = eng.solve_linear(eng.make_opts(solver=solver, tol=1e-12, max_iter=200000))
     if solver == 'direct':
-        _production_paths_taken(eng.counters(), want_later_groups=True)
+        _production_paths_taken(eng.counters(), want_later_groups=True, want_ll=False)
+        assert eng.counters()['dof_classes'] == 3
     Do, Ro = _mat_oracle(A)
     for c in range(2):
         assert rel_err(D[c], Do[c].reshape(-1)) < TOL_D, (solver, c, rel_err(D[c], Do[c].reshape(-1)), st.iterations)
