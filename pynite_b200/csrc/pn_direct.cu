@@ -2017,8 +2017,11 @@ static void build_dist_plan(Ctx *c) {
     const int nl = d.n_levels;
     P.active = false;
     P.cut = -1;
-    P.lo.assign(nl, 0); P.hi.assign(nl, 0);
-    for (int l = 0; l < nl; ++l) { P.lo[l] = d.level_ptr[l]; P.hi[l] = d.level_ptr[l + 1]; }
+    auto whole_levels = [&]() {
+        P.lo.assign(nl, 0); P.hi.assign(nl, 0);
+        for (int l = 0; l < nl; ++l) { P.lo[l] = d.level_ptr[l]; P.hi[l] = d.level_ptr[l + 1]; }
+    };
+    whole_levels();
     c->ctr[PC_DIST_CUT_LEVEL] = -1;
     if (world <= 1 || !c->dist_allgather || nl < 2) return;
     // Cut level.  Everything above it is replicated on every rank, everything on and below it is shared out as whole
@@ -2050,59 +2053,76 @@ static void build_dist_plan(Ctx *c) {
             for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q)
                 if (anc[q] >= 0) cost[anc[q] - cf_] += front_cost(q);
     };
-    // contiguous blocks of the cut level, balanced by cost, at least one front per rank; returns the largest share
-    auto share_out = [&](int cut_, std::vector<int32_t> &lo_, std::vector<int32_t> &hi_) {
+    // contiguous blocks of the cut level, balanced by cost, at least one group per rank (a group = the fronts of one
+    // separator of the node dissection, one per DOF-type class: they sit side by side on the level and their
+    // descendants interleave below, so they go to one rank); returns the largest share, or -1 with too few groups
+    const DirectSym &S = d.sym;
+    auto share_out = [&](int cut_, std::vector<int32_t> &lo_, std::vector<int32_t> &hi_) -> double {
         const int cf_ = d.level_ptr[cut_], nc_ = d.level_ptr[cut_ + 1] - cf_;
+        std::vector<int32_t> gbeg;                      // first front (index into the level) of every group
+        std::vector<double> gcost;
+        for (int q = 0; q < nc_; ++q) {
+            if (q == 0 || S.fronts[S.level_fronts[cf_ + q]].group != S.fronts[S.level_fronts[cf_ + q - 1]].group) {
+                gbeg.push_back(q);
+                gcost.push_back(0.0);
+            }
+            gcost.back() += cost[q];
+        }
+        const int ng = (int)gbeg.size();
+        gbeg.push_back(nc_);
+        if (ng < world) return -1.0;
         lo_.assign(world, 0); hi_.assign(world, 0);
         double total = 0.0, worst = 0.0;
-        for (double v : cost) total += v;
-        int q = 0;
+        for (double v : gcost) total += v;
+        int g = 0;
         double acc = 0.0;
         for (int r = 0; r < world; ++r) {
-            lo_[r] = cf_ + q;
-            const int must_leave = world - 1 - r;          // one front at least for every later rank
+            lo_[r] = cf_ + gbeg[g];
+            const int must_leave = world - 1 - r;          // one group at least for every later rank
             const double before = acc;
-            acc += cost[q]; ++q;
-            while (q < nc_ - must_leave && acc + 0.5 * cost[q] <= total * (r + 1) / world) { acc += cost[q]; ++q; }
-            if (r == world - 1) { while (q < nc_) { acc += cost[q]; ++q; } }
-            hi_[r] = cf_ + q;
+            acc += gcost[g]; ++g;
+            while (g < ng - must_leave && acc + 0.5 * gcost[g] <= total * (r + 1) / world) { acc += gcost[g]; ++g; }
+            if (r == world - 1) { while (g < ng) { acc += gcost[g]; ++g; } }
+            hi_[r] = cf_ + gbeg[g];
             worst = std::max(worst, acc - before);
         }
         return worst;
     };
     int cut = -1;
     {
-        int top = -1;
-        for (int l = nl - 2; l >= 0; --l)
-            if (d.level_ptr[l + 1] - d.level_ptr[l] >= world) { top = l; break; }
-        if (top < 0) return;                            // too narrow: replicated solve
-        double best = 0.0, above = 0.0;
-        for (int l = nl - 1; l > top; --l) above += level_cost[l];
+        double best = 0.0, above = level_cost[nl - 1];
         std::vector<int32_t> lo_, hi_;
-        for (int l = top; l >= 0; --l) {
-            subtree_costs(l);
-            const double obj = share_out(l, lo_, hi_) + above;
-            if (cut < 0 || obj < best) { cut = l; best = obj; }
-            if (d.level_ptr[l + 1] - d.level_ptr[l] >= 8 * world) break;
+        for (int l = nl - 2; l >= 0; --l) {
+            if (d.level_ptr[l + 1] - d.level_ptr[l] >= world) {
+                subtree_costs(l);
+                const double worst = share_out(l, lo_, hi_);
+                if (worst >= 0.0) {
+                    const double obj = worst + above;
+                    if (cut < 0 || obj < best) { cut = l; best = obj; }
+                    if (d.level_ptr[l + 1] - d.level_ptr[l] >= 8 * world) break;
+                }
+            }
             above += level_cost[l];
         }
     }
     if (const char *e = getenv("PN_DIST_CUT_BELOW")) cut = std::max(0, cut - atoi(e));     // experiments: deeper cut
-    if (cut < 0 || cut >= nl - 1) return;
+    if (cut < 0 || cut >= nl - 1) return;              // too narrow: replicated solve
     const int cf = d.level_ptr[cut], nc = d.level_ptr[cut + 1] - cf;
     subtree_costs(cut);
-    share_out(cut, P.cut_lo, P.cut_hi);
-    // per-level ranges of this rank: fronts whose cut ancestor is in [cut_lo[rank], cut_hi[rank]); contiguous per level
+    if (share_out(cut, P.cut_lo, P.cut_hi) < 0.0) return;
+    // per-level ranges of this rank: fronts whose cut ancestor is in [cut_lo[rank], cut_hi[rank]); contiguous per level.
+    // A tree this does not hold for (a front without ancestor on the cut level, a rank's fronts interleaved with
+    // another rank's) is solved replicated on every rank instead.
     for (int l = 0; l <= cut; ++l) {
         int lo = -1, hi = -1;
         for (int q = d.level_ptr[l]; q < d.level_ptr[l + 1]; ++q) {
             const bool mine = anc[q] >= P.cut_lo[rank] && anc[q] < P.cut_hi[rank];
             if (mine) { if (lo < 0) lo = q; hi = q + 1; }
-            else if (anc[q] < 0) throw ArgError("direct solver: a front below the cut level has no ancestor on it");
+            else if (anc[q] < 0) { whole_levels(); return; }
         }
         if (lo < 0) { lo = hi = d.level_ptr[l]; }
         for (int q = lo; q < hi; ++q)
-            if (!(anc[q] >= P.cut_lo[rank] && anc[q] < P.cut_hi[rank])) throw ArgError("direct solver: a subtree is not contiguous on its level");
+            if (!(anc[q] >= P.cut_lo[rank] && anc[q] < P.cut_hi[rank])) { whole_levels(); return; }
         P.lo[l] = lo; P.hi[l] = hi;
     }
     // exchange layouts
@@ -2123,7 +2143,6 @@ static void build_dist_plan(Ctx *c) {
     }
     // elimination-position range of every rank: from the first pivot of the first front of its first subtree to the last
     // pivot of its last subtree root (top-level fronts that fall inside are replicated anyway)
-    const DirectSym &S = d.sym;
     P.pos_lo.assign(world, 0); P.pos_hi.assign(world, 0);
     P.x_seg = 0;
     {
@@ -2143,7 +2162,7 @@ static void build_dist_plan(Ctx *c) {
             P.x_seg = std::max(P.x_seg, hi - lo);
         }
         for (int r = 0; r + 1 < world; ++r)
-            if (P.pos_hi[r] > P.pos_lo[r + 1]) throw ArgError("direct solver: subtree position ranges overlap");
+            if (P.pos_hi[r] > P.pos_lo[r + 1]) { whole_levels(); return; }      // replicated solve
     }
     cudaStream_t st = c->stream;
     {

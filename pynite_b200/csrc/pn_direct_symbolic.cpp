@@ -191,13 +191,38 @@ struct Builder {
             out.roots.push_back(0);
             return out;
         }
+        const bool par = verts.size() > 16384;
+        const int64_t nvs = (int64_t)verts.size();
+        // the large subproblems near the root are few, so their passes over the vertex set are cut into chunks that run
+        // as tasks (bounding box, side of the cut, contact with the other side, ordered compaction): the serial passes
+        // of the top three levels were half of the ordering time.  Chunk results are combined in chunk order, so the
+        // tree does not depend on the schedule.
+        constexpr int64_t CH = 8192;
+        const int64_t nch = (nvs + CH - 1) / CH;
         // widest coordinate axis
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        for (int32_t v : verts)
-            for (int k = 0; k < 3; ++k) {
-                lo[k] = std::min(lo[k], coords[3 * v + k]);
-                hi[k] = std::max(hi[k], coords[3 * v + k]);
+        if (par) {
+            std::vector<double> box((size_t)nch * 6);
+#pragma omp taskloop grainsize(1) default(shared)
+            for (int64_t ch = 0; ch < nch; ++ch) {
+                double l[3] = {1e300, 1e300, 1e300}, h[3] = {-1e300, -1e300, -1e300};
+                const int64_t e = std::min(nvs, (ch + 1) * CH);
+                for (int64_t i = ch * CH; i < e; ++i)
+                    for (int k = 0; k < 3; ++k) {
+                        const double x = coords[3 * verts[i] + k];
+                        l[k] = std::min(l[k], x); h[k] = std::max(h[k], x);
+                    }
+                for (int k = 0; k < 3; ++k) { box[ch * 6 + k] = l[k]; box[ch * 6 + 3 + k] = h[k]; }
             }
+            for (int64_t ch = 0; ch < nch; ++ch)
+                for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], box[ch * 6 + k]); hi[k] = std::max(hi[k], box[ch * 6 + 3 + k]); }
+        } else {
+            for (int32_t v : verts)
+                for (int k = 0; k < 3; ++k) {
+                    lo[k] = std::min(lo[k], coords[3 * v + k]);
+                    hi[k] = std::max(hi[k], coords[3 * v + k]);
+                }
+        }
         int axis = 0;
         for (int k = 1; k < 3; ++k) if (hi[k] - lo[k] > hi[axis] - lo[axis]) axis = k;
         size_t mid = verts.size() / 2;
@@ -205,61 +230,97 @@ struct Builder {
             double ca = coords[3 * a + axis], cb = coords[3 * b + axis];
             return ca < cb || (ca == cb && a < b);
         };
+        std::vector<int32_t> A, B, S;
         // Large sets: the cut coordinate is the median of a fixed-stride sample (the exact median needs an nth_element
         // over indirect keys, which was a third of the serial time at the top of the recursion); the set is then
         // split by coordinate, so vertices sharing the cut coordinate stay on one side and the separators of
         // structured meshes are straight lines / planes.  Small or degenerate sets take the exact path.
         bool split_done = false;
+        int32_t ra = 0, rb = 0;
         if (verts.size() > 8192) {
             const size_t ns = 2047, stride = verts.size() / ns;
             double sample[2047];
             for (size_t q = 0; q < ns; ++q) sample[q] = coords[3 * verts[q * stride] + axis];
             std::nth_element(sample, sample + ns / 2, sample + ns);
             const double cm = sample[ns / 2];
-            auto it = std::partition(verts.begin(), verts.end(), [&](int32_t v) { return coords[3 * v + axis] < cm; });
-            const size_t cut = it - verts.begin();
-            if (cut > verts.size() / 4 && cut < verts.size() - verts.size() / 4) { mid = cut; split_done = true; }
-        }
-        if (!split_done) {
-            std::nth_element(verts.begin(), verts.begin() + mid, verts.end(), cmp);
-            // keep vertices with the same coordinate as the median on one side when possible
-            double cm = coords[3 * verts[mid] + axis];
-            size_t lo_cnt = 0;
-            for (int32_t v : verts) if (coords[3 * v + axis] < cm) ++lo_cnt;
-            if (lo_cnt > verts.size() / 4) {
+            if (par) {
+                // side of every vertex and the region marks in one pass; sizes per chunk
+                std::vector<uint8_t> side(nvs);
+                std::vector<int64_t> cntA(nch + 1, 0), cntB(nch + 1, 0), cntS(nch + 1, 0);
+                ra = next_region.fetch_add(2); rb = ra + 1;
+#pragma omp taskloop grainsize(1) default(shared)
+                for (int64_t ch = 0; ch < nch; ++ch) {
+                    const int64_t e = std::min(nvs, (ch + 1) * CH);
+                    int64_t a = 0;
+                    for (int64_t i = ch * CH; i < e; ++i) {
+                        const bool low = coords[3 * verts[i] + axis] < cm;
+                        side[i] = low ? 0 : 1;
+                        region[verts[i]] = low ? ra : rb;
+                        a += low;
+                    }
+                    cntA[ch + 1] = a;
+                }
+                int64_t cut = 0;
+                for (int64_t ch = 0; ch < nch; ++ch) cut += cntA[ch + 1];
+                if (cut > nvs / 4 && cut < nvs - nvs / 4) {
+                    // separator = vertices of the upper side touching the lower side (the upper side holds the median plane)
+#pragma omp taskloop grainsize(1) default(shared)
+                    for (int64_t ch = 0; ch < nch; ++ch) {
+                        const int64_t e = std::min(nvs, (ch + 1) * CH);
+                        int64_t nb_ = 0, ns_ = 0;
+                        for (int64_t i = ch * CH; i < e; ++i) {
+                            if (!side[i]) continue;
+                            const int32_t v = verts[i];
+                            bool t = false;
+                            for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k)
+                                if (region[adj[k]] == ra) { t = true; break; }
+                            if (t) { side[i] = 2; ++ns_; } else ++nb_;
+                        }
+                        cntB[ch + 1] = nb_; cntS[ch + 1] = ns_;
+                    }
+                    for (int64_t ch = 0; ch < nch; ++ch) { cntA[ch + 1] += cntA[ch]; cntB[ch + 1] += cntB[ch]; cntS[ch + 1] += cntS[ch]; }
+                    A.resize(cntA[nch]); B.resize(cntB[nch]); S.resize(cntS[nch]);
+#pragma omp taskloop grainsize(1) default(shared)
+                    for (int64_t ch = 0; ch < nch; ++ch) {
+                        const int64_t e = std::min(nvs, (ch + 1) * CH);
+                        int64_t pa = cntA[ch], pb = cntB[ch], ps = cntS[ch];
+                        for (int64_t i = ch * CH; i < e; ++i) {
+                            if (side[i] == 0) A[pa++] = verts[i];
+                            else if (side[i] == 1) B[pb++] = verts[i];
+                            else S[ps++] = verts[i];
+                        }
+                    }
+                    split_done = true;
+                }
+            } else {
                 auto it = std::partition(verts.begin(), verts.end(), [&](int32_t v) { return coords[3 * v + axis] < cm; });
-                mid = it - verts.begin();
+                const size_t cut = it - verts.begin();
+                if (cut > verts.size() / 4 && cut < verts.size() - verts.size() / 4) { mid = cut; split_done = true; }
             }
         }
-        int32_t ra = next_region.fetch_add(2), rb = ra + 1;
-        const bool par = verts.size() > 16384;
-        const int64_t nvs = (int64_t)verts.size();
-        // the large subproblems near the root are few: their vertex loops are split into tasks as well
-#pragma omp taskloop grainsize(8192) if (par) default(shared)
-        for (int64_t i = 0; i < nvs; ++i) region[verts[i]] = i < (int64_t)mid ? ra : rb;
-        std::vector<int32_t> A, B, S;
-        // separator = vertices of B touching A (B holds the median plane, which is the natural cut)
-        std::vector<uint8_t> touch(par ? nvs : 0);
-        if (par) {
-#pragma omp taskloop grainsize(4096) default(shared)
-            for (int64_t i = (int64_t)mid; i < nvs; ++i) {
+        if (!(par && split_done)) {
+            if (!split_done) {
+                std::nth_element(verts.begin(), verts.begin() + mid, verts.end(), cmp);
+                // keep vertices with the same coordinate as the median on one side when possible
+                double cm = coords[3 * verts[mid] + axis];
+                size_t lo_cnt = 0;
+                for (int32_t v : verts) if (coords[3 * v + axis] < cm) ++lo_cnt;
+                if (lo_cnt > verts.size() / 4) {
+                    auto it = std::partition(verts.begin(), verts.end(), [&](int32_t v) { return coords[3 * v + axis] < cm; });
+                    mid = it - verts.begin();
+                }
+            }
+            ra = next_region.fetch_add(2); rb = ra + 1;
+            for (int64_t i = 0; i < nvs; ++i) region[verts[i]] = i < (int64_t)mid ? ra : rb;
+            // separator = vertices of B touching A (B holds the median plane, which is the natural cut)
+            A.assign(verts.begin(), verts.begin() + mid);
+            for (size_t i = mid; i < verts.size(); ++i) {
                 int32_t v = verts[i];
-                uint8_t t = 0;
-                for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k)
-                    if (region[adj[k]] == ra) { t = 1; break; }
-                touch[i] = t;
-            }
-        }
-        A.assign(verts.begin(), verts.begin() + mid);
-        if (par) { B.reserve(verts.size() - mid); S.reserve(4096); }
-        for (size_t i = mid; i < verts.size(); ++i) {
-            int32_t v = verts[i];
-            bool touches = false;
-            if (par) touches = touch[i] != 0;
-            else
+                bool touches = false;
                 for (int64_t k = adj_ptr[v]; k < adj_ptr[v + 1]; ++k)
                     if (region[adj[k]] == ra) { touches = true; break; }
-            (touches ? S : B).push_back(v);
+                (touches ? S : B).push_back(v);
+            }
         }
         std::vector<int32_t>().swap(verts);
         SubTree ta, tb;
@@ -318,7 +379,10 @@ static std::vector<int32_t> join_forest(std::vector<int32_t> &parent) {
         const int32_t dp = std::max(0, H - 1 - height[f]);
         parent[f] = cand[dp][next[dp]++ % cand[dp].size()];
     }
-    // post-order renumbering (roots and children in ascending old id: the result depends on the input only)
+    // Renumbering.  The fronts of the tallest trees keep their relative order -- the caller lists them by (node front,
+    // class), i.e. node-tree post-order with the classes of one separator side by side, so that the fronts of one
+    // geometric region form one id range on every level (the subtree-to-GPU plan hands such ranges to the ranks) --
+    // and every attached tree is emitted, in post-order, right before the front it hangs from.
     std::vector<int32_t> cptr(nf + 1, 0), cidx(nf);
     for (int32_t f = 0; f < nf; ++f) if (parent[f] >= 0) ++cptr[parent[f] + 1];
     for (int32_t f = 0; f < nf; ++f) cptr[f + 1] += cptr[f];
@@ -329,8 +393,7 @@ static std::vector<int32_t> join_forest(std::vector<int32_t> &parent) {
     std::vector<int32_t> new_id(nf, -1), order;
     order.reserve(nf);
     std::vector<std::pair<int32_t, int32_t>> stack;     // (front, next child slot)
-    for (int32_t r = 0; r < nf; ++r) {
-        if (parent[r] >= 0) continue;
+    auto emit_tree = [&](int32_t r) {                   // post-order of the (short) tree rooted at r
         stack.push_back({r, cptr[r]});
         while (!stack.empty()) {
             auto &top = stack.back();
@@ -343,6 +406,13 @@ static std::vector<int32_t> join_forest(std::vector<int32_t> &parent) {
                 stack.pop_back();
             }
         }
+    };
+    for (int32_t f = 0; f < nf; ++f) {
+        if (height[root_of[f]] != H) continue;          // (root_of / height: of the forest before the join)
+        for (int32_t k = cptr[f]; k < cptr[f + 1]; ++k)
+            if (height[root_of[cidx[k]]] != H) emit_tree(cidx[k]);
+        new_id[f] = (int32_t)order.size();
+        order.push_back(f);
     }
     if ((int32_t)order.size() != nf) throw std::runtime_error("direct_symbolic: forest join lost fronts");
     std::vector<int32_t> np(nf);
@@ -504,21 +574,28 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         if (const char *e = getenv("PN_DIAG_RUN")) run_len = std::max(1, atoi(e));
         for (int c = 0; c < C; ++c) {
             if (!diag[c]) continue;
-            std::vector<int32_t> cur;
-            for (int64_t r = 0; r < n; ++r) {
-                if (row_class[r] != c) continue;
-                cur.push_back((int32_t)r);
-                if ((int64_t)cur.size() == run_len) {
-                    cf.push_back({-1, c, (int32_t)diag_runs.size()});
-                    parent_of.push_back(-1);
-                    diag_runs.push_back(std::move(cur));
-                    cur.clear();
-                }
+            // rows of the class in K11 order (chunked count + ordered fill), cut into runs
+            constexpr int64_t CH = 65536;
+            const int64_t nch = (n + CH - 1) / CH;
+            std::vector<int64_t> cnt(nch + 1, 0);
+#pragma omp parallel for schedule(static)
+            for (int64_t ch = 0; ch < nch; ++ch) {
+                int64_t k = 0;
+                for (int64_t r = ch * CH; r < std::min(n, (ch + 1) * CH); ++r) k += row_class[r] == c;
+                cnt[ch + 1] = k;
             }
-            if (!cur.empty()) {
+            for (int64_t ch = 0; ch < nch; ++ch) cnt[ch + 1] += cnt[ch];
+            std::vector<int32_t> rows_c((size_t)cnt[nch]);
+#pragma omp parallel for schedule(static)
+            for (int64_t ch = 0; ch < nch; ++ch) {
+                int64_t k = cnt[ch];
+                for (int64_t r = ch * CH; r < std::min(n, (ch + 1) * CH); ++r)
+                    if (row_class[r] == c) rows_c[k++] = (int32_t)r;
+            }
+            for (int64_t i = 0; i < (int64_t)rows_c.size(); i += run_len) {
                 cf.push_back({-1, c, (int32_t)diag_runs.size()});
                 parent_of.push_back(-1);
-                diag_runs.push_back(std::move(cur));
+                diag_runs.emplace_back(rows_c.begin() + i, rows_c.begin() + std::min<int64_t>((int64_t)rows_c.size(), i + run_len));
             }
         }
         order = join_forest(parent_of);
@@ -586,6 +663,7 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         F.pos_start = pos_start[f];
         F.ns = ns_of[f];
         F.nb = nb_of[f];
+        F.group = cf[order[f]].run < 0 ? cf[order[f]].node_front : -1 - cf[order[f]].run;
         F.idx_off = total_idx;
         F.rel_off = total_rel;
         total_idx += F.ns + F.nb;
@@ -604,6 +682,7 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
     // inverse of perm_pos for index lists in K11 numbering
     std::vector<int32_t> &pos_dof = out.s_pos_dof;
     pos_dof.resize(n);
+#pragma omp parallel for schedule(static)
     for (int64_t d = 0; d < n; ++d) pos_dof[out.perm_pos[d]] = (int32_t)d;
     out.fpos.resize(total_idx);
     out.fidx.resize(total_idx);

@@ -43,6 +43,7 @@ struct FrontSym {
     int32_t pos_start = 0;   // elimination position of the first pivot DOF
     int64_t idx_off = 0;     // offset into fidx / fpos (length ns + nb)
     int64_t rel_off = 0;     // offset into rel (length nb)
+    int32_t group = 0;       // fronts of one separator / leaf of the node dissection (one per DOF-type class) share a group
 };
 
 struct DirectSym {
