@@ -1366,8 +1366,8 @@ __device__ __noinline__ void sweep_add_child(double *w, const double *__restrict
     }
 }
 
-template <int CW>
-__global__ void __launch_bounds__(256, 2)
+template <int CW, int MINB = 2, int PAD = SW_PAD_ROWS>
+__global__ void __launch_bounds__(256, MINB)
 k_front_forward_sm(int first, int s, int H, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
                    const int32_t *__restrict__ rel, const int32_t *__restrict__ child_ptr, const int32_t *__restrict__ child_idx,
                    const double *__restrict__ L, const double *__restrict__ inv, double *__restrict__ X,
@@ -1381,7 +1381,7 @@ k_front_forward_sm(int first, int s, int H, const FrontDev *__restrict__ fronts,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t *fi = fidx + F.idx_off;
     // own rows from X, boundary rows and the padding rows zero
-    sweep_gather<CW>(w, X, fi, F.ns, n + SW_PAD_ROWS, s, c0, tid);
+    sweep_gather<CW>(w, X, fi, F.ns, n + PAD, s, c0, tid);
     __syncthreads();
     // update vectors of the children, in child-rank order (fixed summation order)
     for (int ci = child_ptr[f]; ci < child_ptr[f + 1]; ++ci) {
@@ -1423,8 +1423,8 @@ k_front_forward_sm(int first, int s, int H, const FrontDev *__restrict__ fronts,
     }
 }
 
-template <int CW>
-__global__ void __launch_bounds__(256, 2)
+template <int CW, int MINB = 2, int PAD = SW_PAD_ROWS>
+__global__ void __launch_bounds__(256, MINB)
 k_front_backward_sm(int first, int s, int H, const FrontDev *__restrict__ fronts, const int32_t *__restrict__ fidx,
                     const double *__restrict__ L, const double *__restrict__ U, const double *__restrict__ inv,
                     double *__restrict__ X) {
@@ -1435,7 +1435,7 @@ k_front_backward_sm(int first, int s, int H, const FrontDev *__restrict__ fronts
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t *fi = fidx + F.idx_off;
     // own rows hold y, boundary rows the final x of the ancestors
-    sweep_gather<CW>(w, X, fi, n, n + SW_PAD_ROWS, s, c0, tid);
+    sweep_gather<CW>(w, X, fi, n, n + PAD, s, c0, tid);
     __syncthreads();
     if (F.nb) {                                // w[0:ns] -= U12 w[ns:n]
         const int nslabs = (F.ns + 15) >> 4;
@@ -1614,9 +1614,22 @@ k_ll_sweep(int first, int nfl, int s, int H, int T, int backward, const FrontDev
 // Largest column chunk in {32, 16} whose block leaves room for two CTAs per SM (measured: with one CTA per SM, or
 // 8-column chunks, the per-step GEMM launches of the general path are faster); 8 only when there are <= 8
 // right-hand sides.  0 = the level uses the general path.
-static int sweep_chunk(int maxn, int s, size_t *smem) {
+// Three CTAs per SM (80 registers per thread, 16 padding rows: the 32-column kernels read B rows at most 15 past the
+// block) for the levels of the smallest fronts: their sweeps are bound by the latency of the panel loads (ncu:
+// long_scoreboard first, tensor pipe 23 % active at 16 warps per SM).  Measured on config 3 (B200, 64 right-hand sides,
+// forward / backward): fronts up to 162 rows 0.904 / 1.101 -> 0.874 / 0.986 ms, up to 174 rows 0.346 / 0.390 -> 0.287 /
+// 0.338 ms, but up to 240 rows 0.840 / 0.866 -> 0.879 / 0.909 ms (the spills cost more than the third CTA hides), hence
+// the 64 KB limit (206 rows).
+constexpr int SW_THREE_CTA_SMEM = 64 * 1024, SW_PAD_ROWS_3 = 16;
+static int sweep_chunk(int maxn, int s, size_t *smem, bool *three = nullptr) {
+    static const bool no3 = getenv("PN_SWEEP_TWO_CTAS") != nullptr;
     const int cand[3] = {32, 16, 8};
     const int scap = std::max(8, ((s + 7) / 8) * 8);
+    if (three) {
+        *three = false;
+        const size_t need3 = (size_t)(maxn + SW_PAD_ROWS_3) * (32 + 4) * sizeof(double);
+        if (!no3 && scap >= 32 && need3 <= (size_t)SW_THREE_CTA_SMEM) { *smem = need3; *three = true; return 32; }
+    }
     for (int cw : cand) {
         if (cw > scap || (cw == 8 && s > 8)) continue;
         size_t need = (size_t)(maxn + SW_PAD_ROWS) * (cw + 4) * sizeof(double);
@@ -1860,6 +1873,8 @@ static void analyse(Ctx *c) {
         PN_CUDA(cudaFuncSetAttribute(k_front_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_solve_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_solve_forward_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<32, 3, SW_PAD_ROWS_3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
+        PN_CUDA(cudaFuncSetAttribute(k_front_backward_sm<32, 3, SW_PAD_ROWS_3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
         PN_CUDA(cudaFuncSetAttribute(k_front_forward_sm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_MAX_SMEM));
@@ -2563,14 +2578,15 @@ static void solve_forward_level(Ctx *c, double *X, int s, int l, cudaStream_t st
     double *W = d.warena[l & 1].ptr;
     int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
     size_t sw_smem = 0;
-    const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
+    bool three = false;
+    const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem, &three);
     if (cw) {
         ProfScope ps_(c, PS_SOLVE_FUSED);
         const int H = (s + cw - 1) / cw;
         const unsigned grid = (unsigned)nfl * (unsigned)H;
-#define PN_FWD(CW_) k_front_forward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, \
+#define PN_FWD(...) k_front_forward_sm<__VA_ARGS__><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.rel.ptr, d.child_ptr.ptr, d.child_idx.ptr, \
                                                                 d.L.ptr, d.inv.ptr, X, W, d.warena[(l + 1) & 1].ptr)
-        if (cw == 32) PN_FWD(32); else if (cw == 16) PN_FWD(16); else PN_FWD(8);
+        if (three) PN_FWD(32, 3, SW_PAD_ROWS_3); else if (cw == 32) PN_FWD(32); else if (cw == 16) PN_FWD(16); else PN_FWD(8);
 #undef PN_FWD
         c->count_launch();
         c->ctr[PC_SWEEP_SMEM]++;
@@ -2660,13 +2676,14 @@ static void solve_inplace(Ctx *c, double *X, int s, bool forward_done = false) {
         double *W = d.warena[l & 1].ptr;
         int maxn = d.level_max_n[l], maxns = d.level_max_ns[l];
         size_t sw_smem = 0;
-        const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem);
+        bool three = false;
+        const int cw = no_sm_sweeps ? 0 : sweep_chunk(maxn, s, &sw_smem, &three);
         if (cw) {
             ProfScope ps_(c, PS_SOLVE_FUSED);
             const int H = (s + cw - 1) / cw;
             const unsigned grid = (unsigned)nfl * (unsigned)H;
-#define PN_BWD(CW_) k_front_backward_sm<CW_><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X)
-            if (cw == 32) PN_BWD(32); else if (cw == 16) PN_BWD(16); else PN_BWD(8);
+#define PN_BWD(...) k_front_backward_sm<__VA_ARGS__><<<grid, 256, sw_smem, st>>>(first, s, H, fr, d.fidx.ptr, d.L.ptr, d.U.ptr, d.inv.ptr, X)
+            if (three) PN_BWD(32, 3, SW_PAD_ROWS_3); else if (cw == 32) PN_BWD(32); else if (cw == 16) PN_BWD(16); else PN_BWD(8);
 #undef PN_BWD
             c->count_launch();
             c->ctr[PC_SWEEP_SMEM]++;
