@@ -545,15 +545,21 @@ def run_ours(args, rank, local_rank, world):
     if roof is not None:
         roof['kernel'] = dom_key
         roof['traffic'] = None
-        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_final_lu_update_dram.json')
-        if dom_key.startswith('lu_update') and args.n == 500 and args.combos == 64 and os.path.exists(tpath):
+        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload (a stopgap
+        # the line says so: the traffic is not measured inside this run)
+        root = os.path.dirname(os.path.abspath(__file__))
+        tpath = os.path.join(root, 'profiles', 'r2_final_dram.json')
+        if args.n == 500 and args.combos == 64 and world == 1 and args.dof_classes and os.path.exists(tpath):
             with open(tpath) as f:
                 tr = json.load(f)
-            roof['traffic'] = tr['dram_bytes_per_launch']
-            roof['traffic_unit'] = 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu, %d launches per step)' % tr['launches']
-            roof['traffic_source'] = 'profiles/r1_final_lu_update_dram.json'
-            roof['flops_per_launch'] = roof['flops_per_step']/tr['launches']
+            if dom_key.startswith('solve sweeps'):
+                sw = tr['sweeps']
+                roof['traffic'] = sw['dram_bytes_per_launch']
+                roof['traffic_unit'] = ('bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu, %d launches of the shared-memory '
+                                        'sweep kernels per step; the left-looking sweeps of the top levels add %d launches)'
+                                        % (sw['launches'], int(prof['solve_update'][1]/K)))
+                roof['traffic_source'] = 'profiles/r2_final_dram.json (committed ncu capture of tools/one_step.py, not measured in this run)'
+                roof['flops_per_launch'] = roof['flops_per_step']/(sw['launches'] + prof['solve_update'][1]/K)
         roof['peak_is'] = ('measured (' + hbm_src + ')') if roof['bound'] == 'hbm' else roof.get('peak_source')
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
