@@ -243,9 +243,12 @@ double residual_check(Ctx *c, const double *vals11, int percol, int s, const pn_
     if (o.solver != PN_SOLVER_PCG) direct_dist_row_share(c, n1, &r0, &r1);
     residual_dd(c, c->blk[0], vals11, percol ? c->blk[0].nnz : 0, c->X.ptr, c->B.ptr, AX.ptr, s, st, nullptr, r0, r1 - r0);
     std::vector<double> rr(s), bb(s), xx(s);
-    column_dots(c, r1 - r0, s, AX.ptr + r0 * s, AX.ptr + r0 * s, rr.data());
-    column_dots(c, r1 - r0, s, c->B.ptr + r0 * s, c->B.ptr + r0 * s, bb.data());
-    column_dots(c, r1 - r0, s, c->X.ptr + r0 * s, c->X.ptr + r0 * s, xx.data());
+    {
+        const double *v[3] = {AX.ptr + r0 * s, c->B.ptr + r0 * s, c->X.ptr + r0 * s};
+        std::vector<double> all((size_t)3 * s);
+        column_dots_multi(c, r1 - r0, s, 3, v, v, all.data());
+        for (int j = 0; j < s; ++j) { rr[j] = all[j]; bb[j] = all[s + j]; xx[j] = all[2 * s + j]; }
+    }
     if (r1 - r0 != n1) {
         std::vector<double> all((size_t)3 * s);
         for (int j = 0; j < s; ++j) { all[j] = rr[j]; all[s + j] = bb[j]; all[2 * s + j] = xx[j]; }

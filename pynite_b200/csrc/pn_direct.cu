@@ -2919,8 +2919,12 @@ void direct_invalidate_pattern(Ctx *c) {
 static void refinement_norms(Ctx *c, int64_t n1, int s, const double *Dv, const double *Xv, double *dd, double *xx) {
     int64_t r0 = 0, r1 = n1;
     direct_dist_row_share(c, n1, &r0, &r1);
-    column_dots(c, r1 - r0, s, Dv + r0 * s, Dv + r0 * s, dd);
-    column_dots(c, r1 - r0, s, Xv + r0 * s, Xv + r0 * s, xx);
+    {
+        const double *v[2] = {Dv + r0 * s, Xv + r0 * s};
+        std::vector<double> all((size_t)2 * s);
+        column_dots_multi(c, r1 - r0, s, 2, v, v, all.data());
+        for (int j = 0; j < s; ++j) { dd[j] = all[j]; xx[j] = all[s + j]; }
+    }
     if (r1 - r0 != n1) {
         std::vector<double> both((size_t)2 * s);
         for (int j = 0; j < s; ++j) { both[j] = dd[j]; both[s + j] = xx[j]; }

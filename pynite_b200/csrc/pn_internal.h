@@ -441,6 +441,8 @@ void pcg_strip_update(Ctx *c, int s, int64_t node0, int64_t node1, int first, co
 void pcg_strip_direction(Ctx *c, int s, int64_t row0, int64_t row1, int first, const double *rz_dev, const double *rz_new_dev,
                          const double *Z, double *P);
 void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host);
+// up to three products in one pass; out_host is [n_which][s]
+void column_dots_multi(Ctx *c, int64_t n, int s, int n_which, const double *const *A, const double *const *B, double *out_host);
 void direct_solve(Ctx *c, const double *vals11, int per_column_vals, int s, const pn_solve_opts &o);
 void direct_release(Ctx *c);
 void direct_prefetch(Ctx *c);     // start the host half of the analysis on a worker thread (after the DOF partition is known)

@@ -199,6 +199,59 @@ __global__ void k_copy_s(int s, const double *__restrict__ a, double *__restrict
 }
 
 // out_host[j] = sum_i A[i][j] * B[i][j] for row-major [n][s] arrays (deterministic reduction tree)
+// Up to three column-wise dot products in ONE pass and one host synchronisation: out_host[w][j] = sum_i A_w[i][j] B_w[i][j].
+// (The refinement needs |d|^2 and |x|^2, the residual check |r|^2, |b|^2 and |x|^2: five launches of k_dot_partial, five
+// serial 592-term sums in k_dot_final and five stream synchronisations became two of each.)  Block partials as in
+// k_dot_partial; the final sum of a (product, column) pair is done by one warp in a fixed order.
+struct DotPairs { const double *A[3], *B[3]; };
+__global__ void __launch_bounds__(RED_TPB)
+k_dot_partial_multi(int64_t n, int s, DotPairs p, int n_which, double *__restrict__ partial) {
+    __shared__ double sm[3][RED_TPB];
+    const int lanes = RED_TPB / s;
+    const int t = threadIdx.x, j = t % s, rl = t / s;
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (rl < lanes)
+        for (int64_t i = (int64_t)blockIdx.x * lanes + rl; i < n; i += (int64_t)gridDim.x * lanes)
+#pragma unroll
+            for (int w = 0; w < 3; ++w)
+                if (w < n_which) acc[w] = fma(p.A[w][i * s + j], p.B[w][i * s + j], acc[w]);
+#pragma unroll
+    for (int w = 0; w < 3; ++w) sm[w][t] = acc[w];
+    __syncthreads();
+    if (t < s)
+        for (int w = 0; w < n_which; ++w) {
+            double tot = 0.0;
+            for (int l = 0; l < lanes; ++l) tot += sm[w][l * s + t];
+            partial[((int64_t)blockIdx.x * n_which + w) * s + t] = tot;
+        }
+}
+// one warp per (product, column): lane l adds the partials of blocks l, l + 32, ... in order, then a shuffle tree
+__global__ void k_dot_final_warp(int grid, int s, int n_which, const double *__restrict__ partial, double *__restrict__ out) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= s * n_which) return;
+    const int w = wid / s, j = wid % s;
+    double tot = 0.0;
+    for (int b = lane; b < grid; b += 32) tot += partial[((int64_t)b * n_which + w) * s + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+    if (lane == 0) out[w * s + j] = tot;
+}
+void column_dots_multi(Ctx *c, int64_t n, int s, int n_which, const double *const *A, const double *const *B, double *out_host) {
+    if (s > 256) throw ArgError("column_dots: at most 256 columns");
+    if (n_which < 1 || n_which > 3) throw ArgError("column_dots_multi: one to three products");
+    const int grid = 148 * 4;
+    DevBuf<double> &partial = c->dots_partial, &out = c->dots_out;
+    partial.resize((int64_t)grid * s * n_which);
+    out.resize((int64_t)s * n_which);
+    DotPairs p{};
+    for (int w = 0; w < 3; ++w) { p.A[w] = A[w < n_which ? w : 0]; p.B[w] = B[w < n_which ? w : 0]; }
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_partial_multi<<<grid, RED_TPB, 0, c->stream>>>(n, s, p, n_which, partial.ptr); }
+    { ProfScope ps_(c, PS_PCG_VECTOR); k_dot_final_warp<<<grid_for((int64_t)s * n_which * 32, 128), 128, 0, c->stream>>>(grid, s, n_which, partial.ptr, out.ptr); }
+    c->count_launch(2);
+    PN_CUDA(cudaMemcpyAsync(out_host, out.ptr, sizeof(double) * s * n_which, cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+}
+
 void column_dots(Ctx *c, int64_t n, int s, const double *A, const double *B, double *out_host) {
     if (s > 256) throw ArgError("column_dots: at most 256 columns");
     const int grid = 148 * 4;
