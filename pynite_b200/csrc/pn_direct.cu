@@ -1727,10 +1727,12 @@ static void join_host_analysis(DirectSolver &d) {
 // model's support / enforced-displacement masks (same rule as k_known_flags + k_partition_lists), so the worker needs
 // nothing from the device and can start as soon as the model arrays are set (pn_prefetch_analysis), well before the
 // symbolic phase.  A model change joins and discards it (direct_invalidate).
+static bool shared_ordering(const Ctx *c);
 void direct_prefetch(Ctx *c) {
     static const bool off = getenv("PN_NO_ANALYSIS_PREFETCH") != nullptr;
     const Model &m = c->model;
     if (off || !m.n_nodes) return;
+    if (shared_ordering(c) && c->dist_rank != 0) return;          // rank 0 orders for all ranks (share_ordering)
     if (!c->direct) c->direct = new DirectSolver();
     DirectSolver &d = *c->direct;
     if (d.host_state != 0) return;                       // running, or done and still valid for this model
@@ -1757,6 +1759,73 @@ void direct_prefetch(Ctx *c) {
 
 static void build_dist_plan(Ctx *c);
 
+// ---- one ordering for all ranks of a subtree-to-GPU solve -----------------------------------------------------------
+// The ranks of one box share its cores (16 cores / 8 ranks leaves one OpenMP thread per rank) and would all compute the
+// same elimination tree; rank 0 computes it with the threads of the whole box and the others receive it: a header and
+// one blob (index lists, front table, level lists) through the caller's all-gather, i.e. over NVLink, segment 0 being
+// rank 0's.  ~90 MB for config 3; the other ranks' segments carry nothing.
+static bool shared_ordering(const Ctx *c) {
+    static const bool off = getenv("PN_DIST_PRIVATE_ORDERING") != nullptr;
+    return !off && c->dist_world > 1 && c->dist_allgather != nullptr;
+}
+static void dist_allgather(Ctx *c, int64_t seg);
+static void share_ordering(Ctx *c) {
+    DirectSolver &d = *c->direct;
+    DirectSym &S = d.sym;
+    DistPlan &P = d.dist;
+    cudaStream_t st = c->stream;
+    const int world = c->dist_world;
+    const bool root = c->dist_rank == 0;
+    constexpr int NH = 16;
+    double hdr[NH] = {0};
+    if (root) {
+        hdr[0] = (double)S.n; hdr[1] = (double)S.fronts.size(); hdr[2] = (double)S.fidx.size(); hdr[3] = (double)S.rel.size();
+        hdr[4] = (double)S.level_ptr.size(); hdr[5] = (double)S.max_children; hdr[6] = (double)S.factor_entries;
+        hdr[7] = S.factor_flops; hdr[8] = (double)S.max_front; hdr[9] = (double)d.n_classes; hdr[10] = 1.0;
+    }
+    P.send.resize(std::max<int64_t>(P.send.n, NH));
+    P.recv.resize(std::max<int64_t>(P.recv.n, (int64_t)NH * world));
+    PN_CUDA(cudaMemcpyAsync(P.send.ptr, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+    dist_allgather(c, NH);
+    PN_CUDA(cudaMemcpyAsync(hdr, P.recv.ptr, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+    PN_CUDA(cudaStreamSynchronize(st));
+    if (hdr[10] != 1.0) throw StatusError(PN_ERR_CUDA, "pn_set_distributed: rank 0 did not deliver the ordering");
+    const int64_t n = (int64_t)hdr[0], nf = (int64_t)hdr[1], nidx = (int64_t)hdr[2], nrel = (int64_t)hdr[3], nlp = (int64_t)hdr[4];
+    if (!root) {
+        S.n = n; S.max_children = (int32_t)hdr[5]; S.factor_entries = (int64_t)hdr[6]; S.factor_flops = hdr[7];
+        S.max_front = (int64_t)hdr[8]; d.n_classes = (int)hdr[9];
+        S.perm_pos.resize(n); S.dof_front.resize(n); S.s_pos_dof.resize(n); d.h_dof_front_lm.resize(n);
+        S.fronts.resize(nf); S.fidx.resize(nidx); S.fpos.resize(nidx); S.rel.resize(nrel);
+        S.level_ptr.resize(nlp); S.level_fronts.resize(nf);
+    }
+    struct Part { void *host; int64_t bytes; };
+    const Part parts[] = {
+        {S.perm_pos.data(), n * 4}, {S.dof_front.data(), n * 4}, {S.s_pos_dof.data(), n * 4}, {d.h_dof_front_lm.data(), n * 4},
+        {S.fidx.data(), nidx * 4}, {S.fpos.data(), nidx * 4}, {S.rel.data(), nrel * 4},
+        {S.level_ptr.data(), nlp * 4}, {S.level_fronts.data(), nf * 4}, {S.fronts.data(), nf * (int64_t)sizeof(FrontSym)}};
+    int64_t total = 0;
+    for (const Part &pt : parts) total += (pt.bytes + 15) / 16 * 16;
+    const int64_t seg = total / 8;
+    P.send.resize(std::max<int64_t>(P.send.n, seg));
+    P.recv.resize(std::max<int64_t>(P.recv.n, seg * world));
+    if (root) {
+        int64_t off = 0;
+        for (const Part &pt : parts) {
+            if (pt.bytes) PN_CUDA(cudaMemcpyAsync((char *)P.send.ptr + off, pt.host, (size_t)pt.bytes, cudaMemcpyHostToDevice, st));
+            off += (pt.bytes + 15) / 16 * 16;
+        }
+    }
+    dist_allgather(c, seg);
+    if (!root) {
+        int64_t off = 0;
+        for (const Part &pt : parts) {
+            if (pt.bytes) PN_CUDA(cudaMemcpyAsync(pt.host, (const char *)P.recv.ptr + off, (size_t)pt.bytes, cudaMemcpyDeviceToHost, st));
+            off += (pt.bytes + 15) / 16 * 16;
+        }
+        PN_CUDA(cudaStreamSynchronize(st));
+    }
+}
+
 static void analyse(Ctx *c) {
     if (!c->direct) c->direct = new DirectSolver();
     DirectSolver &d = *c->direct;
@@ -1764,18 +1833,31 @@ static void analyse(Ctx *c) {
     const Model &m = c->model;
     (void)m;
     HostTick tick("direct analyse");
+    const bool shared = shared_ordering(c);
+    if (shared && c->dist_rank != 0) {
+        // rank 0 computes the ordering for everybody (share_ordering)
+        if (d.host_state == 1) { try { join_host_analysis(d); } catch (...) {} }
+        share_ordering(c);
+        d.host_state = 2;
+        tick.lap("ordering received from rank 0");
+    }
     if (d.host_state == 1) {
         d.host_state = 0;
         join_host_analysis(d);
         if (d.prefetch_n1 == c->n1) d.host_state = 2;    // (always, unless the partition rule and its host copy diverge)
         tick.lap("join prefetched host analysis");
     }
+    const bool computed_here = !(shared && c->dist_rank != 0);
     if (d.host_state != 2) {
         std::vector<int32_t> newidx(c->n_dof);
         PN_CUDA(cudaMemcpyAsync(newidx.data(), c->newidx.ptr, sizeof(int32_t) * c->n_dof, cudaMemcpyDeviceToHost, st));
         PN_CUDA(cudaStreamSynchronize(st));
         analyse_host(c, newidx, true, c->n1);
         d.host_state = 2;
+    }
+    if (shared && computed_here) {
+        share_ordering(c);
+        tick.lap("ordering sent to the other ranks");
     }
     const DirectSym &S = d.sym;
 

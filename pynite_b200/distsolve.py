@@ -71,6 +71,12 @@ def attach(engine, group=None):
             print('pynite_b200.distsolve: all-gather failed:', err)
             return 1
     _register(engine, rank, world, allgather)
+    # rank 0 computes the ordering for all ranks (share_ordering in pn_direct.cu): it gets the cores of the box less one
+    # per other rank, the others keep one worker thread (result zero fill)
+    import os
+    local_world = int(os.environ.get('LOCAL_WORLD_SIZE', str(world)) or world)
+    if local_world > 1:
+        engine.set_option('host_threads', max(1, (os.cpu_count() or 1) - local_world) if rank == 0 else 1)
     return rank, world
 
 

@@ -146,6 +146,13 @@ def test_solve_linear(eng, name, solver):
         assert rel_err(D[c], ref['D'][c]) < TOL_D, (c, rel_err(D[c], ref['D'][c]))
         assert rel_err(R[c], ref['Rxn'][c]) < TOL_D, (c, rel_err(R[c], ref['Rxn'][c]))
     assert st.kernel_launches > 0
+    if solver == 'direct':
+        # the DOF-type classes predicted from the element list are never contradicted by the pattern the reference
+        # produced: flat shell fixtures in an axis plane take three classes, everything else one
+        ctr = eng.counters()
+        assert ctr['dof_class_rejects'] == 0, ctr
+        flat = name in ('quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz', 'mat_foundation')
+        assert ctr['dof_classes'] == (3 if flat else 1), (name, ctr)
     # element end forces (Member3D.F/f, Quad3D.F, Plate3D.F, Spring3D.F)
     for c in range(A.factors.shape[0]):
         for kind in ('spring', 'member', 'quad', 'plate'):
