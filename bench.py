@@ -440,10 +440,12 @@ def run_ours(args, rank, local_rank, world):
     sup_bits = np.unpackbits(np.asarray(A.support, dtype=np.uint8).reshape(-1, 1), axis=1, bitorder='little')[:, :6].reshape(-1)
     nsf = np.asarray(A.nspring_flag, dtype=np.uint8).reshape(-1)
     n_rxn = int(np.count_nonzero((sup_bits != 0) | (((nsf & 1) != 0) & ((nsf & 2) != 0))))
-    rxn_bytes = R_host.nbytes if subtree else (n_rxn*my_combos*8 if n_rxn*8 < n_dof else R_host.nbytes)
+    rxn_bytes = n_rxn*n_out*8 if n_rxn*8 < n_dof else R_host.nbytes
     d2h = int(D_host.nbytes + rxn_bytes)
 
     e2e_phases = {}
+    if subtree:
+        eng.set_output_combos(shards[rank][0] if len(shards[rank]) else 0, len(shards[rank]))
 
     def e2e_step():
         t = [time.perf_counter()]
@@ -457,10 +459,8 @@ def run_ours(args, rank, local_rank, world):
         t.append(time.perf_counter())
         if subtree:
             # all ranks hold all of X after the solve; each delivers its share of the combinations to its host
-            eng.solve_linear(opts, reactions=False, download=False)
-            for k, cj in enumerate(shards[rank]):
-                eng.displacements(cj, out=D_host[k])
-                eng.reactions(cj, out=R_host[k])
+            # (pn_set_output_combos: one copy of the result reaches host memory, 1/N of it per rank)
+            eng.solve_linear(opts, reactions=True, D_out=D_host, R_out=R_host)
         else:
             eng.solve_linear(opts, reactions=True, D_out=D_host, R_out=R_host)
         t.append(time.perf_counter())

@@ -130,6 +130,12 @@ PN_EXPORT int pn_member_kg(pn_ctx *ctx, const double *P, double *out);
  * rejected).  Same solution up to rounding; counter "dof_classes" reports the number of classes in use.
  * "host_threads": OpenMP threads of the host worker (ordering, result zero fill). */
 PN_EXPORT int pn_set_option(pn_ctx *ctx, const char *name, int64_t value);
+/* Multi-GPU runs: every rank of the subtree-to-GPU solve (pn_set_distributed) ends with all displacements on its device,
+ * but only one copy of the result has to reach host memory.  After this call D_out / Rxn_out of pn_solve_linear and
+ * pn_solve_pdelta hold rows for combinations [combo0, combo0 + n_combo) only (arrays of n_combo x 6 N doubles);
+ * n_combo < 0 restores "all combinations".  FEModel3D._D / node.Rxn* (Analysis.py:847, 1059) are per-combination
+ * dictionaries, so a rank fills the entries of its share and the caller gathers them if it wants them everywhere. */
+PN_EXPORT int pn_set_output_combos(pn_ctx *ctx, int32_t combo0, int32_t n_combo);
 /* Optional hint, callable once every pn_set_nodes / pn_set_springs / pn_set_members / pn_set_quads / pn_set_plates call
  * of a model has been made: starts the host half of the direct solver's analysis (node graph, nested dissection,
  * fronts; the reference has no counterpart, SuperLU orders inside spsolve, Analysis.py:217) on a worker thread so

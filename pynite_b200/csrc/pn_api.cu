@@ -313,10 +313,21 @@ static bool reactions_compact(Ctx *c) {
 // Starts the zero fill of the caller's reaction array on the host worker.  The job queues behind the ordering of the
 // direct solver (same worker, FIFO), i.e. it runs while the device factorises and its threads do not compete with the
 // ordering, which is on the critical path.
+// combinations [*o0, *o0 + *on) go to the caller's host arrays (pn_set_output_combos; default: all)
+static void output_range(const Ctx *c, int *o0, int *on) {
+    const int nc = c->loads.n_combo;
+    *o0 = 0; *on = nc;
+    if (c->out_ncombo >= 0) {
+        *o0 = std::min<int>(std::max<int>(c->out_combo0, 0), nc);
+        *on = std::min<int>(c->out_ncombo, nc - *o0);
+    }
+}
+
 void reactions_prepare(Ctx *c, double *Rxn_out) {
     c->rxn_zero = std::future<void>();
     if (!Rxn_out || !reactions_compact(c)) return;
-    const int nc = c->loads.n_combo;
+    int o0 = 0, nc = 0;
+    output_range(c, &o0, &nc);
     const int64_t n_dof = c->n_dof;
     const int wt = host_worker_threads(c);
     c->rxn_zero = host_worker_submit([Rxn_out, nc, n_dof, wt]() {
@@ -334,15 +345,17 @@ void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
     tick.sync = false;
     build_incidence(c);
     tick.lap("incidence");
-    const int nc = c->loads.n_combo;
+    int o0 = 0, nc = 0;
+    output_range(c, &o0, &nc);
+    if (!nc) return;
     const int64_t n_dof = c->n_dof;
     const bool compact = reactions_compact(c);
     const int64_t nr = (int64_t)c->h_rxn_dofs.size();
     if (!compact) {
         DevBuf<double> &rx = c->work_rx;
         rx.resize((int64_t)nc * n_dof);
-        compute_reactions_batch(c, 0, nc, pdelta, nullptr, 0, rx.ptr);
-        download(rx, Rxn_out, c->stream);
+        compute_reactions_batch(c, o0, nc, pdelta, nullptr, 0, rx.ptr);
+        PN_CUDA(cudaMemcpyAsync(Rxn_out, rx.ptr, sizeof(double) * (size_t)nc * n_dof, cudaMemcpyDeviceToHost, c->stream));
         PN_CUDA(cudaStreamSynchronize(c->stream));
         return;
     }
@@ -350,7 +363,7 @@ void reactions_out(Ctx *c, bool pdelta, double *Rxn_out) {
     c->rxn_rows.resize(nr * nc);
     c->h_rxn_rows.resize((size_t)(nr * nc));
     if (nr) {
-        compute_reactions_batch(c, 0, nc, pdelta, c->rxn_dofs.ptr, nr, c->rxn_rows.ptr);
+        compute_reactions_batch(c, o0, nc, pdelta, c->rxn_dofs.ptr, nr, c->rxn_rows.ptr);
         download(c->rxn_rows, c->h_rxn_rows.data(), c->stream);
     }
     tick.lap("launches enqueued");
@@ -394,10 +407,15 @@ void solve_linear_all(Ctx *c, const pn_solve_opts &o, double *D_out = nullptr) {
         }
         merge_displacements(c, j0, s);
         if (D_out) {
-            PN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-            PN_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-            PN_CUDA(cudaMemcpyAsync(D_out + (int64_t)j0 * c->n_dof, c->D_all.ptr + (int64_t)j0 * c->n_dof,
-                                    sizeof(double) * (size_t)s * c->n_dof, cudaMemcpyDeviceToHost, c->stream2));
+            int o0 = 0, on = 0;
+            output_range(c, &o0, &on);
+            const int a = std::max(j0, o0), b = std::min(j0 + s, o0 + on);      // this batch's part of the output range
+            if (b > a) {
+                PN_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+                PN_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+                PN_CUDA(cudaMemcpyAsync(D_out + (int64_t)(a - o0) * c->n_dof, c->D_all.ptr + (int64_t)a * c->n_dof,
+                                        sizeof(double) * (size_t)(b - a) * c->n_dof, cudaMemcpyDeviceToHost, c->stream2));
+            }
         }
         if (c->n1 && s) {
             const double worst = residual_check(c, c->blk[0].vals.ptr, 0, s, o, o.check_stability != 0);
@@ -628,6 +646,14 @@ int pn_set_option(pn_ctx *ctx, const char *name, int64_t value) {
         if ((int)value != c->opt_dof_classes) { c->opt_dof_classes = (int)value; direct_invalidate(c); }
     }
     else throw ArgError(std::string("pn_set_option: unknown option ") + name);
+    PN_API_END
+}
+
+int pn_set_output_combos(pn_ctx *ctx, int32_t combo0, int32_t n_combo) {
+    PN_API_BEGIN(ctx)
+    if (n_combo >= 0 && combo0 < 0) throw ArgError("pn_set_output_combos: negative first combination");
+    c->out_combo0 = n_combo < 0 ? 0 : combo0;
+    c->out_ncombo = n_combo < 0 ? -1 : n_combo;
     PN_API_END
 }
 
@@ -943,7 +969,11 @@ int pn_solve_pdelta(pn_ctx *ctx, const pn_solve_opts *opts, double *D_out, doubl
         }
     }
     c->solved = c->solved_pdelta = true;
-    if (D_out) download(c->D_all, D_out, st);
+    if (D_out) {
+        int o0 = 0, on = 0;
+        output_range(c, &o0, &on);
+        if (on) PN_CUDA(cudaMemcpyAsync(D_out, c->D_all.ptr + (int64_t)o0 * c->n_dof, sizeof(double) * (size_t)on * c->n_dof, cudaMemcpyDeviceToHost, st));
+    }
     PN_CUDA(cudaStreamSynchronize(st));
     reactions_out(c, true, Rxn_out);
     c->stats.kernel_launches = c->launches;

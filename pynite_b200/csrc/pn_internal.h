@@ -298,6 +298,9 @@ struct Ctx {
     DevBuf<int64_t> tc_group_start;      // sub-member range of every physical member
     int64_t tc_n_groups = 0;
     bool tc_any_member_mode = false;
+    // pn_set_output_combos: the host arrays of pn_solve_linear / pn_solve_pdelta hold combinations [out_combo0,
+    // out_combo0 + out_ncombo) only (out_ncombo < 0: all).  A rank of a multi-GPU solve delivers its share.
+    int32_t out_combo0 = 0, out_ncombo = -1;
     // multi-GPU direct solve (pn_set_distributed): this context is rank `dist_rank` of `dist_world`
     int dist_rank = 0, dist_world = 1;
     pn_allgather_fn dist_allgather = nullptr;

@@ -124,6 +124,7 @@ SIGNATURES = {
     'pn_prefetch_analysis': (ct.c_int, [_P]),
     'pn_k11_col_range': (ct.c_int, [_P, ct.c_int64, ct.c_int64, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64)]),
     'pn_set_option': (ct.c_int, [_P, ct.c_char_p, ct.c_int64]),
+    'pn_set_output_combos': (ct.c_int, [_P, ct.c_int32, ct.c_int32]),
     'pn_dev_spmm_k11_rows': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
     'pn_dev_block_jacobi_setup': (ct.c_int, [_P]),
     'pn_dev_block_jacobi_nodes': (ct.c_int, [_P, ct.c_int32, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p]),
@@ -248,6 +249,12 @@ class Engine:
         lo, hi = ct.c_int64(0), ct.c_int64(0)
         self._check(self._lib.pn_k11_col_range(self._h, row0, row1, ct.byref(lo), ct.byref(hi)))
         return lo.value, hi.value
+
+    def set_output_combos(self, combo0, n_combo):
+        """`solve_linear` / `solve_pdelta` deliver combinations [combo0, combo0 + n_combo) to the host arrays (n_combo < 0:
+        all).  A rank of a multi-GPU solve downloads its share only."""
+        self._check(self._lib.pn_set_output_combos(self._h, int(combo0), int(n_combo)))
+        self._out_range = None if n_combo < 0 else (int(combo0), int(n_combo))
 
     def set_option(self, name, value):
         self._check(self._lib.pn_set_option(self._h, name.encode(), int(value)))
@@ -379,8 +386,13 @@ class Engine:
 
     def _solve(self, fn, opts, want_reactions, D_out=None, R_out=None, download=True):
         n = self.n_dof
-        D = (D_out if D_out is not None else np.empty((self.n_combo, n))) if download else None
-        R = (R_out if R_out is not None else np.empty((self.n_combo, n))) if want_reactions else None
+        rng = getattr(self, '_out_range', None)
+        rows = self.n_combo if rng is None else max(0, min(rng[1], self.n_combo - rng[0]))
+        D = (D_out if D_out is not None else np.empty((rows, n))) if download else None
+        R = (R_out if R_out is not None else np.empty((rows, n))) if want_reactions else None
+        for a in (D, R):
+            if a is not None and a.size < rows*n:
+                raise ValueError('solve: host array smaller than the output range (set_output_combos)')
         st = Stats()
         rc = fn(self._h, ct.byref(opts) if opts is not None else None, _ptr(D, _F64P), _ptr(R, _F64P), ct.byref(st))
         self._check(rc)

@@ -653,6 +653,26 @@ def test_dof_class_ordering_equals_node_ordering(eng, case):
             assert rel_err(out[1][0][c], Do[c].reshape(-1)) < TOL_D
 
 
+def test_output_combo_range(eng):
+    """`pn_set_output_combos`: the host arrays of a solve hold a range of the combinations only (a rank of a multi-GPU run
+    delivers its share); same rows as the full download, compact and full reaction paths."""
+    from pynite_b200 import synthetic
+    for A in (synthetic.quad_plate_arrays(n=40, n_combos=5), synthetic.moment_frame_arrays(bays_x=3, bays_z=2, stories=4, n_combos=5)):
+        _upload(eng, A)
+        D, R, _ = eng.solve_linear(eng.make_opts())
+        try:
+            eng.set_output_combos(1, 3)
+            D1, R1, _ = eng.solve_linear(eng.make_opts())
+            assert D1.shape[0] == 3 and np.array_equal(D1, D[1:4]) and np.array_equal(R1, R[1:4])
+            eng.set_output_combos(4, 9)                     # clipped to the last combination
+            D2, R2, _ = eng.solve_linear(eng.make_opts())
+            assert D2.shape[0] == 1 and np.array_equal(D2[0], D[4]) and np.array_equal(R2[0], R[4])
+        finally:
+            eng.set_output_combos(0, -1)
+        D3, R3, _ = eng.solve_linear(eng.make_opts())
+        assert np.array_equal(D3, D) and np.array_equal(R3, R)
+
+
 def test_subtree_distributed_solve_on_eight_ranks():
     """The class-split tree (two roots on the top level, cost-balanced cut) shared out over 8 ranks, against one rank."""
     from pynite_b200 import distsolve, synthetic
