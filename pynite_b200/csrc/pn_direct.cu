@@ -2263,14 +2263,16 @@ static void build_dist_plan(Ctx *c) {
     }
     cudaStream_t st = c->stream;
     {
-        std::vector<int32_t> rows;
-        rows.reserve((size_t)(P.pos_hi[rank] - P.pos_lo[rank]) + 16384);
+        // (ascending row numbers through a mark array: sorting 800 000 indices cost 20 ms of every analysis)
+        std::vector<uint8_t> mark((size_t)S.n, 0);
         for (int l = 0; l < nl; ++l)
             for (int q = (l <= cut ? P.lo[l] : d.level_ptr[l]); q < (l <= cut ? P.hi[l] : d.level_ptr[l + 1]); ++q) {
                 const FrontSym &fs = S.fronts[S.level_fronts[q]];
-                for (int64_t pp = fs.pos_start; pp < (int64_t)fs.pos_start + fs.ns; ++pp) rows.push_back(S.s_pos_dof[(size_t)pp]);
+                for (int64_t pp = fs.pos_start; pp < (int64_t)fs.pos_start + fs.ns; ++pp) mark[(size_t)S.s_pos_dof[(size_t)pp]] = 1;
             }
-        std::sort(rows.begin(), rows.end());
+        std::vector<int32_t> rows;
+        rows.reserve((size_t)(P.pos_hi[rank] - P.pos_lo[rank]) + 16384);
+        for (int64_t r = 0; r < S.n; ++r) if (mark[(size_t)r]) rows.push_back((int32_t)r);
         P.n_res_rows = (int64_t)rows.size();
         P.res_rows.upload(rows.data(), P.n_res_rows, st);
     }
