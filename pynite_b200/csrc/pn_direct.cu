@@ -1860,6 +1860,12 @@ static void analyse(Ctx *c) {
         tick.lap("ordering sent to the other ranks");
     }
     const DirectSym &S = d.sym;
+    // the index lists are page-locked: their DMA runs while the host builds the front table and the children lists
+    d.fidx.upload(S.fidx.data(), (int64_t)S.fidx.size(), st);
+    d.fpos.upload(S.fpos.data(), (int64_t)S.fpos.size(), st);
+    d.rel.upload(S.rel.data(), (int64_t)S.rel.size(), st);
+    d.perm_pos.upload(S.perm_pos.data(), (int64_t)S.perm_pos.size(), st);
+    d.dof_front_lm.upload(d.h_dof_front_lm.data(), (int64_t)d.h_dof_front_lm.size(), st);     // filled by analyse_host
 
     // level-major renumbering of fronts
     int nf = (int)S.fronts.size();
@@ -1896,6 +1902,7 @@ static void analyse(Ctx *c) {
         d.level_f_total[l] = foff; d.level_n_total[l] = noff;
     }
     if (d.n_levels > 255) throw ArgError("direct solver: elimination tree too deep");
+    tick.lap("maps: front table");
     // Subtree-to-GPU plan first: the permanent factor (panels, U12, diagonal inverses) is stored only for the fronts
     // this rank factorises -- its subtrees and the replicated top -- so N GPUs hold an N times larger bottom of the tree.
     build_dist_plan(c);
@@ -1910,25 +1917,25 @@ static void analyse(Ctx *c) {
         }
     }
     {
-        std::vector<std::vector<std::pair<int32_t, int32_t>>> kids(nf);      // (child rank, child id), level-major ids
-        for (int q = 0; q < nf; ++q)
-            if (d.h_fronts[q].parent >= 0) kids[d.h_fronts[q].parent].push_back({d.h_fronts[q].child_rank, q});
+        // children of every front in child-rank order (level-major ids): counting sort, ranks are 0 .. #children - 1
         std::vector<int32_t> cptr(nf + 1, 0), cidx;
+        for (int q = 0; q < nf; ++q)
+            if (d.h_fronts[q].parent >= 0) ++cptr[d.h_fronts[q].parent + 1];
+        for (int q = 0; q < nf; ++q) cptr[q + 1] += cptr[q];
+        cidx.assign((size_t)cptr[nf], -1);
         for (int q = 0; q < nf; ++q) {
-            std::sort(kids[q].begin(), kids[q].end());
-            for (auto &kc : kids[q]) cidx.push_back(kc.second);
-            cptr[q + 1] = (int32_t)cidx.size();
+            const FrontDev &F = d.h_fronts[q];
+            if (F.parent < 0) continue;
+            const int32_t slot = cptr[F.parent] + F.child_rank;
+            if (slot >= cptr[F.parent + 1] || cidx[slot] >= 0) throw ArgError("direct solver: inconsistent child ranks");
+            cidx[slot] = q;
         }
         d.child_ptr.upload(cptr.data(), nf + 1, st);
         d.child_idx.upload(cidx.data(), (int64_t)cidx.size(), st);
         PN_CUDA(cudaStreamSynchronize(st));
     }
+    tick.lap("maps: dist plan + children");
     d.fronts.upload(d.h_fronts.data(), nf, st);
-    d.fidx.upload(S.fidx.data(), (int64_t)S.fidx.size(), st);
-    d.fpos.upload(S.fpos.data(), (int64_t)S.fpos.size(), st);
-    d.rel.upload(S.rel.data(), (int64_t)S.rel.size(), st);
-    d.perm_pos.upload(S.perm_pos.data(), (int64_t)S.perm_pos.size(), st);
-    d.dof_front_lm.upload(d.h_dof_front_lm.data(), (int64_t)d.h_dof_front_lm.size(), st);     // filled by analyse_host
     d.L.resize(l_total); d.U.resize(u_total); d.inv.resize(inv_total);
     d.ll_flags.resize(inv_total / (2 * NB * NB) * LL_MAX_CHUNKS + 1);
     PN_CUDA(cudaMemsetAsync(d.ll_flags.ptr, 0, sizeof(uint32_t) * (inv_total / (2 * NB * NB) * LL_MAX_CHUNKS + 1), st));
@@ -1989,6 +1996,7 @@ static void analyse(Ctx *c) {
     }
     d.status.resize(1);
     d.status.zero(st);
+    tick.lap("maps: uploads + factor storage");
     // per-entry destination maps
     const CsrBlock &A = c->blk[0];
     DevBuf<int32_t> &ent_row = c->sym_ent_row;
@@ -2021,6 +2029,7 @@ static void analyse(Ctx *c) {
     int status = 0;
     PN_CUDA(cudaMemcpyAsync(&status, d.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     PN_CUDA(cudaStreamSynchronize(st));
+    tick.lap("maps: entry destinations");
     if (status == 2 && d.n_classes > 1) {
         // an assembled entry joins two of the predicted DOF-type classes: order again with one class (node-based)
         d.classes_rejected = true;
