@@ -462,10 +462,10 @@ def test_load_stepping_with_a_spring_that_flips_mid_stepping():
     subs = [s for pm in m.members.values() for s in pm.sub_members.values()]
     for c, combo in enumerate(m.load_combos):      # first combos are no longer resident on the engine
         for k, sub in enumerate(subs):
-            assert rel_err(sub.F(combo).reshape(-1), ref['member_F'][c][k]) < 1e-8, (combo, k)
-            assert rel_err(sub.f(combo).reshape(-1), ref['member_f'][c][k]) < 1e-8, (combo, k)
+            assert rel_err(sub.F(combo).reshape(-1), ref['member_F'][c][k]) < TOL_D, (combo, k)
+            assert rel_err(sub.f(combo).reshape(-1), ref['member_f'][c][k]) < TOL_D, (combo, k)
         sp = m.springs['TIE']
-        assert rel_err(sp.F(combo).reshape(-1), ref['spring_F'][c][0]) < 1e-8        # also while inactive (Spring3D.D :222-225)
+        assert rel_err(sp.F(combo).reshape(-1), ref['spring_F'][c][0]) < TOL_D       # also while inactive (Spring3D.D :222-225)
 
 
 def test_inspection_calls_do_not_disturb_results():
@@ -482,7 +482,7 @@ def test_inspection_calls_do_not_disturb_results():
     assert K.shape == (36, 36)
     sub = [s for pm in m.members.values() for s in pm.sub_members.values()][0]
     for c, combo in enumerate(combos):
-        assert rel_err(sub.F(combo).reshape(-1), ref['member_F'][c][0]) < 1e-8, combo
+        assert rel_err(sub.F(combo).reshape(-1), ref['member_F'][c][0]) < TOL_D, combo
         assert rel_err(m._D[combo].reshape(-1), ref['D'][c]) < TOL_D
 
 
@@ -651,6 +651,20 @@ def test_dof_class_ordering_equals_node_ordering(eng, case):
         Do, Ro = om.solve_linear(A)
         for c in range(len(Do)):
             assert rel_err(out[1][0][c], Do[c].reshape(-1)) < TOL_D
+
+
+def test_pcg_reports_non_convergence(eng):
+    """`PN_ERR_NOT_CONVERGED`: a PCG run that hits its iteration cap raises instead of returning a partial answer (the
+    reference has no iterative solver; its analogue is the `singular` exception of `Analysis.py:239`)."""
+    from pynite_b200 import synthetic
+    from pynite_b200.engine import NotConverged
+    A = synthetic.quad_plate_arrays(n=40, n_combos=2)
+    _upload(eng, A)
+    with pytest.raises(NotConverged):
+        eng.solve_linear(eng.make_opts(solver='pcg', tol=1e-13, max_iter=5))
+    D, R, st = eng.solve_linear(eng.make_opts(solver='pcg', tol=1e-12, max_iter=200000))       # the context stays usable
+    Dd, Rd, _ = eng.solve_linear(eng.make_opts())
+    assert rel_err(D, Dd) < 1e-8 and st.iterations > 5
 
 
 def test_output_combo_range(eng):
