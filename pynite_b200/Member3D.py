@@ -3,7 +3,7 @@
 `Member3D` carries what `Pynite/Member3D.py:37-105` stores for the stiffness path (nodes, material,
 section, roll angle, loads, releases, tension/compression-only flags, per-combo activity).  All
 stiffness math (`_ke_unc` :176, `ke` :147, `kg` :210, `T` :933, `Ke` :1038, `fer` :742, `f` :872)
-runs in the sm_100a member kernels (`csrc/elem_member.cuh`); `f()/F()` here read the end forces the
+runs in the sm_100a member kernels (`csrc/elem_line.cuh`, `csrc/pn_elements.cu`); `f()/F()` here read the end forces the
 GPU solve produced.
 
 `PhysMember.descritize` restates `Pynite/PhysMember.py:37-200`: a physical member is split at every
