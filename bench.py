@@ -518,8 +518,15 @@ def run_ours(args, rank, local_rank, world):
         spmm_bytes = sizes.nnz11*12 + (sizes.n1 + 1)*4 + 2*sizes.n1*s*8
         kms, n = prof['spmm']
         a = spmm_bytes/(kms/n*1e-3)/1e9
+        # 10 FP64 instructions per stored entry and column (TwoProd by fma, TwoSum, two accumulations; k_residual_dd in
+        # pn_sparse.cu), none of them contractable: against the FP64 issue rate (half the DFMA flop rate measured by
+        # tools/microbench/fp64_pipes.cu, 36.7 TFLOP/s) the kernel is FP64-bound before it is HBM-bound
+        dd_instr = 10.0*sizes.nnz11*s
+        dd_floor_ms = dd_instr/(36.7e12/2)*1e3
         rooflines['residual_dd(K11, %d rhs, double-double)' % s] = {'bound': 'hbm', 'achieved': a, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': a/hbm_peak,
-                                              'algorithmic_bytes': spmm_bytes, 'ms': kms/n}
+                                              'algorithmic_bytes': spmm_bytes, 'ms': kms/n, 'fp64_instructions': dd_instr,
+                                              'fp64_issue_floor_ms': dd_floor_ms, 'frac_of_fp64_issue_rate': dd_floor_ms/(kms/n),
+                                              'note': 'FP64-issue-bound: the HBM fraction is reported for comparison with the plain SpMM'}
     if 'lu_update' in prof and first_stats.get('update_flops', 0) > 0:
         kms, n = prof['lu_update']
         a = first_stats['update_flops']*K/(kms*1e-3)/1e12
