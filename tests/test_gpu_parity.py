@@ -616,7 +616,7 @@ def test_midsize_plate_150_against_oracle(eng, classes):
         assert rel_err(R[c], Ro[c].reshape(-1)) < TOL_D
 
 
-@pytest.mark.parametrize('case', ['plate_xy', 'plate_yz', 'mat', 'frame'])
+@pytest.mark.parametrize('case', ['plate_xy', 'plate_yz', 'mat', 'frame', 'plate_jitter', 'plate_ortho'])
 def test_dof_class_ordering_equals_node_ordering(eng, case):
     """`pn_set_option("dof_classes")`: the class-split ordering (1, default), the node-based ordering (0) and a prediction
     the device verification has to reject (2) give the same displacements and reactions; flat shell models use three
@@ -624,6 +624,12 @@ def test_dof_class_ordering_equals_node_ordering(eng, case):
     from pynite_b200 import synthetic
     if case == 'plate_xy':
         A = synthetic.quad_plate_arrays(n=72, n_combos=3)
+    elif case == 'plate_jitter':                # general in-plane geometry: still planar, still three classes
+        A = synthetic.quad_plate_arrays(n=56, n_combos=2, jitter=0.1)
+    elif case == 'plate_ortho':                 # kx_mod != ky_mod: unsymmetric membrane block, general LU mode
+        A = synthetic.quad_plate_arrays(n=64, n_combos=2)
+        A.quad_props = np.ascontiguousarray(A.quad_props)
+        A.quad_props[:, 3] = 0.6
     elif case == 'mat':
         A = synthetic.quad_plate_arrays(n=60, n_combos=2, mat_springs=0.1)
     elif case == 'frame':
