@@ -493,16 +493,16 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
     std::vector<int32_t> &vfront = out.s_vfront, &vorder = out.s_vorder;      // vorder: rank of the vertex in elimination order
     vfront.resize(nv); vorder.resize(nv);
     std::vector<int32_t> &vert_seq = out.s_vert_seq;   // vertices in elimination order
-    vert_seq.clear();
-    vert_seq.reserve(nv);
     std::vector<int32_t> &f_vbeg = out.s_f_vbeg;
     f_vbeg.assign(nf0 + 1, 0);
+    for (int32_t f = 0; f < nf0; ++f) f_vbeg[f + 1] = f_vbeg[f] + (int32_t)front_verts[f].size();
+    if (f_vbeg[nf0] != nv) throw std::runtime_error("direct_symbolic: vertices lost in dissection");
+    vert_seq.resize(nv);
+#pragma omp parallel for schedule(dynamic, 256)
     for (int32_t f = 0; f < nf0; ++f) {
-        f_vbeg[f] = (int32_t)vert_seq.size();
-        for (int32_t v : front_verts[f]) { vfront[v] = f; vorder[v] = (int32_t)vert_seq.size(); vert_seq.push_back(v); }
+        int32_t o = f_vbeg[f];
+        for (int32_t v : front_verts[f]) { vfront[v] = f; vorder[v] = o; vert_seq[o++] = v; }
     }
-    f_vbeg[nf0] = (int32_t)vert_seq.size();
-    if ((int32_t)vert_seq.size() != nv) throw std::runtime_error("direct_symbolic: vertices lost in dissection");
     lap("orders");
 
     // boundary vertex sets of the node tree, bottom-up (as vertex orders, ascending); fronts of one depth are independent
@@ -651,8 +651,6 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
     lap("positions");
 
     // fronts, index lists
-    std::vector<std::vector<int32_t>> children(nf);
-    for (int32_t f = 0; f < nf; ++f) if (parent_of[f] >= 0) children[parent_of[f]].push_back(f);
     std::vector<int32_t> depth(nf, 0);
     int32_t maxdepth = 0;
     for (int32_t f = nf - 1; f >= 0; --f) {
@@ -687,10 +685,15 @@ void direct_symbolic(int64_t n, int32_t nv, const int32_t *vstart, const double 
         out.factor_entries += (int64_t)(F.ns + F.nb) * F.ns + (int64_t)F.ns * F.nb;
         out.factor_flops += 2.0 / 3.0 * ns * ns * ns + 2.0 * ns * ns * nbv + 2.0 * ns * nbv * nbv;
     }
-    for (int32_t f = 0; f < nf; ++f) {
-        int32_t rank = 0;
-        for (int32_t c : children[f]) out.fronts[c].child_rank = rank++;
-        out.max_children = std::max(out.max_children, rank);
+    {
+        // child ranks in ascending child id (children precede their parent, so one counter per parent suffices)
+        std::vector<int32_t> seen(nf, 0);
+        for (int32_t f = 0; f < nf; ++f) {
+            const int32_t p = parent_of[f];
+            if (p < 0) continue;
+            out.fronts[f].child_rank = seen[p]++;
+            out.max_children = std::max(out.max_children, seen[p]);
+        }
     }
     lap("front sizes");
     // inverse of perm_pos for index lists in K11 numbering
