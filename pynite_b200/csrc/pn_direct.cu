@@ -647,10 +647,14 @@ __device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *are
             a[r][c] = (i < bs && j < bs) ? A[(int64_t)si * n + sj] : (i == j ? 1.0 : 0.0);
         }
     PN_CLK(1);
+    // rows / columns >= bs are identity padding: their pivot steps are exact no-ops and are skipped (a 16-pivot tail
+    // block of a 144-pivot leaf front used to cost a full 64-step chain); their reciprocal pivots are 1
+    if (t >= bs && t < NB) rdiag[t] = 1.0;
 #pragma unroll
     for (int qb = 0; qb < 4; ++qb) {
         for (int pp = 0; pp < 16; ++pp) {
             const int p = 16 * qb + pp;
+            if (p >= bs) break;                  // (uniform; the trip counts stay compile-time constants)
             double *R = rowb + (pp & 1) * NB, *Cc = colb + (pp & 1) * NB;
             if (ti == pp) {
 #pragma unroll
@@ -739,6 +743,14 @@ __device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *are
     // thread = (matrix m, row group w of 8 rows, column lane): the B operand row is read contiguously across the
     // lanes, the A operand as warp-wide broadcasts
     const int m = t >> 7, r0 = 8 * ((t >> 5) & 3);
+    if (bs <= 32) {
+        // the off-diagonal blocks of a block with at most 32 real pivots are zero (identity padding): no GEMMs
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (m == 0) Li[32 + r0 + r][lane] = 0.0; else Ui[r0 + r][32 + lane] = 0.0;
+        }
+        __syncthreads();
+    } else {
     {
         double acc[8];
 #pragma unroll
@@ -789,6 +801,7 @@ __device__ __forceinline__ void diag_step(const FrontDev &F, int kb, double *are
         }
     }
     __syncthreads();
+    }
     PN_CLK(5);
     double *out = inv + F.inv_off + (int64_t)(kb / NB) * (2 * NB * NB);
     for (int e = t; e < NB * NB; e += blockDim.x) {
