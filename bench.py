@@ -469,9 +469,12 @@ def run_ours(args, rank, local_rank, world):
 
     e2e_step()
     barrier()
+    e2e_each = []
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
+        ts = time.perf_counter()
         e2e_step()
+        e2e_each.append(round(1e3*(time.perf_counter() - ts), 2))
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = units_per_step_all*args.e2e_steps/t_e2e
@@ -573,7 +576,7 @@ def run_ours(args, rank, local_rank, world):
             'ms_per_step': ms/args.steps, 'ms_per_step_profiled_pass': ms_profiled/args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(args, world),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': 1e3*t_e2e/args.e2e_steps, 'steps': args.e2e_steps, 'host_phases_ms_last_step': e2e_phases,
+                    'ms_per_step': 1e3*t_e2e/args.e2e_steps, 'steps': args.e2e_steps, 'ms_each_step': e2e_each, 'host_phases_ms_last_step': e2e_phases,
                     'device_phases_ms_last_step': {k: round(v, 2) for k, v in e2e_stats.items() if k.startswith('ms_')},
                     'includes': 'pn_set_* uploads, symbolic phase, elimination-tree analysis, assembly, solve, reactions, D and Rxn copies to pinned host memory'},
             'gpu_launches': int(st['kernel_launches']), 'clocks': clocks,
