@@ -111,7 +111,7 @@ void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xy
     // vstart needs an end sentinel: rows are contiguous and ascending over vertices
     vstart.push_back((int32_t)n1);
     // count, fill (with duplicates, in any order: atomics), then sort + unique per vertex
-    std::vector<int64_t> &deg = sc.deg, &ptr = sc.ptr, &fill = sc.fill, &cnt = sc.cnt;
+    std::vector<int64_t> &deg = sc.deg, &ptr = sc.ptr, &fill = sc.fill;
     std::vector<int32_t> &raw = sc.raw;
     deg.assign(nv + 1, 0);
     for (const ConnView &cv : conn) {
@@ -161,7 +161,6 @@ void build_vertex_graph(int64_t n_nodes, const int32_t *newidx, const double *xy
     // The lists keep their duplicates (a neighbour shared by two elements appears twice) and the order the threads
     // produced: the dissection only asks "does v touch a vertex of the other side" and the boundary sets are sorted and
     // made unique where they are built, so neither shows in the result; sorting 250 000 lists cost more than it saved.
-    (void)cnt;
     adj_ptr.assign(ptr.begin(), ptr.end());
     adj.swap(raw);
 }
@@ -207,6 +206,7 @@ struct Builder {
         }
         const bool par = verts.size() > 16384;
         const int64_t nvs = (int64_t)verts.size();
+        const int64_t verts_n = nvs;              // (verts is released before the recursion)
         // the large subproblems near the root are few, so their passes over the vertex set are cut into chunks that run
         // as tasks (bounding box, side of the cut, contact with the other side, ordered compaction): the serial passes
         // of the top three levels were half of the ordering time.  Chunk results are combined in chunk order, so the
@@ -338,7 +338,9 @@ struct Builder {
         }
         std::vector<int32_t>().swap(verts);
         SubTree ta, tb;
-        if (par) {
+        // the two halves as tasks down to 2 048 vertices: with the 16 384 of the chunked passes there were 16 serial
+        // subproblems for 15 threads, i.e. two rounds
+        if (verts_n > 2048) {
 #pragma omp task shared(ta, A)
             ta = dissect(A);
 #pragma omp task shared(tb, B)
