@@ -68,11 +68,14 @@ class FEModel3D:
         return name
 
     def unique_name(self, dictionary, prefix):
-        """First unused prefix+integer name (reference helper used by mesh builders)."""
-        i = 1
-        while prefix + str(i) in dictionary:
+        """Next available name for a dictionary of objects (`FEModel3D.py:2882-2901`): prefix + (count + 1), bumped
+        until unused -- the names the mesh builders hand out are API-visible, so the rule is the reference's."""
+        name = prefix + str(len(dictionary) + 1)
+        i = 2
+        while name in dictionary:
+            name = prefix + str(len(dictionary) + i)
             i += 1
-        return prefix + str(i)
+        return name
 
     def _nodes_by_name(self, *names):
         try:
@@ -141,6 +144,28 @@ class FEModel3D:
         name = self._auto_name(name, self.quads, 'Q', 'Quad')
         n = self._nodes_by_name(i_node, j_node, m_node, n_node)
         self.quads[name] = Quad3D(name, n[0], n[1], n[2], n[3], t, material_name, self, kx_mod, ky_mod)
+        self.solution = None
+        return name
+
+    def add_rectangle_mesh(self, name, mesh_size, width, height, thickness, material_name, kx_mod=1.0, ky_mod=1.0,
+                           origin=(0, 0, 0), plane='XY', x_control=None, y_control=None, start_node=None,
+                           start_element=None, element_type='Quad'):
+        """`FEModel3D.add_rectangle_mesh` (:617-683).  The mesh is generated by `model.meshes[name].generate()` or by the
+        next analysis (`Analysis._prepare_model` :53-56), as in the reference."""
+        from pynite_b200.Mesh import RectangleMesh
+        if name:
+            if name in self.meshes:
+                raise NameError(f"Mesh name '{name}' already exists")
+        else:
+            name = self.unique_name(self.meshes, 'MSH')
+        if start_node is None:
+            start_node = self.unique_name(self.nodes, 'N')
+        if element_type == 'Rect' and start_element is None:
+            start_element = self.unique_name(self.plates, 'R')
+        elif element_type == 'Quad' and start_element is None:
+            start_element = self.unique_name(self.quads, 'Q')
+        self.meshes[name] = RectangleMesh(mesh_size, width, height, thickness, material_name, self, kx_mod, ky_mod, origin,
+                                          plane, x_control, y_control, start_node, start_element, element_type=element_type)
         self.solution = None
         return name
 

@@ -548,6 +548,16 @@ def shell_stress(model, kind, elem_id, combo_name, u, v, local):
     return run.force_cache[key][elem_id]
 
 
+def shell_stress_points(model, kind, combo_name, pts, local):
+    """[count][n_pts][9] results of every quad / plate of the model at a list of points for a solved combo: one
+    `pn_shell_stresses` launch (the mesh queries `Mesh.max_shear` ... read corners + centre of all elements at once)."""
+    run = model._run
+    if run is None or combo_name not in model._D:
+        raise KeyError(f"load combination '{combo_name}' has not been analysed")
+    j = _make_resident(model, combo_name)
+    return _engine(model).shell_stresses(kind, j, 1, [[float(u), float(v)] for u, v in pts], local)[0]
+
+
 def _rotate_saved(model, kind, F):
     """Global -> local end forces for results saved from an earlier combo of a per-combo analysis."""
     out = np.empty_like(F)

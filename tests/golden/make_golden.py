@@ -167,6 +167,21 @@ def flatten_pair(build, ref, mode):
     return out
 
 
+MESH_QUERIES = [('shear', d) for d in ('Qx', 'Qy', 'QX', 'QY')] + [('moment', d) for d in ('Mx', 'My', 'Mxy', 'MX', 'MY', 'MZ')] + \
+               [('membrane', d) for d in ('Sx', 'Sy', 'Sxy', 'SX', 'SY')]
+
+
+def mesh_extremes(ref):
+    """`Mesh.max_* / min_*` (`Mesh.py:172-716`) of every mesh for every combination: [mesh][combo][query][max, min]."""
+    out = np.zeros((len(ref.meshes), len(ref.load_combos), len(MESH_QUERIES), 2))
+    for a, mesh in enumerate(ref.meshes.values()):
+        for b, combo in enumerate(ref.load_combos):
+            for q, (what, direction) in enumerate(MESH_QUERIES):
+                out[a, b, q, 0] = getattr(mesh, 'max_' + what)(direction, combo)
+                out[a, b, q, 1] = getattr(mesh, 'min_' + what)(direction, combo)
+    return {'ref_mesh_extremes': out}
+
+
 def main(argv):
     names = argv[1:] or list(models.SMALL_MODELS.keys())
     for name in names:
@@ -174,6 +189,8 @@ def main(argv):
         ref = reference_run(build, mode)
         data = collect(ref, mode)
         data.update(flatten_pair(build, ref, mode))
+        if getattr(ref, 'meshes', None):
+            data.update(mesh_extremes(ref))
         data['mode'] = np.array(mode)
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **data)

@@ -492,6 +492,95 @@ def tc_load_steps(FE):
     return m
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# `FEModel3D.add_rectangle_mesh` (`Mesh.py:719-1096`): every case returns a model whose meshes have been generated.
+# tests/golden/make_mesh_golden.py runs them with the reference and stores names, coordinates and connectivity.
+# ---------------------------------------------------------------------------------------------------------------------
+def _mesh_model(FE):
+    m = FE()
+    m.add_material('Conc', 3605.0, 1540.6, 0.17, 8.68e-5)
+    return m
+
+
+def rect_mesh_basic(FE):
+    m = _mesh_model(FE)
+    m.add_rectangle_mesh('M1', 1.0, 10.0, 6.0, 8.0, 'Conc')
+    m.meshes['M1'].generate()
+    return m
+
+
+def rect_mesh_uneven_yz_rect(FE):
+    """mesh size that does not divide the sides, YZ plane, shifted origin, rectangular plate elements"""
+    m = _mesh_model(FE)
+    m.add_rectangle_mesh('W', 1.0, 7.3, 4.1, 6.0, 'Conc', origin=[2.5, -1.25, 40.0], plane='YZ', element_type='Rect')
+    m.meshes['W'].generate()
+    return m
+
+
+def rect_mesh_controls_xz(FE):
+    """control points (one of them a near duplicate of an edge, one outside the mesh) in the XZ plane"""
+    m = _mesh_model(FE)
+    m.add_rectangle_mesh('S', 0.75, 6.0, 5.0, 7.0, 'Conc', kx_mod=0.8, ky_mod=0.9, origin=[1.0, 2.0, 3.0], plane='XZ',
+                         x_control=[2.5, 6.0 + 1e-12, 7.5], y_control=[1.7, 3.3, 1.7])
+    m.meshes['S'].generate()
+    return m
+
+
+def rect_mesh_opening(FE):
+    m = _mesh_model(FE)
+    m.add_rectangle_mesh('M', 1.0, 12.0, 9.0, 8.0, 'Conc')
+    m.meshes['M'].add_rect_opening('door', 3.0, 0.0, 3.0, 4.5)
+    m.meshes['M'].add_rect_opening('window', 7.5, 3.2, 2.2, 2.6)
+    m.meshes['M'].generate()
+    return m
+
+
+def rect_mesh_renamed(FE):
+    """two meshes added before either is generated (both start at N1 / Q1), user nodes already in the model, and a
+    regeneration after an opening was added: `_rename_duplicates`, `unique_name`, `_remove_from_model`"""
+    m = _mesh_model(FE)
+    m.add_node('N2', -5.0, 0.0, 0.0)
+    m.add_node('A', -6.0, 0.0, 0.0)
+    m.add_rectangle_mesh('M1', 2.0, 6.0, 4.0, 8.0, 'Conc')
+    m.add_rectangle_mesh('M2', 2.0, 4.0, 4.0, 8.0, 'Conc', origin=[6.0, 0.0, 0.0])
+    m.meshes['M1'].generate()
+    m.meshes['M2'].generate()
+    m.meshes['M1'].add_rect_opening('o', 2.0, 0.0, 2.0, 2.0)
+    m.meshes['M1'].generate()
+    return m
+
+
+RECT_MESH_CASES = {
+    'basic': rect_mesh_basic,
+    'uneven_yz_rect': rect_mesh_uneven_yz_rect,
+    'controls_xz': rect_mesh_controls_xz,
+    'opening': rect_mesh_opening,
+    'renamed': rect_mesh_renamed,
+}
+
+
+def rect_mesh_slab(FE):
+    """A slab with an opening built by `add_rectangle_mesh` (generated by the analysis itself), edge nodes pinned,
+    pressures on every element, three combos: the mesh generator inside the full path."""
+    m = _mesh_model(FE)
+    m.add_rectangle_mesh('SLAB', 12.0, 96.0, 72.0, 8.0, 'Conc', x_control=[30.0], y_control=[20.0, 50.0])
+    mesh = m.meshes['SLAB']
+    mesh.add_rect_opening('shaft', 30.0, 20.0, 24.0, 30.0)
+    mesh.generate()
+    for node in mesh.nodes.values():
+        x, y = mesh.node_local_coords(node)
+        if x in (0.0, 96.0) or y in (0.0, 72.0):
+            m.def_support(node.name, True, True, True, False, False, False)
+    for k, name in enumerate(mesh.elements):
+        m.add_quad_surface_pressure(name, 0.002, case='D')
+        if k % 3 == 0:
+            m.add_quad_surface_pressure(name, 0.001, case='L')
+    m.add_load_combo('C1', {'D': 1.4})
+    m.add_load_combo('C2', {'D': 1.2, 'L': 1.6})
+    m.add_load_combo('C3', {'D': 0.9})
+    return m
+
+
 SMALL_MODELS = {
     'space_frame': (space_frame, 'tc'),
     'portal_frame': (portal_frame, 'linear'),
@@ -509,6 +598,7 @@ SMALL_MODELS = {
     'pdelta_near_buckling': (pdelta_near_buckling, 'pdelta'),
     'tc_load_steps': (tc_load_steps, 'tc_steps'),
     'mat_tc': (mat_tc, 'tc'),
+    'rect_mesh_slab': (rect_mesh_slab, 'linear'),
 }
 
 # keyword arguments of `analyze` for the load-stepping fixture (mode 'tc_steps')

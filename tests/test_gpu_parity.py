@@ -151,7 +151,7 @@ def test_solve_linear(eng, name, solver):
         # produced: flat shell fixtures in an axis plane take three classes, everything else one
         ctr = eng.counters()
         assert ctr['dof_class_rejects'] == 0, ctr
-        flat = name in ('quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz', 'mat_foundation')
+        flat = name in ('quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz', 'mat_foundation', 'rect_mesh_slab')
         assert ctr['dof_classes'] == (3 if flat else 1), (name, ctr)
     # element end forces (Member3D.F/f, Quad3D.F, Plate3D.F, Spring3D.F)
     for c in range(A.factors.shape[0]):
@@ -657,6 +657,32 @@ def test_dof_class_ordering_equals_node_ordering(eng, case):
         Do, Ro = om.solve_linear(A)
         for c in range(len(Do)):
             assert rel_err(out[1][0][c], Do[c].reshape(-1)) < TOL_D
+
+
+def test_rectangle_mesh_model_and_mesh_queries():
+    """A slab with an opening built by `FEModel3D.add_rectangle_mesh` (pynite_b200/Mesh.py; generated names, order and
+    coordinates are checked against the reference's generator in tests/test_mesh_cpu.py) through `analyze_linear`, and the
+    mesh result queries `Mesh.max_* / min_*` (`Mesh.py:172-716`: corners and centre of every element, one batched
+    `pn_shell_stresses` table per combination here) against what the reference's element-by-element loops returned."""
+    from pynite_b200 import FEModel3D
+    A, ref, _ = load_fixture('rect_mesh_slab')
+    m = models.rect_mesh_slab(FEModel3D)
+    m.analyze_linear()
+    for c, combo in enumerate(m.load_combos):
+        assert rel_err(m._D[combo].reshape(-1), ref['D'][c]) < TOL_D, combo
+    queries = [('shear', d) for d in ('Qx', 'Qy', 'QX', 'QY')] + [('moment', d) for d in ('Mx', 'My', 'Mxy', 'MX', 'MY', 'MZ')] + \
+              [('membrane', d) for d in ('Sx', 'Sy', 'Sxy', 'SX', 'SY')]
+    gold = ref['mesh_extremes']
+    mesh = m.meshes['SLAB']
+    scale = np.abs(gold).max(axis=(0, 1, 3))
+    for b, combo in enumerate(m.load_combos):
+        for q, (what, direction) in enumerate(queries):
+            hi = getattr(mesh, 'max_' + what)(direction, combo)
+            lo = getattr(mesh, 'min_' + what)(direction, combo)
+            assert abs(hi - gold[0, b, q, 0]) <= 1e-9*scale[q] + 1e-300, (combo, what, direction, hi, gold[0, b, q, 0])
+            assert abs(lo - gold[0, b, q, 1]) <= 1e-9*scale[q] + 1e-300, (combo, what, direction, lo, gold[0, b, q, 1])
+    with pytest.raises(Exception):
+        mesh.max_moment('Mq', 'C1')
 
 
 def test_pcg_reports_non_convergence(eng):

@@ -8,7 +8,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 FIXTURES = ['space_frame', 'portal_frame', 'continuous_beam', 'quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz',
             'skew_shell', 'moment_frame', 'mat_foundation', 'mixed_building', 'pdelta_column', 'pdelta_frame',
-            'braced_tc', 'pdelta_near_buckling', 'tc_load_steps', 'mat_tc']
+            'braced_tc', 'pdelta_near_buckling', 'tc_load_steps', 'mat_tc', 'rect_mesh_slab']
 
 
 # fixtures whose stored displacements come from the tension/compression-only iteration (input arrays carry the
@@ -67,3 +67,25 @@ def compare_general_pattern(K, Kr, tol_values=1e-12, tol_noise=1e-14):
     for r, c in zip(only.row[only.data != 0], only.col[only.data != 0]):
         assert abs(K[r, c]) <= tol_noise*scale and abs(Kr[r, c]) <= tol_noise*scale
     return n_only
+
+
+def mesh_record(model):
+    """Names, coordinates and connectivity of a model built with `add_rectangle_mesh`, and of each of its meshes, in
+    dictionary order (works on the reference's objects and on ours)."""
+    rec = {}
+    nodes = list(model.nodes.values())
+    rec['node_names'] = np.array([n.name for n in nodes])
+    rec['node_keys'] = np.array(list(model.nodes.keys()))
+    rec['node_xyz'] = np.array([[n.X, n.Y, n.Z] for n in nodes], dtype=float).reshape(-1, 3)
+    for kind, table in (('quad', model.quads), ('plate', model.plates)):
+        elems = list(table.values())
+        rec[kind + '_names'] = np.array([e.name for e in elems], dtype=str)
+        rec[kind + '_keys'] = np.array(list(table.keys()), dtype=str)
+        rec[kind + '_conn'] = np.array([[e.i_node.name, e.j_node.name, e.m_node.name, e.n_node.name] for e in elems],
+                                       dtype=str).reshape(-1, 4)
+        rec[kind + '_props'] = np.array([[e.t, e.kx_mod, e.ky_mod] for e in elems], dtype=float).reshape(-1, 3)
+    for mname, mesh in model.meshes.items():
+        rec['mesh_' + mname + '_nodes'] = np.array(list(mesh.nodes.keys()), dtype=str)
+        rec['mesh_' + mname + '_elements'] = np.array(list(mesh.elements.keys()), dtype=str)
+        rec['mesh_' + mname + '_last'] = np.array([mesh.last_node.name, mesh.last_element.name])
+    return rec
