@@ -39,6 +39,7 @@ class FEModel3D:
         self.quads = {}
         self.plates = {}
         self.meshes = {}
+        self.mats = {}
         self.load_combos = {}
         self._D = {}        # {combo: (6N, 1) displacement vector}
         self._Rxn = {}      # {combo: (6N, 1) reaction vector}; read through node.RxnFX[...] etc.
@@ -94,6 +95,8 @@ class FEModel3D:
             cases.extend(load[5] for load in member.DistLoads)
         for shell in list(self.plates.values()) + list(self.quads.values()):
             cases.extend(load[1] for load in shell.pressures)
+        for mat in self.mats.values():
+            cases.extend(load[3] for load in mat.pt_loads)
         return sorted(dict.fromkeys(cases))
 
     # ------------------------------------------------------------------------------------------
@@ -168,6 +171,20 @@ class FEModel3D:
                                           plane, x_control, y_control, start_node, start_element, element_type=element_type)
         self.solution = None
         return name
+
+    def add_mat_foundation(self, name, mesh_size, length_X, length_Z, thickness, material_name, ks, origin=[0, 0, 0],
+                           x_control=[], y_control=[]):
+        """`FEModel3D.add_mat_foundation` (:935-951).  (The default control lists are shared between calls, as the
+        reference's mutable defaults are.)"""
+        from pynite_b200.MatFoundation import MatFoundation
+        if name:
+            if name in self.mats:
+                raise NameError(f"Mat foundation name '{name}' already exists")
+        else:
+            name = self.unique_name(self.mats, 'MAT')
+        self.mats[name] = MatFoundation(name, mesh_size, length_X, length_Z, thickness, material_name, self, ks, origin,
+                                        x_control, y_control)
+        self.solution = None
 
     def delete_node(self, node_name):
         """Removes a node and every member / plate / quad attached to it (`FEModel3D.py:1060-1077`)."""

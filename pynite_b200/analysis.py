@@ -63,14 +63,15 @@ def renumber(model):
 
 
 def prepare_model(model):
-    """`Analysis._prepare_model` (:20-79) minus mesh generators and modal combos (out of scope)."""
+    """`Analysis._prepare_model` (:20-79): rectangle meshes and mat foundations are generated here when they have not
+    been (shear walls and modal combos: out of scope)."""
     model._D = {}
     model._Rxn = {}
     if model.load_combos == {}:
         model.load_combos['Combo 1'] = LoadCombo('Combo 1', factors={'Case 1': 1.0})
     for name in [n for n, c in model.load_combos.items() if c.combo_tags is not None and 'modal' in c.combo_tags]:
         model.load_combos.pop(name)
-    for mesh in getattr(model, 'meshes', {}).values():
+    for mesh in list(getattr(model, 'meshes', {}).values()) + list(getattr(model, 'mats', {}).values()):
         if not mesh.is_generated or mesh.needs_update:
             mesh.generate()
     combos = list(model.load_combos.keys())

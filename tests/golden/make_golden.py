@@ -191,6 +191,9 @@ def main(argv):
         data.update(flatten_pair(build, ref, mode))
         if getattr(ref, 'meshes', None):
             data.update(mesh_extremes(ref))
+        if getattr(ref, 'mats', None):
+            data['ref_soil_pressure'] = np.array([[[mat.soil_pressure(x, z, combo) for (x, z) in models.MAT_PRESSURE_POINTS]
+                                                   for combo in ref.load_combos] for mat in ref.mats.values()], dtype=float)
         data['mode'] = np.array(mode)
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **data)

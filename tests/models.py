@@ -550,12 +550,26 @@ def rect_mesh_renamed(FE):
     return m
 
 
+def mat_mesh_generated(FE):
+    """`add_mat_foundation` + point loads (control points) + an opening, generated explicitly"""
+    m = _mesh_model(FE)
+    m.add_mat_foundation('MAT1', 2.0, 14.0, 9.0, 18.0, 'Conc', 0.15, origin=[1.0, 0.0, -2.0], x_control=[], y_control=[])
+    mat = m.mats['MAT1']
+    mat.add_mat_pt_load([4.5, 1.5], 'FY', -120.0, case='D')
+    mat.add_mat_pt_load([11.0, 5.25], 'FY', -80.0, case='L')
+    mat.add_mat_pt_load([11.0, 5.25], 'MX', 30.0, case='L')
+    mat.add_rect_opening('pit', 7.0, 2.0, 9.5, 4.0)
+    mat.generate()
+    return m
+
+
 RECT_MESH_CASES = {
     'basic': rect_mesh_basic,
     'uneven_yz_rect': rect_mesh_uneven_yz_rect,
     'controls_xz': rect_mesh_controls_xz,
     'opening': rect_mesh_opening,
     'renamed': rect_mesh_renamed,
+    'mat': mat_mesh_generated,
 }
 
 
@@ -581,6 +595,29 @@ def rect_mesh_slab(FE):
     return m
 
 
+def mat_mesh_tc(FE):
+    """A mat built by `add_mat_foundation` (generated by the analysis), one heavy eccentric column load: part of the mat
+    lifts off its compression-only springs (`MatFoundation.py:136`), so `analyze` iterates."""
+    m = _mesh_model(FE)
+    m.add_mat_foundation('MAT', 30.0, 240.0, 180.0, 24.0, 'Conc', 0.1, x_control=[], y_control=[])
+    mat = m.mats['MAT']
+    mat.add_mat_pt_load([40.0, 45.0], 'FY', -400.0, case='D')
+    mat.add_mat_pt_load([40.0, 45.0], 'MZ', 9000.0, case='W')
+    mat.add_mat_pt_load([200.0, 135.0], 'FY', -150.0, case='D')
+    mat.generate()
+    # in-plane restraint (the springs act in DY only)
+    first, last = list(mat.nodes.values())[0], mat.last_node
+    m.def_support(first.name, True, False, True, False, True, False)
+    m.def_support(last.name, False, False, True, False, False, False)
+    m.add_load_combo('G', {'D': 1.0})
+    m.add_load_combo('GW', {'D': 0.9, 'W': 1.0})
+    return m
+
+
+# points (global X, Z) at which `MatFoundation.soil_pressure` is compared with the reference
+MAT_PRESSURE_POINTS = [(40.0, 45.0), (0.0, 0.0), (123.4, 56.7), (240.0, 180.0), (200.0, 135.0), (15.0, 170.0), (300.0, 10.0)]
+
+
 SMALL_MODELS = {
     'space_frame': (space_frame, 'tc'),
     'portal_frame': (portal_frame, 'linear'),
@@ -599,6 +636,7 @@ SMALL_MODELS = {
     'tc_load_steps': (tc_load_steps, 'tc_steps'),
     'mat_tc': (mat_tc, 'tc'),
     'rect_mesh_slab': (rect_mesh_slab, 'linear'),
+    'mat_mesh_tc': (mat_mesh_tc, 'tc'),
 }
 
 # keyword arguments of `analyze` for the load-stepping fixture (mode 'tc_steps')

@@ -989,6 +989,27 @@ def test_tc_iteration_compression_only_mat():
     assert np.array_equal(got, (A.nspring_flag[:, 1] >> 1) & 1)
 
 
+def test_mat_foundation_builder_through_analyze():
+    """BASELINE config 4's caller: `FEModel3D.add_mat_foundation` + `add_mat_pt_load` (pynite_b200/MatFoundation.py; the
+    generated nodes, spring stiffnesses and loads are checked against the reference's generator in tests/test_mesh_cpu.py),
+    generated by `analyze()` itself, compression-only springs switched on the device: displacements, reactions and
+    `MatFoundation.soil_pressure` (`MatFoundation.py:138-223`) against the reference."""
+    from pynite_b200 import FEModel3D
+    A, ref, _ = load_fixture('mat_mesh_tc')
+    m = models.mat_mesh_tc(FEModel3D)
+    m.analyze()
+    for c, combo in enumerate(m.load_combos):
+        assert rel_err(m._D[combo].reshape(-1), ref['D'][c]) < TOL_D, combo
+        assert rel_err(m._Rxn[combo].reshape(-1), ref['Rxn'][c]) < TOL_D, combo
+    gold = ref['soil_pressure']
+    mat = m.mats['MAT']
+    for b, combo in enumerate(m.load_combos):
+        for k, (x, z) in enumerate(models.MAT_PRESSURE_POINTS):
+            p = mat.soil_pressure(x, z, combo)
+            assert abs(p - gold[0, b, k]) <= 1e-9*np.abs(gold).max(), (combo, x, z, p, gold[0, b, k])
+    assert (gold[0] == 0).any() and (gold[0] > 0).any()          # part of the mat lifted off, part bears
+
+
 def test_tc_iteration_mat_config4_shape_properties():
     """BASELINE config 4's stretch: 60 x 60 quads on compression-only springs through `analyze()`: the converged state
     satisfies the reference's own convergence rule (a '-' spring is active iff its node moved down), vertical

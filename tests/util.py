@@ -8,12 +8,12 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 FIXTURES = ['space_frame', 'portal_frame', 'continuous_beam', 'quad_mesh_xy', 'quad_mesh_yz_ortho', 'plate_mesh_xz',
             'skew_shell', 'moment_frame', 'mat_foundation', 'mixed_building', 'pdelta_column', 'pdelta_frame',
-            'braced_tc', 'pdelta_near_buckling', 'tc_load_steps', 'mat_tc', 'rect_mesh_slab']
+            'braced_tc', 'pdelta_near_buckling', 'tc_load_steps', 'mat_tc', 'rect_mesh_slab', 'mat_mesh_tc']
 
 
 # fixtures whose stored displacements come from the tension/compression-only iteration (input arrays carry the
 # reference's final element activity; a plain linear solve of them is not what the reference stored)
-TC_FIXTURES = ('braced_tc', 'tc_load_steps', 'mat_tc')
+TC_FIXTURES = ('braced_tc', 'tc_load_steps', 'mat_tc', 'mat_mesh_tc')
 PDELTA_FIXTURES = ('pdelta_column', 'pdelta_frame', 'pdelta_near_buckling')
 
 
@@ -84,7 +84,17 @@ def mesh_record(model):
         rec[kind + '_conn'] = np.array([[e.i_node.name, e.j_node.name, e.m_node.name, e.n_node.name] for e in elems],
                                        dtype=str).reshape(-1, 4)
         rec[kind + '_props'] = np.array([[e.t, e.kx_mod, e.ky_mod] for e in elems], dtype=float).reshape(-1, 3)
-    for mname, mesh in model.meshes.items():
+    springs, loads = [], []
+    for n in nodes:
+        for dof in ('DX', 'DY', 'DZ', 'RX', 'RY', 'RZ'):
+            k, direction, active = getattr(n, 'spring_' + dof)
+            if k is not None:
+                springs.append((n.name, dof, repr(float(k)), str(direction), str(active)))
+        for load in n.NodeLoads:
+            loads.append((n.name, str(load[0]), repr(float(load[1])), str(load[2])))
+    rec['node_springs'] = np.array(springs, dtype=str).reshape(-1, 5)
+    rec['node_loads'] = np.array(loads, dtype=str).reshape(-1, 4)
+    for mname, mesh in list(model.meshes.items()) + list(getattr(model, 'mats', {}).items()):
         rec['mesh_' + mname + '_nodes'] = np.array(list(mesh.nodes.keys()), dtype=str)
         rec['mesh_' + mname + '_elements'] = np.array(list(mesh.elements.keys()), dtype=str)
         rec['mesh_' + mname + '_last'] = np.array([mesh.last_node.name, mesh.last_element.name])
