@@ -186,6 +186,66 @@ class FEModel3D:
                                         x_control, y_control)
         self.solution = None
 
+    def merge_duplicate_nodes(self, tolerance=0.001):
+        """`FEModel3D.merge_duplicate_nodes` (:953-1058): a node within `tolerance` of an EARLIER surviving node is merged
+        into the first such node (references in elements and meshes, supports, support springs) and removed; returns the
+        removed names in the reference's order.  The reference compares all pairs; here the survivors are kept in a
+        spatial hash with cells of one tolerance, so two adjacent 500 x 500 meshes merge in seconds."""
+        node_lookup = {name: [] for name in self.nodes}
+        for table in (self.springs, self.members, self.plates, self.quads):
+            for element in table.values():
+                for node_type in ('i_node', 'j_node', 'm_node', 'n_node'):
+                    node = getattr(element, node_type, None)
+                    if node is not None:
+                        node_lookup[node.name].append((element, node_type))
+        names = list(self.nodes.keys())
+        cell = tolerance if tolerance > 0 else 1.0
+        grid = {}            # cell -> [(order, name)] of surviving nodes
+        merged_into = {}     # removed name -> surviving name
+        absorbed = {}        # surviving name -> [removed names] in dictionary order
+        for order, name in enumerate(names):
+            node = self.nodes[name]
+            cx, cy, cz = int(node.X//cell), int(node.Y//cell), int(node.Z//cell)
+            best = None
+            for dx in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    for dz in (-1, 0, 1):
+                        for o, other in grid.get((cx + dx, cy + dy, cz + dz), ()):
+                            if (best is None or o < best[0]) and not self.nodes[other].distance(node) > tolerance:
+                                best = (o, other)
+            if best is None:
+                grid.setdefault((cx, cy, cz), []).append((order, name))
+            else:
+                merged_into[name] = best[1]
+                absorbed.setdefault(best[1], []).append(name)
+        # the reference removes in the order (survivor by dictionary position, then its duplicates by position)
+        remove_list = []
+        for name_1 in names:
+            if name_1 in merged_into:
+                continue
+            node_1 = self.nodes[name_1]
+            for name_2 in absorbed.get(name_1, ()):
+                node_2 = self.nodes[name_2]
+                for element, node_type in node_lookup[name_2]:
+                    setattr(element, node_type, node_1)
+                for dof in ('support_DX', 'support_DY', 'support_DZ', 'support_RX', 'support_RY', 'support_RZ'):
+                    if getattr(node_2, dof) == True:                 # noqa: E712 -- the reference's comparison
+                        setattr(node_1, dof, True)
+                for dof in ('spring_DX', 'spring_DY', 'spring_DZ', 'spring_RX', 'spring_RY', 'spring_RZ'):
+                    value = getattr(node_2, dof)
+                    if value != [None, None, None]:
+                        setattr(node_1, dof, value)
+                for mesh in self.meshes.values():
+                    if name_2 in mesh.nodes:
+                        mesh.nodes[name_2] = node_1
+                        mesh.nodes[name_1] = mesh.nodes.pop(name_2)
+                        # (the elements of the mesh are the model's element objects: their references were replaced above)
+                remove_list.append(name_2)
+        for name in remove_list:
+            self.nodes.pop(name)
+        self.solution = None
+        return remove_list
+
     def delete_node(self, node_name):
         """Removes a node and every member / plate / quad attached to it (`FEModel3D.py:1060-1077`)."""
         self.nodes.pop(node_name)

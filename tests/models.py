@@ -563,6 +563,22 @@ def mat_mesh_generated(FE):
     return m
 
 
+def rect_mesh_merged(FE):
+    """two meshes sharing an edge (and a wall standing on the slab), supports on one of the duplicates, merged"""
+    m = _mesh_model(FE)
+    m.add_rectangle_mesh('A', 2.0, 6.0, 4.0, 8.0, 'Conc')
+    m.meshes['A'].generate()
+    m.add_rectangle_mesh('B', 2.0, 4.0, 4.0, 8.0, 'Conc', origin=[6.0, 0.0, 0.0])
+    m.meshes['B'].generate()
+    m.add_rectangle_mesh('W', 2.0, 4.0, 6.0, 6.0, 'Conc', origin=[6.0, 0.0, 0.0], plane='YZ')
+    m.meshes['W'].generate()
+    first_b = list(m.meshes['B'].nodes.values())[0]
+    m.def_support(first_b.name, True, True, True, False, False, False)
+    m.def_support_spring(list(m.meshes['W'].nodes.values())[1].name, 'DY', 55.0, '-')
+    m._test_removed = m.merge_duplicate_nodes()
+    return m
+
+
 RECT_MESH_CASES = {
     'basic': rect_mesh_basic,
     'uneven_yz_rect': rect_mesh_uneven_yz_rect,
@@ -570,6 +586,7 @@ RECT_MESH_CASES = {
     'opening': rect_mesh_opening,
     'renamed': rect_mesh_renamed,
     'mat': mat_mesh_generated,
+    'merged': rect_mesh_merged,
 }
 
 

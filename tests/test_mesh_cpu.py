@@ -53,3 +53,22 @@ def test_large_mesh_is_linear_time():
     assert (q.i_node.name, q.j_node.name, q.m_node.name, q.n_node.name) == ('N250499', 'N250500', 'N251001', 'N251000')
     assert m.nodes['N251001'].X == 6000.0 and m.nodes['N251001'].Y == 6000.0
     assert dt < 60.0, dt
+
+
+def test_merge_duplicate_nodes_is_linear_time():
+    """Two 150 x 150 meshes sharing an edge: the reference compares all 1e9 node pairs; the spatial hash here merges the
+    151 duplicates in seconds, and the quads of the second mesh end up on the first mesh's edge nodes."""
+    import time
+    m = FEModel3D()
+    m.add_material('Conc', 3605.0, 1540.6, 0.17, 8.68e-5)
+    m.add_rectangle_mesh('A', 1.0, 150.0, 150.0, 8.0, 'Conc')
+    m.meshes['A'].generate()
+    m.add_rectangle_mesh('B', 1.0, 150.0, 150.0, 8.0, 'Conc', origin=[150.0, 0.0, 0.0])
+    m.meshes['B'].generate()
+    t0 = time.perf_counter()
+    removed = m.merge_duplicate_nodes()
+    dt = time.perf_counter() - t0
+    assert len(removed) == 151 and len(m.nodes) == 2*151*151 - 151
+    first_b = list(m.meshes['B'].elements.values())[0]
+    assert first_b.i_node is m.meshes['A'].nodes['N151'] and first_b.i_node.X == 150.0
+    assert dt < 30.0, dt

@@ -92,6 +92,9 @@ def mesh_record(model):
                 springs.append((n.name, dof, repr(float(k)), str(direction), str(active)))
         for load in n.NodeLoads:
             loads.append((n.name, str(load[0]), repr(float(load[1])), str(load[2])))
+    rec['removed'] = np.array(list(getattr(model, '_test_removed', [])), dtype=str)
+    rec['node_supports'] = np.array([[n.support_DX, n.support_DY, n.support_DZ, n.support_RX, n.support_RY, n.support_RZ]
+                                     for n in nodes], dtype=bool).reshape(-1, 6)
     rec['node_springs'] = np.array(springs, dtype=str).reshape(-1, 5)
     rec['node_loads'] = np.array(loads, dtype=str).reshape(-1, 4)
     for mname, mesh in list(model.meshes.items()) + list(getattr(model, 'mats', {}).items()):
