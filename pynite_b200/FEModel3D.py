@@ -172,6 +172,53 @@ class FEModel3D:
         self.solution = None
         return name
 
+    def _new_mesh_name(self, name):
+        if name:
+            if name in self.meshes:
+                raise NameError(f"Mesh name '{name}' already exists")
+            return name
+        return self.unique_name(self.meshes, 'MSH')
+
+    def add_annulus_mesh(self, name, mesh_size, outer_radius, inner_radius, thickness, material_name, kx_mod=1.0, ky_mod=1.0,
+                         origin=(0, 0, 0), axis='Y', start_node=None, start_element=None):
+        """`FEModel3D.add_annulus_mesh` (:685-746)."""
+        from pynite_b200.Mesh import AnnulusMesh
+        name = self._new_mesh_name(name)
+        start_node = self.unique_name(self.nodes, 'N') if start_node is None else start_node
+        start_element = self.unique_name(self.quads, 'Q') if start_element is None else start_element
+        self.meshes[name] = AnnulusMesh(mesh_size, outer_radius, inner_radius, thickness, material_name, self, kx_mod, ky_mod,
+                                        origin, axis, start_node, start_element)
+        self.solution = None
+        return name
+
+    def add_frustrum_mesh(self, name, mesh_size, large_radius, small_radius, height, thickness, material_name, kx_mod=1.0,
+                          ky_mod=1.0, origin=(0, 0, 0), axis='Y', start_node=None, start_element=None):
+        """`FEModel3D.add_frustrum_mesh` (:748-808)."""
+        from pynite_b200.Mesh import FrustrumMesh
+        name = self._new_mesh_name(name)
+        start_node = self.unique_name(self.nodes, 'N') if start_node is None else start_node
+        start_element = self.unique_name(self.quads, 'Q') if start_element is None else start_element
+        self.meshes[name] = FrustrumMesh(mesh_size, large_radius, small_radius, height, thickness, material_name, self, kx_mod,
+                                         ky_mod, origin, axis, start_node, start_element)
+        self.solution = None
+        return name
+
+    def add_cylinder_mesh(self, name, mesh_size, radius, height, thickness, material_name, kx_mod=1, ky_mod=1, origin=(0, 0, 0),
+                          axis='Y', num_elements=None, start_node=None, start_element=None, element_type='Quad'):
+        """`FEModel3D.add_cylinder_mesh` (:810-890).  The cylinder is generated on construction, as in the reference."""
+        from pynite_b200.Mesh import CylinderMesh
+        name = self._new_mesh_name(name)
+        if start_node is None:
+            start_node = self.unique_name(self.nodes, 'N')
+        if element_type == 'Rect' and start_element is None:
+            start_element = self.unique_name(self.plates, 'R')
+        elif element_type == 'Quad' and start_element is None:
+            start_element = self.unique_name(self.quads, 'Q')
+        self.meshes[name] = CylinderMesh(mesh_size, radius, height, thickness, material_name, self, kx_mod, ky_mod, origin, axis,
+                                         start_node, start_element, num_elements, element_type)
+        self.solution = None
+        return name
+
     def add_mat_foundation(self, name, mesh_size, length_X, length_Z, thickness, material_name, ks, origin=[0, 0, 0],
                            x_control=[], y_control=[]):
         """`FEModel3D.add_mat_foundation` (:935-951).  (The default control lists are shared between calls, as the

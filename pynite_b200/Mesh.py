@@ -9,12 +9,12 @@ scans per node (`Mesh.py:1013-1021`, quadratic in the reference), and the result
 read one batched stress table per load combination from the device (`pn_shell_stresses`) instead of five kernel-free
 Python evaluations per element.
 
-Annulus, cylinder and frustrum meshes are not rebuilt (SURVEY 2 marks the meshers out of the hot path; the rectangle is
-the one the benchmark configurations use).
+The annulus, frustrum and cylinder meshes (`Mesh.py:1126-2036`) follow at the end of the file, ring by ring like the
+reference's.
 """
 from __future__ import annotations
 
-from math import ceil, isclose
+from math import ceil, cos, isclose, pi, sin
 
 import numpy as np
 
@@ -348,3 +348,308 @@ def mesh_arrays(mesh):
     elems = list(mesh.elements.values())
     return ([n.name for n in nodes], np.array([[n.X, n.Y, n.Z] for n in nodes], dtype=float).reshape(-1, 3),
             [e.name for e in elems], [[e.i_node.name, e.j_node.name, e.m_node.name, e.n_node.name] for e in elems])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Curved meshes (`Mesh.py:1126-2036`): annulus, frustrum, cylinder, built ring by ring like the reference's.  A ring is
+# a list of node circles and a connectivity rule; the coordinates use the reference's expressions (`Xo + r*cos(angle)`
+# with the angle formed exactly as there), because names, order and coordinates are API-visible.  The reference's
+# quirks are kept: rings file themselves in the model when they are constructed, a cylinder uses only the axis
+# component of its origin and stacks rings up to the ABSOLUTE coordinate `height`, and its rings are built with
+# kx_mod = ky_mod = 1.
+# ---------------------------------------------------------------------------------------------------------------------
+def _on_circle(axis, Xo, Yo, Zo, r, angle, lift, who):
+    """A point of a circle about a global axis; `lift` (or None) is added along the axis."""
+    if axis == 'Y':
+        return Xo + r*cos(angle), (Yo if lift is None else Yo + lift), Zo + r*sin(angle)
+    if axis == 'X':
+        return (Xo if lift is None else Xo + lift), Yo + r*sin(angle), Zo + r*cos(angle)
+    if axis == 'Z':
+        return Xo + r*sin(angle), Yo + r*cos(angle), (Zo if lift is None else Zo + lift)
+    raise Exception('Invalid axis specified for ' + who + '.')
+
+
+class _RingBase(Mesh):
+    """Nodes on consecutive circles (numbered circle by circle from `start_node`), quads from 1-based node indices."""
+
+    def _build(self, circles, conn, prefix, cls, who):
+        if self.is_generated:
+            self._remove_from_model()
+        node_offset = self._offset(self.start_node, 'Invalid node name. Enter a letter followed by a number (e.g. \'N25\')')
+        element_offset = self._offset(self.start_element, 'Invalid element ame. Enter a letter followed by a number (e.g. \'Q83\')')
+        made = []
+        for r, angles, lift in circles:
+            for angle in angles:
+                name = 'N' + str(len(made) + 1 + node_offset)
+                node = Node3D(self.model, name, *_on_circle(self.axis, self.Xo, self.Yo, self.Zo, r, angle, lift, who))
+                self.nodes[name] = node
+                made.append(node)
+        for k, (i_node, j_node, m_node, n_node) in enumerate(conn, start=1):
+            name = prefix + str(k + element_offset)
+            self.elements[name] = cls(name, made[i_node - 1], made[j_node - 1], made[m_node - 1], made[n_node - 1],
+                                      self.thickness, self.material_name, self.model, self.kx_mod, self.ky_mod)
+        for node in self.nodes.values():
+            self.model.nodes[node.name] = node
+        for element in self.elements.values():
+            (self.model.quads if element.type == 'Quad' else self.model.plates)[element.name] = element
+        self.is_generated = True
+        self.needs_update = False
+
+    @staticmethod
+    def _offset(name, message):
+        try:
+            return int(name[1:]) - 1
+        except Exception:
+            raise ValueError(message)
+
+    @staticmethod
+    def _band(n):
+        """Quads between a circle of n nodes (1 .. n) and the next one (n + 1 .. 2 n), closing on the first column."""
+        return [(i + n, (i + 1 + n) if i != n else (1 + n), (i + 1) if i != n else 1, i) for i in range(1, n + 1)]
+
+
+class AnnulusRingMesh(_RingBase):
+    """`Mesh.py:1259-1418`: one ring of `num_quads` quads between two radii."""
+
+    def __init__(self, outer_radius, inner_radius, num_quads, thickness, material_name, model, kx_mod=1, ky_mod=1,
+                 origin=[0, 0, 0], axis='Y', start_node='N1', start_element='Q1'):
+        super().__init__(thickness, material_name, model, kx_mod, ky_mod, start_node=start_node, start_element=start_element)
+        self.inner_radius = inner_radius
+        self.outer_radius = outer_radius
+        self.n = num_quads
+        self.Xo, self.Yo, self.Zo = origin[0], origin[1], origin[2]
+        self.axis = axis
+        self.generate()
+
+    def __repr__(self):
+        return (f"AnnulusRingMesh(material_name={self.material_name!r}, outer_radius={self.outer_radius}, "
+                f"inner_radius={self.inner_radius}, thickness={self.thickness})")
+
+    def generate(self):
+        n = self.n
+        theta = 2*pi/self.n
+        angles = [theta*(i - 1) for i in range(1, n + 1)]
+        self._build([(self.inner_radius, angles, None), (self.outer_radius, angles, None)], self._band(n), 'Q', Quad3D,
+                    'AnnulusRingMesh')
+
+
+class AnnulusTransRingMesh(_RingBase):
+    """`Mesh.py:1420-1621`: a ring whose outer edge has three times the quads of its inner edge (n coarse quads, then
+    3 n fine ones), through a middle circle of 2 n nodes."""
+
+    def __init__(self, outer_radius, inner_radius, num_inner_quads, thickness, material_name, model, kx_mod=1, ky_mod=1,
+                 origin=[0, 0, 0], axis='Y', start_node='N1', start_element='Q1'):
+        super().__init__(thickness, material_name, model, kx_mod, ky_mod, start_node=start_node, start_element=start_element)
+        self.inner_radius = inner_radius
+        self.outer_radius = (inner_radius + outer_radius)/2
+        self.r3 = outer_radius
+        self.n = num_inner_quads
+        self.Xo, self.Yo, self.Zo = origin[0], origin[1], origin[2]
+        self.axis = axis
+        self.generate()
+
+    def __repr__(self):
+        return (f"AnnulusTransRingMesh(material_name={self.material_name!r}, outer_radius={self.r3}, "
+                f"inner_radius={self.inner_radius}, thickness={self.thickness})")
+
+    def generate(self):
+        n = self.n
+        theta1 = 2*pi/self.n
+        theta2 = 2*pi/(self.n*3)
+        theta3 = 2*pi/(self.n*3)
+        inner = [theta1*(i - 1) for i in range(1, n + 1)]
+        middle, angle = [], 0
+        for k in range(1, 2*n + 1):          # the angle is accumulated: thirds of a coarse quad, skipping its corners
+            if k == 1:
+                angle = theta2
+            elif k % 2 == 0:
+                angle += theta2
+            else:
+                angle += 2*theta2
+            middle.append(angle)
+        outer = [0 if k == 1 else theta3*(k - 1) for k in range(1, 3*n + 1)]
+        conn = []
+        for i in range(1, 4*n + 1):
+            third = (i - (n + 1))//3
+            if i <= n:                                    # coarse quads on the inner circle
+                conn.append((2*i + n - 1, 2*i + n, (i + 1) if i != n else 1, i))
+            elif (i - n) % 3 == 1:
+                conn.append((i + 2*n, i + 2*n + 1, i - third, 1 + third))
+            elif (i - n) % 3 == 2:
+                conn.append((i + 2*n, i + 2*n + 1, i - third, i - 1 - third))
+            elif i != 4*n:
+                conn.append((i + 2*n, i + 2*n + 1, 2 + third, i - 1 - third))
+            else:
+                conn.append((i + 2*n, 1 + 3*n, 1, i - 1 - third))
+        self._build([(self.inner_radius, inner, None), (self.outer_radius, middle, None), (self.r3, outer, None)], conn, 'Q',
+                    Quad3D, 'AnnulusTransRingMesh')
+
+
+class CylinderRingMesh(_RingBase):
+    """`Mesh.py:1847-2036`: one course of a cylinder."""
+
+    def __init__(self, radius, height, num_elements, thickness, material_name, model, kx_mod=1, ky_mod=1, origin=[0, 0, 0],
+                 axis='Y', start_node='N1', start_element='Q1', element_type='Quad'):
+        super().__init__(thickness, material_name, model, kx_mod, ky_mod, start_node=start_node, start_element=start_element)
+        self.radius = radius
+        self.height = height
+        self.num_elements = num_elements
+        self.Xo, self.Yo, self.Zo = origin[0], origin[1], origin[2]
+        self.axis = axis
+        self.element_type = element_type
+        self.generate()
+
+    def __repr__(self):
+        return (f"CylinderRingMesh(material_name={self.material_name!r}, radius={self.radius}, height={self.height}, "
+                f"thickness={self.thickness})")
+
+    def generate(self):
+        n = self.num_elements
+        theta = 2*pi/n
+        angles = [theta*(i - 1) for i in range(1, n + 1)]
+        if self.element_type == 'Quad':
+            prefix, cls = 'Q', Quad3D
+        elif self.element_type == 'Rect':
+            prefix, cls = 'R', Plate3D
+        else:
+            raise Exception('Invalid element type specified for cylinder ring mesh.')
+        self._build([(self.radius, angles, None), (self.radius, angles, self.height)], self._band(n), prefix, cls,
+                    'CylinderRingMesh')
+
+
+class _Stacked(Mesh):
+    """A mesh made of rings that share their boundary circles: later rings' nodes replace the equally named nodes of
+    earlier ones (`dict.update`), the elements are re-pointed at the surviving objects, everything is filed in the model."""
+
+    def _adopt(self, ring):
+        self.nodes.update(ring.nodes)
+        self.elements.update(ring.elements)
+
+    def _file(self):
+        for element in self.elements.values():
+            element.i_node = self.nodes[element.i_node.name]
+            element.j_node = self.nodes[element.j_node.name]
+            element.m_node = self.nodes[element.m_node.name]
+            element.n_node = self.nodes[element.n_node.name]
+        for node in self.nodes.values():
+            self.model.nodes[node.name] = node
+        for element in self.elements.values():
+            (self.model.quads if element.type.upper() == 'QUAD' else self.model.plates)[element.name] = element
+        self.is_generated = True
+        self.needs_update = False
+
+
+class AnnulusMesh(_Stacked):
+    """`Mesh.py:1126-1257`: rings from the inner to the outer radius; a ring whose quads have become wider than three mesh
+    sizes is a transition ring that triples the count."""
+
+    def __init__(self, mesh_size, outer_radius, inner_radius, thickness, material_name, model, kx_mod=1, ky_mod=1,
+                 origin=[0, 0, 0], axis='Y', start_node='N1', start_element='Q1'):
+        super().__init__(thickness, material_name, model, kx_mod, ky_mod, start_node, start_element)
+        self.inner_radius = inner_radius
+        self.outer_radius = outer_radius
+        self.mesh_size = mesh_size
+        self.origin = origin
+        self.axis = axis
+        self.num_quads_inner = None
+        self.num_quads_outer = None
+
+    def __repr__(self):
+        return (f"AnnulusMesh(material_name={self.material_name!r}, outer_radius={self.outer_radius}, "
+                f"inner_radius={self.inner_radius}, thickness={self.thickness})")
+
+    def generate(self):
+        if self.is_generated:
+            self._remove_from_model()
+        mesh_size, r_outer, r_inner = self.mesh_size, self.outer_radius, self.inner_radius
+        n = int(self.start_node[1:])
+        q = int(self.start_element[1:])
+        n_circ = int(2*pi*r_inner/mesh_size)
+        self.num_quads_outer = n_circ
+        while round(r_inner, 10) < round(r_outer, 10):
+            radial = r_outer - r_inner
+            b_circ = 2*pi*r_inner/n_circ
+            n_rad = int(radial/min(mesh_size, 3*b_circ))
+            h_rad = radial/n_rad
+            args = (self.thickness, self.material_name, self.model, self.kx_mod, self.ky_mod, self.origin, self.axis,
+                    'N' + str(n), 'Q' + str(q))
+            if b_circ > 3*mesh_size:
+                ring = AnnulusTransRingMesh(r_inner + h_rad, r_inner, n_circ, *args)
+                n += 3*n_circ
+                q += 4*n_circ
+                n_circ *= 3
+                self.num_quads_outer = n_circ
+            else:
+                ring = AnnulusRingMesh(r_inner + h_rad, r_inner, n_circ, *args)
+                n += n_circ
+                q += n_circ
+            self._adopt(ring)
+            r_inner += h_rad
+        self._file()
+
+
+class FrustrumMesh(AnnulusMesh):
+    """`Mesh.py:1623-1701`: an annulus whose nodes are lifted along the axis in proportion to their radius."""
+
+    def __init__(self, mesh_size, large_radius, small_radius, height, thickness, material_name, model, kx_mod=1, ky_mod=1,
+                 origin=[0, 0, 0], axis='Y', start_node='N1', start_element='Q1'):
+        super().__init__(mesh_size, large_radius, small_radius, thickness, material_name, model, kx_mod, ky_mod, origin, axis,
+                         start_node, start_element)
+        self.height = height
+
+    def __repr__(self):
+        return (f"FrustrumMesh(material_name={self.material_name!r}, large_radius={self.outer_radius}, "
+                f"small_radius={self.inner_radius}, height={self.height}, thickness={self.thickness})")
+
+    def generate(self):
+        super().generate()
+        Xo, Yo, Zo = self.origin[0], self.origin[1], self.origin[2]
+        span = self.outer_radius - self.inner_radius
+        for node in self.nodes.values():
+            X, Y, Z = node.X, node.Y, node.Z
+            if self.axis == 'Y':
+                node.Y += (((X - Xo)**2 + (Z - Zo)**2)**0.5 - self.outer_radius)/span*self.height
+            elif self.axis == 'X':
+                node.X += (((Y - Yo)**2 + (Z - Zo)**2)**0.5 - self.outer_radius)/span*self.height
+            elif self.axis == 'Z':
+                node.Z += (((X - Xo)**2 + (Y - Yo)**2)**0.5 - self.outer_radius)/span*self.height
+            else:
+                raise Exception('Invalid axis specified for frustrum mesh.')
+
+
+class CylinderMesh(_Stacked):
+    """`Mesh.py:1703-1845`: courses of `CylinderRingMesh` stacked along the axis (generated on construction)."""
+
+    def __init__(self, mesh_size, radius, height, thickness, material_name, model, kx_mod=1, ky_mod=1, origin=[0, 0, 0],
+                 axis='Y', start_node='N1', start_element='Q1', num_elements=None, element_type='Quad'):
+        super().__init__(thickness, material_name, model, kx_mod, ky_mod, start_node, start_element)
+        self.radius = radius
+        self.h = height
+        self.mesh_size = mesh_size
+        self.origin = origin
+        self.axis = axis
+        self.num_elements = int(round(2*pi*radius/mesh_size, 0)) if num_elements is None else num_elements
+        self.element_type = element_type
+        self.generate()
+
+    def __repr__(self):
+        return f"CylinderMesh(material_name={self.material_name!r}, radius={self.radius}, height={self.h}, thickness={self.thickness})"
+
+    def generate(self):
+        if self.is_generated:
+            self._remove_from_model()
+        along = {'Y': 1, 'X': 0, 'Z': 2}[self.axis]
+        y = self.origin[along]
+        n = int(self.start_node[1:])
+        q = int(self.start_element[1:])
+        while round(y, 10) < round(self.h, 10):
+            height = self.h - y
+            h_y = height/max(int(abs(height)/self.mesh_size), 1)
+            base = [0, 0, 0]
+            base[along] = y
+            self._adopt(CylinderRingMesh(self.radius, h_y, self.num_elements, self.thickness, self.material_name, self.model, 1, 1,
+                                         base, self.axis, 'N' + str(n), 'Q' + str(q), self.element_type))
+            n += self.num_elements
+            q += self.num_elements
+            y += h_y
+        self._file()

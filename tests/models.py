@@ -579,6 +579,31 @@ def rect_mesh_merged(FE):
     return m
 
 
+def annulus_mesh_case(FE):
+    """annulus about Y with two transition rings, then a second annulus about Z that continues the numbering"""
+    m = _mesh_model(FE)
+    m.add_annulus_mesh('A1', 1.0, 10.0, 1.0, 8.0, 'Conc', origin=[3.0, 1.0, -2.0])
+    m.meshes['A1'].generate()
+    m.add_annulus_mesh('A2', 2.0, 9.0, 4.0, 6.0, 'Conc', kx_mod=0.7, ky_mod=0.8, axis='Z')
+    m.meshes['A2'].generate()
+    return m
+
+
+def frustrum_mesh_case(FE):
+    m = _mesh_model(FE)
+    m.add_frustrum_mesh('F', 1.5, 8.0, 3.0, 5.0, 7.0, 'Conc', origin=[0.0, 2.0, 0.0], axis='X')
+    m.meshes['F'].generate()
+    return m
+
+
+def cylinder_mesh_case(FE):
+    """cylinders are generated on construction; the second one uses rectangles, a given element count and the Z axis"""
+    m = _mesh_model(FE)
+    m.add_cylinder_mesh('C1', 2.0, 5.0, 9.0, 8.0, 'Conc', origin=[4.0, 1.0, 7.0])
+    m.add_cylinder_mesh('C2', 1.5, 3.0, 4.0, 6.0, 'Conc', axis='Z', num_elements=10, element_type='Rect')
+    return m
+
+
 RECT_MESH_CASES = {
     'basic': rect_mesh_basic,
     'uneven_yz_rect': rect_mesh_uneven_yz_rect,
@@ -587,6 +612,9 @@ RECT_MESH_CASES = {
     'renamed': rect_mesh_renamed,
     'mat': mat_mesh_generated,
     'merged': rect_mesh_merged,
+    'annulus': annulus_mesh_case,
+    'frustrum': frustrum_mesh_case,
+    'cylinder': cylinder_mesh_case,
 }
 
 
@@ -635,6 +663,26 @@ def mat_mesh_tc(FE):
 MAT_PRESSURE_POINTS = [(40.0, 45.0), (0.0, 0.0), (123.4, 56.7), (240.0, 180.0), (200.0, 135.0), (15.0, 170.0), (300.0, 10.0)]
 
 
+def cylinder_tank(FE):
+    """A tank wall (`add_cylinder_mesh`) with a frustrum roof (`add_frustrum_mesh`, merged onto the wall's top ring): quads
+    in general position, base fixed, pressure on the wall and on the roof, two combos."""
+    m = _mesh_model(FE)
+    m.add_cylinder_mesh('WALL', 30.0, 60.0, 72.0, 10.0, 'Conc', num_elements=12)
+    m.add_frustrum_mesh('ROOF', 30.0, 60.0, 15.0, -18.0, 8.0, 'Conc', origin=[0.0, 72.0, 0.0])
+    m.meshes['ROOF'].generate()
+    m.merge_duplicate_nodes(tolerance=1e-6)
+    for node in m.nodes.values():
+        if node.Y == 0.0:
+            m.def_support(node.name, True, True, True, True, True, True)
+    for name in m.meshes['WALL'].elements:
+        m.add_quad_surface_pressure(name, 0.004, case='H')
+    for k, name in enumerate(m.meshes['ROOF'].elements):
+        m.add_quad_surface_pressure(name, -0.001 if k % 2 else -0.0015, case='S')
+    m.add_load_combo('C1', {'H': 1.0})
+    m.add_load_combo('C2', {'H': 1.2, 'S': 1.6})
+    return m
+
+
 SMALL_MODELS = {
     'space_frame': (space_frame, 'tc'),
     'portal_frame': (portal_frame, 'linear'),
@@ -654,6 +702,7 @@ SMALL_MODELS = {
     'mat_tc': (mat_tc, 'tc'),
     'rect_mesh_slab': (rect_mesh_slab, 'linear'),
     'mat_mesh_tc': (mat_mesh_tc, 'tc'),
+    'cylinder_tank': (cylinder_tank, 'linear'),
 }
 
 # keyword arguments of `analyze` for the load-stepping fixture (mode 'tc_steps')
