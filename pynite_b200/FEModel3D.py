@@ -119,6 +119,13 @@ class FEModel3D:
         self.sections[name] = Section(self, name, A, Iy, Iz, J)
         return name
 
+    def add_steel_section(self, name, A, Iy, Iz, J, Zy, Zz, material_name):
+        """`FEModel3D.add_steel_section` (:340-377)."""
+        from pynite_b200.Material import SteelSection
+        name = self._auto_name(name, self.sections, 'SC', 'Section')
+        self.sections[name] = SteelSection(self, name, A, Iy, Iz, J, Zy, Zz, material_name)
+        return name
+
     def add_spring(self, name, i_node, j_node, ks, tension_only=False, comp_only=False):
         name = self._auto_name(name, self.springs, 'S', 'Spring')
         ni, nj = self._nodes_by_name(i_node, j_node)
@@ -312,6 +319,36 @@ class FEModel3D:
     def delete_member(self, member_name):
         self.members.pop(member_name)
         self.solution = None
+
+    def delete_mesh(self, mesh_name):
+        """Removes a mesh and its elements; nodes shared with elements outside the mesh stay (`FEModel3D.py:1107-1130`)."""
+        if mesh_name not in self.meshes:
+            raise KeyError(f"Mesh '{mesh_name}' does not exist in the model.")
+        self.meshes[mesh_name]._remove_from_model()
+        self.meshes.pop(mesh_name)
+        self.solution = None
+
+    def rename(self):
+        """Renames nodes N1.., springs S1.., members M1.., plates P1.., quads Q1.. in dictionary order
+        (`FEModel3D.py:2904-2952`).  The entries are re-keyed one at a time over a snapshot of the old keys, as in the
+        reference: where an old name equals a new name handed out earlier the reference's outcome (an entry replaced)
+        is reproduced rather than repaired."""
+        for table, prefix in ((self.nodes, 'N'), (self.springs, 'S'), (self.members, 'M'), (self.plates, 'P'),
+                              (self.quads, 'Q')):
+            for k, old_key in enumerate(list(table.keys()), start=1):
+                new_key = prefix + str(k)
+                table[new_key] = table.pop(old_key)
+                table[new_key].name = new_key
+
+    def orphaned_nodes(self):
+        """Names of the nodes no spring, member, plate or quad is attached to (`FEModel3D.py:2954-2981`), in node order;
+        one pass over the elements instead of one pass per node."""
+        attached = set()
+        for elem in list(self.quads.values()) + list(self.plates.values()):
+            attached.update((id(elem.i_node), id(elem.j_node), id(elem.m_node), id(elem.n_node)))
+        for elem in list(self.members.values()) + list(self.springs.values()):
+            attached.update((id(elem.i_node), id(elem.j_node)))
+        return [node.name for node in self.nodes.values() if id(node) not in attached]
 
     def def_support(self, node_name, support_DX=False, support_DY=False, support_DZ=False,
                     support_RX=False, support_RY=False, support_RZ=False):

@@ -604,6 +604,29 @@ def cylinder_mesh_case(FE):
     return m
 
 
+def mesh_edited_case(FE):
+    """two meshes sharing an edge, one deleted again (shared nodes stay), a free-standing node, `orphaned_nodes`, then
+    `rename`: the second mesh's names start at N100 / Q100, so every entry is re-keyed, and the loose node is named like
+    a name `rename` hands out earlier (the reference then replaces an entry -- reproduced, see `FEModel3D.rename`)"""
+    m = _mesh_model(FE)
+    m.add_rectangle_mesh('A', 1.0, 3.0, 2.0, 8.0, 'Conc')
+    m.meshes['A'].generate()
+    m.add_rectangle_mesh('B', 1.0, 2.0, 2.0, 8.0, 'Conc', origin=[3.0, 0.0, 0.0], start_node='N100', start_element='Q100')
+    m.meshes['B'].generate()
+    m.merge_duplicate_nodes()
+    m.add_node('N3000', 50.0, 0.0, 0.0)
+    m.add_steel_section('W', 10.0, 20.0, 100.0, 1.5, 12.0, 30.0, 'Conc')
+    m.add_node('LOOSE', 70.0, 1.0, 0.0)
+    m.add_member('BM', 'N3000', 'LOOSE', 'Conc', 'W')
+    m.add_spring('SP', 'N1', 'N3000', 5.0)
+    m.delete_mesh('A')
+    m.add_node('ALONE', 80.0, 0.0, 0.0)
+    m.add_node('N2', 90.0, 0.0, 0.0)      # mesh A's N2 is gone; `rename` hands 'N2' out before it reaches this entry
+    m._test_removed = m.orphaned_nodes()
+    m.rename()
+    return m
+
+
 RECT_MESH_CASES = {
     'basic': rect_mesh_basic,
     'uneven_yz_rect': rect_mesh_uneven_yz_rect,
@@ -615,6 +638,7 @@ RECT_MESH_CASES = {
     'annulus': annulus_mesh_case,
     'frustrum': frustrum_mesh_case,
     'cylinder': cylinder_mesh_case,
+    'edited': mesh_edited_case,
 }
 
 

@@ -84,6 +84,11 @@ def mesh_record(model):
         rec[kind + '_conn'] = np.array([[e.i_node.name, e.j_node.name, e.m_node.name, e.n_node.name] for e in elems],
                                        dtype=str).reshape(-1, 4)
         rec[kind + '_props'] = np.array([[e.t, e.kx_mod, e.ky_mod] for e in elems], dtype=float).reshape(-1, 3)
+    for kind, table in (('member', model.members), ('spring', model.springs)):
+        rec[kind + '_keys'] = np.array(list(table.keys()), dtype=str)
+        rec[kind + '_names'] = np.array([e.name for e in table.values()], dtype=str)
+        rec[kind + '_ij'] = np.array([[e.i_node.name, e.j_node.name] for e in table.values()], dtype=str).reshape(-1, 2)
+    rec['section_reprs'] = np.array([repr(sec) for sec in model.sections.values()], dtype=str)
     springs, loads = [], []
     for n in nodes:
         for dof in ('DX', 'DY', 'DZ', 'RX', 'RY', 'RZ'):
