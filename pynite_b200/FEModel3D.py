@@ -498,6 +498,28 @@ class FEModel3D:
         """Two-step P-Delta analysis (`FEModel3D.py:2413-2467`, `Analysis.py:329-471`)."""
         _analysis.run_pdelta(self, log, check_stability, max_iter, sparse, combo_tags)
 
+    def _calculate_characteristic_length(self):
+        """Average member length, else the bounding-box diagonal of the nodes, else 1.0 (`FEModel3D.py:1984-2002`)."""
+        if self.members:
+            return sum(member.L() for member in self.members.values())/len(self.members)
+        if self.nodes:
+            xyz = np.array([(node.X, node.Y, node.Z) for node in self.nodes.values()], dtype=float)
+            return float(sum((xyz.max(axis=0) - xyz.min(axis=0))**2)**0.5)
+        return 1.0
+
+    def M(self, mass_combo_name=None, mass_direction='Y', gravity=1.0, log=False, sparse=True):
+        """Global mass matrix (`FEModel3D.py:2004-2134`): consistent member mass from self-weight loads, member and
+        nodal loads of the mass combination along `mass_direction` converted with m = F/g."""
+        from pynite_b200 import modal as _modal
+        return _modal.global_M(self, mass_combo_name, mass_direction, gravity, log, sparse)
+
+    def analyze_modal(self, num_modes=12, mass_combo_name='Combo 1', mass_direction='Y', gravity=1.0, log=False,
+                      check_stability=True):
+        """Natural frequencies (`model.frequencies`, Hz) and mode shapes (`model._D['Mode i']`, `node.DX['Mode i']`)
+        (`FEModel3D.py:2469-2568`); block shift-invert Lanczos whose solves run on the GPU (`modal.py`)."""
+        from pynite_b200 import modal as _modal
+        _modal.run_modal(self, num_modes, mass_combo_name, mass_direction, gravity, log, check_stability)
+
     # ------------------------------------------------------------------------------------------
     # result plumbing used by the element objects
     # ------------------------------------------------------------------------------------------

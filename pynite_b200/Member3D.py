@@ -58,6 +58,22 @@ class Member3D:
         """Global end forces (12, 1) for a combo (`Member3D.py:1072-1078`)."""
         return self.model._element_force('member', self.ID, combo_name, local=False)
 
+    def m(self, mass_combo_name, mass_direction='Y', gravity=1.0):
+        """Condensed local mass matrix (`Member3D.py:605-646`)."""
+        from pynite_b200 import modal
+        combo = self.model.load_combos[mass_combo_name]
+        lm, x = modal.member_load_mass(self, combo, mass_direction, gravity)
+        m = modal.member_local_mass(np.array([self.L()]), np.array([self.section.A]), np.array([self.section.J]),
+                                    np.array([lm]), np.array([x]),
+                                    np.array([modal.member_material_mass(self, combo, gravity)]))[0]
+        return modal.condense_released(m, self.Releases)
+
+    def M(self, mass_combo_name=None, mass_direction='Y', gravity=1.0):
+        """Global mass matrix `T^T m T` (`Member3D.py:648-672`)."""
+        from pynite_b200 import modal
+        return modal.member_global_mass(self.model, [self], self.model.load_combos[mass_combo_name], mass_direction,
+                                        gravity)[0]
+
 
 class PhysMember(Member3D):
 

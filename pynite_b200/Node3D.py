@@ -95,6 +95,22 @@ class Node3D:
         """Euclidean distance to another node (`Pynite/Node3D.py:90-99`)."""
         return ((self.X - other.X)**2 + (self.Y - other.Y)**2 + (self.Z - other.Z)**2)**0.5
 
+    def M(self, mass_combo_name=None, mass_direction='Y', gravity=1.0, characteristic_length=None):
+        """6 x 6 nodal mass matrix (`Pynite/Node3D.py:101-151`): the mass of the nodal loads of the mass combination on
+        the three translations, and 1 % of m L^2 on the unsupported rotations when a characteristic length is given."""
+        from pynite_b200.modal import node_mass
+        if mass_combo_name not in self.model.load_combos:
+            raise ValueError(f'Load combination {mass_combo_name} not found in the model.')
+        m = np.zeros((6, 6))
+        total = node_mass(self, self.model.load_combos[mass_combo_name], mass_direction, gravity)
+        if total > 0:
+            m[0, 0] = m[1, 1] = m[2, 2] = total
+            if characteristic_length is not None:
+                for k, held in enumerate((self.support_RX, self.support_RY, self.support_RZ)):
+                    if not held:
+                        m[3 + k, 3 + k] = total*characteristic_length**2*0.01
+        return m
+
 
 def _make_view_property(store_name, comp):
     def getter(self):

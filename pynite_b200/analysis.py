@@ -62,15 +62,18 @@ def renumber(model):
         quad.ID = i
 
 
-def prepare_model(model):
-    """`Analysis._prepare_model` (:20-79): rectangle meshes and mat foundations are generated here when they have not
-    been (shear walls and modal combos: out of scope)."""
+def prepare_model(model, n_modes=0):
+    """`Analysis._prepare_model` (:20-79): meshes and mat foundations are generated here when they have not been; the
+    combinations tagged 'modal' are dropped and `n_modes` fresh ones ('Mode 1', ...) added (:44-51).  Shear walls: out of
+    scope."""
     model._D = {}
     model._Rxn = {}
     if model.load_combos == {}:
         model.load_combos['Combo 1'] = LoadCombo('Combo 1', factors={'Case 1': 1.0})
     for name in [n for n, c in model.load_combos.items() if c.combo_tags is not None and 'modal' in c.combo_tags]:
         model.load_combos.pop(name)
+    for i in range(n_modes):
+        model.add_load_combo(f'Mode {i + 1}', {}, ['modal'])
     for mesh in list(getattr(model, 'meshes', {}).values()) + list(getattr(model, 'mats', {}).values()):
         if not mesh.is_generated or mesh.needs_update:
             mesh.generate()

@@ -732,3 +732,80 @@ SMALL_MODELS = {
 # keyword arguments of `analyze` for the load-stepping fixture (mode 'tc_steps')
 TC_STEPS_KW = dict(num_steps=4, spring_tolerance=0.2, member_tolerance=0.0)
 
+
+
+# ---------------------------------------------------------------------------------------------
+# modal analysis (`FEModel3D.analyze_modal`, `FEModel3D.py:2469-2568`): builder -> keyword arguments of the call
+# ---------------------------------------------------------------------------------------------
+def modal_cantilever(FE):
+    """ten members along X (the shape of the reference's `test_modal_analysis.py` cantilever, with Iy != Iz so that the
+    two bending families are not degenerate): consistent mass from self weight plus nodal masses in one combination"""
+    m = FE()
+    L, A, rho = 5.0, 0.01, 7800.0
+    for n in range(11):
+        m.add_node(f'N{n + 1}', n*L/10, 0.0, 0.0)
+    m.def_support('N1', True, True, True, True, True, True)
+    m.add_material('Steel', 200e9, 80e9, 0.3, rho)
+    m.add_section('BeamSection', A, 8.33e-6, 5.1e-6, 1.67e-6)
+    for n in range(10):
+        m.add_member(f'M{n + 1}', f'N{n + 1}', f'N{n + 2}', 'Steel', 'BeamSection')
+    m.add_member_self_weight('FY', -1.0, 'D1')
+    for n in range(11):
+        m.add_node_load(f'N{n + 1}', 'FY', -A*rho*L/(20 if n in (0, 10) else 10), 'D2')
+    m.add_load_combo('Consistent Mass Combo', {'D1': 1.0})
+    m.add_load_combo('Both', {'D1': 1.0, 'D2': 0.5})
+    return m
+
+
+def modal_frame(FE):
+    """two-bay space frame in general position: a physical member split at an interior node, an inclined and a rolled
+    member, an end release, non-self-weight distributed and point loads in the mass direction, nodal masses, a spring, an
+    enforced support displacement (must come back in the mode shapes' known DOFs) and a support spring"""
+    m = FE()
+    m.add_material('Steel', 29000.0, 11200.0, 0.3, 0.000283)
+    m.add_section('Col', 20.0, 150.0, 400.0, 3.0)
+    m.add_section('Bm', 12.0, 60.0, 300.0, 1.5)
+    pts = {'A0': (0, 0, 0), 'B0': (240, 0, 0), 'C0': (240, 0, 200), 'D0': (0, 0, 200),
+           'A1': (0, 144, 0), 'B1': (240, 144, 0), 'C1': (250, 150, 210), 'D1': (0, 144, 200), 'AM': (0, 72, 0), 'E1': (120, 190, 100)}
+    for name, (x, y, z) in pts.items():
+        m.add_node(name, float(x), float(y), float(z))
+    for base in ('A0', 'B0', 'C0'):
+        m.def_support(base, True, True, True, True, True, True)
+    m.def_support('D0', True, True, True, False, False, False)
+    m.def_node_disp('D0', 'DY', -0.25)
+    m.def_support_spring('E1', 'DY', 40.0)
+    m.add_member('CA', 'A0', 'A1', 'Steel', 'Col')           # split at AM
+    m.add_member('CB', 'B0', 'B1', 'Steel', 'Col', rotation=30.0)
+    m.add_member('CC', 'C0', 'C1', 'Steel', 'Col')           # inclined
+    m.add_member('CD', 'D0', 'D1', 'Steel', 'Col')
+    m.add_member('B1', 'A1', 'B1', 'Steel', 'Bm')
+    m.add_member('B2', 'B1', 'C1', 'Steel', 'Bm')
+    m.add_member('B3', 'C1', 'D1', 'Steel', 'Bm')
+    m.add_member('B4', 'D1', 'A1', 'Steel', 'Bm')
+    m.add_member('R1', 'A1', 'E1', 'Steel', 'Bm')
+    m.add_member('R2', 'C1', 'E1', 'Steel', 'Bm', rotation=-15.0)
+    m.def_releases('B3', Rzj=True, Ryj=True)
+    m.add_spring('BR', 'AM', 'B1', 35.0)
+    m.add_member_self_weight('FY', -1.0, 'SW')
+    m.add_member_dist_load('B1', 'FY', -0.05, -0.08, 20.0, 200.0, case='SD')
+    m.add_member_dist_load('B2', 'FY', -0.04, -0.04, case='SD')
+    m.add_member_dist_load('B2', 'FX', 0.03, 0.03, case='SD')        # not in the mass direction
+    m.add_member_pt_load('B4', 'FY', -3.0, 80.0, case='SD')
+    m.add_member_pt_load('CA', 'FY', -2.0, 100.0, case='SD')
+    m.add_node_load('E1', 'FY', -6.0, 'SD')
+    m.add_node_load('B1', 'FY', -1.5, 'L')
+    m.add_node_load('B1', 'FX', 4.0, 'L')
+    m.add_load_combo('Mass', {'SW': 1.0, 'SD': 1.0, 'L': 0.25})
+    m.add_load_combo('Mass nodal', {'SW': 1.0, 'L': 0.25})
+    return m
+
+
+MODAL_MODELS = {
+    'modal_cantilever_consistent': (modal_cantilever, dict(num_modes=3, mass_combo_name='Consistent Mass Combo',
+                                                           mass_direction='Y', gravity=9.81)),
+    'modal_cantilever_both': (modal_cantilever, dict(num_modes=6, mass_combo_name='Both', mass_direction='Y', gravity=9.81)),
+    'modal_frame': (modal_frame, dict(num_modes=9, mass_combo_name='Mass nodal', mass_direction='Y', gravity=386.4)),
+    # member loads as masses: the reference's `lumped_m` end shares `(1 - x)/L`, `x/L` make this mass matrix indefinite (its
+    # own `analyze_modal` returns NaN frequencies), so only the matrices are compared
+    'modal_frame_member_loads': (modal_frame, dict(num_modes=0, mass_combo_name='Mass', mass_direction='Y', gravity=386.4)),
+}
