@@ -4,7 +4,8 @@
 section, roll angle, loads, releases, tension/compression-only flags, per-combo activity).  All
 stiffness math (`_ke_unc` :176, `ke` :147, `kg` :210, `T` :933, `Ke` :1038, `fer` :742, `f` :872)
 runs in the sm_100a member kernels (`csrc/elem_line.cuh`, `csrc/pn_elements.cu`); `f()/F()` here read the end forces the
-GPU solve produced.
+GPU solve produced, and the result diagrams (`shear/moment/axial/torque/deflection`, their extremes and arrays,
+`Member3D.py:1163-2834`, `PhysMember.py:202-1404`) are evaluated from them in `diagrams.py`.
 
 `PhysMember.descritize` restates `Pynite/PhysMember.py:37-200`: a physical member is split at every
 model node lying strictly inside it (perpendicular distance <= 1e-12 (1+L)), sub-members are named
@@ -17,8 +18,10 @@ from math import isclose
 
 import numpy as np
 
+from pynite_b200.diagrams import PhysMemberDiagrams, SubMemberDiagrams
 
-class Member3D:
+
+class Member3D(SubMemberDiagrams):
 
     def __init__(self, model, name, i_node, j_node, material_name, section_name,
                  rotation=0.0, tension_only=False, comp_only=False):
@@ -75,7 +78,7 @@ class Member3D:
                                         gravity)[0]
 
 
-class PhysMember(Member3D):
+class PhysMember(PhysMemberDiagrams, Member3D):
 
     def __init__(self, model, name, i_node, j_node, material_name, section_name,
                  rotation=0.0, tension_only=False, comp_only=False):
@@ -164,76 +167,3 @@ class PhysMember(Member3D):
                     sub.PtLoads.append([direction, P, x - xi, case])
 
             self.sub_members[sub_name] = sub
-
-    # -- axial-force extremes used by the tension/compression-only iteration ------------------
-    def _axial_extremes(self, combo_name):
-        """(max, min) axial force over all sub-members (`Analysis.py:1022,1037` consumers).
-
-        Sign convention as the reference's `Member3D.axial`: positive = compression.  The axial
-        force at station x of a sub-member is f[0] (local i-end force) plus the axial loads applied
-        between 0 and x; extremes of a piecewise linear/quadratic diagram are at load stations and
-        at interior stationary points of distributed loads.
-        """
-        model = self.model
-        combo = model.load_combos[combo_name]
-        best_max, best_min = -np.inf, np.inf
-        for sub in self.sub_members.values():
-            f0 = sub.f(combo_name)[0, 0]
-            L = sub.L()
-            R = model._member_dircos(sub)
-            pts, dists = [], []
-            for direction, P, x, case in sub.PtLoads:
-                factor = combo.factors.get(case)
-                if factor is None:
-                    continue
-                if direction == 'Fx':
-                    pts.append((x, factor*P))
-                elif direction in ('FX', 'FY', 'FZ'):
-                    g = np.zeros(3)
-                    g['XYZ'.index(direction[1])] = P
-                    pts.append((x, factor*(R @ g)[0]))
-            for direction, w1, w2, x1, x2, case, _sw in sub.DistLoads:
-                factor = combo.factors.get(case)
-                if factor is None:
-                    continue
-                if direction == 'Fx':
-                    dists.append((x1, x2, factor*w1, factor*w2))
-                elif direction in ('FX', 'FY', 'FZ'):
-                    k = 'XYZ'.index(direction[1])
-                    g1 = np.zeros(3)
-                    g2 = np.zeros(3)
-                    g1[k], g2[k] = w1, w2
-                    dists.append((x1, x2, factor*(R @ g1)[0], factor*(R @ g2)[0]))
-
-            def axial_at(x, after):
-                n = f0
-                for xp, p in pts:
-                    if xp < x or (after and xp == x):
-                        n += p
-                for x1, x2, p1, p2 in dists:
-                    if x > x1 and x2 > x1:
-                        xe = min(x, x2)
-                        pe = p1 + (p2 - p1)*(xe - x1)/(x2 - x1)
-                        n += 0.5*(p1 + pe)*(xe - x1)
-                return n
-
-            stations = {0.0, L}
-            for xp, _p in pts:
-                stations.add(xp)
-            for x1, x2, p1, p2 in dists:
-                stations.add(x1)
-                stations.add(x2)
-                if p1*p2 < 0:
-                    stations.add(x1 + (x2 - x1)*p1/(p1 - p2))
-            for x in stations:
-                for after in (False, True):
-                    n = axial_at(x, after)
-                    best_max = max(best_max, n)
-                    best_min = min(best_min, n)
-        return best_max, best_min
-
-    def max_axial(self, combo_name='Combo 1'):
-        return self._axial_extremes(combo_name)[0]
-
-    def min_axial(self, combo_name='Combo 1'):
-        return self._axial_extremes(combo_name)[1]

@@ -1,0 +1,39 @@
+"""Member result diagrams after a real GPU analysis, against the reference's (tests/golden/member_diagrams.npz).
+
+The diagram arithmetic itself is pinned on the CPU (tests/test_diagrams_cpu.py feeds it the reference's displacements and end
+forces); this file closes the loop `analyze*() on the GPU -> member.f() / model._D -> diagrams`.  It was written after the
+round's GPU minutes were spent and has NOT run on hardware yet, hence xfail(strict=False): a pass shows as XPASS, a failure
+does not stop the suite (it sorts last for the same reason).  Remove the mark after the first green run on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import models
+from tests.util import diagram_record
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason='added after the GPU budget of the round was spent: not yet run on hardware')]
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'member_diagrams.npz'))
+
+
+@pytest.mark.parametrize('name', ['portal_frame', 'continuous_beam', 'pdelta_frame', 'braced_tc'])
+def test_diagrams_after_gpu_analysis(name):
+    from pynite_b200 import FEModel3D
+    build, mode = models.SMALL_MODELS[name]
+    m = build(FEModel3D)
+    if mode == 'linear':
+        m.analyze_linear()
+    elif mode == 'tc':
+        m.analyze()
+    else:
+        m.analyze_PDelta()
+    rec = diagram_record(m)
+    assert np.array_equal(rec['active'], GOLD[name + '/active'])
+    tol = 1e-5 if mode == 'pdelta' else 1e-8              # (the P-Delta displacements themselves are held to 1e-6)
+    for key in ('arrays', 'points', 'extremes'):
+        ours, ref = rec[key], GOLD[name + '/' + key]
+        for q in range(ours.shape[2]):
+            a, b = (ours[:, :, q, 1], ref[:, :, q, 1]) if key == 'arrays' else (ours[:, :, q], ref[:, :, q])
+            assert np.abs(a - b).max() <= tol*max(np.abs(b).max(), 1e-300), (key, q)

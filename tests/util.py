@@ -107,3 +107,51 @@ def mesh_record(model):
         rec['mesh_' + mname + '_elements'] = np.array(list(mesh.elements.keys()), dtype=str)
         rec['mesh_' + mname + '_last'] = np.array([getattr(mesh.last_node, 'name', 'None'), getattr(mesh.last_element, 'name', 'None')])
     return rec
+
+
+# ---------------------------------------------------------------------------------------------
+# member result diagrams (tests/golden/member_diagrams.npz, tests/test_diagrams_cpu.py)
+# ---------------------------------------------------------------------------------------------
+DIAGRAM_FIXTURES = ['portal_frame', 'continuous_beam', 'moment_frame', 'pdelta_frame', 'pdelta_column',
+                    'pdelta_near_buckling', 'braced_tc', 'tc_load_steps']
+DIAGRAM_POINTS = 9
+DIAGRAM_ARRAYS = [('shear_array', 'Fy'), ('shear_array', 'Fz'), ('moment_array', 'My'), ('moment_array', 'Mz'),
+                  ('axial_array', None), ('torque_array', None), ('deflection_array', 'dx'), ('deflection_array', 'dy'),
+                  ('deflection_array', 'dz')]
+DIAGRAM_POINT_QUERIES = [('shear', 'Fy'), ('shear', 'Fz'), ('moment', 'My'), ('moment', 'Mz'), ('axial', None),
+                         ('torque', None), ('deflection', 'dx'), ('deflection', 'dy'), ('deflection', 'dz'),
+                         ('rel_deflection', 'dy'), ('rel_deflection', 'dz')]
+DIAGRAM_EXTREMES = [('shear', 'Fy'), ('shear', 'Fz'), ('moment', 'My'), ('moment', 'Mz'), ('axial', None), ('torque', None),
+                    ('deflection', 'dx'), ('deflection', 'dy'), ('deflection', 'dz')]
+DIAGRAM_STATIONS = (0.0, 0.37, 0.5, 0.81, 1.0)             # fractions of the physical member's length
+
+
+def _call(obj, method, direction, *rest):
+    fn = getattr(obj, method)
+    return fn(direction, *rest) if direction is not None else fn(*rest)
+
+
+def diagram_record(model):
+    """Every physical member's diagrams for every combination (works on the reference's objects and on ours):
+    arrays[combo, member, quantity, 2, DIAGRAM_POINTS], points[combo, member, query, station], extremes[combo, member,
+    quantity, (max, min)], and the members' activity."""
+    combos = list(model.load_combos.keys())
+    members = list(model.members.values())
+    arrays = np.zeros((len(combos), len(members), len(DIAGRAM_ARRAYS), 2, DIAGRAM_POINTS))
+    points = np.zeros((len(combos), len(members), len(DIAGRAM_POINT_QUERIES), len(DIAGRAM_STATIONS)))
+    extremes = np.zeros((len(combos), len(members), len(DIAGRAM_EXTREMES), 2))
+    active = np.zeros((len(combos), len(members)), dtype=bool)
+    for c, combo in enumerate(combos):
+        for k, member in enumerate(members):
+            active[c, k] = bool(member.active[combo])
+            L = member.L()
+            for q, (method, direction) in enumerate(DIAGRAM_ARRAYS):
+                arrays[c, k, q] = _call(member, method, direction, DIAGRAM_POINTS, combo)
+            for q, (method, direction) in enumerate(DIAGRAM_POINT_QUERIES):
+                for s, frac in enumerate(DIAGRAM_STATIONS):
+                    points[c, k, q, s] = _call(member, method, direction, frac*L, combo)
+            for q, (what, direction) in enumerate(DIAGRAM_EXTREMES):
+                extremes[c, k, q, 0] = _call(member, 'max_' + what, direction, combo)
+                extremes[c, k, q, 1] = _call(member, 'min_' + what, direction, combo)
+    return {'arrays': arrays, 'points': points, 'extremes': extremes, 'active': active,
+            'member_names': np.array([m.name for m in members], dtype=str)}
