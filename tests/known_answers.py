@@ -1,0 +1,146 @@
+"""The known-answer models of the reference's own test suite for the assembly + solve path, restated with the
+reference's builder calls: each entry returns the model and a list of checks `(kind, node, component, expected, rel_tol,
+abs_tol)`, `kind` in {'D', 'Rxn'}, with the tolerance the reference's test applies.  Used twice: the CPU oracle is pinned
+against them (tests/test_known_answers.py, `-m "not gpu"`), and the CUDA path reproduces them through the public API
+(`-m gpu`)."""
+import math
+
+
+def logan_5_30_frame_xy(FE):
+    """`Testing/test_2D_frames.py:25-83` (Logan, A First Course in the FEM, problem 5.30; kips, inches)."""
+    m = FE()
+    for name, x, y in (('N1', 0, 0), ('N2', 0, 30*12), ('N3', 15*12, 40*12), ('N4', 35*12, 40*12), ('N5', 50*12, 30*12),
+                       ('N6', 50*12, 0)):
+        m.add_node(name, x, y, 0)
+    m.def_support('N1', True, True, True, True, True, True)
+    m.def_support('N6', True, True, True, True, True, True)
+    m.add_material('Steel', 30000, 250, 0.5, 490/1000/12**3)
+    m.add_section('FrameSection', 12, 250, 200, 250)
+    for k in range(5):
+        m.add_member(f'M{k + 1}', f'N{k + 1}', f'N{k + 2}', 'Steel', 'FrameSection')
+    m.add_node_load('N3', 'FY', -30)
+    m.add_node_load('N4', 'FY', -30)
+    checks = []
+    for node, sign in (('N1', 1.0), ('N6', -1.0)):
+        checks += [('Rxn', node, 'FX', sign*11.6877, 5e-3, 0), ('Rxn', node, 'FY', 30.0, 5e-3, 0),
+                   ('Rxn', node, 'MZ', -sign*1810.0745, 5e-3, 0)]
+    return m, 'tc', checks
+
+
+def frame_member_ptload(FE):
+    """`Testing/test_2D_frames.py:85-121` (W8x24 portal, point + distributed member load; kips, feet)."""
+    m = FE()
+    for name, x, y in (('N1', 0, 0), ('N2', 0, 7.667), ('N3', 7.75, 7.667), ('N4', 7.75, 0)):
+        m.add_node(name, x, y, 0)
+    m.def_support('N1', True, True, True, True, True, False)
+    m.def_support('N4', True, True, True, True, True, False)
+    m.add_material('Steel', 29000*12**2, 1111200*12**2, 0.5, 490/1000/12**3)
+    m.add_section('FrameSection', 5.26/12**2, 18.3/12**4, 82.7/12**4, 0.346/12**4)
+    m.add_member('M1', 'N1', 'N2', 'Steel', 'FrameSection')
+    m.add_member('M2', 'N2', 'N3', 'Steel', 'FrameSection')
+    m.add_member('M3', 'N4', 'N3', 'Steel', 'FrameSection')
+    m.add_member_pt_load('M2', 'Fy', -5, 7.75/2)
+    m.add_member_dist_load('M2', 'Fy', -0.024, -0.024)
+    return m, 'tc', [('D', 'N1', 'RZ', 0.00022794540510395617, 5e-3, 0)]
+
+
+def kassimali_3_35(FE):
+    """`Testing/test_2D_frames.py:230-293` (global-direction member loads, an internal hinge, the XZ plane)."""
+    m = FE()
+    for name, x, z in (('A', 0, 0), ('B', 0, 24), ('C', 12, 0), ('D', 12, 24), ('E', 24, 12)):
+        m.add_node(name, x, 0, z)
+    m.add_material('Steel', 29000*12**2, 11200*12**2, 0.5, 490/1000)
+    m.add_section('FrameSection', 7.65/12**2, 17.3/12**4, 204/12**4, 0.3/12**4)
+    for name, i, j in (('AC', 'A', 'C'), ('BD', 'B', 'D'), ('CE', 'C', 'E'), ('ED', 'E', 'D')):
+        m.add_member(name, i, j, 'Steel', 'FrameSection')
+    m.def_support('A', support_DX=True, support_DY=True, support_DZ=True)
+    m.def_support('B', support_DX=True, support_DY=True, support_DZ=True)
+    m.def_support('E', support_DY=True)
+    m.def_releases('CE', Rzj=True)
+    m.add_member_pt_load('AC', 'FZ', 20, 12)
+    m.add_member_dist_load('CE', 'FX', -1.5, -1.5)
+    m.add_member_dist_load('ED', 'FX', -1.5, -1.5)
+    return m, 'tc', [('Rxn', 'A', 'FZ', -8.63, 0.1, 0), ('Rxn', 'A', 'FX', 15.46, 0.05, 0), ('Rxn', 'B', 'FZ', -11.37, 0.7, 0),
+                     ('Rxn', 'B', 'FX', 35.45, 0.05, 0)]
+
+
+def support_settlement(FE):
+    """`Testing/test_support_settlement.py:30-93` (three-span beam, enforced support displacements; 7.6 % as there)."""
+    m = FE()
+    for k, name in enumerate('ABCD'):
+        m.add_node(name, k*20*12, 0, 0)
+    m.add_material('Steel', 29000, 11200, 0.3, 490/1000/12**3)
+    m.add_section('Section', 20, 1000, 7800, 8800)
+    for i, j in ('AB', 'BC', 'CD'):
+        m.add_member(i + j, i, j, 'Steel', 'Section')
+        m.add_member_dist_load(i + j, 'Fy', -2/12, -2/12)
+    m.def_support('A', True, True, True, True, False, False)
+    for name in 'BCD':
+        m.def_support(name, False, True, True, False, False, False)
+    m.def_node_disp('B', 'DY', -5/8)
+    m.def_node_disp('C', 'DY', -1.5)
+    m.def_node_disp('D', 'DY', -0.75)
+    return m, 'tc', [('Rxn', 'A', 'FY', -1.098, 0.076, 0), ('Rxn', 'B', 'FY', 122.373, 0.076, 0),
+                     ('Rxn', 'C', 'FY', -61.451, 0.076, 0), ('Rxn', 'D', 'FY', 60.176, 0.076, 0)]
+
+
+def logan_12_1_plate(FE):
+    """`Testing/test_plates&quads.py:11-64` (Logan example 12.1: clamped square plate, centre load; pounds, inches)."""
+    m = FE()
+    for k in range(9):
+        m.add_node(f'N{k + 1}', 10*(k % 3), 10*(k//3), 0)
+    m.add_material('Steel', 30000000, 11200000, 0.3, 0.284)
+    m.add_plate('P1', 'N1', 'N2', 'N5', 'N4', 0.1, 'Steel')
+    m.add_plate('P2', 'N2', 'N3', 'N6', 'N5', 0.1, 'Steel')
+    m.add_plate('P3', 'N4', 'N5', 'N8', 'N7', 0.1, 'Steel')
+    m.add_plate('P4', 'N5', 'N6', 'N9', 'N8', 0.1, 'Steel')
+    m.add_node_load('N5', 'FZ', -100)
+    for k in (1, 2, 3, 4, 6, 7, 8, 9):
+        m.def_support(f'N{k}', True, True, True, True, True, True)
+    m.def_support('N5', True, True, False, False, False, True)
+    return m, 'tc', [('D', 'N5', 'DZ', -0.0861742424242424, 0.01, 0)]
+
+
+def torque_beam(FE):
+    """`Testing/test_torsion.py:25-60` (two member torques on a beam fixed in torsion at both ends)."""
+    m = FE()
+    m.add_node('N1', 0, 0, 0)
+    m.add_node('N2', 168, 0, 0)
+    m.add_material('Steel', 29000, 11400, 0.5, 490/1000/12**3)
+    m.add_section('Section', 20, 100, 150, 250)
+    m.add_member('M1', 'N1', 'N2', 'Steel', 'Section')
+    m.def_support('N1', False, True, True, True, True, True)
+    m.def_support('N2', True, True, True, True, True, True)
+    m.add_member_pt_load('M1', 'Mx', 5, 3*12)
+    m.add_member_pt_load('M1', 'Mx', 10, 11*12)
+    return m, 'tc', [('Rxn', 'N1', 'MX', -6.07, 0, 5e-3), ('Rxn', 'N2', 'MX', -8.93, 0, 5e-3)]
+
+
+def aisc_cantilever_pdelta(FE):
+    """`Testing/test_AISC_PDelta_benchmarks.py:8-68` (axially loaded cantilever, closed form `H L tan(a)/a`; kips, feet)."""
+    m = FE()
+    L, H, P, I = 20, 5, 100, 100/12**4
+    E, G = 29000*12**2, 11200*12**2
+    m.add_material('Steel', E, G, 0.3, 0.490)
+    m.add_section('BeamSection', 10/12**2, I, I, 200/12**4)
+    for i in range(6):
+        m.add_node('N' + str(i + 1), 0, i*L/5, 0)
+    m.add_member('M1', 'N1', 'N6', 'Steel', 'BeamSection')
+    m.def_support('N1', True, True, True, True, True, True)
+    m.add_node_load('N6', 'FY', -P)
+    m.add_node_load('N6', 'FX', H)
+    alpha = (P*L**2/(E*I))**0.5
+    Mmax = H*L*(math.tan(alpha)/alpha)
+    ymax = H*L**3/(3*E*I)*(3*(math.tan(alpha) - alpha)/alpha**3)
+    return m, 'pdelta', [('Rxn', 'N1', 'MZ', Mmax, 0.01, 0), ('D', 'N6', 'DX', ymax, 0.01, 0)]
+
+
+KNOWN_ANSWERS = {
+    'logan_5_30_frame_xy': logan_5_30_frame_xy,
+    'frame_member_ptload': frame_member_ptload,
+    'kassimali_3_35': kassimali_3_35,
+    'support_settlement': support_settlement,
+    'logan_12_1_plate': logan_12_1_plate,
+    'torque_beam': torque_beam,
+    'aisc_cantilever_pdelta': aisc_cantilever_pdelta,
+}
