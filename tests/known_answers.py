@@ -135,6 +135,80 @@ def aisc_cantilever_pdelta(FE):
     return m, 'pdelta', [('Rxn', 'N1', 'MZ', Mmax, 0.01, 0), ('D', 'N6', 'DX', ymax, 0.01, 0)]
 
 
+def _aisc_column(FE, nodes, weak_axis=False):
+    m = FE()
+    for name, y in nodes:
+        m.add_node(name, 0, y, 0)
+    m.add_material('Steel', 29000*12**2, 11200*12**2, 0.3, 0.490)
+    strong, weak = 484/12**4, 51.4/12**4
+    m.add_section('ColumnSection', 14.1/12**2, strong if weak_axis else weak, weak if weak_axis else strong, 1.45/12**4)
+    m.add_member('M1', 'N1', 'N2', 'Steel', 'ColumnSection')
+    for k in range(4):
+        m.add_load_combo(f'Combo {k + 1}', {f'P{k + 1}': 1})
+    return m
+
+
+def aisc_case1(FE):
+    """`Testing/test_AISC_PDelta_benchmarks.py:71-135`: pinned column, uniform transverse load, axial 0 / 150 / 300 / 450 k;
+    mid-height moment (kip-in, 3 %) and deflection (in, 5 %) read from the member diagrams."""
+    m = _aisc_column(FE, (('N1', 0), ('N2', 28), ('N4', 14)))
+    m.def_support('N1', True, True, True, False, True, False)
+    m.def_support('N2', True, False, True, False, False, False)
+    for k, P in enumerate((0, 150, 300, 450)):
+        m.add_member_dist_load('M1', 'Fy', -0.200, -0.200, case=f'P{k + 1}')
+        if P:
+            m.add_node_load('N2', 'FY', -P, f'P{k + 1}')
+    checks = []
+    for k, (M, d) in enumerate(zip((235, 269, 313, 375), (0.197, 0.224, 0.261, 0.311))):
+        checks += [('moment', 'M1', 'Mz', 14, f'Combo {k + 1}', -M/12, 0.03), ('deflection', 'M1', 'dy', 14, f'Combo {k + 1}', -d/12, 0.05)]
+    return m, 'pdelta', checks
+
+
+def aisc_case2(FE, weak_axis=False):
+    """`Testing/test_AISC_PDelta_benchmarks.py:138-203` (and `:208-273` about the weak axis): cantilever, unit tip load,
+    axial 0 / 100 / 150 / 200 k; base moment (3 %) and tip deflection (5 %) from the member diagrams."""
+    m = _aisc_column(FE, (('N1', 0), ('N2', 28), ('N4', 28/3), ('N5', 56/3)), weak_axis)
+    m.def_support('N1', True, True, True, True, True, True)
+    for k, P in enumerate((0, 100, 150, 200)):
+        m.add_node_load('N2', 'FZ' if weak_axis else 'FX', 1, case=f'P{k + 1}')
+        if P:
+            m.add_node_load('N2', 'FY', -P, f'P{k + 1}')
+    sign = -1.0 if weak_axis else 1.0
+    checks = []
+    for k, (M, d) in enumerate(zip((336, 469, 598, 848), (-0.901, -1.33, -1.75, -2.56))):
+        checks += [('moment', 'M1', 'My' if weak_axis else 'Mz', 0, f'Combo {k + 1}', sign*M/12, 0.03),
+                   ('deflection', 'M1', 'dz' if weak_axis else 'dy', 28, f'Combo {k + 1}', sign*d/12, 0.05)]
+    return m, 'pdelta', checks
+
+
+def aisc_case2_weak_axis(FE):
+    return aisc_case2(FE, True)
+
+
+def end_release_beam(FE):
+    """`Testing/test_end_releases.py:25-61`: fixed-fixed beam with both ends released about z: simple-span moment."""
+    m = FE()
+    m.add_material('Steel', 29000, 11200, 0.3, 0.490/12**3)
+    m.add_section('ColumnSection', 10, 100, 150, 250)
+    m.add_node('N1', 0, 0, 0)
+    m.add_node('N2', 10*12, 0, 0)
+    m.def_support('N1', True, True, True, True, True, True)
+    m.def_support('N2', True, True, True, True, True, True)
+    m.add_member('M1', 'N1', 'N2', 'Steel', 'ColumnSection')
+    m.def_releases('M1', False, False, False, False, False, True, False, False, False, False, False, True)
+    m.add_member_dist_load('M1', 'Fy', -0.5, -0.5)
+    return m, 'tc', [('min_moment', 'M1', 'Mz', None, 'Combo 1', -0.5*(10*12)**2/8, 1e-7)]
+
+
+# member-diagram known answers: (query, member, direction, station, combo, expected, rel_tol)
+DIAGRAM_KNOWN_ANSWERS = {
+    'aisc_case1': aisc_case1,
+    'aisc_case2': aisc_case2,
+    'aisc_case2_weak_axis': aisc_case2_weak_axis,
+    'end_release_beam': end_release_beam,
+}
+
+
 KNOWN_ANSWERS = {
     'logan_5_30_frame_xy': logan_5_30_frame_xy,
     'frame_member_ptload': frame_member_ptload,
