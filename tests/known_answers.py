@@ -200,13 +200,105 @@ def end_release_beam(FE):
     return m, 'tc', [('min_moment', 'M1', 'Mz', None, 'Combo 1', -0.5*(10*12)**2/8, 1e-7)]
 
 
-# member-diagram known answers: (query, member, direction, station, combo, expected, rel_tol)
+def beam_rotation(FE):
+    """`Testing/test_member_rotation.py:6-42`: simple beam rolled 45 degrees under a global load: equal and opposite
+    bending about both local axes."""
+    m = FE()
+    m.add_node('N1', 0, 0, 0)
+    m.add_node('N2', 10, 0, 0)
+    m.def_support('N1', True, True, True, True, False, False)
+    m.def_support('N2', False, True, True, False, False, False)
+    m.add_material('Steel', 29000/12**2, 11200/12**2, 0.3, 0.490, 60)
+    m.add_section('W12x26', 7.65/12**2, 17.3/12**4, 204/12**4, 0.3/12**4)
+    m.add_member('M1', 'N1', 'N2', 'Steel', 'W12x26', 45)
+    m.add_member_dist_load('M1', 'FY', -2, -2)
+    return m, 'tc', [('max_moment', 'M1', 'Mz', None, 'Combo 1', 0.0, 0, 1e-9), ('min_moment', 'M1', 'Mz', None, 'Combo 1', -17.677, 1e-2),
+                     ('max_moment', 'M1', 'My', None, 'Combo 1', 17.677, 1e-2), ('min_moment', 'M1', 'My', None, 'Combo 1', 0.0, 0, 1e-9)]
+
+
+def column_rotation(FE):
+    """`Testing/test_member_rotation.py:45-89`: pinned column rolled 90 degrees, global Z point load at mid-height:
+    Mz = -P L / 4 = -2.5 to ten decimals, My = 0."""
+    m = FE()
+    m.add_material(name='Steel', E=29000, G=11200, nu=0.3, rho=0.0002836)
+    m.add_section(name='W14x90', A=26.5, Iy=362, Iz=999, J=6.14)
+    m.add_node(name='N1', X=0, Y=0, Z=0)
+    m.add_node(name='N2', X=0, Y=10, Z=0)
+    m.add_member(name='M2', i_node='N1', j_node='N2', material_name='Steel', section_name='W14x90', rotation=90)
+    m.def_support('N1', support_DX=True, support_DY=True, support_DZ=True, support_RY=True)
+    m.def_support('N2', support_DX=True, support_DY=True, support_DZ=True)
+    m.add_load_combo('Combo 1', {'Default': 1.0})
+    m.add_member_pt_load(member_name='M2', direction='FZ', P=-1.0, x=5.0, case='Default')
+    return m, 'tc', [('moment', 'M2', 'Mz', 5.0, 'Combo 1', -2.5, 0, 5e-11), ('moment', 'M2', 'My', 5.0, 'Combo 1', 0.0, 0, 5e-11)]
+
+
+# member-diagram known answers: (query, member, direction, station, combo, expected, rel_tol[, abs_tol])
 DIAGRAM_KNOWN_ANSWERS = {
     'aisc_case1': aisc_case1,
     'aisc_case2': aisc_case2,
     'aisc_case2_weak_axis': aisc_case2_weak_axis,
     'end_release_beam': end_release_beam,
+    'beam_rotation': beam_rotation,
+    'column_rotation': column_rotation,
 }
+
+
+def spring_elements(FE):
+    """`Testing/test_springs.py:6-53`: three springs in series between two walls."""
+    m = FE()
+    for name, x in (('1', 0), ('2', 30), ('3', 10), ('4', 20)):
+        m.add_node(name, x, 0, 0)
+    m.add_spring('S1', '1', '3', 1000)
+    m.add_spring('S2', '3', '4', 2000)
+    m.add_spring('S3', '4', '2', 3000)
+    m.def_support('1', True, True, True, True, True, True)
+    m.def_support('2', True, True, True, True, True, True)
+    m.def_support('3', False, True, True, True, True, True)
+    m.def_support('4', False, True, True, True, True, True)
+    m.add_node_load('4', 'FX', 5000)
+    return m, 'tc', [('D', '3', 'DX', 10/11, 0, 5e-5), ('D', '4', 'DX', 15/11, 0, 5e-5), ('Rxn', '1', 'FX', -10000/11, 0, 0.5),
+                     ('Rxn', '2', 'FX', -45000/11, 0, 0.5)]
+
+
+def nodal_springs(FE):
+    """`Testing/test_springs.py:56-85`: one node on six support springs, loads equal to minus the stiffnesses: every
+    displacement is exactly -1."""
+    m = FE()
+    m.add_node('N1', 0, 0, 0)
+    for k, (dof, load) in enumerate(zip(('DX', 'DY', 'DZ', 'RX', 'RY', 'RZ'), ('FX', 'FY', 'FZ', 'MX', 'MY', 'MZ'))):
+        m.def_support_spring('N1', dof, 1000*(k + 1))
+        m.add_node_load('N1', load, -1000*(k + 1))
+    return m, 'tc', [('D', 'N1', dof, -1.0, 0, 1e-15) for dof in ('DX', 'DY', 'DZ', 'RX', 'RY', 'RZ')]
+
+
+def spring_reaction(FE):
+    """`Testing/test_reactions.py:6-19`: one node, a compression-only support spring given as the string '5'; the
+    reaction is exactly 5."""
+    m = FE()
+    m.add_node('N1', 0, 0, 0)
+    m.add_node_load('N1', 'FY', -5)
+    m.def_support('N1', True, False, True, True, True, True)
+    m.def_support_spring('N1', 'DY', '5', '-')
+    return m, 'tc', [('Rxn', 'N1', 'FY', 5.0, 0, 1e-15)]
+
+
+def sloped_beam(FE):
+    """`Testing/test_sloped_beam.py:25-66`: inclined member fixed at both nodes with bending releases at both ends, global
+    point loads at the third points, P-Delta driver (no free DOF at all)."""
+    m = FE()
+    m.add_node('N1', 0, 0, 0)
+    m.add_node('N2', 10, 10, 0)
+    m.def_support('N1', True, True, True, True, True, True)
+    m.def_support('N2', True, True, True, True, True, True)
+    m.add_material('Steel', 29000*144, 11200*144, 0.3, 490/1000)
+    m.add_section('Section', 12/12**2, 200/12**4, 200/12**4, 400/12**4)
+    m.add_member('M1', 'N1', 'N2', 'Steel', 'Section')
+    m.def_releases('M1', False, False, False, False, True, True, False, False, False, False, True, True)
+    L = (10**2 + 10**2)**0.5
+    m.add_member_pt_load('M1', 'FY', -5, L/3, 'D')
+    m.add_member_pt_load('M1', 'FY', -5, 2*L/3, 'D')
+    m.add_load_combo('1.4D', {'D': 1.4})
+    return m, 'pdelta', [('Rxn', 'N1', 'FY', 1.4*5, 5e-3, 0), ('Rxn', 'N2', 'FY', 1.4*5, 5e-3, 0)]
 
 
 KNOWN_ANSWERS = {
@@ -217,4 +309,12 @@ KNOWN_ANSWERS = {
     'logan_12_1_plate': logan_12_1_plate,
     'torque_beam': torque_beam,
     'aisc_cantilever_pdelta': aisc_cantilever_pdelta,
+    'spring_elements': spring_elements,
+    'nodal_springs': nodal_springs,
+    'spring_reaction': spring_reaction,
+    'sloped_beam': sloped_beam,
 }
+
+# models without a member / shell, or without a free degree of freedom: oracle only (the GPU path's handling of these
+# degenerate sizes has not been exercised on hardware)
+CPU_ONLY = ('nodal_springs', 'spring_reaction', 'sloped_beam')
