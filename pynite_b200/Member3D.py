@@ -61,6 +61,40 @@ class Member3D(SubMemberDiagrams):
         """Global end forces (12, 1) for a combo (`Member3D.py:1072-1078`)."""
         return self.model._element_force('member', self.ID, combo_name, local=False)
 
+    def _engine_id(self):
+        """Row of this member in the engine's member arrays.  A physical member is there through its sub-members: its own
+        matrices exist only when it was not split."""
+        subs = getattr(self, 'sub_members', None)
+        if subs is None:
+            return self.ID
+        if not subs:
+            from pynite_b200.analysis import renumber
+            renumber(self.model)
+        if len(self.sub_members) != 1:
+            raise ValueError(f"member '{self.name}' is split into {len(self.sub_members)} sub-members: query "
+                             "`member.sub_members[...]` instead")
+        return next(iter(self.sub_members.values())).ID
+
+    def Ke(self):
+        """Global stiffness matrix (12, 12), computed by the member kernel (`Member3D.py:1038-1046`)."""
+        from pynite_b200.analysis import element_matrix
+        return element_matrix(self.model, 'member', self._engine_id())
+
+    def ke(self):
+        """Local (condensed) stiffness matrix `T Ke T^T` (`Member3D.py:147-174`)."""
+        T = self.T()
+        return T @ self.Ke() @ T.T
+
+    def Kg(self, P=0.0):
+        """Global geometric stiffness matrix for an axial force P (`Member3D.py:1048-1058`)."""
+        from pynite_b200.analysis import element_matrix
+        return element_matrix(self.model, 'member', self._engine_id(), 'Kg', P)
+
+    def kg(self, P=0):
+        """Local geometric stiffness matrix (`Member3D.py:210-266`)."""
+        T = self.T()
+        return T @ self.Kg(P) @ T.T
+
     def m(self, mass_combo_name, mass_direction='Y', gravity=1.0):
         """Condensed local mass matrix (`Member3D.py:605-646`)."""
         from pynite_b200 import modal

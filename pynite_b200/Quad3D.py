@@ -35,6 +35,36 @@ class _Shell4:
             raise KeyError('Please define the material ' + str(material_name) +
                            ' before assigning it to plates.')
 
+    def _nodes(self):
+        return (self.i_node, self.j_node, self.m_node, self.n_node)
+
+    def T(self):
+        """24 x 24 transformation matrix (`Quad3D.T` :884-950, `Plate3D.T` :451-500)."""
+        from pynite_b200.analysis import block_T, shell_dircos_host
+        return block_T(shell_dircos_host(self), 8)
+
+    def Ke(self):
+        """Global stiffness matrix (24, 24), computed by the shell kernel (`Quad3D.Ke` :858-868, `Plate3D.Ke` :502-508)."""
+        from pynite_b200.analysis import element_matrix
+        if self.ID is None:
+            from pynite_b200.analysis import renumber
+            renumber(self.model)
+        return element_matrix(self.model, self._kind, self.ID)
+
+    def ke(self):
+        """Local stiffness matrix `T Ke T^T` (`Quad3D.ke` :107-141, `Plate3D.ke` :77-96)."""
+        T = self.T()
+        return T @ self.Ke() @ T.T
+
+    def D(self, combo_name='Combo 1'):
+        """Global nodal displacements (24, 1) (`Quad3D.D` :790-829)."""
+        from pynite_b200.analysis import element_D
+        return element_D(self.model, self._nodes(), combo_name)
+
+    def d(self, combo_name='Combo 1'):
+        """Local nodal displacements `T D` (`Quad3D.d` :779-788)."""
+        return self.T() @ self.D(combo_name)
+
     def F(self, combo_name='Combo 1'):
         """Global end force vector (24, 1) from the last GPU solve."""
         return self.model._element_force(self._kind, self.ID, combo_name, local=False)

@@ -27,6 +27,35 @@ class Spring3D:
     def L(self):
         return self.i_node.distance(self.j_node)
 
+    def T(self):
+        """12 x 12 transformation matrix (`Spring3D.py:114-188`): a member's, without a roll angle."""
+        from pynite_b200.analysis import block_T, member_dircos_host
+        return block_T(member_dircos_host(self), 4)
+
+    def Ke(self):
+        """Global stiffness matrix (12, 12), computed by the member kernel (`Spring3D.py:191-197`)."""
+        from pynite_b200.analysis import element_matrix, renumber
+        if self.ID is None:
+            renumber(self.model)
+        return element_matrix(self.model, 'spring', self.ID)
+
+    def ke(self):
+        """Local stiffness matrix `T Ke T^T` (`Spring3D.py:59-83`)."""
+        T = self.T()
+        return T @ self.Ke() @ T.T
+
+    def D(self, combo_name='Combo 1'):
+        """Global end displacements (12, 1); an inactive spring reports no global X translation (`Spring3D.py:209-243`)."""
+        from pynite_b200.analysis import element_D
+        D = element_D(self.model, (self.i_node, self.j_node), combo_name)
+        if not self.active[combo_name] == True:             # noqa: E712
+            D[0, 0] = D[6, 0] = 0.0
+        return D
+
+    def d(self, combo_name='Combo 1'):
+        """Local end displacements `T D` (`Spring3D.py:100-111`)."""
+        return self.T() @ self.D(combo_name)
+
     def f(self, combo_name='Combo 1'):
         """Local end force vector (12, 1) from the last GPU solve (`Spring3D.py:86-97`)."""
         return self.model._element_force('spring', self.ID, combo_name, local=True)

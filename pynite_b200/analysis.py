@@ -502,6 +502,38 @@ def global_load_vector(model, combo_name, which):
     return eng.load_vector(run.engine_combo[combo_name], which)
 
 
+def element_matrix(model, kind, elem_id, which='Ke', P=0.0):
+    """Global stiffness matrix `Ke()` of one element (`Member3D.Ke` :1038, `Spring3D.Ke` :191, `Quad3D.Ke` :858,
+    `Plate3D.Ke` :502) or a member's geometric stiffness `Kg(P)` (:1048).  One batched launch computes the matrices of
+    every element of the kind (`pn_element_ke` / `pn_member_kg`); they are kept with the engine state they belong to, so a
+    loop over the elements of a solved model costs one launch."""
+    name = next(iter(model.load_combos), 'Combo 1')
+    run, eng = _fresh_engine_state(model, name)
+    cache = run.__dict__.setdefault('matrix_cache', {})
+    key = (kind, which, float(P))
+    if key not in cache:
+        if which == 'Ke':
+            cache[key] = eng.element_ke(kind)
+        else:
+            cache[key] = eng.member_kg(np.full(len(run.arrays.mem_rot), float(P)))
+    return cache[key][elem_id].copy()
+
+
+def block_T(R, blocks):
+    """Transformation matrix with the 3 x 3 direction cosines `R` repeated on the diagonal (`Member3D.T` :1029-1036,
+    `Quad3D.T` :941-950)."""
+    T = np.zeros((3*blocks, 3*blocks))
+    for k in range(blocks):
+        T[3*k:3*k + 3, 3*k:3*k + 3] = R
+    return T
+
+
+def element_D(model, nodes, combo_name):
+    """Global displacements of an element's nodes as a column (`Quad3D.D` :790-829, `Plate3D.D`, `Spring3D.D`)."""
+    D = model._D[combo_name]
+    return np.concatenate([D[6*n.ID:6*n.ID + 6, 0] for n in nodes]).reshape(-1, 1)
+
+
 def element_force(model, kind, elem_id, combo_name, local):
     """End forces of one element for a solved combo (`Member3D.f/F`, `Quad3D.f/F`, `Plate3D.f/F`, `Spring3D.f/F`)."""
     run = model._run

@@ -311,11 +311,8 @@ class SubMemberDiagrams:
 
     def T(self):
         """12 x 12 transformation matrix (`Member3D.T`, `:933-1036`): the direction cosines four times on the diagonal."""
-        R = self.model._member_dircos(self)
-        T = np.zeros((12, 12))
-        for k in range(4):
-            T[3*k:3*k + 3, 3*k:3*k + 3] = R
-        return T
+        from pynite_b200.analysis import block_T
+        return block_T(self.model._member_dircos(self), 4)
 
     def D(self, combo_name='Combo 1'):
         """Global end displacements (12, 1); an inactive member reports no global X translation (`:1093-1127`)."""

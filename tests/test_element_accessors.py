@@ -1,0 +1,80 @@
+"""Per-element inspection methods of the host mirror (`Member3D/Spring3D/Quad3D/Plate3D.T/D/d/Ke/ke`, `Member3D.Kg/kg`).
+
+`-m "not gpu"`: the host-side ones (`T`, `D`, `d`) against the oracle's transformation matrices -- the oracle being pinned
+to the reference's element matrices by tests/test_oracle_golden.py -- and the fixtures' stored displacements.
+`-m gpu`: `Ke / ke / Kg / kg`, which come from one batched kernel launch per element kind, against the reference's matrices
+in the fixture files.  The GPU half was added after the round's GPU minutes were spent and has NOT run on hardware yet:
+xfail(strict=False).  Remove the mark after the first green run on a B200."""
+import numpy as np
+import pytest
+
+from oracle import elements as el
+from oracle import model as om
+from pynite_b200 import FEModel3D, analysis
+from tests import models
+from tests.util import load_fixture, rel_err
+
+CASES = ['portal_frame', 'continuous_beam', 'skew_shell', 'plate_mesh_xz', 'mixed_building', 'quad_mesh_yz_ortho']
+
+
+def _prepared(name):
+    build, _ = models.SMALL_MODELS[name]
+    A, ref, _ = load_fixture(name)
+    m = build(FEModel3D)
+    analysis.prepare_model(m)
+    for c, combo in enumerate(m.load_combos):
+        m._D[combo] = ref['D'][c].reshape(-1, 1).copy()
+    return m, A, ref
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_transformations_and_displacements(name):
+    m, A, ref = _prepared(name)
+    combo = next(iter(m.load_combos))
+    D = m._D[combo]
+    subs = [s for pm in m.members.values() for s in pm.sub_members.values()]
+    for k, sub in enumerate(subs):
+        T = om.member_Ke(A, k)[1]
+        assert rel_err(sub.T(), T) < 1e-14
+        assert rel_err(sub.d(combo), T @ D[[6*int(n) + j for n in A.mem_ij[k] for j in range(6)], :]) < 1e-13
+    for k, spring in enumerate(m.springs.values()):
+        T = om.spring_Ke(A, k)[1]
+        assert rel_err(spring.T(), T) < 1e-14
+        assert np.array_equal(spring.D(combo), D[[6*int(n) + j for n in A.spring_ij[k] for j in range(6)], :])
+    for table, ijmn, fn in ((m.quads, A.quad_ijmn, om.quad_Ke), (m.plates, A.plate_ijmn, om.plate_Ke)):
+        for k, shell in enumerate(table.values()):
+            T = fn(A, k)[1]
+            assert rel_err(shell.T(), T) < 1e-14
+            dofs = [6*int(n) + j for n in ijmn[k] for j in range(6)]
+            assert np.array_equal(shell.D(combo), D[dofs, :])
+            assert rel_err(shell.d(combo), T @ D[dofs, :]) < 1e-13
+
+
+def test_split_member_has_no_matrix_of_its_own():
+    m, _, _ = _prepared('continuous_beam')
+    pm = next(pm for pm in m.members.values() if len(pm.sub_members) > 1)
+    with pytest.raises(ValueError, match='sub-members'):
+        pm._engine_id()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason='added after the GPU budget of the round was spent: not yet run on hardware')
+@pytest.mark.parametrize('name', CASES)
+def test_element_matrices_through_the_objects(name):
+    build, mode = models.SMALL_MODELS[name]
+    _, ref, _ = load_fixture(name)
+    m = build(FEModel3D)
+    m.analyze_linear()
+    subs = [s for pm in m.members.values() for s in pm.sub_members.values()]
+    for kind, elems in (('member', subs), ('spring', list(m.springs.values())), ('quad', list(m.quads.values())),
+                        ('plate', list(m.plates.values()))):
+        for k, e in enumerate(elems):
+            assert rel_err(e.Ke(), ref[kind + '_Ke'][k]) < 1e-12, (kind, k)
+            T = e.T()
+            assert rel_err(e.ke(), T @ ref[kind + '_Ke'][k] @ T.T) < 1e-12, (kind, k)
+    if subs:
+        A, _, _ = load_fixture(name)
+        for k in (0, len(subs) - 1):
+            assert rel_err(subs[k].Kg(-37.5), om.member_Kg(A, k, -37.5)[0]) < 1e-12
+            assert rel_err(subs[k].kg(12.0), om.member_Kg(A, k, 12.0)[2]) < 1e-11
+    assert m.solution == 'Linear' and next(iter(m.load_combos)) in m._D        # inspection leaves the results alone
