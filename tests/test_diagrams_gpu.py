@@ -2,8 +2,8 @@
 
 The diagram arithmetic itself is pinned on the CPU (tests/test_diagrams_cpu.py feeds it the reference's displacements and end
 forces); this file closes the loop `analyze*() on the GPU -> member.f() / model._D -> diagrams`.  It was written after the
-round's GPU minutes were spent and has NOT run on hardware yet, hence xfail(strict=False): a pass shows as XPASS, a failure
-does not stop the suite (it sorts last for the same reason).  Remove the mark after the first green run on a B200."""
+round's GPU minutes were spent and has NOT run on hardware yet, hence `unverified_gpu` (tests/conftest.py:
+non-strict xfail, scheduled after every verified test)."""
 import os
 
 import numpy as np
@@ -12,8 +12,7 @@ import pytest
 from tests import models
 from tests.util import diagram_record
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='added after the GPU budget of the round was spent: not yet run on hardware')]
+pytestmark = [pytest.mark.gpu, pytest.mark.unverified_gpu]
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'member_diagrams.npz'))
 

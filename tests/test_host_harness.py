@@ -242,3 +242,34 @@ def test_direct_symbolic_dof_classes(libs, name, leaf, expect):
         out.append(stats.copy())
     # fewer factor entries and flops than the node-based ordering of the same matrix
     assert out[0][0] < out[1][0] and out[0][1] < out[1][1]
+
+
+@pytest.mark.parametrize('name', ['torque_beam', 'spring_elements', 'logan_12_1_plate', 'nodal_springs'])
+def test_direct_symbolic_host_on_tiny_systems(libs, name):
+    """The known-answer models of the reference's tests (tests/known_answers.py) have as few as ONE free degree of freedom:
+    the ordering / front tables must cope with a vertex graph of one vertex and no edge, and with every leaf size."""
+    from pynite_b200 import FEModel3D, analysis
+    from pynite_b200.flatten import flatten_model
+    from tests.known_answers import DIAGRAM_KNOWN_ANSWERS, KNOWN_ANSWERS
+    _, dh = libs
+    m, _, _ = {**KNOWN_ANSWERS, **DIAGRAM_KNOWN_ANSWERS}[name](FEModel3D)
+    analysis.prepare_model(m)
+    combos = analysis.identify_combos(m)
+    A = flatten_model(m, combos, combos[0].name)
+    d1, d2, _ = om.partition_D(A)
+    K11 = sps.csr_matrix(om.ke_csr(A)[d1, :][:, d1])
+    K11.sort_indices()
+    assert 1 <= len(d1) <= 6
+    vstart, coords, adj_ptr, adj = _vertex_graph(K11, A, d1)
+    B = np.ascontiguousarray(np.random.default_rng(1).standard_normal((len(d1), 2)))
+    Xs = spla.splu(K11.tocsc()).solve(B)
+    for leaf in (1, 2, 8):
+        X = np.empty_like(B)
+        stats = np.zeros(8)
+        rc = dh.hh_direct_solve(ct.c_int64(len(d1)), K11.indptr.astype(np.int32).ctypes.data_as(I32P),
+                                K11.indices.astype(np.int32).ctypes.data_as(I32P), _p(np.ascontiguousarray(K11.data)),
+                                ct.c_int32(len(vstart) - 1), vstart.ctypes.data_as(I32P), _p(coords),
+                                adj_ptr.ctypes.data_as(I64P), adj.ctypes.data_as(I32P), leaf, 2, _p(B), _p(X), _p(stats),
+                                None, 1, None)
+        assert rc == 0
+        assert rel_err(X, Xs) < 1e-9, (name, leaf)
