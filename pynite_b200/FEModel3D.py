@@ -40,6 +40,7 @@ class FEModel3D:
         self.plates = {}
         self.meshes = {}
         self.mats = {}
+        self.shear_walls = {}
         self.load_combos = {}
         self._D = {}        # {combo: (6N, 1) displacement vector}
         self._Rxn = {}      # {combo: (6N, 1) reaction vector}; read through node.RxnFX[...] etc.
@@ -225,6 +226,19 @@ class FEModel3D:
                                          start_node, start_element, num_elements, element_type)
         self.solution = None
         return name
+
+    def add_shear_wall(self, name, mesh_size, length, height, thickness, material_name, ky_mod=0.35, plane='XY',
+                       origin=[0, 0, 0]):
+        """`FEModel3D.add_shear_wall` (:890-933).  Returns nothing, like the reference's."""
+        from pynite_b200.ShearWall import ShearWall
+        if name:
+            if name in self.shear_walls:
+                raise NameError(f"Shear wall name '{name}' already exists")
+        else:
+            name = self.unique_name(self.shear_walls, 'SW')
+        self.shear_walls[name] = ShearWall(self, name, mesh_size, length, height, thickness, material_name, ky_mod, origin,
+                                           plane)
+        self.solution = None
 
     def add_mat_foundation(self, name, mesh_size, length_X, length_Z, thickness, material_name, ks, origin=[0, 0, 0],
                            x_control=[], y_control=[]):

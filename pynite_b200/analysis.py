@@ -64,8 +64,7 @@ def renumber(model):
 
 def prepare_model(model, n_modes=0):
     """`Analysis._prepare_model` (:20-79): meshes and mat foundations are generated here when they have not been; the
-    combinations tagged 'modal' are dropped and `n_modes` fresh ones ('Mode 1', ...) added (:44-51).  Shear walls: out of
-    scope."""
+    combinations tagged 'modal' are dropped and `n_modes` fresh ones ('Mode 1', ...) added (:44-51)."""
     model._D = {}
     model._Rxn = {}
     if model.load_combos == {}:
@@ -74,9 +73,11 @@ def prepare_model(model, n_modes=0):
         model.load_combos.pop(name)
     for i in range(n_modes):
         model.add_load_combo(f'Mode {i + 1}', {}, ['modal'])
-    for mesh in list(getattr(model, 'meshes', {}).values()) + list(getattr(model, 'mats', {}).values()):
-        if not mesh.is_generated or mesh.needs_update:
-            mesh.generate()
+    # (:53-66) meshes, then shear walls -- which create and generate meshes of their own --, then mat foundations
+    for table in ('meshes', 'shear_walls', 'mats'):
+        for mesh in list(getattr(model, table, {}).values()):
+            if not mesh.is_generated or mesh.needs_update:
+                mesh.generate()
     combos = list(model.load_combos.keys())
     for spring in model.springs.values():
         for name in combos:

@@ -627,6 +627,58 @@ def mesh_edited_case(FE):
     return m
 
 
+def shear_wall_case(FE):
+    """the two walls of the reference's `Testing/test_shear_wall.py:6-60` (openings, three flanges each, a support line, a
+    story with a shear), one in the XY plane and one in YZ, on a 2 ft mesh; plus a second material region, an axial load and
+    a partial-length story on the first wall"""
+    m = FE()
+    Em = 900*2000/1000*144
+    m.add_material('CMU', Em, 0.4*Em, 0.17, 0.140)
+    m.add_material('Grouted', 1.3*Em, 0.52*Em, 0.2, 0.150)
+    for wall_name, plane, origin in (('W1', 'XY', [0, 0, 0]), ('W2', 'YZ', [40, 0, 0])):
+        m.add_shear_wall(wall_name, mesh_size=2, length=26, height=16, thickness=0.667, material_name='CMU', ky_mod=1,
+                         plane=plane, origin=origin)
+        w = m.shear_walls[wall_name]
+        w.add_opening('Door 1', x_start=2, y_start=0, width=4, height=12, tie=None)
+        w.add_opening('Window 1', x_start=8, y_start=8, width=4, height=4, tie=None)
+        w.add_opening('Window 2', x_start=14, y_start=8, width=4, height=4, tie=None)
+        w.add_opening('Door 2', x_start=20, y_start=0, width=4, height=12, tie=None)
+        w.add_support(elevation=0, x_start=0, x_end=26)
+        w.add_story('Roof', elevation=16, x_start=0, x_end=26)
+        w.add_shear(story_name='Roof', force=100, case='E')
+        w.add_flange(thickness=0.667, width=0.75*16, x=0, y_start=0, y_end=16, material='CMU', side='-z')
+        w.add_flange(thickness=0.667, width=0.75*16, x=7, y_start=0, y_end=16, material='CMU', side='+z')
+        w.add_flange(thickness=0.667, width=0.75*16, x=26, y_start=0, y_end=16, material='CMU', side='-z')
+    w1 = m.shear_walls['W1']
+    w1.asign_material('Grouted', 1.0, x_start=6, x_end=20, y_start=0, y_end=8)
+    w1.add_story('Mezzanine', elevation=8, x_start=6, x_end=20)
+    w1.add_axial('Roof', 30.0, case='D')
+    m.add_load_combo('1.0E', {'E': 1.0}, combo_tags='strength')
+    for wall in m.shear_walls.values():
+        wall.generate()
+    return m
+
+
+def shear_wall_regenerated(FE):
+    """`Testing/test_shear_wall.py:364-440`: a plain wall, generated, then two openings added and generated again"""
+    m = FE()
+    Em = 900*2000/1000*144
+    m.add_material('CMU', Em, 0.4*Em, 0.17, 0.140)
+    m.add_shear_wall('Wall', mesh_size=2, length=24, height=16, thickness=0.667, material_name='CMU', ky_mod=1, plane='XY',
+                     origin=[0, 0, 0])
+    w = m.shear_walls['Wall']
+    w.add_support(elevation=0, x_start=0, x_end=24)
+    w.add_story('Roof', elevation=16, x_start=0, x_end=24)
+    w.add_shear(story_name='Roof', force=100, case='E')
+    w.generate()
+    m.add_load_combo('1.0E', {'E': 1.0}, combo_tags='strength')
+    w.add_opening('Door', x_start=6, y_start=0, width=6, height=12, tie=None)
+    w.add_opening('Window', x_start=16, y_start=8, width=6, height=4, tie=None)
+    assert w.needs_update
+    w.generate()
+    return m
+
+
 RECT_MESH_CASES = {
     'basic': rect_mesh_basic,
     'uneven_yz_rect': rect_mesh_uneven_yz_rect,
@@ -639,6 +691,8 @@ RECT_MESH_CASES = {
     'frustrum': frustrum_mesh_case,
     'cylinder': cylinder_mesh_case,
     'edited': mesh_edited_case,
+    'shear_wall': shear_wall_case,
+    'shear_wall_regenerated': shear_wall_regenerated,
 }
 
 

@@ -83,11 +83,12 @@ def mesh_record(model):
         rec[kind + '_keys'] = np.array(list(table.keys()), dtype=str)
         rec[kind + '_conn'] = np.array([[e.i_node.name, e.j_node.name, e.m_node.name, e.n_node.name] for e in elems],
                                        dtype=str).reshape(-1, 4)
-        rec[kind + '_props'] = np.array([[e.t, e.kx_mod, e.ky_mod] for e in elems], dtype=float).reshape(-1, 3)
+        rec[kind + '_props'] = np.array([[e.t, e.kx_mod, e.ky_mod, e.E, e.nu] for e in elems], dtype=float).reshape(-1, 5)
     for kind, table in (('member', model.members), ('spring', model.springs)):
         rec[kind + '_keys'] = np.array(list(table.keys()), dtype=str)
         rec[kind + '_names'] = np.array([e.name for e in table.values()], dtype=str)
         rec[kind + '_ij'] = np.array([[e.i_node.name, e.j_node.name] for e in table.values()], dtype=str).reshape(-1, 2)
+    rec['combos'] = np.array([f'{c.name}|{c.combo_tags}|{sorted(c.factors.items())}' for c in model.load_combos.values()], dtype=str)
     rec['section_reprs'] = np.array([repr(sec) for sec in model.sections.values()], dtype=str)
     springs, loads = [], []
     for n in nodes:
@@ -106,6 +107,13 @@ def mesh_record(model):
         rec['mesh_' + mname + '_nodes'] = np.array(list(mesh.nodes.keys()), dtype=str)
         rec['mesh_' + mname + '_elements'] = np.array(list(mesh.elements.keys()), dtype=str)
         rec['mesh_' + mname + '_last'] = np.array([getattr(mesh.last_node, 'name', 'None'), getattr(mesh.last_element, 'name', 'None')])
+    for wname, wall in getattr(model, 'shear_walls', {}).items():
+        for label, table, ext in (('piers', wall.piers, 'width'), ('beams', wall.coupling_beams, 'length')):
+            regions = list(table.values())
+            rec[f'wall_{wname}_{label}_names'] = np.array([r.name for r in regions] + list(table.keys()), dtype=str)
+            rec[f'wall_{wname}_{label}_box'] = np.array([[r.x, r.y, getattr(r, ext), r.height] for r in regions],
+                                                        dtype=float).reshape(-1, 4)
+            rec[f'wall_{wname}_{label}_quads'] = np.array([','.join(q.name for q in r.plates) for r in regions], dtype=str)
     return rec
 
 
@@ -155,3 +163,19 @@ def diagram_record(model):
                 extremes[c, k, q, 1] = _call(member, 'min_' + what, direction, combo)
     return {'arrays': arrays, 'points': points, 'extremes': extremes, 'active': active,
             'member_names': np.array([m.name for m in members], dtype=str)}
+
+
+# ---------------------------------------------------------------------------------------------
+# shear wall results (tests/golden/shear_walls.npz)
+# ---------------------------------------------------------------------------------------------
+SHEAR_WALL_COMBOS = ['1.0E', 'Stiffness: Roof']
+
+
+def shear_wall_record(model):
+    """`sum_forces` of every pier and coupling beam of every wall for SHEAR_WALL_COMBOS, and the walls' roof stiffness."""
+    rec = {}
+    for wname, wall in model.shear_walls.items():
+        for label, table in (('piers', wall.piers), ('beams', wall.coupling_beams)):
+            rec[f'{wname}_{label}'] = np.array([[r.sum_forces(c) for r in table.values()] for c in SHEAR_WALL_COMBOS], dtype=float)
+        rec[f'{wname}_stiffness'] = np.array(wall.stiffness('Roof'))
+    return rec
