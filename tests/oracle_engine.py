@@ -1,0 +1,145 @@
+"""An `engine.Engine` look-alike backed by the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+The drivers of `pynite_b200/analysis.py` and `modal.py` talk to the GPU through `engine.Engine`.  The container the tests
+run in has no GPU, so the Python glue between the reference-facing API and the engine (upload, result storing, diagrams after
+an analysis, the modal operator, the shear-wall results, the per-object matrices) would only ever run on the B200 box.
+`OracleEngine` implements the slice of the Engine interface those drivers use for models WITHOUT tension/compression-only
+features, with `oracle.model` doing the arithmetic, so that the glue can be driven end to end on the CPU
+(tests/test_drivers_cpu.py).  Nothing in the product package imports this module, and the parity of the CUDA kernels is
+established by the `-m gpu` tests, not here."""
+import copy
+
+import numpy as np
+
+from oracle import model as om
+from pynite_b200 import engine as real
+
+
+class _Stats:
+    def as_dict(self):
+        return {}
+
+
+class OracleEngine:
+
+    def __init__(self, device=0):
+        self.device = device
+        self.A = None
+        self.D = None
+        self.pdelta = False
+
+    # ---- upload ----------------------------------------------------------------------------------------------
+    def set_model(self, A):
+        self.A = copy.copy(A)
+        self.n_dof = 6*A.n_nodes
+        self.counts = {'spring': len(A.spring_ks), 'member': len(A.mem_rot), 'quad': len(A.quad_ijmn),
+                       'plate': len(A.plate_ijmn)}
+
+    def set_loads(self, L):
+        for name in ('cases', 'nl_dof', 'nl_case', 'nl_val', 'ml_member', 'ml_case', 'ml_kind', 'ml_params', 'qp_elem', 'qp_case',
+                     'qp_val', 'pp_elem', 'pp_case', 'pp_val'):
+            setattr(self.A, name, copy.copy(getattr(L, name)))
+
+    def set_combos(self, factors):
+        n_case = max(len(self.A.cases), 1)
+        self.A.factors = np.asarray(factors, dtype=float).reshape(-1, n_case) if len(self.A.cases) else np.zeros((len(factors), 0))
+        self.n_combo = self.A.factors.shape[0]
+
+    def set_output_combos(self, combo0, n_combo):
+        pass
+
+    def reset_stats(self):
+        pass
+
+    def stats(self):
+        return _Stats()
+
+    # ---- assembly / solve ------------------------------------------------------------------------------------
+    def symbolic(self, flags=0):
+        return None
+
+    def assemble_ke(self):
+        pass
+
+    def check_nodal_stability(self, cap=4096):
+        pass
+
+    def partition(self):
+        return om.partition_D(self.A)
+
+    def _solve(self, fn, reactions):
+        try:
+            D, R = fn(self.A, with_reactions=reactions)
+        except Exception as err:                              # noqa: BLE001
+            raise real.SingularMatrix(str(err))
+        self.D = np.array([np.asarray(d).reshape(-1) for d in D]).reshape(len(D), self.n_dof)
+        Rm = np.array([np.asarray(r).reshape(-1) for r in R]).reshape(len(R), self.n_dof) if reactions else None
+        return self.D.copy(), Rm, _Stats()
+
+    def solve_linear(self, opts=None, reactions=True, D_out=None, R_out=None, download=True):
+        self.pdelta = False
+        return self._solve(om.solve_linear, reactions)
+
+    def solve_pdelta(self, opts=None, reactions=True, D_out=None, R_out=None, download=True):
+        self.pdelta = True
+        return self._solve(om.solve_pdelta, reactions)
+
+    def set_displacements(self, combo, D):
+        self.D[combo] = np.asarray(D, dtype=float).reshape(-1)
+
+    def reactions(self, combo, pdelta=False, out=None):
+        return om.reactions(self.A, combo, self.D[combo].reshape(-1, 1), pdelta=pdelta)
+
+    # ---- element level ---------------------------------------------------------------------------------------
+    def element_ke(self, kind):
+        fn = {'spring': om.spring_Ke, 'member': om.member_Ke, 'quad': om.quad_Ke, 'plate': om.plate_Ke}[kind]
+        nd = 12 if kind in ('spring', 'member') else 24
+        return np.array([fn(self.A, k)[0] for k in range(self.counts[kind])]).reshape(self.counts[kind], nd, nd)
+
+    def member_kg(self, P):
+        return np.array([om.member_Kg(self.A, k, float(P[k]))[0] for k in range(self.counts['member'])]).reshape(-1, 12, 12)
+
+    def element_forces(self, kind, combo, local=False, pdelta=False):
+        A, D = self.A, self.D[combo].reshape(-1, 1)
+        factors = om.combo_factors(A, combo)
+        conn = {'spring': A.spring_ij, 'member': A.mem_ij, 'quad': A.quad_ijmn, 'plate': A.plate_ijmn}[kind]
+        out = []
+        for k in range(self.counts[kind]):
+            dofs = [6*int(n) + j for n in conn[k] for j in range(6)]
+            if kind == 'spring':
+                _, T, ke = om.spring_Ke(A, k)
+                f = ke @ (T @ D[dofs, :])
+            elif kind == 'member':
+                _, T, ke = om.member_Ke(A, k)
+                d = T @ D[dofs, :]
+                if pdelta:
+                    L = om.member_geometry(A, k)[0]
+                    E, G, Ar, Iy, Iz, J = A.mem_props[k]
+                    ke = ke + om.member_Kg(A, k, (d[6, 0] - d[0, 0])*Ar*E/L)[2]
+                f = ke @ d + om.member_fer_local(A, k, factors)
+            elif kind == 'quad':
+                _, T, ke = om.quad_Ke(A, k)
+                f = ke @ (T @ D[dofs, :]) + om.quad_fer_local(A, k, factors)
+            else:
+                _, T, ke = om.plate_Ke(A, k)
+                f = ke @ (T @ D[dofs, :]) + om.plate_fer_local(A, k, factors)
+            out.append((f if local else np.linalg.inv(T) @ f).reshape(-1))
+        nd = 12 if kind in ('spring', 'member') else 24
+        return np.array(out).reshape(self.counts[kind], nd)
+
+    def shell_stresses(self, kind, combo0, n_combo, pts, local=True):
+        pts = np.asarray(pts, dtype=float).reshape(-1, 2)
+        return np.array([om.shell_stresses(self.A, self.D[c], kind, [tuple(p) for p in pts], local)
+                         for c in range(combo0, combo0 + n_combo)]).reshape(n_combo, self.counts[kind], len(pts), 9)
+
+
+def install(monkeypatch):
+    """Makes `analysis._engine(model)` hand out an OracleEngine (one per model) for the duration of a test."""
+    from pynite_b200 import analysis
+
+    def engine_of(model):
+        if not isinstance(getattr(model, '_engine', None), OracleEngine):
+            model._engine = OracleEngine()
+        return model._engine
+    monkeypatch.setattr(analysis, '_engine', engine_of)
+    monkeypatch.setattr(real, 'Engine', type('Engine', (OracleEngine,), {'make_opts': staticmethod(real.Engine.make_opts)}))
