@@ -7,8 +7,9 @@ everything between "objects are numbered" and "results are stored" -- element st
 assembly, partition, right-hand sides, the solve for every load combination, reactions -- is done by
 the sm_100a library behind `pynite_b200.engine` (C ABI in `include/pynite_b200.h`).
 
-There is no CPU solver in this package: `sparse=False` raises NotImplementedError and a missing
-CUDA library raises at the first analysis call.
+There is no CPU solver in this package: a missing CUDA library raises at the first analysis call, and
+`sparse=False` (the reference's dense NumPy path) runs the same device path -- only `Ke / Kg / M` then return
+dense arrays, as in the reference.
 """
 from __future__ import annotations
 
@@ -96,6 +97,9 @@ class FEModel3D:
             cases.extend(load[5] for load in member.DistLoads)
         for shell in list(self.plates.values()) + list(self.quads.values()):
             cases.extend(load[1] for load in shell.pressures)
+        for wall in self.shear_walls.values():
+            cases.extend(load[2] for load in wall._shears)
+            cases.extend(load[2] for load in wall._axials)
         for mat in self.mats.values():
             cases.extend(load[3] for load in mat.pt_loads)
         return sorted(dict.fromkeys(cases))

@@ -156,9 +156,11 @@ def _store(model, combo_list, D, R):
             model._Rxn[combo.name] = R[i].reshape(-1, 1)
 
 
-def _require_sparse(sparse):
-    if sparse is not True and sparse != True:   # noqa: E712
-        raise NotImplementedError('pynite_b200 runs the sparse path on the GPU only; sparse=False is not available')
+def _wants_dense(sparse):
+    """True when the caller asked for the reference's dense storage (`sparse=False`).  The drivers run the same device
+    path either way -- the flag picks a host storage format and solver in the reference, not a different result, and there
+    is no CPU solver here -- and the inspection calls (`Ke`, `Kg`, `M`) return dense arrays instead of COO matrices."""
+    return not (sparse is True or sparse == True)   # noqa: E712
 
 
 # ---------------------------------------------------------------------------------------------
@@ -166,7 +168,7 @@ def _require_sparse(sparse):
 # ---------------------------------------------------------------------------------------------
 def run_linear(model, log, check_stability, check_statics, sparse, combo_tags):
     """`FEModel3D.analyze_linear` (:2250-2332): one stiffness matrix, every combo as one multi-RHS solve."""
-    _require_sparse(sparse)
+    _wants_dense(sparse)
     if log:
         print('+-------------------+')
         print('| Analyzing: Linear |')
@@ -366,7 +368,7 @@ def _per_combo_loop(model, combo_list, log, check_stability, max_iter, spring_to
 def run_first_order(model, log, check_stability, check_statics, max_iter, sparse, combo_tags,
                     spring_tolerance, member_tolerance, num_steps):
     """`FEModel3D.analyze` (:2334-2411)."""
-    _require_sparse(sparse)
+    _wants_dense(sparse)
     if log:
         print('+-----------+')
         print('| Analyzing |')
@@ -402,7 +404,7 @@ def run_first_order(model, log, check_stability, check_statics, max_iter, sparse
 
 def run_pdelta(model, log, check_stability, max_iter, sparse, combo_tags):
     """`FEModel3D.analyze_PDelta` (:2413-2467) -> `Analysis._PDelta` (:329-471)."""
-    _require_sparse(sparse)
+    _wants_dense(sparse)
     if log:
         print('+--------------------+')
         print('| Analyzing: P-Delta |')
@@ -473,7 +475,7 @@ def _fresh_engine_state(model, combo_name):
 
 
 def global_Ke(model, combo_name, log, check_stability, sparse):
-    _require_sparse(sparse)
+    dense = _wants_dense(sparse)
     run, eng = _fresh_engine_state(model, combo_name)
     s = eng.symbolic(0)
     row, col, data = eng.coo()
@@ -483,11 +485,12 @@ def global_Ke(model, combo_name, log, check_stability, sparse):
             eng.check_nodal_stability()
         except _eng.UnstableNodes as err:
             _report_unstable(model, err)
-    return sps.coo_matrix((data, (row, col)), shape=(s.n_dof, s.n_dof))
+    K = sps.coo_matrix((data, (row, col)), shape=(s.n_dof, s.n_dof))
+    return K.toarray() if dense else K
 
 
 def global_Kg(model, combo_name, log, sparse, first_step):
-    _require_sparse(sparse)
+    dense = _wants_dense(sparse)
     run = model._run
     eng = _engine(model)
     if first_step or run is None or combo_name not in run.engine_combo:
@@ -495,7 +498,8 @@ def global_Kg(model, combo_name, log, sparse, first_step):
         first_step = True if (model.solution is None or eng is not model._engine) else first_step
     row, col, data = eng.kg_coo(run.engine_combo[combo_name], first_step)
     n = run.arrays.n_dof
-    return sps.coo_matrix((data, (row, col)), shape=(n, n))
+    K = sps.coo_matrix((data, (row, col)), shape=(n, n))
+    return K.toarray() if dense else K
 
 
 def global_load_vector(model, combo_name, which):

@@ -142,8 +142,6 @@ def global_M(model, mass_combo_name=None, mass_direction='Y', gravity=1.0, log=F
     """`FEModel3D.M` (`FEModel3D.py:2004-2134`): member blocks (active physical members, sub-member by sub-member), then
     the translational nodal masses, exact zeros dropped from every block (`_append_sparse_block`, `:99-151`), and a mass of
     1e-6 x the smallest positive diagonal entry on every DOF whose diagonal is zero."""
-    if sparse is not True and sparse != True:   # noqa: E712
-        raise NotImplementedError('pynite_b200 builds the sparse mass matrix only; sparse=False is not available')
     if mass_combo_name not in model.load_combos:
         raise ValueError(f'Load combination {mass_combo_name} not found in the model.')
     combo = model.load_combos[mass_combo_name]
@@ -177,7 +175,8 @@ def global_M(model, mass_combo_name=None, mass_direction='Y', gravity=1.0, log=F
     positive = diag[diag > 0]
     if positive.size == 0:
         raise Exception('Unable to perform modal analysis. Model is massless.')
-    return M + sps.diags(positive.min()*1e-6*(diag == 0).astype(float), 0, shape=M.shape)
+    M = M + sps.diags(positive.min()*1e-6*(diag == 0).astype(float), 0, shape=M.shape)
+    return M if (sparse is True or sparse == True) else M.toarray()   # noqa: E712
 
 
 # ---------------------------------------------------------------------------------------------

@@ -56,7 +56,15 @@ class OracleEngine:
 
     # ---- assembly / solve ------------------------------------------------------------------------------------
     def symbolic(self, flags=0):
-        return None
+        return self.sizes()
+
+    def sizes(self):
+        from types import SimpleNamespace
+        d1, d2, _ = om.partition_D(self.A)
+        return SimpleNamespace(n_dof=self.n_dof, n1=len(d1), n2=len(d2))
+
+    def coo(self):
+        return om.assemble_coo(self.A)
 
     def assemble_ke(self):
         pass
@@ -86,6 +94,10 @@ class OracleEngine:
 
     def set_displacements(self, combo, D):
         self.D[combo] = np.asarray(D, dtype=float).reshape(-1)
+
+    def load_vector(self, combo, which):
+        P, FER = om.load_vectors(self.A, combo)
+        return np.asarray(FER if which in (1, 'FER', 'fer') else P).reshape(-1, 1)
 
     def reactions(self, combo, pdelta=False, out=None):
         return om.reactions(self.A, combo, self.D[combo].reshape(-1, 1), pdelta=pdelta)

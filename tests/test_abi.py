@@ -43,8 +43,8 @@ def test_no_cpu_fallback_without_device():
     m = models.space_frame(FEModel3D)
     with pytest.raises(engine.EngineUnavailable):
         m.analyze()
-    with pytest.raises(NotImplementedError):
-        m.analyze_linear(sparse=False)
+    with pytest.raises(engine.EngineUnavailable):
+        m.analyze_linear(sparse=False)         # the dense flag does not select a CPU solver either
 
 
 def test_product_package_never_imports_oracle():

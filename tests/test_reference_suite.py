@@ -1,0 +1,42 @@
+"""The reference's OWN test files, run unmodified against this package: `import Pynite` resolves to `pynite_b200`
+(tests/pynite_alias.py).  Development container only -- /root/reference does not travel to the GPU box, so this is a
+`-m "not gpu"` test that skips itself where the reference is absent, and the engine behind the drivers is the oracle-backed
+stand-in (tests/oracle_engine.py).  What it shows is the drop-in claim at the API level: builders, naming, regeneration
+flags, mesh / wall / mat generators, member diagrams, modal driver, result queries and error behaviour are what the
+reference's tests expect.  The CUDA arithmetic behind the same calls is what the `-m gpu` tests check.
+
+Not run (each needs something the stand-in does not emulate, not something the package lacks):
+  test_TC_analysis, test_spring_support, test_reactions, one case of test_analysis_regeneration -- the tension /
+      compression-only iteration lives on the device (`pn_tc_update`; GPU tests `braced_tc`, `mat_tc`, `mat_mesh_tc`);
+  test_instability, test_unstable_structure -- nodal-stability and singularity detection are device checks
+      (`pn_check_nodal_stability`, the residual test; GPU tests `test_unstable_*`, `test_singular_*`);
+  test_pushover, test_Visualization, test_vtkwriter, test_reporting, test_meshes (imports IPython) -- out of scope."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+TESTING = '/root/reference/Testing'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FILES = ['test_2D_frames', 'test_AISC_PDelta_benchmarks', 'test_continuous_beam', 'test_end_releases', 'test_member_rotation',
+         'test_sloped_beam', 'test_support_settlement', 'test_torsion', 'test_loads', 'test_delete_mesh', 'test_node_merge',
+         'test_needs_update_flag', 'test_mesh_regen_simple', 'test_mesh_regeneration', 'test_reanalysis',
+         'test_material_section_coverage', 'test_node_spring_coverage', 'test_member_internal_results', 'test_modal_analysis',
+         'test_shear_wall', 'test_springs', 'test_plates&quads', 'test_analysis_regeneration']
+DESELECT = ['test_analysis_regenerates_mat_foundation_needing_update']       # (compression-only soil springs: see above)
+
+
+@pytest.mark.skipif(not os.path.isdir(TESTING), reason='the reference is not present (GPU box)')
+def test_reference_test_files_pass_against_this_package():
+    cmd = [sys.executable, '-m', 'pytest', '-p', 'tests.pynite_alias', '-p', 'no:cacheprovider', '-q', '-x']
+    cmd += ['-k', ' and '.join('not ' + name for name in DESELECT)]
+    cmd += [os.path.join(TESTING, f + '.py') for f in FILES]
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    run = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    tail = '\n'.join(run.stdout.splitlines()[-25:])
+    assert run.returncode == 0, tail
+    assert ' passed' in tail and 'failed' not in tail, tail
+    passed = int(tail.split(' passed')[0].split()[-1])
+    assert passed >= 110, tail
