@@ -306,7 +306,58 @@ def _combo_names(member, combo_tags):
             if combo.combo_tags is not None and any(tag in combo.combo_tags for tag in combo_tags)]
 
 
-class SubMemberDiagrams:
+def plot_diagram(member, array_method, direction, label, combo_name, n_points, figsize):
+    """The reference's `plot_*` methods (`Member3D.py:1354-1412` and siblings): one combination as a line, a list of
+    combination tags as the max / min envelope of the matching combinations.  matplotlib is imported here, on use."""
+    from matplotlib import pyplot as plt
+    names = _combo_names(member, combo_name)
+    args = () if direction is None else (direction,)
+    fig, ax = plt.subplots(figsize=figsize)
+    ax.axhline(0, color='black', lw=1)
+    ax.grid()
+    if len(names) == 1:
+        x, y = getattr(member, array_method)(*args, n_points, names[0])
+        ax.plot(x, y)
+        ax.set_title('Member ' + member.name + '\n' + names[0])
+    else:
+        high = low = None
+        for name in names:
+            x, y = getattr(member, array_method)(*args, n_points, name)
+            high = y if high is None else np.maximum(high, y)
+            low = y if low is None else np.minimum(low, y)
+        ax.plot(x, high, color='green', lw=2, label='Max Envelope')
+        ax.plot(x, low, color='red', lw=2, label='Min Envelope')
+        ax.legend(fontsize='small')
+        ax.set_title('Member ' + member.name + '\nEnvelope')
+    ax.set_ylabel(label)
+    ax.set_xlabel('Location')
+    plt.show()
+
+
+class _Plots:
+    """`plot_shear / plot_moment / plot_torque / plot_axial / plot_deflection / plot_rel_deflection`, shared by the
+    sub-member and the physical member (each plots its own `*_array`)."""
+
+    def plot_shear(self, Direction, combo_name='Combo 1', n_points=20, figsize=(7, 3)):
+        plot_diagram(self, 'shear_array', Direction, 'Shear', combo_name, n_points, figsize)
+
+    def plot_moment(self, Direction, combo_name='Combo 1', n_points=20, figsize=(7, 3)):
+        plot_diagram(self, 'moment_array', Direction, 'Moment', combo_name, n_points, figsize)
+
+    def plot_torque(self, combo_name='Combo 1', n_points=20, figsize=(7, 3)):
+        plot_diagram(self, 'torque_array', None, 'Torsional Moment (Warping Torsion Not Included)', combo_name, n_points, figsize)
+
+    def plot_axial(self, combo_name='Combo 1', n_points=20, figsize=(7, 3)):
+        plot_diagram(self, 'axial_array', None, 'Axial Force', combo_name, n_points, figsize)
+
+    def plot_deflection(self, Direction, combo_name='Combo 1', n_points=20, figsize=(7, 3)):
+        plot_diagram(self, 'deflection_array', Direction, 'Deflection', combo_name, n_points, figsize)
+
+    def plot_rel_deflection(self, Direction, combo_name='Combo 1', n_points=20, figsize=(7, 3)):
+        plot_diagram(self, 'rel_deflection_array', Direction, 'Relative Deflection', combo_name, n_points, figsize)
+
+
+class SubMemberDiagrams(_Plots):
     """Result queries of an analysis sub-member (`Member3D.py:1093-2834`)."""
 
     def T(self):
@@ -487,7 +538,7 @@ class SubMemberDiagrams:
         return np.array([xs, np.array([self.rel_deflection(Direction, x, combo_name) for x in xs])])
 
 
-class PhysMemberDiagrams:
+class PhysMemberDiagrams(_Plots):
     """The same queries on a physical member: each is answered by the sub-member the station lies on, extremes run over
     all sub-members, arrays are stitched in member coordinates (`PhysMember.py:202-1404`)."""
 

@@ -84,3 +84,41 @@ def test_tag_lists_and_errors():
     arr = sub.moment_array('Mz', 0, names[0], x_array=xs)
     assert np.allclose(arr[1], [sub.moment('Mz', x, names[0]) for x in xs], rtol=1e-12, atol=0)
     assert sub.T().shape == (12, 12) and np.allclose(sub.T() @ sub.T().T, np.eye(12))
+
+
+def test_plot_methods_draw_the_arrays(monkeypatch):
+    """`plot_*` with a recording stand-in for matplotlib (absent from this image): one line for a single combination, the
+    max / min envelope for a list of tags."""
+    import sys
+    import types
+    calls = []
+
+    class Axes:
+        def __getattr__(self, name):
+            return lambda *a, **k: calls.append((name, a, k))
+
+    pyplot = types.ModuleType('matplotlib.pyplot')
+    pyplot.subplots = lambda **k: (object(), Axes())
+    pyplot.show = lambda: calls.append(('show', (), {}))
+    pkg = types.ModuleType('matplotlib')
+    pkg.pyplot = pyplot
+    monkeypatch.setitem(sys.modules, 'matplotlib', pkg)
+    monkeypatch.setitem(sys.modules, 'matplotlib.pyplot', pyplot)
+    m = solved_like_the_reference('portal_frame')
+    names = list(m.load_combos.keys())
+    pm = list(m.members.values())[0]
+    pm.plot_moment('Mz', names[0], n_points=7)
+    line = [c for c in calls if c[0] == 'plot'][0]
+    assert np.array_equal(line[1][1], pm.moment_array('Mz', 7, names[0])[1])
+    assert ('set_ylabel', ('Moment',), {}) in calls and calls[-1][0] == 'show'
+    del calls[:]
+    for name in names[:2]:
+        m.load_combos[name].combo_tags = ['env']
+    pm.plot_shear('Fy', ['env'], n_points=5)
+    high, low = [c for c in calls if c[0] == 'plot']
+    both = np.array([pm.shear_array('Fy', 5, n)[1] for n in names[:2]])
+    assert np.array_equal(high[1][1], both.max(axis=0)) and np.array_equal(low[1][1], both.min(axis=0))
+    for method, args in (('plot_torque', ()), ('plot_axial', ()), ('plot_deflection', ('dy',)), ('plot_rel_deflection', ('dy',))):
+        getattr(list(pm.sub_members.values())[0], method)(*args, names[0], 4)
+    assert [c[1][0] for c in calls if c[0] == 'set_ylabel'][-4:] == ['Torsional Moment (Warping Torsion Not Included)',
+                                                                    'Axial Force', 'Deflection', 'Relative Deflection']
