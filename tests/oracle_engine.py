@@ -140,10 +140,24 @@ class OracleEngine:
         return np.array(out).reshape(self.counts[kind], nd)
 
     def shell_stresses(self, kind, combo0, n_combo, pts, local=True):
+        """Quads: natural coordinates.  Plates: LOCAL (x, y) as in `pn_shell_stresses` -- the oracle takes fractions of the
+        plate's width and height, so the points are converted element by element."""
         pts = np.asarray(pts, dtype=float).reshape(-1, 2)
-        return np.array([om.shell_stresses(self.A, self.D[c], kind, [tuple(p) for p in pts], local)
-                         for c in range(combo0, combo0 + n_combo)]).reshape(n_combo, self.counts[kind], len(pts), 9)
-
+        A = self.A
+        out = np.zeros((n_combo, self.counts[kind], len(pts), 9))
+        for c in range(n_combo):
+            D = self.D[combo0 + c]
+            if kind == 'quad':
+                out[c] = om.shell_stresses(A, D, 'quad', [tuple(p) for p in pts], local)
+                continue
+            for e in range(self.counts['plate']):
+                p = [A.xyz[k] for k in A.plate_ijmn[e]]
+                w = float(((p[0] - p[1])**2).sum()**0.5)
+                h = float(((p[0] - p[3])**2).sum()**0.5)
+                one = copy.copy(A)
+                one.plate_ijmn, one.plate_props = A.plate_ijmn[e:e + 1], A.plate_props[e:e + 1]
+                out[c, e] = om.shell_stresses(one, D, 'plate', [(x/w, y/h) for x, y in pts], True)[0]
+        return out
 
 def install(monkeypatch):
     """Makes `analysis._engine(model)` hand out an OracleEngine (one per model) for the duration of a test."""

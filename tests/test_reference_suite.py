@@ -10,7 +10,7 @@ Not run (each needs something the stand-in does not emulate, not something the p
       compression-only iteration lives on the device (`pn_tc_update`; GPU tests `braced_tc`, `mat_tc`, `mat_mesh_tc`);
   test_instability, test_unstable_structure -- nodal-stability and singularity detection are device checks
       (`pn_check_nodal_stability`, the residual test; GPU tests `test_unstable_*`, `test_singular_*`);
-  test_pushover, test_Visualization, test_vtkwriter, test_reporting, test_meshes (imports IPython) -- out of scope."""
+  test_pushover, test_Visualization, test_vtkwriter, test_reporting -- out of scope."""
 import os
 import subprocess
 import sys
@@ -24,8 +24,9 @@ FILES = ['test_2D_frames', 'test_AISC_PDelta_benchmarks', 'test_continuous_beam'
          'test_sloped_beam', 'test_support_settlement', 'test_torsion', 'test_loads', 'test_delete_mesh', 'test_node_merge',
          'test_needs_update_flag', 'test_mesh_regen_simple', 'test_mesh_regeneration', 'test_reanalysis',
          'test_material_section_coverage', 'test_node_spring_coverage', 'test_member_internal_results', 'test_modal_analysis',
-         'test_shear_wall', 'test_springs', 'test_plates&quads', 'test_analysis_regeneration']
-DESELECT = ['test_analysis_regenerates_mat_foundation_needing_update']       # (compression-only soil springs: see above)
+         'test_shear_wall', 'test_springs', 'test_plates&quads', 'test_analysis_regeneration', 'test_meshes']
+DESELECT = ['test_analysis_regenerates_mat_foundation_needing_update',      # (compression-only soil springs: see above)
+            'test_PCA_7_rect']       # passes too, but the oracle's plate stress loop makes it a two-minute test
 
 
 @pytest.mark.skipif(not os.path.isdir(TESTING), reason='the reference is not present (GPU box)')
@@ -39,7 +40,7 @@ def test_reference_test_files_pass_against_this_package():
     assert run.returncode == 0, tail
     assert ' passed' in tail and 'failed' not in tail, tail
     passed = int(tail.split(' passed')[0].split()[-1])
-    assert passed >= 110, tail
+    assert passed >= 119, tail
 
 
 EXAMPLES = ['Circular Bin with Conical Hopper', 'Modal Analysis', 'P-Delta Analysis', 'Rectangular Plate Bending - Qauds',
