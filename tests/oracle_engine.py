@@ -27,6 +27,7 @@ class OracleEngine:
         self.A = None
         self.D = None
         self.pdelta = False
+        self._check = True
 
     # ---- upload ----------------------------------------------------------------------------------------------
     def set_model(self, A):
@@ -70,7 +71,13 @@ class OracleEngine:
         pass
 
     def check_nodal_stability(self, cap=4096):
-        pass
+        """`Analysis._check_stability` (`Analysis.py:111-168`): a free DOF with a zero diagonal stiffness."""
+        from math import isclose
+        d1, _, _ = om.partition_D(self.A)
+        diag = om.ke_csr(self.A).diagonal()
+        bad = [int(i) for i in d1 if isclose(diag[i], 0.0)]
+        if bad:
+            raise real.UnstableNodes('unstable nodes', bad)
 
     def partition(self):
         return om.partition_D(self.A)
@@ -81,15 +88,29 @@ class OracleEngine:
         except Exception as err:                              # noqa: BLE001
             raise real.SingularMatrix(str(err))
         self.D = np.array([np.asarray(d).reshape(-1) for d in D]).reshape(len(D), self.n_dof)
+        if self._check and len(D):
+            # the reference's solution check (`Analysis.py:228-239`): finite, and the residual on the free DOFs small
+            d1, _, _ = om.partition_D(self.A)
+            K = om.ke_csr(self.A)
+            for c in range(len(D)):
+                P, FER = om.load_vectors(self.A, c)
+                rhs = (P - FER)[d1, 0]
+                res = (K @ self.D[c])[d1] - rhs
+                scale = np.linalg.norm(rhs)
+                if not np.isfinite(self.D[c]).all() or (fn is om.solve_linear and np.linalg.norm(res) > 1e-6*max(scale, 1e-300)
+                                                        and scale > 0):
+                    raise real.SingularMatrix('singular stiffness matrix')
         Rm = np.array([np.asarray(r).reshape(-1) for r in R]).reshape(len(R), self.n_dof) if reactions else None
         return self.D.copy(), Rm, _Stats()
 
     def solve_linear(self, opts=None, reactions=True, D_out=None, R_out=None, download=True):
         self.pdelta = False
+        self._check = bool(opts is None or opts.check_stability)
         return self._solve(om.solve_linear, reactions)
 
     def solve_pdelta(self, opts=None, reactions=True, D_out=None, R_out=None, download=True):
         self.pdelta = True
+        self._check = bool(opts is None or opts.check_stability)
         return self._solve(om.solve_pdelta, reactions)
 
     def set_displacements(self, combo, D):
@@ -101,6 +122,86 @@ class OracleEngine:
 
     def reactions(self, combo, pdelta=False, out=None):
         return om.reactions(self.A, combo, self.D[combo].reshape(-1, 1), pdelta=pdelta)
+
+    # ---- tension / compression-only iteration (`pn_tc.cu`, `Analysis._check_TC_convergence` `Analysis.py:917-1056`) -------
+    def set_tc_modes(self, spring_mode, member_mode, group_start):
+        self.smode, self.mmode, self.starts = np.asarray(spring_mode), np.asarray(member_mode), np.asarray(group_start)
+
+    def tc_reset(self):
+        self.A.spring_active = np.ones_like(self.A.spring_active)
+        self.A.mem_active = np.ones_like(self.A.mem_active)
+
+    def activity(self, n_nodes):
+        return self.A.nspring_flag.copy(), self.A.spring_active.copy(), self.A.mem_active.copy()
+
+    def set_activity(self, nspring_flag=None, spring_active=None, member_active=None):
+        for name, value in (('nspring_flag', nspring_flag), ('spring_active', spring_active), ('mem_active', member_active)):
+            if value is not None:
+                setattr(self.A, name, np.array(value, copy=True))
+
+    def _member_axial_extremes(self, m, f, D):
+        """(max, min) of the axial force diagram of sub-member m, through the package's own segment table."""
+        from pynite_b200.diagrams import SegmentTable
+        A = self.A
+        L, R, _ = om.member_geometry(A, m)
+        factors = om.combo_factors(A, 0)
+        pts, dists, stations = [], [], []
+        raw_pts, raw_dists = om._member_loads(A, m)
+        for direction, P, x, case in raw_pts:
+            stations.append(x)
+            if case in factors:
+                v = np.zeros(6)
+                k = 'xyz'.find(direction[1].lower())
+                if direction[1].isupper():
+                    v[3*(direction[0] == 'M'):3*(direction[0] == 'M') + 3] = R[:, k]*P*factors[case]
+                else:
+                    v[3*(direction[0] == 'M') + k] = P*factors[case]
+                pts.append((x, v))
+        for direction, w1, w2, x1, x2, case in raw_dists:
+            stations += [x1, x2]
+            if case in factors:
+                k = 'xyz'.find(direction[1].lower())
+                if direction[1].isupper():
+                    a, b = R[:, k]*w1*factors[case], R[:, k]*w2*factors[case]
+                else:
+                    a, b = np.zeros(3), np.zeros(3)
+                    a[k], b[k] = w1*factors[case], w2*factors[case]
+                dists.append((x1, x2, a, b))
+        E, G, Ar, Iy, Iz, J = A.mem_props[m]
+        dofs = [6*int(n) + j for n in A.mem_ij[m] for j in range(6)]
+        d = np.kron(np.eye(4), R) @ D[dofs]
+        table = SegmentTable(L, E, Ar, Iy, Iz, f, d, pts, dists, stations, False)
+        return table.extreme('axial', 'z', True), table.extreme('axial', 'z', False)
+
+    def tc_update(self, combo, pdelta, spring_tol, member_tol):
+        A, D = self.A, self.D[combo]
+        changes = 0
+        flags = A.nspring_flag.copy()
+        for n, k in zip(*np.nonzero(flags & 12)):
+            disp = D[6*n + k]
+            should = bool(((flags[n, k] & 8) and disp <= -spring_tol) or ((flags[n, k] & 4) and disp >= spring_tol))
+            if bool(flags[n, k] & 2) != should:
+                flags[n, k] = (flags[n, k] & ~np.uint8(2)) | (2 if should else 0)
+                changes += 1
+        sf = self.element_forces('spring', combo, local=True)
+        spring_active = A.spring_active.copy()
+        for s in range(self.counts['spring']):
+            if spring_active[s] and (((self.smode[s] & 1) and sf[s, 0] > spring_tol) or ((self.smode[s] & 2) and sf[s, 0] < -spring_tol)):
+                spring_active[s] = 0
+                changes += 1
+        mf = self.element_forces('member', combo, local=True, pdelta=pdelta)
+        mem_active = A.mem_active.copy()
+        for g in range(len(self.starts) - 1):
+            subs = range(int(self.starts[g]), int(self.starts[g + 1]))
+            if not len(subs) or not mem_active[subs[0]] or not self.mmode[subs[0]]:
+                continue
+            ext = [self._member_axial_extremes(m, mf[m], D) for m in subs]
+            if ((self.mmode[subs[0]] & 1) and max(e[0] for e in ext) > member_tol) or \
+                    ((self.mmode[subs[0]] & 2) and min(e[1] for e in ext) < -member_tol):
+                mem_active[list(subs)] = 0
+                changes += 1
+        A.nspring_flag, A.spring_active, A.mem_active = flags, spring_active, mem_active
+        return changes
 
     # ---- element level ---------------------------------------------------------------------------------------
     def element_ke(self, kind):
@@ -120,7 +221,9 @@ class OracleEngine:
             dofs = [6*int(n) + j for n in conn[k] for j in range(6)]
             if kind == 'spring':
                 _, T, ke = om.spring_Ke(A, k)
-                f = ke @ (T @ D[dofs, :])
+                f = ke @ (T @ D[dofs, :])*(1.0 if A.spring_active[k] else 0.0)
+            elif kind == 'member' and not A.mem_active[k]:
+                T, f = om.member_Ke(A, k)[1], np.zeros((12, 1))
             elif kind == 'member':
                 _, T, ke = om.member_Ke(A, k)
                 d = T @ D[dofs, :]
