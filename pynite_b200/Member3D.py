@@ -75,6 +75,26 @@ class Member3D(SubMemberDiagrams):
                              "`member.sub_members[...]` instead")
         return next(iter(self.sub_members.values())).ID
 
+    def _local_loads(self, combo_name):
+        from pynite_b200.diagrams import local_loads
+        return local_loads(self, self.model.load_combos[combo_name], np.asarray(self.model._member_dircos(self), dtype=float))
+
+    def _fer_unc(self, combo_name='Combo 1'):
+        """Local fixed-end reaction vector (12, 1) ignoring the end releases (`Member3D.py:774-850`)."""
+        from pynite_b200.fixed_end import member_fer_unc
+        return member_fer_unc(*self._local_loads(combo_name), self.L()).reshape(12, 1)
+
+    def fer(self, combo_name='Combo 1'):
+        """Condensed (and expanded) local fixed-end reaction vector (`Member3D.py:742-772`)."""
+        from pynite_b200.fixed_end import condense_vector, member_ke_unc
+        k = member_ke_unc(self.material.E, self.material.G, self.section.A, self.section.Iy, self.section.Iz, self.section.J,
+                          self.L())
+        return condense_vector(k, self._fer_unc(combo_name).reshape(12), self.Releases).reshape(12, 1)
+
+    def FER(self, combo_name='Combo 1'):
+        """Global fixed-end reaction vector `T^T fer` (`Member3D.py:1080-1091`)."""
+        return self.T().T @ self.fer(combo_name)
+
     def Ke(self):
         """Global stiffness matrix (12, 12), computed by the member kernel (`Member3D.py:1038-1046`)."""
         from pynite_b200.analysis import element_matrix

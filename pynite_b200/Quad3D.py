@@ -56,6 +56,16 @@ class _Shell4:
         T = self.T()
         return T @ self.Ke() @ T.T
 
+    def fer(self, combo_name='Combo 1'):
+        """Local fixed-end reaction vector (24, 1) of the element's pressures (`Quad3D.fer` :721-788, `Plate3D.fer` :324-393)."""
+        from pynite_b200 import fixed_end
+        fn = fixed_end.quad_fer if self._kind == 'quad' else fixed_end.plate_fer
+        return fn(self, self.model.load_combos[combo_name])
+
+    def FER(self, combo_name='Combo 1'):
+        """Global fixed-end reaction vector `T^T fer` (`Quad3D.FER` :870-882, `Plate3D.FER` :510-522)."""
+        return self.T().T @ self.fer(combo_name)
+
     def D(self, combo_name='Combo 1'):
         """Global nodal displacements (24, 1) (`Quad3D.D` :790-829)."""
         from pynite_b200.analysis import element_D

@@ -26,8 +26,6 @@ from math import isclose
 import numpy as np
 
 _SIGMA = {'z': 1.0, 'y': -1.0}
-_G3_X = np.array([-(3/5)**0.5, 0.0, (3/5)**0.5])
-_G3_W = np.array([5/9, 8/9, 5/9])
 _LOCAL = {'Fx': 0, 'Fy': 1, 'Fz': 2, 'Mx': 3, 'My': 4, 'Mz': 5}
 _GLOBAL_F = {'FX': 0, 'FY': 1, 'FZ': 2}
 _GLOBAL_M = {'MX': 0, 'MY': 1, 'MZ': 2}
@@ -72,29 +70,10 @@ def local_loads(sub, combo, R):
 
 
 def fixed_end_moments(pts, dists, L):
-    """Entries (4, 5, 10, 11) of the uncondensed local fixed-end reaction vector (`Member3D._fer_unc`, `:774-850`): the
-    end moments of the clamped member.  A transverse unit load at station s clamps to `-s b^2/L^2` and `s^2 b/L^2`
-    (b = L - s); a distributed load is that influence integrated with three Gauss points, exact for a linearly varying
-    intensity (the integrand has degree four)."""
-    m = np.zeros(4)                                        # [My_i, Mz_i, My_j, Mz_j]
-
-    def transverse(py, pz, s):
-        b = L - s
-        gi, gj = s*b*b/L**2, s*s*b/L**2
-        return np.array([pz*gi, -py*gi, -pz*gj, py*gj])
-
-    for x, v in pts:
-        b = L - x
-        m += transverse(v[1], v[2], x)
-        ci, cj = b*(2*x - b)/L**2, x*(2*b - x)/L**2
-        m += np.array([v[4]*ci, v[5]*ci, v[4]*cj, v[5]*cj])
-    for x1, x2, a, b in dists:
-        half, mid = (x2 - x1)/2, (x2 + x1)/2
-        for gx, gw in zip(_G3_X, _G3_W):
-            s = mid + half*gx
-            w = a + (b - a)*((s - x1)/(x2 - x1)) if x2 != x1 else a
-            m += gw*half*transverse(w[1], w[2], s)
-    return m
+    """Entries (4, 5, 10, 11) of the uncondensed local fixed-end reaction vector (`Member3D._fer_unc`, `:774-850`): the end
+    moments [My_i, Mz_i, My_j, Mz_j] of the clamped member (`fixed_end.member_fer_unc`)."""
+    from pynite_b200.fixed_end import member_fer_unc
+    return member_fer_unc(pts, dists, L)[[4, 5, 10, 11]]
 
 
 class SegmentTable:

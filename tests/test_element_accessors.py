@@ -78,3 +78,20 @@ def test_element_matrices_through_the_objects(name):
             assert rel_err(subs[k].Kg(-37.5), om.member_Kg(A, k, -37.5)[0]) < 1e-12
             assert rel_err(subs[k].kg(12.0), om.member_Kg(A, k, 12.0)[2]) < 1e-11
     assert m.solution == 'Linear' and next(iter(m.load_combos)) in m._D        # inspection leaves the results alone
+
+
+@pytest.mark.parametrize('name', __import__('tests.util', fromlist=['FER_FIXTURES']).FER_FIXTURES)
+def test_fixed_end_reactions_of_single_elements(name):
+    """`Member3D._fer_unc / fer / FER`, `Quad3D.fer / FER`, `Plate3D.fer / FER` (`pynite_b200/fixed_end.py`) against the
+    reference's (tests/golden/element_fer.npz, written by tests/golden/make_fer_golden.py running the reference)."""
+    import os
+    from tests.util import fer_record
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'element_fer.npz'))
+    build, _ = models.SMALL_MODELS[name]
+    m = build(FEModel3D)
+    analysis.prepare_model(m)
+    for key, ours in fer_record(m).items():
+        ref = gold[name + '/' + key]
+        assert ours.shape == ref.shape, key
+        if ref.size:
+            assert np.abs(ours - ref).max() <= 1e-12*max(np.abs(ref).max(), 1e-300), (key, float(np.abs(ours - ref).max()))

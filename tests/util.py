@@ -179,3 +179,23 @@ def shear_wall_record(model):
             rec[f'{wname}_{label}'] = np.array([[r.sum_forces(c) for r in table.values()] for c in SHEAR_WALL_COMBOS], dtype=float)
         rec[f'{wname}_stiffness'] = np.array(wall.stiffness('Roof'))
     return rec
+
+
+# ---------------------------------------------------------------------------------------------
+# per-element fixed-end reactions (tests/golden/element_fer.npz)
+# ---------------------------------------------------------------------------------------------
+FER_FIXTURES = ['portal_frame', 'continuous_beam', 'moment_frame', 'quad_mesh_xy', 'skew_shell', 'plate_mesh_xz', 'mixed_building']
+
+
+def fer_record(model):
+    """[combo][element][...] fixed-end reaction vectors of every sub-member, quad and plate (reference objects or ours)."""
+    combos = list(model.load_combos.keys())
+    subs = [s for pm in model.members.values() for s in pm.sub_members.values()]
+    rec = {}
+    for label, elems, methods in (('member', subs, ('_fer_unc', 'fer', 'FER')), ('quad', list(model.quads.values()), ('fer', 'FER')),
+                                  ('plate', list(model.plates.values()), ('fer', 'FER'))):
+        for method in methods:
+            width = 12 if label == 'member' else 24
+            rec[f'{label}_{method}'] = np.array([[np.asarray(getattr(e, method)(c), dtype=float).reshape(-1) for e in elems]
+                                                 for c in combos], dtype=float).reshape(len(combos), len(elems), width)
+    return rec
