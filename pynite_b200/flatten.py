@@ -10,6 +10,7 @@ then 'a', 'b', ...), quads, plates (`FEModel3D.py:1587-1771`).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
+from operator import attrgetter
 
 import numpy as np
 
@@ -18,6 +19,15 @@ PT_KINDS = {'Fx': 0, 'Fy': 1, 'Fz': 2, 'Mx': 3, 'My': 4, 'Mz': 5,
 DIST_KINDS = {'Fx': 12, 'Fy': 13, 'Fz': 14, 'FX': 15, 'FY': 16, 'FZ': 17}
 _NODE_LOAD_DOF = {'FX': 0, 'FY': 1, 'FZ': 2, 'MX': 3, 'MY': 4, 'MZ': 5}
 _DOFS = ('DX', 'DY', 'DZ', 'RX', 'RY', 'RZ')
+# one C-level attribute sweep per node / shell instead of one `getattr` per field (2.5e5 nodes x 21 fields otherwise)
+_NODE_XYZ = attrgetter('X', 'Y', 'Z')
+_NODE_SUPPORTS = attrgetter(*('support_' + d for d in _DOFS))
+_NODE_ENFORCED = attrgetter(*('Enforced' + d for d in _DOFS))
+_NODE_SPRINGS = attrgetter(*('spring_' + d for d in _DOFS))
+_NOTHING_ENFORCED = (None,)*6
+_NO_SPRINGS = tuple([None, None, None] for _ in range(6))
+_SHELL_NODES = attrgetter('i_node.ID', 'j_node.ID', 'm_node.ID', 'n_node.ID')
+_SHELL_PROPS = attrgetter('t', 'E', 'nu', 'kx_mod', 'ky_mod')
 
 
 class NodeIndex:
@@ -119,31 +129,33 @@ def flatten_model(model, combo_list, active_combo=None):
     if active_combo is None:
         active_combo = combo_list[0].name if combo_list else None
 
-    A.xyz = _f64([(nd.X, nd.Y, nd.Z) for nd in nodes], (N, 3))
-    support = np.zeros(N, dtype=np.uint8)
+    A.xyz = _f64(list(map(_NODE_XYZ, nodes)), (N, 3))
     enf_mask = np.zeros(N, dtype=np.uint8)
     enf_val = np.zeros((N, 6))
     nsk = np.zeros((N, 6))
     nsf = np.zeros((N, 6), dtype=np.uint8)
-    for k, dof in enumerate(_DOFS):
-        sup = np.fromiter((bool(getattr(nd, 'support_' + dof)) for nd in nodes), dtype=bool, count=N)
-        support |= (sup.astype(np.uint8) << k)
-        for i, nd in enumerate(nodes):
-            e = getattr(nd, 'Enforced' + dof)
-            if e is not None:
-                enf_mask[i] |= (1 << k)
-                enf_val[i, k] = e
-            sp = getattr(nd, 'spring_' + dof)
-            if sp[0] is not None:
-                nsk[i, k] = float(sp[0])
-                flag = 1
-                if sp[2] == True:   # noqa: E712  (the reference tests `== True`)
-                    flag |= 2
-                if sp[1] == '+':
-                    flag |= 4
-                elif sp[1] == '-':
-                    flag |= 8
-                nsf[i, k] = flag
+    sup = np.array(list(map(_NODE_SUPPORTS, nodes)), dtype=bool).reshape(N, 6)         # (None counts as unsupported)
+    support = (sup.astype(np.uint8) << np.arange(6, dtype=np.uint8)).sum(axis=1).astype(np.uint8)
+    # enforced displacements and support springs are rare: only the nodes that differ from a fresh node are walked
+    for i, enforced in enumerate(map(_NODE_ENFORCED, nodes)):
+        if enforced != _NOTHING_ENFORCED:
+            for k, e in enumerate(enforced):
+                if e is not None:
+                    enf_mask[i] |= (1 << k)
+                    enf_val[i, k] = e
+    for i, node_springs in enumerate(map(_NODE_SPRINGS, nodes)):
+        if node_springs != _NO_SPRINGS:
+            for k, sp in enumerate(node_springs):
+                if sp[0] is not None:
+                    nsk[i, k] = float(sp[0])
+                    flag = 1
+                    if sp[2] == True:   # noqa: E712  (the reference tests `== True`)
+                        flag |= 2
+                    if sp[1] == '+':
+                        flag |= 4
+                    elif sp[1] == '-':
+                        flag |= 8
+                    nsf[i, k] = flag
     A.support, A.enf_mask, A.enf_val = support, enf_mask, np.ascontiguousarray(enf_val)
     A.nspring_k, A.nspring_flag = np.ascontiguousarray(nsk), np.ascontiguousarray(nsf)
 
@@ -179,10 +191,10 @@ def flatten_model(model, combo_list, active_combo=None):
 
     quads = list(model.quads.values())
     plates = list(model.plates.values())
-    A.quad_ijmn = _i32([(q.i_node.ID, q.j_node.ID, q.m_node.ID, q.n_node.ID) for q in quads], (len(quads), 4))
-    A.quad_props = _f64([(q.t, q.E, q.nu, q.kx_mod, q.ky_mod) for q in quads], (len(quads), 5))
-    A.plate_ijmn = _i32([(p.i_node.ID, p.j_node.ID, p.m_node.ID, p.n_node.ID) for p in plates], (len(plates), 4))
-    A.plate_props = _f64([(p.t, p.E, p.nu, p.kx_mod, p.ky_mod) for p in plates], (len(plates), 5))
+    A.quad_ijmn = _i32(list(map(_SHELL_NODES, quads)), (len(quads), 4))
+    A.quad_props = _f64(list(map(_SHELL_PROPS, quads)), (len(quads), 5))
+    A.plate_ijmn = _i32(list(map(_SHELL_NODES, plates)), (len(plates), 4))
+    A.plate_props = _f64(list(map(_SHELL_PROPS, plates)), (len(plates), 5))
 
     # ---- load cases, combos ------------------------------------------------------------------
     case_set = {}
