@@ -317,4 +317,7 @@ KNOWN_ANSWERS = {
 
 # models without a member / shell, or without a free degree of freedom: oracle only (the GPU path's handling of these
 # degenerate sizes has not been exercised on hardware)
-CPU_ONLY = ('nodal_springs', 'spring_reaction', 'sloped_beam', 'end_release_beam')
+CPU_ONLY = ('nodal_springs', 'spring_reaction', 'sloped_beam', 'end_release_beam',
+            # one to three free DOFs: smaller than anything the CUDA path has been run on (the smallest verified fixture has
+            # six); kept off the hardware run until someone can watch it -- the oracle and the drivers cover them on the CPU
+            'torque_beam', 'spring_elements', 'logan_12_1_plate')
